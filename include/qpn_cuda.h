@@ -1,0 +1,205 @@
+/*
+ * libqpn_cuda -- C ABI of the B200 (sm_100a) equilibrium engine for Quadratic
+ * Program Networks.  This is the drop-in boundary for the numeric hot path of
+ * forrestlaine/QuadraticProgramNetworks.jl v0.4.0: each entry point replaces one
+ * reference call site (cited per function).  The Julia side reaches these with
+ * `ccall`; nothing here depends on torch or on C++ types.
+ *
+ * Conventions
+ *  - fp64 everywhere; matrices are column-major (Julia native); batched vectors
+ *    are  n x batch  column-major, i.e. instance b starts at  ptr + b*n.
+ *  - +-Inf are passed as IEEE infinities.
+ *  - Return value: 0 ok, <0 error (message via qpn_last_error).  Per-instance
+ *    outcomes are only reported in status arrays (StatusCode of avi.jl:1-6):
+ *    1 SUCCESS, 2 RAY_TERM, 3 MAX_ITERS, 4 FAILURE.  No exceptions, no callbacks.
+ *  - Host entry points copy in/out on the handle's stream and do not retain host
+ *    pointers past return.  `_dev` entry points take device pointers of the
+ *    handle's device and run asynchronously on the stream given (0 = handle's).
+ *  - One handle per GPU; calls on one handle must be serialised by the caller.
+ *  - There is no CPU fallback: without a usable CUDA device qpn_create fails.
+ */
+#ifndef QPN_CUDA_H
+#define QPN_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct qpn_handle qpn_handle;
+
+#define QPN_SUCCESS 1
+#define QPN_RAY_TERM 2
+#define QPN_MAX_ITERS 3
+#define QPN_FAILURE 4
+
+/* basis / active-set codes written to basis_out (same coding as
+ * comp_indices' primary sets, avi_solutions.jl:568-585) */
+#define QPN_AT_LOWER 1
+#define QPN_BASIC 2
+#define QPN_AT_UPPER 3
+#define QPN_FIXED 4
+
+/* Matrix operand of an AVI: either dense column-major (dense != NULL) or CSC
+ * (colptr/rowval/nzval, PATH's Cint indices as in avi.jl:11-12).  index_base is 1
+ * for Julia's SparseMatrixCSC, 0 for C.  When is_shared == 0 the dense array is
+ * n x n x batch and nzval is nnz x batch (the pattern is always shared). */
+typedef struct {
+    const double *dense;
+    const int32_t *colptr;
+    const int32_t *rowval;
+    const double *nzval;
+    int32_t nnz;
+    int32_t index_base;
+    int32_t is_shared;
+} qpn_matrix;
+
+int qpn_create(int device, qpn_handle **out);
+int qpn_destroy(qpn_handle *h);
+const char *qpn_last_error(qpn_handle *h);       /* h may be NULL: last create error */
+int qpn_device(qpn_handle *h);
+/* Number of kernel launches this handle has issued (bench.py's gpu_launches). */
+int64_t qpn_launch_count(qpn_handle *h);
+int qpn_synchronize(qpn_handle *h);
+
+/*
+ * Replaces PATHSolver.solve_mcp at /root/reference/src/avi.jl:64-70 plus the check at
+ * avi.jl:71-75 (`solve_avi`).  Finds z with (M z + q) complementary to l <= z <= u,
+ * started from z0, by bounded-variable complementary pivoting (one CTA per instance).
+ *   q, z0, z_out:  n x batch.   l, u:  n (lu_is_shared) or n x batch.
+ *   status_out, pivots_out: batch.   basis_out: n x batch int8 (may be NULL).
+ *   max_pivots <= 0 selects 50 n + 100.
+ */
+int qpn_avi_solve_batched(qpn_handle *h, int n, int batch, const qpn_matrix *M, const double *q,
+                          const double *l, const double *u, int lu_is_shared, const double *z0,
+                          int max_pivots, double *z_out, int32_t *status_out, int32_t *pivots_out,
+                          int8_t *basis_out);
+int qpn_avi_solve_batched_dev(qpn_handle *h, int n, int batch, const qpn_matrix *M, const double *q,
+                              const double *l, const double *u, int lu_is_shared, const double *z0,
+                              int max_pivots, double *z_out, int32_t *status_out,
+                              int32_t *pivots_out, int8_t *basis_out, void *stream);
+
+/*
+ * Replaces check_avi_solution, /root/reference/src/avi.jl:148-156.
+ *   bad_out[b] = number of violated conditions (0 = solution ok); r_out (n x batch, may be
+ *   NULL) = M z + q.
+ */
+int qpn_check_avi_batched(qpn_handle *h, int n, int batch, const qpn_matrix *M, const double *q,
+                          const double *l, const double *u, int lu_is_shared, const double *z,
+                          double tol, int32_t *bad_out, double *r_out);
+
+/* A generalized AVI (struct GAVI, avi.jl:29-39), dense blocks shared by the batch:
+ *   (M z + N w + o) comp. l1 <= z1 <= u1 ;  z2 comp. l2 <= A z + B w <= u2,  z = [z1; z2]. */
+typedef struct {
+    int32_t d1, d2, np;
+    const double *M;   /* d1 x (d1+d2) */
+    const double *N;   /* d1 x np      */
+    const double *o;   /* d1           */
+    const double *l1, *u1;
+    const double *A;   /* d2 x (d1+d2) */
+    const double *B;   /* d2 x np      */
+    const double *l2, *u2;
+} qpn_gavi;
+
+/*
+ * Replaces solve_gavi, /root/reference/src/avi.jl:101-111: the presolve projection
+ * find_closest_feasible! (avi.jl:79-99, OSQP in the reference), the GAVI->AVI lift
+ * `convert` (avi.jl:113-128) and solve_avi, fused in one kernel.
+ *   w: np x batch, z0: (d1+d2) x batch, z_out: (d1+d2) x batch,
+ *   basis_out: (d1+2 d2) x batch (may be NULL), zfull_out: (d1+2 d2) x batch (may be NULL).
+ */
+int qpn_gavi_solve_batched(qpn_handle *h, const qpn_gavi *g, int batch, const double *w,
+                           const double *z0, int presolve, int max_pivots, double *z_out,
+                           double *zfull_out, int32_t *status_out, int32_t *pivots_out,
+                           int8_t *basis_out);
+int qpn_gavi_solve_batched_dev(qpn_handle *h, const qpn_gavi *g, int batch, const double *w,
+                               const double *z0, int presolve, int max_pivots, double *z_out,
+                               double *zfull_out, int32_t *status_out, int32_t *pivots_out,
+                               int8_t *basis_out, void *stream);
+
+/*
+ * Replaces comp_indices(gavi, z, w), /root/reference/src/avi_solutions.jl:511-612 (the
+ * request branch is inert).  mask_out: (d1+d2) x batch, one 4-bit mask per
+ * index: bit0 -> set 1, bit1 -> set 2, bit2 -> set 3, bit3 -> set 4 (block 2: 5..8).
+ * A mask of 0 marks an index for which the reference's @assert would fire.
+ */
+int qpn_comp_indices_batched(qpn_handle *h, const qpn_gavi *g, int batch, const double *z,
+                             const double *w, double tol, int8_t *mask_out);
+
+/*
+ * Replaces Base.in(x, ::Poly; tol), /root/reference/src/sets.jl:820-825,850-853, for
+ * npoly polyhedra over the same embedded dimension d, stacked row-wise:
+ *   A: mtot x d, l/u: mtot, rl/ru: mtot (1 = strict '<', 0 = '<='; NULL = all closed),
+ *   poly_ptr: npoly+1 row offsets.  x: d x npts.
+ *   in_out: npoly x npts (uint8), in_out[p + npoly*j] = (x_j in poly p).
+ */
+int qpn_halfspace_in_batched(qpn_handle *h, int npoly, int d, int mtot, const int32_t *poly_ptr,
+                             const double *A, const double *l, const double *u, const uint8_t *rl,
+                             const uint8_t *ru, int npts, const double *x, double tol,
+                             uint8_t *in_out);
+
+/* One node's view of verify_solution: Qd = Q[dec,:] (nd x nv), qd = q[dec], stacked
+ * constraint rows A (m x nv), l, u, dec (nd 0-based indices into x). */
+typedef struct {
+    int32_t nd, nv, m;
+    const double *Qd, *qd, *A, *l, *u;
+    const int32_t *dec;
+} qpn_node;
+
+/*
+ * Replaces verify_solution, /root/reference/src/qp_processing.jl:57-149 (without the
+ * check_convexity / debug branches): feasibility at 1e-3, active sets at 1e-2, dual
+ * recovery  lam = Abar \ qt  (Householder QR), acceptance at tol, and the
+ * sign-constrained least-squares fallback (PATH in the reference) through the same
+ * pivoting solve.  x: nv x batch.
+ *   solution_out: batch (1/0);  lam_out: m x batch;  how_out: batch (0 infeasible,
+ *   1 unconstrained, 2 least squares, 3 fallback accepted, 4 fallback rejected,
+ *   5 fallback failed);  active_out: m x batch (0 inactive, 1 lower, 2 upper, 3 both),
+ *   either may be NULL.
+ */
+int qpn_verify_solution_batched(qpn_handle *h, const qpn_node *node, int batch, const double *x,
+                                double tol, uint8_t *solution_out, double *lam_out,
+                                int32_t *how_out, int8_t *active_out);
+
+/* A level of a network with no child solution pieces (bottom level, or a flat Nash
+ * game): its players and the level GAVI assembled by solve_qep (avi.jl:382-404). */
+typedef struct {
+    int32_t nv, nplayers;
+    const qpn_node *players;
+    qpn_gavi gavi;
+    const int32_t *dec;     /* gavi decision indices into x (nd_level of them) */
+    int32_t nd_level;
+    const int32_t *par;     /* parameter indices into x (gavi.np of them) */
+    int32_t max_iters;      /* QPNetOptions.max_iters, programs.jl:63 */
+    int32_t num_projections;/* cycle check, algorithm.jl:14-30; 0 disables */
+    const double *proj;     /* nv x num_projections */
+} qpn_level;
+
+/*
+ * Replaces the iterate-until-equilibrium loop of solve_base! for one level without
+ * children (/root/reference/src/algorithm.jl:13-118: process_qp -> verify_solution per
+ * player, solve_qep when not an equilibrium, the 1e-4 disagreement test and the cycle
+ * check), fused in one kernel, one CTA per instance.
+ *   x_init, x_out: nv x batch.  solved_out: batch (1 solved, 0 not).
+ *   iters_out, pivots_out: batch.  lam_out (may be NULL): sum(m_p) x batch.
+ */
+int qpn_level_equilibrium_batched(qpn_handle *h, const qpn_level *lv, int batch,
+                                  const double *x_init, double *x_out, uint8_t *solved_out,
+                                  int32_t *iters_out, int32_t *pivots_out, double *lam_out);
+int qpn_level_equilibrium_batched_dev(qpn_handle *h, const qpn_level *lv, int batch,
+                                      const double *x_init, double *x_out, uint8_t *solved_out,
+                                      int32_t *iters_out, int32_t *pivots_out, double *lam_out,
+                                      void *stream);
+
+/* Device buffers owned by the handle (for callers without their own allocator). */
+int qpn_malloc(qpn_handle *h, size_t bytes, void **dptr);
+int qpn_free(qpn_handle *h, void *dptr);
+int qpn_memcpy_h2d(qpn_handle *h, void *dst, const void *src, size_t bytes);
+int qpn_memcpy_d2h(qpn_handle *h, void *dst, const void *src, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QPN_CUDA_H */

@@ -410,3 +410,77 @@ def verify_solution(Qd, qd, A, l, u, dec, x, polys=None, tol=1e-4, solver=avi_pi
     if nrm(res) <= 1e-4:
         return True, lam2, "nnls"
     return False, lam2, "suboptimal"
+
+
+# --------------------------------------------------------------------------
+# algorithm.jl: one level without children (bottom level / flat Nash game)
+# --------------------------------------------------------------------------
+def node_view(net, pid, S=None):
+    """What verify_solution reads for a node (qp_processing.jl:57-66): Q[dec,:], q[dec],
+    stacked rows of its constraint polys followed by the chosen child pieces."""
+    S = S or {}
+    dec = net.decision_inds(pid)
+    qp = net.qps[pid]
+    polys = [net_polys(net)[ci] for ci in qp["cons"]] + [S[j] for j in net.edges[pid]]
+    A = np.vstack([p.A for p in polys]) if polys else np.zeros((0, net.n_vars))
+    l = np.concatenate([p.l for p in polys]) if polys else np.zeros(0)
+    u = np.concatenate([p.u for p in polys]) if polys else np.zeros(0)
+    return qp["Q"][dec, :], qp["q"][dec], A, l, u, np.array(dec, dtype=np.int32)
+
+
+def projections_equal(a, b):
+    """`proj_vals ≈ prev` (algorithm.jl:24) = isapprox with rtol = sqrt(eps), atol = 0."""
+    nrm = lambda v: math.sqrt(sum(fma(t, t, 0.0) if False else t * t for t in v))
+    dd = na = nb = 0.0
+    for x, y in zip(a, b):
+        e = x - y
+        dd = fma(e, e, dd); na = fma(x, x, na); nb = fma(y, y, nb)
+    return math.sqrt(dd) <= 1.4901161193847656e-8 * max(math.sqrt(na), math.sqrt(nb))
+
+
+def solve_level_bottom(net, level, x_init, proj=None, max_iters=None):
+    """algorithm.jl:13-118 for a level whose players have no children, with the C oracle
+    doing the numerics.  proj: (nproj, nv) projection vectors or None."""
+    from . import cport
+    players = net.depth[level]
+    views = [node_view(net, p) for p in players]
+    g, dec, par = level_gavi(net, players, {})
+    max_iters = max_iters or net.options["max_iters"]
+    x = np.array(x_init, dtype=float)
+    hist, piv, it = [], 0, 0
+    for it in range(1, max_iters + 1):
+        if proj is not None and len(proj):
+            pv = [float(sum_fma(x, v)) for v in proj]
+            if any(projections_equal(pv, h) for h in hist):
+                return dict(solved=False, x=x, iters=it, pivots=piv, why="cycle")
+            hist.append(pv)
+        all_sol, lams = True, []
+        for (Qd, qd, A, l, u, d) in views:
+            sol, lam, how, act = cport.verify_solution(Qd, qd, A, l, u, d, x)
+            lams.append(lam if sol else np.zeros(len(l)))
+            all_sol &= sol
+        if all_sol:
+            return dict(solved=True, x=x, iters=it, pivots=piv, lam=np.concatenate(lams) if lams else np.zeros(0))
+        w = x[par]
+        z0 = np.concatenate([x[dec], np.zeros(g["M"].shape[1] - len(dec))])
+        ret = cport.gavi_solve(g, z0, w)
+        piv += ret["pivots"]
+        if ret["status"] != SUCCESS:
+            return dict(solved=False, x=x, iters=it, pivots=piv, why="avi")
+        xn = x.copy()
+        xn[dec] = ret["z"][:len(dec)]
+        dn = 0.0
+        for a, b in zip(xn, x):
+            e = a - b
+            dn = fma(e, e, dn)
+        if math.sqrt(dn) < 1e-4:
+            return dict(solved=False, x=x, iters=it, pivots=piv, why="disagreement")
+        x = xn
+    return dict(solved=False, x=x, iters=it, pivots=piv, why="max_iters")
+
+
+def sum_fma(x, v):
+    acc = 0.0
+    for a, b in zip(x, v):
+        acc = fma(a, b, acc)
+    return acc

@@ -1,0 +1,8 @@
+"""qpn_b200: B200-native equilibrium engine for Quadratic Program Networks.
+
+Host-side mirror of the reference's API for the numeric hot path
+(`setup(:name)` -> `solve(qpn, init)`, plus the batched `solve(qpn, inits)`), driving
+libqpn_cuda through its C ABI (include/qpn_cuda.h).  Import as `qpn_b200` (the shim
+at the repo root) -- the directory name carries a dot and is not importable directly.
+"""
+from .engine import Engine, EngineError, GaviArrays, NodeArrays, LevelArrays, load_library, LIB_PATH  # noqa: F401

@@ -1,0 +1,411 @@
+// libqpn_cuda: host side of the C ABI declared in include/qpn_cuda.h.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/qpn_cuda.h"
+#include "qpn_kernels.cuh"
+#include "qpn_level.cuh"
+
+using namespace qpn;
+
+struct qpn_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    int max_smem_optin = 0;
+    int sm_count = 0;
+    // grow-only device scratch arena for the host-pointer entry points
+    unsigned char* arena = nullptr;
+    size_t arena_bytes = 0;
+    size_t arena_used = 0;
+};
+
+static std::string g_create_error;
+
+static int fail(qpn_handle* h, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return -1;
+}
+
+#define CK(call)                                                                           \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess) return fail(h, "%s: %s", #call, cudaGetErrorString(e_));    \
+    } while (0)
+
+static inline int roundup32(int n) { return n < 32 ? 32 : ((n + 31) / 32) * 32; }
+static inline int odd_ld(int n) { return n | 1; }
+
+extern "C" int qpn_create(int device, qpn_handle** out) {
+    qpn_handle* h = nullptr;
+    if (!out) return fail(nullptr, "qpn_create: out is NULL");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, "qpn_create: no CUDA device (%s); libqpn_cuda has no CPU fallback",
+                    cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(nullptr, "qpn_create: device %d out of range (%d)", device, count);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+        return fail(nullptr, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, "qpn_create: device %d is sm_%d%d; this library is built for sm_100a only",
+                    device, prop.major, prop.minor);
+    h = new qpn_handle();
+    h->device = device;
+    h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    h->sm_count = prop.multiProcessorCount;
+    if ((e = cudaSetDevice(device)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete h;
+        return fail(nullptr, "qpn_create: %s", cudaGetErrorString(e));
+    }
+    *out = h;
+    return 0;
+}
+
+extern "C" int qpn_destroy(qpn_handle* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    if (h->arena) cudaFree(h->arena);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+extern "C" const char* qpn_last_error(qpn_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+extern "C" int qpn_device(qpn_handle* h) { return h ? h->device : -1; }
+extern "C" int64_t qpn_launch_count(qpn_handle* h) { return h ? h->launches : 0; }
+extern "C" int qpn_synchronize(qpn_handle* h) {
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int qpn_malloc(qpn_handle* h, size_t bytes, void** dptr) {
+    CK(cudaSetDevice(h->device));
+    CK(cudaMalloc(dptr, bytes ? bytes : 8));
+    return 0;
+}
+extern "C" int qpn_free(qpn_handle* h, void* dptr) {
+    CK(cudaSetDevice(h->device));
+    CK(cudaFree(dptr));
+    return 0;
+}
+extern "C" int qpn_memcpy_h2d(qpn_handle* h, void* dst, const void* src, size_t bytes) {
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+extern "C" int qpn_memcpy_d2h(qpn_handle* h, void* dst, const void* src, size_t bytes) {
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ---- scratch arena -------------------------------------------------------------------------
+// Host-pointer entry points stage their operands here.  reset -> reserve (grow once) -> take.
+struct Arena {
+    qpn_handle* h;
+    size_t need = 0;
+    std::vector<std::pair<size_t, size_t>> slots;   // (offset, bytes)
+    explicit Arena(qpn_handle* hh) : h(hh) {}
+    int add(size_t bytes) {
+        size_t off = (need + 255) & ~(size_t)255;
+        need = off + bytes;
+        slots.push_back({off, bytes});
+        return (int)slots.size() - 1;
+    }
+    int commit() {
+        if (need > h->arena_bytes) {
+            if (h->arena) cudaFree(h->arena);
+            h->arena = nullptr; h->arena_bytes = 0;
+            size_t cap = need + need / 4 + 4096;
+            cudaError_t e = cudaMalloc((void**)&h->arena, cap);
+            if (e != cudaSuccess) return fail(h, "cudaMalloc(%zu): %s", cap, cudaGetErrorString(e));
+            h->arena_bytes = cap;
+        }
+        return 0;
+    }
+    template <typename T> T* ptr(int slot) { return slot < 0 ? nullptr : reinterpret_cast<T*>(h->arena + slots[slot].first); }
+};
+
+static int up(qpn_handle* h, void* dst, const void* src, size_t bytes) {
+    if (!bytes || !src) return 0;
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+static int down(qpn_handle* h, void* dst, const void* src, size_t bytes) {
+    if (!bytes || !dst) return 0;
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+    return 0;
+}
+
+static int check_matrix(qpn_handle* h, const qpn_matrix* M, int n) {
+    if (!M) return fail(h, "matrix descriptor is NULL");
+    if (!M->dense && !(M->colptr && M->rowval && M->nzval)) return fail(h, "matrix: neither dense nor CSC given");
+    if (n <= 0) return fail(h, "n must be positive");
+    return 0;
+}
+
+static MatDesc to_desc(const qpn_matrix* M) {
+    MatDesc d;
+    d.dense = M->dense; d.colptr = M->colptr; d.rowval = M->rowval; d.nzval = M->nzval;
+    d.nnz = M->nnz; d.base = M->index_base; d.shared = M->is_shared;
+    return d;
+}
+
+// Stage a host qpn_matrix into the arena; returns the device descriptor.
+struct MatSlots { int dense = -1, colptr = -1, rowval = -1, nzval = -1; };
+static MatSlots plan_matrix(Arena& a, const qpn_matrix* M, int n, int batch) {
+    MatSlots s;
+    size_t reps = M->is_shared ? 1 : (size_t)batch;
+    if (M->dense) s.dense = a.add(sizeof(double) * (size_t)n * n * reps);
+    else {
+        s.colptr = a.add(sizeof(int32_t) * (size_t)(n + 1));
+        s.rowval = a.add(sizeof(int32_t) * (size_t)M->nnz);
+        s.nzval = a.add(sizeof(double) * (size_t)M->nnz * reps);
+    }
+    return s;
+}
+static int stage_matrix(qpn_handle* h, Arena& a, const MatSlots& s, const qpn_matrix* M, int n, int batch, MatDesc* out) {
+    size_t reps = M->is_shared ? 1 : (size_t)batch;
+    MatDesc d = to_desc(M);
+    if (M->dense) {
+        if (up(h, a.ptr<double>(s.dense), M->dense, sizeof(double) * (size_t)n * n * reps)) return -1;
+        d.dense = a.ptr<double>(s.dense);
+    } else {
+        if (up(h, a.ptr<int32_t>(s.colptr), M->colptr, sizeof(int32_t) * (size_t)(n + 1))) return -1;
+        if (up(h, a.ptr<int32_t>(s.rowval), M->rowval, sizeof(int32_t) * (size_t)M->nnz)) return -1;
+        if (up(h, a.ptr<double>(s.nzval), M->nzval, sizeof(double) * (size_t)M->nnz * reps)) return -1;
+        d.colptr = a.ptr<int32_t>(s.colptr); d.rowval = a.ptr<int32_t>(s.rowval); d.nzval = a.ptr<double>(s.nzval);
+    }
+    *out = d;
+    return 0;
+}
+
+// ---- solve_avi -----------------------------------------------------------------------------
+static int launch_avi(qpn_handle* h, int n, int batch, const MatDesc& M, const double* q, const double* l,
+                      const double* u, int lu_shared, const double* z0, int max_pivots, double* z,
+                      int32_t* st, int32_t* pv, int8_t* basis, cudaStream_t s) {
+    if (batch <= 0) return 0;
+    const int ld = odd_ld(n);
+    const size_t smem = tab_smem_bytes(n, ld) + 2 * sizeof(double) * (size_t)n;
+    if (smem > (size_t)h->max_smem_optin)
+        return fail(h, "AVI of size n=%d needs %zu B of shared memory per CTA (limit %d): the shared-memory "
+                       "tableau path does not cover this size", n, smem, h->max_smem_optin);
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(avi_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (max_pivots <= 0) max_pivots = 50 * n + 100;
+    avi_solve_kernel<<<batch, roundup32(n), smem, s>>>(n, ld, batch, M, q, l, u, lu_shared, z0, max_pivots, z, st, pv, basis);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int qpn_avi_solve_batched_dev(qpn_handle* h, int n, int batch, const qpn_matrix* M, const double* q,
+                                         const double* l, const double* u, int lu_is_shared, const double* z0,
+                                         int max_pivots, double* z_out, int32_t* status_out, int32_t* pivots_out,
+                                         int8_t* basis_out, void* stream) {
+    if (!h) return -1;
+    if (check_matrix(h, M, n)) return -1;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+    return launch_avi(h, n, batch, to_desc(M), q, l, u, lu_is_shared, z0, max_pivots, z_out, status_out, pivots_out, basis_out, s);
+}
+
+extern "C" int qpn_avi_solve_batched(qpn_handle* h, int n, int batch, const qpn_matrix* M, const double* q,
+                                     const double* l, const double* u, int lu_is_shared, const double* z0,
+                                     int max_pivots, double* z_out, int32_t* status_out, int32_t* pivots_out,
+                                     int8_t* basis_out) {
+    if (!h) return -1;
+    if (check_matrix(h, M, n)) return -1;
+    CK(cudaSetDevice(h->device));
+    const size_t nb = (size_t)n * batch, lub = lu_is_shared ? (size_t)n : nb;
+    Arena a(h);
+    MatSlots ms = plan_matrix(a, M, n, batch);
+    int sq = a.add(8 * nb), sl = a.add(8 * lub), su = a.add(8 * lub), sz0 = a.add(8 * nb), sz = a.add(8 * nb);
+    int sst = a.add(4 * (size_t)batch), spv = a.add(4 * (size_t)batch), sb = basis_out ? a.add(nb) : -1;
+    if (a.commit()) return -1;
+    MatDesc d;
+    if (stage_matrix(h, a, ms, M, n, batch, &d)) return -1;
+    if (up(h, a.ptr<double>(sq), q, 8 * nb) || up(h, a.ptr<double>(sl), l, 8 * lub) || up(h, a.ptr<double>(su), u, 8 * lub) ||
+        up(h, a.ptr<double>(sz0), z0, 8 * nb)) return -1;
+    if (launch_avi(h, n, batch, d, a.ptr<double>(sq), a.ptr<double>(sl), a.ptr<double>(su), lu_is_shared, a.ptr<double>(sz0),
+                   max_pivots, a.ptr<double>(sz), a.ptr<int32_t>(sst), a.ptr<int32_t>(spv), a.ptr<int8_t>(sb), h->stream)) return -1;
+    if (down(h, z_out, a.ptr<double>(sz), 8 * nb) || down(h, status_out, a.ptr<int32_t>(sst), 4 * (size_t)batch) ||
+        down(h, pivots_out, a.ptr<int32_t>(spv), 4 * (size_t)batch) || down(h, basis_out, a.ptr<int8_t>(sb), nb)) return -1;
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ---- check_avi_solution ----------------------------------------------------------------------
+extern "C" int qpn_check_avi_batched(qpn_handle* h, int n, int batch, const qpn_matrix* M, const double* q,
+                                     const double* l, const double* u, int lu_is_shared, const double* z, double tol,
+                                     int32_t* bad_out, double* r_out) {
+    if (!h) return -1;
+    if (check_matrix(h, M, n)) return -1;
+    if (batch <= 0) return 0;
+    CK(cudaSetDevice(h->device));
+    const size_t nb = (size_t)n * batch, lub = lu_is_shared ? (size_t)n : nb;
+    Arena a(h);
+    MatSlots ms = plan_matrix(a, M, n, batch);
+    int sq = a.add(8 * nb), sl = a.add(8 * lub), su = a.add(8 * lub), sz = a.add(8 * nb);
+    int sbad = a.add(4 * (size_t)batch), sr = r_out ? a.add(8 * nb) : -1;
+    if (a.commit()) return -1;
+    MatDesc d;
+    if (stage_matrix(h, a, ms, M, n, batch, &d)) return -1;
+    if (up(h, a.ptr<double>(sq), q, 8 * nb) || up(h, a.ptr<double>(sl), l, 8 * lub) || up(h, a.ptr<double>(su), u, 8 * lub) ||
+        up(h, a.ptr<double>(sz), z, 8 * nb)) return -1;
+    const int threads = 128, warps_per_block = threads / 32;
+    check_avi_kernel<<<(batch + warps_per_block - 1) / warps_per_block, threads, 0, h->stream>>>(
+        n, batch, d, a.ptr<double>(sq), a.ptr<double>(sl), a.ptr<double>(su), lu_is_shared, a.ptr<double>(sz), tol,
+        a.ptr<int32_t>(sbad), a.ptr<double>(sr));
+    h->launches++;
+    CK(cudaGetLastError());
+    if (down(h, bad_out, a.ptr<int32_t>(sbad), 4 * (size_t)batch) || down(h, r_out, a.ptr<double>(sr), 8 * nb)) return -1;
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ---- GAVI staging ----------------------------------------------------------------------------
+struct GaviSlots { int M, N, o, l1, u1, A, B, l2, u2; };
+static GaviSlots plan_gavi(Arena& a, const qpn_gavi* g) {
+    const size_t d1 = g->d1, d2 = g->d2, np = g->np, dz = d1 + d2;
+    GaviSlots s;
+    s.M = a.add(8 * d1 * dz); s.N = a.add(8 * d1 * np); s.o = a.add(8 * d1); s.l1 = a.add(8 * d1); s.u1 = a.add(8 * d1);
+    s.A = a.add(8 * d2 * dz); s.B = a.add(8 * d2 * np); s.l2 = a.add(8 * d2); s.u2 = a.add(8 * d2);
+    return s;
+}
+static int stage_gavi(qpn_handle* h, Arena& a, const GaviSlots& s, const qpn_gavi* g, GaviDesc* out) {
+    const size_t d1 = g->d1, d2 = g->d2, np = g->np, dz = d1 + d2;
+    if (up(h, a.ptr<double>(s.M), g->M, 8 * d1 * dz) || up(h, a.ptr<double>(s.N), g->N, 8 * d1 * np) ||
+        up(h, a.ptr<double>(s.o), g->o, 8 * d1) || up(h, a.ptr<double>(s.l1), g->l1, 8 * d1) ||
+        up(h, a.ptr<double>(s.u1), g->u1, 8 * d1) || up(h, a.ptr<double>(s.A), g->A, 8 * d2 * dz) ||
+        up(h, a.ptr<double>(s.B), g->B, 8 * d2 * np) || up(h, a.ptr<double>(s.l2), g->l2, 8 * d2) ||
+        up(h, a.ptr<double>(s.u2), g->u2, 8 * d2)) return -1;
+    GaviDesc d;
+    d.d1 = g->d1; d.d2 = g->d2; d.np = g->np;
+    d.M = a.ptr<double>(s.M); d.N = a.ptr<double>(s.N); d.o = a.ptr<double>(s.o); d.l1 = a.ptr<double>(s.l1);
+    d.u1 = a.ptr<double>(s.u1); d.A = a.ptr<double>(s.A); d.B = a.ptr<double>(s.B); d.l2 = a.ptr<double>(s.l2);
+    d.u2 = a.ptr<double>(s.u2);
+    *out = d;
+    return 0;
+}
+static GaviDesc gavi_dev_desc(const qpn_gavi* g) {
+    GaviDesc d;
+    d.d1 = g->d1; d.d2 = g->d2; d.np = g->np;
+    d.M = g->M; d.N = g->N; d.o = g->o; d.l1 = g->l1; d.u1 = g->u1; d.A = g->A; d.B = g->B; d.l2 = g->l2; d.u2 = g->u2;
+    return d;
+}
+
+// ---- solve_gavi ------------------------------------------------------------------------------
+static int launch_gavi(qpn_handle* h, const GaviDesc& g, int batch, const double* w, const double* z0, int presolve,
+                       int max_pivots, double* z, double* zfull, int32_t* st, int32_t* pv, int8_t* basis, cudaStream_t s) {
+    if (batch <= 0) return 0;
+    const int n = g.d1 + 2 * g.d2, ld = odd_ld(n);
+    const size_t smem = gavi_smem_bytes(g.d1, g.d2, g.np);
+    if (smem > (size_t)h->max_smem_optin)
+        return fail(h, "GAVI with d1=%d d2=%d needs %zu B of shared memory per CTA (limit %d)", g.d1, g.d2, smem, h->max_smem_optin);
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(gavi_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (max_pivots <= 0) max_pivots = 50 * n + 100;
+    gavi_solve_kernel<<<batch, roundup32(n), smem, s>>>(g, ld, batch, w, z0, presolve, max_pivots, z, zfull, st, pv, basis);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int qpn_gavi_solve_batched_dev(qpn_handle* h, const qpn_gavi* g, int batch, const double* w, const double* z0,
+                                          int presolve, int max_pivots, double* z_out, double* zfull_out,
+                                          int32_t* status_out, int32_t* pivots_out, int8_t* basis_out, void* stream) {
+    if (!h || !g) return -1;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+    return launch_gavi(h, gavi_dev_desc(g), batch, w, z0, presolve, max_pivots, z_out, zfull_out, status_out, pivots_out, basis_out, s);
+}
+
+extern "C" int qpn_gavi_solve_batched(qpn_handle* h, const qpn_gavi* g, int batch, const double* w, const double* z0,
+                                      int presolve, int max_pivots, double* z_out, double* zfull_out,
+                                      int32_t* status_out, int32_t* pivots_out, int8_t* basis_out) {
+    if (!h || !g) return -1;
+    CK(cudaSetDevice(h->device));
+    const size_t dz = (size_t)g->d1 + g->d2, n = dz + g->d2, B = batch;
+    Arena a(h);
+    GaviSlots gs = plan_gavi(a, g);
+    int sw = a.add(8 * (size_t)g->np * B), sz0 = a.add(8 * dz * B), sz = a.add(8 * dz * B);
+    int szf = zfull_out ? a.add(8 * n * B) : -1, sst = a.add(4 * B), spv = a.add(4 * B), sb = basis_out ? a.add(n * B) : -1;
+    if (a.commit()) return -1;
+    GaviDesc d;
+    if (stage_gavi(h, a, gs, g, &d)) return -1;
+    if (up(h, a.ptr<double>(sw), w, 8 * (size_t)g->np * B) || up(h, a.ptr<double>(sz0), z0, 8 * dz * B)) return -1;
+    if (launch_gavi(h, d, batch, a.ptr<double>(sw), a.ptr<double>(sz0), presolve, max_pivots, a.ptr<double>(sz),
+                    a.ptr<double>(szf), a.ptr<int32_t>(sst), a.ptr<int32_t>(spv), a.ptr<int8_t>(sb), h->stream)) return -1;
+    if (down(h, z_out, a.ptr<double>(sz), 8 * dz * B) || down(h, zfull_out, a.ptr<double>(szf), 8 * n * B) ||
+        down(h, status_out, a.ptr<int32_t>(sst), 4 * B) || down(h, pivots_out, a.ptr<int32_t>(spv), 4 * B) ||
+        down(h, basis_out, a.ptr<int8_t>(sb), n * B)) return -1;
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ---- comp_indices ------------------------------------------------------------------------------
+extern "C" int qpn_comp_indices_batched(qpn_handle* h, const qpn_gavi* g, int batch, const double* z, const double* w,
+                                        double tol, int8_t* mask_out) {
+    if (!h || !g) return -1;
+    if (batch <= 0) return 0;
+    CK(cudaSetDevice(h->device));
+    const size_t dz = (size_t)g->d1 + g->d2, B = batch;
+    Arena a(h);
+    GaviSlots gs = plan_gavi(a, g);
+    int sz = a.add(8 * dz * B), sw = a.add(8 * (size_t)g->np * B), sm = a.add(dz * B);
+    if (a.commit()) return -1;
+    GaviDesc d;
+    if (stage_gavi(h, a, gs, g, &d)) return -1;
+    if (up(h, a.ptr<double>(sz), z, 8 * dz * B) || up(h, a.ptr<double>(sw), w, 8 * (size_t)g->np * B)) return -1;
+    const long long total = (long long)dz * B;
+    comp_indices_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(d, batch, a.ptr<double>(sz), a.ptr<double>(sw), tol, a.ptr<int8_t>(sm));
+    h->launches++;
+    CK(cudaGetLastError());
+    if (down(h, mask_out, a.ptr<int8_t>(sm), dz * B)) return -1;
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ---- Base.in -------------------------------------------------------------------------------------
+extern "C" int qpn_halfspace_in_batched(qpn_handle* h, int npoly, int d, int mtot, const int32_t* poly_ptr,
+                                        const double* A, const double* l, const double* u, const uint8_t* rl,
+                                        const uint8_t* ru, int npts, const double* x, double tol, uint8_t* in_out) {
+    if (!h) return -1;
+    if (npoly <= 0 || npts <= 0) return 0;
+    CK(cudaSetDevice(h->device));
+    Arena a(h);
+    const size_t m = mtot;
+    int sp = a.add(4 * (size_t)(npoly + 1)), sA = a.add(8 * m * d), sl = a.add(8 * m), su = a.add(8 * m);
+    int srl = rl ? a.add(m) : -1, sru = ru ? a.add(m) : -1, sx = a.add(8 * (size_t)d * npts), so = a.add((size_t)npoly * npts);
+    if (a.commit()) return -1;
+    if (up(h, a.ptr<int32_t>(sp), poly_ptr, 4 * (size_t)(npoly + 1)) || up(h, a.ptr<double>(sA), A, 8 * m * d) ||
+        up(h, a.ptr<double>(sl), l, 8 * m) || up(h, a.ptr<double>(su), u, 8 * m) || up(h, a.ptr<uint8_t>(srl), rl, m) ||
+        up(h, a.ptr<uint8_t>(sru), ru, m) || up(h, a.ptr<double>(sx), x, 8 * (size_t)d * npts)) return -1;
+    const long long warps = (long long)npoly * npts;
+    const int threads = 256;
+    halfspace_in_kernel<<<(unsigned)((warps * 32 + threads - 1) / threads), threads, 0, h->stream>>>(
+        npoly, d, mtot, a.ptr<int32_t>(sp), a.ptr<double>(sA), a.ptr<double>(sl), a.ptr<double>(su), a.ptr<uint8_t>(srl),
+        a.ptr<uint8_t>(sru), npts, a.ptr<double>(sx), tol, a.ptr<uint8_t>(so));
+    h->launches++;
+    CK(cudaGetLastError());
+    if (down(h, in_out, a.ptr<uint8_t>(so), (size_t)npoly * npts)) return -1;
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+#include "qpn_level_host.inc"

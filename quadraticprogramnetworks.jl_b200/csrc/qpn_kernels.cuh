@@ -1,0 +1,191 @@
+// Kernels of libqpn_cuda (sm_100a).  One CTA per instance for everything that pivots;
+// one warp per (poly, point) / one thread per index for the coalesced evaluation kernels.
+#pragma once
+#include "avi_pivot.cuh"
+
+namespace qpn {
+
+// Device view of qpn_matrix.
+struct MatDesc {
+    const double* dense;
+    const int32_t* colptr;
+    const int32_t* rowval;
+    const double* nzval;
+    int nnz, base, shared;
+};
+
+// T[:, 0:n] = -M for instance b.  Ends with a barrier.
+__device__ inline void load_neg_matrix(Tab& t, const MatDesc& M, int b) {
+    const int n = t.n, ld = t.ld;
+    if (M.dense) {
+        const double* src = M.dense + (M.shared ? 0 : (size_t)b * n * n);
+        for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+            const int j = e / n, i = e - j * n;
+            t.T[(size_t)j * ld + i] = -src[e];
+        }
+    } else {
+        for (int e = threadIdx.x; e < n * ld; e += blockDim.x) t.T[e] = 0.0;
+        __syncthreads();
+        const double* nz = M.nzval + (M.shared ? 0 : (size_t)b * M.nnz);
+        for (int j = 0; j < n; ++j) {
+            const int k0 = M.colptr[j] - M.base, k1 = M.colptr[j + 1] - M.base;
+            for (int k = k0 + threadIdx.x; k < k1; k += blockDim.x)
+                t.T[(size_t)j * ld + (M.rowval[k] - M.base)] = -nz[k];
+        }
+    }
+    __syncthreads();
+}
+
+// r_i = (M z)_i + q_i with T[:, 0:n] = -M and z in shared memory; sequential in j.
+__device__ inline double residual_row(const Tab& t, const double* zs, double qi, int i) {
+    double acc = 0.0;
+    for (int j = 0; j < t.n; ++j) {
+        const double mij = -t.T[(size_t)j * t.ld + i];
+        if (mij != 0.0) acc = fma(mij, zs[j], acc);
+    }
+    return acc + qi;
+}
+
+// ---- solve_avi (avi.jl:63-77) ------------------------------------------------------------
+// grid = batch, block = roundup32(n).  Dynamic smem: Tab + q(n) + z(n).
+__global__ void avi_solve_kernel(int n, int ld, int batch, MatDesc M, const double* __restrict__ q,
+                                 const double* __restrict__ l, const double* __restrict__ u,
+                                 int lu_shared, const double* __restrict__ z0, int max_pivots,
+                                 double* __restrict__ z_out, int32_t* __restrict__ status_out,
+                                 int32_t* __restrict__ pivots_out, int8_t* __restrict__ basis_out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int b = blockIdx.x, i = threadIdx.x;
+    Tab t;
+    tab_carve(t, n, ld, smem);
+    double* qs = reinterpret_cast<double*>(smem + tab_smem_bytes(n, ld));
+    double* zs = qs + n;
+    if (i < n) {
+        qs[i] = q[(size_t)b * n + i];
+        zs[i] = z0[(size_t)b * n + i];
+        t.l[i] = l[(lu_shared ? 0 : (size_t)b * n) + i];
+        t.u[i] = u[(lu_shared ? 0 : (size_t)b * n) + i];
+    }
+    load_neg_matrix(t, M, b);
+    tab_start(t, qs, zs);
+    double zi = 0.0; int8_t code = 0;
+    int st = avi_pivot_run(t, max_pivots, &zi, &code);
+    const int piv = t.pivots;
+    // final check (avi.jl:71-74) against the original matrix
+    __syncthreads();
+    if (i < n) zs[i] = zi;
+    load_neg_matrix(t, M, b);
+    int bad = 0;
+    if (i < n) bad = check_avi_index(residual_row(t, zs, qs[i], i), zi, t.l[i], t.u[i], 1e-6);
+    bad = __syncthreads_or(bad);
+    if (st == ST_SUCCESS && bad) st = ST_FAILURE;
+    if (i < n) {
+        z_out[(size_t)b * n + i] = zi;
+        if (basis_out) basis_out[(size_t)b * n + i] = code;
+    }
+    if (i == 0) { status_out[b] = st; pivots_out[b] = piv; }
+}
+
+// ---- check_avi_solution (avi.jl:148-156): one warp per instance, lanes over rows -----------
+__global__ void check_avi_kernel(int n, int batch, MatDesc M, const double* __restrict__ q,
+                                 const double* __restrict__ l, const double* __restrict__ u,
+                                 int lu_shared, const double* __restrict__ z, double tol,
+                                 int32_t* __restrict__ bad_out, double* __restrict__ r_out) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= batch) return;
+    const int b = warp;
+    const double* zb = z + (size_t)b * n;
+    int bad = 0;
+    for (int i = lane; i < n; i += 32) {
+        double acc = 0.0;
+        if (M.dense) {
+            const double* src = M.dense + (M.shared ? 0 : (size_t)b * n * n);
+            for (int j = 0; j < n; ++j) {
+                const double mij = src[(size_t)j * n + i];
+                if (mij != 0.0) acc = fma(mij, zb[j], acc);
+            }
+        } else {
+            const double* nz = M.nzval + (M.shared ? 0 : (size_t)b * M.nnz);
+            for (int j = 0; j < n; ++j) {           // row i of a CSC matrix: scan the columns
+                const int k0 = M.colptr[j] - M.base, k1 = M.colptr[j + 1] - M.base;
+                for (int k = k0; k < k1; ++k)
+                    if (M.rowval[k] - M.base == i) acc = fma(nz[k], zb[j], acc);
+            }
+        }
+        const double r = acc + q[(size_t)b * n + i];
+        if (r_out) r_out[(size_t)b * n + i] = r;
+        const size_t o = (lu_shared ? 0 : (size_t)b * n) + i;
+        bad += check_avi_index(r, zb[i], l[o], u[o], tol);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
+    if (lane == 0) bad_out[b] = bad;
+}
+
+// Device view of qpn_gavi.
+struct GaviDesc {
+    int d1, d2, np;
+    const double *M, *N, *o, *l1, *u1, *A, *B, *l2, *u2;
+};
+
+// ---- comp_indices (avi_solutions.jl:511-612): one thread per (index, instance) -------------
+__device__ inline bool approx_eq(double a, double b, double atol) { return a == b || fabs(a - b) <= atol; }
+
+__device__ inline int8_t comp_mask(double l, double u, double r, double z, double tol) {
+    const bool eq = approx_eq(l, u, tol);
+    int m = 0;
+    if (approx_eq(z, l, tol) && r >= -tol && !eq) m |= 1;
+    if (l - tol <= z && z <= u + tol && approx_eq(r, 0.0, tol) && !eq) m |= 2;
+    if (approx_eq(z, u, tol) && r <= tol && !eq) m |= 4;
+    if (m == 0) m = eq ? 8 : 0;
+    return (int8_t)m;
+}
+
+__global__ void comp_indices_kernel(GaviDesc g, int batch, const double* __restrict__ z,
+                                    const double* __restrict__ w, double tol, int8_t* __restrict__ mask) {
+    const int dz = g.d1 + g.d2;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)batch * dz) return;
+    const int b = (int)(gid / dz), i = (int)(gid - (long long)b * dz);
+    const double* zb = z + (size_t)b * dz;
+    const double* wb = w + (size_t)b * g.np;
+    if (i < g.d1) {
+        double acc = 0.0, acc2 = 0.0;
+        for (int j = 0; j < dz; ++j) acc = fma(g.M[(size_t)j * g.d1 + i], zb[j], acc);
+        for (int j = 0; j < g.np; ++j) acc2 = fma(g.N[(size_t)j * g.d1 + i], wb[j], acc2);
+        const double r = (acc + acc2) + g.o[i];
+        mask[(size_t)b * dz + i] = comp_mask(g.l1[i], g.u1[i], r, zb[i], tol);
+    } else {
+        const int k = i - g.d1;
+        double acc = 0.0, acc2 = 0.0;
+        for (int j = 0; j < dz; ++j) acc = fma(g.A[(size_t)j * g.d2 + k], zb[j], acc);
+        for (int j = 0; j < g.np; ++j) acc2 = fma(g.B[(size_t)j * g.d2 + k], wb[j], acc2);
+        const double s = acc + acc2;
+        mask[(size_t)b * dz + i] = comp_mask(g.l2[k], g.u2[k], zb[i], s, tol);
+    }
+}
+
+// ---- Base.in(x, poly) (sets.jl:820-825,850-853): one warp per (poly, point) -----------------
+// Lanes take rows of the poly; each row dot product is sequential in the coordinate index.
+__global__ void halfspace_in_kernel(int npoly, int d, int mtot, const int32_t* __restrict__ poly_ptr,
+                                    const double* __restrict__ A, const double* __restrict__ l,
+                                    const double* __restrict__ u, const uint8_t* __restrict__ rl,
+                                    const uint8_t* __restrict__ ru, int npts, const double* __restrict__ x,
+                                    double tol, uint8_t* __restrict__ in_out) {
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= (long long)npoly * npts) return;
+    const int p = (int)(warp % npoly), pt = (int)(warp / npoly);
+    const double* xp = x + (size_t)pt * d;
+    int ok = 1;
+    for (int row = poly_ptr[p] + lane; row < poly_ptr[p + 1]; row += 32) {
+        double ax = 0.0;
+        for (int j = 0; j < d; ++j) ax = fma(A[(size_t)j * mtot + row], xp[j], ax);
+        const bool lo = (rl && rl[row]) ? (l[row] - tol < ax) : (l[row] - tol <= ax);
+        const bool up = (ru && ru[row]) ? (ax - tol < u[row]) : (ax - tol <= u[row]);
+        if (!(lo && up)) ok = 0;
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    if (lane == 0) in_out[(size_t)pt * npoly + p] = (uint8_t)ok;
+}
+
+}  // namespace qpn

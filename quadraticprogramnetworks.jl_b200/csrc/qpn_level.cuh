@@ -1,0 +1,577 @@
+// solve_gavi, verify_solution and the fused per-level equilibrium loop on sm_100a.
+// One CTA per instance; everything an instance needs lives in shared memory.
+#pragma once
+#include "qpn_kernels.cuh"
+
+namespace qpn {
+
+// Solve (M z + q) comp. l <= z <= u in the shared-memory tableau.  `build(t)` must fill
+// T[:, 0:n] with -M and end with a barrier; it is called twice (start and final check).
+// t.l / t.u hold the bounds, qs the vector q, zs the start on entry and z on exit.
+// code (optional, smem, n entries) receives the basis codes.  Mirrors qpo_avi_solve.
+template <class Build>
+__device__ inline int solve_avi_smem(Tab& t, int n, Build build, const double* qs, double* zs,
+                                     int max_pivots, int8_t* code_out, int* pivots_acc) {
+    t.n = n;
+    build(t);
+    tab_start(t, qs, zs);
+    double zi = 0.0; int8_t code = 0;
+    int st = avi_pivot_run(t, max_pivots, &zi, &code);
+    *pivots_acc += t.pivots;
+    const int i = threadIdx.x;
+    __syncthreads();
+    if (i < n) { zs[i] = zi; if (code_out) code_out[i] = code; }
+    build(t);
+    int bad = 0;
+    if (i < n) bad = check_avi_index(residual_row(t, zs, qs[i], i), zi, t.l[i], t.u[i], 1e-6);
+    bad = __syncthreads_or(bad);
+    if (st == ST_SUCCESS && bad) st = ST_FAILURE;
+    return st;
+}
+
+// ---- shared-memory plan of a GAVI solve ------------------------------------------------------
+struct GaviSmem {
+    Tab t;
+    double *qs, *zs;      // n each (n = d1 + 2 d2)
+    double *w;            // np
+    double *z0;           // d1 + d2
+    double *c, *s0;       // d2 each
+    int* cols;            // d1 + d2 (+1: count)
+    int8_t* code;         // n
+};
+
+__host__ __device__ inline size_t gavi_extra_bytes(int d1, int d2, int np) {
+    const size_t n = (size_t)d1 + 2 * d2, dz = (size_t)d1 + d2;
+    size_t dbl = 2 * n + np + dz + 2 * (size_t)d2;
+    size_t ints = dz + 2;
+    return dbl * 8 + ((ints * 4 + 7) / 8) * 8 + ((n + 7) / 8) * 8;
+}
+__host__ __device__ inline size_t gavi_smem_bytes(int d1, int d2, int np) {
+    const int n = d1 + 2 * d2;
+    return tab_smem_bytes(n, n | 1) + gavi_extra_bytes(d1, d2, np);
+}
+
+__device__ inline unsigned char* gavi_carve(GaviSmem& s, const GaviDesc& g, int ld, unsigned char* smem) {
+    const int n = g.d1 + 2 * g.d2, dz = g.d1 + g.d2;
+    tab_carve(s.t, n, ld, smem);
+    unsigned char* p = smem + tab_smem_bytes(n, ld);
+    double* d = reinterpret_cast<double*>(p);
+    s.qs = d; d += n;
+    s.zs = d; d += n;
+    s.w = d;  d += g.np;
+    s.z0 = d; d += dz;
+    s.c = d;  d += g.d2;
+    s.s0 = d; d += g.d2;
+    s.cols = reinterpret_cast<int*>(d);
+    unsigned char* q = reinterpret_cast<unsigned char*>(d) + (((size_t)(dz + 2) * 4 + 7) / 8) * 8;
+    s.code = reinterpret_cast<int8_t*>(q);
+    return q + (((size_t)n + 7) / 8) * 8;
+}
+
+// s0 = A z0 + B w (c = B w kept).  Ends with a barrier.
+__device__ inline void gavi_slack(GaviSmem& s, const GaviDesc& g, bool recompute_c) {
+    const int i = threadIdx.x, dz = g.d1 + g.d2;
+    for (int r = i; r < g.d2; r += blockDim.x) {
+        if (recompute_c) {
+            double acc = 0.0;
+            for (int j = 0; j < g.np; ++j) acc = fma(g.B[(size_t)j * g.d2 + r], s.w[j], acc);
+            s.c[r] = acc;
+        }
+        double acc = 0.0;
+        for (int j = 0; j < dz; ++j) acc = fma(g.A[(size_t)j * g.d2 + r], s.z0[j], acc);
+        s.s0[r] = acc + s.c[r];
+    }
+    __syncthreads();
+}
+
+// solve_gavi (avi.jl:101-111) for the instance whose w and z0 are already in s.w / s.z0.
+// On return s.zs holds the lifted solution [z1; z2; s] and s.code the basis codes.
+__device__ inline int gavi_solve_smem(GaviSmem& s, const GaviDesc& g, int presolve, int max_pivots, int* pivots) {
+    const int d1 = g.d1, d2 = g.d2, dz = d1 + d2, n = d1 + 2 * d2, i = threadIdx.x;
+    Tab& t = s.t;
+    gavi_slack(s, g, true);
+    if (presolve && d2 > 0) {
+        int infeasible = 0;
+        for (int r = i; r < d2; r += blockDim.x)
+            if (!(g.l2[r] <= s.s0[r] && s.s0[r] <= g.u2[r])) infeasible = 1;
+        infeasible = __syncthreads_or(infeasible);
+        if (infeasible) {
+            // find_closest_feasible! (avi.jl:79-99): min |z - z0|^2 s.t. l2 - Bw <= A z <= u2 - Bw over
+            // the columns of A that are not structurally zero, as the lifted KKT AVI.
+            for (int j = i; j < dz; j += blockDim.x) {
+                bool nz = false;
+                for (int r = 0; r < d2; ++r) nz |= (g.A[(size_t)j * d2 + r] != 0.0);
+                s.cols[j] = nz ? 1 : 0;
+            }
+            __syncthreads();
+            if (i == 0) {
+                int k = 0;
+                for (int j = 0; j < dz; ++j) if (s.cols[j]) s.cols[k++] = j;
+                s.cols[dz] = k;
+            }
+            __syncthreads();
+            const int k = s.cols[dz], pn = k + 2 * d2;
+            if (i < pn) {
+                if (i < k) { s.qs[i] = -s.z0[s.cols[i]]; s.zs[i] = s.z0[s.cols[i]]; t.l[i] = -QPN_INF; t.u[i] = QPN_INF; }
+                else if (i < k + d2) {
+                    const int r = i - k;
+                    double full = 0.0, part = 0.0;
+                    for (int j = 0; j < dz; ++j) full = fma(g.A[(size_t)j * d2 + r], s.z0[j], full);
+                    for (int a = 0; a < k; ++a) part = fma(g.A[(size_t)s.cols[a] * d2 + r], s.z0[s.cols[a]], part);
+                    s.qs[i] = (full - part) + s.c[r];
+                    s.zs[i] = 0.0; t.l[i] = -QPN_INF; t.u[i] = QPN_INF;
+                } else {
+                    const int r = i - k - d2;
+                    s.qs[i] = 0.0; s.zs[i] = s.s0[r]; t.l[i] = g.l2[r]; t.u[i] = g.u2[r];
+                }
+            }
+            __syncthreads();
+            auto build = [&](Tab& tt) {
+                const int ld = tt.ld;
+                for (int e = threadIdx.x; e < pn * ld; e += blockDim.x) tt.T[e] = 0.0;
+                __syncthreads();
+                for (int e = threadIdx.x; e < k * d2; e += blockDim.x) {
+                    const int a = e / d2, r = e - a * d2;
+                    const double v = g.A[(size_t)s.cols[a] * d2 + r];
+                    tt.T[(size_t)(k + r) * ld + a] = v;          // -(-A')
+                    tt.T[(size_t)a * ld + (k + r)] = -v;         // -(A)
+                }
+                for (int e = threadIdx.x; e < k; e += blockDim.x) tt.T[(size_t)e * ld + e] = -1.0;
+                for (int e = threadIdx.x; e < d2; e += blockDim.x) {
+                    tt.T[(size_t)(k + d2 + e) * ld + (k + e)] = 1.0;     // -(-1)
+                    tt.T[(size_t)(k + e) * ld + (k + d2 + e)] = -1.0;    // -(+1)
+                }
+                __syncthreads();
+            };
+            const int pst = solve_avi_smem(t, pn, build, s.qs, s.zs, 50 * pn + 100, nullptr, pivots);
+            __syncthreads();
+            if (pst == ST_SUCCESS && i < k) s.z0[s.cols[i]] = s.zs[i];
+            __syncthreads();
+            gavi_slack(s, g, false);
+        }
+    }
+    // convert (avi.jl:113-128): lifted AVI over [z1; z2; s]
+    if (i < n) {
+        if (i < d1) {
+            double acc = 0.0;
+            for (int j = 0; j < g.np; ++j) acc = fma(g.N[(size_t)j * d1 + i], s.w[j], acc);
+            s.qs[i] = acc + g.o[i];
+            t.l[i] = g.l1[i]; t.u[i] = g.u1[i];
+        } else if (i < dz) {
+            s.qs[i] = s.c[i - d1]; t.l[i] = -QPN_INF; t.u[i] = QPN_INF;
+        } else {
+            s.qs[i] = 0.0; t.l[i] = g.l2[i - dz]; t.u[i] = g.u2[i - dz];
+        }
+        s.zs[i] = i < dz ? s.z0[i] : s.s0[i - dz];
+    }
+    __syncthreads();
+    auto build = [&](Tab& tt) {
+        const int ld = tt.ld;
+        for (int e = threadIdx.x; e < n * ld; e += blockDim.x) tt.T[e] = 0.0;
+        __syncthreads();
+        for (int e = threadIdx.x; e < d1 * dz; e += blockDim.x) {
+            const int j = e / d1, r = e - j * d1;
+            tt.T[(size_t)j * ld + r] = -g.M[e];
+        }
+        for (int e = threadIdx.x; e < d2 * dz; e += blockDim.x) {
+            const int j = e / d2, r = e - j * d2;
+            tt.T[(size_t)j * ld + d1 + r] = -g.A[e];
+        }
+        for (int e = threadIdx.x; e < d2; e += blockDim.x) {
+            tt.T[(size_t)(dz + e) * ld + d1 + e] = 1.0;      // -(-I)
+            tt.T[(size_t)(d1 + e) * ld + dz + e] = -1.0;     // -(+I)
+        }
+        __syncthreads();
+    };
+    return solve_avi_smem(t, n, build, s.qs, s.zs, max_pivots, s.code, pivots);
+}
+
+__global__ void gavi_solve_kernel(GaviDesc g, int ld, int batch, const double* __restrict__ w,
+                                  const double* __restrict__ z0, int presolve, int max_pivots,
+                                  double* __restrict__ z_out, double* __restrict__ zfull_out,
+                                  int32_t* __restrict__ status_out, int32_t* __restrict__ pivots_out,
+                                  int8_t* __restrict__ basis_out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int b = blockIdx.x, i = threadIdx.x;
+    const int dz = g.d1 + g.d2, n = g.d1 + 2 * g.d2;
+    GaviSmem s;
+    gavi_carve(s, g, ld, smem);
+    for (int j = i; j < g.np; j += blockDim.x) s.w[j] = w[(size_t)b * g.np + j];
+    for (int j = i; j < dz; j += blockDim.x) s.z0[j] = z0[(size_t)b * dz + j];
+    __syncthreads();
+    int piv = 0;
+    const int st = gavi_solve_smem(s, g, presolve, max_pivots, &piv);
+    __syncthreads();
+    if (i < dz) z_out[(size_t)b * dz + i] = s.zs[i];
+    if (i < n) {
+        if (zfull_out) zfull_out[(size_t)b * n + i] = s.zs[i];
+        if (basis_out) basis_out[(size_t)b * n + i] = s.code[i];
+    }
+    if (i == 0) { status_out[b] = st; pivots_out[b] = piv; }
+}
+
+// ---- verify_solution (qp_processing.jl:57-149) ---------------------------------------------------
+struct NodeDesc {
+    int nd, nv, m;
+    const double *Qd, *qd, *A, *l, *u;
+    const int32_t* dec;
+};
+
+struct VerifySmem {
+    double *qt;     // nd
+    double *ax;     // m
+    double *Ab;     // nd x m
+    double *Ab0;    // nd x m
+    double *b;      // nd
+    double *lam;    // m
+    double *v;      // nd + m
+    double *lam_out;// m
+    double *qs, *zs;// m each (fallback AVI)
+    int *idx;       // m
+    int *perm;      // m
+    int8_t *kind;   // m
+};
+
+__host__ __device__ inline size_t verify_smem_bytes(int nd, int m) {
+    size_t dbl = (size_t)nd + m + 2 * (size_t)nd * m + nd + m + (nd + m) + m + 2 * (size_t)m;
+    size_t ints = 2 * (size_t)m;
+    return dbl * 8 + ((ints * 4 + 7) / 8) * 8 + (((size_t)m + 7) / 8) * 8;
+}
+
+__device__ inline void verify_carve(VerifySmem& v, int nd, int m, unsigned char* p) {
+    double* d = reinterpret_cast<double*>(p);
+    v.qt = d; d += nd;
+    v.ax = d; d += m;
+    v.Ab = d; d += (size_t)nd * m;
+    v.Ab0 = d; d += (size_t)nd * m;
+    v.b = d; d += nd;
+    v.lam = d; d += m;
+    v.v = d; d += nd + m;
+    v.lam_out = d; d += m;
+    v.qs = d; d += m;
+    v.zs = d; d += m;
+    int* ip = reinterpret_cast<int*>(d);
+    v.idx = ip; ip += m;
+    v.perm = ip; ip += m;
+    v.kind = reinterpret_cast<int8_t*>(reinterpret_cast<unsigned char*>(d) + (((size_t)2 * m * 4 + 7) / 8) * 8);
+}
+
+// Householder QR least squares with column pivoting, one thread per column; reductions run
+// down a column sequentially so the bits match oracle/qpn_oracle.c:lstsq_basic.
+// `red` gives the block reduction scratch (Tab with red_d / red_i).
+__device__ inline void lstsq_basic_block(const Tab& red, int nd, int k, double* Ab, double* b, double* lam,
+                                         int* perm, double* v) {
+    const int j = threadIdx.x;
+    const int steps = nd < k ? nd : k;
+    for (int c = j; c < k; c += blockDim.x) perm[c] = c;
+    __syncthreads();
+    int rank = 0;
+    for (int c = 0; c < steps; ++c) {
+        double best = -1.0; int jb = -1;
+        // candidates j in [c, k): handled in strides so k may exceed blockDim
+        for (int jj = j; jj < k; jj += blockDim.x) {
+            if (jj < c) continue;
+            double s = 0.0;
+            for (int i = c; i < nd; ++i) s = fma(Ab[(size_t)jj * nd + i], Ab[(size_t)jj * nd + i], s);
+            if (jb < 0 || s > best) { best = s; jb = jj; }
+        }
+        block_argmax(red, best, jb);
+        const double nrm = sqrt(best);
+        if (nrm <= 1e-10) break;
+        __syncthreads();
+        if (jb != c) {
+            for (int i = j; i < nd; i += blockDim.x) {
+                const double tmp = Ab[(size_t)c * nd + i];
+                Ab[(size_t)c * nd + i] = Ab[(size_t)jb * nd + i];
+                Ab[(size_t)jb * nd + i] = tmp;
+            }
+            if (j == 0) { const int tp = perm[c]; perm[c] = perm[jb]; perm[jb] = tp; }
+        }
+        __syncthreads();
+        const double alpha = Ab[(size_t)c * nd + c] > 0.0 ? -nrm : nrm;
+        for (int i = c + j; i < nd; i += blockDim.x) v[i] = Ab[(size_t)c * nd + i] - (i == c ? alpha : 0.0);
+        __syncthreads();
+        double vn = 0.0;
+        for (int i = c; i < nd; ++i) vn = fma(v[i], v[i], vn);
+        if (vn > 0.0) {
+            for (int jj = j; jj < k + 1; jj += blockDim.x) {
+                if (jj < c) continue;
+                double* col = (jj < k) ? Ab + (size_t)jj * nd : b;     // the rhs rides as column k
+                double s = 0.0;
+                for (int i = c; i < nd; ++i) s = fma(v[i], col[i], s);
+                s = (2.0 * s) / vn;
+                for (int i = c; i < nd; ++i) col[i] = fma(-s, v[i], col[i]);
+            }
+        }
+        rank++;
+        __syncthreads();
+    }
+    __syncthreads();
+    if (j == 0) {
+        for (int t = 0; t < k; ++t) lam[t] = 0.0;
+        for (int i = rank - 1; i >= 0; --i) {
+            double acc = b[i];
+            for (int t = i + 1; t < rank; ++t) acc = fma(-Ab[(size_t)t * nd + i], v[t], acc);
+            v[i] = acc / Ab[(size_t)i * nd + i];
+        }
+        for (int i = 0; i < rank; ++i) lam[perm[i]] = v[i];
+    }
+    __syncthreads();
+}
+
+// Returns 1 when x (shared memory, nv entries) is a solution for the node; lam in vs.lam_out.
+// tab: a tableau workspace large enough for an AVI of size m (used by the fallback and for
+// the reduction scratch).
+__device__ inline int verify_solution_smem(Tab& tab, VerifySmem& vs, const NodeDesc& nd_, const double* x, double tol,
+                                           int* how, int* pivots) {
+    const int nd = nd_.nd, nv = nd_.nv, m = nd_.m, i = threadIdx.x;
+    for (int r = i; r < nd; r += blockDim.x) {
+        double acc = 0.0;
+        for (int j = 0; j < nv; ++j) acc = fma(nd_.Qd[(size_t)j * nd + r], x[j], acc);
+        vs.qt[r] = acc + nd_.qd[r];
+    }
+    int infeasible = 0;
+    for (int r = i; r < m; r += blockDim.x) {
+        double acc = 0.0;
+        for (int j = 0; j < nv; ++j) acc = fma(nd_.A[(size_t)j * m + r], x[j], acc);
+        vs.ax[r] = acc;
+        vs.lam_out[r] = 0.0;
+        const double lo = nd_.l[r], up = nd_.u[r];
+        if (!((lo - 1e-3 <= acc) && (acc - 1e-3 <= up))) infeasible = 1;
+        const bool pos = acc < lo + 1e-2, neg = acc > up - 1e-2;
+        vs.kind[r] = (pos && neg) ? 3 : pos ? 1 : neg ? 2 : 0;
+    }
+    infeasible = __syncthreads_or(infeasible);
+    if (infeasible) { *how = 0; return 0; }
+    double nq = 0.0;
+    for (int r = 0; r < nd; ++r) nq = fma(vs.qt[r], vs.qt[r], nq);
+    if (m == 0) { *how = 1; return sqrt(nq) <= tol ? 1 : 0; }
+    // order the active rows: lower-active, upper-active, both (qp_processing.jl:105-114)
+    if (i == 0) {
+        int k = 0, np_ = 0, nn = 0;
+        for (int r = 0; r < m; ++r) if (vs.kind[r] == 1) { vs.idx[k++] = r; np_++; }
+        for (int r = 0; r < m; ++r) if (vs.kind[r] == 2) { vs.idx[k++] = r; nn++; }
+        for (int r = 0; r < m; ++r) if (vs.kind[r] == 3) { vs.idx[k++] = r; }
+        tab.red_i[32] = k; tab.red_i[33] = np_; vs.perm[0] = 0;
+        tab.red_d[33] = (double)nn;
+    }
+    __syncthreads();
+    const int k = tab.red_i[32], np_ = tab.red_i[33], nn = (int)tab.red_d[33];
+    for (int e = i; e < nd * k; e += blockDim.x) {
+        const int tcol = e / nd, r = e - tcol * nd;
+        const double sgn = (tcol >= np_ && tcol < np_ + nn) ? -1.0 : 1.0;
+        const double val = sgn * nd_.A[(size_t)nd_.dec[r] * m + vs.idx[tcol]];
+        vs.Ab[e] = val; vs.Ab0[e] = val;
+    }
+    for (int r = i; r < nd; r += blockDim.x) vs.b[r] = vs.qt[r];
+    __syncthreads();
+    lstsq_basic_block(tab, nd, k, vs.Ab, vs.b, vs.lam, vs.perm, vs.v);
+    // acceptance (qp_processing.jl:119)
+    if (i == 0) {
+        int ok = 1;
+        for (int t = 0; t < np_ + nn; ++t) if (!(vs.lam[t] > -tol)) ok = 0;
+        double res = 0.0;
+        for (int r = 0; r < nd; ++r) {
+            double acc = 0.0;
+            for (int t = 0; t < k; ++t) acc = fma(vs.Ab0[(size_t)t * nd + r], vs.lam[t], acc);
+            const double e = acc - vs.qt[r];
+            res = fma(e, e, res);
+        }
+        if (!(sqrt(res) <= tol)) ok = 0;
+        tab.red_i[32] = ok;
+    }
+    __syncthreads();
+    if (tab.red_i[32]) {
+        for (int t = i; t < k; t += blockDim.x)
+            vs.lam_out[vs.idx[t]] = (t >= np_ && t < np_ + nn) ? -vs.lam[t] : vs.lam[t];
+        __syncthreads();
+        *how = 2;
+        return 1;
+    }
+    // fallback (qp_processing.jl:129-146): sign-constrained least squares as the box AVI
+    //   (Ad Ad') lam - Ad qt  comp.  lb <= lam <= ub
+    __syncthreads();
+    for (int r = i; r < m; r += blockDim.x) {
+        double acc = 0.0;
+        for (int t = 0; t < nd; ++t) acc = fma(nd_.A[(size_t)nd_.dec[t] * m + r], vs.qt[t], acc);
+        vs.qs[r] = -acc;
+        vs.zs[r] = 0.0;
+        const int8_t kd = vs.kind[r];
+        tab.l[r] = (kd == 2 || kd == 3) ? -QPN_INF : 0.0;
+        tab.u[r] = (kd == 1 || kd == 3) ? QPN_INF : 0.0;
+    }
+    __syncthreads();
+    auto build = [&](Tab& tt) {
+        const int ld = tt.ld;
+        for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
+            const int c = e / m, r = e - c * m;
+            double acc = 0.0;
+            for (int t = 0; t < nd; ++t) acc = fma(nd_.A[(size_t)nd_.dec[t] * m + r], nd_.A[(size_t)nd_.dec[t] * m + c], acc);
+            tt.T[(size_t)c * ld + r] = -acc;
+        }
+        __syncthreads();
+    };
+    const int n_keep = tab.n;
+    const int st = solve_avi_smem(tab, m, build, vs.qs, vs.zs, 50 * m + 100, nullptr, pivots);
+    tab.n = n_keep;
+    __syncthreads();
+    if (st != ST_SUCCESS) { *how = 5; return 0; }
+    if (i == 0) {
+        double res2 = 0.0;
+        for (int t = 0; t < nd; ++t) {
+            double acc = 0.0;
+            for (int r = 0; r < m; ++r) acc = fma(nd_.A[(size_t)nd_.dec[t] * m + r], vs.zs[r], acc);
+            const double e = acc - vs.qt[t];
+            res2 = fma(e, e, res2);
+        }
+        tab.red_i[32] = sqrt(res2) <= 1e-4 ? 1 : 0;
+    }
+    for (int r = i; r < m; r += blockDim.x) vs.lam_out[r] = vs.zs[r];
+    __syncthreads();
+    const int ok2 = tab.red_i[32];
+    *how = ok2 ? 3 : 4;
+    return ok2;
+}
+
+// grid = batch, block = roundup32(max(m, nd, 1)).  Dynamic smem: Tab(m) + VerifySmem + x(nv).
+__global__ void verify_solution_kernel(NodeDesc node, int ld, int batch, const double* __restrict__ x, double tol,
+                                       uint8_t* __restrict__ solution_out, double* __restrict__ lam_out,
+                                       int32_t* __restrict__ how_out, int8_t* __restrict__ active_out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int b = blockIdx.x, i = threadIdx.x, m = node.m;
+    const int tn = m > 0 ? m : 1;
+    Tab tab;
+    tab_carve(tab, tn, ld, smem);
+    VerifySmem vs;
+    unsigned char* p = smem + tab_smem_bytes(tn, ld);
+    verify_carve(vs, node.nd, m, p);
+    double* xs = reinterpret_cast<double*>(p + verify_smem_bytes(node.nd, m));
+    for (int j = i; j < node.nv; j += blockDim.x) xs[j] = x[(size_t)b * node.nv + j];
+    __syncthreads();
+    int how = 0, piv = 0;
+    const int sol = verify_solution_smem(tab, vs, node, xs, tol, &how, &piv);
+    __syncthreads();
+    for (int r = i; r < m; r += blockDim.x) {
+        if (lam_out) lam_out[(size_t)b * m + r] = vs.lam_out[r];
+        if (active_out) active_out[(size_t)b * m + r] = how == 0 ? 0 : vs.kind[r];
+    }
+    if (i == 0) { solution_out[b] = (uint8_t)sol; if (how_out) how_out[b] = how; }
+}
+
+// ---- fused per-level equilibrium loop (algorithm.jl:13-118, level without children) --------------
+constexpr int QPN_MAX_PLAYERS = 8;
+
+struct LevelDesc {
+    int nv, nplayers;
+    NodeDesc players[QPN_MAX_PLAYERS];
+    GaviDesc g;
+    const int32_t* dec;     // nd_level
+    const int32_t* par;     // g.np
+    int nd_level;
+    int max_iters;
+    int nproj;
+    const double* proj;     // nv x nproj
+    int max_nd, max_m;      // over players
+    int lam_total;          // sum of m over players
+};
+
+__host__ __device__ inline size_t level_smem_bytes(const LevelDesc& lv) {
+    return gavi_smem_bytes(lv.g.d1, lv.g.d2, lv.g.np) + verify_smem_bytes(lv.max_nd, lv.max_m) +
+           8 * (2 * (size_t)lv.nv + (size_t)(lv.nproj > 0 ? lv.nproj : 1));
+}
+
+// hist: global scratch, batch x hist_cap x nproj (cycle check history); hist_count: batch.
+__global__ void level_equilibrium_kernel(LevelDesc lv, int ld, int batch, const double* __restrict__ x_init,
+                                         double* __restrict__ x_out, uint8_t* __restrict__ solved_out,
+                                         int32_t* __restrict__ iters_out, int32_t* __restrict__ pivots_out,
+                                         double* __restrict__ lam_out, double* __restrict__ hist,
+                                         int32_t* __restrict__ hist_count, int hist_cap, int presolve) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int b = blockIdx.x, i = threadIdx.x, nv = lv.nv;
+    GaviSmem gs;
+    unsigned char* p = gavi_carve(gs, lv.g, ld, smem);
+    VerifySmem vs;
+    verify_carve(vs, lv.max_nd, lv.max_m, p);
+    double* xs = reinterpret_cast<double*>(p + verify_smem_bytes(lv.max_nd, lv.max_m));
+    double* pv = xs + nv;                  // nproj
+    double* xn = pv + (lv.nproj > 0 ? lv.nproj : 1);
+    for (int j = i; j < nv; j += blockDim.x) xs[j] = x_init[(size_t)b * nv + j];
+    __syncthreads();
+    const int n_level = lv.g.d1 + 2 * lv.g.d2;
+    const int max_piv = 50 * n_level + 100;
+    int solved = 0, piv = 0, iters = 0;
+    // The history outlives one call when the caller keeps hist / hist_count (the reference's
+    // iterate_cache persists across the calls of one top-level solve, algorithm.jl:20-28).
+    double* myhist = hist ? hist + (size_t)b * hist_cap * lv.nproj : nullptr;
+    int nhist = (hist && hist_count) ? hist_count[b] : 0;
+    for (int it = 1; it <= lv.max_iters; ++it) {
+        iters = it;
+        // cycle check (algorithm.jl:14-30): random projections of the iterate against the history
+        if (lv.nproj > 0 && myhist) {
+            for (int k = i; k < lv.nproj; k += blockDim.x) {
+                double acc = 0.0;
+                for (int j = 0; j < nv; ++j) acc = fma(xs[j], lv.proj[(size_t)k * nv + j], acc);
+                pv[k] = acc;
+            }
+            __syncthreads();
+            int cyc = 0;
+            for (int h = i; h < nhist; h += blockDim.x) {
+                const double* ph = myhist + (size_t)h * lv.nproj;
+                double dd = 0.0, na = 0.0, nb2 = 0.0;
+                for (int k = 0; k < lv.nproj; ++k) {
+                    const double e = pv[k] - ph[k];
+                    dd = fma(e, e, dd); na = fma(pv[k], pv[k], na); nb2 = fma(ph[k], ph[k], nb2);
+                }
+                // isapprox with the default rtol = sqrt(eps)
+                if (sqrt(dd) <= 1.4901161193847656e-8 * fmax(sqrt(na), sqrt(nb2))) cyc = 1;
+            }
+            cyc = __syncthreads_or(cyc);
+            if (cyc) break;
+            if (nhist < hist_cap) {
+                for (int k = i; k < lv.nproj; k += blockDim.x) myhist[(size_t)nhist * lv.nproj + k] = pv[k];
+                nhist++;
+            }
+            __syncthreads();
+        }
+        // process_qp for every player at the level (algorithm.jl:47-49)
+        int all_sol = 1, lam_off = 0;
+        for (int pl = 0; pl < lv.nplayers; ++pl) {
+            const NodeDesc& node = lv.players[pl];
+            int how = 0;
+            gs.t.n = n_level;
+            const int sol = verify_solution_smem(gs.t, vs, node, xs, 1e-4, &how, &piv);
+            __syncthreads();
+            if (lam_out)
+                for (int r = i; r < node.m; r += blockDim.x) lam_out[(size_t)b * lv.lam_total + lam_off + r] = sol ? vs.lam_out[r] : 0.0;
+            lam_off += node.m;
+            if (!sol) all_sol = 0;
+            __syncthreads();
+        }
+        if (all_sol) { solved = 1; break; }
+        // solve_qep (avi.jl:382-444)
+        for (int j = i; j < lv.g.np; j += blockDim.x) gs.w[j] = xs[lv.par[j]];
+        for (int j = i; j < lv.g.d1 + lv.g.d2; j += blockDim.x) gs.z0[j] = j < lv.nd_level ? xs[lv.dec[j]] : 0.0;
+        __syncthreads();
+        gs.t.n = n_level;
+        const int st = gavi_solve_smem(gs, lv.g, presolve, max_piv, &piv);
+        __syncthreads();
+        if (st != ST_SUCCESS) break;
+        for (int j = i; j < nv; j += blockDim.x) xn[j] = xs[j];
+        __syncthreads();
+        for (int j = i; j < lv.nd_level; j += blockDim.x) xn[lv.dec[j]] = gs.zs[j];
+        __syncthreads();
+        double dn = 0.0;
+        for (int j = 0; j < nv; ++j) { const double e = xn[j] - xs[j]; dn = fma(e, e, dn); }
+        if (sqrt(dn) < 1e-4) break;        // algorithm.jl:96-97: disagreement -> solved = false
+        __syncthreads();
+        for (int j = i; j < nv; j += blockDim.x) xs[j] = xn[j];
+        __syncthreads();
+    }
+    for (int j = i; j < nv; j += blockDim.x) x_out[(size_t)b * nv + j] = xs[j];
+    if (i == 0) {
+        solved_out[b] = (uint8_t)solved; iters_out[b] = iters; pivots_out[b] = piv;
+        if (hist && hist_count) hist_count[b] = nhist;
+    }
+}
+
+}  // namespace qpn

@@ -1,0 +1,218 @@
+"""GPU parity tests: every C-ABI entry point of libqpn_cuda against the C oracle on the
+same seeded inputs.  Bar: status / pivots / basis / masks bit-exact; z within 1e-8
+relative (north_star) -- and in fact bit-identical, which is asserted where noted."""
+import numpy as np
+import pytest
+
+from oracle import cport, examples, qpn_ref
+from tests import problems
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-8
+
+
+def assert_close(a, b, what=""):
+    a, b = np.asarray(a), np.asarray(b)
+    scale = np.maximum(1.0, np.maximum(np.abs(a), np.abs(b)))
+    err = np.abs(a - b) / scale
+    assert err.max(initial=0.0) <= RTOL, f"{what}: max rel err {err.max()}"
+
+
+def test_avi_four_player_dense_and_csc(engine):
+    rng = np.random.default_rng(11)
+    net, g, avi, dec, par = problems.fp_avi()
+    B = 512
+    X, z0 = problems.fp_starts(rng, B)
+    q = np.tile(avi["o"], (B, 1))
+    zo, so, po, bo = cport.avi_solve_batched(avi["M"], q, avi["l"], avi["u"], z0)
+    z, s, p, b = engine.avi_solve(avi["M"], q, avi["l"], avi["u"], z0)
+    assert (so == 1).all()
+    assert np.array_equal(s, so) and np.array_equal(p, po) and np.array_equal(b, bo)
+    assert np.array_equal(z, zo), "z must match the oracle bit for bit"
+    zc, sc, pc, bc = engine.avi_solve(None, q, avi["l"], avi["u"], z0, csc=problems.dense_to_csc(avi["M"], base=1), index_base=1)
+    assert np.array_equal(zc, zo) and np.array_equal(sc, so) and np.array_equal(pc, po) and np.array_equal(bc, bo)
+    # uniqueness (strongly monotone game): every start reaches the same equilibrium
+    assert np.ptp(z[:, :8], axis=0).max() < 1e-9
+
+
+def test_avi_tight_box_active_bounds(engine):
+    """Same game in a box so small that bounds are active at the solution."""
+    rng = np.random.default_rng(12)
+    net, g, avi, dec, par = problems.fp_avi()
+    l, u = avi["l"].copy(), avi["u"].copy()
+    l[24:] = -0.4; u[24:] = 0.4
+    B = 256
+    X = rng.uniform(-0.4, 0.4, (B, 8))
+    X[: B // 2] = rng.uniform(-2, 2, (B // 2, 8))            # half the starts are outside the box
+    z0 = np.zeros((B, 32)); z0[:, :8] = X; z0[:, 24:] = X
+    q = np.tile(avi["o"], (B, 1))
+    zo, so, po, bo = cport.avi_solve_batched(avi["M"], q, l, u, z0)
+    z, s, p, b = engine.avi_solve(avi["M"], q, l, u, z0)
+    assert (so == 1).all() and (bo[:, 24:] != 2).any()
+    assert np.array_equal(s, so) and np.array_equal(p, po) and np.array_equal(b, bo) and np.array_equal(z, zo)
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_avi_random_qps_per_instance_matrix(engine, kind):
+    rng = np.random.default_rng(100 + kind)
+    for trial in range(12):
+        n, m = int(rng.integers(2, 6)), None
+        probs = []
+        Q, c, A, l, u, z0 = problems.random_qp(rng, kind, n=n)
+        m = len(l)
+        B = 16
+        Ms, qs, ls, us, z0s = [], [], [], [], []
+        for _ in range(B):
+            Q, c, A, l, u, z0 = problems.random_qp(rng, kind, n=n, m=m - (n if kind != 1 else 0))
+            g = problems.qp_gavi(Q, c, A, l, u)
+            avi = qpn_ref.convert(g)
+            s0 = g["A"] @ z0
+            Ms.append(avi["M"]); qs.append(avi["o"]); ls.append(avi["l"]); us.append(avi["u"]); z0s.append(np.concatenate([z0, s0]))
+        Ms, qs, ls, us, z0s = map(np.array, (Ms, qs, ls, us, z0s))
+        zo, so, po, bo = cport.avi_solve_batched(Ms, qs, ls, us, z0s)
+        z, s, p, b = engine.avi_solve(Ms, qs, ls, us, z0s)
+        assert np.array_equal(s, so) and np.array_equal(p, po) and np.array_equal(b, bo)
+        assert_close(z, zo, "z")
+        assert np.array_equal(z, zo)
+
+
+def test_check_avi(engine):
+    rng = np.random.default_rng(13)
+    net, g, avi, dec, par = problems.fp_avi()
+    B = 64
+    X, z0 = problems.fp_starts(rng, B)
+    q = np.tile(avi["o"], (B, 1))
+    z, s, p, b = engine.avi_solve(avi["M"], q, avi["l"], avi["u"], z0)
+    zz = np.vstack([z[:32], z0[:32]])                    # solutions and non-solutions
+    bad, r = engine.check_avi(avi["M"], q[:64], avi["l"], avi["u"], zz)
+    for k in range(64):
+        sol_bad, cnt, rr = cport.check_avi(avi["M"], q[k], avi["l"], avi["u"], zz[k])
+        assert cnt == bad[k] and np.array_equal(rr, r[k])
+    assert (bad[:32] == 0).all() and (bad[32:] > 0).all()
+
+
+def _gavi_cases():
+    rng = np.random.default_rng(14)
+    cases = []
+    net = examples.simple_bilevel()
+    g, dec, par = qpn_ref.level_gavi(net, net.depth[2], {})
+    X = rng.normal(size=(64, 4)) * 2
+    cases.append(("simple_bilevel L2", g, dec, par, X))
+    net, g, avi, dec, par = problems.fp_avi()
+    cases.append(("four_player L1", g, dec, par, rng.uniform(-7, 7, (128, 8))))     # some outside the box -> presolve
+    net, X = problems.ra_inits(rng, 128)
+    g, dec, par = qpn_ref.level_gavi(net, net.depth[3], {})
+    cases.append(("robust_avoid L3", g, dec, par, X))
+    return cases
+
+
+def test_gavi_solve_and_comp_indices(engine):
+    for name, g, dec, par, X in _gavi_cases():
+        B = len(X)
+        dz = g["M"].shape[1]
+        w = X[:, par]
+        z0 = np.zeros((B, dz)); z0[:, :len(dec)] = X[:, dec]
+        ret = engine.gavi_solve(g, w, z0)
+        masks = engine.comp_indices(g, ret["z"], w)
+        presolved = 0
+        for k in range(B):
+            ro = cport.gavi_solve(g, z0[k], w[k])
+            presolved += int(not np.array_equal(ro["z0_projected"], z0[k]))
+            assert ro["status"] == ret["status"][k], name
+            assert ro["pivots"] == ret["pivots"][k], name
+            assert np.array_equal(ro["basis"], ret["basis"][k]), name
+            assert np.array_equal(ro["z_full"], ret["z_full"][k]), name
+            assert np.array_equal(cport.comp_indices(g, ro["z"], w[k]), masks[k]), name
+        assert (ret["status"] == 1).all(), name
+        if name != "simple_bilevel L2":
+            assert presolved > 0, f"{name}: the presolve projection was never exercised"
+
+
+def test_halfspace_in(engine):
+    rng = np.random.default_rng(15)
+    d = 6
+    polys = []
+    for _ in range(9):
+        m = int(rng.integers(1, 40))
+        A = rng.normal(size=(m, d)) * (rng.uniform(size=(m, d)) < 0.6)
+        l = rng.normal(size=m) - 1.0; u = l + rng.uniform(0, 3, m)
+        l[rng.uniform(size=m) < 0.2] = -np.inf; u[rng.uniform(size=m) < 0.2] = np.inf
+        rl = (rng.uniform(size=m) < 0.3).astype(np.uint8); ru = (rng.uniform(size=m) < 0.3).astype(np.uint8)
+        polys.append((A, l, u, rl, ru))
+    x = rng.normal(size=(200, d)) * 0.5
+    # points exactly on a boundary exercise the strict / non-strict relations
+    A0, l0 = polys[0][0], polys[0][1]
+    for tol in (1e-6, 1e-3):
+        got = engine.halfspace_in(polys, x, tol=tol)
+        for j in range(len(x)):
+            for p, (A, l, u, rl, ru) in enumerate(polys):
+                assert got[j, p] == cport.halfspace_in(A, l, u, x[j], tol, rl, ru)
+    assert got.any() and not got.all()
+
+
+def _verify_cases():
+    rng = np.random.default_rng(16)
+    cases = []
+    net = examples.four_player_matrix_game()
+    r = qpn_ref.solve_level_bottom(net, 1, np.zeros(8))
+    X = np.vstack([np.tile(r["x"], (8, 1)) + 1e-6 * rng.normal(size=(8, 8)), rng.uniform(-5, 5, (24, 8)),
+                   np.clip(rng.uniform(-9, 9, (16, 8)), -5, 5)])
+    for pid in net.depth[1]:
+        cases.append((f"four_player node {pid}", qpn_ref.node_view(net, pid), X))
+    net, Xr = problems.ra_inits(rng, 24)
+    sols = np.array([qpn_ref.solve_level_bottom(net, 3, x)["x"] for x in Xr])
+    Xall = np.vstack([sols, Xr])
+    for pid in net.depth[3]:
+        cases.append((f"robust_avoid node {pid}", qpn_ref.node_view(net, pid), Xall))
+    net = examples.simple_bilevel()
+    cases.append(("simple_bilevel node 1", qpn_ref.node_view(net, 1), np.array([[0, 0, 1.0, 1.0], [0, 0, -1.0, 0.0], [0, 0, 0.0, 0.0], [0, 0, 1.0, 0.5]])))
+    return cases
+
+
+def test_verify_solution(engine):
+    seen = set()
+    for name, view, X in _verify_cases():
+        sol, lam, how, act = engine.verify_solution(view, X)
+        for k in range(len(X)):
+            so, lo, ho, ao = cport.verify_solution(*view, X[k])
+            assert so == sol[k] and ho == how[k], (name, k, ho, how[k])
+            assert np.array_equal(ao, act[k]), (name, k)
+            assert np.array_equal(lo, lam[k]), (name, k, lo, lam[k])
+            seen.add(int(ho))
+    assert {0, 2, 4} <= seen, f"verify_solution branches exercised: {seen}"
+
+
+def test_level_equilibrium_four_player(engine):
+    import qpn_b200
+    rng = np.random.default_rng(17)
+    net = examples.four_player_matrix_game()
+    g, dec, par = qpn_ref.level_gavi(net, net.depth[1], {})
+    proj = rng.normal(size=(4, 8))
+    lv = qpn_b200.LevelArrays(8, [qpn_ref.node_view(net, p) for p in net.depth[1]], g, dec, par, max_iters=150, proj=proj)
+    B = 256
+    X = rng.uniform(-5, 5, (B, 8))
+    ret = engine.level_equilibrium(lv, X)
+    assert ret["solved"].all()
+    for k in range(0, B, 8):
+        ro = qpn_ref.solve_level_bottom(net, 1, X[k], proj)
+        assert ro["solved"] and ro["iters"] == ret["iters"][k] and ro["pivots"] == ret["pivots"][k]
+        assert np.array_equal(ro["x"], ret["x"][k])
+        assert np.array_equal(ro["lam"], ret["lam"][k])
+    assert np.ptp(ret["x"], axis=0).max() < 1e-9
+
+
+def test_level_equilibrium_robust_avoid_bottom(engine):
+    import qpn_b200
+    rng = np.random.default_rng(18)
+    net, X = problems.ra_inits(rng, 64)
+    g, dec, par = qpn_ref.level_gavi(net, net.depth[3], {})
+    lv = qpn_b200.LevelArrays(net.n_vars, [qpn_ref.node_view(net, p) for p in net.depth[3]], g, dec, par, max_iters=150, proj=None)
+    ret = engine.level_equilibrium(lv, X)
+    for k in range(len(X)):
+        ro = qpn_ref.solve_level_bottom(net, 3, X[k], None)
+        assert ro["solved"] == ret["solved"][k] and ro["iters"] == ret["iters"][k] and ro["pivots"] == ret["pivots"][k], k
+        assert np.array_equal(ro["x"], ret["x"][k])
+        if ro["solved"]:
+            assert np.array_equal(ro["lam"], ret["lam"][k])
+    assert ret["solved"].all()
