@@ -137,6 +137,8 @@ def verify_solution(Qd, qd, A, l, u, dec, x, tol=1e-4):
     lam = np.zeros(max(m, 1))
     how = np.zeros(1, np.int32)
     act = np.zeros(max(m, 1), np.int8)
+    fpiv = np.zeros(1, np.int32)
     sol = L.qpo_verify_solution(nd, nv, m, _p(Qd), _p(_f(qd)), _p(A), _p(_f(l)), _p(_f(u)), _p(dec, ip), _p(_f(x)),
-                                C.c_double(tol), _p(lam), _p(how, ip), _p(act, bp))
+                                C.c_double(tol), _p(lam), _p(how, ip), _p(act, bp), _p(fpiv, ip))
+    verify_solution.last_fallback_pivots = int(fpiv[0])
     return bool(sol), lam[:m], int(how[0]), act[:m]

@@ -602,16 +602,18 @@ static void lstsq_basic(int nd, int k, double *Ab, double *b, double *lam, int *
 /* Qd: nd x nv (rows dec of Q), qd: nd, A: m x nv stacked constraint rows, dec: nd indices
  * (0-based) into x.  lam_out: m.  Returns: 1 solution, 0 not a solution; *how: 0 infeasible,
  * 1 unconstrained, 2 least squares accepted, 3 sign-constrained fallback accepted,
- * 4 fallback rejected, 5 fallback solve failed. */
+ * 4 fallback rejected, 5 fallback solve failed.  fallback_pivots (optional): pivots the
+ * sign-constrained fallback spent. */
 int qpo_verify_solution(int nd, int nv, int m, const double *Qd, const double *qd, const double *A,
                         const double *l, const double *u, const int32_t *dec, const double *x,
-                        double tol, double *lam_out, int32_t *how, int8_t *active) {
+                        double tol, double *lam_out, int32_t *how, int8_t *active, int32_t *fallback_pivots) {
     double *qt = (double *)malloc(sizeof(double) * (size_t)(nd + 1));
     double *ax = (double *)malloc(sizeof(double) * (size_t)(m + 1));
     matvec(nd, nv, Qd, x, qt);
     for (int i = 0; i < nd; ++i) qt[i] += qd[i];
     matvec(m, nv, A, x, ax);
     int ret = 0;
+    if (fallback_pivots) *fallback_pivots = 0;
     for (int i = 0; i < m; ++i) { lam_out[i] = 0.0; if (active) active[i] = 0; }
     for (int i = 0; i < m; ++i)
         if (!((l[i] - 1e-3 <= ax[i]) && (ax[i] - 1e-3 <= u[i]))) { *how = 0; goto done; }
@@ -679,6 +681,7 @@ int qpo_verify_solution(int nd, int nv, int m, const double *Qd, const double *q
             }
             int32_t st, pv;
             qpo_avi_solve(m, G, h, lb, ub, z0, 0, lam2, &st, &pv, NULL);
+            if (fallback_pivots) *fallback_pivots = pv;
             if (st != QPO_SUCCESS) { *how = 5; ret = 0; }
             else {
                 double res2 = 0.0;

@@ -457,6 +457,7 @@ def solve_level_bottom(net, level, x_init, proj=None, max_iters=None):
         all_sol, lams = True, []
         for (Qd, qd, A, l, u, d) in views:
             sol, lam, how, act = cport.verify_solution(Qd, qd, A, l, u, d, x)
+            piv += cport.verify_solution.last_fallback_pivots      # the fused kernel counts these too
             lams.append(lam if sol else np.zeros(len(l)))
             all_sol &= sol
         if all_sol:

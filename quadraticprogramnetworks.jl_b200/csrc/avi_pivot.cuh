@@ -25,6 +25,37 @@ enum : int { ST_SUCCESS = 1, ST_RAY_TERM = 2, ST_MAX_ITERS = 3, ST_FAILURE = 4 }
 
 #define QPN_INF CUDART_INF
 
+// Debug build only (-DQPN_TRACE): barrier wrappers that verify that every warp of the CTA
+// arrived at the same source line with all 32 lanes active; mismatches are recorded in a
+// host-mapped buffer (4 ints per CTA), which stays readable after a device fault.
+#ifdef QPN_TRACE
+__device__ int* qpn_trace_ptr = nullptr;
+__device__ inline void qpn_dbg_record(int slot, int value) {
+    if (qpn_trace_ptr) ((volatile int*)qpn_trace_ptr)[blockIdx.x * 16 + slot] = value;
+}
+__device__ inline void qpn_dbg_presync(int line) {
+    __shared__ int dbg_line[32];
+    const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const unsigned am = __activemask();
+    if (am != 0xffffffffu) qpn_dbg_record(2, line * 100 + __popc(am));       // partial warp at a barrier
+    if ((threadIdx.x & 31) == 0) dbg_line[w] = line;
+    __syncthreads();
+    int other = 0;
+    for (int k = 0; k < nw; ++k) if (dbg_line[k] != line) other = dbg_line[k];
+    if (other && (threadIdx.x & 31) == 0 && qpn_trace_ptr && ((volatile int*)qpn_trace_ptr)[blockIdx.x * 16 + 3] == -1) {
+        qpn_dbg_record(3, w); qpn_dbg_record(0, line); qpn_dbg_record(1, other);      // first mismatch only
+    }
+    __syncthreads();
+}
+#define QPN_SYNC() do { qpn::qpn_dbg_presync(__LINE__); } while (0)
+#define QPN_SYNC_OR(x) (qpn::qpn_dbg_presync(__LINE__), __syncthreads_or(x))
+#define QPN_SITE(id, extra) do {} while (0)
+#else
+#define QPN_SYNC() __syncthreads()
+#define QPN_SYNC_OR(x) __syncthreads_or(x)
+#define QPN_SITE(id, extra) do {} while (0)
+#endif
+
 // Shared-memory workspace of one instance.  Sizes in elements for a problem of size n.
 struct Tab {
     int n;          // rows
@@ -88,9 +119,9 @@ __device__ inline void block_argmax(const Tab& t, double& v, int& idx) {
     const int nw = blockDim.x >> 5;
     if (nw > 1) {
         const int w = threadIdx.x >> 5;
-        __syncthreads();                        // red_* free for reuse
+        QPN_SYNC();                        // red_* free for reuse
         if ((threadIdx.x & 31) == 0) { t.red_d[w] = v; t.red_i[w] = idx; }
-        __syncthreads();
+        QPN_SYNC();
         v = t.red_d[0]; idx = t.red_i[0];
         for (int k = 1; k < nw; ++k) {
             double v2 = t.red_d[k]; int i2 = t.red_i[k];
@@ -107,9 +138,9 @@ __device__ inline double block_min(const Tab& t, double v) {
     const int nw = blockDim.x >> 5;
     if (nw > 1) {
         const int w = threadIdx.x >> 5;
-        __syncthreads();
+        QPN_SYNC();
         if ((threadIdx.x & 31) == 0) t.red_d[w] = v;
-        __syncthreads();
+        QPN_SYNC();
         v = t.red_d[0];
         for (int k = 1; k < nw; ++k) v = fmin(v, t.red_d[k]);
     }
@@ -144,7 +175,7 @@ __device__ inline void tab_start(Tab& t, const double* q, const double* z0) {
     const int n = t.n, i = threadIdx.x;
     double* zb = t.prow;
     if (i < n) zb[i] = fmin(fmax(z0[i], t.l[i]), t.u[i]);
-    __syncthreads();
+    QPN_SYNC();
     if (i < n) {
         double acc = 0.0;
         for (int j = 0; j < n; ++j) {
@@ -167,7 +198,7 @@ __device__ inline void tab_start(Tab& t, const double* q, const double* z0) {
         t.rowof[2 * n] = -1; t.colof[2 * n] = n;
     }
     t.pivots = 0;
-    __syncthreads();
+    QPN_SYNC();
 }
 
 // ---- rank-1 pivot on the compact tableau (avi_scratch.jl:2-7) --------------------------
@@ -178,7 +209,7 @@ __device__ inline void pivot(Tab& t, int rho, int c) {
     for (int j = i; j < nc; j += blockDim.x)
         t.prow[j] = (j == c) ? (1.0 / p) : T[(size_t)j * ld + rho] / p;
     const double d = (i < n) ? T[(size_t)c * ld + i] : 0.0;
-    __syncthreads();
+    QPN_SYNC();
     if (i < n) {
         if (i == rho) {
             for (int j = 0; j < nc; ++j) T[(size_t)j * ld + i] = t.prow[j];
@@ -200,7 +231,7 @@ __device__ inline void pivot(Tab& t, int rho, int c) {
         const double tmp = t.beta[rho]; t.beta[rho] = t.nbval[c]; t.nbval[c] = tmp;
     }
     t.pivots++;
-    __syncthreads();
+    QPN_SYNC();
 }
 
 __device__ inline int best_artificial_row(const Tab& t, int c) {
@@ -233,7 +264,7 @@ __device__ inline double ratio_test(const Tab& t, int c, double sigma, int& rho,
     }
     const double theta = block_min(t, r);
     rho = -1; which = 0;
-    if (theta == QPN_INF) return QPN_INF;
+    if (theta == QPN_INF) { QPN_SYNC(); return QPN_INF; }   // every exit ends with a barrier
     const double cut = theta + TIE_TOL * (1.0 + theta);
     // among ties: t first (so the path terminates), then largest |d|, then lowest row
     double key = -1.0; int idx = -1;
@@ -241,9 +272,9 @@ __device__ inline double ratio_test(const Tab& t, int c, double sigma, int& rho,
     block_argmax(t, key, idx);
     rho = idx;
     // the winner publishes its own ratio
-    if (blockDim.x > 32) __syncthreads();
+    if (blockDim.x > 32) QPN_SYNC();
     if (i == rho) t.red_d[32] = r;
-    __syncthreads();
+    QPN_SYNC();
     const double th = t.red_d[32];
     which = (sigma * t.T[(size_t)c * t.ld + rho] > 0.0) ? -1 : +1;
     return th;
@@ -257,7 +288,7 @@ __device__ inline void move(Tab& t, int c, double sigma, double theta) {
         if (ci != 0.0) t.beta[i] = fma(-(sigma * theta), ci, t.beta[i]);
     }
     if (i == 0) t.nbval[c] = fma(sigma, theta, t.nbval[c]);
-    __syncthreads();
+    QPN_SYNC();
 }
 
 __device__ inline void leave_at(Tab& t, int rho, int which) {
@@ -266,13 +297,13 @@ __device__ inline void leave_at(Tab& t, int rho, int which) {
         var_bounds(t, t.rowvar[rho], lo, up);
         t.beta[rho] = which < 0 ? lo : up;
     }
-    __syncthreads();
+    QPN_SYNC();
 }
 
 __device__ inline void set_zst(Tab& t, int k, int8_t s) {
-    __syncthreads();
+    QPN_SYNC();
     if (threadIdx.x == 0) t.zst[k] = s;
-    __syncthreads();
+    QPN_SYNC();
 }
 
 __device__ inline bool try_exchange(Tab& t, int var) {
@@ -293,10 +324,11 @@ __device__ inline void crash(Tab& t) {
         if (rho >= 0) { pivot(t, rho, c); set_zst(t, i, BASIC); continue; }
         // dependent column: walk towards an extreme point (Cao-Ferris stage 2)
         int rb[2], wb[2]; double th[2], own[2], step[2];
+        own[0] = t.u[i] - t.nbval[c];        // read before the ratio tests (see lemke)
+        own[1] = t.nbval[c] - t.l[i];
         for (int s = 0; s < 2; ++s) {
             const double sigma = s == 0 ? 1.0 : -1.0;
             th[s] = ratio_test(t, c, sigma, rb[s], wb[s]);
-            own[s] = s == 0 ? (t.u[i] - t.nbval[c]) : (t.nbval[c] - t.l[i]);
             step[s] = fmin(th[s], own[s]);
         }
         const int s = step[0] <= step[1] ? 0 : 1;
@@ -304,9 +336,9 @@ __device__ inline void crash(Tab& t) {
         if (step[s] == QPN_INF) continue;          // lineality direction: stays parked
         if (own[s] <= th[s]) {
             move(t, c, sigma, own[s]);
-            __syncthreads();
+            QPN_SYNC();
             if (threadIdx.x == 0) { t.nbval[c] = s == 0 ? t.u[i] : t.l[i]; t.zst[i] = s == 0 ? AT_U : AT_L; }
-            __syncthreads();
+            QPN_SYNC();
             continue;
         }
         move(t, c, sigma, th[s]);
@@ -332,7 +364,7 @@ __device__ inline void repair(Tab& t) {
         progress = false;
         int any = 0;
         if (threadIdx.x < n) any = artificial_row(t, threadIdx.x) ? 1 : 0;
-        any = __syncthreads_or(any);
+        any = QPN_SYNC_OR(any);
         if (!any) return;
         for (int k = 0; k < n; ++k) {
             const int8_t s = t.zst[k];
@@ -355,15 +387,17 @@ __device__ inline int lemke(Tab& t, int max_pivots) {
         if (t.pivots > max_pivots) return ST_MAX_ITERS;
         const int c = t.colof[ent];
         int rb, wb;
-        const double th = ratio_test(t, c, sigma, rb, wb);
+        // Read everything the branch below depends on BEFORE the ratio test: its barriers then
+        // separate these reads from the writes in move() (a read after it would race with them).
         const double own = ent == 2 * n ? 1.0 - t.nbval[c] : ent < n ? (t.u[ent] - t.l[ent]) : QPN_INF;
+        const double th = ratio_test(t, c, sigma, rb, wb);
         if (own == QPN_INF && th == QPN_INF) return ST_RAY_TERM;
         if (own <= th) {
             move(t, c, sigma, own);
-            __syncthreads();
-            if (ent == 2 * n) { if (threadIdx.x == 0) t.nbval[c] = 1.0; __syncthreads(); return ST_SUCCESS; }
+            QPN_SYNC();
+            if (ent == 2 * n) { if (threadIdx.x == 0) t.nbval[c] = 1.0; QPN_SYNC(); return ST_SUCCESS; }
             if (threadIdx.x == 0) { t.nbval[c] = sigma > 0 ? t.u[ent] : t.l[ent]; t.zst[ent] = sigma > 0 ? AT_U : AT_L; }
-            __syncthreads();
+            QPN_SYNC();
             ent = n + ent; sigma = -sigma;
             continue;
         }

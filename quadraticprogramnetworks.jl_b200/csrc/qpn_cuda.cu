@@ -27,6 +27,20 @@ struct qpn_handle {
 
 static std::string g_create_error;
 
+#ifdef QPN_TRACE
+// Debug build: qpn_trace_enable(h, batch) maps a pinned host buffer of 4 ints per CTA.
+static int* g_trace_host = nullptr;
+extern "C" int* qpn_trace_enable(qpn_handle* h, int batch) {
+    int* dptr = nullptr;
+    if (g_trace_host) cudaFreeHost(g_trace_host);
+    if (cudaHostAlloc((void**)&g_trace_host, sizeof(int) * 16 * (size_t)batch, cudaHostAllocMapped) != cudaSuccess) return nullptr;
+    for (size_t k = 0; k < 16 * (size_t)batch; ++k) g_trace_host[k] = -1;
+    cudaHostGetDevicePointer((void**)&dptr, g_trace_host, 0);
+    cudaMemcpyToSymbol(qpn::qpn_trace_ptr, &dptr, sizeof(dptr));
+    return g_trace_host;
+}
+#endif
+
 static int fail(qpn_handle* h, const char* fmt, ...) {
     char buf[512];
     va_list ap;

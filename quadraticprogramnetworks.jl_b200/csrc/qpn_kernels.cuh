@@ -25,7 +25,7 @@ __device__ inline void load_neg_matrix(Tab& t, const MatDesc& M, int b) {
         }
     } else {
         for (int e = threadIdx.x; e < n * ld; e += blockDim.x) t.T[e] = 0.0;
-        __syncthreads();
+        QPN_SYNC();
         const double* nz = M.nzval + (M.shared ? 0 : (size_t)b * M.nnz);
         for (int j = 0; j < n; ++j) {
             const int k0 = M.colptr[j] - M.base, k1 = M.colptr[j + 1] - M.base;
@@ -33,7 +33,7 @@ __device__ inline void load_neg_matrix(Tab& t, const MatDesc& M, int b) {
                 t.T[(size_t)j * ld + (M.rowval[k] - M.base)] = -nz[k];
         }
     }
-    __syncthreads();
+    QPN_SYNC();
 }
 
 // r_i = (M z)_i + q_i with T[:, 0:n] = -M and z in shared memory; sequential in j.
@@ -71,12 +71,12 @@ __global__ void avi_solve_kernel(int n, int ld, int batch, MatDesc M, const doub
     int st = avi_pivot_run(t, max_pivots, &zi, &code);
     const int piv = t.pivots;
     // final check (avi.jl:71-74) against the original matrix
-    __syncthreads();
+    QPN_SYNC();
     if (i < n) zs[i] = zi;
     load_neg_matrix(t, M, b);
     int bad = 0;
     if (i < n) bad = check_avi_index(residual_row(t, zs, qs[i], i), zi, t.l[i], t.u[i], 1e-6);
-    bad = __syncthreads_or(bad);
+    bad = QPN_SYNC_OR(bad);
     if (st == ST_SUCCESS && bad) st = ST_FAILURE;
     if (i < n) {
         z_out[(size_t)b * n + i] = zi;

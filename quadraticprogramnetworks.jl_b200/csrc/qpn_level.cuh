@@ -19,12 +19,12 @@ __device__ inline int solve_avi_smem(Tab& t, int n, Build build, const double* q
     int st = avi_pivot_run(t, max_pivots, &zi, &code);
     *pivots_acc += t.pivots;
     const int i = threadIdx.x;
-    __syncthreads();
+    QPN_SYNC();
     if (i < n) { zs[i] = zi; if (code_out) code_out[i] = code; }
     build(t);
     int bad = 0;
     if (i < n) bad = check_avi_index(residual_row(t, zs, qs[i], i), zi, t.l[i], t.u[i], 1e-6);
-    bad = __syncthreads_or(bad);
+    bad = QPN_SYNC_OR(bad);
     if (st == ST_SUCCESS && bad) st = ST_FAILURE;
     return st;
 }
@@ -81,7 +81,7 @@ __device__ inline void gavi_slack(GaviSmem& s, const GaviDesc& g, bool recompute
         for (int j = 0; j < dz; ++j) acc = fma(g.A[(size_t)j * g.d2 + r], s.z0[j], acc);
         s.s0[r] = acc + s.c[r];
     }
-    __syncthreads();
+    QPN_SYNC();
 }
 
 // solve_gavi (avi.jl:101-111) for the instance whose w and z0 are already in s.w / s.z0.
@@ -94,7 +94,7 @@ __device__ inline int gavi_solve_smem(GaviSmem& s, const GaviDesc& g, int presol
         int infeasible = 0;
         for (int r = i; r < d2; r += blockDim.x)
             if (!(g.l2[r] <= s.s0[r] && s.s0[r] <= g.u2[r])) infeasible = 1;
-        infeasible = __syncthreads_or(infeasible);
+        infeasible = QPN_SYNC_OR(infeasible);
         if (infeasible) {
             // find_closest_feasible! (avi.jl:79-99): min |z - z0|^2 s.t. l2 - Bw <= A z <= u2 - Bw over
             // the columns of A that are not structurally zero, as the lifted KKT AVI.
@@ -103,13 +103,13 @@ __device__ inline int gavi_solve_smem(GaviSmem& s, const GaviDesc& g, int presol
                 for (int r = 0; r < d2; ++r) nz |= (g.A[(size_t)j * d2 + r] != 0.0);
                 s.cols[j] = nz ? 1 : 0;
             }
-            __syncthreads();
+            QPN_SYNC();
             if (i == 0) {
                 int k = 0;
                 for (int j = 0; j < dz; ++j) if (s.cols[j]) s.cols[k++] = j;
                 s.cols[dz] = k;
             }
-            __syncthreads();
+            QPN_SYNC();
             const int k = s.cols[dz], pn = k + 2 * d2;
             if (i < pn) {
                 if (i < k) { s.qs[i] = -s.z0[s.cols[i]]; s.zs[i] = s.z0[s.cols[i]]; t.l[i] = -QPN_INF; t.u[i] = QPN_INF; }
@@ -125,11 +125,11 @@ __device__ inline int gavi_solve_smem(GaviSmem& s, const GaviDesc& g, int presol
                     s.qs[i] = 0.0; s.zs[i] = s.s0[r]; t.l[i] = g.l2[r]; t.u[i] = g.u2[r];
                 }
             }
-            __syncthreads();
+            QPN_SYNC();
             auto build = [&](Tab& tt) {
                 const int ld = tt.ld;
                 for (int e = threadIdx.x; e < pn * ld; e += blockDim.x) tt.T[e] = 0.0;
-                __syncthreads();
+                QPN_SYNC();
                 for (int e = threadIdx.x; e < k * d2; e += blockDim.x) {
                     const int a = e / d2, r = e - a * d2;
                     const double v = g.A[(size_t)s.cols[a] * d2 + r];
@@ -141,12 +141,12 @@ __device__ inline int gavi_solve_smem(GaviSmem& s, const GaviDesc& g, int presol
                     tt.T[(size_t)(k + d2 + e) * ld + (k + e)] = 1.0;     // -(-1)
                     tt.T[(size_t)(k + e) * ld + (k + d2 + e)] = -1.0;    // -(+1)
                 }
-                __syncthreads();
+                QPN_SYNC();
             };
             const int pst = solve_avi_smem(t, pn, build, s.qs, s.zs, 50 * pn + 100, nullptr, pivots);
-            __syncthreads();
+            QPN_SYNC();
             if (pst == ST_SUCCESS && i < k) s.z0[s.cols[i]] = s.zs[i];
-            __syncthreads();
+            QPN_SYNC();
             gavi_slack(s, g, false);
         }
     }
@@ -164,11 +164,11 @@ __device__ inline int gavi_solve_smem(GaviSmem& s, const GaviDesc& g, int presol
         }
         s.zs[i] = i < dz ? s.z0[i] : s.s0[i - dz];
     }
-    __syncthreads();
+    QPN_SYNC();
     auto build = [&](Tab& tt) {
         const int ld = tt.ld;
         for (int e = threadIdx.x; e < n * ld; e += blockDim.x) tt.T[e] = 0.0;
-        __syncthreads();
+        QPN_SYNC();
         for (int e = threadIdx.x; e < d1 * dz; e += blockDim.x) {
             const int j = e / d1, r = e - j * d1;
             tt.T[(size_t)j * ld + r] = -g.M[e];
@@ -181,7 +181,7 @@ __device__ inline int gavi_solve_smem(GaviSmem& s, const GaviDesc& g, int presol
             tt.T[(size_t)(dz + e) * ld + d1 + e] = 1.0;      // -(-I)
             tt.T[(size_t)(d1 + e) * ld + dz + e] = -1.0;     // -(+I)
         }
-        __syncthreads();
+        QPN_SYNC();
     };
     return solve_avi_smem(t, n, build, s.qs, s.zs, max_pivots, s.code, pivots);
 }
@@ -194,14 +194,18 @@ __global__ void gavi_solve_kernel(GaviDesc g, int ld, int batch, const double* _
     extern __shared__ __align__(16) unsigned char smem[];
     const int b = blockIdx.x, i = threadIdx.x;
     const int dz = g.d1 + g.d2, n = g.d1 + 2 * g.d2;
+#ifdef QPN_ZERO_SMEM
+    for (size_t e = i; e < gavi_smem_bytes(g.d1, g.d2, g.np) / 8; e += blockDim.x) reinterpret_cast<double*>(smem)[e] = 0.0;
+    QPN_SYNC();
+#endif
     GaviSmem s;
     gavi_carve(s, g, ld, smem);
     for (int j = i; j < g.np; j += blockDim.x) s.w[j] = w[(size_t)b * g.np + j];
     for (int j = i; j < dz; j += blockDim.x) s.z0[j] = z0[(size_t)b * dz + j];
-    __syncthreads();
+    QPN_SYNC();
     int piv = 0;
     const int st = gavi_solve_smem(s, g, presolve, max_pivots, &piv);
-    __syncthreads();
+    QPN_SYNC();
     if (i < dz) z_out[(size_t)b * dz + i] = s.zs[i];
     if (i < n) {
         if (zfull_out) zfull_out[(size_t)b * n + i] = s.zs[i];
@@ -264,7 +268,7 @@ __device__ inline void lstsq_basic_block(const Tab& red, int nd, int k, double* 
     const int j = threadIdx.x;
     const int steps = nd < k ? nd : k;
     for (int c = j; c < k; c += blockDim.x) perm[c] = c;
-    __syncthreads();
+    QPN_SYNC();
     int rank = 0;
     for (int c = 0; c < steps; ++c) {
         double best = -1.0; int jb = -1;
@@ -278,7 +282,7 @@ __device__ inline void lstsq_basic_block(const Tab& red, int nd, int k, double* 
         block_argmax(red, best, jb);
         const double nrm = sqrt(best);
         if (nrm <= 1e-10) break;
-        __syncthreads();
+        QPN_SYNC();
         if (jb != c) {
             for (int i = j; i < nd; i += blockDim.x) {
                 const double tmp = Ab[(size_t)c * nd + i];
@@ -287,10 +291,10 @@ __device__ inline void lstsq_basic_block(const Tab& red, int nd, int k, double* 
             }
             if (j == 0) { const int tp = perm[c]; perm[c] = perm[jb]; perm[jb] = tp; }
         }
-        __syncthreads();
+        QPN_SYNC();
         const double alpha = Ab[(size_t)c * nd + c] > 0.0 ? -nrm : nrm;
         for (int i = c + j; i < nd; i += blockDim.x) v[i] = Ab[(size_t)c * nd + i] - (i == c ? alpha : 0.0);
-        __syncthreads();
+        QPN_SYNC();
         double vn = 0.0;
         for (int i = c; i < nd; ++i) vn = fma(v[i], v[i], vn);
         if (vn > 0.0) {
@@ -304,9 +308,9 @@ __device__ inline void lstsq_basic_block(const Tab& red, int nd, int k, double* 
             }
         }
         rank++;
-        __syncthreads();
+        QPN_SYNC();
     }
-    __syncthreads();
+    QPN_SYNC();
     if (j == 0) {
         for (int t = 0; t < k; ++t) lam[t] = 0.0;
         for (int i = rank - 1; i >= 0; --i) {
@@ -316,7 +320,7 @@ __device__ inline void lstsq_basic_block(const Tab& red, int nd, int k, double* 
         }
         for (int i = 0; i < rank; ++i) lam[perm[i]] = v[i];
     }
-    __syncthreads();
+    QPN_SYNC();
 }
 
 // Returns 1 when x (shared memory, nv entries) is a solution for the node; lam in vs.lam_out.
@@ -341,7 +345,7 @@ __device__ inline int verify_solution_smem(Tab& tab, VerifySmem& vs, const NodeD
         const bool pos = acc < lo + 1e-2, neg = acc > up - 1e-2;
         vs.kind[r] = (pos && neg) ? 3 : pos ? 1 : neg ? 2 : 0;
     }
-    infeasible = __syncthreads_or(infeasible);
+    infeasible = QPN_SYNC_OR(infeasible);
     if (infeasible) { *how = 0; return 0; }
     double nq = 0.0;
     for (int r = 0; r < nd; ++r) nq = fma(vs.qt[r], vs.qt[r], nq);
@@ -355,7 +359,7 @@ __device__ inline int verify_solution_smem(Tab& tab, VerifySmem& vs, const NodeD
         tab.red_i[32] = k; tab.red_i[33] = np_; vs.perm[0] = 0;
         tab.red_d[33] = (double)nn;
     }
-    __syncthreads();
+    QPN_SYNC();
     const int k = tab.red_i[32], np_ = tab.red_i[33], nn = (int)tab.red_d[33];
     for (int e = i; e < nd * k; e += blockDim.x) {
         const int tcol = e / nd, r = e - tcol * nd;
@@ -364,7 +368,7 @@ __device__ inline int verify_solution_smem(Tab& tab, VerifySmem& vs, const NodeD
         vs.Ab[e] = val; vs.Ab0[e] = val;
     }
     for (int r = i; r < nd; r += blockDim.x) vs.b[r] = vs.qt[r];
-    __syncthreads();
+    QPN_SYNC();
     lstsq_basic_block(tab, nd, k, vs.Ab, vs.b, vs.lam, vs.perm, vs.v);
     // acceptance (qp_processing.jl:119)
     if (i == 0) {
@@ -380,17 +384,17 @@ __device__ inline int verify_solution_smem(Tab& tab, VerifySmem& vs, const NodeD
         if (!(sqrt(res) <= tol)) ok = 0;
         tab.red_i[32] = ok;
     }
-    __syncthreads();
+    QPN_SYNC();
     if (tab.red_i[32]) {
         for (int t = i; t < k; t += blockDim.x)
             vs.lam_out[vs.idx[t]] = (t >= np_ && t < np_ + nn) ? -vs.lam[t] : vs.lam[t];
-        __syncthreads();
+        QPN_SYNC();
         *how = 2;
         return 1;
     }
     // fallback (qp_processing.jl:129-146): sign-constrained least squares as the box AVI
     //   (Ad Ad') lam - Ad qt  comp.  lb <= lam <= ub
-    __syncthreads();
+    QPN_SYNC();
     for (int r = i; r < m; r += blockDim.x) {
         double acc = 0.0;
         for (int t = 0; t < nd; ++t) acc = fma(nd_.A[(size_t)nd_.dec[t] * m + r], vs.qt[t], acc);
@@ -400,7 +404,7 @@ __device__ inline int verify_solution_smem(Tab& tab, VerifySmem& vs, const NodeD
         tab.l[r] = (kd == 2 || kd == 3) ? -QPN_INF : 0.0;
         tab.u[r] = (kd == 1 || kd == 3) ? QPN_INF : 0.0;
     }
-    __syncthreads();
+    QPN_SYNC();
     auto build = [&](Tab& tt) {
         const int ld = tt.ld;
         for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
@@ -409,12 +413,12 @@ __device__ inline int verify_solution_smem(Tab& tab, VerifySmem& vs, const NodeD
             for (int t = 0; t < nd; ++t) acc = fma(nd_.A[(size_t)nd_.dec[t] * m + r], nd_.A[(size_t)nd_.dec[t] * m + c], acc);
             tt.T[(size_t)c * ld + r] = -acc;
         }
-        __syncthreads();
+        QPN_SYNC();
     };
     const int n_keep = tab.n;
     const int st = solve_avi_smem(tab, m, build, vs.qs, vs.zs, 50 * m + 100, nullptr, pivots);
     tab.n = n_keep;
-    __syncthreads();
+    QPN_SYNC();
     if (st != ST_SUCCESS) { *how = 5; return 0; }
     if (i == 0) {
         double res2 = 0.0;
@@ -427,7 +431,7 @@ __device__ inline int verify_solution_smem(Tab& tab, VerifySmem& vs, const NodeD
         tab.red_i[32] = sqrt(res2) <= 1e-4 ? 1 : 0;
     }
     for (int r = i; r < m; r += blockDim.x) vs.lam_out[r] = vs.zs[r];
-    __syncthreads();
+    QPN_SYNC();
     const int ok2 = tab.red_i[32];
     *how = ok2 ? 3 : 4;
     return ok2;
@@ -447,10 +451,10 @@ __global__ void verify_solution_kernel(NodeDesc node, int ld, int batch, const d
     verify_carve(vs, node.nd, m, p);
     double* xs = reinterpret_cast<double*>(p + verify_smem_bytes(node.nd, m));
     for (int j = i; j < node.nv; j += blockDim.x) xs[j] = x[(size_t)b * node.nv + j];
-    __syncthreads();
+    QPN_SYNC();
     int how = 0, piv = 0;
     const int sol = verify_solution_smem(tab, vs, node, xs, tol, &how, &piv);
-    __syncthreads();
+    QPN_SYNC();
     for (int r = i; r < m; r += blockDim.x) {
         if (lam_out) lam_out[(size_t)b * m + r] = vs.lam_out[r];
         if (active_out) active_out[(size_t)b * m + r] = how == 0 ? 0 : vs.kind[r];
@@ -496,7 +500,7 @@ __global__ void level_equilibrium_kernel(LevelDesc lv, int ld, int batch, const 
     double* pv = xs + nv;                  // nproj
     double* xn = pv + (lv.nproj > 0 ? lv.nproj : 1);
     for (int j = i; j < nv; j += blockDim.x) xs[j] = x_init[(size_t)b * nv + j];
-    __syncthreads();
+    QPN_SYNC();
     const int n_level = lv.g.d1 + 2 * lv.g.d2;
     const int max_piv = 50 * n_level + 100;
     int solved = 0, piv = 0, iters = 0;
@@ -513,7 +517,7 @@ __global__ void level_equilibrium_kernel(LevelDesc lv, int ld, int batch, const 
                 for (int j = 0; j < nv; ++j) acc = fma(xs[j], lv.proj[(size_t)k * nv + j], acc);
                 pv[k] = acc;
             }
-            __syncthreads();
+            QPN_SYNC();
             int cyc = 0;
             for (int h = i; h < nhist; h += blockDim.x) {
                 const double* ph = myhist + (size_t)h * lv.nproj;
@@ -525,13 +529,13 @@ __global__ void level_equilibrium_kernel(LevelDesc lv, int ld, int batch, const 
                 // isapprox with the default rtol = sqrt(eps)
                 if (sqrt(dd) <= 1.4901161193847656e-8 * fmax(sqrt(na), sqrt(nb2))) cyc = 1;
             }
-            cyc = __syncthreads_or(cyc);
+            cyc = QPN_SYNC_OR(cyc);
             if (cyc) break;
             if (nhist < hist_cap) {
                 for (int k = i; k < lv.nproj; k += blockDim.x) myhist[(size_t)nhist * lv.nproj + k] = pv[k];
                 nhist++;
             }
-            __syncthreads();
+            QPN_SYNC();
         }
         // process_qp for every player at the level (algorithm.jl:47-49)
         int all_sol = 1, lam_off = 0;
@@ -540,32 +544,32 @@ __global__ void level_equilibrium_kernel(LevelDesc lv, int ld, int batch, const 
             int how = 0;
             gs.t.n = n_level;
             const int sol = verify_solution_smem(gs.t, vs, node, xs, 1e-4, &how, &piv);
-            __syncthreads();
+            QPN_SYNC();
             if (lam_out)
                 for (int r = i; r < node.m; r += blockDim.x) lam_out[(size_t)b * lv.lam_total + lam_off + r] = sol ? vs.lam_out[r] : 0.0;
             lam_off += node.m;
             if (!sol) all_sol = 0;
-            __syncthreads();
+            QPN_SYNC();
         }
         if (all_sol) { solved = 1; break; }
         // solve_qep (avi.jl:382-444)
         for (int j = i; j < lv.g.np; j += blockDim.x) gs.w[j] = xs[lv.par[j]];
         for (int j = i; j < lv.g.d1 + lv.g.d2; j += blockDim.x) gs.z0[j] = j < lv.nd_level ? xs[lv.dec[j]] : 0.0;
-        __syncthreads();
+        QPN_SYNC();
         gs.t.n = n_level;
         const int st = gavi_solve_smem(gs, lv.g, presolve, max_piv, &piv);
-        __syncthreads();
+        QPN_SYNC();
         if (st != ST_SUCCESS) break;
         for (int j = i; j < nv; j += blockDim.x) xn[j] = xs[j];
-        __syncthreads();
+        QPN_SYNC();
         for (int j = i; j < lv.nd_level; j += blockDim.x) xn[lv.dec[j]] = gs.zs[j];
-        __syncthreads();
+        QPN_SYNC();
         double dn = 0.0;
         for (int j = 0; j < nv; ++j) { const double e = xn[j] - xs[j]; dn = fma(e, e, dn); }
         if (sqrt(dn) < 1e-4) break;        // algorithm.jl:96-97: disagreement -> solved = false
-        __syncthreads();
+        QPN_SYNC();
         for (int j = i; j < nv; j += blockDim.x) xs[j] = xn[j];
-        __syncthreads();
+        QPN_SYNC();
     }
     for (int j = i; j < nv; j += blockDim.x) x_out[(size_t)b * nv + j] = xs[j];
     if (i == 0) {

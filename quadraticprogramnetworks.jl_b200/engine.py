@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libqpn_cuda.so")
+LIB_PATH = os.environ.get("QPN_CUDA_LIB") or os.path.join(_HERE, "lib", "libqpn_cuda.so")   # override: debug builds only
 
 SUCCESS, RAY_TERM, MAX_ITERS, FAILURE = 1, 2, 3, 4
 
