@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""Benchmark of the QPNet equilibrium hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's engine
+    python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference path
+
+One "step" = one pass of the hot path over one batch: `solve(qpn, inits)` for the
+four-player Nash game (BASELINE.json configs[1]: examples/four_player_matrix_game.jl, 4,096
+random initialisations per GPU).  Metric: equilibria/sec (whole job, all GPUs).
+
+  value  device-timed (CUDA events on the launching stream), inputs already resident in HBM,
+         L2 flushed between steps;
+  e2e    the same work through the C-ABI call with pinned HOST buffers (H2D + kernel + D2H
+         inside the timed region);
+  roofline / cpu_baseline / clocks / gpu_launches as the bench contract asks.
+
+Multi-GPU: independent instances are sharded over the ranks (weak scaling, 4,096 per GPU);
+the only collective is the final NCCL all-gather of solutions / statuses / pivot counts.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "QPNet equilibria/sec (batched AVI solves)"
+UNIT = "equilibria/s"
+WORKLOAD = "four_player_matrix_game Nash (edge_list=[]), random inits ~ U(-5,5)^8, one fused level-equilibrium launch per batch"
+HBM_FALLBACK_GBS = 6650.0     # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def inits_for(rank, batch, step=0):
+    rng = np.random.default_rng([0xB200, rank, step])
+    return rng.uniform(-5.0, 5.0, (batch, 8))
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(gpu_index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_level(threads_hint=None):
+    """The CPU restatement of the path (oracle/), used ONLY as the reported baseline."""
+    from oracle import cport, examples as oex, qpn_ref
+    net = oex.four_player_matrix_game()
+    g, dec, par = qpn_ref.level_gavi(net, net.depth[1], {})
+    import qpn_b200
+    proj = qpn_b200.projection_vectors(qpn_b200.setup("four_player_matrix_game"))
+    return cport.Level(8, [qpn_ref.node_view(net, p) for p in net.depth[1]], g, dec, par, 150, proj)
+
+
+def cpu_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_baseline(sample_batches=16, batch=4096):
+    cores = cpu_cores()
+    L = oracle_level()
+    X = np.vstack([inits_for(10_000 + k, batch) for k in range(sample_batches)])
+    L.solve(X[:batch], threads=cores)                       # warm
+    t0 = time.perf_counter()
+    r = L.solve(X, threads=cores)
+    dt = time.perf_counter() - t0
+    assert r["solved"].all()
+    return {"value": len(X) / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{len(X)} four_player equilibria ({sample_batches} batches of {batch}), C oracle, {cores} pthreads, {dt:.2f} s wall"}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU path.  Julia / PATH / OSQP are absent from this
+    image, so the arm times the oracle port on all host cores."""
+    if rank != 0:
+        return
+    cores = cpu_cores()
+    L = oracle_level()
+    B = args.batch
+    for w in range(max(args.warmup, 1)):
+        L.solve(inits_for(0, B, 1000 + w), threads=cores)
+    times = []
+    for k in range(args.steps):
+        X = inits_for(0, B, k)
+        t0 = time.perf_counter()
+        r = L.solve(X, threads=cores)
+        times.append(time.perf_counter() - t0)
+        assert r["solved"].all()
+    total = sum(times)
+    val = B * args.steps / total
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_step": B,
+                       "note": "CPU arm: one step = one batch of 4096 instances on the host cores (rank 0 only)"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} steps x {B} equilibria, C oracle (oracle/qpn_oracle.c), {cores} pthreads"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="instances per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import qpn_b200
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    net = qpn_b200.setup("four_player_matrix_game")
+    solver = qpn_b200.BatchedSolver(net, device=local_rank)     # raises if libqpn_cuda / the GPU is missing
+    eng = solver.engine
+    level = solver.resident_level(1)
+    B, nv, K, W = args.batch, net.n_vars, args.steps, args.warmup
+    # An explicit stream: torch's default stream has handle 0, which the C ABI reads as "use the
+    # handle's own stream" -- the events below must sit on the stream the kernel is launched on.
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+
+    # ---- device-resident arm -------------------------------------------------------------------
+    x_in = [torch.from_numpy(inits_for(rank, B, k)).to(dev) for k in range(min(K, 8))]
+    x_out = torch.empty((B, nv), dtype=torch.float64, device=dev)
+    solved = torch.empty(B, dtype=torch.uint8, device=dev)
+    iters = torch.empty(B, dtype=torch.int32, device=dev)
+    pivots = torch.empty(B, dtype=torch.int32, device=dev)
+    if world > 1:
+        g_x = torch.empty((world * B, nv), dtype=torch.float64, device=dev)
+        g_solved = torch.empty(world * B, dtype=torch.uint8, device=dev)
+        g_piv = torch.empty(world * B, dtype=torch.int32, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def step_dev(k):
+        level.solve_dev(B, x_in[k % len(x_in)].data_ptr(), x_out.data_ptr(), solved.data_ptr(), iters.data_ptr(),
+                        pivots.data_ptr(), None, stream.cuda_stream)
+
+    def gather():
+        if world > 1:
+            dist.all_gather_into_tensor(g_x, x_out)
+            dist.all_gather_into_tensor(g_solved, solved)
+            dist.all_gather_into_tensor(g_piv, pivots)
+
+    for k in range(W):
+        step_dev(k); gather()
+    torch.cuda.synchronize()
+    assert bool(solved.bool().all()), "warm-up: not every instance reached an equilibrium"
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = eng.launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for k in range(K):
+        flush.zero_()                                   # evict the previous step's lines from L2 (not timed)
+        ev[k][0].record(stream)
+        step_dev(k)
+        ev[k][1].record(stream)
+        gather()
+        ev[k][2].record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = eng.launches - launches0
+    t_kernel = sum(a.elapsed_time(b) for a, b, _ in ev) * 1e-3
+    t_step = sum(a.elapsed_time(c) for a, _, c in ev) * 1e-3
+    piv_host = pivots.cpu().numpy()
+    all_solved = bool(solved.bool().all())
+
+    # ---- end-to-end arm: pinned host buffers through the C ABI ---------------------------------
+    hx = [torch.from_numpy(inits_for(rank, B, 100 + k)).pin_memory() for k in range(min(K, 8))]
+    out = dict(x=torch.empty((B, nv), dtype=torch.float64).pin_memory().numpy(),
+               solved=torch.empty(B, dtype=torch.uint8).pin_memory().numpy(),
+               iters=torch.empty(B, dtype=torch.int32).pin_memory().numpy(),
+               pivots=torch.empty(B, dtype=torch.int32).pin_memory().numpy(), lam=None)
+    hxn = [t.numpy() for t in hx]
+    for k in range(W):
+        level.solve(hxn[k % len(hxn)], out=out, want_lam=False)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_e2e = 0.0
+    for k in range(K):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        level.solve(hxn[k % len(hxn)], out=out, want_lam=False)        # H2D + kernel + D2H + sync
+        t_e2e += time.perf_counter() - t0
+        assert out["solved"].all()
+    clocks = sampler.stop() if sampler else None
+
+    if world > 1:
+        t = torch.tensor([t_kernel, t_step, t_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_kernel, t_step, t_e2e = (float(v) for v in t.cpu())
+        ok = torch.tensor([int(all_solved)], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        all_solved = bool(ok.item())
+
+    if rank == 0:
+        peak, peak_src = measured_hbm_peak()
+        # algorithmic HBM bytes of one launch: x in, x/solved/iters/pivots out, + the level's matrices once
+        alg_bytes = B * (8 * nv + 8 * nv + 1 + 4 + 4) + 8 * (32 * 32 + 3 * 32 + 4 * (2 * 8 + 2 + 2 * 8 + 4)) + 8 * 4 * nv
+        achieved = alg_bytes / (t_kernel / K) / 1e9
+        line = {
+            "metric": METRIC, "value": world * B * K / t_step, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": 1e3 * t_step / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "n_vars": nv, "avi_size": 32, "l2": "flushed between steps (256 MB write)",
+                       "timing": "CUDA events on the launching stream, max over ranks", "all_solved": all_solved,
+                       "p50_pivots_per_solve": float(np.median(piv_host)), "kernel_ms_per_step": 1e3 * t_kernel / K},
+            "e2e": {"value": world * B * K / t_e2e, "unit": UNIT, "h2d_bytes_per_step": B * nv * 8, "d2h_bytes_per_step": B * (nv * 8 + 1 + 4 + 4),
+                    "timing": "host clock around the synchronous C-ABI call (qpn_level_equilibrium_resident), pinned buffers"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "level_equilibrium_kernel", "peak_source": peak_src,
+                         "note": "the fused pivoting kernel is issue/latency bound in shared memory, not HBM bound; see DESIGN.md"},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line), flush=True)
+    solver.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -193,6 +193,24 @@ int qpn_level_equilibrium_batched_dev(qpn_handle *h, const qpn_level *lv, int ba
                                       int32_t *iters_out, int32_t *pivots_out, double *lam_out,
                                       void *stream);
 
+/*
+ * Resident form: upload a level's problem data (players, GAVI blocks, index maps,
+ * projection vectors) once -- SURVEY.md 8e: "problem matrices broadcast once" -- and run
+ * batches against it.  `qpn_level_equilibrium_resident` takes HOST x_init / outputs and
+ * copies only those; `_resident_dev` takes DEVICE x_init / outputs and is asynchronous on
+ * `stream` (0 = the handle's stream).  lam_out may be NULL.
+ */
+typedef struct qpn_level_dev qpn_level_dev;
+int qpn_level_upload(qpn_handle *h, const qpn_level *lv, qpn_level_dev **out);
+int qpn_level_release(qpn_handle *h, qpn_level_dev *lvd);
+int qpn_level_equilibrium_resident(qpn_handle *h, qpn_level_dev *lvd, int batch, const double *x_init,
+                                   double *x_out, uint8_t *solved_out, int32_t *iters_out,
+                                   int32_t *pivots_out, double *lam_out);
+int qpn_level_equilibrium_resident_dev(qpn_handle *h, qpn_level_dev *lvd, int batch,
+                                       const double *x_init, double *x_out, uint8_t *solved_out,
+                                       int32_t *iters_out, int32_t *pivots_out, double *lam_out,
+                                       void *stream);
+
 /* Device buffers owned by the handle (for callers without their own allocator). */
 int qpn_malloc(qpn_handle *h, size_t bytes, void **dptr);
 int qpn_free(qpn_handle *h, void *dptr);

@@ -142,3 +142,47 @@ def verify_solution(Qd, qd, A, l, u, dec, x, tol=1e-4):
                                 C.c_double(tol), _p(lam), _p(how, ip), _p(act, bp), _p(fpiv, ip))
     verify_solution.last_fallback_pivots = int(fpiv[0])
     return bool(sol), lam[:m], int(how[0]), act[:m]
+
+
+class _Node(C.Structure):
+    _fields_ = [("nd", C.c_int32), ("nv", C.c_int32), ("m", C.c_int32),
+                ("Qd", dp), ("qd", dp), ("A", dp), ("l", dp), ("u", dp), ("dec", ip)]
+
+
+class _Gavi(C.Structure):
+    _fields_ = [("d1", C.c_int32), ("d2", C.c_int32), ("np", C.c_int32),
+                ("M", dp), ("N", dp), ("o", dp), ("l1", dp), ("u1", dp), ("A", dp), ("B", dp), ("l2", dp), ("u2", dp)]
+
+
+class Level:
+    """Column-major copies of a level's data for qpo_level_solve_batched."""
+
+    def __init__(self, nv, views, g, dec, par, max_iters=150, proj=None):
+        self.keep = []
+        nodes = []
+        for (Qd, qd, A, l, u, d) in views:
+            Qd = _f(np.atleast_2d(Qd)); A = _f(np.asarray(A, dtype=np.float64).reshape(-1, nv))
+            arrs = [Qd, _f(qd), A, _f(l), _f(u), np.ascontiguousarray(d, dtype=np.int32)]
+            self.keep.append(arrs)
+            nodes.append(_Node(Qd.shape[0], nv, A.shape[0], _p(arrs[0]), _p(arrs[1]), _p(arrs[2]), _p(arrs[3]), _p(arrs[4]), _p(arrs[5], ip)))
+        self.nodes = (_Node * len(nodes))(*nodes)
+        ga = [_f(g[k]) for k in ("M", "N", "o", "l1", "u1", "A", "B", "l2", "u2")]
+        self.keep.append(ga)
+        self.g = _Gavi(len(g["l1"]), len(g["l2"]), g["N"].shape[1], *[_p(a) for a in ga])
+        self.dec = np.ascontiguousarray(dec, dtype=np.int32)
+        self.par = np.ascontiguousarray(par, dtype=np.int32)
+        self.proj = None if proj is None or len(proj) == 0 else np.ascontiguousarray(proj, dtype=np.float64)
+        self.nv, self.max_iters = nv, max_iters
+        self.lam_total = sum(n.m for n in nodes)
+
+    def solve(self, x_init, threads=1):
+        L = lib()
+        x_init = np.ascontiguousarray(x_init, dtype=np.float64)
+        B = x_init.shape[0]
+        x = np.zeros((B, self.nv)); solved = np.zeros(B, np.uint8); iters = np.zeros(B, np.int32); piv = np.zeros(B, np.int32)
+        lam = np.zeros((B, max(self.lam_total, 1)))
+        nproj = 0 if self.proj is None else self.proj.shape[0]
+        L.qpo_level_solve_batched(self.nv, len(self.nodes), self.nodes, C.byref(self.g), _p(self.dec, ip), len(self.dec),
+                                  _p(self.par, ip), int(self.max_iters), nproj, _p(self.proj) if nproj else None, B,
+                                  _p(x_init), _p(x), _p(solved, ubp), _p(iters, ip), _p(piv, ip), _p(lam), int(threads))
+        return dict(x=x, solved=solved.astype(bool), iters=iters, pivots=piv, lam=lam[:, :self.lam_total])

@@ -702,3 +702,116 @@ done:
     free(qt); free(ax);
     return ret;
 }
+
+/* ---- algorithm.jl:13-118 for a level without children --------------------------------- */
+typedef struct { int32_t nd, nv, m; const double *Qd, *qd, *A, *l, *u; const int32_t *dec; } qpo_node;
+typedef struct { int32_t d1, d2, np; const double *M, *N, *o, *l1, *u1, *A, *B, *l2, *u2; } qpo_gavi;
+
+/* proj: nv x nproj (column k = projection vector k).  lam_out (optional): sum(m_p).
+ * pivots counts the AVI pivots of solve_qep, of its presolve and of verify_solution's
+ * fallback.  Returns 0. */
+int qpo_level_solve(int nv, int nplayers, const qpo_node *players, const qpo_gavi *g, const int32_t *dec,
+                    int nd_level, const int32_t *par, int max_iters, int nproj, const double *proj,
+                    const double *x_init, double *x_out, uint8_t *solved_out, int32_t *iters_out,
+                    int32_t *pivots_out, double *lam_out) {
+    int dz = g->d1 + g->d2, lam_total = 0, max_m = 1;
+    for (int p = 0; p < nplayers; ++p) { lam_total += players[p].m; if (players[p].m > max_m) max_m = players[p].m; }
+    double *x = (double *)malloc(sizeof(double) * (size_t)(nv + 1));
+    double *xn = (double *)malloc(sizeof(double) * (size_t)(nv + 1));
+    double *w = (double *)malloc(sizeof(double) * (size_t)(g->np + 1));
+    double *z0 = (double *)malloc(sizeof(double) * (size_t)(dz + 1));
+    double *z = (double *)malloc(sizeof(double) * (size_t)(dz + 1));
+    double *lam = (double *)malloc(sizeof(double) * (size_t)(max_m + 1));
+    double *hist = (double *)malloc(sizeof(double) * ((size_t)max_iters * (nproj > 0 ? nproj : 1) + 1));
+    double *pv = (double *)malloc(sizeof(double) * (size_t)(nproj + 1));
+    memcpy(x, x_init, sizeof(double) * (size_t)nv);
+    int solved = 0, piv = 0, it = 0, nhist = 0;
+    for (it = 1; it <= max_iters; ++it) {
+        if (nproj > 0) {
+            int cyc = 0;
+            for (int k = 0; k < nproj; ++k) {
+                double acc = 0.0;
+                for (int j = 0; j < nv; ++j) acc = fma(x[j], proj[(size_t)k * nv + j], acc);
+                pv[k] = acc;
+            }
+            for (int h = 0; h < nhist && !cyc; ++h) {
+                double dd = 0.0, na = 0.0, nb = 0.0;
+                for (int k = 0; k < nproj; ++k) {
+                    double e = pv[k] - hist[(size_t)h * nproj + k];
+                    dd = fma(e, e, dd); na = fma(pv[k], pv[k], na);
+                    nb = fma(hist[(size_t)h * nproj + k], hist[(size_t)h * nproj + k], nb);
+                }
+                if (sqrt(dd) <= 1.4901161193847656e-8 * fmax(sqrt(na), sqrt(nb))) cyc = 1;   /* isapprox, rtol = sqrt(eps) */
+            }
+            if (cyc) break;
+            memcpy(hist + (size_t)nhist * nproj, pv, sizeof(double) * (size_t)nproj);
+            nhist++;
+        }
+        int all_sol = 1, off = 0;
+        for (int p = 0; p < nplayers; ++p) {
+            const qpo_node *nd = &players[p];
+            int32_t how, fpiv;
+            int sol = qpo_verify_solution(nd->nd, nd->nv, nd->m, nd->Qd, nd->qd, nd->A, nd->l, nd->u, nd->dec, x, 1e-4,
+                                          lam, &how, NULL, &fpiv);
+            piv += fpiv;
+            if (lam_out) for (int r = 0; r < nd->m; ++r) lam_out[off + r] = sol ? lam[r] : 0.0;
+            off += nd->m;
+            if (!sol) all_sol = 0;
+        }
+        if (all_sol) { solved = 1; break; }
+        for (int j = 0; j < g->np; ++j) w[j] = x[par[j]];
+        for (int j = 0; j < dz; ++j) z0[j] = j < nd_level ? x[dec[j]] : 0.0;
+        int32_t st, gp;
+        qpo_gavi_solve(g->d1, g->d2, g->np, g->M, g->N, g->o, g->l1, g->u1, g->A, g->B, g->l2, g->u2, w, z0, 1, 0, z,
+                       NULL, &st, &gp, NULL);
+        piv += gp;
+        if (st != QPO_SUCCESS) break;
+        memcpy(xn, x, sizeof(double) * (size_t)nv);
+        for (int j = 0; j < nd_level; ++j) xn[dec[j]] = z[j];
+        double dn = 0.0;
+        for (int j = 0; j < nv; ++j) { double e = xn[j] - x[j]; dn = fma(e, e, dn); }
+        if (sqrt(dn) < 1e-4) break;
+        memcpy(x, xn, sizeof(double) * (size_t)nv);
+    }
+    if (it > max_iters) it = max_iters;
+    memcpy(x_out, x, sizeof(double) * (size_t)nv);
+    *solved_out = (uint8_t)solved; *iters_out = it; *pivots_out = piv;
+    free(x); free(xn); free(w); free(z0); free(z); free(lam); free(hist); free(pv);
+    return 0;
+}
+
+typedef struct {
+    int nv, nplayers, nd_level, max_iters, nproj, batch, tid, nthreads, lam_total;
+    const qpo_node *players; const qpo_gavi *g; const int32_t *dec, *par; const double *proj, *x_init;
+    double *x_out; uint8_t *solved; int32_t *iters, *pivots; double *lam;
+} level_job_t;
+
+static void *level_worker(void *arg) {
+    level_job_t *j = (level_job_t *)arg;
+    for (int b = j->tid; b < j->batch; b += j->nthreads)
+        qpo_level_solve(j->nv, j->nplayers, j->players, j->g, j->dec, j->nd_level, j->par, j->max_iters, j->nproj, j->proj,
+                        j->x_init + (size_t)b * j->nv, j->x_out + (size_t)b * j->nv, j->solved + b, j->iters + b,
+                        j->pivots + b, j->lam ? j->lam + (size_t)b * j->lam_total : NULL);
+    return NULL;
+}
+
+int qpo_level_solve_batched(int nv, int nplayers, const qpo_node *players, const qpo_gavi *g, const int32_t *dec,
+                            int nd_level, const int32_t *par, int max_iters, int nproj, const double *proj, int batch,
+                            const double *x_init, double *x_out, uint8_t *solved_out, int32_t *iters_out,
+                            int32_t *pivots_out, double *lam_out, int threads) {
+    if (threads < 1) threads = 1;
+    if (threads > 256) threads = 256;
+    int lam_total = 0;
+    for (int p = 0; p < nplayers; ++p) lam_total += players[p].m;
+    level_job_t jobs[256];
+    pthread_t th[256];
+    for (int t = 0; t < threads; ++t) {
+        level_job_t j = {nv, nplayers, nd_level, max_iters, nproj, batch, t, threads, lam_total, players, g, dec, par, proj,
+                         x_init, x_out, solved_out, iters_out, pivots_out, lam_out};
+        jobs[t] = j;
+    }
+    for (int t = 1; t < threads; ++t) pthread_create(&th[t], NULL, level_worker, &jobs[t]);
+    level_worker(&jobs[0]);
+    for (int t = 1; t < threads; ++t) pthread_join(th[t], NULL);
+    return 0;
+}

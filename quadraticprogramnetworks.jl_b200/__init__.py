@@ -5,4 +5,8 @@ Host-side mirror of the reference's API for the numeric hot path
 libqpn_cuda through its C ABI (include/qpn_cuda.h).  Import as `qpn_b200` (the shim
 at the repo root) -- the directory name carries a dot and is not importable directly.
 """
-from .engine import Engine, EngineError, GaviArrays, NodeArrays, LevelArrays, load_library, LIB_PATH  # noqa: F401
+from .engine import Engine, EngineError, GaviArrays, NodeArrays, LevelArrays, ResidentLevel, load_library, LIB_PATH  # noqa: F401
+from .model import QPNet, QP, Poly, Aff, Quad, QPNetOptions, sumsq, dot, matvec, INF  # noqa: F401,E402
+from .examples import setup  # noqa: F401,E402
+from .algorithm import solve, BatchedSolver, projection_vectors  # noqa: F401,E402
+from . import assembly, examples, model, algorithm, engine  # noqa: F401,E402

@@ -79,6 +79,7 @@ EXPORTS = [
     "qpn_gavi_solve_batched", "qpn_gavi_solve_batched_dev", "qpn_comp_indices_batched",
     "qpn_halfspace_in_batched", "qpn_verify_solution_batched",
     "qpn_level_equilibrium_batched", "qpn_level_equilibrium_batched_dev",
+    "qpn_level_upload", "qpn_level_release", "qpn_level_equilibrium_resident", "qpn_level_equilibrium_resident_dev",
     "qpn_malloc", "qpn_free", "qpn_memcpy_h2d", "qpn_memcpy_d2h",
 ]
 
@@ -258,6 +259,42 @@ class Engine:
         self._ck(self.lib.qpn_level_equilibrium_batched(self.h, C.byref(level.struct), B, _p(x_init), _p(x), _p(solved, ubp),
                                                         _p(iters, ip), _p(piv, ip), _p(lam)))
         return dict(x=x, solved=solved.astype(bool), iters=iters, pivots=piv, lam=lam)
+
+
+class ResidentLevel:
+    """A level whose problem data lives on the GPU (qpn_level_upload).  Batches then move only
+    x_init in and the results out -- or nothing at all with the `_dev` form."""
+
+    def __init__(self, engine, level):
+        self.engine, self.level = engine, level
+        self.lam_total, self.nv = level.lam_total, level.struct.nv
+        ptr = C.c_void_p()
+        engine._ck(engine.lib.qpn_level_upload(engine.h, C.byref(level.struct), C.byref(ptr)))
+        self.ptr = ptr
+
+    def release(self):
+        if getattr(self, "ptr", None):
+            self.engine.lib.qpn_level_release(self.engine.h, self.ptr)
+            self.ptr = None
+
+    def solve(self, x_init, out=None, want_lam=True):
+        """Host buffers (numpy, ideally pinned): copies x_init in, results out, synchronises."""
+        e = self.engine
+        x_init = _c(x_init)
+        B = x_init.shape[0]
+        if out is None:
+            out = dict(x=np.empty((B, self.nv)), solved=np.empty(B, np.uint8), iters=np.empty(B, np.int32),
+                       pivots=np.empty(B, np.int32), lam=np.empty((B, self.lam_total)) if want_lam else None)
+        e._ck(e.lib.qpn_level_equilibrium_resident(e.h, self.ptr, B, _p(x_init), _p(out["x"]), _p(out["solved"], ubp),
+                                                   _p(out["iters"], ip), _p(out["pivots"], ip), _p(out.get("lam"))))
+        return out
+
+    def solve_dev(self, batch, x_init_ptr, x_out_ptr, solved_ptr, iters_ptr, pivots_ptr, lam_ptr=None, stream=0):
+        """Device pointers (e.g. torch tensors' data_ptr()); asynchronous on `stream`."""
+        e = self.engine
+        vp = lambda p: C.c_void_p(int(p)) if p else None
+        e._ck(e.lib.qpn_level_equilibrium_resident_dev(e.h, self.ptr, int(batch), vp(x_init_ptr), vp(x_out_ptr), vp(solved_ptr),
+                                                       vp(iters_ptr), vp(pivots_ptr), vp(lam_ptr), vp(stream)))
 
 
 class LevelArrays:
