@@ -9,4 +9,4 @@ from .engine import Engine, EngineError, GaviArrays, NodeArrays, LevelArrays, Re
 from .model import QPNet, QP, Poly, Aff, Quad, QPNetOptions, sumsq, dot, matvec, INF  # noqa: F401,E402
 from .examples import setup  # noqa: F401,E402
 from .algorithm import solve, BatchedSolver, projection_vectors  # noqa: F401,E402
-from . import assembly, examples, model, algorithm, engine  # noqa: F401,E402
+from . import assembly, examples, model, algorithm, engine, sharding  # noqa: F401,E402

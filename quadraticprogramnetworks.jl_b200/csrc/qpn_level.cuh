@@ -8,7 +8,7 @@ namespace qpn {
 // Solve (M z + q) comp. l <= z <= u in the shared-memory tableau.  `build(t)` must fill
 // T[:, 0:n] with -M and end with a barrier; it is called twice (start and final check).
 // t.l / t.u hold the bounds, qs the vector q, zs the start on entry and z on exit.
-// code (optional, smem, n entries) receives the basis codes.  Mirrors qpo_avi_solve.
+// code (optional, smem, n entries) receives the basis codes.  Same procedure as the oracle's single-instance solve.
 template <class Build>
 __device__ inline int solve_avi_smem(Tab& t, int n, Build build, const double* qs, double* zs,
                                      int max_pivots, int8_t* code_out, int* pivots_acc) {
