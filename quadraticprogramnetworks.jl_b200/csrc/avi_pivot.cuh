@@ -6,9 +6,18 @@
 // (/root/reference/src/avi.jl:63-77); the pivotal method is the one sketched in
 // /root/reference/src/deprecated/avi_scratch.jl:2-134 (normal-map start :17-50, ratio
 // test :65-77, rank-1 pivot :2-7, complementary entering rule :105-131) completed with a
-// crash / extreme-point phase.  The arithmetic is, operation for operation, the one
-// oracle/qpn_oracle.c performs (explicit fma, sequential dot products), so discrete
-// outputs (basis, status, pivot counts) and z agree bit for bit.
+// crash / extreme-point phase.  The arithmetic is, operation for operation, the one the
+// CPU oracle's specification prescribes (explicit fma, sequential dot products), so
+// discrete outputs (basis, status, pivot counts) and z agree bit for bit with it.
+//
+// Layout: T is ROW-major with row stride ldr = 2*odd doubles.  Thread i owns row i and
+// walks it with 128-bit shared-memory accesses (two columns per LDS/STS, conflict-free
+// across the warp); the scaled pivot row is broadcast from shared memory.  Columns of
+// slack variables that can never re-enter (w_k of a free z_k) are swapped out of the live
+// range [0, ncol) as soon as they appear, so later pivots touch fewer columns.
+//
+// Synchronisation rule: a value that steers control flow is read from
+// shared memory BEFORE the last barrier that precedes any write to it.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -26,8 +35,8 @@ enum : int { ST_SUCCESS = 1, ST_RAY_TERM = 2, ST_MAX_ITERS = 3, ST_FAILURE = 4 }
 #define QPN_INF CUDART_INF
 
 // Debug build only (-DQPN_TRACE): barrier wrappers that verify that every warp of the CTA
-// arrived at the same source line with all 32 lanes active; mismatches are recorded in a
-// host-mapped buffer (4 ints per CTA), which stays readable after a device fault.
+// arrived at the same source line with all 32 lanes active; the first mismatch of a CTA is
+// recorded in a host-mapped buffer (16 ints per CTA), readable after a device fault.
 #ifdef QPN_TRACE
 __device__ int* qpn_trace_ptr = nullptr;
 __device__ inline void qpn_dbg_record(int slot, int value) {
@@ -49,103 +58,153 @@ __device__ inline void qpn_dbg_presync(int line) {
 }
 #define QPN_SYNC() do { qpn::qpn_dbg_presync(__LINE__); } while (0)
 #define QPN_SYNC_OR(x) (qpn::qpn_dbg_presync(__LINE__), __syncthreads_or(x))
-#define QPN_SITE(id, extra) do {} while (0)
 #else
 #define QPN_SYNC() __syncthreads()
 #define QPN_SYNC_OR(x) __syncthreads_or(x)
-#define QPN_SITE(id, extra) do {} while (0)
 #endif
 
-// Shared-memory workspace of one instance.  Sizes in elements for a problem of size n.
+// Row stride for `cols` columns: even (rows stay 16-byte aligned) with ldr/2 odd, so that the
+// 32 lanes of a warp, each reading 16 bytes of its own row, fall into distinct bank groups.
+__host__ __device__ inline int row_stride(int cols) {
+    int e = (cols + 1) & ~1;
+    if ((e >> 1) % 2 == 0) e += 2;
+    return e;
+}
+
+// Shared-memory workspace of one instance (sized for n rows and cap >= n+1 columns).
 struct Tab {
     int n;          // rows
-    int ld;         // leading dimension of T (>= n)
-    double* T;      // ld x (n+1), column-major: column j = d(basic)/d(nonbasic j), negated
-    double* beta;   // n   values of the basic variables
-    double* nbval;  // n+1 values of the nonbasic variables
-    double* prow;   // n+1 scaled pivot row
+    int ldr;        // row stride of T in doubles
+    int ncol;       // live columns [0, ncol); uniform across the CTA
+    int pivots;     // uniform across the CTA
+    double* T;      // n x ldr, row-major: T[i][j] = d(basic_i)/d(nonbasic_j), negated
+    double* beta;   // n     values of the basic variables
+    double* nbval;  // ldr   values of the nonbasic variables
+    double* prow;   // ldr   scaled pivot row
     double* l;      // n
     double* u;      // n
-    int* rowvar;    // n     variable basic in row i      (z_i = i, w_i = n+i, t = 2n)
-    int* colvar;    // n+1   variable nonbasic in column j
-    int* rowof;     // 2n+1  row of a variable or -1
-    int* colof;     // 2n+1  column of a variable or -1
-    int8_t* zst;    // n     AT_L / AT_U / FLOATING / BASIC
-    double* red_d;  // 32 + 2
-    int* red_i;     // 32 + 2
-    int pivots;     // uniform across the CTA
+    int* rowvar;    // n      variable basic in row i      (z_i = i, w_i = n+i, t = 2n)
+    int* colvar;    // ldr    variable nonbasic in column j
+    int* rowof;     // 2n+1   row of a variable or -1
+    int* colof;     // 2n+1   column of a variable or -1 (also -1 once its column is dead)
+    int8_t* zst;    // n      AT_L / AT_U / FLOATING / BASIC
+    double* red_d;  // 36: per-warp partials [0,32) + broadcast slots
+    int* red_i;     // 36
 };
 
-__host__ __device__ inline size_t tab_smem_bytes(int n, int ld) {
-    size_t d = (size_t)ld * (n + 1) + (size_t)n /*beta*/ + 2 * (size_t)(n + 1) /*nbval,prow*/ +
-               2 * (size_t)n /*l,u*/ + 34 /*red_d*/;
-    size_t i = (size_t)n + (n + 1) + 2 * (size_t)(2 * n + 1) + 34;
+__host__ __device__ inline size_t tab_smem_bytes(int n, int cap) {
+    const size_t ldr = (size_t)row_stride(cap);
+    size_t d = (size_t)n * ldr + (size_t)n + 2 * ldr + 2 * (size_t)n + 36;
+    size_t i = (size_t)n + ldr + 2 * (size_t)(2 * n + 1) + 36;
     size_t b = (size_t)n;
-    return d * 8 + ((i * 4 + 7) / 8) * 8 + ((b + 7) / 8) * 8;
+    return d * 8 + ((i * 4 + 15) / 16) * 16 + ((b + 15) / 16) * 16;
 }
 
-__device__ inline void tab_carve(Tab& t, int n, int ld, unsigned char* smem) {
-    t.n = n; t.ld = ld;
+__device__ inline void tab_carve(Tab& t, int n, int cap, unsigned char* smem) {
+    const int ldr = row_stride(cap);
+    t.n = n; t.ldr = ldr; t.ncol = 0; t.pivots = 0;
     double* d = reinterpret_cast<double*>(smem);
-    t.T = d;      d += (size_t)ld * (n + 1);
+    t.T = d;      d += (size_t)n * ldr;
+    t.prow = d;   d += ldr;                 // 16-byte aligned: n*ldr is even
+    t.nbval = d;  d += ldr;
     t.beta = d;   d += n;
-    t.nbval = d;  d += n + 1;
-    t.prow = d;   d += n + 1;
     t.l = d;      d += n;
     t.u = d;      d += n;
-    t.red_d = d;  d += 34;
+    t.red_d = d;  d += 36;
     int* ip = reinterpret_cast<int*>(d);
     t.rowvar = ip; ip += n;
-    t.colvar = ip; ip += n + 1;
+    t.colvar = ip; ip += ldr;
     t.rowof = ip;  ip += 2 * n + 1;
     t.colof = ip;  ip += 2 * n + 1;
-    t.red_i = ip;  ip += 34;
-    size_t ib = (size_t)(ip - reinterpret_cast<int*>(d));
-    t.zst = reinterpret_cast<int8_t*>(reinterpret_cast<unsigned char*>(d) + ((ib * 4 + 7) / 8) * 8);
-    t.pivots = 0;
+    t.red_i = ip;  ip += 36;
+    const size_t ib = (size_t)(ip - reinterpret_cast<int*>(d));
+    t.zst = reinterpret_cast<int8_t*>(reinterpret_cast<unsigned char*>(d) + ((ib * 4 + 15) / 16) * 16);
 }
 
-// ---- block-wide arg-best: larger value wins, ties -> lower index --------------------
-// Every thread receives the winner.  idx < 0 marks "no candidate" and loses to anything.
-__device__ inline void block_argmax(const Tab& t, double& v, int& idx) {
+// ---- block-wide reductions on non-negative doubles (+inf allowed, no NaN) ---------------------
+// The IEEE bit pattern of a non-negative double orders like an unsigned integer, so a 64-bit
+// max / min is two 32-bit REDUX instructions instead of a five-round shuffle butterfly.
+__device__ inline void warp_max_bits(unsigned& hi, unsigned& lo) {
     const unsigned full = 0xffffffffu;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        double v2 = __shfl_xor_sync(full, v, o);
-        int i2 = __shfl_xor_sync(full, idx, o);
-        bool take = (i2 >= 0) && (idx < 0 || v2 > v || (v2 == v && i2 < idx));
-        if (take) { v = v2; idx = i2; }
-    }
+    const unsigned mh = __reduce_max_sync(full, hi);
+    const unsigned ml = __reduce_max_sync(full, hi == mh ? lo : 0u);
+    hi = mh; lo = ml;
+}
+__device__ inline void warp_min_bits(unsigned& hi, unsigned& lo) {
+    const unsigned full = 0xffffffffu;
+    const unsigned mh = __reduce_min_sync(full, hi);
+    const unsigned ml = __reduce_min_sync(full, hi == mh ? lo : 0xffffffffu);
+    hi = mh; lo = ml;
+}
+
+// arg-max over the rows: larger value wins, ties -> lower row.  `valid` lanes carry v >= 0.
+// Every thread receives (v, idx); idx = -1 when no lane is valid.
+__device__ inline void block_argmax(const Tab& t, bool valid, double& v, int& idx) {
+    const unsigned full = 0xffffffffu;
+    unsigned hi = valid ? (unsigned)__double2hiint(v) : 0u, lo = valid ? (unsigned)__double2loint(v) : 0u;
+    const unsigned mine_hi = hi, mine_lo = lo;
+    warp_max_bits(hi, lo);
+    const unsigned ball = __ballot_sync(full, valid && mine_hi == hi && mine_lo == lo);
+    int widx = ball ? (int)(threadIdx.x & ~31u) + (__ffs(ball) - 1) : -1;
+    double wv = __hiloint2double((int)hi, (int)lo);
     const int nw = blockDim.x >> 5;
     if (nw > 1) {
         const int w = threadIdx.x >> 5;
         QPN_SYNC();                        // red_* free for reuse
-        if ((threadIdx.x & 31) == 0) { t.red_d[w] = v; t.red_i[w] = idx; }
+        if ((threadIdx.x & 31) == 0) { t.red_d[w] = wv; t.red_i[w] = widx; }
         QPN_SYNC();
-        v = t.red_d[0]; idx = t.red_i[0];
+        wv = t.red_d[0]; widx = t.red_i[0];
         for (int k = 1; k < nw; ++k) {
-            double v2 = t.red_d[k]; int i2 = t.red_i[k];
-            bool take = (i2 >= 0) && (idx < 0 || v2 > v || (v2 == v && i2 < idx));
-            if (take) { v = v2; idx = i2; }
+            const double v2 = t.red_d[k]; const int i2 = t.red_i[k];
+            if (i2 >= 0 && (widx < 0 || v2 > wv)) { wv = v2; widx = i2; }      // warps are in row order: ties keep the lower row
         }
     }
+    v = wv; idx = widx;
 }
 
-__device__ inline double block_min(const Tab& t, double v) {
+// Same reduction when the candidates are not the tableau rows: every thread offers (v >= 0, idx);
+// larger v wins, ties -> lower idx.
+__device__ inline void block_argmax_idx(const Tab& t, bool valid, double& v, int& idx) {
     const unsigned full = 0xffffffffu;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(full, v, o));
+    unsigned hi = valid ? (unsigned)__double2hiint(v) : 0u, lo = valid ? (unsigned)__double2loint(v) : 0u;
+    const unsigned mine_hi = hi, mine_lo = lo;
+    warp_max_bits(hi, lo);
+    const bool win = valid && mine_hi == hi && mine_lo == lo;
+    int widx = (int)__reduce_min_sync(full, win ? (unsigned)idx : 0x7fffffffu);
+    if (widx == 0x7fffffff) widx = -1;
+    double wv = __hiloint2double((int)hi, (int)lo);
     const int nw = blockDim.x >> 5;
     if (nw > 1) {
         const int w = threadIdx.x >> 5;
         QPN_SYNC();
-        if ((threadIdx.x & 31) == 0) t.red_d[w] = v;
+        if ((threadIdx.x & 31) == 0) { t.red_d[w] = wv; t.red_i[w] = widx; }
         QPN_SYNC();
-        v = t.red_d[0];
-        for (int k = 1; k < nw; ++k) v = fmin(v, t.red_d[k]);
+        wv = t.red_d[0]; widx = t.red_i[0];
+        for (int k = 1; k < nw; ++k) {
+            const double v2 = t.red_d[k]; const int i2 = t.red_i[k];
+            if (i2 >= 0 && (widx < 0 || v2 > wv || (v2 == wv && i2 < widx))) { wv = v2; widx = i2; }
+        }
     }
-    return v;
+    v = wv; idx = widx;
 }
+
+__device__ inline double block_min(const Tab& t, double v) {   // v >= 0 or +inf
+    unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    warp_min_bits(hi, lo);
+    double m = __hiloint2double((int)hi, (int)lo);
+    const int nw = blockDim.x >> 5;
+    if (nw > 1) {
+        const int w = threadIdx.x >> 5;
+        QPN_SYNC();
+        if ((threadIdx.x & 31) == 0) t.red_d[w] = m;
+        QPN_SYNC();
+        m = t.red_d[0];
+        for (int k = 1; k < nw; ++k) m = fmin(m, t.red_d[k]);
+    }
+    return m;
+}
+
+__device__ inline bool is_free_var(const Tab& t, int k) { return t.l[k] == -QPN_INF && t.u[k] == QPN_INF; }
 
 __device__ inline void var_bounds(const Tab& t, int var, double& lo, double& up) {
     const int n = t.n;
@@ -169,90 +228,114 @@ __device__ inline bool artificial_row(const Tab& t, int i) {
 }
 
 // ---- start of the normal-map path (avi_scratch.jl:17-50) -----------------------------
-// Expects T[:, 0:n] = -M, t.l, t.u filled, q and z0 readable (shared or global), and
-// zb = t.prow as scratch.  Ends with a barrier.
+// Expects T[i][0:n] = -M[i][:] (thread i wrote its own row), t.l, t.u filled, q and z0
+// readable.  zb = t.prow is scratch (needs ldr >= n; every caller has cap >= n+1).
+// Ends with a barrier.
 __device__ inline void tab_start(Tab& t, const double* q, const double* z0) {
     const int n = t.n, i = threadIdx.x;
     double* zb = t.prow;
     if (i < n) zb[i] = fmin(fmax(z0[i], t.l[i]), t.u[i]);
     QPN_SYNC();
     if (i < n) {
+        double* row = t.T + (size_t)i * t.ldr;
         double acc = 0.0;
         for (int j = 0; j < n; ++j) {
-            const double mij = -t.T[(size_t)j * t.ld + i];
+            const double mij = -row[j];
             if (mij != 0.0) acc = fma(mij, zb[j], acc);
         }
         const double zi = z0[i], zbi = zb[i];
         const double r = ((acc + q[i]) + zi) - zbi;
-        t.T[(size_t)n * t.ld + i] = -r;
+        row[n] = -r;                                      // the homotopy column goes last
         t.beta[i] = zbi - zi;
         t.rowvar[i] = n + i;
         t.zst[i] = (zi <= t.l[i]) ? AT_L : (zi >= t.u[i]) ? AT_U : FLOATING;
-        t.colvar[i] = i;
-        t.nbval[i] = zbi;
         t.rowof[i] = -1; t.colof[i] = i;
         t.rowof[n + i] = i; t.colof[n + i] = -1;
+        t.colvar[i] = i;
+        t.nbval[i] = zbi;
     }
     if (i == 0) {
         t.colvar[n] = 2 * n; t.nbval[n] = 0.0;
         t.rowof[2 * n] = -1; t.colof[2 * n] = n;
     }
+    t.ncol = n + 1;
     t.pivots = 0;
     QPN_SYNC();
 }
 
 // ---- rank-1 pivot on the compact tableau (avi_scratch.jl:2-7) --------------------------
 __device__ inline void pivot(Tab& t, int rho, int c) {
-    const int n = t.n, nc = n + 1, ld = t.ld, i = threadIdx.x;
+    const int n = t.n, ldr = t.ldr, i = threadIdx.x;
+    const int ncol = t.ncol;
+    const int nce = (ncol + 1) & ~1;                      // even: the update runs two columns at a time
     double* T = t.T;
-    const double p = T[(size_t)c * ld + rho];
-    for (int j = i; j < nc; j += blockDim.x)
-        t.prow[j] = (j == c) ? (1.0 / p) : T[(size_t)j * ld + rho] / p;
-    const double d = (i < n) ? T[(size_t)c * ld + i] : 0.0;
+    const double* prho = T + (size_t)rho * ldr;
+    const double p = prho[c];
+    for (int j = i; j < nce; j += blockDim.x)
+        t.prow[j] = (j >= ncol) ? 0.0 : (j == c) ? (1.0 / p) : prho[j] / p;
+    const double d = (i < n) ? T[(size_t)i * ldr + c] : 0.0;
+    const int lv = t.rowvar[rho];                         // leaving variable (read before the barrier)
+    // A slack of a free variable never comes back: its column leaves the live range.
+    const bool dead = lv >= n && lv < 2 * n && is_free_var(t, lv - n);
+    const int last = ncol - 1;
     QPN_SYNC();
     if (i < n) {
-        if (i == rho) {
-            for (int j = 0; j < nc; ++j) T[(size_t)j * ld + i] = t.prow[j];
-        } else if (d != 0.0) {
-            const double nd = -d;
-#pragma unroll 4
-            for (int j = 0; j < nc; ++j) {
-                const double pj = t.prow[j];
-                if (j == c) T[(size_t)j * ld + i] = fma(nd, pj, 0.0);
-                else if (pj != 0.0) T[(size_t)j * ld + i] = fma(nd, pj, T[(size_t)j * ld + i]);
-            }
+        double* row = T + (size_t)i * ldr;
+        row[c] = 0.0;                                     // then column c follows the common formula
+        const bool isrho = (i == rho);
+        const double nd = -d;
+#pragma unroll 2
+        for (int j = 0; j < nce; j += 2) {
+            const double2 pj = *reinterpret_cast<const double2*>(t.prow + j);
+            if (pj.x == 0.0 && pj.y == 0.0) continue;     // uniform: both columns untouched by this pivot
+            double2 tv = *reinterpret_cast<double2*>(row + j);
+            tv.x = isrho ? pj.x : fma(nd, pj.x, tv.x);
+            tv.y = isrho ? pj.y : fma(nd, pj.y, tv.y);
+            *reinterpret_cast<double2*>(row + j) = tv;
         }
+        if (dead && c != last) row[c] = row[last];        // own row only: no barrier needed
     }
     if (i == 0) {
-        const int ev = t.colvar[c], lv = t.rowvar[rho];
-        t.rowvar[rho] = ev; t.colvar[c] = lv;
-        t.rowof[ev] = rho; t.colof[ev] = -1;
-        t.rowof[lv] = -1;  t.colof[lv] = c;
-        const double tmp = t.beta[rho]; t.beta[rho] = t.nbval[c]; t.nbval[c] = tmp;
+        const int ev = t.colvar[c];
+        const double vent = t.nbval[c], vlv = t.beta[rho];
+        t.rowvar[rho] = ev; t.rowof[ev] = rho; t.colof[ev] = -1; t.rowof[lv] = -1;
+        t.beta[rho] = vent;
+        if (dead) {
+            t.colof[lv] = -1;
+            if (c != last) {
+                const int mv = t.colvar[last];
+                t.colvar[c] = mv; t.nbval[c] = t.nbval[last]; t.colof[mv] = c;
+            }
+        } else {
+            t.colvar[c] = lv; t.colof[lv] = c; t.nbval[c] = vlv;
+        }
     }
+    if (dead) t.ncol = last;
     t.pivots++;
     QPN_SYNC();
 }
 
 __device__ inline int best_artificial_row(const Tab& t, int c) {
     const int i = threadIdx.x;
-    double a = 0.0; int idx = -1;
+    double a = 0.0; bool valid = false;
     if (i < t.n && artificial_row(t, i)) {
-        a = fabs(t.T[(size_t)c * t.ld + i]);
-        if (a > 0.0) idx = i;
+        a = fabs(t.T[(size_t)i * t.ldr + c]);
+        valid = a > 0.0;
     }
-    block_argmax(t, a, idx);
+    int idx;
+    block_argmax(t, valid, a, idx);
     return (idx >= 0 && a > PIV_TOL) ? idx : -1;
 }
 
 // ---- ratio test over the finite bounds of the basics (avi_scratch.jl:65-77) ------------
 // Returns the step of the blocking row (INF if none); all threads get the same answer.
+// Every exit ends with a barrier.
 __device__ inline double ratio_test(const Tab& t, int c, double sigma, int& rho, int& which) {
     const int n = t.n, i = threadIdx.x;
     double r = QPN_INF, a = 0.0;
     bool is_t = false;
     if (i < n) {
-        const double ci = t.T[(size_t)c * t.ld + i];
+        const double ci = t.T[(size_t)i * t.ldr + c];
         const double d = sigma * ci;
         const int v = t.rowvar[i];
         double lo, up;
@@ -264,19 +347,19 @@ __device__ inline double ratio_test(const Tab& t, int c, double sigma, int& rho,
     }
     const double theta = block_min(t, r);
     rho = -1; which = 0;
-    if (theta == QPN_INF) { QPN_SYNC(); return QPN_INF; }   // every exit ends with a barrier
+    if (theta == QPN_INF) { QPN_SYNC(); return QPN_INF; }
     const double cut = theta + TIE_TOL * (1.0 + theta);
     // among ties: t first (so the path terminates), then largest |d|, then lowest row
-    double key = -1.0; int idx = -1;
-    if (i < n && r <= cut) { key = is_t ? QPN_INF : a; idx = i; }
-    block_argmax(t, key, idx);
+    const bool cand = (i < n) && (r <= cut);
+    double key = is_t ? QPN_INF : a;
+    int idx;
+    block_argmax(t, cand, key, idx);
     rho = idx;
-    // the winner publishes its own ratio
     if (blockDim.x > 32) QPN_SYNC();
-    if (i == rho) t.red_d[32] = r;
+    if (i == rho) t.red_d[32] = r;                        // the winner publishes its own ratio
     QPN_SYNC();
     const double th = t.red_d[32];
-    which = (sigma * t.T[(size_t)c * t.ld + rho] > 0.0) ? -1 : +1;
+    which = (sigma * t.T[(size_t)rho * t.ldr + c] > 0.0) ? -1 : +1;
     return th;
 }
 
@@ -284,7 +367,7 @@ __device__ inline void move(Tab& t, int c, double sigma, double theta) {
     if (theta == 0.0) return;
     const int i = threadIdx.x;
     if (i < t.n) {
-        const double ci = t.T[(size_t)c * t.ld + i];
+        const double ci = t.T[(size_t)i * t.ldr + c];
         if (ci != 0.0) t.beta[i] = fma(-(sigma * theta), ci, t.beta[i]);
     }
     if (i == 0) t.nbval[c] = fma(sigma, theta, t.nbval[c]);
@@ -308,6 +391,7 @@ __device__ inline void set_zst(Tab& t, int k, int8_t s) {
 
 __device__ inline bool try_exchange(Tab& t, int var) {
     const int c = t.colof[var];
+    if (c < 0) return false;
     const int rho = best_artificial_row(t, c);
     if (rho < 0) return false;
     pivot(t, rho, c);
@@ -324,7 +408,7 @@ __device__ inline void crash(Tab& t) {
         if (rho >= 0) { pivot(t, rho, c); set_zst(t, i, BASIC); continue; }
         // dependent column: walk towards an extreme point (Cao-Ferris stage 2)
         int rb[2], wb[2]; double th[2], own[2], step[2];
-        own[0] = t.u[i] - t.nbval[c];        // read before the ratio tests (see lemke)
+        own[0] = t.u[i] - t.nbval[c];        // read before the ratio tests (synchronisation rule)
         own[1] = t.nbval[c] - t.l[i];
         for (int s = 0; s < 2; ++s) {
             const double sigma = s == 0 ? 1.0 : -1.0;

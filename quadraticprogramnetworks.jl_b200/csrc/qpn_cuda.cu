@@ -58,7 +58,6 @@ static int fail(qpn_handle* h, const char* fmt, ...) {
     } while (0)
 
 static inline int roundup32(int n) { return n < 32 ? 32 : ((n + 31) / 32) * 32; }
-static inline int odd_ld(int n) { return n | 1; }
 
 extern "C" int qpn_create(int device, qpn_handle** out) {
     qpn_handle* h = nullptr;
@@ -215,14 +214,13 @@ static int launch_avi(qpn_handle* h, int n, int batch, const MatDesc& M, const d
                       const double* u, int lu_shared, const double* z0, int max_pivots, double* z,
                       int32_t* st, int32_t* pv, int8_t* basis, cudaStream_t s) {
     if (batch <= 0) return 0;
-    const int ld = odd_ld(n);
-    const size_t smem = tab_smem_bytes(n, ld) + 2 * sizeof(double) * (size_t)n;
+    const size_t smem = tab_smem_bytes(n, n + 1) + 2 * sizeof(double) * (size_t)n;
     if (smem > (size_t)h->max_smem_optin)
         return fail(h, "AVI of size n=%d needs %zu B of shared memory per CTA (limit %d): the shared-memory "
                        "tableau path does not cover this size", n, smem, h->max_smem_optin);
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(avi_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (max_pivots <= 0) max_pivots = 50 * n + 100;
-    avi_solve_kernel<<<batch, roundup32(n), smem, s>>>(n, ld, batch, M, q, l, u, lu_shared, z0, max_pivots, z, st, pv, basis);
+    avi_solve_kernel<<<batch, roundup32(n), smem, s>>>(n, batch, M, q, l, u, lu_shared, z0, max_pivots, z, st, pv, basis);
     h->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -328,13 +326,13 @@ static GaviDesc gavi_dev_desc(const qpn_gavi* g) {
 static int launch_gavi(qpn_handle* h, const GaviDesc& g, int batch, const double* w, const double* z0, int presolve,
                        int max_pivots, double* z, double* zfull, int32_t* st, int32_t* pv, int8_t* basis, cudaStream_t s) {
     if (batch <= 0) return 0;
-    const int n = g.d1 + 2 * g.d2, ld = odd_ld(n);
+    const int n = g.d1 + 2 * g.d2;
     const size_t smem = gavi_smem_bytes(g.d1, g.d2, g.np);
     if (smem > (size_t)h->max_smem_optin)
         return fail(h, "GAVI with d1=%d d2=%d needs %zu B of shared memory per CTA (limit %d)", g.d1, g.d2, smem, h->max_smem_optin);
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(gavi_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (max_pivots <= 0) max_pivots = 50 * n + 100;
-    gavi_solve_kernel<<<batch, roundup32(n), smem, s>>>(g, ld, batch, w, z0, presolve, max_pivots, z, zfull, st, pv, basis);
+    gavi_solve_kernel<<<batch, roundup32(n), smem, s>>>(g, batch, w, z0, presolve, max_pivots, z, zfull, st, pv, basis);
     h->launches++;
     CK(cudaGetLastError());
     return 0;

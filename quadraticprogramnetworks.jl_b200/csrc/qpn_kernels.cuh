@@ -14,41 +14,45 @@ struct MatDesc {
     int nnz, base, shared;
 };
 
-// T[:, 0:n] = -M for instance b.  Ends with a barrier.
+// T[i][0:n] = -M[i][:] for instance b (row-major tableau).  Ends with a barrier.
 __device__ inline void load_neg_matrix(Tab& t, const MatDesc& M, int b) {
-    const int n = t.n, ld = t.ld;
+    const int n = t.n, ldr = t.ldr, i = threadIdx.x;
     if (M.dense) {
         const double* src = M.dense + (M.shared ? 0 : (size_t)b * n * n);
-        for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
-            const int j = e / n, i = e - j * n;
-            t.T[(size_t)j * ld + i] = -src[e];
+        if (i < n) {
+            double* row = t.T + (size_t)i * ldr;
+            for (int j = 0; j < n; ++j) row[j] = -src[(size_t)j * n + i];      // coalesced across the warp
         }
     } else {
-        for (int e = threadIdx.x; e < n * ld; e += blockDim.x) t.T[e] = 0.0;
+        if (i < n) {
+            double* row = t.T + (size_t)i * ldr;
+            for (int j = 0; j < n; ++j) row[j] = 0.0;
+        }
         QPN_SYNC();
         const double* nz = M.nzval + (M.shared ? 0 : (size_t)b * M.nnz);
         for (int j = 0; j < n; ++j) {
             const int k0 = M.colptr[j] - M.base, k1 = M.colptr[j + 1] - M.base;
-            for (int k = k0 + threadIdx.x; k < k1; k += blockDim.x)
-                t.T[(size_t)j * ld + (M.rowval[k] - M.base)] = -nz[k];
+            for (int k = k0 + i; k < k1; k += blockDim.x)
+                t.T[(size_t)(M.rowval[k] - M.base) * ldr + j] = -nz[k];
         }
     }
     QPN_SYNC();
 }
 
-// r_i = (M z)_i + q_i with T[:, 0:n] = -M and z in shared memory; sequential in j.
+// r_i = (M z)_i + q_i with T[i][0:n] = -M[i][:] and z in shared memory; sequential in j.
 __device__ inline double residual_row(const Tab& t, const double* zs, double qi, int i) {
+    const double* row = t.T + (size_t)i * t.ldr;
     double acc = 0.0;
     for (int j = 0; j < t.n; ++j) {
-        const double mij = -t.T[(size_t)j * t.ld + i];
+        const double mij = -row[j];
         if (mij != 0.0) acc = fma(mij, zs[j], acc);
     }
     return acc + qi;
 }
 
 // ---- solve_avi (avi.jl:63-77) ------------------------------------------------------------
-// grid = batch, block = roundup32(n).  Dynamic smem: Tab + q(n) + z(n).
-__global__ void avi_solve_kernel(int n, int ld, int batch, MatDesc M, const double* __restrict__ q,
+// grid = batch, block = roundup32(n).  Dynamic smem: Tab(n, n+1) + q(n) + z(n).
+__global__ void avi_solve_kernel(int n, int batch, MatDesc M, const double* __restrict__ q,
                                  const double* __restrict__ l, const double* __restrict__ u,
                                  int lu_shared, const double* __restrict__ z0, int max_pivots,
                                  double* __restrict__ z_out, int32_t* __restrict__ status_out,
@@ -56,8 +60,8 @@ __global__ void avi_solve_kernel(int n, int ld, int batch, MatDesc M, const doub
     extern __shared__ __align__(16) unsigned char smem[];
     const int b = blockIdx.x, i = threadIdx.x;
     Tab t;
-    tab_carve(t, n, ld, smem);
-    double* qs = reinterpret_cast<double*>(smem + tab_smem_bytes(n, ld));
+    tab_carve(t, n, n + 1, smem);
+    double* qs = reinterpret_cast<double*>(smem + tab_smem_bytes(n, n + 1));
     double* zs = qs + n;
     if (i < n) {
         qs[i] = q[(size_t)b * n + i];

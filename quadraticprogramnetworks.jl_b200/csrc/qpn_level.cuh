@@ -48,13 +48,13 @@ __host__ __device__ inline size_t gavi_extra_bytes(int d1, int d2, int np) {
 }
 __host__ __device__ inline size_t gavi_smem_bytes(int d1, int d2, int np) {
     const int n = d1 + 2 * d2;
-    return tab_smem_bytes(n, n | 1) + gavi_extra_bytes(d1, d2, np);
+    return tab_smem_bytes(n, n + 1) + gavi_extra_bytes(d1, d2, np);
 }
 
-__device__ inline unsigned char* gavi_carve(GaviSmem& s, const GaviDesc& g, int ld, unsigned char* smem) {
+__device__ inline unsigned char* gavi_carve(GaviSmem& s, const GaviDesc& g, unsigned char* smem) {
     const int n = g.d1 + 2 * g.d2, dz = g.d1 + g.d2;
-    tab_carve(s.t, n, ld, smem);
-    unsigned char* p = smem + tab_smem_bytes(n, ld);
+    tab_carve(s.t, n, n + 1, smem);
+    unsigned char* p = smem + tab_smem_bytes(n, n + 1);
     double* d = reinterpret_cast<double*>(p);
     s.qs = d; d += n;
     s.zs = d; d += n;
@@ -127,19 +127,22 @@ __device__ inline int gavi_solve_smem(GaviSmem& s, const GaviDesc& g, int presol
             }
             QPN_SYNC();
             auto build = [&](Tab& tt) {
-                const int ld = tt.ld;
-                for (int e = threadIdx.x; e < pn * ld; e += blockDim.x) tt.T[e] = 0.0;
+                const int ldr = tt.ldr;
+                if (threadIdx.x < pn) {
+                    double* row = tt.T + (size_t)threadIdx.x * ldr;
+                    for (int j = 0; j < pn; ++j) row[j] = 0.0;
+                }
                 QPN_SYNC();
                 for (int e = threadIdx.x; e < k * d2; e += blockDim.x) {
                     const int a = e / d2, r = e - a * d2;
                     const double v = g.A[(size_t)s.cols[a] * d2 + r];
-                    tt.T[(size_t)(k + r) * ld + a] = v;          // -(-A')
-                    tt.T[(size_t)a * ld + (k + r)] = -v;         // -(A)
+                    tt.T[(size_t)a * ldr + (k + r)] = v;         // -(-A')   row a, column k+r
+                    tt.T[(size_t)(k + r) * ldr + a] = -v;        // -(A)     row k+r, column a
                 }
-                for (int e = threadIdx.x; e < k; e += blockDim.x) tt.T[(size_t)e * ld + e] = -1.0;
+                for (int e = threadIdx.x; e < k; e += blockDim.x) tt.T[(size_t)e * ldr + e] = -1.0;
                 for (int e = threadIdx.x; e < d2; e += blockDim.x) {
-                    tt.T[(size_t)(k + d2 + e) * ld + (k + e)] = 1.0;     // -(-1)
-                    tt.T[(size_t)(k + e) * ld + (k + d2 + e)] = -1.0;    // -(+1)
+                    tt.T[(size_t)(k + e) * ldr + (k + d2 + e)] = 1.0;      // -(-1)  row k+e, column k+d2+e
+                    tt.T[(size_t)(k + d2 + e) * ldr + (k + e)] = -1.0;     // -(+1)  row k+d2+e, column k+e
                 }
                 QPN_SYNC();
             };
@@ -166,27 +169,25 @@ __device__ inline int gavi_solve_smem(GaviSmem& s, const GaviDesc& g, int presol
     }
     QPN_SYNC();
     auto build = [&](Tab& tt) {
-        const int ld = tt.ld;
-        for (int e = threadIdx.x; e < n * ld; e += blockDim.x) tt.T[e] = 0.0;
-        QPN_SYNC();
-        for (int e = threadIdx.x; e < d1 * dz; e += blockDim.x) {
-            const int j = e / d1, r = e - j * d1;
-            tt.T[(size_t)j * ld + r] = -g.M[e];
-        }
-        for (int e = threadIdx.x; e < d2 * dz; e += blockDim.x) {
-            const int j = e / d2, r = e - j * d2;
-            tt.T[(size_t)j * ld + d1 + r] = -g.A[e];
-        }
-        for (int e = threadIdx.x; e < d2; e += blockDim.x) {
-            tt.T[(size_t)(dz + e) * ld + d1 + e] = 1.0;      // -(-I)
-            tt.T[(size_t)(d1 + e) * ld + dz + e] = -1.0;     // -(+I)
+        const int ldr = tt.ldr, r = threadIdx.x;
+        if (r < n) {                                         // thread r writes row r of -[M 0; A -I; 0 I 0]
+            double* row = tt.T + (size_t)r * ldr;
+            if (r < d1) {
+                for (int j = 0; j < dz; ++j) row[j] = -g.M[(size_t)j * d1 + r];
+                for (int j = dz; j < n; ++j) row[j] = 0.0;
+            } else if (r < dz) {
+                for (int j = 0; j < dz; ++j) row[j] = -g.A[(size_t)j * d2 + (r - d1)];
+                for (int j = dz; j < n; ++j) row[j] = (j - dz == r - d1) ? 1.0 : 0.0;
+            } else {
+                for (int j = 0; j < n; ++j) row[j] = (j - d1 == r - dz) ? -1.0 : 0.0;
+            }
         }
         QPN_SYNC();
     };
     return solve_avi_smem(t, n, build, s.qs, s.zs, max_pivots, s.code, pivots);
 }
 
-__global__ void gavi_solve_kernel(GaviDesc g, int ld, int batch, const double* __restrict__ w,
+__global__ void gavi_solve_kernel(GaviDesc g, int batch, const double* __restrict__ w,
                                   const double* __restrict__ z0, int presolve, int max_pivots,
                                   double* __restrict__ z_out, double* __restrict__ zfull_out,
                                   int32_t* __restrict__ status_out, int32_t* __restrict__ pivots_out,
@@ -199,7 +200,7 @@ __global__ void gavi_solve_kernel(GaviDesc g, int ld, int batch, const double* _
     QPN_SYNC();
 #endif
     GaviSmem s;
-    gavi_carve(s, g, ld, smem);
+    gavi_carve(s, g, smem);
     for (int j = i; j < g.np; j += blockDim.x) s.w[j] = w[(size_t)b * g.np + j];
     for (int j = i; j < dz; j += blockDim.x) s.z0[j] = z0[(size_t)b * dz + j];
     QPN_SYNC();
@@ -222,7 +223,7 @@ struct NodeDesc {
 };
 
 struct VerifySmem {
-    double *qt;     // nd
+    double *qt;     // nd   (standalone kernel only; the level kernel points these at its batched arrays)
     double *ax;     // m
     double *Ab;     // nd x m
     double *Ab0;    // nd x m
@@ -279,7 +280,9 @@ __device__ inline void lstsq_basic_block(const Tab& red, int nd, int k, double* 
             for (int i = c; i < nd; ++i) s = fma(Ab[(size_t)jj * nd + i], Ab[(size_t)jj * nd + i], s);
             if (jb < 0 || s > best) { best = s; jb = jj; }
         }
-        block_argmax(red, best, jb);
+        // squared norms are >= 0; with more columns than threads a thread's own best is already
+        // the lowest-index maximum of its strided set, so ties across threads keep the lower thread
+        block_argmax_idx(red, jb >= 0, best, jb);
         const double nrm = sqrt(best);
         if (nrm <= 1e-10) break;
         QPN_SYNC();
@@ -323,22 +326,32 @@ __device__ inline void lstsq_basic_block(const Tab& red, int nd, int k, double* 
     QPN_SYNC();
 }
 
-// Returns 1 when x (shared memory, nv entries) is a solution for the node; lam in vs.lam_out.
-// tab: a tableau workspace large enough for an AVI of size m (used by the fallback and for
-// the reduction scratch).
-__device__ inline int verify_solution_smem(Tab& tab, VerifySmem& vs, const NodeDesc& nd_, const double* x, double tol,
-                                           int* how, int* pivots) {
-    const int nd = nd_.nd, nv = nd_.nv, m = nd_.m, i = threadIdx.x;
-    for (int r = i; r < nd; r += blockDim.x) {
+// Gradient and constraint values of one node:  qt = Q[dec,:] x + q[dec],  ax = A x.
+// Thread r takes row r; each dot product is sequential in the variable index.
+__device__ inline void node_products(const NodeDesc& nd_, const double* x, double* qt, double* ax) {
+    const int nd = nd_.nd, nv = nd_.nv, m = nd_.m;
+    for (int r = threadIdx.x; r < nd + m; r += blockDim.x) {
         double acc = 0.0;
-        for (int j = 0; j < nv; ++j) acc = fma(nd_.Qd[(size_t)j * nd + r], x[j], acc);
-        vs.qt[r] = acc + nd_.qd[r];
+        if (r < nd) {
+            for (int j = 0; j < nv; ++j) acc = fma(nd_.Qd[(size_t)j * nd + r], x[j], acc);
+            qt[r] = acc + nd_.qd[r];
+        } else {
+            const int rr = r - nd;
+            for (int j = 0; j < nv; ++j) acc = fma(nd_.A[(size_t)j * m + rr], x[j], acc);
+            ax[rr] = acc;
+        }
     }
+}
+
+// Returns 1 when the point whose products qt / ax are given is a solution for the node; lam in
+// vs.lam_out.  tab: a tableau workspace large enough for an AVI of size m (used by the fallback
+// and for the reduction scratch).  qt / ax must be complete (barrier) on entry.
+__device__ inline int verify_solution_smem(Tab& tab, VerifySmem& vs, const NodeDesc& nd_, const double* qt, const double* ax,
+                                           double tol, int* how, int* pivots) {
+    const int nd = nd_.nd, m = nd_.m, i = threadIdx.x;
     int infeasible = 0;
     for (int r = i; r < m; r += blockDim.x) {
-        double acc = 0.0;
-        for (int j = 0; j < nv; ++j) acc = fma(nd_.A[(size_t)j * m + r], x[j], acc);
-        vs.ax[r] = acc;
+        const double acc = ax[r];
         vs.lam_out[r] = 0.0;
         const double lo = nd_.l[r], up = nd_.u[r];
         if (!((lo - 1e-3 <= acc) && (acc - 1e-3 <= up))) infeasible = 1;
@@ -348,7 +361,7 @@ __device__ inline int verify_solution_smem(Tab& tab, VerifySmem& vs, const NodeD
     infeasible = QPN_SYNC_OR(infeasible);
     if (infeasible) { *how = 0; return 0; }
     double nq = 0.0;
-    for (int r = 0; r < nd; ++r) nq = fma(vs.qt[r], vs.qt[r], nq);
+    for (int r = 0; r < nd; ++r) nq = fma(qt[r], qt[r], nq);
     if (m == 0) { *how = 1; return sqrt(nq) <= tol ? 1 : 0; }
     // order the active rows: lower-active, upper-active, both (qp_processing.jl:105-114)
     if (i == 0) {
@@ -356,18 +369,26 @@ __device__ inline int verify_solution_smem(Tab& tab, VerifySmem& vs, const NodeD
         for (int r = 0; r < m; ++r) if (vs.kind[r] == 1) { vs.idx[k++] = r; np_++; }
         for (int r = 0; r < m; ++r) if (vs.kind[r] == 2) { vs.idx[k++] = r; nn++; }
         for (int r = 0; r < m; ++r) if (vs.kind[r] == 3) { vs.idx[k++] = r; }
-        tab.red_i[32] = k; tab.red_i[33] = np_; vs.perm[0] = 0;
-        tab.red_d[33] = (double)nn;
+        tab.red_i[32] = k; tab.red_i[33] = np_; tab.red_i[34] = nn;
     }
     QPN_SYNC();
-    const int k = tab.red_i[32], np_ = tab.red_i[33], nn = (int)tab.red_d[33];
+    const int k = tab.red_i[32], np_ = tab.red_i[33], nn = tab.red_i[34];
+    if (k == 0) {
+        // No active row: lam = 0 and the residual is qt itself.  The least-squares step rejects
+        // (else we would have returned above only for m == 0) unless |qt| <= tol; the fallback has
+        // every multiplier fixed at 0, so it returns lam = 0 after 0 pivots and rejects as well.
+        QPN_SYNC();
+        if (sqrt(nq) <= tol) { *how = 2; return 1; }
+        *how = 4;
+        return 0;
+    }
     for (int e = i; e < nd * k; e += blockDim.x) {
         const int tcol = e / nd, r = e - tcol * nd;
         const double sgn = (tcol >= np_ && tcol < np_ + nn) ? -1.0 : 1.0;
         const double val = sgn * nd_.A[(size_t)nd_.dec[r] * m + vs.idx[tcol]];
         vs.Ab[e] = val; vs.Ab0[e] = val;
     }
-    for (int r = i; r < nd; r += blockDim.x) vs.b[r] = vs.qt[r];
+    for (int r = i; r < nd; r += blockDim.x) vs.b[r] = qt[r];
     QPN_SYNC();
     lstsq_basic_block(tab, nd, k, vs.Ab, vs.b, vs.lam, vs.perm, vs.v);
     // acceptance (qp_processing.jl:119)
@@ -378,14 +399,14 @@ __device__ inline int verify_solution_smem(Tab& tab, VerifySmem& vs, const NodeD
         for (int r = 0; r < nd; ++r) {
             double acc = 0.0;
             for (int t = 0; t < k; ++t) acc = fma(vs.Ab0[(size_t)t * nd + r], vs.lam[t], acc);
-            const double e = acc - vs.qt[r];
+            const double e = acc - qt[r];
             res = fma(e, e, res);
         }
         if (!(sqrt(res) <= tol)) ok = 0;
-        tab.red_i[32] = ok;
+        tab.red_i[35] = ok;
     }
     QPN_SYNC();
-    if (tab.red_i[32]) {
+    if (tab.red_i[35]) {
         for (int t = i; t < k; t += blockDim.x)
             vs.lam_out[vs.idx[t]] = (t >= np_ && t < np_ + nn) ? -vs.lam[t] : vs.lam[t];
         QPN_SYNC();
@@ -397,7 +418,7 @@ __device__ inline int verify_solution_smem(Tab& tab, VerifySmem& vs, const NodeD
     QPN_SYNC();
     for (int r = i; r < m; r += blockDim.x) {
         double acc = 0.0;
-        for (int t = 0; t < nd; ++t) acc = fma(nd_.A[(size_t)nd_.dec[t] * m + r], vs.qt[t], acc);
+        for (int t = 0; t < nd; ++t) acc = fma(nd_.A[(size_t)nd_.dec[t] * m + r], qt[t], acc);
         vs.qs[r] = -acc;
         vs.zs[r] = 0.0;
         const int8_t kd = vs.kind[r];
@@ -406,12 +427,12 @@ __device__ inline int verify_solution_smem(Tab& tab, VerifySmem& vs, const NodeD
     }
     QPN_SYNC();
     auto build = [&](Tab& tt) {
-        const int ld = tt.ld;
+        const int ldr = tt.ldr;
         for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
             const int c = e / m, r = e - c * m;
             double acc = 0.0;
             for (int t = 0; t < nd; ++t) acc = fma(nd_.A[(size_t)nd_.dec[t] * m + r], nd_.A[(size_t)nd_.dec[t] * m + c], acc);
-            tt.T[(size_t)c * ld + r] = -acc;
+            tt.T[(size_t)r * ldr + c] = -acc;
         }
         QPN_SYNC();
     };
@@ -425,35 +446,39 @@ __device__ inline int verify_solution_smem(Tab& tab, VerifySmem& vs, const NodeD
         for (int t = 0; t < nd; ++t) {
             double acc = 0.0;
             for (int r = 0; r < m; ++r) acc = fma(nd_.A[(size_t)nd_.dec[t] * m + r], vs.zs[r], acc);
-            const double e = acc - vs.qt[t];
+            const double e = acc - qt[t];
             res2 = fma(e, e, res2);
         }
-        tab.red_i[32] = sqrt(res2) <= 1e-4 ? 1 : 0;
+        tab.red_i[35] = sqrt(res2) <= 1e-4 ? 1 : 0;
     }
     for (int r = i; r < m; r += blockDim.x) vs.lam_out[r] = vs.zs[r];
     QPN_SYNC();
-    const int ok2 = tab.red_i[32];
+    const int ok2 = tab.red_i[35];
     *how = ok2 ? 3 : 4;
     return ok2;
 }
 
-// grid = batch, block = roundup32(max(m, nd, 1)).  Dynamic smem: Tab(m) + VerifySmem + x(nv).
-__global__ void verify_solution_kernel(NodeDesc node, int ld, int batch, const double* __restrict__ x, double tol,
+// grid = batch, block = roundup32(max(m, nd, 1)).  Dynamic smem: Tab(m, m+1) + VerifySmem + x(nv) + qt(nd) + ax(m).
+__global__ void verify_solution_kernel(NodeDesc node, int batch, const double* __restrict__ x, double tol,
                                        uint8_t* __restrict__ solution_out, double* __restrict__ lam_out,
                                        int32_t* __restrict__ how_out, int8_t* __restrict__ active_out) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int b = blockIdx.x, i = threadIdx.x, m = node.m;
     const int tn = m > 0 ? m : 1;
     Tab tab;
-    tab_carve(tab, tn, ld, smem);
+    tab_carve(tab, tn, tn + 1, smem);
     VerifySmem vs;
-    unsigned char* p = smem + tab_smem_bytes(tn, ld);
+    unsigned char* p = smem + tab_smem_bytes(tn, tn + 1);
     verify_carve(vs, node.nd, m, p);
     double* xs = reinterpret_cast<double*>(p + verify_smem_bytes(node.nd, m));
+    double* qt = xs + node.nv;
+    double* ax = qt + node.nd;
     for (int j = i; j < node.nv; j += blockDim.x) xs[j] = x[(size_t)b * node.nv + j];
     QPN_SYNC();
+    node_products(node, xs, qt, ax);
+    QPN_SYNC();
     int how = 0, piv = 0;
-    const int sol = verify_solution_smem(tab, vs, node, xs, tol, &how, &piv);
+    const int sol = verify_solution_smem(tab, vs, node, qt, ax, tol, &how, &piv);
     QPN_SYNC();
     for (int r = i; r < m; r += blockDim.x) {
         if (lam_out) lam_out[(size_t)b * m + r] = vs.lam_out[r];
@@ -468,6 +493,7 @@ constexpr int QPN_MAX_PLAYERS = 8;
 struct LevelDesc {
     int nv, nplayers;
     NodeDesc players[QPN_MAX_PLAYERS];
+    int nd_off[QPN_MAX_PLAYERS], m_off[QPN_MAX_PLAYERS];   // offsets into the stacked qt / ax (= lam) arrays
     GaviDesc g;
     const int32_t* dec;     // nd_level
     const int32_t* par;     // g.np
@@ -476,16 +502,17 @@ struct LevelDesc {
     int nproj;
     const double* proj;     // nv x nproj
     int max_nd, max_m;      // over players
+    int nd_total;           // sum of nd over players
     int lam_total;          // sum of m over players
 };
 
 __host__ __device__ inline size_t level_smem_bytes(const LevelDesc& lv) {
     return gavi_smem_bytes(lv.g.d1, lv.g.d2, lv.g.np) + verify_smem_bytes(lv.max_nd, lv.max_m) +
-           8 * (2 * (size_t)lv.nv + (size_t)(lv.nproj > 0 ? lv.nproj : 1));
+           8 * (2 * (size_t)lv.nv + (size_t)(lv.nproj > 0 ? lv.nproj : 1) + (size_t)lv.nd_total + (size_t)lv.lam_total);
 }
 
 // hist: global scratch, batch x hist_cap x nproj (cycle check history); hist_count: batch.
-__global__ void level_equilibrium_kernel(LevelDesc lv, int ld, int batch, const double* __restrict__ x_init,
+__global__ void level_equilibrium_kernel(LevelDesc lv, int batch, const double* __restrict__ x_init,
                                          double* __restrict__ x_out, uint8_t* __restrict__ solved_out,
                                          int32_t* __restrict__ iters_out, int32_t* __restrict__ pivots_out,
                                          double* __restrict__ lam_out, double* __restrict__ hist,
@@ -493,16 +520,19 @@ __global__ void level_equilibrium_kernel(LevelDesc lv, int ld, int batch, const 
     extern __shared__ __align__(16) unsigned char smem[];
     const int b = blockIdx.x, i = threadIdx.x, nv = lv.nv;
     GaviSmem gs;
-    unsigned char* p = gavi_carve(gs, lv.g, ld, smem);
+    unsigned char* p = gavi_carve(gs, lv.g, smem);
     VerifySmem vs;
     verify_carve(vs, lv.max_nd, lv.max_m, p);
     double* xs = reinterpret_cast<double*>(p + verify_smem_bytes(lv.max_nd, lv.max_m));
     double* pv = xs + nv;                  // nproj
     double* xn = pv + (lv.nproj > 0 ? lv.nproj : 1);
+    double* qt_all = xn + nv;              // nd_total
+    double* ax_all = qt_all + lv.nd_total; // lam_total
     for (int j = i; j < nv; j += blockDim.x) xs[j] = x_init[(size_t)b * nv + j];
     QPN_SYNC();
     const int n_level = lv.g.d1 + 2 * lv.g.d2;
     const int max_piv = 50 * n_level + 100;
+    const int rows_all = lv.nd_total + lv.lam_total;
     int solved = 0, piv = 0, iters = 0;
     // The history outlives one call when the caller keeps hist / hist_count (the reference's
     // iterate_cache persists across the calls of one top-level solve, algorithm.jl:20-28).
@@ -537,17 +567,39 @@ __global__ void level_equilibrium_kernel(LevelDesc lv, int ld, int batch, const 
             }
             QPN_SYNC();
         }
-        // process_qp for every player at the level (algorithm.jl:47-49)
-        int all_sol = 1, lam_off = 0;
+        // process_qp for every player at the level (algorithm.jl:47-49): first every player's
+        // gradient and constraint values in one pass over the stacked rows ...
+        for (int r = i; r < rows_all; r += blockDim.x) {
+            int pl = 0;
+            if (r < lv.nd_total) {
+                while (pl + 1 < lv.nplayers && r >= lv.nd_off[pl + 1]) ++pl;
+                const NodeDesc& node = lv.players[pl];
+                const int rr = r - lv.nd_off[pl];
+                double acc = 0.0;
+                for (int j = 0; j < nv; ++j) acc = fma(node.Qd[(size_t)j * node.nd + rr], xs[j], acc);
+                qt_all[r] = acc + node.qd[rr];
+            } else {
+                const int q = r - lv.nd_total;
+                while (pl + 1 < lv.nplayers && q >= lv.m_off[pl + 1]) ++pl;
+                const NodeDesc& node = lv.players[pl];
+                const int rr = q - lv.m_off[pl];
+                double acc = 0.0;
+                for (int j = 0; j < nv; ++j) acc = fma(node.A[(size_t)j * node.m + rr], xs[j], acc);
+                ax_all[q] = acc;
+            }
+        }
+        QPN_SYNC();
+        // ... then the per-player tests
+        int all_sol = 1;
         for (int pl = 0; pl < lv.nplayers; ++pl) {
             const NodeDesc& node = lv.players[pl];
             int how = 0;
             gs.t.n = n_level;
-            const int sol = verify_solution_smem(gs.t, vs, node, xs, 1e-4, &how, &piv);
+            const int sol = verify_solution_smem(gs.t, vs, node, qt_all + lv.nd_off[pl], ax_all + lv.m_off[pl], 1e-4, &how, &piv);
             QPN_SYNC();
             if (lam_out)
-                for (int r = i; r < node.m; r += blockDim.x) lam_out[(size_t)b * lv.lam_total + lam_off + r] = sol ? vs.lam_out[r] : 0.0;
-            lam_off += node.m;
+                for (int r = i; r < node.m; r += blockDim.x)
+                    lam_out[(size_t)b * lv.lam_total + lv.m_off[pl] + r] = sol ? vs.lam_out[r] : 0.0;
             if (!sol) all_sol = 0;
             QPN_SYNC();
         }
