@@ -64,6 +64,7 @@ class _Tab:
             for j in range(n):
                 acc = fma(M[i, j], zb[j], acc)
             r[i] = ((acc + q[i]) + z0[i]) - zb[i]
+        self.r = r
         self.T = np.empty((n, n + 1))
         self.T[:, :n] = -M
         self.T[:, n] = -r
@@ -204,8 +205,53 @@ class _Tab:
         self.pivot(rho, c)
         return True
 
+    def is_free(self, k):
+        return self.l[k] == -INF and self.u[k] == INF
+
+    def best_free_row(self, c):
+        """Largest |T[i,c]| over rows still holding the slack w_k of a FREE variable (such a
+        row is artificial whatever the start point is)."""
+        best, brow = 0.0, -1
+        for i in range(self.n):
+            v = self.rowvar[i]
+            if self.n <= v < 2 * self.n and self.is_free(v - self.n):
+                a = abs(self.T[i, c])
+                if a > best:
+                    best, brow = a, i
+        return brow if best > PIV_TOL else -1
+
+    def recompute_tcol(self):
+        """T[:, t] = B^-1 r from the slack columns: column of a nonbasic w_k is -B^-1 e_k, a basic
+        w_k sitting in row rho means B^-1 e_k = -e_rho.  Sequential fma over k."""
+        n = self.n
+        tc = self.col_of(2 * n)
+        cols = [self.colvar.index(n + k) if (n + k) in self.colvar else -1 for k in range(n)]
+        rows = [self.rowvar.index(n + k) if (n + k) in self.rowvar else -1 for k in range(n)]
+        for i in range(n):
+            acc = 0.0
+            for k in range(n):
+                pik = -self.T[i, cols[k]] if cols[k] >= 0 else (-1.0 if rows[k] == i else 0.0)
+                if pik != 0.0:
+                    acc = fma(pik, self.r[k], acc)
+            self.T[i, tc] = acc
+
     def crash(self):
         n = self.n
+        # phase 0: free variables exchange against rows of free variables only.  Nothing here
+        # depends on the start point or on q, so for a matrix shared by a batch it is done once
+        # (the GPU engine precomputes it per matrix); the homotopy column is then rebuilt from r.
+        piv0 = self.pivots
+        for i in range(n):
+            if not self.is_free(i):
+                continue
+            c = self.col_of(i)
+            rho = self.best_free_row(c)
+            if rho >= 0:
+                self.pivot(rho, c)
+                self.zst[i] = BASIC
+        if self.pivots > piv0:
+            self.recompute_tcol()
+        # phase 1: everything still floating, against any artificial row
         for i in range(n):
             if self.zst[i] != FLOAT:
                 continue

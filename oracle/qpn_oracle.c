@@ -42,7 +42,7 @@ enum { AT_L = 0, AT_U = 1, FLOATING = 2, BASIC = 3 };
 typedef struct {
     int n, ncol;            /* ncol = n + 1 */
     double *T;              /* n x ncol, column-major */
-    double *beta, *nbval, *prow;
+    double *beta, *nbval, *prow, *r;
     const double *l, *u;
     int *rowvar, *colvar;   /* variable ids: z_i = i, w_i = n+i, t = 2n */
     int *rowof, *colof;     /* inverse maps, -1 when absent */
@@ -58,6 +58,7 @@ static void tab_init(tab_t *t, int n, const double *M, const double *q, const do
     t->beta = work;                    work += n;
     t->nbval = work;                   work += n + 1;
     t->prow = work;                    work += n + 1;
+    t->r = work;                       work += n;
     double *zb = work;                 /* n, scratch */
     t->l = l; t->u = u;
     t->rowvar = iwork;                 iwork += n;
@@ -71,6 +72,7 @@ static void tab_init(tab_t *t, int n, const double *M, const double *q, const do
         double acc = 0.0;
         for (int j = 0; j < n; ++j) acc = fma(M[(size_t)j * n + i], zb[j], acc);
         double r = ((acc + q[i]) + z0[i]) - zb[i];
+        t->r[i] = r;
         t->T[(size_t)n * n + i] = -r;
         t->beta[i] = zb[i] - z0[i];
         t->rowvar[i] = n + i;
@@ -204,9 +206,52 @@ static int try_exchange(tab_t *t, int var) {
     return 1;
 }
 
-/* ---- phase 1: bring interior / free variables into the basis ---------------- */
+static int is_free(const tab_t *t, int k) { return t->l[k] == -INFINITY && t->u[k] == INFINITY; }
+
+/* largest |T[i,c]| over rows still holding the slack of a FREE variable */
+static int best_free_row(const tab_t *t, int c) {
+    double best = 0.0; int brow = -1, n = t->n;
+    for (int i = 0; i < n; ++i) {
+        int v = t->rowvar[i];
+        if (v >= n && v < 2 * n && is_free(t, v - n)) {
+            double a = fabs(t->T[(size_t)c * n + i]);
+            if (a > best) { best = a; brow = i; }
+        }
+    }
+    return best > PIV_TOL ? brow : -1;
+}
+
+/* T[:, t] = B^-1 r rebuilt from the slack columns (nonbasic w_k: column = -B^-1 e_k; w_k basic
+ * in row rho: B^-1 e_k = -e_rho), sequential fma over k */
+static void recompute_tcol(tab_t *t) {
+    int n = t->n, tc = t->colof[2 * n];
+    double *out = t->prow;
+    for (int i = 0; i < n; ++i) {
+        double acc = 0.0;
+        for (int k = 0; k < n; ++k) {
+            int ck = t->colof[n + k];
+            double pik = ck >= 0 ? -t->T[(size_t)ck * n + i] : (t->rowof[n + k] == i ? -1.0 : 0.0);
+            if (pik != 0.0) acc = fma(pik, t->r[k], acc);
+        }
+        out[i] = acc;
+    }
+    for (int i = 0; i < n; ++i) t->T[(size_t)tc * n + i] = out[i];
+}
+
+/* ---- crash: bring interior / free variables into the basis -------------------- */
 static void crash(tab_t *t) {
     int n = t->n;
+    /* phase 0: free variables against rows of free variables only -- independent of the start
+     * point and of q, hence computed once per shared matrix by the GPU engine */
+    int piv0 = t->pivots;
+    for (int i = 0; i < n; ++i) {
+        if (!is_free(t, i)) continue;
+        int c = t->colof[i];
+        int rho = best_free_row(t, c);
+        if (rho >= 0) { pivot(t, rho, c); t->zst[i] = BASIC; }
+    }
+    if (t->pivots > piv0) recompute_tcol(t);
+    /* phase 1: everything still floating, against any artificial row */
     for (int i = 0; i < n; ++i) {
         if (t->zst[i] != FLOATING) continue;
         int c = t->colof[i];
@@ -319,7 +364,7 @@ int qpo_check_avi(int n, const double *M, const double *q, const double *l, cons
     return bad;
 }
 
-size_t qpo_avi_work_doubles(int n) { return (size_t)n * (n + 1) + 4 * (size_t)n + 2; }
+size_t qpo_avi_work_doubles(int n) { return (size_t)n * (n + 1) + 5 * (size_t)n + 2; }
 size_t qpo_avi_work_ints(int n) { return 6 * (size_t)n + 3; }
 
 /* avi.jl:63-77 with q = N*w + o already formed.  basis: 1 at lower, 2 interior/basic,

@@ -83,6 +83,7 @@ struct Tab {
     double* prow;   // ldr   scaled pivot row
     double* l;      // n
     double* u;      // n
+    double* rr;     // n     normal-map residual r at the start (rebuilds the homotopy column)
     int* rowvar;    // n      variable basic in row i      (z_i = i, w_i = n+i, t = 2n)
     int* colvar;    // ldr    variable nonbasic in column j
     int* rowof;     // 2n+1   row of a variable or -1
@@ -92,34 +93,46 @@ struct Tab {
     int* red_i;     // 36
 };
 
-__host__ __device__ inline size_t tab_smem_bytes(int n, int cap) {
-    const size_t ldr = (size_t)row_stride(cap);
-    size_t d = (size_t)n * ldr + (size_t)n + 2 * ldr + 2 * (size_t)n + 36;
-    size_t i = (size_t)n + ldr + 2 * (size_t)(2 * n + 1) + 36;
-    size_t b = (size_t)n;
+// Bytes of a workspace with room for `nmax` rows, a tableau buffer of `tdoubles` doubles and
+// rows of up to `ldrmax` doubles.  One workspace serves several solves of different shapes
+// (tab_shape) inside one kernel.
+__host__ __device__ inline size_t tab_smem_bytes_ex(int nmax, size_t tdoubles, int ldrmax) {
+    tdoubles = (tdoubles + 1) & ~(size_t)1;
+    size_t d = tdoubles + 2 * (size_t)ldrmax + 4 * (size_t)nmax + 36;
+    size_t i = (size_t)nmax + ldrmax + 2 * (size_t)(2 * nmax + 1) + 36;
+    size_t b = (size_t)nmax;
     return d * 8 + ((i * 4 + 15) / 16) * 16 + ((b + 15) / 16) * 16;
 }
+__host__ __device__ inline size_t tab_smem_bytes(int n, int cap) {
+    return tab_smem_bytes_ex(n, (size_t)n * row_stride(cap), row_stride(cap));
+}
 
-__device__ inline void tab_carve(Tab& t, int n, int cap, unsigned char* smem) {
-    const int ldr = row_stride(cap);
-    t.n = n; t.ldr = ldr; t.ncol = 0; t.pivots = 0;
+__device__ inline void tab_carve_ex(Tab& t, int nmax, size_t tdoubles, int ldrmax, unsigned char* smem) {
+    tdoubles = (tdoubles + 1) & ~(size_t)1;
+    t.n = nmax; t.ldr = ldrmax; t.ncol = 0; t.pivots = 0;
     double* d = reinterpret_cast<double*>(smem);
-    t.T = d;      d += (size_t)n * ldr;
-    t.prow = d;   d += ldr;                 // 16-byte aligned: n*ldr is even
-    t.nbval = d;  d += ldr;
-    t.beta = d;   d += n;
-    t.l = d;      d += n;
-    t.u = d;      d += n;
+    t.T = d;      d += tdoubles;
+    t.prow = d;   d += ldrmax;              // 16-byte aligned: tdoubles and ldrmax are even
+    t.nbval = d;  d += ldrmax;
+    t.beta = d;   d += nmax;
+    t.l = d;      d += nmax;
+    t.u = d;      d += nmax;
+    t.rr = d;     d += nmax;
     t.red_d = d;  d += 36;
     int* ip = reinterpret_cast<int*>(d);
-    t.rowvar = ip; ip += n;
-    t.colvar = ip; ip += ldr;
-    t.rowof = ip;  ip += 2 * n + 1;
-    t.colof = ip;  ip += 2 * n + 1;
+    t.rowvar = ip; ip += nmax;
+    t.colvar = ip; ip += ldrmax;
+    t.rowof = ip;  ip += 2 * nmax + 1;
+    t.colof = ip;  ip += 2 * nmax + 1;
     t.red_i = ip;  ip += 36;
     const size_t ib = (size_t)(ip - reinterpret_cast<int*>(d));
     t.zst = reinterpret_cast<int8_t*>(reinterpret_cast<unsigned char*>(d) + ((ib * 4 + 15) / 16) * 16);
 }
+__device__ inline void tab_carve(Tab& t, int n, int cap, unsigned char* smem) {
+    tab_carve_ex(t, n, (size_t)n * row_stride(cap), row_stride(cap), smem);
+}
+// Shape of the next solve inside a carved workspace.
+__device__ inline void tab_shape(Tab& t, int n, int cap) { t.n = n; t.ldr = row_stride(cap); }
 
 // ---- block-wide reductions on non-negative doubles (+inf allowed, no NaN) ---------------------
 // The IEEE bit pattern of a non-negative double orders like an unsigned integer, so a 64-bit
@@ -246,6 +259,7 @@ __device__ inline void tab_start(Tab& t, const double* q, const double* z0) {
         const double zi = z0[i], zbi = zb[i];
         const double r = ((acc + q[i]) + zi) - zbi;
         row[n] = -r;                                      // the homotopy column goes last
+        t.rr[i] = r;
         t.beta[i] = zbi - zi;
         t.rowvar[i] = n + i;
         t.zst[i] = (zi <= t.l[i]) ? AT_L : (zi >= t.u[i]) ? AT_U : FLOATING;
@@ -264,7 +278,7 @@ __device__ inline void tab_start(Tab& t, const double* q, const double* z0) {
 }
 
 // ---- rank-1 pivot on the compact tableau (avi_scratch.jl:2-7) --------------------------
-__device__ inline void pivot(Tab& t, int rho, int c) {
+__device__ inline void pivot(Tab& t, int rho, int c, bool compact = true) {
     const int n = t.n, ldr = t.ldr, i = threadIdx.x;
     const int ncol = t.ncol;
     const int nce = (ncol + 1) & ~1;                      // even: the update runs two columns at a time
@@ -276,7 +290,7 @@ __device__ inline void pivot(Tab& t, int rho, int c) {
     const double d = (i < n) ? T[(size_t)i * ldr + c] : 0.0;
     const int lv = t.rowvar[rho];                         // leaving variable (read before the barrier)
     // A slack of a free variable never comes back: its column leaves the live range.
-    const bool dead = lv >= n && lv < 2 * n && is_free_var(t, lv - n);
+    const bool dead = compact && lv >= n && lv < 2 * n && is_free_var(t, lv - n);
     const int last = ncol - 1;
     QPN_SYNC();
     if (i < n) {
@@ -398,9 +412,86 @@ __device__ inline bool try_exchange(Tab& t, int var) {
     return true;
 }
 
-// ---- phase 1: bring interior / free variables into the basis ----------------------------
+// Largest |T[i][c]| over rows still holding the slack of a FREE variable (artificial whatever
+// the start point is).
+__device__ inline int best_free_row(const Tab& t, int c) {
+    const int i = threadIdx.x, n = t.n;
+    double a = 0.0; bool valid = false;
+    if (i < n) {
+        const int v = t.rowvar[i];
+        if (v >= n && v < 2 * n && is_free_var(t, v - n)) {
+            a = fabs(t.T[(size_t)i * t.ldr + c]);
+            valid = a > 0.0;
+        }
+    }
+    int idx;
+    block_argmax(t, valid, a, idx);
+    return (idx >= 0 && a > PIV_TOL) ? idx : -1;
+}
+
+// T[:, t] = B^-1 r rebuilt from the slack columns: the column of a nonbasic w_k is -B^-1 e_k, a
+// w_k basic in row rho means B^-1 e_k = -e_rho.  Sequential fma over k.  Needs every slack
+// column still in place (no compaction yet).  Ends with a barrier.
+__device__ inline void recompute_tcol(Tab& t) {
+    const int n = t.n, i = threadIdx.x;
+    const int tc = t.colof[2 * n];
+    if (i < n) {
+        double* row = t.T + (size_t)i * t.ldr;
+        double acc = 0.0;
+        for (int k = 0; k < n; ++k) {
+            const int ck = t.colof[n + k];
+            const double pik = ck >= 0 ? -row[ck] : (t.rowof[n + k] == i ? -1.0 : 0.0);
+            if (pik != 0.0) acc = fma(pik, t.rr[k], acc);
+        }
+        row[tc] = acc;
+    }
+    QPN_SYNC();
+}
+
+// Drop every dead column (slack of a free variable) from the live range at once.
+__device__ inline void compact_dead(Tab& t) {
+    const int n = t.n, i = threadIdx.x;
+    int* map = reinterpret_cast<int*>(t.prow);            // scratch: prow is free between pivots
+    if (i == 0) {
+        int nl = 0;
+        for (int j = 0; j < t.ncol; ++j) {
+            const int v = t.colvar[j];
+            if (v >= n && v < 2 * n && is_free_var(t, v - n)) t.colof[v] = -1;
+            else map[nl++] = j;
+        }
+        for (int d = 0; d < nl; ++d) {
+            const int sidx = map[d];
+            if (sidx != d) { const int v = t.colvar[sidx]; t.colvar[d] = v; t.nbval[d] = t.nbval[sidx]; t.colof[v] = d; }
+        }
+        t.red_i[32] = nl;
+    }
+    QPN_SYNC();
+    const int nl = t.red_i[32];
+    if (i < n) {
+        double* row = t.T + (size_t)i * t.ldr;
+        for (int d = 0; d < nl; ++d) { const int sidx = map[d]; if (sidx != d) row[d] = row[sidx]; }   // sidx >= d: in place
+    }
+    t.ncol = nl;
+    QPN_SYNC();
+}
+
+// ---- crash: bring interior / free variables into the basis ----------------------------
 __device__ inline void crash(Tab& t) {
     const int n = t.n;
+    // phase 0: free variables exchange against rows of free variables only.  Nothing here depends
+    // on the start point or on q (a shared matrix could do it once); the homotopy column is then
+    // rebuilt from r.
+    {
+        const int piv0 = t.pivots;
+        for (int i = 0; i < n; ++i) {
+            if (!is_free_var(t, i)) continue;
+            const int c = t.colof[i];
+            const int rho = best_free_row(t, c);
+            if (rho >= 0) { pivot(t, rho, c, false); set_zst(t, i, BASIC); }
+        }
+        if (t.pivots > piv0) { recompute_tcol(t); compact_dead(t); }
+    }
+    // phase 1: everything still floating, against any artificial row
     for (int i = 0; i < n; ++i) {
         if (t.zst[i] != FLOATING) continue;
         const int c = t.colof[i];

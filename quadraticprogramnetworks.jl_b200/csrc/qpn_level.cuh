@@ -5,14 +5,77 @@
 
 namespace qpn {
 
+// ---- plans: the instance-independent part of a solve, computed once per shared matrix ----------
+// Phase 0 of the crash (free variables against rows of free variables) depends only on the
+// matrix and on which variables are free.  plan_build_kernel runs it once and exports the
+// exchanged tableau (live columns only), B^-1 (to rebuild the homotopy column from an instance's
+// r), the basis maps and the original matrix in CSR (for r and for the final check).
+struct PlanDesc {
+    int n, ncol0, npiv0, tcol0;
+    const double* T0;        // n x row_stride(ncol0), row-major
+    const double* PT;        // n x n, PT[k*n + i] = (B^-1)[i][k]
+    const int* rowvar0;      // n
+    const int* colvar0;      // ncol0
+    const int* csr_ptr;      // n + 1
+    const int* csr_col;
+    const double* csr_val;
+    const int* cols;         // presolve plans: columns of A that are not structurally zero
+    int ncols;
+};
+
+__device__ inline double csr_row_dot(const PlanDesc& P, int i, const double* v) {
+    double acc = 0.0;
+    for (int k = P.csr_ptr[i]; k < P.csr_ptr[i + 1]; ++k) acc = fma(P.csr_val[k], v[P.csr_col[k]], acc);
+    return acc;
+}
+
+// Start of a solve from a plan: same state as tab_start + phase 0 + recompute_tcol + compact_dead.
+// t.l / t.u hold the bounds; zb: n doubles of scratch.  Ends with a barrier.
+__device__ inline void tab_start_plan(Tab& t, const PlanDesc& P, const double* q, const double* z0, double* zb) {
+    const int n = P.n, i = threadIdx.x;
+    tab_shape(t, n, P.ncol0);
+    const int ldr = t.ldr;
+    if (i < n) zb[i] = fmin(fmax(z0[i], t.l[i]), t.u[i]);
+    for (int e = i; e < n * ldr; e += blockDim.x) t.T[e] = P.T0[e];
+    for (int v = i; v <= 2 * n; v += blockDim.x) { t.rowof[v] = -1; t.colof[v] = -1; }
+    QPN_SYNC();
+    double zi = 0.0;
+    if (i < n) {
+        zi = z0[i];
+        t.rr[i] = ((csr_row_dot(P, i, zb) + q[i]) + zi) - zb[i];
+        t.zst[i] = (zi <= t.l[i]) ? AT_L : (zi >= t.u[i]) ? AT_U : FLOATING;
+    }
+    for (int j = i; j < P.ncol0; j += blockDim.x) {
+        const int v = P.colvar0[j];
+        t.colvar[j] = v; t.colof[v] = j; t.nbval[j] = v < n ? zb[v] : 0.0;
+    }
+    QPN_SYNC();
+    if (i < n) {
+        double acc = 0.0;
+        for (int k = 0; k < n; ++k) {
+            const double pik = P.PT[(size_t)k * n + i];
+            if (pik != 0.0) acc = fma(pik, t.rr[k], acc);
+        }
+        t.T[(size_t)i * ldr + P.tcol0] = acc;
+        const int rv = P.rowvar0[i];
+        t.rowvar[i] = rv; t.rowof[rv] = i;
+        t.beta[i] = rv < n ? zb[rv] : zb[i] - zi;
+        if (rv < n) t.zst[rv] = BASIC;            // after the barrier that followed the default marks
+    }
+    t.ncol = P.ncol0;
+    t.pivots = P.npiv0;
+    QPN_SYNC();
+}
+
 // Solve (M z + q) comp. l <= z <= u in the shared-memory tableau.  `build(t)` must fill
-// T[:, 0:n] with -M and end with a barrier; it is called twice (start and final check).
+// T[i][0:n] with -M[i][:] and end with a barrier; it is called twice (start and final check).
 // t.l / t.u hold the bounds, qs the vector q, zs the start on entry and z on exit.
-// code (optional, smem, n entries) receives the basis codes.  Same procedure as the oracle's single-instance solve.
+// code (optional, smem, n entries) receives the basis codes.  Same procedure as the oracle's
+// single-instance solve.
 template <class Build>
 __device__ inline int solve_avi_smem(Tab& t, int n, Build build, const double* qs, double* zs,
                                      int max_pivots, int8_t* code_out, int* pivots_acc) {
-    t.n = n;
+    tab_shape(t, n, n + 1);
     build(t);
     tab_start(t, qs, zs);
     double zi = 0.0; int8_t code = 0;
@@ -29,10 +92,28 @@ __device__ inline int solve_avi_smem(Tab& t, int n, Build build, const double* q
     return st;
 }
 
+// The same solve started from a plan; the final check uses the plan's CSR rows.
+__device__ inline int solve_avi_plan(Tab& t, const PlanDesc& P, const double* qs, double* zs, double* zb,
+                                     int max_pivots, int8_t* code_out, int* pivots_acc) {
+    const int n = P.n, i = threadIdx.x;
+    tab_start_plan(t, P, qs, zs, zb);
+    double zi = 0.0; int8_t code = 0;
+    int st = avi_pivot_run(t, max_pivots, &zi, &code);
+    *pivots_acc += t.pivots;
+    QPN_SYNC();
+    if (i < n) { zs[i] = zi; if (code_out) code_out[i] = code; }
+    QPN_SYNC();
+    int bad = 0;
+    if (i < n) bad = check_avi_index(csr_row_dot(P, i, zs) + qs[i], zi, t.l[i], t.u[i], 1e-6);
+    bad = QPN_SYNC_OR(bad);
+    if (st == ST_SUCCESS && bad) st = ST_FAILURE;
+    return st;
+}
+
 // ---- shared-memory plan of a GAVI solve ------------------------------------------------------
 struct GaviSmem {
     Tab t;
-    double *qs, *zs;      // n each (n = d1 + 2 d2)
+    double *qs, *zs, *zb; // n each (n = d1 + 2 d2)
     double *w;            // np
     double *z0;           // d1 + d2
     double *c, *s0;       // d2 each
@@ -42,30 +123,35 @@ struct GaviSmem {
 
 __host__ __device__ inline size_t gavi_extra_bytes(int d1, int d2, int np) {
     const size_t n = (size_t)d1 + 2 * d2, dz = (size_t)d1 + d2;
-    size_t dbl = 2 * n + np + dz + 2 * (size_t)d2;
+    size_t dbl = 3 * n + np + dz + 2 * (size_t)d2;
     size_t ints = dz + 2;
-    return dbl * 8 + ((ints * 4 + 7) / 8) * 8 + ((n + 7) / 8) * 8;
+    return dbl * 8 + ((ints * 4 + 15) / 16) * 16 + ((n + 15) / 16) * 16;
 }
+// Workspace shape of a GAVI solve without plans (tableau n x (n+1)).
 __host__ __device__ inline size_t gavi_smem_bytes(int d1, int d2, int np) {
     const int n = d1 + 2 * d2;
     return tab_smem_bytes(n, n + 1) + gavi_extra_bytes(d1, d2, np);
 }
 
-__device__ inline unsigned char* gavi_carve(GaviSmem& s, const GaviDesc& g, unsigned char* smem) {
+__device__ inline unsigned char* gavi_carve_extra(GaviSmem& s, const GaviDesc& g, unsigned char* p) {
     const int n = g.d1 + 2 * g.d2, dz = g.d1 + g.d2;
-    tab_carve(s.t, n, n + 1, smem);
-    unsigned char* p = smem + tab_smem_bytes(n, n + 1);
     double* d = reinterpret_cast<double*>(p);
     s.qs = d; d += n;
     s.zs = d; d += n;
+    s.zb = d; d += n;
     s.w = d;  d += g.np;
     s.z0 = d; d += dz;
     s.c = d;  d += g.d2;
     s.s0 = d; d += g.d2;
     s.cols = reinterpret_cast<int*>(d);
-    unsigned char* q = reinterpret_cast<unsigned char*>(d) + (((size_t)(dz + 2) * 4 + 7) / 8) * 8;
+    unsigned char* q = reinterpret_cast<unsigned char*>(d) + (((size_t)(dz + 2) * 4 + 15) / 16) * 16;
     s.code = reinterpret_cast<int8_t*>(q);
-    return q + (((size_t)n + 7) / 8) * 8;
+    return q + (((size_t)n + 15) / 16) * 16;
+}
+__device__ inline unsigned char* gavi_carve(GaviSmem& s, const GaviDesc& g, unsigned char* smem) {
+    const int n = g.d1 + 2 * g.d2;
+    tab_carve(s.t, n, n + 1, smem);
+    return gavi_carve_extra(s, g, smem + tab_smem_bytes(n, n + 1));
 }
 
 // s0 = A z0 + B w (c = B w kept).  Ends with a barrier.
@@ -84,9 +170,69 @@ __device__ inline void gavi_slack(GaviSmem& s, const GaviDesc& g, bool recompute
     QPN_SYNC();
 }
 
+// -M of the presolve AVI (avi.jl:79-99 as a lifted KKT system over the non-zero columns `cols`
+// of A):  M = [I -A' 0; A 0 -I; 0 I 0] over [z(k); lambda(d2); s(d2)].  Ends with a barrier.
+__device__ inline void build_presolve(Tab& tt, const GaviDesc& g, const int* cols, int k) {
+    const int ldr = tt.ldr, d2 = g.d2, pn = k + 2 * d2;
+    if (threadIdx.x < pn) {
+        double* row = tt.T + (size_t)threadIdx.x * ldr;
+        for (int j = 0; j < pn; ++j) row[j] = 0.0;
+    }
+    QPN_SYNC();
+    for (int e = threadIdx.x; e < k * d2; e += blockDim.x) {
+        const int a = e / d2, r = e - a * d2;
+        const double v = g.A[(size_t)cols[a] * d2 + r];
+        tt.T[(size_t)a * ldr + (k + r)] = v;         // -(-A')   row a, column k+r
+        tt.T[(size_t)(k + r) * ldr + a] = -v;        // -(A)     row k+r, column a
+    }
+    for (int e = threadIdx.x; e < k; e += blockDim.x) tt.T[(size_t)e * ldr + e] = -1.0;
+    for (int e = threadIdx.x; e < d2; e += blockDim.x) {
+        tt.T[(size_t)(k + e) * ldr + (k + d2 + e)] = 1.0;      // -(-1)  row k+e, column k+d2+e
+        tt.T[(size_t)(k + d2 + e) * ldr + (k + e)] = -1.0;     // -(+1)  row k+d2+e, column k+e
+    }
+    QPN_SYNC();
+}
+
+// -M of the lifted AVI of `convert` (avi.jl:113-128): M = [M 0; A -I; 0 I 0].  Ends with a barrier.
+__device__ inline void build_lifted(Tab& tt, const GaviDesc& g) {
+    const int ldr = tt.ldr, r = threadIdx.x, d1 = g.d1, d2 = g.d2, dz = d1 + d2, n = d1 + 2 * d2;
+    if (r < n) {
+        double* row = tt.T + (size_t)r * ldr;
+        if (r < d1) {
+            for (int j = 0; j < dz; ++j) row[j] = -g.M[(size_t)j * d1 + r];
+            for (int j = dz; j < n; ++j) row[j] = 0.0;
+        } else if (r < dz) {
+            for (int j = 0; j < dz; ++j) row[j] = -g.A[(size_t)j * d2 + (r - d1)];
+            for (int j = dz; j < n; ++j) row[j] = (j - dz == r - d1) ? 1.0 : 0.0;
+        } else {
+            for (int j = 0; j < n; ++j) row[j] = (j - d1 == r - dz) ? -1.0 : 0.0;
+        }
+    }
+    QPN_SYNC();
+}
+
+// Non-zero columns of A into cols[0..k), k into cols[dz].  Ends with a barrier.
+__device__ inline void find_cols(const GaviDesc& g, int* cols) {
+    const int dz = g.d1 + g.d2, d2 = g.d2, i = threadIdx.x;
+    for (int j = i; j < dz; j += blockDim.x) {
+        bool nz = false;
+        for (int r = 0; r < d2; ++r) nz |= (g.A[(size_t)j * d2 + r] != 0.0);
+        cols[j] = nz ? 1 : 0;
+    }
+    QPN_SYNC();
+    if (i == 0) {
+        int k = 0;
+        for (int j = 0; j < dz; ++j) if (cols[j]) cols[k++] = j;
+        cols[dz] = k;
+    }
+    QPN_SYNC();
+}
+
 // solve_gavi (avi.jl:101-111) for the instance whose w and z0 are already in s.w / s.z0.
+// planA (lifted AVI) / planB (presolve AVI) may be null: the instance then runs phase 0 itself.
 // On return s.zs holds the lifted solution [z1; z2; s] and s.code the basis codes.
-__device__ inline int gavi_solve_smem(GaviSmem& s, const GaviDesc& g, int presolve, int max_pivots, int* pivots) {
+__device__ inline int gavi_solve_smem(GaviSmem& s, const GaviDesc& g, const PlanDesc* planA, const PlanDesc* planB,
+                                      int presolve, int max_pivots, int* pivots) {
     const int d1 = g.d1, d2 = g.d2, dz = d1 + d2, n = d1 + 2 * d2, i = threadIdx.x;
     Tab& t = s.t;
     gavi_slack(s, g, true);
@@ -98,26 +244,18 @@ __device__ inline int gavi_solve_smem(GaviSmem& s, const GaviDesc& g, int presol
         if (infeasible) {
             // find_closest_feasible! (avi.jl:79-99): min |z - z0|^2 s.t. l2 - Bw <= A z <= u2 - Bw over
             // the columns of A that are not structurally zero, as the lifted KKT AVI.
-            for (int j = i; j < dz; j += blockDim.x) {
-                bool nz = false;
-                for (int r = 0; r < d2; ++r) nz |= (g.A[(size_t)j * d2 + r] != 0.0);
-                s.cols[j] = nz ? 1 : 0;
-            }
-            QPN_SYNC();
-            if (i == 0) {
-                int k = 0;
-                for (int j = 0; j < dz; ++j) if (s.cols[j]) s.cols[k++] = j;
-                s.cols[dz] = k;
-            }
-            QPN_SYNC();
-            const int k = s.cols[dz], pn = k + 2 * d2;
+            const int* cols;
+            int k;
+            if (planB) { cols = planB->cols; k = planB->ncols; }
+            else { find_cols(g, s.cols); cols = s.cols; k = s.cols[dz]; }
+            const int pn = k + 2 * d2;
             if (i < pn) {
-                if (i < k) { s.qs[i] = -s.z0[s.cols[i]]; s.zs[i] = s.z0[s.cols[i]]; t.l[i] = -QPN_INF; t.u[i] = QPN_INF; }
+                if (i < k) { s.qs[i] = -s.z0[cols[i]]; s.zs[i] = s.z0[cols[i]]; t.l[i] = -QPN_INF; t.u[i] = QPN_INF; }
                 else if (i < k + d2) {
                     const int r = i - k;
                     double full = 0.0, part = 0.0;
                     for (int j = 0; j < dz; ++j) full = fma(g.A[(size_t)j * d2 + r], s.z0[j], full);
-                    for (int a = 0; a < k; ++a) part = fma(g.A[(size_t)s.cols[a] * d2 + r], s.z0[s.cols[a]], part);
+                    for (int a = 0; a < k; ++a) part = fma(g.A[(size_t)cols[a] * d2 + r], s.z0[cols[a]], part);
                     s.qs[i] = (full - part) + s.c[r];
                     s.zs[i] = 0.0; t.l[i] = -QPN_INF; t.u[i] = QPN_INF;
                 } else {
@@ -126,29 +264,11 @@ __device__ inline int gavi_solve_smem(GaviSmem& s, const GaviDesc& g, int presol
                 }
             }
             QPN_SYNC();
-            auto build = [&](Tab& tt) {
-                const int ldr = tt.ldr;
-                if (threadIdx.x < pn) {
-                    double* row = tt.T + (size_t)threadIdx.x * ldr;
-                    for (int j = 0; j < pn; ++j) row[j] = 0.0;
-                }
-                QPN_SYNC();
-                for (int e = threadIdx.x; e < k * d2; e += blockDim.x) {
-                    const int a = e / d2, r = e - a * d2;
-                    const double v = g.A[(size_t)s.cols[a] * d2 + r];
-                    tt.T[(size_t)a * ldr + (k + r)] = v;         // -(-A')   row a, column k+r
-                    tt.T[(size_t)(k + r) * ldr + a] = -v;        // -(A)     row k+r, column a
-                }
-                for (int e = threadIdx.x; e < k; e += blockDim.x) tt.T[(size_t)e * ldr + e] = -1.0;
-                for (int e = threadIdx.x; e < d2; e += blockDim.x) {
-                    tt.T[(size_t)(k + e) * ldr + (k + d2 + e)] = 1.0;      // -(-1)  row k+e, column k+d2+e
-                    tt.T[(size_t)(k + d2 + e) * ldr + (k + e)] = -1.0;     // -(+1)  row k+d2+e, column k+e
-                }
-                QPN_SYNC();
-            };
-            const int pst = solve_avi_smem(t, pn, build, s.qs, s.zs, 50 * pn + 100, nullptr, pivots);
+            int pst;
+            if (planB) pst = solve_avi_plan(t, *planB, s.qs, s.zs, s.zb, 50 * pn + 100, nullptr, pivots);
+            else pst = solve_avi_smem(t, pn, [&](Tab& tt) { build_presolve(tt, g, cols, k); }, s.qs, s.zs, 50 * pn + 100, nullptr, pivots);
             QPN_SYNC();
-            if (pst == ST_SUCCESS && i < k) s.z0[s.cols[i]] = s.zs[i];
+            if (pst == ST_SUCCESS && i < k) s.z0[cols[i]] = s.zs[i];
             QPN_SYNC();
             gavi_slack(s, g, false);
         }
@@ -168,23 +288,8 @@ __device__ inline int gavi_solve_smem(GaviSmem& s, const GaviDesc& g, int presol
         s.zs[i] = i < dz ? s.z0[i] : s.s0[i - dz];
     }
     QPN_SYNC();
-    auto build = [&](Tab& tt) {
-        const int ldr = tt.ldr, r = threadIdx.x;
-        if (r < n) {                                         // thread r writes row r of -[M 0; A -I; 0 I 0]
-            double* row = tt.T + (size_t)r * ldr;
-            if (r < d1) {
-                for (int j = 0; j < dz; ++j) row[j] = -g.M[(size_t)j * d1 + r];
-                for (int j = dz; j < n; ++j) row[j] = 0.0;
-            } else if (r < dz) {
-                for (int j = 0; j < dz; ++j) row[j] = -g.A[(size_t)j * d2 + (r - d1)];
-                for (int j = dz; j < n; ++j) row[j] = (j - dz == r - d1) ? 1.0 : 0.0;
-            } else {
-                for (int j = 0; j < n; ++j) row[j] = (j - d1 == r - dz) ? -1.0 : 0.0;
-            }
-        }
-        QPN_SYNC();
-    };
-    return solve_avi_smem(t, n, build, s.qs, s.zs, max_pivots, s.code, pivots);
+    if (planA) return solve_avi_plan(t, *planA, s.qs, s.zs, s.zb, max_pivots, s.code, pivots);
+    return solve_avi_smem(t, n, [&](Tab& tt) { build_lifted(tt, g); }, s.qs, s.zs, max_pivots, s.code, pivots);
 }
 
 __global__ void gavi_solve_kernel(GaviDesc g, int batch, const double* __restrict__ w,
@@ -195,17 +300,13 @@ __global__ void gavi_solve_kernel(GaviDesc g, int batch, const double* __restric
     extern __shared__ __align__(16) unsigned char smem[];
     const int b = blockIdx.x, i = threadIdx.x;
     const int dz = g.d1 + g.d2, n = g.d1 + 2 * g.d2;
-#ifdef QPN_ZERO_SMEM
-    for (size_t e = i; e < gavi_smem_bytes(g.d1, g.d2, g.np) / 8; e += blockDim.x) reinterpret_cast<double*>(smem)[e] = 0.0;
-    QPN_SYNC();
-#endif
     GaviSmem s;
     gavi_carve(s, g, smem);
     for (int j = i; j < g.np; j += blockDim.x) s.w[j] = w[(size_t)b * g.np + j];
     for (int j = i; j < dz; j += blockDim.x) s.z0[j] = z0[(size_t)b * dz + j];
     QPN_SYNC();
     int piv = 0;
-    const int st = gavi_solve_smem(s, g, presolve, max_pivots, &piv);
+    const int st = gavi_solve_smem(s, g, nullptr, nullptr, presolve, max_pivots, &piv);
     QPN_SYNC();
     if (i < dz) z_out[(size_t)b * dz + i] = s.zs[i];
     if (i < n) {
@@ -213,6 +314,90 @@ __global__ void gavi_solve_kernel(GaviDesc g, int batch, const double* __restric
         if (basis_out) basis_out[(size_t)b * n + i] = s.code[i];
     }
     if (i == 0) { status_out[b] = st; pivots_out[b] = piv; }
+}
+
+// ---- plan construction: one CTA, once per shared matrix ---------------------------------------
+// kind 0: lifted AVI of the GAVI; kind 1: its presolve AVI.  Buffers are sized by the host for the
+// worst case (T0: n x row_stride(n+1), CSR: n*n entries).  hdr: [ncol0, npiv0, tcol0, ncols].
+__global__ void plan_build_kernel(GaviDesc g, int kind, double* __restrict__ T0, double* __restrict__ PT,
+                                  int* __restrict__ rowvar0, int* __restrict__ colvar0, int* __restrict__ csr_ptr,
+                                  int* __restrict__ csr_col, double* __restrict__ csr_val, int* __restrict__ cols_out,
+                                  int* __restrict__ hdr) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int i = threadIdx.x, d1 = g.d1, d2 = g.d2, dz = d1 + d2;
+    GaviSmem s;
+    gavi_carve(s, g, smem);
+    Tab& t = s.t;
+    int n, k = 0;
+    if (kind == 1) {
+        find_cols(g, s.cols);
+        k = s.cols[dz];
+        n = k + 2 * d2;
+        for (int j = i; j < k; j += blockDim.x) cols_out[j] = s.cols[j];
+        if (i < n) {
+            const bool fr = i < k + d2;
+            t.l[i] = fr ? -QPN_INF : g.l2[i - k - d2];
+            t.u[i] = fr ? QPN_INF : g.u2[i - k - d2];
+        }
+    } else {
+        n = d1 + 2 * d2;
+        if (i < n) {
+            t.l[i] = i < d1 ? g.l1[i] : i < dz ? -QPN_INF : g.l2[i - dz];
+            t.u[i] = i < d1 ? g.u1[i] : i < dz ? QPN_INF : g.u2[i - dz];
+        }
+    }
+    if (i < n) { s.qs[i] = 0.0; s.zs[i] = 0.0; }
+    QPN_SYNC();
+    tab_shape(t, n, n + 1);
+    if (kind == 1) build_presolve(t, g, s.cols, k); else build_lifted(t, g);
+    // the original matrix in CSR (rows ascending in the column index)
+    int* cnt = reinterpret_cast<int*>(s.zb);
+    if (i < n) {
+        const double* row = t.T + (size_t)i * t.ldr;
+        int c = 0;
+        for (int j = 0; j < n; ++j) c += (row[j] != 0.0);
+        cnt[i] = c;
+    }
+    QPN_SYNC();
+    if (i == 0) {
+        int acc = 0;
+        for (int r = 0; r < n; ++r) { csr_ptr[r] = acc; acc += cnt[r]; }
+        csr_ptr[n] = acc;
+    }
+    QPN_SYNC();
+    if (i < n) {
+        const double* row = t.T + (size_t)i * t.ldr;
+        int o = csr_ptr[i];
+        for (int j = 0; j < n; ++j) if (row[j] != 0.0) { csr_col[o] = j; csr_val[o] = -row[j]; ++o; }
+    }
+    QPN_SYNC();
+    tab_start(t, s.qs, s.zs);
+    // phase 0 exactly as crash() runs it
+    for (int v = 0; v < n; ++v) {
+        if (!is_free_var(t, v)) continue;
+        const int c = t.colof[v];
+        const int rho = best_free_row(t, c);
+        if (rho >= 0) { pivot(t, rho, c, false); set_zst(t, v, BASIC); }
+    }
+    // B^-1 from the slack columns (see recompute_tcol)
+    if (i < n) {
+        const double* row = t.T + (size_t)i * t.ldr;
+        for (int kk = 0; kk < n; ++kk) {
+            const int ck = t.colof[n + kk];
+            PT[(size_t)kk * n + i] = ck >= 0 ? -row[ck] : (t.rowof[n + kk] == i ? -1.0 : 0.0);
+        }
+    }
+    const int npiv0 = t.pivots;
+    QPN_SYNC();
+    compact_dead(t);
+    const int ncol0 = t.ncol, ldr0 = row_stride(ncol0);
+    if (i < n) {
+        const double* row = t.T + (size_t)i * t.ldr;
+        for (int j = 0; j < ldr0; ++j) T0[(size_t)i * ldr0 + j] = j < ncol0 ? row[j] : 0.0;
+        rowvar0[i] = t.rowvar[i];
+    }
+    for (int j = i; j < ncol0; j += blockDim.x) colvar0[j] = t.colvar[j];
+    if (i == 0) { hdr[0] = ncol0; hdr[1] = npiv0; hdr[2] = t.colof[2 * n]; hdr[3] = k; }
 }
 
 // ---- verify_solution (qp_processing.jl:57-149) ---------------------------------------------------
@@ -504,10 +689,30 @@ struct LevelDesc {
     int max_nd, max_m;      // over players
     int nd_total;           // sum of nd over players
     int lam_total;          // sum of m over players
+    // plans (resident levels only) and the workspace shape they allow
+    int has_plans;
+    PlanDesc planA, planB;  // lifted AVI / presolve AVI
+    int t_doubles, ldr_max; // tableau buffer (doubles) and longest row of any solve in the kernel
 };
 
+// Fills t_doubles / ldr_max: the largest (rows x row stride) among the solves the level kernel runs.
+__host__ inline void level_workspace_shape(LevelDesc& lv) {
+    const int n = lv.g.d1 + 2 * lv.g.d2;
+    int ldr = row_stride(lv.max_m + 1);
+    size_t td = (size_t)lv.max_m * ldr;                                   // verify_solution's fallback
+    auto take = [&](int rows, int cap) {
+        const int l = row_stride(cap);
+        if (l > ldr) ldr = l;
+        if ((size_t)rows * l > td) td = (size_t)rows * l;
+    };
+    if (lv.has_plans) { take(lv.planA.n, lv.planA.ncol0); take(lv.planB.n, lv.planB.ncol0); }
+    else take(n, n + 1);
+    lv.t_doubles = (int)td; lv.ldr_max = ldr;
+}
+
 __host__ __device__ inline size_t level_smem_bytes(const LevelDesc& lv) {
-    return gavi_smem_bytes(lv.g.d1, lv.g.d2, lv.g.np) + verify_smem_bytes(lv.max_nd, lv.max_m) +
+    return tab_smem_bytes_ex(lv.g.d1 + 2 * lv.g.d2, (size_t)lv.t_doubles, lv.ldr_max) + gavi_extra_bytes(lv.g.d1, lv.g.d2, lv.g.np) +
+           verify_smem_bytes(lv.max_nd, lv.max_m) +
            8 * (2 * (size_t)lv.nv + (size_t)(lv.nproj > 0 ? lv.nproj : 1) + (size_t)lv.nd_total + (size_t)lv.lam_total);
 }
 
@@ -520,7 +725,9 @@ __global__ void level_equilibrium_kernel(LevelDesc lv, int batch, const double* 
     extern __shared__ __align__(16) unsigned char smem[];
     const int b = blockIdx.x, i = threadIdx.x, nv = lv.nv;
     GaviSmem gs;
-    unsigned char* p = gavi_carve(gs, lv.g, smem);
+    const int n_level = lv.g.d1 + 2 * lv.g.d2;
+    tab_carve_ex(gs.t, n_level, (size_t)lv.t_doubles, lv.ldr_max, smem);
+    unsigned char* p = gavi_carve_extra(gs, lv.g, smem + tab_smem_bytes_ex(n_level, (size_t)lv.t_doubles, lv.ldr_max));
     VerifySmem vs;
     verify_carve(vs, lv.max_nd, lv.max_m, p);
     double* xs = reinterpret_cast<double*>(p + verify_smem_bytes(lv.max_nd, lv.max_m));
@@ -530,7 +737,6 @@ __global__ void level_equilibrium_kernel(LevelDesc lv, int batch, const double* 
     double* ax_all = qt_all + lv.nd_total; // lam_total
     for (int j = i; j < nv; j += blockDim.x) xs[j] = x_init[(size_t)b * nv + j];
     QPN_SYNC();
-    const int n_level = lv.g.d1 + 2 * lv.g.d2;
     const int max_piv = 50 * n_level + 100;
     const int rows_all = lv.nd_total + lv.lam_total;
     int solved = 0, piv = 0, iters = 0;
@@ -609,7 +815,7 @@ __global__ void level_equilibrium_kernel(LevelDesc lv, int batch, const double* 
         for (int j = i; j < lv.g.d1 + lv.g.d2; j += blockDim.x) gs.z0[j] = j < lv.nd_level ? xs[lv.dec[j]] : 0.0;
         QPN_SYNC();
         gs.t.n = n_level;
-        const int st = gavi_solve_smem(gs, lv.g, presolve, max_piv, &piv);
+        const int st = gavi_solve_smem(gs, lv.g, lv.has_plans ? &lv.planA : nullptr, lv.has_plans ? &lv.planB : nullptr, presolve, max_piv, &piv);
         QPN_SYNC();
         if (st != ST_SUCCESS) break;
         for (int j = i; j < nv; j += blockDim.x) xn[j] = xs[j];

@@ -214,3 +214,36 @@ def test_level_equilibrium_robust_avoid_bottom(engine):
         if ro["solved"]:
             assert np.array_equal(ro["lam"], ret["lam"][k])
     assert ret["solved"].all()
+
+
+def test_resident_level_with_plans_matches_oracle(engine):
+    """qpn_level_upload precomputes the instance-independent crash prefix (plans); results must
+    still equal the oracle, which runs every pivot per instance."""
+    import qpn_b200
+    rng = np.random.default_rng(19)
+    # four_player: inside the box (no presolve) and outside (presolve plan exercised)
+    net = examples.four_player_matrix_game()
+    g, dec, par = qpn_ref.level_gavi(net, net.depth[1], {})
+    proj = rng.normal(size=(4, 8))
+    views = [qpn_ref.node_view(net, p) for p in net.depth[1]]
+    lv = qpn_b200.ResidentLevel(engine, qpn_b200.LevelArrays(8, views, g, dec, par, max_iters=150, proj=proj))
+    X = np.vstack([rng.uniform(-5, 5, (96, 8)), rng.uniform(-8, 8, (96, 8))])
+    ret = lv.solve(X)
+    L = cport.Level(8, views, g, dec, par, 150, proj)
+    ro = L.solve(X)
+    assert ro["solved"].all() and (ro["pivots"] != ro["pivots"][0]).any()
+    for k in ("x", "iters", "pivots", "lam"):
+        assert np.array_equal(ret[k], ro[k]), k
+    assert np.array_equal(ret["solved"].astype(bool), ro["solved"])
+    lv.release()
+    # robust_avoid bottom level: LP-like nodes, presolve on every instance
+    net, X = problems.ra_inits(rng, 160)
+    g, dec, par = qpn_ref.level_gavi(net, net.depth[3], {})
+    views = [qpn_ref.node_view(net, p) for p in net.depth[3]]
+    lv = qpn_b200.ResidentLevel(engine, qpn_b200.LevelArrays(net.n_vars, views, g, dec, par, max_iters=150, proj=None))
+    ret = lv.solve(X)
+    ro = cport.Level(net.n_vars, views, g, dec, par, 150, None).solve(X)
+    assert ro["solved"].all()
+    for k in ("x", "iters", "pivots", "lam"):
+        assert np.array_equal(ret[k], ro[k]), k
+    lv.release()
