@@ -39,10 +39,10 @@ enum : int { ST_SUCCESS = 1, ST_RAY_TERM = 2, ST_MAX_ITERS = 3, ST_FAILURE = 4 }
 // recorded in a host-mapped buffer (16 ints per CTA), readable after a device fault.
 #ifdef QPN_TRACE
 __device__ int* qpn_trace_ptr = nullptr;
-__device__ inline void qpn_dbg_record(int slot, int value) {
+__device__ __forceinline__ void qpn_dbg_record(int slot, int value) {
     if (qpn_trace_ptr) ((volatile int*)qpn_trace_ptr)[blockIdx.x * 16 + slot] = value;
 }
-__device__ inline void qpn_dbg_presync(int line) {
+__device__ __forceinline__ void qpn_dbg_presync(int line) {
     __shared__ int dbg_line[32];
     const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const unsigned am = __activemask();
@@ -65,85 +65,81 @@ __device__ inline void qpn_dbg_presync(int line) {
 
 // Row stride for `cols` columns: even (rows stay 16-byte aligned) with ldr/2 odd, so that the
 // 32 lanes of a warp, each reading 16 bytes of its own row, fall into distinct bank groups.
-__host__ __device__ inline int row_stride(int cols) {
+__host__ __device__ __forceinline__ int row_stride(int cols) {
     int e = (cols + 1) & ~1;
     if ((e >> 1) % 2 == 0) e += 2;
     return e;
 }
 
-// Shared-memory workspace of one instance (sized for n rows and cap >= n+1 columns).
-struct Tab {
-    int n;          // rows
-    int ldr;        // row stride of T in doubles
-    int ncol;       // live columns [0, ncol); uniform across the CTA
-    int pivots;     // uniform across the CTA
-    double* T;      // n x ldr, row-major: T[i][j] = d(basic_i)/d(nonbasic_j), negated
-    double* beta;   // n     values of the basic variables
-    double* nbval;  // ldr   values of the nonbasic variables
-    double* prow;   // ldr   scaled pivot row
-    double* l;      // n
-    double* u;      // n
-    double* rr;     // n     normal-map residual r at the start (rebuilds the homotopy column)
-    int* rowvar;    // n      variable basic in row i      (z_i = i, w_i = n+i, t = 2n)
-    int* colvar;    // ldr    variable nonbasic in column j
-    int* rowof;     // 2n+1   row of a variable or -1
-    int* colof;     // 2n+1   column of a variable or -1 (also -1 once its column is dead)
-    int8_t* zst;    // n      AT_L / AT_U / FLOATING / BASIC
-    double* red_d;  // 36: per-warp partials [0,32) + broadcast slots
-    int* red_i;     // 36
-};
+// All dynamic shared memory of every kernel in this library.
+extern __shared__ __align__(16) unsigned char qpn_smem[];
 
 // Bytes of a workspace with room for `nmax` rows, a tableau buffer of `tdoubles` doubles and
 // rows of up to `ldrmax` doubles.  One workspace serves several solves of different shapes
 // (tab_shape) inside one kernel.
-__host__ __device__ inline size_t tab_smem_bytes_ex(int nmax, size_t tdoubles, int ldrmax) {
+__host__ __device__ __forceinline__ size_t tab_smem_bytes_ex(int nmax, size_t tdoubles, int ldrmax) {
     tdoubles = (tdoubles + 1) & ~(size_t)1;
     size_t d = tdoubles + 2 * (size_t)ldrmax + 4 * (size_t)nmax + 36;
     size_t i = (size_t)nmax + ldrmax + 2 * (size_t)(2 * nmax + 1) + 36;
     size_t b = (size_t)nmax;
     return d * 8 + ((i * 4 + 15) / 16) * 16 + ((b + 15) / 16) * 16;
 }
-__host__ __device__ inline size_t tab_smem_bytes(int n, int cap) {
+__host__ __device__ __forceinline__ size_t tab_smem_bytes(int n, int cap) {
     return tab_smem_bytes_ex(n, (size_t)n * row_stride(cap), row_stride(cap));
 }
 
-__device__ inline void tab_carve_ex(Tab& t, int nmax, size_t tdoubles, int ldrmax, unsigned char* smem) {
-    tdoubles = (tdoubles + 1) & ~(size_t)1;
+// Shared-memory workspace of one instance.  Only a base offset and three sizes are stored; the
+// arrays are addressed by offset arithmetic (keeping a dozen pointers alive cost the level kernel
+// a local-memory stack frame and a load per access).
+struct Tab {
+    int base;       // byte offset of the workspace in qpn_smem
+    int nmax, ldrmax, td;   // capacity: rows, longest row, tableau doubles (even)
+    int n;          // rows of the current solve
+    int ldr;        // row stride of T in doubles for the current solve
+    int ncol;       // live columns [0, ncol); uniform across the CTA
+    int pivots;     // uniform across the CTA
+
+    __device__ __forceinline__ double* dbl(int off) const { return reinterpret_cast<double*>(qpn_smem + base) + off; }
+    __device__ __forceinline__ double* T() const { return dbl(0); }                       // n x ldr, row-major, negated
+    __device__ __forceinline__ double* prow() const { return dbl(td); }                   // ldr  scaled pivot row
+    __device__ __forceinline__ double* nbval() const { return dbl(td + ldrmax); }         // ldr  nonbasic values
+    __device__ __forceinline__ double* beta() const { return dbl(td + 2 * ldrmax); }      // n    basic values
+    __device__ __forceinline__ double* l() const { return dbl(td + 2 * ldrmax + nmax); }
+    __device__ __forceinline__ double* u() const { return dbl(td + 2 * ldrmax + 2 * nmax); }
+    __device__ __forceinline__ double* rr() const { return dbl(td + 2 * ldrmax + 3 * nmax); }   // residual r at the start
+    __device__ __forceinline__ double* red_d() const { return dbl(td + 2 * ldrmax + 4 * nmax); }  // 36
+    __device__ __forceinline__ int* ints() const { return reinterpret_cast<int*>(dbl(td + 2 * ldrmax + 4 * nmax + 36)); }
+    __device__ __forceinline__ int* rowvar() const { return ints(); }                     // n     z_i = i, w_i = n+i, t = 2n
+    __device__ __forceinline__ int* colvar() const { return ints() + nmax; }              // ldr
+    __device__ __forceinline__ int* rowof() const { return ints() + nmax + ldrmax; }      // 2n+1  row of a variable or -1
+    __device__ __forceinline__ int* colof() const { return ints() + nmax + ldrmax + 2 * nmax + 1; }   // 2n+1 (-1: basic or dead)
+    __device__ __forceinline__ int* red_i() const { return ints() + nmax + ldrmax + 2 * (2 * nmax + 1); }   // 36
+    __device__ __forceinline__ int8_t* zst() const {                                      // n  AT_L / AT_U / FLOATING / BASIC
+        const int ib = nmax + ldrmax + 2 * (2 * nmax + 1) + 36;
+        return reinterpret_cast<int8_t*>(reinterpret_cast<unsigned char*>(ints()) + ((ib * 4 + 15) / 16) * 16);
+    }
+};
+
+__device__ __forceinline__ void tab_carve_ex(Tab& t, int nmax, size_t tdoubles, int ldrmax, int base_off) {
+    t.base = base_off; t.nmax = nmax; t.ldrmax = ldrmax; t.td = (int)((tdoubles + 1) & ~(size_t)1);
     t.n = nmax; t.ldr = ldrmax; t.ncol = 0; t.pivots = 0;
-    double* d = reinterpret_cast<double*>(smem);
-    t.T = d;      d += tdoubles;
-    t.prow = d;   d += ldrmax;              // 16-byte aligned: tdoubles and ldrmax are even
-    t.nbval = d;  d += ldrmax;
-    t.beta = d;   d += nmax;
-    t.l = d;      d += nmax;
-    t.u = d;      d += nmax;
-    t.rr = d;     d += nmax;
-    t.red_d = d;  d += 36;
-    int* ip = reinterpret_cast<int*>(d);
-    t.rowvar = ip; ip += nmax;
-    t.colvar = ip; ip += ldrmax;
-    t.rowof = ip;  ip += 2 * nmax + 1;
-    t.colof = ip;  ip += 2 * nmax + 1;
-    t.red_i = ip;  ip += 36;
-    const size_t ib = (size_t)(ip - reinterpret_cast<int*>(d));
-    t.zst = reinterpret_cast<int8_t*>(reinterpret_cast<unsigned char*>(d) + ((ib * 4 + 15) / 16) * 16);
 }
-__device__ inline void tab_carve(Tab& t, int n, int cap, unsigned char* smem) {
-    tab_carve_ex(t, n, (size_t)n * row_stride(cap), row_stride(cap), smem);
+__device__ __forceinline__ void tab_carve(Tab& t, int n, int cap, int base_off) {
+    tab_carve_ex(t, n, (size_t)n * row_stride(cap), row_stride(cap), base_off);
 }
 // Shape of the next solve inside a carved workspace.
-__device__ inline void tab_shape(Tab& t, int n, int cap) { t.n = n; t.ldr = row_stride(cap); }
+__device__ __forceinline__ void tab_shape(Tab& t, int n, int cap) { t.n = n; t.ldr = row_stride(cap); }
 
 // ---- block-wide reductions on non-negative doubles (+inf allowed, no NaN) ---------------------
 // The IEEE bit pattern of a non-negative double orders like an unsigned integer, so a 64-bit
 // max / min is two 32-bit REDUX instructions instead of a five-round shuffle butterfly.
-__device__ inline void warp_max_bits(unsigned& hi, unsigned& lo) {
+__device__ __forceinline__ void warp_max_bits(unsigned& hi, unsigned& lo) {
     const unsigned full = 0xffffffffu;
     const unsigned mh = __reduce_max_sync(full, hi);
     const unsigned ml = __reduce_max_sync(full, hi == mh ? lo : 0u);
     hi = mh; lo = ml;
 }
-__device__ inline void warp_min_bits(unsigned& hi, unsigned& lo) {
+__device__ __forceinline__ void warp_min_bits(unsigned& hi, unsigned& lo) {
     const unsigned full = 0xffffffffu;
     const unsigned mh = __reduce_min_sync(full, hi);
     const unsigned ml = __reduce_min_sync(full, hi == mh ? lo : 0xffffffffu);
@@ -152,7 +148,7 @@ __device__ inline void warp_min_bits(unsigned& hi, unsigned& lo) {
 
 // arg-max over the rows: larger value wins, ties -> lower row.  `valid` lanes carry v >= 0.
 // Every thread receives (v, idx); idx = -1 when no lane is valid.
-__device__ inline void block_argmax(const Tab& t, bool valid, double& v, int& idx) {
+__device__ __forceinline__ void block_argmax(const Tab& t, bool valid, double& v, int& idx) {
     const unsigned full = 0xffffffffu;
     unsigned hi = valid ? (unsigned)__double2hiint(v) : 0u, lo = valid ? (unsigned)__double2loint(v) : 0u;
     const unsigned mine_hi = hi, mine_lo = lo;
@@ -164,11 +160,11 @@ __device__ inline void block_argmax(const Tab& t, bool valid, double& v, int& id
     if (nw > 1) {
         const int w = threadIdx.x >> 5;
         QPN_SYNC();                        // red_* free for reuse
-        if ((threadIdx.x & 31) == 0) { t.red_d[w] = wv; t.red_i[w] = widx; }
+        if ((threadIdx.x & 31) == 0) { t.red_d()[w] = wv; t.red_i()[w] = widx; }
         QPN_SYNC();
-        wv = t.red_d[0]; widx = t.red_i[0];
+        wv = t.red_d()[0]; widx = t.red_i()[0];
         for (int k = 1; k < nw; ++k) {
-            const double v2 = t.red_d[k]; const int i2 = t.red_i[k];
+            const double v2 = t.red_d()[k]; const int i2 = t.red_i()[k];
             if (i2 >= 0 && (widx < 0 || v2 > wv)) { wv = v2; widx = i2; }      // warps are in row order: ties keep the lower row
         }
     }
@@ -177,7 +173,7 @@ __device__ inline void block_argmax(const Tab& t, bool valid, double& v, int& id
 
 // Same reduction when the candidates are not the tableau rows: every thread offers (v >= 0, idx);
 // larger v wins, ties -> lower idx.
-__device__ inline void block_argmax_idx(const Tab& t, bool valid, double& v, int& idx) {
+__device__ __forceinline__ void block_argmax_idx(const Tab& t, bool valid, double& v, int& idx) {
     const unsigned full = 0xffffffffu;
     unsigned hi = valid ? (unsigned)__double2hiint(v) : 0u, lo = valid ? (unsigned)__double2loint(v) : 0u;
     const unsigned mine_hi = hi, mine_lo = lo;
@@ -190,18 +186,18 @@ __device__ inline void block_argmax_idx(const Tab& t, bool valid, double& v, int
     if (nw > 1) {
         const int w = threadIdx.x >> 5;
         QPN_SYNC();
-        if ((threadIdx.x & 31) == 0) { t.red_d[w] = wv; t.red_i[w] = widx; }
+        if ((threadIdx.x & 31) == 0) { t.red_d()[w] = wv; t.red_i()[w] = widx; }
         QPN_SYNC();
-        wv = t.red_d[0]; widx = t.red_i[0];
+        wv = t.red_d()[0]; widx = t.red_i()[0];
         for (int k = 1; k < nw; ++k) {
-            const double v2 = t.red_d[k]; const int i2 = t.red_i[k];
+            const double v2 = t.red_d()[k]; const int i2 = t.red_i()[k];
             if (i2 >= 0 && (widx < 0 || v2 > wv || (v2 == wv && i2 < widx))) { wv = v2; widx = i2; }
         }
     }
     v = wv; idx = widx;
 }
 
-__device__ inline double block_min(const Tab& t, double v) {   // v >= 0 or +inf
+__device__ __forceinline__ double block_min(const Tab& t, double v) {   // v >= 0 or +inf
     unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
     warp_min_bits(hi, lo);
     double m = __hiloint2double((int)hi, (int)lo);
@@ -209,48 +205,48 @@ __device__ inline double block_min(const Tab& t, double v) {   // v >= 0 or +inf
     if (nw > 1) {
         const int w = threadIdx.x >> 5;
         QPN_SYNC();
-        if ((threadIdx.x & 31) == 0) t.red_d[w] = m;
+        if ((threadIdx.x & 31) == 0) t.red_d()[w] = m;
         QPN_SYNC();
-        m = t.red_d[0];
-        for (int k = 1; k < nw; ++k) m = fmin(m, t.red_d[k]);
+        m = t.red_d()[0];
+        for (int k = 1; k < nw; ++k) m = fmin(m, t.red_d()[k]);
     }
     return m;
 }
 
-__device__ inline bool is_free_var(const Tab& t, int k) { return t.l[k] == -QPN_INF && t.u[k] == QPN_INF; }
+__device__ __forceinline__ bool is_free_var(const Tab& t, int k) { return t.l()[k] == -QPN_INF && t.u()[k] == QPN_INF; }
 
-__device__ inline void var_bounds(const Tab& t, int var, double& lo, double& up) {
+__device__ __forceinline__ void var_bounds(const Tab& t, int var, double& lo, double& up) {
     const int n = t.n;
     if (var == 2 * n) { lo = 0.0; up = 1.0; return; }
-    if (var < n) { lo = t.l[var]; up = t.u[var]; return; }
+    if (var < n) { lo = t.l()[var]; up = t.u()[var]; return; }
     const int k = var - n;
-    if (t.l[k] == t.u[k]) { lo = -QPN_INF; up = QPN_INF; return; }
-    const int8_t s = t.zst[k];
+    if (t.l()[k] == t.u()[k]) { lo = -QPN_INF; up = QPN_INF; return; }
+    const int8_t s = t.zst()[k];
     if (s == AT_L) { lo = 0.0; up = QPN_INF; return; }
     if (s == AT_U) { lo = -QPN_INF; up = 0.0; return; }
     lo = 0.0; up = 0.0;  // z_k basic or floating: w_k is an artificial fixed at 0
 }
 
-__device__ inline bool artificial_row(const Tab& t, int i) {
-    const int v = t.rowvar[i], n = t.n;
+__device__ __forceinline__ bool artificial_row(const Tab& t, int i) {
+    const int v = t.rowvar()[i], n = t.n;
     if (v < n || v == 2 * n) return false;
     const int k = v - n;
-    if (t.l[k] == t.u[k]) return false;
-    const int8_t s = t.zst[k];
+    if (t.l()[k] == t.u()[k]) return false;
+    const int8_t s = t.zst()[k];
     return s == FLOATING || s == BASIC;
 }
 
 // ---- start of the normal-map path (avi_scratch.jl:17-50) -----------------------------
-// Expects T[i][0:n] = -M[i][:] (thread i wrote its own row), t.l, t.u filled, q and z0
-// readable.  zb = t.prow is scratch (needs ldr >= n; every caller has cap >= n+1).
+// Expects T[i][0:n] = -M[i][:] (thread i wrote its own row), t.l(), t.u() filled, q and z0
+// readable.  zb = t.prow() is scratch (needs ldr >= n; every caller has cap >= n+1).
 // Ends with a barrier.
-__device__ inline void tab_start(Tab& t, const double* q, const double* z0) {
+__device__ __forceinline__ void tab_start(Tab& t, const double* q, const double* z0) {
     const int n = t.n, i = threadIdx.x;
-    double* zb = t.prow;
-    if (i < n) zb[i] = fmin(fmax(z0[i], t.l[i]), t.u[i]);
+    double* zb = t.prow();
+    if (i < n) zb[i] = fmin(fmax(z0[i], t.l()[i]), t.u()[i]);
     QPN_SYNC();
     if (i < n) {
-        double* row = t.T + (size_t)i * t.ldr;
+        double* row = t.T() + (size_t)i * t.ldr;
         double acc = 0.0;
         for (int j = 0; j < n; ++j) {
             const double mij = -row[j];
@@ -259,18 +255,18 @@ __device__ inline void tab_start(Tab& t, const double* q, const double* z0) {
         const double zi = z0[i], zbi = zb[i];
         const double r = ((acc + q[i]) + zi) - zbi;
         row[n] = -r;                                      // the homotopy column goes last
-        t.rr[i] = r;
-        t.beta[i] = zbi - zi;
-        t.rowvar[i] = n + i;
-        t.zst[i] = (zi <= t.l[i]) ? AT_L : (zi >= t.u[i]) ? AT_U : FLOATING;
-        t.rowof[i] = -1; t.colof[i] = i;
-        t.rowof[n + i] = i; t.colof[n + i] = -1;
-        t.colvar[i] = i;
-        t.nbval[i] = zbi;
+        t.rr()[i] = r;
+        t.beta()[i] = zbi - zi;
+        t.rowvar()[i] = n + i;
+        t.zst()[i] = (zi <= t.l()[i]) ? AT_L : (zi >= t.u()[i]) ? AT_U : FLOATING;
+        t.rowof()[i] = -1; t.colof()[i] = i;
+        t.rowof()[n + i] = i; t.colof()[n + i] = -1;
+        t.colvar()[i] = i;
+        t.nbval()[i] = zbi;
     }
     if (i == 0) {
-        t.colvar[n] = 2 * n; t.nbval[n] = 0.0;
-        t.rowof[2 * n] = -1; t.colof[2 * n] = n;
+        t.colvar()[n] = 2 * n; t.nbval()[n] = 0.0;
+        t.rowof()[2 * n] = -1; t.colof()[2 * n] = n;
     }
     t.ncol = n + 1;
     t.pivots = 0;
@@ -278,17 +274,17 @@ __device__ inline void tab_start(Tab& t, const double* q, const double* z0) {
 }
 
 // ---- rank-1 pivot on the compact tableau (avi_scratch.jl:2-7) --------------------------
-__device__ inline void pivot(Tab& t, int rho, int c, bool compact = true) {
+__device__ __forceinline__ void pivot(Tab& t, int rho, int c, bool compact = true) {
     const int n = t.n, ldr = t.ldr, i = threadIdx.x;
     const int ncol = t.ncol;
     const int nce = (ncol + 1) & ~1;                      // even: the update runs two columns at a time
-    double* T = t.T;
+    double* T = t.T();
     const double* prho = T + (size_t)rho * ldr;
     const double p = prho[c];
     for (int j = i; j < nce; j += blockDim.x)
-        t.prow[j] = (j >= ncol) ? 0.0 : (j == c) ? (1.0 / p) : prho[j] / p;
+        t.prow()[j] = (j >= ncol) ? 0.0 : (j == c) ? (1.0 / p) : prho[j] / p;
     const double d = (i < n) ? T[(size_t)i * ldr + c] : 0.0;
-    const int lv = t.rowvar[rho];                         // leaving variable (read before the barrier)
+    const int lv = t.rowvar()[rho];                         // leaving variable (read before the barrier)
     // A slack of a free variable never comes back: its column leaves the live range.
     const bool dead = compact && lv >= n && lv < 2 * n && is_free_var(t, lv - n);
     const int last = ncol - 1;
@@ -300,7 +296,7 @@ __device__ inline void pivot(Tab& t, int rho, int c, bool compact = true) {
         const double nd = -d;
 #pragma unroll 2
         for (int j = 0; j < nce; j += 2) {
-            const double2 pj = *reinterpret_cast<const double2*>(t.prow + j);
+            const double2 pj = *reinterpret_cast<const double2*>(t.prow() + j);
             if (pj.x == 0.0 && pj.y == 0.0) continue;     // uniform: both columns untouched by this pivot
             double2 tv = *reinterpret_cast<double2*>(row + j);
             tv.x = isrho ? pj.x : fma(nd, pj.x, tv.x);
@@ -310,18 +306,18 @@ __device__ inline void pivot(Tab& t, int rho, int c, bool compact = true) {
         if (dead && c != last) row[c] = row[last];        // own row only: no barrier needed
     }
     if (i == 0) {
-        const int ev = t.colvar[c];
-        const double vent = t.nbval[c], vlv = t.beta[rho];
-        t.rowvar[rho] = ev; t.rowof[ev] = rho; t.colof[ev] = -1; t.rowof[lv] = -1;
-        t.beta[rho] = vent;
+        const int ev = t.colvar()[c];
+        const double vent = t.nbval()[c], vlv = t.beta()[rho];
+        t.rowvar()[rho] = ev; t.rowof()[ev] = rho; t.colof()[ev] = -1; t.rowof()[lv] = -1;
+        t.beta()[rho] = vent;
         if (dead) {
-            t.colof[lv] = -1;
+            t.colof()[lv] = -1;
             if (c != last) {
-                const int mv = t.colvar[last];
-                t.colvar[c] = mv; t.nbval[c] = t.nbval[last]; t.colof[mv] = c;
+                const int mv = t.colvar()[last];
+                t.colvar()[c] = mv; t.nbval()[c] = t.nbval()[last]; t.colof()[mv] = c;
             }
         } else {
-            t.colvar[c] = lv; t.colof[lv] = c; t.nbval[c] = vlv;
+            t.colvar()[c] = lv; t.colof()[lv] = c; t.nbval()[c] = vlv;
         }
     }
     if (dead) t.ncol = last;
@@ -329,11 +325,11 @@ __device__ inline void pivot(Tab& t, int rho, int c, bool compact = true) {
     QPN_SYNC();
 }
 
-__device__ inline int best_artificial_row(const Tab& t, int c) {
+__device__ __forceinline__ int best_artificial_row(const Tab& t, int c) {
     const int i = threadIdx.x;
     double a = 0.0; bool valid = false;
     if (i < t.n && artificial_row(t, i)) {
-        a = fabs(t.T[(size_t)i * t.ldr + c]);
+        a = fabs(t.T()[(size_t)i * t.ldr + c]);
         valid = a > 0.0;
     }
     int idx;
@@ -344,18 +340,18 @@ __device__ inline int best_artificial_row(const Tab& t, int c) {
 // ---- ratio test over the finite bounds of the basics (avi_scratch.jl:65-77) ------------
 // Returns the step of the blocking row (INF if none); all threads get the same answer.
 // Every exit ends with a barrier.
-__device__ inline double ratio_test(const Tab& t, int c, double sigma, int& rho, int& which) {
+__device__ __forceinline__ double ratio_test(const Tab& t, int c, double sigma, int& rho, int& which) {
     const int n = t.n, i = threadIdx.x;
     double r = QPN_INF, a = 0.0;
     bool is_t = false;
     if (i < n) {
-        const double ci = t.T[(size_t)i * t.ldr + c];
+        const double ci = t.T()[(size_t)i * t.ldr + c];
         const double d = sigma * ci;
-        const int v = t.rowvar[i];
+        const int v = t.rowvar()[i];
         double lo, up;
         var_bounds(t, v, lo, up);
-        if (d > D_TOL && lo > -QPN_INF) r = fmax((t.beta[i] - lo) / d, 0.0);
-        else if (d < -D_TOL && up < QPN_INF) r = fmax((up - t.beta[i]) / (-d), 0.0);
+        if (d > D_TOL && lo > -QPN_INF) r = fmax((t.beta()[i] - lo) / d, 0.0);
+        else if (d < -D_TOL && up < QPN_INF) r = fmax((up - t.beta()[i]) / (-d), 0.0);
         a = fabs(ci);
         is_t = (v == 2 * n);
     }
@@ -370,41 +366,41 @@ __device__ inline double ratio_test(const Tab& t, int c, double sigma, int& rho,
     block_argmax(t, cand, key, idx);
     rho = idx;
     if (blockDim.x > 32) QPN_SYNC();
-    if (i == rho) t.red_d[32] = r;                        // the winner publishes its own ratio
+    if (i == rho) t.red_d()[32] = r;                        // the winner publishes its own ratio
     QPN_SYNC();
-    const double th = t.red_d[32];
-    which = (sigma * t.T[(size_t)rho * t.ldr + c] > 0.0) ? -1 : +1;
+    const double th = t.red_d()[32];
+    which = (sigma * t.T()[(size_t)rho * t.ldr + c] > 0.0) ? -1 : +1;
     return th;
 }
 
-__device__ inline void move(Tab& t, int c, double sigma, double theta) {
+__device__ __forceinline__ void move(Tab& t, int c, double sigma, double theta) {
     if (theta == 0.0) return;
     const int i = threadIdx.x;
     if (i < t.n) {
-        const double ci = t.T[(size_t)i * t.ldr + c];
-        if (ci != 0.0) t.beta[i] = fma(-(sigma * theta), ci, t.beta[i]);
+        const double ci = t.T()[(size_t)i * t.ldr + c];
+        if (ci != 0.0) t.beta()[i] = fma(-(sigma * theta), ci, t.beta()[i]);
     }
-    if (i == 0) t.nbval[c] = fma(sigma, theta, t.nbval[c]);
+    if (i == 0) t.nbval()[c] = fma(sigma, theta, t.nbval()[c]);
     QPN_SYNC();
 }
 
-__device__ inline void leave_at(Tab& t, int rho, int which) {
+__device__ __forceinline__ void leave_at(Tab& t, int rho, int which) {
     if (threadIdx.x == 0) {
         double lo, up;
-        var_bounds(t, t.rowvar[rho], lo, up);
-        t.beta[rho] = which < 0 ? lo : up;
+        var_bounds(t, t.rowvar()[rho], lo, up);
+        t.beta()[rho] = which < 0 ? lo : up;
     }
     QPN_SYNC();
 }
 
-__device__ inline void set_zst(Tab& t, int k, int8_t s) {
+__device__ __forceinline__ void set_zst(Tab& t, int k, int8_t s) {
     QPN_SYNC();
-    if (threadIdx.x == 0) t.zst[k] = s;
+    if (threadIdx.x == 0) t.zst()[k] = s;
     QPN_SYNC();
 }
 
-__device__ inline bool try_exchange(Tab& t, int var) {
-    const int c = t.colof[var];
+__device__ __forceinline__ bool try_exchange(Tab& t, int var) {
+    const int c = t.colof()[var];
     if (c < 0) return false;
     const int rho = best_artificial_row(t, c);
     if (rho < 0) return false;
@@ -414,13 +410,13 @@ __device__ inline bool try_exchange(Tab& t, int var) {
 
 // Largest |T[i][c]| over rows still holding the slack of a FREE variable (artificial whatever
 // the start point is).
-__device__ inline int best_free_row(const Tab& t, int c) {
+__device__ __forceinline__ int best_free_row(const Tab& t, int c) {
     const int i = threadIdx.x, n = t.n;
     double a = 0.0; bool valid = false;
     if (i < n) {
-        const int v = t.rowvar[i];
+        const int v = t.rowvar()[i];
         if (v >= n && v < 2 * n && is_free_var(t, v - n)) {
-            a = fabs(t.T[(size_t)i * t.ldr + c]);
+            a = fabs(t.T()[(size_t)i * t.ldr + c]);
             valid = a > 0.0;
         }
     }
@@ -432,16 +428,16 @@ __device__ inline int best_free_row(const Tab& t, int c) {
 // T[:, t] = B^-1 r rebuilt from the slack columns: the column of a nonbasic w_k is -B^-1 e_k, a
 // w_k basic in row rho means B^-1 e_k = -e_rho.  Sequential fma over k.  Needs every slack
 // column still in place (no compaction yet).  Ends with a barrier.
-__device__ inline void recompute_tcol(Tab& t) {
+__device__ __forceinline__ void recompute_tcol(Tab& t) {
     const int n = t.n, i = threadIdx.x;
-    const int tc = t.colof[2 * n];
+    const int tc = t.colof()[2 * n];
     if (i < n) {
-        double* row = t.T + (size_t)i * t.ldr;
+        double* row = t.T() + (size_t)i * t.ldr;
         double acc = 0.0;
         for (int k = 0; k < n; ++k) {
-            const int ck = t.colof[n + k];
-            const double pik = ck >= 0 ? -row[ck] : (t.rowof[n + k] == i ? -1.0 : 0.0);
-            if (pik != 0.0) acc = fma(pik, t.rr[k], acc);
+            const int ck = t.colof()[n + k];
+            const double pik = ck >= 0 ? -row[ck] : (t.rowof()[n + k] == i ? -1.0 : 0.0);
+            if (pik != 0.0) acc = fma(pik, t.rr()[k], acc);
         }
         row[tc] = acc;
     }
@@ -449,26 +445,26 @@ __device__ inline void recompute_tcol(Tab& t) {
 }
 
 // Drop every dead column (slack of a free variable) from the live range at once.
-__device__ inline void compact_dead(Tab& t) {
+__device__ __forceinline__ void compact_dead(Tab& t) {
     const int n = t.n, i = threadIdx.x;
-    int* map = reinterpret_cast<int*>(t.prow);            // scratch: prow is free between pivots
+    int* map = reinterpret_cast<int*>(t.prow());            // scratch: prow is free between pivots
     if (i == 0) {
         int nl = 0;
         for (int j = 0; j < t.ncol; ++j) {
-            const int v = t.colvar[j];
-            if (v >= n && v < 2 * n && is_free_var(t, v - n)) t.colof[v] = -1;
+            const int v = t.colvar()[j];
+            if (v >= n && v < 2 * n && is_free_var(t, v - n)) t.colof()[v] = -1;
             else map[nl++] = j;
         }
         for (int d = 0; d < nl; ++d) {
             const int sidx = map[d];
-            if (sidx != d) { const int v = t.colvar[sidx]; t.colvar[d] = v; t.nbval[d] = t.nbval[sidx]; t.colof[v] = d; }
+            if (sidx != d) { const int v = t.colvar()[sidx]; t.colvar()[d] = v; t.nbval()[d] = t.nbval()[sidx]; t.colof()[v] = d; }
         }
-        t.red_i[32] = nl;
+        t.red_i()[32] = nl;
     }
     QPN_SYNC();
-    const int nl = t.red_i[32];
+    const int nl = t.red_i()[32];
     if (i < n) {
-        double* row = t.T + (size_t)i * t.ldr;
+        double* row = t.T() + (size_t)i * t.ldr;
         for (int d = 0; d < nl; ++d) { const int sidx = map[d]; if (sidx != d) row[d] = row[sidx]; }   // sidx >= d: in place
     }
     t.ncol = nl;
@@ -476,7 +472,7 @@ __device__ inline void compact_dead(Tab& t) {
 }
 
 // ---- crash: bring interior / free variables into the basis ----------------------------
-__device__ inline void crash(Tab& t) {
+__device__ __forceinline__ void crash(Tab& t) {
     const int n = t.n;
     // phase 0: free variables exchange against rows of free variables only.  Nothing here depends
     // on the start point or on q (a shared matrix could do it once); the homotopy column is then
@@ -485,7 +481,7 @@ __device__ inline void crash(Tab& t) {
         const int piv0 = t.pivots;
         for (int i = 0; i < n; ++i) {
             if (!is_free_var(t, i)) continue;
-            const int c = t.colof[i];
+            const int c = t.colof()[i];
             const int rho = best_free_row(t, c);
             if (rho >= 0) { pivot(t, rho, c, false); set_zst(t, i, BASIC); }
         }
@@ -493,14 +489,14 @@ __device__ inline void crash(Tab& t) {
     }
     // phase 1: everything still floating, against any artificial row
     for (int i = 0; i < n; ++i) {
-        if (t.zst[i] != FLOATING) continue;
-        const int c = t.colof[i];
+        if (t.zst()[i] != FLOATING) continue;
+        const int c = t.colof()[i];
         const int rho = best_artificial_row(t, c);
         if (rho >= 0) { pivot(t, rho, c); set_zst(t, i, BASIC); continue; }
         // dependent column: walk towards an extreme point (Cao-Ferris stage 2)
         int rb[2], wb[2]; double th[2], own[2], step[2];
-        own[0] = t.u[i] - t.nbval[c];        // read before the ratio tests (synchronisation rule)
-        own[1] = t.nbval[c] - t.l[i];
+        own[0] = t.u()[i] - t.nbval()[c];        // read before the ratio tests (synchronisation rule)
+        own[1] = t.nbval()[c] - t.l()[i];
         for (int s = 0; s < 2; ++s) {
             const double sigma = s == 0 ? 1.0 : -1.0;
             th[s] = ratio_test(t, c, sigma, rb[s], wb[s]);
@@ -512,18 +508,18 @@ __device__ inline void crash(Tab& t) {
         if (own[s] <= th[s]) {
             move(t, c, sigma, own[s]);
             QPN_SYNC();
-            if (threadIdx.x == 0) { t.nbval[c] = s == 0 ? t.u[i] : t.l[i]; t.zst[i] = s == 0 ? AT_U : AT_L; }
+            if (threadIdx.x == 0) { t.nbval()[c] = s == 0 ? t.u()[i] : t.l()[i]; t.zst()[i] = s == 0 ? AT_U : AT_L; }
             QPN_SYNC();
             continue;
         }
         move(t, c, sigma, th[s]);
         leave_at(t, rb[s], wb[s]);
-        const int lv = t.rowvar[rb[s]];
+        const int lv = t.rowvar()[rb[s]];
         pivot(t, rb[s], c);
         set_zst(t, i, BASIC);
         if (lv < n) {
             set_zst(t, lv, wb[s] < 0 ? AT_L : AT_U);
-            if (t.rowof[n + lv] < 0) try_exchange(t, n + lv);
+            if (t.rowof()[n + lv] < 0) try_exchange(t, n + lv);
         } else {
             const int k = lv - n;
             if (try_exchange(t, k)) set_zst(t, k, BASIC);
@@ -532,7 +528,7 @@ __device__ inline void crash(Tab& t) {
     }
 }
 
-__device__ inline void repair(Tab& t) {
+__device__ __forceinline__ void repair(Tab& t) {
     const int n = t.n;
     bool progress = true;
     while (progress) {
@@ -542,78 +538,83 @@ __device__ inline void repair(Tab& t) {
         any = QPN_SYNC_OR(any);
         if (!any) return;
         for (int k = 0; k < n; ++k) {
-            const int8_t s = t.zst[k];
-            if ((s == AT_L || s == AT_U) && t.l[k] != t.u[k] && t.rowof[k] < 0 && t.rowof[n + k] < 0) {
+            const int8_t s = t.zst()[k];
+            if ((s == AT_L || s == AT_U) && t.l()[k] != t.u()[k] && t.rowof()[k] < 0 && t.rowof()[n + k] < 0) {
                 if (try_exchange(t, n + k)) progress = true;
                 else if (try_exchange(t, k)) { set_zst(t, k, BASIC); progress = true; }
             }
         }
         for (int k = 0; k < n; ++k)
-            if (t.zst[k] == FLOATING && t.rowof[k] < 0)
+            if (t.zst()[k] == FLOATING && t.rowof()[k] < 0)
                 if (try_exchange(t, k)) { set_zst(t, k, BASIC); progress = true; }
     }
 }
 
 // ---- phase 2: complementary pivoting (avi_scratch.jl:59-132) ------------------------------
-__device__ inline int lemke(Tab& t, int max_pivots) {
+__device__ __forceinline__ int lemke(Tab& t, int max_pivots) {
     const int n = t.n;
     int ent = 2 * n; double sigma = 1.0;
     for (;;) {
         if (t.pivots > max_pivots) return ST_MAX_ITERS;
-        const int c = t.colof[ent];
+        const int c = t.colof()[ent];
         int rb, wb;
         // Read everything the branch below depends on BEFORE the ratio test: its barriers then
         // separate these reads from the writes in move() (a read after it would race with them).
-        const double own = ent == 2 * n ? 1.0 - t.nbval[c] : ent < n ? (t.u[ent] - t.l[ent]) : QPN_INF;
+        const double own = ent == 2 * n ? 1.0 - t.nbval()[c] : ent < n ? (t.u()[ent] - t.l()[ent]) : QPN_INF;
         const double th = ratio_test(t, c, sigma, rb, wb);
         if (own == QPN_INF && th == QPN_INF) return ST_RAY_TERM;
         if (own <= th) {
             move(t, c, sigma, own);
             QPN_SYNC();
-            if (ent == 2 * n) { if (threadIdx.x == 0) t.nbval[c] = 1.0; QPN_SYNC(); return ST_SUCCESS; }
-            if (threadIdx.x == 0) { t.nbval[c] = sigma > 0 ? t.u[ent] : t.l[ent]; t.zst[ent] = sigma > 0 ? AT_U : AT_L; }
+            if (ent == 2 * n) { if (threadIdx.x == 0) t.nbval()[c] = 1.0; QPN_SYNC(); return ST_SUCCESS; }
+            if (threadIdx.x == 0) { t.nbval()[c] = sigma > 0 ? t.u()[ent] : t.l()[ent]; t.zst()[ent] = sigma > 0 ? AT_U : AT_L; }
             QPN_SYNC();
             ent = n + ent; sigma = -sigma;
             continue;
         }
         move(t, c, sigma, th);
         leave_at(t, rb, wb);
-        const int lv = t.rowvar[rb];
+        const int lv = t.rowvar()[rb];
         const bool was_art = artificial_row(t, rb);
         pivot(t, rb, c);
         if (ent < n) set_zst(t, ent, BASIC);
         if (lv == 2 * n) return wb > 0 ? ST_SUCCESS : ST_RAY_TERM;
         if (lv < n) {
             set_zst(t, lv, wb < 0 ? AT_L : AT_U);
-            if (t.rowof[n + lv] >= 0) return ST_FAILURE;
+            if (t.rowof()[n + lv] >= 0) return ST_FAILURE;
             ent = n + lv; sigma = wb < 0 ? 1.0 : -1.0;
         } else {
             const int k = lv - n;
-            const int8_t s = t.zst[k];
-            if (was_art || t.rowof[k] >= 0 || !(s == AT_L || s == AT_U)) return ST_FAILURE;
+            const int8_t s = t.zst()[k];
+            if (was_art || t.rowof()[k] >= 0 || !(s == AT_L || s == AT_U)) return ST_FAILURE;
             ent = k; sigma = s == AT_L ? 1.0 : -1.0;
         }
     }
 }
 
-// Runs crash + repair + path following on a started tableau.  On return thread i < n holds
-// z_i in *zi and its basis code in *code (1 lower, 2 basic/interior, 3 upper, 4 fixed).
-__device__ inline int avi_pivot_run(Tab& t, int max_pivots, double* zi, int8_t* code) {
+// Runs crash + repair + path following on a started tableau.  Thread i < n gets z_i and its
+// basis code (1 lower, 2 basic/interior, 3 upper, 4 fixed).  Deliberately NOT inlined: a kernel
+// that solves several AVIs per instance then holds one copy of the engine, and the workspace
+// descriptor travels in registers instead of a local-memory struct.
+struct PivotResult { double zi; int st; int pivots; int code; };
+__device__ __noinline__ PivotResult avi_pivot_run(Tab t, int max_pivots) {
     crash(t);
     repair(t);
-    const int st = lemke(t, max_pivots);
+    PivotResult out;
+    out.st = lemke(t, max_pivots);
+    out.zi = 0.0; out.code = 0; out.pivots = t.pivots;
     const int i = threadIdx.x;
     if (i < t.n) {
-        const int r = t.rowof[i];
-        *zi = r >= 0 ? t.beta[r] : t.nbval[t.colof[i]];
-        const int8_t s = t.zst[i];
-        *code = (t.l[i] == t.u[i]) ? 4 : (r >= 0 || s == FLOATING) ? 2 : (s == AT_L ? 1 : 3);
+        const int r = t.rowof()[i];
+        out.zi = r >= 0 ? t.beta()[r] : t.nbval()[t.colof()[i]];
+        const int8_t s = t.zst()[i];
+        out.code = (t.l()[i] == t.u()[i]) ? 4 : (r >= 0 || s == FLOATING) ? 2 : (s == AT_L ? 1 : 3);
     }
-    return st;
+    return out;
 }
 
 // check_avi_solution (avi.jl:148-156) contribution of one index.
-__device__ inline int check_avi_index(double r, double z, double l, double u, double tol) {
+__device__ __forceinline__ int check_avi_index(double r, double z, double l, double u, double tol) {
     int bad = 0;
     if (r > tol && fabs(z - l) > tol) bad++;
     if (r < -tol && fabs(z - u) > tol) bad++;

@@ -59,6 +59,22 @@ static int fail(qpn_handle* h, const char* fmt, ...) {
 
 static inline int roundup32(int n) { return n < 32 ? 32 : ((n + 31) / 32) * 32; }
 
+// Kernels that pivot are instantiated per block-size bucket so that __launch_bounds__ can cap the
+// registers at 768 resident threads per SM (24 CTAs of 32 threads: one wave for 4,096 instances / 148 SMs... nearly).
+#define QPN_LAUNCH_BUCKETED(KERNEL, threads, grid, smem, stream, ...)                                            \
+    do {                                                                                                         \
+        const int thr_ = (threads);                                                                              \
+        if (thr_ <= 32) { QPN_LAUNCH_ONE(KERNEL<32>, 32, grid, smem, stream, __VA_ARGS__); }                     \
+        else if (thr_ <= 64) { QPN_LAUNCH_ONE(KERNEL<64>, thr_, grid, smem, stream, __VA_ARGS__); }              \
+        else if (thr_ <= 128) { QPN_LAUNCH_ONE(KERNEL<128>, thr_, grid, smem, stream, __VA_ARGS__); }            \
+        else { QPN_LAUNCH_ONE(KERNEL<256>, thr_, grid, smem, stream, __VA_ARGS__); }                             \
+    } while (0)
+#define QPN_LAUNCH_ONE(KINST, thr, grid, smem, stream, ...)                                                      \
+    do {                                                                                                         \
+        if ((smem) > 48 * 1024) CK(cudaFuncSetAttribute(KINST, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))); \
+        KINST<<<(grid), (thr), (smem), (stream)>>>(__VA_ARGS__);                                                 \
+    } while (0)
+
 extern "C" int qpn_create(int device, qpn_handle** out) {
     qpn_handle* h = nullptr;
     if (!out) return fail(nullptr, "qpn_create: out is NULL");
@@ -218,9 +234,9 @@ static int launch_avi(qpn_handle* h, int n, int batch, const MatDesc& M, const d
     if (smem > (size_t)h->max_smem_optin)
         return fail(h, "AVI of size n=%d needs %zu B of shared memory per CTA (limit %d): the shared-memory "
                        "tableau path does not cover this size", n, smem, h->max_smem_optin);
-    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(avi_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (max_pivots <= 0) max_pivots = 50 * n + 100;
-    avi_solve_kernel<<<batch, roundup32(n), smem, s>>>(n, batch, M, q, l, u, lu_shared, z0, max_pivots, z, st, pv, basis);
+    if (n > 256) return fail(h, "AVI of size n=%d exceeds the one-thread-per-row limit of 256", n);
+    QPN_LAUNCH_BUCKETED(avi_solve_kernel, roundup32(n), batch, smem, s, n, batch, M, q, l, u, lu_shared, z0, max_pivots, z, st, pv, basis);
     h->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -330,9 +346,9 @@ static int launch_gavi(qpn_handle* h, const GaviDesc& g, int batch, const double
     const size_t smem = gavi_smem_bytes(g.d1, g.d2, g.np);
     if (smem > (size_t)h->max_smem_optin)
         return fail(h, "GAVI with d1=%d d2=%d needs %zu B of shared memory per CTA (limit %d)", g.d1, g.d2, smem, h->max_smem_optin);
-    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(gavi_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (max_pivots <= 0) max_pivots = 50 * n + 100;
-    gavi_solve_kernel<<<batch, roundup32(n), smem, s>>>(g, batch, w, z0, presolve, max_pivots, z, zfull, st, pv, basis);
+    if (n > 256) return fail(h, "GAVI of lifted size n=%d exceeds the one-thread-per-row limit of 256", n);
+    QPN_LAUNCH_BUCKETED(gavi_solve_kernel, roundup32(n), batch, smem, s, g, batch, w, z0, presolve, max_pivots, z, zfull, st, pv, basis);
     h->launches++;
     CK(cudaGetLastError());
     return 0;

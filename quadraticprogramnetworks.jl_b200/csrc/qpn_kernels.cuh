@@ -15,17 +15,17 @@ struct MatDesc {
 };
 
 // T[i][0:n] = -M[i][:] for instance b (row-major tableau).  Ends with a barrier.
-__device__ inline void load_neg_matrix(Tab& t, const MatDesc& M, int b) {
+__device__ __forceinline__ void load_neg_matrix(Tab& t, const MatDesc& M, int b) {
     const int n = t.n, ldr = t.ldr, i = threadIdx.x;
     if (M.dense) {
         const double* src = M.dense + (M.shared ? 0 : (size_t)b * n * n);
         if (i < n) {
-            double* row = t.T + (size_t)i * ldr;
+            double* row = t.T() + (size_t)i * ldr;
             for (int j = 0; j < n; ++j) row[j] = -src[(size_t)j * n + i];      // coalesced across the warp
         }
     } else {
         if (i < n) {
-            double* row = t.T + (size_t)i * ldr;
+            double* row = t.T() + (size_t)i * ldr;
             for (int j = 0; j < n; ++j) row[j] = 0.0;
         }
         QPN_SYNC();
@@ -33,15 +33,15 @@ __device__ inline void load_neg_matrix(Tab& t, const MatDesc& M, int b) {
         for (int j = 0; j < n; ++j) {
             const int k0 = M.colptr[j] - M.base, k1 = M.colptr[j + 1] - M.base;
             for (int k = k0 + i; k < k1; k += blockDim.x)
-                t.T[(size_t)(M.rowval[k] - M.base) * ldr + j] = -nz[k];
+                t.T()[(size_t)(M.rowval[k] - M.base) * ldr + j] = -nz[k];
         }
     }
     QPN_SYNC();
 }
 
 // r_i = (M z)_i + q_i with T[i][0:n] = -M[i][:] and z in shared memory; sequential in j.
-__device__ inline double residual_row(const Tab& t, const double* zs, double qi, int i) {
-    const double* row = t.T + (size_t)i * t.ldr;
+__device__ __forceinline__ double residual_row(const Tab& t, const double* zs, double qi, int i) {
+    const double* row = t.T() + (size_t)i * t.ldr;
     double acc = 0.0;
     for (int j = 0; j < t.n; ++j) {
         const double mij = -row[j];
@@ -52,34 +52,35 @@ __device__ inline double residual_row(const Tab& t, const double* zs, double qi,
 
 // ---- solve_avi (avi.jl:63-77) ------------------------------------------------------------
 // grid = batch, block = roundup32(n).  Dynamic smem: Tab(n, n+1) + q(n) + z(n).
-__global__ void avi_solve_kernel(int n, int batch, MatDesc M, const double* __restrict__ q,
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 768 / MAXT) avi_solve_kernel(int n, int batch, const __grid_constant__ MatDesc M, const double* __restrict__ q,
                                  const double* __restrict__ l, const double* __restrict__ u,
                                  int lu_shared, const double* __restrict__ z0, int max_pivots,
                                  double* __restrict__ z_out, int32_t* __restrict__ status_out,
                                  int32_t* __restrict__ pivots_out, int8_t* __restrict__ basis_out) {
-    extern __shared__ __align__(16) unsigned char smem[];
     const int b = blockIdx.x, i = threadIdx.x;
     Tab t;
-    tab_carve(t, n, n + 1, smem);
-    double* qs = reinterpret_cast<double*>(smem + tab_smem_bytes(n, n + 1));
+    tab_carve(t, n, n + 1, 0);
+    double* qs = reinterpret_cast<double*>(qpn_smem + tab_smem_bytes(n, n + 1));
     double* zs = qs + n;
     if (i < n) {
         qs[i] = q[(size_t)b * n + i];
         zs[i] = z0[(size_t)b * n + i];
-        t.l[i] = l[(lu_shared ? 0 : (size_t)b * n) + i];
-        t.u[i] = u[(lu_shared ? 0 : (size_t)b * n) + i];
+        t.l()[i] = l[(lu_shared ? 0 : (size_t)b * n) + i];
+        t.u()[i] = u[(lu_shared ? 0 : (size_t)b * n) + i];
     }
     load_neg_matrix(t, M, b);
     tab_start(t, qs, zs);
-    double zi = 0.0; int8_t code = 0;
-    int st = avi_pivot_run(t, max_pivots, &zi, &code);
-    const int piv = t.pivots;
+    const PivotResult pr = avi_pivot_run(t, max_pivots);
+    const double zi = pr.zi; const int8_t code = (int8_t)pr.code;
+    int st = pr.st;
+    const int piv = pr.pivots;
     // final check (avi.jl:71-74) against the original matrix
     QPN_SYNC();
     if (i < n) zs[i] = zi;
     load_neg_matrix(t, M, b);
     int bad = 0;
-    if (i < n) bad = check_avi_index(residual_row(t, zs, qs[i], i), zi, t.l[i], t.u[i], 1e-6);
+    if (i < n) bad = check_avi_index(residual_row(t, zs, qs[i], i), zi, t.l()[i], t.u()[i], 1e-6);
     bad = QPN_SYNC_OR(bad);
     if (st == ST_SUCCESS && bad) st = ST_FAILURE;
     if (i < n) {
@@ -132,9 +133,9 @@ struct GaviDesc {
 };
 
 // ---- comp_indices (avi_solutions.jl:511-612): one thread per (index, instance) -------------
-__device__ inline bool approx_eq(double a, double b, double atol) { return a == b || fabs(a - b) <= atol; }
+__device__ __forceinline__ bool approx_eq(double a, double b, double atol) { return a == b || fabs(a - b) <= atol; }
 
-__device__ inline int8_t comp_mask(double l, double u, double r, double z, double tol) {
+__device__ __forceinline__ int8_t comp_mask(double l, double u, double r, double z, double tol) {
     const bool eq = approx_eq(l, u, tol);
     int m = 0;
     if (approx_eq(z, l, tol) && r >= -tol && !eq) m |= 1;

@@ -23,44 +23,44 @@ struct PlanDesc {
     int ncols;
 };
 
-__device__ inline double csr_row_dot(const PlanDesc& P, int i, const double* v) {
+__device__ __forceinline__ double csr_row_dot(const PlanDesc& P, int i, const double* v) {
     double acc = 0.0;
     for (int k = P.csr_ptr[i]; k < P.csr_ptr[i + 1]; ++k) acc = fma(P.csr_val[k], v[P.csr_col[k]], acc);
     return acc;
 }
 
 // Start of a solve from a plan: same state as tab_start + phase 0 + recompute_tcol + compact_dead.
-// t.l / t.u hold the bounds; zb: n doubles of scratch.  Ends with a barrier.
-__device__ inline void tab_start_plan(Tab& t, const PlanDesc& P, const double* q, const double* z0, double* zb) {
+// t.l() / t.u() hold the bounds; zb: n doubles of scratch.  Ends with a barrier.
+__device__ __forceinline__ void tab_start_plan(Tab& t, const PlanDesc& P, const double* q, const double* z0, double* zb) {
     const int n = P.n, i = threadIdx.x;
     tab_shape(t, n, P.ncol0);
     const int ldr = t.ldr;
-    if (i < n) zb[i] = fmin(fmax(z0[i], t.l[i]), t.u[i]);
-    for (int e = i; e < n * ldr; e += blockDim.x) t.T[e] = P.T0[e];
-    for (int v = i; v <= 2 * n; v += blockDim.x) { t.rowof[v] = -1; t.colof[v] = -1; }
+    if (i < n) zb[i] = fmin(fmax(z0[i], t.l()[i]), t.u()[i]);
+    for (int e = i; e < n * ldr; e += blockDim.x) t.T()[e] = P.T0[e];
+    for (int v = i; v <= 2 * n; v += blockDim.x) { t.rowof()[v] = -1; t.colof()[v] = -1; }
     QPN_SYNC();
     double zi = 0.0;
     if (i < n) {
         zi = z0[i];
-        t.rr[i] = ((csr_row_dot(P, i, zb) + q[i]) + zi) - zb[i];
-        t.zst[i] = (zi <= t.l[i]) ? AT_L : (zi >= t.u[i]) ? AT_U : FLOATING;
+        t.rr()[i] = ((csr_row_dot(P, i, zb) + q[i]) + zi) - zb[i];
+        t.zst()[i] = (zi <= t.l()[i]) ? AT_L : (zi >= t.u()[i]) ? AT_U : FLOATING;
     }
     for (int j = i; j < P.ncol0; j += blockDim.x) {
         const int v = P.colvar0[j];
-        t.colvar[j] = v; t.colof[v] = j; t.nbval[j] = v < n ? zb[v] : 0.0;
+        t.colvar()[j] = v; t.colof()[v] = j; t.nbval()[j] = v < n ? zb[v] : 0.0;
     }
     QPN_SYNC();
     if (i < n) {
         double acc = 0.0;
         for (int k = 0; k < n; ++k) {
             const double pik = P.PT[(size_t)k * n + i];
-            if (pik != 0.0) acc = fma(pik, t.rr[k], acc);
+            if (pik != 0.0) acc = fma(pik, t.rr()[k], acc);
         }
-        t.T[(size_t)i * ldr + P.tcol0] = acc;
+        t.T()[(size_t)i * ldr + P.tcol0] = acc;
         const int rv = P.rowvar0[i];
-        t.rowvar[i] = rv; t.rowof[rv] = i;
-        t.beta[i] = rv < n ? zb[rv] : zb[i] - zi;
-        if (rv < n) t.zst[rv] = BASIC;            // after the barrier that followed the default marks
+        t.rowvar()[i] = rv; t.rowof()[rv] = i;
+        t.beta()[i] = rv < n ? zb[rv] : zb[i] - zi;
+        if (rv < n) t.zst()[rv] = BASIC;            // after the barrier that followed the default marks
     }
     t.ncol = P.ncol0;
     t.pivots = P.npiv0;
@@ -69,42 +69,44 @@ __device__ inline void tab_start_plan(Tab& t, const PlanDesc& P, const double* q
 
 // Solve (M z + q) comp. l <= z <= u in the shared-memory tableau.  `build(t)` must fill
 // T[i][0:n] with -M[i][:] and end with a barrier; it is called twice (start and final check).
-// t.l / t.u hold the bounds, qs the vector q, zs the start on entry and z on exit.
+// t.l() / t.u() hold the bounds, qs the vector q, zs the start on entry and z on exit.
 // code (optional, smem, n entries) receives the basis codes.  Same procedure as the oracle's
 // single-instance solve.
 template <class Build>
-__device__ inline int solve_avi_smem(Tab& t, int n, Build build, const double* qs, double* zs,
+__device__ __forceinline__ int solve_avi_smem(Tab& t, int n, Build build, const double* qs, double* zs,
                                      int max_pivots, int8_t* code_out, int* pivots_acc) {
     tab_shape(t, n, n + 1);
     build(t);
     tab_start(t, qs, zs);
-    double zi = 0.0; int8_t code = 0;
-    int st = avi_pivot_run(t, max_pivots, &zi, &code);
-    *pivots_acc += t.pivots;
+    const PivotResult pr = avi_pivot_run(t, max_pivots);
+    const double zi = pr.zi; const int8_t code = (int8_t)pr.code;
+    int st = pr.st;
+    *pivots_acc += pr.pivots;
     const int i = threadIdx.x;
     QPN_SYNC();
     if (i < n) { zs[i] = zi; if (code_out) code_out[i] = code; }
     build(t);
     int bad = 0;
-    if (i < n) bad = check_avi_index(residual_row(t, zs, qs[i], i), zi, t.l[i], t.u[i], 1e-6);
+    if (i < n) bad = check_avi_index(residual_row(t, zs, qs[i], i), zi, t.l()[i], t.u()[i], 1e-6);
     bad = QPN_SYNC_OR(bad);
     if (st == ST_SUCCESS && bad) st = ST_FAILURE;
     return st;
 }
 
 // The same solve started from a plan; the final check uses the plan's CSR rows.
-__device__ inline int solve_avi_plan(Tab& t, const PlanDesc& P, const double* qs, double* zs, double* zb,
+__device__ __forceinline__ int solve_avi_plan(Tab& t, const PlanDesc& P, const double* qs, double* zs, double* zb,
                                      int max_pivots, int8_t* code_out, int* pivots_acc) {
     const int n = P.n, i = threadIdx.x;
     tab_start_plan(t, P, qs, zs, zb);
-    double zi = 0.0; int8_t code = 0;
-    int st = avi_pivot_run(t, max_pivots, &zi, &code);
-    *pivots_acc += t.pivots;
+    const PivotResult pr = avi_pivot_run(t, max_pivots);
+    const double zi = pr.zi; const int8_t code = (int8_t)pr.code;
+    int st = pr.st;
+    *pivots_acc += pr.pivots;
     QPN_SYNC();
     if (i < n) { zs[i] = zi; if (code_out) code_out[i] = code; }
     QPN_SYNC();
     int bad = 0;
-    if (i < n) bad = check_avi_index(csr_row_dot(P, i, zs) + qs[i], zi, t.l[i], t.u[i], 1e-6);
+    if (i < n) bad = check_avi_index(csr_row_dot(P, i, zs) + qs[i], zi, t.l()[i], t.u()[i], 1e-6);
     bad = QPN_SYNC_OR(bad);
     if (st == ST_SUCCESS && bad) st = ST_FAILURE;
     return st;
@@ -113,91 +115,89 @@ __device__ inline int solve_avi_plan(Tab& t, const PlanDesc& P, const double* qs
 // ---- shared-memory plan of a GAVI solve ------------------------------------------------------
 struct GaviSmem {
     Tab t;
-    double *qs, *zs, *zb; // n each (n = d1 + 2 d2)
-    double *w;            // np
-    double *z0;           // d1 + d2
-    double *c, *s0;       // d2 each
-    int* cols;            // d1 + d2 (+1: count)
-    int8_t* code;         // n
+    int base;             // byte offset of the extra arrays in qpn_smem
+    int n, np, dz, d2;    // sizes they were carved for
+    __device__ __forceinline__ double* dbl(int off) const { return reinterpret_cast<double*>(qpn_smem + base) + off; }
+    __device__ __forceinline__ double* qs() const { return dbl(0); }              // n (n = d1 + 2 d2)
+    __device__ __forceinline__ double* zs() const { return dbl(n); }              // n
+    __device__ __forceinline__ double* zb() const { return dbl(2 * n); }          // n
+    __device__ __forceinline__ double* w() const { return dbl(3 * n); }           // np
+    __device__ __forceinline__ double* z0() const { return dbl(3 * n + np); }     // d1 + d2
+    __device__ __forceinline__ double* c() const { return dbl(3 * n + np + dz); } // d2
+    __device__ __forceinline__ double* s0() const { return dbl(3 * n + np + dz + d2); }   // d2
+    __device__ __forceinline__ int* cols() const { return reinterpret_cast<int*>(dbl(3 * n + np + dz + 2 * d2)); }   // dz (+1: count)
+    __device__ __forceinline__ int8_t* code() const {                              // n
+        return reinterpret_cast<int8_t*>(reinterpret_cast<unsigned char*>(cols()) + (((dz + 2) * 4 + 15) / 16) * 16);
+    }
 };
 
-__host__ __device__ inline size_t gavi_extra_bytes(int d1, int d2, int np) {
+__host__ __device__ __forceinline__ size_t gavi_extra_bytes(int d1, int d2, int np) {
     const size_t n = (size_t)d1 + 2 * d2, dz = (size_t)d1 + d2;
     size_t dbl = 3 * n + np + dz + 2 * (size_t)d2;
     size_t ints = dz + 2;
     return dbl * 8 + ((ints * 4 + 15) / 16) * 16 + ((n + 15) / 16) * 16;
 }
 // Workspace shape of a GAVI solve without plans (tableau n x (n+1)).
-__host__ __device__ inline size_t gavi_smem_bytes(int d1, int d2, int np) {
+__host__ __device__ __forceinline__ size_t gavi_smem_bytes(int d1, int d2, int np) {
     const int n = d1 + 2 * d2;
     return tab_smem_bytes(n, n + 1) + gavi_extra_bytes(d1, d2, np);
 }
 
-__device__ inline unsigned char* gavi_carve_extra(GaviSmem& s, const GaviDesc& g, unsigned char* p) {
-    const int n = g.d1 + 2 * g.d2, dz = g.d1 + g.d2;
-    double* d = reinterpret_cast<double*>(p);
-    s.qs = d; d += n;
-    s.zs = d; d += n;
-    s.zb = d; d += n;
-    s.w = d;  d += g.np;
-    s.z0 = d; d += dz;
-    s.c = d;  d += g.d2;
-    s.s0 = d; d += g.d2;
-    s.cols = reinterpret_cast<int*>(d);
-    unsigned char* q = reinterpret_cast<unsigned char*>(d) + (((size_t)(dz + 2) * 4 + 15) / 16) * 16;
-    s.code = reinterpret_cast<int8_t*>(q);
-    return q + (((size_t)n + 15) / 16) * 16;
+// Returns the byte offset just past the extra arrays.
+__device__ __forceinline__ int gavi_carve_extra(GaviSmem& s, const GaviDesc& g, int base_off) {
+    s.base = base_off; s.n = g.d1 + 2 * g.d2; s.np = g.np; s.dz = g.d1 + g.d2; s.d2 = g.d2;
+    return base_off + (int)gavi_extra_bytes(g.d1, g.d2, g.np);
 }
-__device__ inline unsigned char* gavi_carve(GaviSmem& s, const GaviDesc& g, unsigned char* smem) {
+__device__ __forceinline__ int gavi_carve(GaviSmem& s, const GaviDesc& g, int base_off) {
     const int n = g.d1 + 2 * g.d2;
-    tab_carve(s.t, n, n + 1, smem);
-    return gavi_carve_extra(s, g, smem + tab_smem_bytes(n, n + 1));
+    tab_carve(s.t, n, n + 1, base_off);
+    return gavi_carve_extra(s, g, base_off + (int)tab_smem_bytes(n, n + 1));
 }
 
 // s0 = A z0 + B w (c = B w kept).  Ends with a barrier.
-__device__ inline void gavi_slack(GaviSmem& s, const GaviDesc& g, bool recompute_c) {
+__device__ __forceinline__ void gavi_slack(GaviSmem& s, const GaviDesc& g, bool recompute_c) {
     const int i = threadIdx.x, dz = g.d1 + g.d2;
     for (int r = i; r < g.d2; r += blockDim.x) {
         if (recompute_c) {
             double acc = 0.0;
-            for (int j = 0; j < g.np; ++j) acc = fma(g.B[(size_t)j * g.d2 + r], s.w[j], acc);
-            s.c[r] = acc;
+            for (int j = 0; j < g.np; ++j) acc = fma(g.B[(size_t)j * g.d2 + r], s.w()[j], acc);
+            s.c()[r] = acc;
         }
         double acc = 0.0;
-        for (int j = 0; j < dz; ++j) acc = fma(g.A[(size_t)j * g.d2 + r], s.z0[j], acc);
-        s.s0[r] = acc + s.c[r];
+        for (int j = 0; j < dz; ++j) acc = fma(g.A[(size_t)j * g.d2 + r], s.z0()[j], acc);
+        s.s0()[r] = acc + s.c()[r];
     }
     QPN_SYNC();
 }
 
 // -M of the presolve AVI (avi.jl:79-99 as a lifted KKT system over the non-zero columns `cols`
 // of A):  M = [I -A' 0; A 0 -I; 0 I 0] over [z(k); lambda(d2); s(d2)].  Ends with a barrier.
-__device__ inline void build_presolve(Tab& tt, const GaviDesc& g, const int* cols, int k) {
+__device__ __forceinline__ void build_presolve(Tab& tt, const GaviDesc& g, const int* cols, int k) {
     const int ldr = tt.ldr, d2 = g.d2, pn = k + 2 * d2;
     if (threadIdx.x < pn) {
-        double* row = tt.T + (size_t)threadIdx.x * ldr;
+        double* row = tt.T() + (size_t)threadIdx.x * ldr;
         for (int j = 0; j < pn; ++j) row[j] = 0.0;
     }
     QPN_SYNC();
     for (int e = threadIdx.x; e < k * d2; e += blockDim.x) {
         const int a = e / d2, r = e - a * d2;
         const double v = g.A[(size_t)cols[a] * d2 + r];
-        tt.T[(size_t)a * ldr + (k + r)] = v;         // -(-A')   row a, column k+r
-        tt.T[(size_t)(k + r) * ldr + a] = -v;        // -(A)     row k+r, column a
+        tt.T()[(size_t)a * ldr + (k + r)] = v;         // -(-A')   row a, column k+r
+        tt.T()[(size_t)(k + r) * ldr + a] = -v;        // -(A)     row k+r, column a
     }
-    for (int e = threadIdx.x; e < k; e += blockDim.x) tt.T[(size_t)e * ldr + e] = -1.0;
+    for (int e = threadIdx.x; e < k; e += blockDim.x) tt.T()[(size_t)e * ldr + e] = -1.0;
     for (int e = threadIdx.x; e < d2; e += blockDim.x) {
-        tt.T[(size_t)(k + e) * ldr + (k + d2 + e)] = 1.0;      // -(-1)  row k+e, column k+d2+e
-        tt.T[(size_t)(k + d2 + e) * ldr + (k + e)] = -1.0;     // -(+1)  row k+d2+e, column k+e
+        tt.T()[(size_t)(k + e) * ldr + (k + d2 + e)] = 1.0;      // -(-1)  row k+e, column k+d2+e
+        tt.T()[(size_t)(k + d2 + e) * ldr + (k + e)] = -1.0;     // -(+1)  row k+d2+e, column k+e
     }
     QPN_SYNC();
 }
 
 // -M of the lifted AVI of `convert` (avi.jl:113-128): M = [M 0; A -I; 0 I 0].  Ends with a barrier.
-__device__ inline void build_lifted(Tab& tt, const GaviDesc& g) {
+__device__ __forceinline__ void build_lifted(Tab& tt, const GaviDesc& g) {
     const int ldr = tt.ldr, r = threadIdx.x, d1 = g.d1, d2 = g.d2, dz = d1 + d2, n = d1 + 2 * d2;
     if (r < n) {
-        double* row = tt.T + (size_t)r * ldr;
+        double* row = tt.T() + (size_t)r * ldr;
         if (r < d1) {
             for (int j = 0; j < dz; ++j) row[j] = -g.M[(size_t)j * d1 + r];
             for (int j = dz; j < n; ++j) row[j] = 0.0;
@@ -212,7 +212,7 @@ __device__ inline void build_lifted(Tab& tt, const GaviDesc& g) {
 }
 
 // Non-zero columns of A into cols[0..k), k into cols[dz].  Ends with a barrier.
-__device__ inline void find_cols(const GaviDesc& g, int* cols) {
+__device__ __forceinline__ void find_cols(const GaviDesc& g, int* cols) {
     const int dz = g.d1 + g.d2, d2 = g.d2, i = threadIdx.x;
     for (int j = i; j < dz; j += blockDim.x) {
         bool nz = false;
@@ -228,10 +228,10 @@ __device__ inline void find_cols(const GaviDesc& g, int* cols) {
     QPN_SYNC();
 }
 
-// solve_gavi (avi.jl:101-111) for the instance whose w and z0 are already in s.w / s.z0.
+// solve_gavi (avi.jl:101-111) for the instance whose w and z0 are already in s.w() / s.z0().
 // planA (lifted AVI) / planB (presolve AVI) may be null: the instance then runs phase 0 itself.
-// On return s.zs holds the lifted solution [z1; z2; s] and s.code the basis codes.
-__device__ inline int gavi_solve_smem(GaviSmem& s, const GaviDesc& g, const PlanDesc* planA, const PlanDesc* planB,
+// On return s.zs() holds the lifted solution [z1; z2; s] and s.code() the basis codes.
+__device__ __forceinline__ int gavi_solve_smem(GaviSmem& s, const GaviDesc& g, const PlanDesc* planA, const PlanDesc* planB,
                                       int presolve, int max_pivots, int* pivots) {
     const int d1 = g.d1, d2 = g.d2, dz = d1 + d2, n = d1 + 2 * d2, i = threadIdx.x;
     Tab& t = s.t;
@@ -239,7 +239,7 @@ __device__ inline int gavi_solve_smem(GaviSmem& s, const GaviDesc& g, const Plan
     if (presolve && d2 > 0) {
         int infeasible = 0;
         for (int r = i; r < d2; r += blockDim.x)
-            if (!(g.l2[r] <= s.s0[r] && s.s0[r] <= g.u2[r])) infeasible = 1;
+            if (!(g.l2[r] <= s.s0()[r] && s.s0()[r] <= g.u2[r])) infeasible = 1;
         infeasible = QPN_SYNC_OR(infeasible);
         if (infeasible) {
             // find_closest_feasible! (avi.jl:79-99): min |z - z0|^2 s.t. l2 - Bw <= A z <= u2 - Bw over
@@ -247,28 +247,28 @@ __device__ inline int gavi_solve_smem(GaviSmem& s, const GaviDesc& g, const Plan
             const int* cols;
             int k;
             if (planB) { cols = planB->cols; k = planB->ncols; }
-            else { find_cols(g, s.cols); cols = s.cols; k = s.cols[dz]; }
+            else { find_cols(g, s.cols()); cols = s.cols(); k = s.cols()[dz]; }
             const int pn = k + 2 * d2;
             if (i < pn) {
-                if (i < k) { s.qs[i] = -s.z0[cols[i]]; s.zs[i] = s.z0[cols[i]]; t.l[i] = -QPN_INF; t.u[i] = QPN_INF; }
+                if (i < k) { s.qs()[i] = -s.z0()[cols[i]]; s.zs()[i] = s.z0()[cols[i]]; t.l()[i] = -QPN_INF; t.u()[i] = QPN_INF; }
                 else if (i < k + d2) {
                     const int r = i - k;
                     double full = 0.0, part = 0.0;
-                    for (int j = 0; j < dz; ++j) full = fma(g.A[(size_t)j * d2 + r], s.z0[j], full);
-                    for (int a = 0; a < k; ++a) part = fma(g.A[(size_t)cols[a] * d2 + r], s.z0[cols[a]], part);
-                    s.qs[i] = (full - part) + s.c[r];
-                    s.zs[i] = 0.0; t.l[i] = -QPN_INF; t.u[i] = QPN_INF;
+                    for (int j = 0; j < dz; ++j) full = fma(g.A[(size_t)j * d2 + r], s.z0()[j], full);
+                    for (int a = 0; a < k; ++a) part = fma(g.A[(size_t)cols[a] * d2 + r], s.z0()[cols[a]], part);
+                    s.qs()[i] = (full - part) + s.c()[r];
+                    s.zs()[i] = 0.0; t.l()[i] = -QPN_INF; t.u()[i] = QPN_INF;
                 } else {
                     const int r = i - k - d2;
-                    s.qs[i] = 0.0; s.zs[i] = s.s0[r]; t.l[i] = g.l2[r]; t.u[i] = g.u2[r];
+                    s.qs()[i] = 0.0; s.zs()[i] = s.s0()[r]; t.l()[i] = g.l2[r]; t.u()[i] = g.u2[r];
                 }
             }
             QPN_SYNC();
             int pst;
-            if (planB) pst = solve_avi_plan(t, *planB, s.qs, s.zs, s.zb, 50 * pn + 100, nullptr, pivots);
-            else pst = solve_avi_smem(t, pn, [&](Tab& tt) { build_presolve(tt, g, cols, k); }, s.qs, s.zs, 50 * pn + 100, nullptr, pivots);
+            if (planB) pst = solve_avi_plan(t, *planB, s.qs(), s.zs(), s.zb(), 50 * pn + 100, nullptr, pivots);
+            else pst = solve_avi_smem(t, pn, [&](Tab& tt) { build_presolve(tt, g, cols, k); }, s.qs(), s.zs(), 50 * pn + 100, nullptr, pivots);
             QPN_SYNC();
-            if (pst == ST_SUCCESS && i < k) s.z0[cols[i]] = s.zs[i];
+            if (pst == ST_SUCCESS && i < k) s.z0()[cols[i]] = s.zs()[i];
             QPN_SYNC();
             gavi_slack(s, g, false);
         }
@@ -277,41 +277,41 @@ __device__ inline int gavi_solve_smem(GaviSmem& s, const GaviDesc& g, const Plan
     if (i < n) {
         if (i < d1) {
             double acc = 0.0;
-            for (int j = 0; j < g.np; ++j) acc = fma(g.N[(size_t)j * d1 + i], s.w[j], acc);
-            s.qs[i] = acc + g.o[i];
-            t.l[i] = g.l1[i]; t.u[i] = g.u1[i];
+            for (int j = 0; j < g.np; ++j) acc = fma(g.N[(size_t)j * d1 + i], s.w()[j], acc);
+            s.qs()[i] = acc + g.o[i];
+            t.l()[i] = g.l1[i]; t.u()[i] = g.u1[i];
         } else if (i < dz) {
-            s.qs[i] = s.c[i - d1]; t.l[i] = -QPN_INF; t.u[i] = QPN_INF;
+            s.qs()[i] = s.c()[i - d1]; t.l()[i] = -QPN_INF; t.u()[i] = QPN_INF;
         } else {
-            s.qs[i] = 0.0; t.l[i] = g.l2[i - dz]; t.u[i] = g.u2[i - dz];
+            s.qs()[i] = 0.0; t.l()[i] = g.l2[i - dz]; t.u()[i] = g.u2[i - dz];
         }
-        s.zs[i] = i < dz ? s.z0[i] : s.s0[i - dz];
+        s.zs()[i] = i < dz ? s.z0()[i] : s.s0()[i - dz];
     }
     QPN_SYNC();
-    if (planA) return solve_avi_plan(t, *planA, s.qs, s.zs, s.zb, max_pivots, s.code, pivots);
-    return solve_avi_smem(t, n, [&](Tab& tt) { build_lifted(tt, g); }, s.qs, s.zs, max_pivots, s.code, pivots);
+    if (planA) return solve_avi_plan(t, *planA, s.qs(), s.zs(), s.zb(), max_pivots, s.code(), pivots);
+    return solve_avi_smem(t, n, [&](Tab& tt) { build_lifted(tt, g); }, s.qs(), s.zs(), max_pivots, s.code(), pivots);
 }
 
-__global__ void gavi_solve_kernel(GaviDesc g, int batch, const double* __restrict__ w,
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 768 / MAXT) gavi_solve_kernel(const __grid_constant__ GaviDesc g, int batch, const double* __restrict__ w,
                                   const double* __restrict__ z0, int presolve, int max_pivots,
                                   double* __restrict__ z_out, double* __restrict__ zfull_out,
                                   int32_t* __restrict__ status_out, int32_t* __restrict__ pivots_out,
                                   int8_t* __restrict__ basis_out) {
-    extern __shared__ __align__(16) unsigned char smem[];
     const int b = blockIdx.x, i = threadIdx.x;
     const int dz = g.d1 + g.d2, n = g.d1 + 2 * g.d2;
     GaviSmem s;
-    gavi_carve(s, g, smem);
-    for (int j = i; j < g.np; j += blockDim.x) s.w[j] = w[(size_t)b * g.np + j];
-    for (int j = i; j < dz; j += blockDim.x) s.z0[j] = z0[(size_t)b * dz + j];
+    gavi_carve(s, g, 0);
+    for (int j = i; j < g.np; j += blockDim.x) s.w()[j] = w[(size_t)b * g.np + j];
+    for (int j = i; j < dz; j += blockDim.x) s.z0()[j] = z0[(size_t)b * dz + j];
     QPN_SYNC();
     int piv = 0;
     const int st = gavi_solve_smem(s, g, nullptr, nullptr, presolve, max_pivots, &piv);
     QPN_SYNC();
-    if (i < dz) z_out[(size_t)b * dz + i] = s.zs[i];
+    if (i < dz) z_out[(size_t)b * dz + i] = s.zs()[i];
     if (i < n) {
-        if (zfull_out) zfull_out[(size_t)b * n + i] = s.zs[i];
-        if (basis_out) basis_out[(size_t)b * n + i] = s.code[i];
+        if (zfull_out) zfull_out[(size_t)b * n + i] = s.zs()[i];
+        if (basis_out) basis_out[(size_t)b * n + i] = s.code()[i];
     }
     if (i == 0) { status_out[b] = st; pivots_out[b] = piv; }
 }
@@ -319,41 +319,40 @@ __global__ void gavi_solve_kernel(GaviDesc g, int batch, const double* __restric
 // ---- plan construction: one CTA, once per shared matrix ---------------------------------------
 // kind 0: lifted AVI of the GAVI; kind 1: its presolve AVI.  Buffers are sized by the host for the
 // worst case (T0: n x row_stride(n+1), CSR: n*n entries).  hdr: [ncol0, npiv0, tcol0, ncols].
-__global__ void plan_build_kernel(GaviDesc g, int kind, double* __restrict__ T0, double* __restrict__ PT,
+__global__ void plan_build_kernel(const __grid_constant__ GaviDesc g, int kind, double* __restrict__ T0, double* __restrict__ PT,
                                   int* __restrict__ rowvar0, int* __restrict__ colvar0, int* __restrict__ csr_ptr,
                                   int* __restrict__ csr_col, double* __restrict__ csr_val, int* __restrict__ cols_out,
                                   int* __restrict__ hdr) {
-    extern __shared__ __align__(16) unsigned char smem[];
     const int i = threadIdx.x, d1 = g.d1, d2 = g.d2, dz = d1 + d2;
     GaviSmem s;
-    gavi_carve(s, g, smem);
+    gavi_carve(s, g, 0);
     Tab& t = s.t;
     int n, k = 0;
     if (kind == 1) {
-        find_cols(g, s.cols);
-        k = s.cols[dz];
+        find_cols(g, s.cols());
+        k = s.cols()[dz];
         n = k + 2 * d2;
-        for (int j = i; j < k; j += blockDim.x) cols_out[j] = s.cols[j];
+        for (int j = i; j < k; j += blockDim.x) cols_out[j] = s.cols()[j];
         if (i < n) {
             const bool fr = i < k + d2;
-            t.l[i] = fr ? -QPN_INF : g.l2[i - k - d2];
-            t.u[i] = fr ? QPN_INF : g.u2[i - k - d2];
+            t.l()[i] = fr ? -QPN_INF : g.l2[i - k - d2];
+            t.u()[i] = fr ? QPN_INF : g.u2[i - k - d2];
         }
     } else {
         n = d1 + 2 * d2;
         if (i < n) {
-            t.l[i] = i < d1 ? g.l1[i] : i < dz ? -QPN_INF : g.l2[i - dz];
-            t.u[i] = i < d1 ? g.u1[i] : i < dz ? QPN_INF : g.u2[i - dz];
+            t.l()[i] = i < d1 ? g.l1[i] : i < dz ? -QPN_INF : g.l2[i - dz];
+            t.u()[i] = i < d1 ? g.u1[i] : i < dz ? QPN_INF : g.u2[i - dz];
         }
     }
-    if (i < n) { s.qs[i] = 0.0; s.zs[i] = 0.0; }
+    if (i < n) { s.qs()[i] = 0.0; s.zs()[i] = 0.0; }
     QPN_SYNC();
     tab_shape(t, n, n + 1);
-    if (kind == 1) build_presolve(t, g, s.cols, k); else build_lifted(t, g);
+    if (kind == 1) build_presolve(t, g, s.cols(), k); else build_lifted(t, g);
     // the original matrix in CSR (rows ascending in the column index)
-    int* cnt = reinterpret_cast<int*>(s.zb);
+    int* cnt = reinterpret_cast<int*>(s.zb());
     if (i < n) {
-        const double* row = t.T + (size_t)i * t.ldr;
+        const double* row = t.T() + (size_t)i * t.ldr;
         int c = 0;
         for (int j = 0; j < n; ++j) c += (row[j] != 0.0);
         cnt[i] = c;
@@ -366,25 +365,25 @@ __global__ void plan_build_kernel(GaviDesc g, int kind, double* __restrict__ T0,
     }
     QPN_SYNC();
     if (i < n) {
-        const double* row = t.T + (size_t)i * t.ldr;
+        const double* row = t.T() + (size_t)i * t.ldr;
         int o = csr_ptr[i];
         for (int j = 0; j < n; ++j) if (row[j] != 0.0) { csr_col[o] = j; csr_val[o] = -row[j]; ++o; }
     }
     QPN_SYNC();
-    tab_start(t, s.qs, s.zs);
+    tab_start(t, s.qs(), s.zs());
     // phase 0 exactly as crash() runs it
     for (int v = 0; v < n; ++v) {
         if (!is_free_var(t, v)) continue;
-        const int c = t.colof[v];
+        const int c = t.colof()[v];
         const int rho = best_free_row(t, c);
         if (rho >= 0) { pivot(t, rho, c, false); set_zst(t, v, BASIC); }
     }
     // B^-1 from the slack columns (see recompute_tcol)
     if (i < n) {
-        const double* row = t.T + (size_t)i * t.ldr;
+        const double* row = t.T() + (size_t)i * t.ldr;
         for (int kk = 0; kk < n; ++kk) {
-            const int ck = t.colof[n + kk];
-            PT[(size_t)kk * n + i] = ck >= 0 ? -row[ck] : (t.rowof[n + kk] == i ? -1.0 : 0.0);
+            const int ck = t.colof()[n + kk];
+            PT[(size_t)kk * n + i] = ck >= 0 ? -row[ck] : (t.rowof()[n + kk] == i ? -1.0 : 0.0);
         }
     }
     const int npiv0 = t.pivots;
@@ -392,12 +391,12 @@ __global__ void plan_build_kernel(GaviDesc g, int kind, double* __restrict__ T0,
     compact_dead(t);
     const int ncol0 = t.ncol, ldr0 = row_stride(ncol0);
     if (i < n) {
-        const double* row = t.T + (size_t)i * t.ldr;
+        const double* row = t.T() + (size_t)i * t.ldr;
         for (int j = 0; j < ldr0; ++j) T0[(size_t)i * ldr0 + j] = j < ncol0 ? row[j] : 0.0;
-        rowvar0[i] = t.rowvar[i];
+        rowvar0[i] = t.rowvar()[i];
     }
-    for (int j = i; j < ncol0; j += blockDim.x) colvar0[j] = t.colvar[j];
-    if (i == 0) { hdr[0] = ncol0; hdr[1] = npiv0; hdr[2] = t.colof[2 * n]; hdr[3] = k; }
+    for (int j = i; j < ncol0; j += blockDim.x) colvar0[j] = t.colvar()[j];
+    if (i == 0) { hdr[0] = ncol0; hdr[1] = npiv0; hdr[2] = t.colof()[2 * n]; hdr[3] = k; }
 }
 
 // ---- verify_solution (qp_processing.jl:57-149) ---------------------------------------------------
@@ -408,48 +407,35 @@ struct NodeDesc {
 };
 
 struct VerifySmem {
-    double *qt;     // nd   (standalone kernel only; the level kernel points these at its batched arrays)
-    double *ax;     // m
-    double *Ab;     // nd x m
-    double *Ab0;    // nd x m
-    double *b;      // nd
-    double *lam;    // m
-    double *v;      // nd + m
-    double *lam_out;// m
-    double *qs, *zs;// m each (fallback AVI)
-    int *idx;       // m
-    int *perm;      // m
-    int8_t *kind;   // m
+    int base, nd, m;      // byte offset in qpn_smem and the sizes it was carved for
+    __device__ __forceinline__ double* dbl(int off) const { return reinterpret_cast<double*>(qpn_smem + base) + off; }
+    __device__ __forceinline__ double* Ab() const { return dbl(0); }                          // nd x m
+    __device__ __forceinline__ double* Ab0() const { return dbl(nd * m); }                    // nd x m
+    __device__ __forceinline__ double* b() const { return dbl(2 * nd * m); }                  // nd
+    __device__ __forceinline__ double* lam() const { return dbl(2 * nd * m + nd); }           // m
+    __device__ __forceinline__ double* v() const { return dbl(2 * nd * m + nd + m); }         // nd + m
+    __device__ __forceinline__ double* lam_out() const { return dbl(2 * nd * m + 2 * nd + 2 * m); }   // m
+    __device__ __forceinline__ double* qs() const { return dbl(2 * nd * m + 2 * nd + 3 * m); }        // m (fallback AVI)
+    __device__ __forceinline__ double* zs() const { return dbl(2 * nd * m + 2 * nd + 4 * m); }        // m
+    __device__ __forceinline__ int* idx() const { return reinterpret_cast<int*>(dbl(2 * nd * m + 2 * nd + 5 * m)); }   // m
+    __device__ __forceinline__ int* perm() const { return idx() + m; }                        // m
+    __device__ __forceinline__ int8_t* kind() const {                                         // m
+        return reinterpret_cast<int8_t*>(reinterpret_cast<unsigned char*>(idx()) + ((2 * m * 4 + 15) / 16) * 16);
+    }
 };
 
-__host__ __device__ inline size_t verify_smem_bytes(int nd, int m) {
-    size_t dbl = (size_t)nd + m + 2 * (size_t)nd * m + nd + m + (nd + m) + m + 2 * (size_t)m;
+__host__ __device__ __forceinline__ size_t verify_smem_bytes(int nd, int m) {
+    size_t dbl = 2 * (size_t)nd * m + 2 * (size_t)nd + 5 * (size_t)m;
     size_t ints = 2 * (size_t)m;
-    return dbl * 8 + ((ints * 4 + 7) / 8) * 8 + (((size_t)m + 7) / 8) * 8;
+    return dbl * 8 + ((ints * 4 + 15) / 16) * 16 + (((size_t)m + 15) / 16) * 16;
 }
 
-__device__ inline void verify_carve(VerifySmem& v, int nd, int m, unsigned char* p) {
-    double* d = reinterpret_cast<double*>(p);
-    v.qt = d; d += nd;
-    v.ax = d; d += m;
-    v.Ab = d; d += (size_t)nd * m;
-    v.Ab0 = d; d += (size_t)nd * m;
-    v.b = d; d += nd;
-    v.lam = d; d += m;
-    v.v = d; d += nd + m;
-    v.lam_out = d; d += m;
-    v.qs = d; d += m;
-    v.zs = d; d += m;
-    int* ip = reinterpret_cast<int*>(d);
-    v.idx = ip; ip += m;
-    v.perm = ip; ip += m;
-    v.kind = reinterpret_cast<int8_t*>(reinterpret_cast<unsigned char*>(d) + (((size_t)2 * m * 4 + 7) / 8) * 8);
-}
+__device__ __forceinline__ void verify_carve(VerifySmem& v, int nd, int m, int base_off) { v.base = base_off; v.nd = nd; v.m = m; }
 
 // Householder QR least squares with column pivoting, one thread per column; reductions run
 // down a column sequentially so the bits match oracle/qpn_oracle.c:lstsq_basic.
 // `red` gives the block reduction scratch (Tab with red_d / red_i).
-__device__ inline void lstsq_basic_block(const Tab& red, int nd, int k, double* Ab, double* b, double* lam,
+__device__ __forceinline__ void lstsq_basic_block(const Tab& red, int nd, int k, double* Ab, double* b, double* lam,
                                          int* perm, double* v) {
     const int j = threadIdx.x;
     const int steps = nd < k ? nd : k;
@@ -513,7 +499,7 @@ __device__ inline void lstsq_basic_block(const Tab& red, int nd, int k, double* 
 
 // Gradient and constraint values of one node:  qt = Q[dec,:] x + q[dec],  ax = A x.
 // Thread r takes row r; each dot product is sequential in the variable index.
-__device__ inline void node_products(const NodeDesc& nd_, const double* x, double* qt, double* ax) {
+__device__ __forceinline__ void node_products(const NodeDesc& nd_, const double* x, double* qt, double* ax) {
     const int nd = nd_.nd, nv = nd_.nv, m = nd_.m;
     for (int r = threadIdx.x; r < nd + m; r += blockDim.x) {
         double acc = 0.0;
@@ -529,19 +515,19 @@ __device__ inline void node_products(const NodeDesc& nd_, const double* x, doubl
 }
 
 // Returns 1 when the point whose products qt / ax are given is a solution for the node; lam in
-// vs.lam_out.  tab: a tableau workspace large enough for an AVI of size m (used by the fallback
+// vs.lam_out().  tab: a tableau workspace large enough for an AVI of size m (used by the fallback
 // and for the reduction scratch).  qt / ax must be complete (barrier) on entry.
-__device__ inline int verify_solution_smem(Tab& tab, VerifySmem& vs, const NodeDesc& nd_, const double* qt, const double* ax,
+__device__ __forceinline__ int verify_solution_smem(Tab& tab, VerifySmem& vs, const NodeDesc& nd_, const double* qt, const double* ax,
                                            double tol, int* how, int* pivots) {
     const int nd = nd_.nd, m = nd_.m, i = threadIdx.x;
     int infeasible = 0;
     for (int r = i; r < m; r += blockDim.x) {
         const double acc = ax[r];
-        vs.lam_out[r] = 0.0;
+        vs.lam_out()[r] = 0.0;
         const double lo = nd_.l[r], up = nd_.u[r];
         if (!((lo - 1e-3 <= acc) && (acc - 1e-3 <= up))) infeasible = 1;
         const bool pos = acc < lo + 1e-2, neg = acc > up - 1e-2;
-        vs.kind[r] = (pos && neg) ? 3 : pos ? 1 : neg ? 2 : 0;
+        vs.kind()[r] = (pos && neg) ? 3 : pos ? 1 : neg ? 2 : 0;
     }
     infeasible = QPN_SYNC_OR(infeasible);
     if (infeasible) { *how = 0; return 0; }
@@ -551,13 +537,13 @@ __device__ inline int verify_solution_smem(Tab& tab, VerifySmem& vs, const NodeD
     // order the active rows: lower-active, upper-active, both (qp_processing.jl:105-114)
     if (i == 0) {
         int k = 0, np_ = 0, nn = 0;
-        for (int r = 0; r < m; ++r) if (vs.kind[r] == 1) { vs.idx[k++] = r; np_++; }
-        for (int r = 0; r < m; ++r) if (vs.kind[r] == 2) { vs.idx[k++] = r; nn++; }
-        for (int r = 0; r < m; ++r) if (vs.kind[r] == 3) { vs.idx[k++] = r; }
-        tab.red_i[32] = k; tab.red_i[33] = np_; tab.red_i[34] = nn;
+        for (int r = 0; r < m; ++r) if (vs.kind()[r] == 1) { vs.idx()[k++] = r; np_++; }
+        for (int r = 0; r < m; ++r) if (vs.kind()[r] == 2) { vs.idx()[k++] = r; nn++; }
+        for (int r = 0; r < m; ++r) if (vs.kind()[r] == 3) { vs.idx()[k++] = r; }
+        tab.red_i()[32] = k; tab.red_i()[33] = np_; tab.red_i()[34] = nn;
     }
     QPN_SYNC();
-    const int k = tab.red_i[32], np_ = tab.red_i[33], nn = tab.red_i[34];
+    const int k = tab.red_i()[32], np_ = tab.red_i()[33], nn = tab.red_i()[34];
     if (k == 0) {
         // No active row: lam = 0 and the residual is qt itself.  The least-squares step rejects
         // (else we would have returned above only for m == 0) unless |qt| <= tol; the fallback has
@@ -570,30 +556,30 @@ __device__ inline int verify_solution_smem(Tab& tab, VerifySmem& vs, const NodeD
     for (int e = i; e < nd * k; e += blockDim.x) {
         const int tcol = e / nd, r = e - tcol * nd;
         const double sgn = (tcol >= np_ && tcol < np_ + nn) ? -1.0 : 1.0;
-        const double val = sgn * nd_.A[(size_t)nd_.dec[r] * m + vs.idx[tcol]];
-        vs.Ab[e] = val; vs.Ab0[e] = val;
+        const double val = sgn * nd_.A[(size_t)nd_.dec[r] * m + vs.idx()[tcol]];
+        vs.Ab()[e] = val; vs.Ab0()[e] = val;
     }
-    for (int r = i; r < nd; r += blockDim.x) vs.b[r] = qt[r];
+    for (int r = i; r < nd; r += blockDim.x) vs.b()[r] = qt[r];
     QPN_SYNC();
-    lstsq_basic_block(tab, nd, k, vs.Ab, vs.b, vs.lam, vs.perm, vs.v);
+    lstsq_basic_block(tab, nd, k, vs.Ab(), vs.b(), vs.lam(), vs.perm(), vs.v());
     // acceptance (qp_processing.jl:119)
     if (i == 0) {
         int ok = 1;
-        for (int t = 0; t < np_ + nn; ++t) if (!(vs.lam[t] > -tol)) ok = 0;
+        for (int t = 0; t < np_ + nn; ++t) if (!(vs.lam()[t] > -tol)) ok = 0;
         double res = 0.0;
         for (int r = 0; r < nd; ++r) {
             double acc = 0.0;
-            for (int t = 0; t < k; ++t) acc = fma(vs.Ab0[(size_t)t * nd + r], vs.lam[t], acc);
+            for (int t = 0; t < k; ++t) acc = fma(vs.Ab0()[(size_t)t * nd + r], vs.lam()[t], acc);
             const double e = acc - qt[r];
             res = fma(e, e, res);
         }
         if (!(sqrt(res) <= tol)) ok = 0;
-        tab.red_i[35] = ok;
+        tab.red_i()[35] = ok;
     }
     QPN_SYNC();
-    if (tab.red_i[35]) {
+    if (tab.red_i()[35]) {
         for (int t = i; t < k; t += blockDim.x)
-            vs.lam_out[vs.idx[t]] = (t >= np_ && t < np_ + nn) ? -vs.lam[t] : vs.lam[t];
+            vs.lam_out()[vs.idx()[t]] = (t >= np_ && t < np_ + nn) ? -vs.lam()[t] : vs.lam()[t];
         QPN_SYNC();
         *how = 2;
         return 1;
@@ -604,11 +590,11 @@ __device__ inline int verify_solution_smem(Tab& tab, VerifySmem& vs, const NodeD
     for (int r = i; r < m; r += blockDim.x) {
         double acc = 0.0;
         for (int t = 0; t < nd; ++t) acc = fma(nd_.A[(size_t)nd_.dec[t] * m + r], qt[t], acc);
-        vs.qs[r] = -acc;
-        vs.zs[r] = 0.0;
-        const int8_t kd = vs.kind[r];
-        tab.l[r] = (kd == 2 || kd == 3) ? -QPN_INF : 0.0;
-        tab.u[r] = (kd == 1 || kd == 3) ? QPN_INF : 0.0;
+        vs.qs()[r] = -acc;
+        vs.zs()[r] = 0.0;
+        const int8_t kd = vs.kind()[r];
+        tab.l()[r] = (kd == 2 || kd == 3) ? -QPN_INF : 0.0;
+        tab.u()[r] = (kd == 1 || kd == 3) ? QPN_INF : 0.0;
     }
     QPN_SYNC();
     auto build = [&](Tab& tt) {
@@ -617,12 +603,12 @@ __device__ inline int verify_solution_smem(Tab& tab, VerifySmem& vs, const NodeD
             const int c = e / m, r = e - c * m;
             double acc = 0.0;
             for (int t = 0; t < nd; ++t) acc = fma(nd_.A[(size_t)nd_.dec[t] * m + r], nd_.A[(size_t)nd_.dec[t] * m + c], acc);
-            tt.T[(size_t)r * ldr + c] = -acc;
+            tt.T()[(size_t)r * ldr + c] = -acc;
         }
         QPN_SYNC();
     };
     const int n_keep = tab.n;
-    const int st = solve_avi_smem(tab, m, build, vs.qs, vs.zs, 50 * m + 100, nullptr, pivots);
+    const int st = solve_avi_smem(tab, m, build, vs.qs(), vs.zs(), 50 * m + 100, nullptr, pivots);
     tab.n = n_keep;
     QPN_SYNC();
     if (st != ST_SUCCESS) { *how = 5; return 0; }
@@ -630,32 +616,31 @@ __device__ inline int verify_solution_smem(Tab& tab, VerifySmem& vs, const NodeD
         double res2 = 0.0;
         for (int t = 0; t < nd; ++t) {
             double acc = 0.0;
-            for (int r = 0; r < m; ++r) acc = fma(nd_.A[(size_t)nd_.dec[t] * m + r], vs.zs[r], acc);
+            for (int r = 0; r < m; ++r) acc = fma(nd_.A[(size_t)nd_.dec[t] * m + r], vs.zs()[r], acc);
             const double e = acc - qt[t];
             res2 = fma(e, e, res2);
         }
-        tab.red_i[35] = sqrt(res2) <= 1e-4 ? 1 : 0;
+        tab.red_i()[35] = sqrt(res2) <= 1e-4 ? 1 : 0;
     }
-    for (int r = i; r < m; r += blockDim.x) vs.lam_out[r] = vs.zs[r];
+    for (int r = i; r < m; r += blockDim.x) vs.lam_out()[r] = vs.zs()[r];
     QPN_SYNC();
-    const int ok2 = tab.red_i[35];
+    const int ok2 = tab.red_i()[35];
     *how = ok2 ? 3 : 4;
     return ok2;
 }
 
 // grid = batch, block = roundup32(max(m, nd, 1)).  Dynamic smem: Tab(m, m+1) + VerifySmem + x(nv) + qt(nd) + ax(m).
-__global__ void verify_solution_kernel(NodeDesc node, int batch, const double* __restrict__ x, double tol,
+__global__ void verify_solution_kernel(const __grid_constant__ NodeDesc node, int batch, const double* __restrict__ x, double tol,
                                        uint8_t* __restrict__ solution_out, double* __restrict__ lam_out,
                                        int32_t* __restrict__ how_out, int8_t* __restrict__ active_out) {
-    extern __shared__ __align__(16) unsigned char smem[];
     const int b = blockIdx.x, i = threadIdx.x, m = node.m;
     const int tn = m > 0 ? m : 1;
     Tab tab;
-    tab_carve(tab, tn, tn + 1, smem);
+    tab_carve(tab, tn, tn + 1, 0);
     VerifySmem vs;
-    unsigned char* p = smem + tab_smem_bytes(tn, tn + 1);
+    const int p = (int)tab_smem_bytes(tn, tn + 1);
     verify_carve(vs, node.nd, m, p);
-    double* xs = reinterpret_cast<double*>(p + verify_smem_bytes(node.nd, m));
+    double* xs = reinterpret_cast<double*>(qpn_smem + p + verify_smem_bytes(node.nd, m));
     double* qt = xs + node.nv;
     double* ax = qt + node.nd;
     for (int j = i; j < node.nv; j += blockDim.x) xs[j] = x[(size_t)b * node.nv + j];
@@ -666,8 +651,8 @@ __global__ void verify_solution_kernel(NodeDesc node, int batch, const double* _
     const int sol = verify_solution_smem(tab, vs, node, qt, ax, tol, &how, &piv);
     QPN_SYNC();
     for (int r = i; r < m; r += blockDim.x) {
-        if (lam_out) lam_out[(size_t)b * m + r] = vs.lam_out[r];
-        if (active_out) active_out[(size_t)b * m + r] = how == 0 ? 0 : vs.kind[r];
+        if (lam_out) lam_out[(size_t)b * m + r] = vs.lam_out()[r];
+        if (active_out) active_out[(size_t)b * m + r] = how == 0 ? 0 : vs.kind()[r];
     }
     if (i == 0) { solution_out[b] = (uint8_t)sol; if (how_out) how_out[b] = how; }
 }
@@ -710,27 +695,27 @@ __host__ inline void level_workspace_shape(LevelDesc& lv) {
     lv.t_doubles = (int)td; lv.ldr_max = ldr;
 }
 
-__host__ __device__ inline size_t level_smem_bytes(const LevelDesc& lv) {
+__host__ __device__ __forceinline__ size_t level_smem_bytes(const LevelDesc& lv) {
     return tab_smem_bytes_ex(lv.g.d1 + 2 * lv.g.d2, (size_t)lv.t_doubles, lv.ldr_max) + gavi_extra_bytes(lv.g.d1, lv.g.d2, lv.g.np) +
            verify_smem_bytes(lv.max_nd, lv.max_m) +
            8 * (2 * (size_t)lv.nv + (size_t)(lv.nproj > 0 ? lv.nproj : 1) + (size_t)lv.nd_total + (size_t)lv.lam_total);
 }
 
 // hist: global scratch, batch x hist_cap x nproj (cycle check history); hist_count: batch.
-__global__ void level_equilibrium_kernel(LevelDesc lv, int batch, const double* __restrict__ x_init,
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 768 / MAXT) level_equilibrium_kernel(const __grid_constant__ LevelDesc lv, int batch, const double* __restrict__ x_init,
                                          double* __restrict__ x_out, uint8_t* __restrict__ solved_out,
                                          int32_t* __restrict__ iters_out, int32_t* __restrict__ pivots_out,
                                          double* __restrict__ lam_out, double* __restrict__ hist,
                                          int32_t* __restrict__ hist_count, int hist_cap, int presolve) {
-    extern __shared__ __align__(16) unsigned char smem[];
     const int b = blockIdx.x, i = threadIdx.x, nv = lv.nv;
     GaviSmem gs;
     const int n_level = lv.g.d1 + 2 * lv.g.d2;
-    tab_carve_ex(gs.t, n_level, (size_t)lv.t_doubles, lv.ldr_max, smem);
-    unsigned char* p = gavi_carve_extra(gs, lv.g, smem + tab_smem_bytes_ex(n_level, (size_t)lv.t_doubles, lv.ldr_max));
+    tab_carve_ex(gs.t, n_level, (size_t)lv.t_doubles, lv.ldr_max, 0);
+    const int p = gavi_carve_extra(gs, lv.g, (int)tab_smem_bytes_ex(n_level, (size_t)lv.t_doubles, lv.ldr_max));
     VerifySmem vs;
     verify_carve(vs, lv.max_nd, lv.max_m, p);
-    double* xs = reinterpret_cast<double*>(p + verify_smem_bytes(lv.max_nd, lv.max_m));
+    double* xs = reinterpret_cast<double*>(qpn_smem + p + verify_smem_bytes(lv.max_nd, lv.max_m));
     double* pv = xs + nv;                  // nproj
     double* xn = pv + (lv.nproj > 0 ? lv.nproj : 1);
     double* qt_all = xn + nv;              // nd_total
@@ -805,14 +790,14 @@ __global__ void level_equilibrium_kernel(LevelDesc lv, int batch, const double* 
             QPN_SYNC();
             if (lam_out)
                 for (int r = i; r < node.m; r += blockDim.x)
-                    lam_out[(size_t)b * lv.lam_total + lv.m_off[pl] + r] = sol ? vs.lam_out[r] : 0.0;
+                    lam_out[(size_t)b * lv.lam_total + lv.m_off[pl] + r] = sol ? vs.lam_out()[r] : 0.0;
             if (!sol) all_sol = 0;
             QPN_SYNC();
         }
         if (all_sol) { solved = 1; break; }
         // solve_qep (avi.jl:382-444)
-        for (int j = i; j < lv.g.np; j += blockDim.x) gs.w[j] = xs[lv.par[j]];
-        for (int j = i; j < lv.g.d1 + lv.g.d2; j += blockDim.x) gs.z0[j] = j < lv.nd_level ? xs[lv.dec[j]] : 0.0;
+        for (int j = i; j < lv.g.np; j += blockDim.x) gs.w()[j] = xs[lv.par[j]];
+        for (int j = i; j < lv.g.d1 + lv.g.d2; j += blockDim.x) gs.z0()[j] = j < lv.nd_level ? xs[lv.dec[j]] : 0.0;
         QPN_SYNC();
         gs.t.n = n_level;
         const int st = gavi_solve_smem(gs, lv.g, lv.has_plans ? &lv.planA : nullptr, lv.has_plans ? &lv.planB : nullptr, presolve, max_piv, &piv);
@@ -820,7 +805,7 @@ __global__ void level_equilibrium_kernel(LevelDesc lv, int batch, const double* 
         if (st != ST_SUCCESS) break;
         for (int j = i; j < nv; j += blockDim.x) xn[j] = xs[j];
         QPN_SYNC();
-        for (int j = i; j < lv.nd_level; j += blockDim.x) xn[lv.dec[j]] = gs.zs[j];
+        for (int j = i; j < lv.nd_level; j += blockDim.x) xn[lv.dec[j]] = gs.zs()[j];
         QPN_SYNC();
         double dn = 0.0;
         for (int j = 0; j < nv; ++j) { const double e = xn[j] - xs[j]; dn = fma(e, e, dn); }
