@@ -53,7 +53,7 @@ __device__ __forceinline__ double residual_row(const Tab& t, const double* zs, d
 // ---- solve_avi (avi.jl:63-77) ------------------------------------------------------------
 // grid = batch, block = roundup32(n).  Dynamic smem: Tab(n, n+1) + q(n) + z(n).
 template <int MAXT>
-__global__ void __launch_bounds__(MAXT, 768 / MAXT) avi_solve_kernel(int n, int batch, const __grid_constant__ MatDesc M, const double* __restrict__ q,
+__global__ void __launch_bounds__(MAXT, 896 / MAXT) avi_solve_kernel(int n, int batch, const __grid_constant__ MatDesc M, const double* __restrict__ q,
                                  const double* __restrict__ l, const double* __restrict__ u,
                                  int lu_shared, const double* __restrict__ z0, int max_pivots,
                                  double* __restrict__ z_out, int32_t* __restrict__ status_out,

@@ -293,7 +293,7 @@ __device__ __forceinline__ int gavi_solve_smem(GaviSmem& s, const GaviDesc& g, c
 }
 
 template <int MAXT>
-__global__ void __launch_bounds__(MAXT, 768 / MAXT) gavi_solve_kernel(const __grid_constant__ GaviDesc g, int batch, const double* __restrict__ w,
+__global__ void __launch_bounds__(MAXT, 896 / MAXT) gavi_solve_kernel(const __grid_constant__ GaviDesc g, int batch, const double* __restrict__ w,
                                   const double* __restrict__ z0, int presolve, int max_pivots,
                                   double* __restrict__ z_out, double* __restrict__ zfull_out,
                                   int32_t* __restrict__ status_out, int32_t* __restrict__ pivots_out,
@@ -534,8 +534,14 @@ __device__ __forceinline__ int verify_solution_smem(Tab& tab, VerifySmem& vs, co
     double nq = 0.0;
     for (int r = 0; r < nd; ++r) nq = fma(qt[r], qt[r], nq);
     if (m == 0) { *how = 1; return sqrt(nq) <= tol ? 1 : 0; }
+    // no active row at all (the common case at an interior point): skip the serial ordering below
+    int any_active = 0;
+    for (int r = i; r < m; r += blockDim.x) any_active |= (vs.kind()[r] != 0);
+    any_active = QPN_SYNC_OR(any_active);
     // order the active rows: lower-active, upper-active, both (qp_processing.jl:105-114)
-    if (i == 0) {
+    if (!any_active) {
+        if (i == 0) { tab.red_i()[32] = 0; tab.red_i()[33] = 0; tab.red_i()[34] = 0; }
+    } else if (i == 0) {
         int k = 0, np_ = 0, nn = 0;
         for (int r = 0; r < m; ++r) if (vs.kind()[r] == 1) { vs.idx()[k++] = r; np_++; }
         for (int r = 0; r < m; ++r) if (vs.kind()[r] == 2) { vs.idx()[k++] = r; nn++; }
@@ -703,7 +709,7 @@ __host__ __device__ __forceinline__ size_t level_smem_bytes(const LevelDesc& lv)
 
 // hist: global scratch, batch x hist_cap x nproj (cycle check history); hist_count: batch.
 template <int MAXT>
-__global__ void __launch_bounds__(MAXT, 768 / MAXT) level_equilibrium_kernel(const __grid_constant__ LevelDesc lv, int batch, const double* __restrict__ x_init,
+__global__ void __launch_bounds__(MAXT, 896 / MAXT) level_equilibrium_kernel(const __grid_constant__ LevelDesc lv, int batch, const double* __restrict__ x_init,
                                          double* __restrict__ x_out, uint8_t* __restrict__ solved_out,
                                          int32_t* __restrict__ iters_out, int32_t* __restrict__ pivots_out,
                                          double* __restrict__ lam_out, double* __restrict__ hist,
