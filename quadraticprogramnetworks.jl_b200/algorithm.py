@@ -73,7 +73,13 @@ def solve(qpn, x_init=None, device=0):
     Julia's `inits::Matrix` is n_vars x B column-major, i.e. a (B, n_vars) C-contiguous array here."""
     x = qpn.default_initialization if x_init is None else np.asarray(x_init, dtype=np.float64)
     single = x.ndim == 1
-    ret = _solver_for(qpn, device).solve_batch(np.atleast_2d(x))
+    solver = _solver_for(qpn, device)
+    if qpn.num_levels() != 1 or qpn.options.gen_solution_map:
+        # networks with children (or with the solution map requested): host recursion per instance
+        ns = NetSolver(qpn, solver.engine)
+        outs = [ns.solve(xi) for xi in np.atleast_2d(x)]
+        return outs[0] if single else outs
+    ret = solver.solve_batch(np.atleast_2d(x))
     results = []
     for b in range(len(ret["solved"])):
         if ret["solved"][b]:
@@ -83,3 +89,203 @@ def solve(qpn, x_init=None, device=0):
             results.append(dict(solved=False, x_fail=ret["x"][b].copy(), x_opt=None,
                                 iters=int(ret["iters"][b]), pivots=int(ret["pivots"][b])))
     return results[0] if single else results
+
+
+# ==============================================================================================
+# Multi-level networks: host recursion of solve_base! with the numeric steps on the device
+# ==============================================================================================
+import itertools  # noqa: E402
+import math  # noqa: E402
+
+from . import polyhedra as ph  # noqa: E402
+from . import solgraph  # noqa: E402
+
+
+class SolveError(RuntimeError):
+    """The reference raises inside solve_base! and turns it into solved=false (algorithm.jl:120-126)."""
+
+
+def _julia_product(ranges):
+    """Iterators.product order: the FIRST iterator varies fastest (qp_processing.jl:169)."""
+    for tup in itertools.product(*reversed(ranges)):
+        yield tuple(reversed(tup))
+
+
+def intersection_leaves(unions, red_lengths, x, lp):
+    """IntersectionRoot (intersection.jl:55-151): all non-empty intersections of one piece per union
+    that contain x in their closure, skipping the combinations made of complements only."""
+    n = len(unions)
+    full = [len(u) for u in unions]
+    out = []
+
+    def alive(poly):
+        return ph.contains(poly, x, closed=True) and not ph.isempty(poly, lp)
+
+    def rec(depth, poly, idx):
+        if depth == n:
+            if all(i >= f - r for i, f, r in zip(idx, full, red_lengths)):
+                return                                    # the all-complements "red zone" (intersection.jl:123)
+            out.append(poly)
+            return
+        for k, piece in enumerate(unions[depth]):
+            cur = piece if poly is None else ph.intersect(piece, poly)
+            if not alive(cur):
+                continue
+            rec(depth + 1, cur, idx + [k])
+
+    rec(0, None, [])
+    return out
+
+
+class NetSolver:
+    """solve(qpn, x_init) for any QPNet: algorithm.jl:1-127 + qp_processing.jl:151-291 on the host,
+    with verify_solution / solve_qep / comp_indices / every LP on the device engine."""
+
+    def __init__(self, net, engine):
+        self.net, self.engine = net, engine
+        self.lp = ph.LPSolver(engine)
+        self.proj = projection_vectors(net)
+        self.iterate_cache = {}
+
+    # ---- qp_processing.jl:57-149 on the device -----------------------------------------------
+    def verify(self, pid, polys, dec, x):
+        net = self.net
+        qp = net.qps[pid]
+        if polys:
+            A = np.vstack([p.A for p in polys]); l = np.concatenate([p.l for p in polys]); u = np.concatenate([p.u for p in polys])
+        else:
+            A, l, u = np.zeros((0, net.n_vars)), np.zeros(0), np.zeros(0)
+        sol, lam, how, act = self.engine.verify_solution((qp.Q[dec, :], qp.q[dec], A, l, u, np.asarray(dec, np.int32)), x[None, :])
+        return bool(sol[0]), lam[0]
+
+    # ---- avi.jl:382-444 on the device ------------------------------------------------------------
+    def solve_qep(self, players, x, pieces):
+        g, dec, par = assembly.level_gavi(self.net, players, pieces)
+        z0 = np.zeros((1, g["M"].shape[1])); z0[0, :len(dec)] = x[dec]
+        ret = self.engine.gavi_solve(g, x[par][None, :], z0)
+        if int(ret["status"][0]) != 1:
+            raise SolveError("AVI solve error. This might be because one of the qps is unbounded or ill-conditioned.")
+        x_opt = x.copy()
+        x_opt[dec] = ret["z"][0, :len(dec)]
+        return x_opt
+
+    def solution_pieces(self, pid, polys, dec, x, lam):
+        gen = solgraph.process_solution_graph(self.net, pid, polys, dec, x, lam, self.engine, self.lp,
+                                              exploration_vertices=self.net.options.exploration_vertices)
+        return gen.collect()
+
+    # ---- qp_processing.jl:151-241 ------------------------------------------------------------------
+    def process_qp(self, pid, x, S):
+        net = self.net
+        base = [net.constraints[c] for c in net.qps[pid].constraint_indices]
+        dec = net.decision_inds(pid)
+        gen = (pid not in net.network_depth_map[1]) or net.options.gen_solution_map
+        children = sorted(net.network_edges[pid])
+        if children:
+            if any(len(S[j]) < 1 for j in children):
+                raise SolveError("Solution graphs were not properly populated.")
+            results = []
+            for combo in _julia_product([range(len(S[j])) for j in children]):
+                pieces = [S[j][ji] for j, ji in zip(children, combo)]
+                polys = base + pieces
+                ok, lam = self.verify(pid, polys, dec, x)
+                if not ok:
+                    results.append(dict(solution=False, subpiece_assignments=dict(zip(children, combo))))
+                else:
+                    sg = None
+                    if gen:
+                        sg = (pieces, ph.remove_subsets(self.solution_pieces(pid, polys, dec, x, lam), self.lp))
+                    results.append(dict(solution=True, solgraph=sg))
+            for r in results:
+                if not r["solution"]:
+                    return dict(solution=False, failed=False, subpiece_assignments=r["subpiece_assignments"])
+            S_out = None
+            if gen:
+                try:
+                    S_out = self.combine([r["solgraph"] for r in results], x)
+                except SolveError:
+                    return dict(solution=False, failed=True, S=None)
+        else:
+            ok, lam = self.verify(pid, base, dec, x)
+            if not ok:
+                return dict(solution=False, failed=False, subpiece_assignments={})
+            S_out = None
+            if gen:
+                S_out = self.solution_pieces(pid, base, dec, x, lam)
+                if len(S_out) == 0:
+                    raise SolveError("This shouldn't happen. Solution graph is empty.")
+        return dict(solution=True, S=S_out, failed=False)
+
+    # ---- qp_processing.jl:243-291 ---------------------------------------------------------------------
+    def combine(self, solgraphs, x):
+        regions = [ph.intersect(*r) for r, _ in solgraphs]
+        solutions = [s for _, s in solgraphs]
+        if len(solutions) == 0:
+            raise SolveError("No solutions to combine")
+        if len(solutions) == 1:
+            return list(solutions[0])
+        complements = [ph.complement(r) for r in regions]
+        combined = [list(s) + rc for s, rc in zip(solutions, complements)]
+        widths = [len(c) for c in combined]
+        if len(widths) > 3 and sum(widths) > 20:
+            raise SolveError("Too many solutions to combine.")
+        return intersection_leaves(combined, [len(c) for c in complements], x, self.lp)
+
+    # ---- algorithm.jl:1-127 -------------------------------------------------------------------------------
+    def solve(self, x_init):
+        self.iterate_cache = {}
+        return self.solve_base(np.asarray(x_init, dtype=np.float64), 1)
+
+    def solve_base(self, x_init, level):
+        net, opt = self.net, self.net.options
+        x = x_init.copy()
+        try:
+            for _ in range(opt.max_iters):
+                if opt.check_for_cycling:
+                    if opt.num_projections == 0:
+                        raise SolveError("Cycling check requested, but num_projections == 0.")
+                    pv = self.proj @ x
+                    cache = self.iterate_cache.setdefault(level, [])
+                    for prev in cache:
+                        if np.linalg.norm(pv - prev) <= 1.4901161193847656e-8 * max(np.linalg.norm(pv), np.linalg.norm(prev)):
+                            raise SolveError("Cycling detected (noticed solution iterate returned to a previous value).")
+                    cache.append(pv)
+                if level < net.num_levels():
+                    low = self.solve_base(x, level + 1)
+                    if not low["solved"]:
+                        return dict(solved=False, x_fail=x, x_opt=None)
+                    S, x = low["Sol"], low["x_opt"]
+                else:
+                    S = {}
+                players = sorted(net.network_depth_map[level])
+                children = sorted(set().union(*[set(net.network_edges[i]) for i in players]))
+                results = [self.process_qp(pid, x, S) for pid in players]
+                equilibrium = True
+                assignments = {i: S[i][0] for i in children}
+                if any(r["failed"] for r in results):
+                    return dict(solved=False, x_fail=x, x_opt=None)
+                for pid, r in zip(players, results):
+                    if not r["solution"]:
+                        equilibrium = False
+                        if level < net.num_levels():
+                            for child, sub in r["subpiece_assignments"].items():
+                                assignments[child] = S[child][sub]
+                    else:
+                        S[pid] = ph.remove_subsets(r["S"], self.lp) if (r["S"] is not None and self._removes(level)) else r["S"]
+                if not equilibrium:
+                    xnew = self.solve_qep(players, x, assignments)
+                    if np.linalg.norm(xnew - x) < 1e-4:
+                        raise SolveError("Detected disagreement in solution status between qp solution processer and equilibrium solver.")
+                    x = xnew
+                    continue
+                if level == 1:
+                    self.iterate_cache = {}
+                return dict(solved=True, x_opt=x, Sol=S, identified_request=set(), x_alts=[])
+            raise SolveError("Can't find solution")
+        except SolveError as err:
+            self.iterate_cache = {}
+            return dict(solved=False, x_fail=x, x_opt=None, error=str(err))
+
+    def _removes(self, level):
+        lv = self.net.options.levels_to_remove_subsets
+        return True if lv is None else (level in lv)

@@ -247,3 +247,12 @@ def test_resident_level_with_plans_matches_oracle(engine):
     for k in ("x", "iters", "pivots", "lam"):
         assert np.array_equal(ret[k], ro[k]), k
     lv.release()
+
+
+def test_simple_bilevel_known_answers_on_gpu(engine):
+    """The reference's own test (test/simple_bilevel.jl:4-21) end to end on the device engine:
+    every AVI solve, dual recovery, active-set classification and LP of the run is a kernel launch."""
+    from tests.test_multilevel_cpu import check_simple_bilevel_kats
+    before = engine.launches
+    check_simple_bilevel_kats(engine)
+    assert engine.launches > before + 50

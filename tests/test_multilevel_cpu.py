@@ -1,0 +1,84 @@
+"""CPU suite: the reference's ONLY test -- test/simple_bilevel.jl:4-21 (KAT-1..8) -- through the
+multi-level host driver, the polyhedral operations and the solution-graph code.  The numeric
+stand-in here is the CPU oracle (tests/oracle_engine.py); tests/test_gpu_parity.py runs the same
+eight cases on the real engine."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+import qpn_b200
+from qpn_b200 import polyhedra as ph
+from qpn_b200.model import INF, Poly
+from tests.oracle_engine import OracleEngine
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def check_simple_bilevel_kats(engine):
+    kat = json.load(open(os.path.join(GOLDEN, "simple_bilevel_kat.json")))
+    net = qpn_b200.setup(":simple_bilevel", gen_solution_map=True)            # test/simple_bilevel.jl:2
+    ns = qpn_b200.NetSolver(net, engine)
+    for w, X, s in zip(kat["W"], kat["X"], kat["S"]):
+        ret = ns.solve(np.array(w + [0.0, 0.0]))                              # solve(qpn, [w; x0]), :18
+        assert ret["solved"], ret.get("error")
+        assert any(np.allclose(ret["x_opt"], w + xi, atol=1e-4) for xi in X), (w, ret["x_opt"])     # :19
+        assert len(ret["Sol"][2]) >= s, (w, len(ret["Sol"][2]), s)                                 # :20
+
+
+def test_simple_bilevel_known_answers():
+    check_simple_bilevel_kats(OracleEngine())
+
+
+def test_lower_level_solution_map_is_the_kink():
+    """y = max(x, 0): the lower node's solution graph has the pieces {x <= 0, y = 0} and {x >= 0, y = x}."""
+    net = qpn_b200.setup(":simple_bilevel", gen_solution_map=True)
+    ns = qpn_b200.NetSolver(net, OracleEngine())
+    ret = ns.solve_base(np.array([0.3, -0.2, 0.0, 0.0]), 2)                   # x = 0: both pieces meet
+    assert ret["solved"]
+    pieces = ret["Sol"][1]
+    assert len(pieces) == 2
+    for x, y, inside in [(-1.0, 0.0, True), (2.0, 2.0, True), (2.0, 0.0, False), (-1.0, 0.5, False), (1.0, 1.5, False)]:
+        pt = np.array([0.0, 0.0, x, y])
+        assert any(ph.contains(p, pt, tol=1e-9) for p in pieces) == inside, (x, y)
+
+
+def test_polyhedra_operations():
+    lp = ph.LPSolver(OracleEngine())
+    box = Poly(np.eye(2), [0.0, 0.0], [1.0, 1.0])
+    tri = Poly(np.array([[1.0, 0.0], [0.0, 1.0], [1.0, 1.0]]), [0.0, 0.0, -INF], [INF, INF, 1.0])
+    assert ph.issubset(tri, box, lp) and not ph.issubset(box, tri, lp)
+    assert len(ph.remove_subsets([box, tri], lp)) == 1
+    assert not ph.isempty(box, lp) and ph.isempty(ph.intersect(box, Poly(np.array([[1.0, 0.0]]), [2.0], [INF])), lp)
+    # open complement pieces: x in box  xor  x in some complement piece
+    comp = ph.complement(box)
+    assert len(comp) == 4
+    for pt in ([0.5, 0.5], [1.5, 0.5], [0.0, 0.0], [1.0, 1.0 + 1e-3]):
+        inside = ph.contains(box, np.array(pt), tol=0.0)
+        assert inside != any(ph.contains(c, np.array(pt), tol=0.0) for c in comp), pt
+    # an open set touching a closed one in a single point is empty (exemplar's dual-activity rule)
+    touching = ph.intersect(box, Poly(np.array([[1.0, 0.0]]), [1.0], [INF], [True], [True], normalize=False))
+    assert ph.isempty(touching, lp)
+    # projection of the unit simplex in 3-D onto (x, y) is the triangle; of a line segment with an equality
+    simplex = Poly(np.vstack([np.eye(3), np.ones((1, 3))]), [0, 0, 0, -INF], [INF, INF, INF, 1.0])
+    pr = ph.project(simplex, [0, 1], lp)
+    for pt, inside in ([0.2, 0.3], True), ([0.7, 0.7], False), ([-0.1, 0.2], False), ([0.5, 0.5], True):
+        assert ph.contains(pr, np.array(pt), tol=1e-9) == inside, pt
+    seg = Poly(np.array([[1.0, -1.0, 0.0], [0.0, 1.0, -1.0], [1.0, 0.0, 0.0]]), [0.0, 0.0, 0.0], [0.0, 0.0, 2.0])   # x=y=z in [0,2]
+    pr = ph.project(seg, [2], lp)
+    assert ph.contains(pr, np.array([1.5])) and not ph.contains(pr, np.array([2.5])) and not ph.contains(pr, np.array([-0.5]))
+    # simplify merges the two one-sided rows that projection produces into one two-sided slice
+    assert len(ph.simplify(pr)) == 1
+
+
+def test_solve_dispatch_keeps_result_fields():
+    """requests.jl:18-22 / algorithm.jl:116,125: result field names of both outcomes."""
+    net = qpn_b200.setup(":simple_bilevel")
+    ns = qpn_b200.NetSolver(net, OracleEngine())
+    ret = ns.solve(np.array([1.0, 0.0, 0.0, 0.0]))
+    assert ret["solved"] and set(ret) >= {"solved", "x_opt", "Sol", "identified_request", "x_alts"}
+    net.options.max_iters = 1                                               # cannot converge in one iteration from here
+    ret = qpn_b200.NetSolver(net, OracleEngine()).solve(np.array([1.0, 0.0, 3.0, 0.0]))
+    assert (not ret["solved"]) and ret["x_opt"] is None and "x_fail" in ret
