@@ -256,3 +256,8 @@ def test_simple_bilevel_known_answers_on_gpu(engine):
     before = engine.launches
     check_simple_bilevel_kats(engine)
     assert engine.launches > before + 50
+
+
+def test_robust_avoid_three_levels_on_gpu(engine):
+    from tests.test_multilevel_cpu import check_robust_avoid_end_to_end
+    check_robust_avoid_end_to_end(engine, seeds=(3,))

@@ -82,3 +82,34 @@ def test_solve_dispatch_keeps_result_fields():
     net.options.max_iters = 1                                               # cannot converge in one iteration from here
     ret = qpn_b200.NetSolver(net, OracleEngine()).solve(np.array([1.0, 0.0, 3.0, 0.0]))
     assert (not ret["solved"]) and ret["x_opt"] is None and "x_fail" in ret
+
+
+def check_robust_avoid_end_to_end(engine, seeds=(3, 5)):
+    """examples/robust_avoid_simple.jl: three levels (ego -> adversaries -> separating planes),
+    exploration_vertices = 10.  With the stand-in problem data there is no reference
+    output to compare with; the result must be a feasible point at which every node passes the
+    reference's own optimality test against the solution pieces of its children."""
+    for seed in seeds:
+        net = qpn_b200.setup(":robust_avoid_simple", seed=seed)
+        ns = qpn_b200.NetSolver(net, engine)
+        ret = ns.solve(net.default_initialization)
+        assert ret["solved"], (seed, ret.get("error"))
+        x = ret["x_opt"]
+        assert np.array_equal(x[:6], net.default_initialization[:6])          # xe, xo are parameters
+        for P in net.constraints.values():
+            assert ph.contains(P, x, tol=1e-6, closed=True)
+        assert set(ret["Sol"]) == {1, 2, 3, 4, 5} and all(len(ret["Sol"][k]) >= 1 for k in (1, 2, 3, 4))
+        # the bottom level alone: each separating-plane LP is at its optimum for the final (xe+ue, xo+uo)
+        low = ns.solve_base(x, 3)
+        assert low["solved"] and np.allclose(low["x_opt"], x, atol=1e-6)
+
+
+def test_robust_avoid_three_levels():
+    check_robust_avoid_end_to_end(OracleEngine())
+
+
+def test_cycling_exit_is_reported_not_raised():
+    """algorithm.jl:16-30,120-126: a repeated iterate ends the solve with solved=false."""
+    net = qpn_b200.setup(":robust_avoid_simple", seed=1)
+    ret = qpn_b200.NetSolver(net, OracleEngine()).solve(net.default_initialization)
+    assert (not ret["solved"]) and "Cycling" in ret["error"] and ret["x_opt"] is None
