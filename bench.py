@@ -36,6 +36,9 @@ METRIC = "QPNet equilibria/sec (batched AVI solves)"
 UNIT = "equilibria/s"
 WORKLOAD = "four_player_matrix_game Nash (edge_list=[]), random inits ~ U(-5,5)^8, one fused level-equilibrium launch per batch"
 HBM_FALLBACK_GBS = 6650.0     # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+# dram__bytes_read.sum + dram__bytes_write.sum of one level_equilibrium_kernel<32> launch at the default
+# batch (4,096), from profiles/r1_final_level_kernel_ncu_full_summary.csv (ncu --set full, same command)
+NCU_DRAM_BYTES_PER_LAUNCH_B4096 = 439_296 + 1_024
 
 
 def inits_for(rank, batch, step=0):
@@ -289,9 +292,12 @@ def main():
             "e2e": {"value": world * B * K / t_e2e, "unit": UNIT, "h2d_bytes_per_step": B * nv * 8, "d2h_bytes_per_step": B * (nv * 8 + 1 + 4 + 4),
                     "timing": "host clock around the synchronous C-ABI call (qpn_level_equilibrium_resident), pinned buffers"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "kernel": "level_equilibrium_kernel", "peak_source": peak_src,
-                         "note": "the fused pivoting kernel is issue/latency bound in shared memory, not HBM bound; see DESIGN.md"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH_B4096 if B == 4096 else None,
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "kernel": "level_equilibrium_kernel<32>", "peak_source": peak_src,
+                         "note": "the fused pivoting kernel is issue/latency bound in shared memory (ncu: IPC 1.8/SM, fp64 pipe 10 %, "
+                                 "0 % tensor), not HBM bound; see DESIGN.md 5 and profiles/"},
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
