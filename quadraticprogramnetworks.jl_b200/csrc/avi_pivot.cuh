@@ -240,7 +240,7 @@ __device__ __forceinline__ bool artificial_row(const Tab& t, int i) {
 // Expects T[i][0:n] = -M[i][:] (thread i wrote its own row), t.l(), t.u() filled, q and z0
 // readable.  zb = t.prow() is scratch (needs ldr >= n; every caller has cap >= n+1).
 // Ends with a barrier.
-__device__ __forceinline__ void tab_start(Tab& t, const double* q, const double* z0) {
+__device__ __noinline__ void tab_start_core(Tab t, const double* q, const double* z0) {
     const int n = t.n, i = threadIdx.x;
     double* zb = t.prow();
     if (i < n) zb[i] = fmin(fmax(z0[i], t.l()[i]), t.u()[i]);
@@ -268,13 +268,19 @@ __device__ __forceinline__ void tab_start(Tab& t, const double* q, const double*
         t.colvar()[n] = 2 * n; t.nbval()[n] = 0.0;
         t.rowof()[2 * n] = -1; t.colof()[2 * n] = n;
     }
-    t.ncol = n + 1;
-    t.pivots = 0;
     QPN_SYNC();
+}
+__device__ __forceinline__ void tab_start(Tab& t, const double* q, const double* z0) {
+    tab_start_core(t, q, z0);
+    t.ncol = t.n + 1;
+    t.pivots = 0;
 }
 
 // ---- rank-1 pivot on the compact tableau (avi_scratch.jl:2-7) --------------------------
-__device__ __forceinline__ void pivot(Tab& t, int rho, int c, bool compact = true) {
+// Not inlined (one copy keeps the engine's code small enough for the instruction cache: with every
+// helper inlined at each call site the robust_avoid kernel stalled mostly on instruction fetch).
+// Returns the new live-column count.
+__device__ __noinline__ int pivot_core(Tab t, int rho, int c, bool compact) {
     const int n = t.n, ldr = t.ldr, i = threadIdx.x;
     const int ncol = t.ncol;
     const int nce = (ncol + 1) & ~1;                      // even: the update runs two columns at a time
@@ -320,12 +326,15 @@ __device__ __forceinline__ void pivot(Tab& t, int rho, int c, bool compact = tru
             t.colvar()[c] = lv; t.colof()[lv] = c; t.nbval()[c] = vlv;
         }
     }
-    if (dead) t.ncol = last;
-    t.pivots++;
     QPN_SYNC();
+    return dead ? last : ncol;
+}
+__device__ __forceinline__ void pivot(Tab& t, int rho, int c, bool compact = true) {
+    t.ncol = pivot_core(t, rho, c, compact);
+    t.pivots++;
 }
 
-__device__ __forceinline__ int best_artificial_row(const Tab& t, int c) {
+__device__ __noinline__ int best_artificial_row(const Tab t, int c) {
     const int i = threadIdx.x;
     double a = 0.0; bool valid = false;
     if (i < t.n && artificial_row(t, i)) {
@@ -340,7 +349,9 @@ __device__ __forceinline__ int best_artificial_row(const Tab& t, int c) {
 // ---- ratio test over the finite bounds of the basics (avi_scratch.jl:65-77) ------------
 // Returns the step of the blocking row (INF if none); all threads get the same answer.
 // Every exit ends with a barrier.
-__device__ __forceinline__ double ratio_test(const Tab& t, int c, double sigma, int& rho, int& which) {
+struct RatioResult { double th; int rho; int which; };
+__device__ __noinline__ RatioResult ratio_test_core(const Tab t, int c, double sigma) {
+    int rho, which;
     const int n = t.n, i = threadIdx.x;
     double r = QPN_INF, a = 0.0;
     bool is_t = false;
@@ -357,7 +368,7 @@ __device__ __forceinline__ double ratio_test(const Tab& t, int c, double sigma, 
     }
     const double theta = block_min(t, r);
     rho = -1; which = 0;
-    if (theta == QPN_INF) { QPN_SYNC(); return QPN_INF; }
+    if (theta == QPN_INF) { QPN_SYNC(); return RatioResult{QPN_INF, -1, 0}; }   // every exit ends with a barrier
     const double cut = theta + TIE_TOL * (1.0 + theta);
     // among ties: t first (so the path terminates), then largest |d|, then lowest row
     const bool cand = (i < n) && (r <= cut);
@@ -370,7 +381,12 @@ __device__ __forceinline__ double ratio_test(const Tab& t, int c, double sigma, 
     QPN_SYNC();
     const double th = t.red_d()[32];
     which = (sigma * t.T()[(size_t)rho * t.ldr + c] > 0.0) ? -1 : +1;
-    return th;
+    return RatioResult{th, rho, which};
+}
+__device__ __forceinline__ double ratio_test(const Tab& t, int c, double sigma, int& rho, int& which) {
+    const RatioResult r = ratio_test_core(t, c, sigma);
+    rho = r.rho; which = r.which;
+    return r.th;
 }
 
 __device__ __forceinline__ void move(Tab& t, int c, double sigma, double theta) {

@@ -23,6 +23,9 @@ struct qpn_handle {
     unsigned char* arena = nullptr;
     size_t arena_bytes = 0;
     size_t arena_used = 0;
+    // grow-only buffers for the plans of one-off calls (cudaMalloc / cudaFree per call cost milliseconds)
+    unsigned char* plan_buf[2] = {nullptr, nullptr};
+    size_t plan_buf_bytes[2] = {0, 0};
 };
 
 static std::string g_create_error;
@@ -107,6 +110,7 @@ extern "C" int qpn_destroy(qpn_handle* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     if (h->arena) cudaFree(h->arena);
+    for (int k = 0; k < 2; ++k) if (h->plan_buf[k]) cudaFree(h->plan_buf[k]);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return 0;
@@ -338,20 +342,76 @@ static GaviDesc gavi_dev_desc(const qpn_gavi* g) {
     return d;
 }
 
+// ---- plans -------------------------------------------------------------------------------------
+// One plan: buffers sized for the worst case, filled by plan_build_kernel.
+// blob_out != NULL: a fresh allocation owned by the caller (resident levels); blob_out == NULL: the
+// handle's reusable buffer for one-off calls.
+static int build_plan(qpn_handle* h, const GaviDesc& g, int kind, PlanDesc* out, unsigned char** blob_out) {
+    const size_t n = (size_t)g.d1 + 2 * g.d2, dz = (size_t)g.d1 + g.d2;
+    const size_t ldrw = row_stride((int)n + 1);
+    size_t need = 0;
+    auto add = [&](size_t bytes) { size_t off = (need + 255) & ~(size_t)255; need = off + bytes; return off; };
+    const size_t oT0 = add(8 * n * ldrw), oPT = add(8 * n * n), oval = add(8 * n * n), orv = add(4 * n), ocv = add(4 * (n + 1)),
+                 optr = add(4 * (n + 1)), ocol = add(4 * n * n), ocols = add(4 * (dz + 1)), ohdr = add(16);
+    unsigned char* b = nullptr;
+    const size_t smem = gavi_smem_bytes(g.d1, g.d2, g.np);
+    if (smem > (size_t)h->max_smem_optin) return fail(h, "plan: d1=%d d2=%d needs %zu B shared memory", g.d1, g.d2, smem);
+    if (blob_out) {
+        CK(cudaMalloc((void**)&b, need + 256));
+    } else {
+        if (need + 256 > h->plan_buf_bytes[kind]) {
+            if (h->plan_buf[kind]) cudaFree(h->plan_buf[kind]);
+            h->plan_buf[kind] = nullptr; h->plan_buf_bytes[kind] = 0;
+            CK(cudaMalloc((void**)&h->plan_buf[kind], 2 * (need + 256)));
+            h->plan_buf_bytes[kind] = 2 * (need + 256);
+        }
+        b = h->plan_buf[kind];
+    }
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(plan_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    plan_build_kernel<<<1, roundup32((int)n), smem, h->stream>>>(g, kind, (double*)(b + oT0), (double*)(b + oPT), (int*)(b + orv), (int*)(b + ocv),
+                                                                  (int*)(b + optr), (int*)(b + ocol), (double*)(b + oval), (int*)(b + ocols),
+                                                                  (int*)(b + ohdr));
+    h->launches++;
+    CK(cudaGetLastError());
+    int hdr[4];
+    CK(cudaMemcpyAsync(hdr, b + ohdr, sizeof hdr, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    PlanDesc P;
+    P.n = kind == 1 ? hdr[3] + 2 * g.d2 : (int)n;
+    P.ncol0 = hdr[0]; P.npiv0 = hdr[1]; P.tcol0 = hdr[2];
+    P.T0 = (double*)(b + oT0); P.PT = (double*)(b + oPT); P.rowvar0 = (int*)(b + orv); P.colvar0 = (int*)(b + ocv);
+    P.csr_ptr = (int*)(b + optr); P.csr_col = (int*)(b + ocol); P.csr_val = (double*)(b + oval);
+    P.cols = (int*)(b + ocols); P.ncols = hdr[3];
+    *out = P;
+    if (blob_out) *blob_out = b;
+    return 0;
+}
+
+
+// Below this batch size a one-off call does not repay the two plan launches and their sync.
+static const int QPN_PLAN_MIN_BATCH = 256;
+
 // ---- solve_gavi ------------------------------------------------------------------------------
 static int launch_gavi(qpn_handle* h, const GaviDesc& g, int batch, const double* w, const double* z0, int presolve,
                        int max_pivots, double* z, double* zfull, int32_t* st, int32_t* pv, int8_t* basis, cudaStream_t s) {
     if (batch <= 0) return 0;
     const int n = g.d1 + 2 * g.d2;
-    const size_t smem = gavi_smem_bytes(g.d1, g.d2, g.np);
+    if (n > 256) return fail(h, "GAVI of lifted size n=%d exceeds the one-thread-per-row limit of 256", n);
+    GaviPlans plans;
+    plans.has = 0;
+    if (batch >= QPN_PLAN_MIN_BATCH && s == h->stream) {       // plans are built (and synchronised) on the handle's stream
+        if (build_plan(h, g, 0, &plans.A, nullptr) || build_plan(h, g, 1, &plans.B, nullptr)) return -1;
+        plans.has = 1;
+    }
+    gavi_workspace_shape(g, plans);
+    const size_t smem = tab_smem_bytes_ex(n, (size_t)plans.t_doubles, plans.ldr_max) + gavi_extra_bytes(g.d1, g.d2, g.np);
     if (smem > (size_t)h->max_smem_optin)
         return fail(h, "GAVI with d1=%d d2=%d needs %zu B of shared memory per CTA (limit %d)", g.d1, g.d2, smem, h->max_smem_optin);
     if (max_pivots <= 0) max_pivots = 50 * n + 100;
-    if (n > 256) return fail(h, "GAVI of lifted size n=%d exceeds the one-thread-per-row limit of 256", n);
-    QPN_LAUNCH_BUCKETED(gavi_solve_kernel, roundup32(n), batch, smem, s, g, batch, w, z0, presolve, max_pivots, z, zfull, st, pv, basis);
+    QPN_LAUNCH_BUCKETED(gavi_solve_kernel, roundup32(n), batch, smem, s, g, plans, batch, w, z0, presolve, max_pivots, z, zfull, st, pv, basis);
     h->launches++;
     CK(cudaGetLastError());
-    return 0;
+    return 0;                                                  // the handle's plan buffers are reused by the next call (stream order)
 }
 
 extern "C" int qpn_gavi_solve_batched_dev(qpn_handle* h, const qpn_gavi* g, int batch, const double* w, const double* z0,

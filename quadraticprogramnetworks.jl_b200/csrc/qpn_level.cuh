@@ -31,9 +31,8 @@ __device__ __forceinline__ double csr_row_dot(const PlanDesc& P, int i, const do
 
 // Start of a solve from a plan: same state as tab_start + phase 0 + recompute_tcol + compact_dead.
 // t.l() / t.u() hold the bounds; zb: n doubles of scratch.  Ends with a barrier.
-__device__ __forceinline__ void tab_start_plan(Tab& t, const PlanDesc& P, const double* q, const double* z0, double* zb) {
+__device__ __noinline__ void tab_start_plan_core(Tab t, const PlanDesc& P, const double* q, const double* z0, double* zb) {
     const int n = P.n, i = threadIdx.x;
-    tab_shape(t, n, P.ncol0);
     const int ldr = t.ldr;
     if (i < n) zb[i] = fmin(fmax(z0[i], t.l()[i]), t.u()[i]);
     for (int e = i; e < n * ldr; e += blockDim.x) t.T()[e] = P.T0[e];
@@ -62,9 +61,13 @@ __device__ __forceinline__ void tab_start_plan(Tab& t, const PlanDesc& P, const 
         t.beta()[i] = rv < n ? zb[rv] : zb[i] - zi;
         if (rv < n) t.zst()[rv] = BASIC;            // after the barrier that followed the default marks
     }
+    QPN_SYNC();
+}
+__device__ __forceinline__ void tab_start_plan(Tab& t, const PlanDesc& P, const double* q, const double* z0, double* zb) {
+    tab_shape(t, P.n, P.ncol0);
+    tab_start_plan_core(t, P, q, z0, zb);
     t.ncol = P.ncol0;
     t.pivots = P.npiv0;
-    QPN_SYNC();
 }
 
 // Solve (M z + q) comp. l <= z <= u in the shared-memory tableau.  `build(t)` must fill
@@ -292,8 +295,28 @@ __device__ __forceinline__ int gavi_solve_smem(GaviSmem& s, const GaviDesc& g, c
     return solve_avi_smem(t, n, [&](Tab& tt) { build_lifted(tt, g); }, s.qs(), s.zs(), max_pivots, s.code(), pivots);
 }
 
+// Plans of a GAVI's two AVIs and the workspace shape they allow.
+struct GaviPlans {
+    int has;
+    PlanDesc A, B;          // lifted AVI / presolve AVI
+    int t_doubles, ldr_max;
+};
+__host__ inline void gavi_workspace_shape(const GaviDesc& g, GaviPlans& pl, int extra_rows = 0, int extra_cap = 0) {
+    const int n = g.d1 + 2 * g.d2;
+    int ldr = 2; size_t td = 2;
+    auto take = [&](int rows, int cap) {
+        const int l = row_stride(cap);
+        if (l > ldr) ldr = l;
+        if ((size_t)rows * l > td) td = (size_t)rows * l;
+    };
+    if (pl.has) { take(pl.A.n, pl.A.ncol0); take(pl.B.n, pl.B.ncol0); }
+    else take(n, n + 1);
+    if (extra_rows > 0) take(extra_rows, extra_cap);
+    pl.t_doubles = (int)td; pl.ldr_max = ldr;
+}
+
 template <int MAXT>
-__global__ void __launch_bounds__(MAXT, 896 / MAXT) gavi_solve_kernel(const __grid_constant__ GaviDesc g, int batch, const double* __restrict__ w,
+__global__ void __launch_bounds__(MAXT, 896 / MAXT) gavi_solve_kernel(const __grid_constant__ GaviDesc g, const __grid_constant__ GaviPlans plans, int batch, const double* __restrict__ w,
                                   const double* __restrict__ z0, int presolve, int max_pivots,
                                   double* __restrict__ z_out, double* __restrict__ zfull_out,
                                   int32_t* __restrict__ status_out, int32_t* __restrict__ pivots_out,
@@ -301,12 +324,13 @@ __global__ void __launch_bounds__(MAXT, 896 / MAXT) gavi_solve_kernel(const __gr
     const int b = blockIdx.x, i = threadIdx.x;
     const int dz = g.d1 + g.d2, n = g.d1 + 2 * g.d2;
     GaviSmem s;
-    gavi_carve(s, g, 0);
+    tab_carve_ex(s.t, n, (size_t)plans.t_doubles, plans.ldr_max, 0);
+    gavi_carve_extra(s, g, (int)tab_smem_bytes_ex(n, (size_t)plans.t_doubles, plans.ldr_max));
     for (int j = i; j < g.np; j += blockDim.x) s.w()[j] = w[(size_t)b * g.np + j];
     for (int j = i; j < dz; j += blockDim.x) s.z0()[j] = z0[(size_t)b * dz + j];
     QPN_SYNC();
     int piv = 0;
-    const int st = gavi_solve_smem(s, g, nullptr, nullptr, presolve, max_pivots, &piv);
+    const int st = gavi_solve_smem(s, g, plans.has ? &plans.A : nullptr, plans.has ? &plans.B : nullptr, presolve, max_pivots, &piv);
     QPN_SYNC();
     if (i < dz) z_out[(size_t)b * dz + i] = s.zs()[i];
     if (i < n) {

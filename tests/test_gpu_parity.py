@@ -261,3 +261,25 @@ def test_simple_bilevel_known_answers_on_gpu(engine):
 def test_robust_avoid_three_levels_on_gpu(engine):
     from tests.test_multilevel_cpu import check_robust_avoid_end_to_end
     check_robust_avoid_end_to_end(engine, seeds=(3,))
+
+
+def test_one_off_calls_with_plans_above_threshold(engine):
+    """qpn_gavi_solve_batched / qpn_level_equilibrium_batched build one-off plans for batches >= 256."""
+    import qpn_b200
+    rng = np.random.default_rng(21)
+    net, X = problems.ra_inits(rng, 320)
+    g, dec, par = qpn_ref.level_gavi(net, net.depth[3], {})
+    dz = g["M"].shape[1]
+    w = X[:, par]
+    z0 = np.zeros((len(X), dz)); z0[:, :len(dec)] = X[:, dec]
+    ret = engine.gavi_solve(g, w, z0)
+    for k in range(0, len(X), 7):
+        ro = cport.gavi_solve(g, z0[k], w[k])
+        assert ro["status"] == ret["status"][k] and ro["pivots"] == ret["pivots"][k]
+        assert np.array_equal(ro["z_full"], ret["z_full"][k]) and np.array_equal(ro["basis"], ret["basis"][k])
+    views = [qpn_ref.node_view(net, p) for p in net.depth[3]]
+    lv = qpn_b200.LevelArrays(net.n_vars, views, g, dec, par, max_iters=150, proj=None)
+    ret = engine.level_equilibrium(lv, X)
+    ro = cport.Level(net.n_vars, views, g, dec, par, 150, None).solve(X, threads=4)
+    for k in ("x", "iters", "pivots", "lam"):
+        assert np.array_equal(ret[k], ro[k]), k
