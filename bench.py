@@ -200,14 +200,17 @@ def main():
 
     # ---- device-resident arm -------------------------------------------------------------------
     x_in = [torch.from_numpy(inits_for(rank, B, k)).to(dev) for k in range(min(K, 8))]
-    x_out = torch.empty((B, nv), dtype=torch.float64, device=dev)
-    solved = torch.empty(B, dtype=torch.uint8, device=dev)
-    iters = torch.empty(B, dtype=torch.int32, device=dev)
-    pivots = torch.empty(B, dtype=torch.int32, device=dev)
+    # Outputs of one rank live in ONE contiguous block [x_out | iters | pivots | solved] so that the
+    # final gather of solutions / statuses / pivot counts is a single NCCL all-gather.
+    o_it, o_pv, o_sol = B * nv * 8, B * nv * 8 + 4 * B, B * nv * 8 + 8 * B
+    nbytes = (o_sol + B + 15) // 16 * 16
+    block = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    x_out = block[:o_it].view(torch.float64).view(B, nv)
+    iters = block[o_it:o_pv].view(torch.int32)
+    pivots = block[o_pv:o_sol].view(torch.int32)
+    solved = block[o_sol:o_sol + B]
     if world > 1:
-        g_x = torch.empty((world * B, nv), dtype=torch.float64, device=dev)
-        g_solved = torch.empty(world * B, dtype=torch.uint8, device=dev)
-        g_piv = torch.empty(world * B, dtype=torch.int32, device=dev)
+        g_block = torch.empty(world * nbytes, dtype=torch.uint8, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
     def step_dev(k):
@@ -216,9 +219,7 @@ def main():
 
     def gather():
         if world > 1:
-            dist.all_gather_into_tensor(g_x, x_out)
-            dist.all_gather_into_tensor(g_solved, solved)
-            dist.all_gather_into_tensor(g_piv, pivots)
+            dist.all_gather_into_tensor(g_block, block)
 
     for k in range(W):
         step_dev(k); gather()
