@@ -283,3 +283,75 @@ def test_one_off_calls_with_plans_above_threshold(engine):
     ro = cport.Level(net.n_vars, views, g, dec, par, 150, None).solve(X, threads=4)
     for k in ("x", "iters", "pivots", "lam"):
         assert np.array_equal(ret[k], ro[k]), k
+
+
+# ---- edge cases and failure statuses through the C ABI --------------------------------------------
+def _lifted(Q, c, A, l, u, z0):
+    g = problems.qp_gavi(np.asarray(Q, float), np.asarray(c, float), np.asarray(A, float), np.asarray(l, float), np.asarray(u, float))
+    avi = qpn_ref.convert(g)
+    z0 = np.asarray(z0, float)
+    return avi["M"], avi["o"], avi["l"], avi["u"], np.concatenate([z0, g["A"] @ z0])
+
+
+def test_edge_cases_and_failure_statuses(engine):
+    INF = np.inf
+    cases = {
+        "unbounded LP": _lifted(np.zeros((1, 1)), [-1.0], [[1.0]], [0.0], [INF], [1.0, 0.0]),
+        "infeasible": _lifted(np.eye(1), [0.0], [[1.0], [1.0]], [-INF, 1.0], [-1.0, INF], [0.0, 0.0, 0.0]),
+        "equality row": _lifted(np.eye(2), [1.0, -2.0], [[1.0, 1.0]], [1.0], [1.0], [0.0, 0.0, 0.0]),
+        "duplicate rows": _lifted(np.zeros((2, 2)), [1.0, 1.0], [[1.0, 0.0], [1.0, 0.0], [0.0, 1.0], [0.0, 1.0]], [0.0] * 4, [INF] * 4,
+                                  [1.0, 2.0, 0, 0, 0, 0]),
+        "degenerate vertex": _lifted(np.zeros((2, 2)), [1.0, 1.0], [[1.0, 0.0], [0.0, 1.0], [1.0, 1.0], [1.0, -1.0]], [0.0, 0.0, 0.0, -INF],
+                                     [INF, INF, INF, 0.0], [0.5, 0.7, 0, 0, 0, 0]),
+    }
+    seen = set()
+    for name, (M, q, l, u, z0) in cases.items():
+        zo, so, po, bo = cport.avi_solve(M, q, l, u, z0)
+        z, s, p, b = engine.avi_solve(M, q[None], l, u, z0[None])
+        assert s[0] == so and p[0] == po and np.array_equal(b[0], bo), name
+        assert np.array_equal(z[0], zo, equal_nan=True), name
+        seen.add(int(so))
+    assert 1 in seen and len(seen) >= 2, seen                       # successes and at least one non-success code
+    # plain box AVIs: n = 1, a fixed variable (l == u), bounds active at the start
+    M = np.array([[2.0]]); q = np.array([[-3.0], [5.0], [0.5]]); l = np.array([0.0]); u = np.array([1.0])
+    z0 = np.array([[0.0], [1.0], [0.25]])
+    zo, so, po, bo = cport.avi_solve_batched(M, q, l, u, z0)
+    z, s, p, b = engine.avi_solve(M, q, l, u, z0)
+    assert np.array_equal(z, zo) and np.array_equal(s, so) and np.array_equal(p, po) and np.array_equal(b, bo)
+    assert np.allclose(z[:, 0], [1.0, 0.0, 0.0])
+    M = np.array([[1.0, 0.5], [0.5, 2.0]]); l = np.array([0.3, -INF]); u = np.array([0.3, INF])       # first variable fixed
+    q = np.array([[1.0, -1.0]]); z0 = np.array([[0.3, 0.0]])
+    zo, so, po, bo = cport.avi_solve(M, q[0], l, u, z0[0])
+    z, s, p, b = engine.avi_solve(M, q, l, u, z0)
+    assert so == 1 and bo[0] == 4 and np.array_equal(z[0], zo) and np.array_equal(b[0], bo) and p[0] == po
+    # pivot budget exhausted -> MAX_ITERS from both
+    net, g, avi, dec, par = problems.fp_avi()
+    X, z0 = problems.fp_starts(np.random.default_rng(3), 4)
+    qq = np.tile(avi["o"], (4, 1))
+    zo, so, po, bo = cport.avi_solve_batched(avi["M"], qq, avi["l"], avi["u"], z0, max_pivots=5)
+    z, s, p, b = engine.avi_solve(avi["M"], qq, avi["l"], avi["u"], z0, max_pivots=5)
+    assert (so == 3).all() and np.array_equal(s, so) and np.array_equal(p, po)
+    # empty batch is a no-op
+    z, s, p, b = engine.avi_solve(avi["M"], np.zeros((0, 32)), avi["l"], avi["u"], np.zeros((0, 32)))
+    assert z.shape == (0, 32) and len(s) == 0
+
+
+def test_avi_larger_random_monotone(engine):
+    """Sizes beyond the examples (n up to 96: three warps per instance), monotone AVIs M = G'G + skew."""
+    rng = np.random.default_rng(33)
+    for n in (40, 64, 96):
+        B = 24
+        Ms, qs, ls, us, z0s = [], [], [], [], []
+        for _ in range(B):
+            G = rng.normal(size=(n, n)) / np.sqrt(n); K = rng.normal(size=(n, n)) * 0.3
+            Ms.append(G.T @ G + 0.05 * np.eye(n) + (K - K.T))
+            qs.append(rng.normal(size=n))
+            l = np.where(rng.uniform(size=n) < 0.3, -np.inf, -rng.uniform(0.1, 1.0, n))
+            u = np.where(rng.uniform(size=n) < 0.3, np.inf, rng.uniform(0.1, 1.0, n))
+            ls.append(l); us.append(u); z0s.append(rng.normal(size=n))
+        Ms, qs, ls, us, z0s = map(np.array, (Ms, qs, ls, us, z0s))
+        zo, so, po, bo = cport.avi_solve_batched(Ms, qs, ls, us, z0s, threads=8)
+        z, s, p, b = engine.avi_solve(Ms, qs, ls, us, z0s)
+        assert (so == 1).all(), (n, np.bincount(so))
+        assert np.array_equal(s, so) and np.array_equal(p, po) and np.array_equal(b, bo), n
+        assert np.array_equal(z, zo), n
