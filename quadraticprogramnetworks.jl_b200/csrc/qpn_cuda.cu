@@ -229,6 +229,90 @@ static int stage_matrix(qpn_handle* h, Arena& a, const MatSlots& s, const qpn_ma
     return 0;
 }
 
+// ---- plans -------------------------------------------------------------------------------------
+// One plan: buffers sized for the worst case, filled by plan_build_kernel.
+// blob_out != NULL: a fresh allocation owned by the caller (resident levels); blob_out == NULL: the
+// handle's reusable buffer for one-off calls.
+static int build_plan(qpn_handle* h, const GaviDesc& g, int kind, PlanDesc* out, unsigned char** blob_out) {
+    const size_t n = (size_t)g.d1 + 2 * g.d2, dz = (size_t)g.d1 + g.d2;
+    const size_t ldrw = row_stride((int)n + 1);
+    size_t need = 0;
+    auto add = [&](size_t bytes) { size_t off = (need + 255) & ~(size_t)255; need = off + bytes; return off; };
+    const size_t oT0 = add(8 * n * ldrw), oPT = add(8 * n * n), oval = add(8 * n * n), orv = add(4 * n), ocv = add(4 * (n + 1)),
+                 optr = add(4 * (n + 1)), ocol = add(4 * n * n), ocols = add(4 * (dz + 1)), ohdr = add(16);
+    unsigned char* b = nullptr;
+    const size_t smem = gavi_smem_bytes(g.d1, g.d2, g.np);
+    if (smem > (size_t)h->max_smem_optin) return fail(h, "plan: d1=%d d2=%d needs %zu B shared memory", g.d1, g.d2, smem);
+    if (blob_out) {
+        CK(cudaMalloc((void**)&b, need + 256));
+    } else {
+        if (need + 256 > h->plan_buf_bytes[kind]) {
+            if (h->plan_buf[kind]) cudaFree(h->plan_buf[kind]);
+            h->plan_buf[kind] = nullptr; h->plan_buf_bytes[kind] = 0;
+            CK(cudaMalloc((void**)&h->plan_buf[kind], 2 * (need + 256)));
+            h->plan_buf_bytes[kind] = 2 * (need + 256);
+        }
+        b = h->plan_buf[kind];
+    }
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(plan_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    plan_build_kernel<<<1, roundup32((int)n), smem, h->stream>>>(g, kind, (double*)(b + oT0), (double*)(b + oPT), (int*)(b + orv), (int*)(b + ocv),
+                                                                  (int*)(b + optr), (int*)(b + ocol), (double*)(b + oval), (int*)(b + ocols),
+                                                                  (int*)(b + ohdr));
+    h->launches++;
+    CK(cudaGetLastError());
+    int hdr[4];
+    CK(cudaMemcpyAsync(hdr, b + ohdr, sizeof hdr, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    PlanDesc P;
+    P.n = kind == 1 ? hdr[3] + 2 * g.d2 : (int)n;
+    P.ncol0 = hdr[0]; P.npiv0 = hdr[1]; P.tcol0 = hdr[2];
+    P.T0 = (double*)(b + oT0); P.PT = (double*)(b + oPT); P.rowvar0 = (int*)(b + orv); P.colvar0 = (int*)(b + ocv);
+    P.csr_ptr = (int*)(b + optr); P.csr_col = (int*)(b + ocol); P.csr_val = (double*)(b + oval);
+    P.cols = (int*)(b + ocols); P.ncols = hdr[3];
+    *out = P;
+    if (blob_out) *blob_out = b;
+    return 0;
+}
+
+
+// Below this batch size a one-off call does not repay the two plan launches and their sync.
+static const int QPN_PLAN_MIN_BATCH = 256;
+
+
+// Plan of a plain AVI with a shared matrix and shared bounds, in the handle's reusable buffer (slot 0).
+static int build_plan_avi(qpn_handle* h, int n_, const MatDesc& M, const double* l, const double* u, PlanDesc* out) {
+    const size_t n = n_, ldrw = row_stride(n_ + 1);
+    size_t need = 0;
+    auto add = [&](size_t bytes) { size_t off = (need + 255) & ~(size_t)255; need = off + bytes; return off; };
+    const size_t oT0 = add(8 * n * ldrw), oPT = add(8 * n * n), oval = add(8 * n * n), orv = add(4 * n), ocv = add(4 * (n + 1)),
+                 optr = add(4 * (n + 1)), ocol = add(4 * n * n), ohdr = add(16);
+    const size_t smem = tab_smem_bytes(n_, n_ + 1) + 8 * 3 * n;
+    if (smem > (size_t)h->max_smem_optin) return fail(h, "plan: AVI of size n=%d needs %zu B shared memory", n_, smem);
+    if (need + 256 > h->plan_buf_bytes[0]) {
+        if (h->plan_buf[0]) cudaFree(h->plan_buf[0]);
+        h->plan_buf[0] = nullptr; h->plan_buf_bytes[0] = 0;
+        CK(cudaMalloc((void**)&h->plan_buf[0], 2 * (need + 256)));
+        h->plan_buf_bytes[0] = 2 * (need + 256);
+    }
+    unsigned char* b = h->plan_buf[0];
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(plan_build_avi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    plan_build_avi_kernel<<<1, roundup32(n_), smem, h->stream>>>(n_, M, l, u, (double*)(b + oT0), (double*)(b + oPT), (int*)(b + orv),
+                                                                  (int*)(b + ocv), (int*)(b + optr), (int*)(b + ocol), (double*)(b + oval),
+                                                                  (int*)(b + ohdr));
+    h->launches++;
+    CK(cudaGetLastError());
+    int hdr[4];
+    CK(cudaMemcpyAsync(hdr, b + ohdr, sizeof hdr, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    PlanDesc P;
+    P.n = n_; P.ncol0 = hdr[0]; P.npiv0 = hdr[1]; P.tcol0 = hdr[2];
+    P.T0 = (double*)(b + oT0); P.PT = (double*)(b + oPT); P.rowvar0 = (int*)(b + orv); P.colvar0 = (int*)(b + ocv);
+    P.csr_ptr = (int*)(b + optr); P.csr_col = (int*)(b + ocol); P.csr_val = (double*)(b + oval);
+    P.cols = nullptr; P.ncols = 0;
+    *out = P;
+    return 0;
+}
+
 // ---- solve_avi -----------------------------------------------------------------------------
 static int launch_avi(qpn_handle* h, int n, int batch, const MatDesc& M, const double* q, const double* l,
                       const double* u, int lu_shared, const double* z0, int max_pivots, double* z,
@@ -240,6 +324,17 @@ static int launch_avi(qpn_handle* h, int n, int batch, const MatDesc& M, const d
                        "tableau path does not cover this size", n, smem, h->max_smem_optin);
     if (max_pivots <= 0) max_pivots = 50 * n + 100;
     if (n > 256) return fail(h, "AVI of size n=%d exceeds the one-thread-per-row limit of 256", n);
+    if (M.shared && lu_shared && batch >= QPN_PLAN_MIN_BATCH && s == h->stream) {
+        // matrix and bounds shared by a large batch: the crash prefix is computed once
+        PlanDesc P;
+        if (build_plan_avi(h, n, M, l, u, &P)) return -1;
+        const int ldr0 = row_stride(P.ncol0);
+        const size_t smem_p = tab_smem_bytes_ex(n, (size_t)n * ldr0, ldr0) + 8 * 3 * (size_t)n;
+        QPN_LAUNCH_BUCKETED(avi_solve_plan_kernel, roundup32(n), batch, smem_p, s, P, batch, q, l, u, z0, max_pivots, z, st, pv, basis);
+        h->launches++;
+        CK(cudaGetLastError());
+        return 0;
+    }
     QPN_LAUNCH_BUCKETED(avi_solve_kernel, roundup32(n), batch, smem, s, n, batch, M, q, l, u, lu_shared, z0, max_pivots, z, st, pv, basis);
     h->launches++;
     CK(cudaGetLastError());
@@ -341,55 +436,6 @@ static GaviDesc gavi_dev_desc(const qpn_gavi* g) {
     d.M = g->M; d.N = g->N; d.o = g->o; d.l1 = g->l1; d.u1 = g->u1; d.A = g->A; d.B = g->B; d.l2 = g->l2; d.u2 = g->u2;
     return d;
 }
-
-// ---- plans -------------------------------------------------------------------------------------
-// One plan: buffers sized for the worst case, filled by plan_build_kernel.
-// blob_out != NULL: a fresh allocation owned by the caller (resident levels); blob_out == NULL: the
-// handle's reusable buffer for one-off calls.
-static int build_plan(qpn_handle* h, const GaviDesc& g, int kind, PlanDesc* out, unsigned char** blob_out) {
-    const size_t n = (size_t)g.d1 + 2 * g.d2, dz = (size_t)g.d1 + g.d2;
-    const size_t ldrw = row_stride((int)n + 1);
-    size_t need = 0;
-    auto add = [&](size_t bytes) { size_t off = (need + 255) & ~(size_t)255; need = off + bytes; return off; };
-    const size_t oT0 = add(8 * n * ldrw), oPT = add(8 * n * n), oval = add(8 * n * n), orv = add(4 * n), ocv = add(4 * (n + 1)),
-                 optr = add(4 * (n + 1)), ocol = add(4 * n * n), ocols = add(4 * (dz + 1)), ohdr = add(16);
-    unsigned char* b = nullptr;
-    const size_t smem = gavi_smem_bytes(g.d1, g.d2, g.np);
-    if (smem > (size_t)h->max_smem_optin) return fail(h, "plan: d1=%d d2=%d needs %zu B shared memory", g.d1, g.d2, smem);
-    if (blob_out) {
-        CK(cudaMalloc((void**)&b, need + 256));
-    } else {
-        if (need + 256 > h->plan_buf_bytes[kind]) {
-            if (h->plan_buf[kind]) cudaFree(h->plan_buf[kind]);
-            h->plan_buf[kind] = nullptr; h->plan_buf_bytes[kind] = 0;
-            CK(cudaMalloc((void**)&h->plan_buf[kind], 2 * (need + 256)));
-            h->plan_buf_bytes[kind] = 2 * (need + 256);
-        }
-        b = h->plan_buf[kind];
-    }
-    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(plan_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    plan_build_kernel<<<1, roundup32((int)n), smem, h->stream>>>(g, kind, (double*)(b + oT0), (double*)(b + oPT), (int*)(b + orv), (int*)(b + ocv),
-                                                                  (int*)(b + optr), (int*)(b + ocol), (double*)(b + oval), (int*)(b + ocols),
-                                                                  (int*)(b + ohdr));
-    h->launches++;
-    CK(cudaGetLastError());
-    int hdr[4];
-    CK(cudaMemcpyAsync(hdr, b + ohdr, sizeof hdr, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    PlanDesc P;
-    P.n = kind == 1 ? hdr[3] + 2 * g.d2 : (int)n;
-    P.ncol0 = hdr[0]; P.npiv0 = hdr[1]; P.tcol0 = hdr[2];
-    P.T0 = (double*)(b + oT0); P.PT = (double*)(b + oPT); P.rowvar0 = (int*)(b + orv); P.colvar0 = (int*)(b + ocv);
-    P.csr_ptr = (int*)(b + optr); P.csr_col = (int*)(b + ocol); P.csr_val = (double*)(b + oval);
-    P.cols = (int*)(b + ocols); P.ncols = hdr[3];
-    *out = P;
-    if (blob_out) *blob_out = b;
-    return 0;
-}
-
-
-// Below this batch size a one-off call does not repay the two plan launches and their sync.
-static const int QPN_PLAN_MIN_BATCH = 256;
 
 // ---- solve_gavi ------------------------------------------------------------------------------
 static int launch_gavi(qpn_handle* h, const GaviDesc& g, int batch, const double* w, const double* z0, int presolve,

@@ -340,6 +340,62 @@ __global__ void __launch_bounds__(MAXT, 896 / MAXT) gavi_solve_kernel(const __gr
     if (i == 0) { status_out[b] = st; pivots_out[b] = piv; }
 }
 
+// Common tail of plan construction: T holds -M (n x n) and t.l / t.u the bounds; qs = zs = 0.
+// Exports the CSR rows, runs phase 0 exactly as crash() does, exports B^-1, compacts, exports T0.
+__device__ __forceinline__ void plan_finish(Tab& t, int n, int k, const double* qs, const double* zs, int* cnt,
+                                            double* __restrict__ T0, double* __restrict__ PT, int* __restrict__ rowvar0,
+                                            int* __restrict__ colvar0, int* __restrict__ csr_ptr, int* __restrict__ csr_col,
+                                            double* __restrict__ csr_val, int* __restrict__ hdr) {
+    const int i = threadIdx.x;
+    // the original matrix in CSR (rows ascending in the column index)
+    if (i < n) {
+        const double* row = t.T() + (size_t)i * t.ldr;
+        int c = 0;
+        for (int j = 0; j < n; ++j) c += (row[j] != 0.0);
+        cnt[i] = c;
+    }
+    QPN_SYNC();
+    if (i == 0) {
+        int acc = 0;
+        for (int r = 0; r < n; ++r) { csr_ptr[r] = acc; acc += cnt[r]; }
+        csr_ptr[n] = acc;
+    }
+    QPN_SYNC();
+    if (i < n) {
+        const double* row = t.T() + (size_t)i * t.ldr;
+        int o = csr_ptr[i];
+        for (int j = 0; j < n; ++j) if (row[j] != 0.0) { csr_col[o] = j; csr_val[o] = -row[j]; ++o; }
+    }
+    QPN_SYNC();
+    tab_start(t, qs, zs);
+    // phase 0 exactly as crash() runs it
+    for (int v = 0; v < n; ++v) {
+        if (!is_free_var(t, v)) continue;
+        const int c = t.colof()[v];
+        const int rho = best_free_row(t, c);
+        if (rho >= 0) { pivot(t, rho, c, false); set_zst(t, v, BASIC); }
+    }
+    // B^-1 from the slack columns (see recompute_tcol)
+    if (i < n) {
+        const double* row = t.T() + (size_t)i * t.ldr;
+        for (int kk = 0; kk < n; ++kk) {
+            const int ck = t.colof()[n + kk];
+            PT[(size_t)kk * n + i] = ck >= 0 ? -row[ck] : (t.rowof()[n + kk] == i ? -1.0 : 0.0);
+        }
+    }
+    const int npiv0 = t.pivots;
+    QPN_SYNC();
+    compact_dead(t);
+    const int ncol0 = t.ncol, ldr0 = row_stride(ncol0);
+    if (i < n) {
+        const double* row = t.T() + (size_t)i * t.ldr;
+        for (int j = 0; j < ldr0; ++j) T0[(size_t)i * ldr0 + j] = j < ncol0 ? row[j] : 0.0;
+        rowvar0[i] = t.rowvar()[i];
+    }
+    for (int j = i; j < ncol0; j += blockDim.x) colvar0[j] = t.colvar()[j];
+    if (i == 0) { hdr[0] = ncol0; hdr[1] = npiv0; hdr[2] = t.colof()[2 * n]; hdr[3] = k; }
+}
+
 // ---- plan construction: one CTA, once per shared matrix ---------------------------------------
 // kind 0: lifted AVI of the GAVI; kind 1: its presolve AVI.  Buffers are sized by the host for the
 // worst case (T0: n x row_stride(n+1), CSR: n*n entries).  hdr: [ncol0, npiv0, tcol0, ncols].
@@ -373,54 +429,7 @@ __global__ void plan_build_kernel(const __grid_constant__ GaviDesc g, int kind, 
     QPN_SYNC();
     tab_shape(t, n, n + 1);
     if (kind == 1) build_presolve(t, g, s.cols(), k); else build_lifted(t, g);
-    // the original matrix in CSR (rows ascending in the column index)
-    int* cnt = reinterpret_cast<int*>(s.zb());
-    if (i < n) {
-        const double* row = t.T() + (size_t)i * t.ldr;
-        int c = 0;
-        for (int j = 0; j < n; ++j) c += (row[j] != 0.0);
-        cnt[i] = c;
-    }
-    QPN_SYNC();
-    if (i == 0) {
-        int acc = 0;
-        for (int r = 0; r < n; ++r) { csr_ptr[r] = acc; acc += cnt[r]; }
-        csr_ptr[n] = acc;
-    }
-    QPN_SYNC();
-    if (i < n) {
-        const double* row = t.T() + (size_t)i * t.ldr;
-        int o = csr_ptr[i];
-        for (int j = 0; j < n; ++j) if (row[j] != 0.0) { csr_col[o] = j; csr_val[o] = -row[j]; ++o; }
-    }
-    QPN_SYNC();
-    tab_start(t, s.qs(), s.zs());
-    // phase 0 exactly as crash() runs it
-    for (int v = 0; v < n; ++v) {
-        if (!is_free_var(t, v)) continue;
-        const int c = t.colof()[v];
-        const int rho = best_free_row(t, c);
-        if (rho >= 0) { pivot(t, rho, c, false); set_zst(t, v, BASIC); }
-    }
-    // B^-1 from the slack columns (see recompute_tcol)
-    if (i < n) {
-        const double* row = t.T() + (size_t)i * t.ldr;
-        for (int kk = 0; kk < n; ++kk) {
-            const int ck = t.colof()[n + kk];
-            PT[(size_t)kk * n + i] = ck >= 0 ? -row[ck] : (t.rowof()[n + kk] == i ? -1.0 : 0.0);
-        }
-    }
-    const int npiv0 = t.pivots;
-    QPN_SYNC();
-    compact_dead(t);
-    const int ncol0 = t.ncol, ldr0 = row_stride(ncol0);
-    if (i < n) {
-        const double* row = t.T() + (size_t)i * t.ldr;
-        for (int j = 0; j < ldr0; ++j) T0[(size_t)i * ldr0 + j] = j < ncol0 ? row[j] : 0.0;
-        rowvar0[i] = t.rowvar()[i];
-    }
-    for (int j = i; j < ncol0; j += blockDim.x) colvar0[j] = t.colvar()[j];
-    if (i == 0) { hdr[0] = ncol0; hdr[1] = npiv0; hdr[2] = t.colof()[2 * n]; hdr[3] = k; }
+    plan_finish(t, n, k, s.qs(), s.zs(), reinterpret_cast<int*>(s.zb()), T0, PT, rowvar0, colvar0, csr_ptr, csr_col, csr_val, hdr);
 }
 
 // ---- verify_solution (qp_processing.jl:57-149) ---------------------------------------------------
@@ -849,6 +858,56 @@ __global__ void __launch_bounds__(MAXT, 896 / MAXT) level_equilibrium_kernel(con
         solved_out[b] = (uint8_t)solved; iters_out[b] = iters; pivots_out[b] = piv;
         if (hist && hist_count) hist_count[b] = nhist;
     }
+}
+
+
+// ---- solve_avi with a shared matrix: plan + solve ---------------------------------------------------
+// Plan of a plain AVI (matrix and bounds shared by the batch).
+__global__ void plan_build_avi_kernel(int n, const __grid_constant__ MatDesc M, const double* __restrict__ l,
+                                      const double* __restrict__ u, double* __restrict__ T0, double* __restrict__ PT,
+                                      int* __restrict__ rowvar0, int* __restrict__ colvar0, int* __restrict__ csr_ptr,
+                                      int* __restrict__ csr_col, double* __restrict__ csr_val, int* __restrict__ hdr) {
+    const int i = threadIdx.x;
+    Tab t;
+    tab_carve(t, n, n + 1, 0);
+    double* qs = reinterpret_cast<double*>(qpn_smem + tab_smem_bytes(n, n + 1));
+    double* zs = qs + n;
+    int* cnt = reinterpret_cast<int*>(zs + n);
+    if (i < n) { qs[i] = 0.0; zs[i] = 0.0; t.l()[i] = l[i]; t.u()[i] = u[i]; }
+    load_neg_matrix(t, M, 0);
+    plan_finish(t, n, 0, qs, zs, cnt, T0, PT, rowvar0, colvar0, csr_ptr, csr_col, csr_val, hdr);
+}
+
+// grid = batch, block = roundup32(n).  Dynamic smem: Tab_ex(n, n*rs(ncol0), rs(ncol0)) + q, z, zb (3n).
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 896 / MAXT) avi_solve_plan_kernel(const __grid_constant__ PlanDesc P, int batch,
+                                 const double* __restrict__ q, const double* __restrict__ l, const double* __restrict__ u,
+                                 const double* __restrict__ z0, int max_pivots, double* __restrict__ z_out,
+                                 int32_t* __restrict__ status_out, int32_t* __restrict__ pivots_out, int8_t* __restrict__ basis_out) {
+    const int b = blockIdx.x, i = threadIdx.x, n = P.n;
+    const int ldr = row_stride(P.ncol0);
+    Tab t;
+    tab_carve_ex(t, n, (size_t)n * ldr, ldr, 0);
+    double* qs = reinterpret_cast<double*>(qpn_smem + tab_smem_bytes_ex(n, (size_t)n * ldr, ldr));
+    double* zs = qs + n;
+    double* zb = zs + n;
+    if (i < n) {
+        qs[i] = q[(size_t)b * n + i];
+        zs[i] = z0[(size_t)b * n + i];
+        t.l()[i] = l[i];
+        t.u()[i] = u[i];
+    }
+    QPN_SYNC();
+    int piv = 0;
+    int8_t* code = reinterpret_cast<int8_t*>(zb);          // zb is free once the solve has started; reuse it for the codes
+    // (solve_avi_plan writes the codes only after avi_pivot_run, when zb is no longer read)
+    const int st = solve_avi_plan(t, P, qs, zs, zb, max_pivots, code, &piv);
+    QPN_SYNC();
+    if (i < n) {
+        z_out[(size_t)b * n + i] = zs[i];
+        if (basis_out) basis_out[(size_t)b * n + i] = code[i];
+    }
+    if (i == 0) { status_out[b] = st; pivots_out[b] = piv; }
 }
 
 }  // namespace qpn
