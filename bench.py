@@ -39,6 +39,11 @@ HBM_FALLBACK_GBS = 6650.0     # B200_PROFILING.md fallback when MEASURED_PEAKS.j
 # dram__bytes_read.sum + dram__bytes_write.sum of one level_equilibrium_kernel<32> launch at the default
 # batch (4,096), from profiles/r1_final_level_kernel_ncu_full_summary.csv (ncu --set full, same command)
 NCU_DRAM_BYTES_PER_LAUNCH_B4096 = 439_296 + 1_024
+# same capture: l1tex__data_pipe_lsu_wavefronts_mem_shared.sum (each wavefront moves up to 128 B) and
+# smsp__inst_executed.sum -- the two on-chip resources that actually bound the pivoting kernel
+NCU_SMEM_WAVEFRONTS_PER_LAUNCH_B4096 = 5_711_598
+NCU_WARP_INSTRUCTIONS_PER_LAUNCH_B4096 = 40_007_087
+SM_COUNT = 148
 
 
 def inits_for(rank, batch, step=0):
@@ -331,6 +336,20 @@ def main():
             "clocks": clocks,
             "extra": extra,
         }
+        if B == 4096:
+            # On-chip view (not the contract's HBM/tensor roofline, which this latency/issue-bound fp64 kernel
+            # cannot approach): shared-memory bandwidth 128 B/clk/SM and issue rate 4 warp-instr/clk/SM at the
+            # SM clock seen during the run; counts per launch from the committed ncu capture.
+            clk = (clocks or {}).get("sm_mhz") or 1965.0
+            t_k = t_kernel / K
+            smem_peak = SM_COUNT * 128 * clk * 1e6 / 1e12
+            issue_peak = SM_COUNT * 4 * clk * 1e6 / 1e12
+            line["roofline_onchip"] = {
+                "smem": {"achieved": NCU_SMEM_WAVEFRONTS_PER_LAUNCH_B4096 * 128 / t_k / 1e12, "peak": smem_peak, "unit": "TB/s",
+                         "frac": NCU_SMEM_WAVEFRONTS_PER_LAUNCH_B4096 * 128 / t_k / 1e12 / smem_peak},
+                "issue": {"achieved": NCU_WARP_INSTRUCTIONS_PER_LAUNCH_B4096 / t_k / 1e12, "peak": issue_peak, "unit": "T warp-instr/s",
+                          "frac": NCU_WARP_INSTRUCTIONS_PER_LAUNCH_B4096 / t_k / 1e12 / issue_peak},
+                "source": "profiles/r1_final_level_kernel_ncu_full_summary.csv"}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line), flush=True)

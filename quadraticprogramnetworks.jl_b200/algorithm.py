@@ -111,15 +111,26 @@ def _julia_product(ranges):
         yield tuple(reversed(tup))
 
 
-def intersection_leaves(unions, red_lengths, x, lp):
+def intersection_leaves(unions, red_lengths, x, lp, engine=None):
     """IntersectionRoot (intersection.jl:55-151): all non-empty intersections of one piece per union
-    that contain x in their closure, skipping the combinations made of complements only."""
+    that contain x in their closure, skipping the combinations made of complements only.
+
+    The membership test `central_point in closure(poly)` (intersection.jl:74,82) is a conjunction over
+    the pieces of a branch, so it is evaluated once per piece for the whole tree by the batched
+    half-space kernel (qpn_halfspace_in_batched); only survivors reach the emptiness LP."""
     n = len(unions)
     full = [len(u) for u in unions]
     out = []
+    inside = {}
+    if engine is not None and hasattr(engine, "halfspace_in"):
+        flat = [p for u in unions for p in u if len(p)]
+        if flat:
+            got = engine.halfspace_in([(p.A, p.l, p.u) for p in flat], np.asarray(x, dtype=np.float64)[None, :], tol=1e-6)[0]
+            inside = {id(p): bool(v) for p, v in zip(flat, got)}
 
-    def alive(poly):
-        return ph.contains(poly, x, closed=True) and not ph.isempty(poly, lp)
+    def alive(piece, poly):
+        member = inside[id(piece)] if id(piece) in inside else ph.contains(piece, x, closed=True)
+        return member and not ph.isempty(poly, lp)
 
     def rec(depth, poly, idx):
         if depth == n:
@@ -129,7 +140,7 @@ def intersection_leaves(unions, red_lengths, x, lp):
             return
         for k, piece in enumerate(unions[depth]):
             cur = piece if poly is None else ph.intersect(piece, poly)
-            if not alive(cur):
+            if not alive(piece, cur):                    # the parent already contains x: only the new piece is tested
                 continue
             rec(depth + 1, cur, idx + [k])
 
@@ -229,7 +240,7 @@ class NetSolver:
         widths = [len(c) for c in combined]
         if len(widths) > 3 and sum(widths) > 20:
             raise SolveError("Too many solutions to combine.")
-        return intersection_leaves(combined, [len(c) for c in complements], x, self.lp)
+        return intersection_leaves(combined, [len(c) for c in complements], x, self.lp, self.engine)
 
     # ---- algorithm.jl:1-127 -------------------------------------------------------------------------------
     def solve(self, x_init):

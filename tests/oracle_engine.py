@@ -28,3 +28,7 @@ class OracleEngine:
     def comp_indices(self, g, z, w, tol=1e-2):
         z = np.atleast_2d(z); w = np.asarray(w, dtype=float).reshape(len(z), -1)
         return np.array([cport.comp_indices(g, z[b], w[b], tol) for b in range(len(z))])
+
+    def halfspace_in(self, polys, x, tol=1e-6):
+        x = np.atleast_2d(x)
+        return np.array([[cport.halfspace_in(P[0], P[1], P[2], x[j], tol) if len(P[1]) else True for P in polys] for j in range(len(x))])
