@@ -211,6 +211,13 @@ int qpn_level_equilibrium_resident_dev(qpn_handle *h, qpn_level_dev *lvd, int ba
                                        int32_t *iters_out, int32_t *pivots_out, double *lam_out,
                                        void *stream);
 
+/*
+ * Engine options (no reference counterpart).  "force_big" = 1 routes every pivoting solve through
+ * the global-memory tableau path that otherwise serves only sizes beyond the shared-memory
+ * tableau (lifted n > ~166; up to n = 1,536); "big_ctas_per_sm" caps that path's resident CTAs.
+ */
+int qpn_set_option(qpn_handle *h, const char *name, int64_t value);
+
 /* Device buffers owned by the handle (for callers without their own allocator). */
 int qpn_malloc(qpn_handle *h, size_t bytes, void **dptr);
 int qpn_free(qpn_handle *h, void *dptr);

@@ -213,9 +213,11 @@ __device__ __forceinline__ double block_min(const Tab& t, double v) {   // v >= 
     return m;
 }
 
-__device__ __forceinline__ bool is_free_var(const Tab& t, int k) { return t.l()[k] == -QPN_INF && t.u()[k] == QPN_INF; }
+template <class TT>
+__device__ __forceinline__ bool is_free_var(const TT& t, int k) { return t.l()[k] == -QPN_INF && t.u()[k] == QPN_INF; }
 
-__device__ __forceinline__ void var_bounds(const Tab& t, int var, double& lo, double& up) {
+template <class TT>
+__device__ __forceinline__ void var_bounds(const TT& t, int var, double& lo, double& up) {
     const int n = t.n;
     if (var == 2 * n) { lo = 0.0; up = 1.0; return; }
     if (var < n) { lo = t.l()[var]; up = t.u()[var]; return; }
@@ -227,7 +229,8 @@ __device__ __forceinline__ void var_bounds(const Tab& t, int var, double& lo, do
     lo = 0.0; up = 0.0;  // z_k basic or floating: w_k is an artificial fixed at 0
 }
 
-__device__ __forceinline__ bool artificial_row(const Tab& t, int i) {
+template <class TT>
+__device__ __forceinline__ bool artificial_row(const TT& t, int i) {
     const int v = t.rowvar()[i], n = t.n;
     if (v < n || v == 2 * n) return false;
     const int k = v - n;
@@ -400,7 +403,8 @@ __device__ __forceinline__ void move(Tab& t, int c, double sigma, double theta) 
     QPN_SYNC();
 }
 
-__device__ __forceinline__ void leave_at(Tab& t, int rho, int which) {
+template <class TT>
+__device__ __forceinline__ void leave_at(TT& t, int rho, int which) {
     if (threadIdx.x == 0) {
         double lo, up;
         var_bounds(t, t.rowvar()[rho], lo, up);
@@ -409,13 +413,15 @@ __device__ __forceinline__ void leave_at(Tab& t, int rho, int which) {
     QPN_SYNC();
 }
 
-__device__ __forceinline__ void set_zst(Tab& t, int k, int8_t s) {
+template <class TT>
+__device__ __forceinline__ void set_zst(TT& t, int k, int8_t s) {
     QPN_SYNC();
     if (threadIdx.x == 0) t.zst()[k] = s;
     QPN_SYNC();
 }
 
-__device__ __forceinline__ bool try_exchange(Tab& t, int var) {
+template <class TT>
+__device__ __forceinline__ bool try_exchange(TT& t, int var) {
     const int c = t.colof()[var];
     if (c < 0) return false;
     const int rho = best_artificial_row(t, c);
@@ -488,7 +494,8 @@ __device__ __forceinline__ void compact_dead(Tab& t) {
 }
 
 // ---- crash: bring interior / free variables into the basis ----------------------------
-__device__ __forceinline__ void crash(Tab& t) {
+template <class TT>
+__device__ __forceinline__ void crash(TT& t) {
     const int n = t.n;
     // phase 0: free variables exchange against rows of free variables only.  Nothing here depends
     // on the start point or on q (a shared matrix could do it once); the homotopy column is then
@@ -544,15 +551,20 @@ __device__ __forceinline__ void crash(Tab& t) {
     }
 }
 
-__device__ __forceinline__ void repair(Tab& t) {
+// Is any row still artificial?  (block-uniform; contains a barrier)
+__device__ __forceinline__ bool any_artificial_row(const Tab& t) {
+    int any = 0;
+    if (threadIdx.x < t.n) any = artificial_row(t, threadIdx.x) ? 1 : 0;
+    return QPN_SYNC_OR(any) != 0;
+}
+
+template <class TT>
+__device__ __forceinline__ void repair(TT& t) {
     const int n = t.n;
     bool progress = true;
     while (progress) {
         progress = false;
-        int any = 0;
-        if (threadIdx.x < n) any = artificial_row(t, threadIdx.x) ? 1 : 0;
-        any = QPN_SYNC_OR(any);
-        if (!any) return;
+        if (!any_artificial_row(t)) return;
         for (int k = 0; k < n; ++k) {
             const int8_t s = t.zst()[k];
             if ((s == AT_L || s == AT_U) && t.l()[k] != t.u()[k] && t.rowof()[k] < 0 && t.rowof()[n + k] < 0) {
@@ -567,7 +579,8 @@ __device__ __forceinline__ void repair(Tab& t) {
 }
 
 // ---- phase 2: complementary pivoting (avi_scratch.jl:59-132) ------------------------------
-__device__ __forceinline__ int lemke(Tab& t, int max_pivots) {
+template <class TT>
+__device__ __forceinline__ int lemke(TT& t, int max_pivots) {
     const int n = t.n;
     int ent = 2 * n; double sigma = 1.0;
     for (;;) {

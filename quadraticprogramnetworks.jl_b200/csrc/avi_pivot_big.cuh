@@ -1,0 +1,331 @@
+// The same complementary-pivoting engine (avi_pivot.cuh) for AVIs whose compact tableau does
+// not fit shared memory (n > ~166) or has more rows than a CTA may have threads: one CTA per
+// instance, the fp64 tableau in GLOBAL memory (row-major, one workspace slot per resident CTA,
+// L2 / HBM streamed), every per-row / per-column vector still in shared memory.
+//
+// Reference sizes this covers: robust_avoid levels 1-2 when pieces make
+// them wide, the synthetic 3-level chain (d1 = 128 / 256 / 384) and the n = 256, m = 512
+// monotone stress AVI (lifted n = 1,280 or 1,536); /root/reference/src/avi.jl:63-77 is still the
+// call site being replaced.
+//
+// Work split: a pivot is one pass over the live tableau -- warps take rows (stride = warps per
+// CTA), lanes take pairs of columns (128-bit accesses, fully coalesced); the scaled pivot row
+// and the entering column are staged in shared memory first.  Rows whose entering-column entry
+// is zero and column pairs whose pivot-row entries are zero are skipped without being read, so a
+// sparse tableau costs its non-zero work only.  The control flow (crash, repair, path following)
+// is the very same template code as the shared-memory engine, and each tableau entry is still
+// updated by exactly one fma(-d_i, prow_j, T_ij): results are bit-identical to the CPU oracle.
+//
+// Roofline: HBM / L2 bandwidth.  Algorithmic bytes per pivot: 16 * n * ncol (read + write of the
+// live tableau), + 8 * (n + ncol) for the staged column and row.
+#pragma once
+#include "avi_pivot.cuh"
+
+namespace qpn {
+
+struct BigTab {
+    Tab v;              // shared-memory vectors (carved with no tableau inside: td = 0)
+    double* Tg;         // this CTA's tableau slot in global memory: n x ldr, row-major, negated
+    int dcol_off;       // byte offset in qpn_smem of the entering-column cache (nmax doubles)
+    int n, ldr, ncol, pivots;
+    int cc, cpiv;       // which column the cache holds and at which pivot count it was read
+
+    __device__ __forceinline__ double* prow() const { return v.prow(); }
+    __device__ __forceinline__ double* nbval() const { return v.nbval(); }
+    __device__ __forceinline__ double* beta() const { return v.beta(); }
+    __device__ __forceinline__ double* l() const { return v.l(); }
+    __device__ __forceinline__ double* u() const { return v.u(); }
+    __device__ __forceinline__ double* rr() const { return v.rr(); }
+    __device__ __forceinline__ int* rowvar() const { return v.rowvar(); }
+    __device__ __forceinline__ int* colvar() const { return v.colvar(); }
+    __device__ __forceinline__ int* rowof() const { return v.rowof(); }
+    __device__ __forceinline__ int* colof() const { return v.colof(); }
+    __device__ __forceinline__ int8_t* zst() const { return v.zst(); }
+    __device__ __forceinline__ double* dcol() const { return reinterpret_cast<double*>(qpn_smem + dcol_off); }
+};
+
+// Shared-memory bytes of the vectors of a big tableau with up to nmax rows (ldr of the full
+// n x (n+1) shape) plus the column cache.
+__host__ __device__ __forceinline__ size_t big_smem_bytes(int nmax) {
+    return tab_smem_bytes_ex(nmax, 0, row_stride(nmax + 1)) + 8 * (size_t)((nmax + 1) & ~1);
+}
+// Doubles of one global workspace slot.
+__host__ __device__ __forceinline__ size_t big_slot_doubles(int nmax) { return (size_t)nmax * row_stride(nmax + 1); }
+
+// Returns the byte offset just past the workspace.
+__device__ __forceinline__ int big_carve(BigTab& t, int nmax, double* slot, int base_off) {
+    tab_carve_ex(t.v, nmax, 0, row_stride(nmax + 1), base_off);
+    t.dcol_off = base_off + (int)tab_smem_bytes_ex(nmax, 0, row_stride(nmax + 1));
+    t.Tg = slot;
+    t.n = nmax; t.ldr = row_stride(nmax + 1); t.ncol = 0; t.pivots = 0; t.cc = -1; t.cpiv = -1;
+    return base_off + (int)big_smem_bytes(nmax);
+}
+__device__ __forceinline__ void big_shape(BigTab& t, int n, int cap) { t.n = n; t.ldr = row_stride(cap); t.cc = -1; }
+
+// ---- entering column into shared memory ------------------------------------------------------
+// Block-uniform; ends with a barrier when it had to read.
+__device__ __forceinline__ void big_col(BigTab& t, int c) {
+    if (t.cc == c && t.cpiv == t.pivots) return;
+    const int n = t.n, ldr = t.ldr;
+    double* d = t.dcol();
+    for (int r = threadIdx.x; r < n; r += blockDim.x) d[r] = t.Tg[(size_t)r * ldr + c];
+    t.cc = c; t.cpiv = t.pivots;
+    QPN_SYNC();
+}
+
+// ---- start of the normal-map path (avi_scratch.jl:17-50) -------------------------------------
+// Expects Tg[i][0:n] = -M[i][:], t.l(), t.u() filled, q and z0 readable (shared or global).
+// Md (may be null): the dense column-major matrix itself (coalesced row products).  Ends with a barrier.
+__device__ __noinline__ void big_start(BigTab& t, const double* Md, const double* q, const double* z0) {
+    const int n = t.n, ldr = t.ldr;
+    double* zb = t.prow();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) zb[i] = fmin(fmax(z0[i], t.l()[i]), t.u()[i]);
+    QPN_SYNC();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double* row = t.Tg + (size_t)i * ldr;
+        double acc = 0.0;
+        if (Md) {
+            for (int j = 0; j < n; ++j) {
+                const double mij = Md[(size_t)j * n + i];
+                if (mij != 0.0) acc = fma(mij, zb[j], acc);
+            }
+        } else {
+            for (int j = 0; j < n; ++j) {
+                const double mij = -row[j];
+                if (mij != 0.0) acc = fma(mij, zb[j], acc);
+            }
+        }
+        const double zi = z0[i], zbi = zb[i];
+        const double r = ((acc + q[i]) + zi) - zbi;
+        row[n] = -r;
+        if (n + 1 < ldr) row[n + 1] = 0.0;
+        t.rr()[i] = r;
+        t.beta()[i] = zbi - zi;
+        t.rowvar()[i] = n + i;
+        t.zst()[i] = (zi <= t.l()[i]) ? AT_L : (zi >= t.u()[i]) ? AT_U : FLOATING;
+        t.rowof()[i] = -1; t.colof()[i] = i;
+        t.rowof()[n + i] = i; t.colof()[n + i] = -1;
+        t.colvar()[i] = i;
+    }
+    QPN_SYNC();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) t.nbval()[i] = zb[i];      // zb aliases prow, nbval is separate
+    if (threadIdx.x == 0) {
+        t.colvar()[n] = 2 * n; t.nbval()[n] = 0.0;
+        t.rowof()[2 * n] = -1; t.colof()[2 * n] = n;
+    }
+    t.ncol = n + 1; t.pivots = 0; t.cc = -1;
+    QPN_SYNC();
+}
+
+// ---- rank-1 pivot (avi_scratch.jl:2-7) -------------------------------------------------------
+__device__ __noinline__ void big_pivot(BigTab& t, int rho, int c, bool compact) {
+    big_col(t, c);
+    const int n = t.n, ldr = t.ldr, ncol = t.ncol;
+    const int nce = (ncol + 1) & ~1;
+    const double* dc = t.dcol();
+    double* prow = t.prow();
+    const double* prho = t.Tg + (size_t)rho * ldr;
+    const double p = dc[rho];
+    for (int j = threadIdx.x; j < nce; j += blockDim.x)
+        prow[j] = (j >= ncol) ? 0.0 : (j == c) ? (1.0 / p) : prho[j] / p;
+    const int lv = t.rowvar()[rho];
+    const bool dead = compact && lv >= n && lv < 2 * n && is_free_var(t, lv - n);
+    const int last = ncol - 1;
+    QPN_SYNC();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int i = w; i < n; i += nw) {
+        double* row = t.Tg + (size_t)i * ldr;
+        const double d = dc[i];
+        if (i == rho) {
+            for (int j = 2 * lane; j < nce; j += 64)
+                *reinterpret_cast<double2*>(row + j) = *reinterpret_cast<const double2*>(prow + j);
+        } else if (d != 0.0) {
+            const double nd = -d;
+#pragma unroll 4
+            for (int j = 2 * lane; j < nce; j += 64) {
+                const double2 pj = *reinterpret_cast<const double2*>(prow + j);
+                if (pj.x == 0.0 && pj.y == 0.0) continue;
+                double2 tv = *reinterpret_cast<double2*>(row + j);
+                if (j == c) tv.x = 0.0;
+                if (j + 1 == c) tv.y = 0.0;
+                tv.x = fma(nd, pj.x, tv.x);
+                tv.y = fma(nd, pj.y, tv.y);
+                *reinterpret_cast<double2*>(row + j) = tv;
+            }
+        }
+        if (dead && c != last) {
+            __syncwarp();
+            if (lane == 0) row[c] = row[last];
+        }
+    }
+    if (threadIdx.x == 0) {
+        const int ev = t.colvar()[c];
+        const double vent = t.nbval()[c], vlv = t.beta()[rho];
+        t.rowvar()[rho] = ev; t.rowof()[ev] = rho; t.colof()[ev] = -1; t.rowof()[lv] = -1;
+        t.beta()[rho] = vent;
+        if (dead) {
+            t.colof()[lv] = -1;
+            if (c != last) {
+                const int mv = t.colvar()[last];
+                t.colvar()[c] = mv; t.nbval()[c] = t.nbval()[last]; t.colof()[mv] = c;
+            }
+        } else {
+            t.colvar()[c] = lv; t.colof()[lv] = c; t.nbval()[c] = vlv;
+        }
+    }
+    t.ncol = dead ? last : ncol;
+    t.pivots++;
+    QPN_SYNC();
+}
+__device__ __forceinline__ void pivot(BigTab& t, int rho, int c, bool compact = true) { big_pivot(t, rho, c, compact); }
+
+// Largest |T[i][c]| over the rows selected by `pick`; ties -> lowest row.  -1 when below PIV_TOL.
+template <class Pick>
+__device__ __forceinline__ int big_best_row(BigTab& t, int c, Pick pick) {
+    big_col(t, c);
+    const double* dc = t.dcol();
+    double a = 0.0; int idx = -1;
+    for (int r = threadIdx.x; r < t.n; r += blockDim.x) {
+        if (!pick(r)) continue;
+        const double v = fabs(dc[r]);
+        if (v > a) { a = v; idx = r; }
+    }
+    block_argmax_idx(t.v, idx >= 0, a, idx);
+    return (idx >= 0 && a > PIV_TOL) ? idx : -1;
+}
+__device__ __noinline__ int best_artificial_row(BigTab& t, int c) {
+    return big_best_row(t, c, [&](int r) { return artificial_row(t, r); });
+}
+__device__ __noinline__ int best_free_row(BigTab& t, int c) {
+    const int n = t.n;
+    return big_best_row(t, c, [&](int r) { const int v = t.rowvar()[r]; return v >= n && v < 2 * n && is_free_var(t, v - n); });
+}
+
+__device__ __forceinline__ bool any_artificial_row(const BigTab& t) {
+    int any = 0;
+    for (int r = threadIdx.x; r < t.n; r += blockDim.x) any |= artificial_row(t, r) ? 1 : 0;
+    return QPN_SYNC_OR(any) != 0;
+}
+
+// ---- ratio test (avi_scratch.jl:65-77); every exit ends with a barrier ---------------------------
+__device__ __forceinline__ double big_ratio(const BigTab& t, const double* dc, int r, double sigma) {
+    const double d = sigma * dc[r];
+    double lo, up;
+    var_bounds(t, t.rowvar()[r], lo, up);
+    if (d > D_TOL && lo > -QPN_INF) return fmax((t.beta()[r] - lo) / d, 0.0);
+    if (d < -D_TOL && up < QPN_INF) return fmax((up - t.beta()[r]) / (-d), 0.0);
+    return QPN_INF;
+}
+__device__ __noinline__ double ratio_test(BigTab& t, int c, double sigma, int& rho, int& which) {
+    big_col(t, c);
+    const int n = t.n;
+    const double* dc = t.dcol();
+    double rmin = QPN_INF;
+    for (int r = threadIdx.x; r < n; r += blockDim.x) rmin = fmin(rmin, big_ratio(t, dc, r, sigma));
+    const double theta = block_min(t.v, rmin);
+    rho = -1; which = 0;
+    if (theta == QPN_INF) { QPN_SYNC(); return QPN_INF; }
+    const double cut = theta + TIE_TOL * (1.0 + theta);
+    // among ties: t first (so the path terminates), then largest |d|, then lowest row
+    double key = 0.0; int idx = -1;
+    for (int r = threadIdx.x; r < n; r += blockDim.x) {
+        if (!(big_ratio(t, dc, r, sigma) <= cut)) continue;
+        const double k = (t.rowvar()[r] == 2 * n) ? QPN_INF : fabs(dc[r]);
+        if (idx < 0 || k > key) { key = k; idx = r; }
+    }
+    block_argmax_idx(t.v, idx >= 0, key, idx);
+    rho = idx;
+    QPN_SYNC();
+    if (threadIdx.x == 0) t.v.red_d()[32] = big_ratio(t, dc, rho, sigma);
+    QPN_SYNC();
+    const double th = t.v.red_d()[32];
+    which = (sigma * dc[rho] > 0.0) ? -1 : +1;
+    return th;
+}
+
+__device__ __forceinline__ void move(BigTab& t, int c, double sigma, double theta) {
+    if (theta == 0.0) return;
+    big_col(t, c);
+    const double* dc = t.dcol();
+    for (int r = threadIdx.x; r < t.n; r += blockDim.x) {
+        const double ci = dc[r];
+        if (ci != 0.0) t.beta()[r] = fma(-(sigma * theta), ci, t.beta()[r]);
+    }
+    if (threadIdx.x == 0) t.nbval()[c] = fma(sigma, theta, t.nbval()[c]);
+    QPN_SYNC();
+}
+
+// T[:, t] = B^-1 r from the slack columns (see avi_pivot.cuh).  Ends with a barrier.
+__device__ __noinline__ void recompute_tcol(BigTab& t) {
+    const int n = t.n, ldr = t.ldr;
+    const int tc = t.colof()[2 * n];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double* row = t.Tg + (size_t)i * ldr;
+        double acc = 0.0;
+        for (int k = 0; k < n; ++k) {
+            const int ck = t.colof()[n + k];
+            const double pik = ck >= 0 ? -row[ck] : (t.rowof()[n + k] == i ? -1.0 : 0.0);
+            if (pik != 0.0) acc = fma(pik, t.rr()[k], acc);
+        }
+        row[tc] = acc;
+    }
+    t.cc = -1;
+    QPN_SYNC();
+}
+
+// Drop every dead column (slack of a free variable) from the live range at once.
+__device__ __noinline__ void compact_dead(BigTab& t) {
+    const int n = t.n, ldr = t.ldr;
+    int* map = reinterpret_cast<int*>(t.prow());
+    if (threadIdx.x == 0) {
+        int nl = 0;
+        for (int j = 0; j < t.ncol; ++j) {
+            const int v = t.colvar()[j];
+            if (v >= n && v < 2 * n && is_free_var(t, v - n)) t.colof()[v] = -1;
+            else map[nl++] = j;
+        }
+        for (int d = 0; d < nl; ++d) {
+            const int sidx = map[d];
+            if (sidx != d) { const int v = t.colvar()[sidx]; t.colvar()[d] = v; t.nbval()[d] = t.nbval()[sidx]; t.colof()[v] = d; }
+        }
+        t.v.red_i()[32] = nl;
+    }
+    QPN_SYNC();
+    const int nl = t.v.red_i()[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int i = w; i < n; i += nw) {
+        double* row = t.Tg + (size_t)i * ldr;
+        for (int d0 = 0; d0 < nl; d0 += 32) {           // map[d] >= d: a chunk only reads at or beyond itself
+            const int d = d0 + lane;
+            double val = 0.0;
+            if (d < nl) val = row[map[d]];
+            __syncwarp();
+            if (d < nl) row[d] = val;
+            __syncwarp();
+        }
+        if (lane == 0 && (nl & 1)) row[nl] = 0.0;
+    }
+    t.ncol = nl; t.cc = -1;
+    QPN_SYNC();
+}
+
+// Runs crash + repair + path following on a started big tableau; z and the basis codes go to
+// zs / code (shared or global, n entries each; code may be null).  Ends with a barrier.
+__device__ __noinline__ int avi_pivot_run_big(BigTab& t, int max_pivots, double* zs, int8_t* code) {
+    crash(t);
+    repair(t);
+    const int st = lemke(t, max_pivots);
+    QPN_SYNC();
+    for (int i = threadIdx.x; i < t.n; i += blockDim.x) {
+        const int r = t.rowof()[i];
+        zs[i] = r >= 0 ? t.beta()[r] : t.nbval()[t.colof()[i]];
+        if (code) {
+            const int8_t s = t.zst()[i];
+            code[i] = (t.l()[i] == t.u()[i]) ? 4 : (r >= 0 || s == FLOATING) ? 2 : (s == AT_L ? 1 : 3);
+        }
+    }
+    QPN_SYNC();
+    return st;
+}
+
+}  // namespace qpn

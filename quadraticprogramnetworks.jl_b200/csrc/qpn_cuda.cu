@@ -9,6 +9,7 @@
 #include "../../include/qpn_cuda.h"
 #include "qpn_kernels.cuh"
 #include "qpn_level.cuh"
+#include "qpn_big.cuh"
 
 using namespace qpn;
 
@@ -26,6 +27,11 @@ struct qpn_handle {
     // grow-only buffers for the plans of one-off calls (cudaMalloc / cudaFree per call cost milliseconds)
     unsigned char* plan_buf[2] = {nullptr, nullptr};
     size_t plan_buf_bytes[2] = {0, 0};
+    // global-memory tableau slots of the big path (avi_pivot_big.cuh), grow-only
+    double* big_work = nullptr;
+    size_t big_work_doubles = 0;
+    int force_big = 0;          // option "force_big": route every pivoting solve through the big path (tests)
+    int big_ctas_per_sm = 0;    // option "big_ctas_per_sm": 0 = as many as fit
 };
 
 static std::string g_create_error;
@@ -111,6 +117,7 @@ extern "C" int qpn_destroy(qpn_handle* h) {
     cudaSetDevice(h->device);
     if (h->arena) cudaFree(h->arena);
     for (int k = 0; k < 2; ++k) if (h->plan_buf[k]) cudaFree(h->plan_buf[k]);
+    if (h->big_work) cudaFree(h->big_work);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return 0;
@@ -123,6 +130,13 @@ extern "C" int qpn_synchronize(qpn_handle* h) {
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
     return 0;
+}
+
+extern "C" int qpn_set_option(qpn_handle* h, const char* name, int64_t value) {
+    if (!h || !name) return -1;
+    if (!strcmp(name, "force_big")) { h->force_big = value != 0; return 0; }
+    if (!strcmp(name, "big_ctas_per_sm")) { h->big_ctas_per_sm = (int)value; return 0; }
+    return fail(h, "qpn_set_option: unknown option '%s'", name);
 }
 
 extern "C" int qpn_malloc(qpn_handle* h, size_t bytes, void** dptr) {
@@ -313,17 +327,137 @@ static int build_plan_avi(qpn_handle* h, int n_, const MatDesc& M, const double*
     return 0;
 }
 
+// ---- big path (global-memory tableau) ----------------------------------------------------------
+// Largest n the big path takes: its vectors must fit shared memory next to a kernel's extras.
+static bool big_needed(qpn_handle* h, int n, size_t smem_small) {
+    return h->force_big || n > 256 || smem_small > (size_t)h->max_smem_optin;
+}
+
+// Grid of persistent CTAs for a big kernel and the workspace for their slots.
+template <class K>
+static int big_grid(qpn_handle* h, K kernel, int nmax, size_t smem, int batch, int* grid_out) {
+    if (smem > (size_t)h->max_smem_optin)
+        return fail(h, "size n=%d needs %zu B of shared memory per CTA on the global-memory tableau path (limit %d)", nmax, smem,
+                    h->max_smem_optin);
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, QPN_BIG_THREADS, smem));
+    if (per_sm < 1) return fail(h, "big path: kernel does not fit an SM (n=%d, %zu B shared memory)", nmax, smem);
+    if (h->big_ctas_per_sm > 0 && per_sm > h->big_ctas_per_sm) per_sm = h->big_ctas_per_sm;
+    int grid = per_sm * h->sm_count;
+    if (grid > batch) grid = batch;
+    const size_t need = (size_t)grid * big_slot_doubles(nmax);
+    if (need > h->big_work_doubles) {
+        CK(cudaStreamSynchronize(h->stream));
+        if (h->big_work) cudaFree(h->big_work);
+        h->big_work = nullptr; h->big_work_doubles = 0;
+        cudaError_t e = cudaMalloc((void**)&h->big_work, 8 * need);
+        if (e != cudaSuccess) return fail(h, "big path: cudaMalloc(%zu B of tableau slots): %s", 8 * need, cudaGetErrorString(e));
+        h->big_work_doubles = need;
+    }
+    *grid_out = grid;
+    return 0;
+}
+
+// Plan through the big kernel.  kind 0 / 1: the GAVI's lifted / presolve AVI; kind 2: plain AVI (M, l, u of size n_avi).
+// Buffers as in build_plan: blob_out != NULL -> fresh allocation owned by the caller, else the handle's slot `slot`.
+static int build_plan_big(qpn_handle* h, const GaviDesc& g, int kind, int n_avi, const MatDesc& M, const double* l, const double* u,
+                          int slot, PlanDesc* out, unsigned char** blob_out) {
+    const size_t n = kind == 2 ? (size_t)n_avi : (size_t)g.d1 + 2 * g.d2, dz = (size_t)g.d1 + g.d2;
+    const size_t ldrw = row_stride((int)n + 1);
+    size_t need = 0;
+    auto add = [&](size_t bytes) { size_t off = (need + 255) & ~(size_t)255; need = off + bytes; return off; };
+    const size_t oT0 = add(8 * n * ldrw), oPT = add(8 * n * n), oval = add(8 * n * n), orv = add(4 * n), ocv = add(4 * (n + 1)),
+                 optr = add(4 * (n + 1)), ocol = add(4 * n * n), ocols = add(4 * (dz + 1)), ohdr = add(16);
+    const size_t smem = big_smem_bytes((int)n) + (kind == 2 ? 16 * n : gavi_extra_bytes(g.d1, g.d2, g.np)) + 4 * n + 16;
+    int grid = 0;
+    if (big_grid(h, plan_build_big_kernel, (int)n, smem, 1, &grid)) return -1;
+    unsigned char* b = nullptr;
+    if (blob_out) {
+        CK(cudaMalloc((void**)&b, need + 256));
+    } else {
+        if (need + 256 > h->plan_buf_bytes[slot]) {
+            if (h->plan_buf[slot]) cudaFree(h->plan_buf[slot]);
+            h->plan_buf[slot] = nullptr; h->plan_buf_bytes[slot] = 0;
+            CK(cudaMalloc((void**)&h->plan_buf[slot], need + 256));
+            h->plan_buf_bytes[slot] = need + 256;
+        }
+        b = h->plan_buf[slot];
+    }
+    plan_build_big_kernel<<<1, QPN_BIG_THREADS, smem, h->stream>>>(g, kind, n_avi, M, l, u, (double*)(b + oT0), (double*)(b + oPT),
+                                                                   (int*)(b + orv), (int*)(b + ocv), (int*)(b + optr), (int*)(b + ocol),
+                                                                   (double*)(b + oval), (int*)(b + ocols), (int*)(b + ohdr), h->big_work);
+    h->launches++;
+    CK(cudaGetLastError());
+    int hdr[4];
+    CK(cudaMemcpyAsync(hdr, b + ohdr, sizeof hdr, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    PlanDesc P;
+    P.n = kind == 1 ? hdr[3] + 2 * g.d2 : (int)n;
+    P.ncol0 = hdr[0]; P.npiv0 = hdr[1]; P.tcol0 = hdr[2];
+    P.T0 = (double*)(b + oT0); P.PT = (double*)(b + oPT); P.rowvar0 = (int*)(b + orv); P.colvar0 = (int*)(b + ocv);
+    P.csr_ptr = (int*)(b + optr); P.csr_col = (int*)(b + ocol); P.csr_val = (double*)(b + oval);
+    P.cols = (int*)(b + ocols); P.ncols = hdr[3];
+    *out = P;
+    if (blob_out) *blob_out = b;
+    return 0;
+}
+
+static int launch_avi_big(qpn_handle* h, int n, int batch, const MatDesc& M, const double* q, const double* l, const double* u,
+                          int lu_shared, const double* z0, int max_pivots, double* z, int32_t* st, int32_t* pv, int8_t* basis,
+                          cudaStream_t s) {
+    if (s != h->stream) return fail(h, "the global-memory tableau path (n=%d) runs on the handle's stream only", n);
+    const size_t smem = big_smem_bytes(n) + 8 * 3 * (size_t)n + (((size_t)n + 15) & ~(size_t)15);
+    int grid = 0;
+    if (big_grid(h, avi_solve_big_kernel, n, smem, batch, &grid)) return -1;
+    PlanDesc P;
+    memset(&P, 0, sizeof P);
+    int has_plan = 0;
+    if (M.shared && lu_shared && batch >= 2) {
+        GaviDesc g0;
+        memset(&g0, 0, sizeof g0);
+        if (build_plan_big(h, g0, 2, n, M, l, u, 0, &P, nullptr)) return -1;
+        has_plan = 1;
+    }
+    avi_solve_big_kernel<<<grid, QPN_BIG_THREADS, smem, s>>>(n, batch, M, P, has_plan, q, l, u, lu_shared, z0, max_pivots, z, st, pv,
+                                                             basis, h->big_work, big_slot_doubles(n));
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int launch_gavi_big(qpn_handle* h, const GaviDesc& g, int batch, const double* w, const double* z0, int presolve,
+                           int max_pivots, double* z, double* zfull, int32_t* st, int32_t* pv, int8_t* basis, cudaStream_t s) {
+    const int n = g.d1 + 2 * g.d2;
+    if (s != h->stream) return fail(h, "the global-memory tableau path (n=%d) runs on the handle's stream only", n);
+    const size_t smem = big_smem_bytes(n) + gavi_extra_bytes(g.d1, g.d2, g.np);
+    int grid = 0;
+    if (big_grid(h, gavi_solve_big_kernel, n, smem, batch, &grid)) return -1;
+    GaviPlans plans;
+    memset(&plans, 0, sizeof plans);
+    if (batch >= 2) {
+        MatDesc m0;
+        memset(&m0, 0, sizeof m0);
+        if (build_plan_big(h, g, 0, 0, m0, nullptr, nullptr, 0, &plans.A, nullptr) ||
+            build_plan_big(h, g, 1, 0, m0, nullptr, nullptr, 1, &plans.B, nullptr)) return -1;
+        plans.has = 1;
+    }
+    if (max_pivots <= 0) max_pivots = 50 * n + 100;
+    gavi_solve_big_kernel<<<grid, QPN_BIG_THREADS, smem, s>>>(g, plans, batch, w, z0, presolve, max_pivots, z, zfull, st, pv, basis,
+                                                              h->big_work, big_slot_doubles(n));
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 // ---- solve_avi -----------------------------------------------------------------------------
 static int launch_avi(qpn_handle* h, int n, int batch, const MatDesc& M, const double* q, const double* l,
                       const double* u, int lu_shared, const double* z0, int max_pivots, double* z,
                       int32_t* st, int32_t* pv, int8_t* basis, cudaStream_t s) {
     if (batch <= 0) return 0;
     const size_t smem = tab_smem_bytes(n, n + 1) + 2 * sizeof(double) * (size_t)n;
-    if (smem > (size_t)h->max_smem_optin)
-        return fail(h, "AVI of size n=%d needs %zu B of shared memory per CTA (limit %d): the shared-memory "
-                       "tableau path does not cover this size", n, smem, h->max_smem_optin);
     if (max_pivots <= 0) max_pivots = 50 * n + 100;
-    if (n > 256) return fail(h, "AVI of size n=%d exceeds the one-thread-per-row limit of 256", n);
+    if (big_needed(h, n, smem)) return launch_avi_big(h, n, batch, M, q, l, u, lu_shared, z0, max_pivots, z, st, pv, basis, s);
     if (M.shared && lu_shared && batch >= QPN_PLAN_MIN_BATCH && s == h->stream) {
         // matrix and bounds shared by a large batch: the crash prefix is computed once
         PlanDesc P;
@@ -442,7 +576,8 @@ static int launch_gavi(qpn_handle* h, const GaviDesc& g, int batch, const double
                        int max_pivots, double* z, double* zfull, int32_t* st, int32_t* pv, int8_t* basis, cudaStream_t s) {
     if (batch <= 0) return 0;
     const int n = g.d1 + 2 * g.d2;
-    if (n > 256) return fail(h, "GAVI of lifted size n=%d exceeds the one-thread-per-row limit of 256", n);
+    if (big_needed(h, n, gavi_smem_bytes(g.d1, g.d2, g.np)))
+        return launch_gavi_big(h, g, batch, w, z0, presolve, max_pivots, z, zfull, st, pv, basis, s);
     GaviPlans plans;
     plans.has = 0;
     if (batch >= QPN_PLAN_MIN_BATCH && s == h->stream) {       // plans are built (and synchronised) on the handle's stream

@@ -80,7 +80,7 @@ EXPORTS = [
     "qpn_halfspace_in_batched", "qpn_verify_solution_batched",
     "qpn_level_equilibrium_batched", "qpn_level_equilibrium_batched_dev",
     "qpn_level_upload", "qpn_level_release", "qpn_level_equilibrium_resident", "qpn_level_equilibrium_resident_dev",
-    "qpn_malloc", "qpn_free", "qpn_memcpy_h2d", "qpn_memcpy_d2h",
+    "qpn_malloc", "qpn_free", "qpn_memcpy_h2d", "qpn_memcpy_d2h", "qpn_set_option",
 ]
 
 
@@ -153,6 +153,10 @@ class Engine:
 
     def synchronize(self):
         self._ck(self.lib.qpn_synchronize(self.h))
+
+    def set_option(self, name, value):
+        """qpn_set_option: "force_big" (global-memory tableau path for every solve), "big_ctas_per_sm"."""
+        self._ck(self.lib.qpn_set_option(self.h, name.encode(), C.c_int64(int(value))))
 
     # ---- matrices ----------------------------------------------------------------------
     @staticmethod

@@ -1,0 +1,138 @@
+"""GPU parity of the global-memory tableau path (csrc/avi_pivot_big.cuh, csrc/qpn_big.cuh) -- the
+engine for AVIs beyond the shared-memory tableau (lifted n up to 1,536).
+
+Two kinds of cases: (1) the small parity suites of test_gpu_parity.py pushed through the big path
+with the "force_big" option, so every branch (plans, per-instance matrices, CSC, presolve) is
+compared bit for bit against the C oracle cheaply; (2) sizes that can ONLY run there."""
+import numpy as np
+import pytest
+
+from oracle import cport, examples, qpn_ref
+from tests import problems
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def big_engine(engine):
+    engine.set_option("force_big", 1)
+    yield engine
+    engine.set_option("force_big", 0)
+
+
+def monotone_gavi(rng, n, m, np_=0):
+    """SURVEY.md 8d config 5 at a chosen size: Q = G'G + 0.1 I, rows of A normalised, l = A xbar - U(0.1,1), u = +inf."""
+    G = rng.normal(size=(n, n)) / np.sqrt(n)
+    Q = G.T @ G + 0.1 * np.eye(n)
+    A = rng.normal(size=(m, n)); A /= np.linalg.norm(A, axis=1, keepdims=True)
+    xbar = rng.normal(size=n)
+    l = A @ xbar - rng.uniform(0.1, 1, m)
+    g = problems.qp_gavi(Q, np.zeros(n), A, l, np.full(m, np.inf))
+    return g, xbar
+
+
+def test_big_avi_four_player_plan_dense_csc(big_engine):
+    rng = np.random.default_rng(21)
+    net, g, avi, dec, par = problems.fp_avi()
+    B = 300
+    X, z0 = problems.fp_starts(rng, B)
+    q = np.tile(avi["o"], (B, 1))
+    zo, so, po, bo = cport.avi_solve_batched(avi["M"], q, avi["l"], avi["u"], z0)
+    z, s, p, b = big_engine.avi_solve(avi["M"], q, avi["l"], avi["u"], z0)           # shared matrix + bounds: plan
+    assert np.array_equal(s, so) and np.array_equal(p, po) and np.array_equal(b, bo) and np.array_equal(z, zo)
+    zc, sc, pc, bc = big_engine.avi_solve(None, q, avi["l"], avi["u"], z0, csc=problems.dense_to_csc(avi["M"], base=1), index_base=1)
+    assert np.array_equal(zc, zo) and np.array_equal(sc, so) and np.array_equal(pc, po) and np.array_equal(bc, bo)
+    # per-instance bounds: no plan, matrix read directly
+    L, U = np.tile(avi["l"], (B, 1)), np.tile(avi["u"], (B, 1))
+    z2, s2, p2, b2 = big_engine.avi_solve(avi["M"], q, L, U, z0)
+    assert np.array_equal(z2, zo) and np.array_equal(s2, so) and np.array_equal(p2, po) and np.array_equal(b2, bo)
+    z3, s3, p3, b3 = big_engine.avi_solve(None, q, L, U, z0, csc=problems.dense_to_csc(avi["M"], base=0), index_base=0)
+    assert np.array_equal(z3, zo) and np.array_equal(s3, so) and np.array_equal(p3, po) and np.array_equal(b3, bo)
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_big_avi_random_qps_per_instance_matrix(big_engine, kind):
+    rng = np.random.default_rng(200 + kind)
+    for trial in range(6):
+        n = int(rng.integers(2, 6))
+        Q, c, A, l, u, z0 = problems.random_qp(rng, kind, n=n)
+        m = len(l)
+        B = 16
+        Ms, qs, ls, us, z0s = [], [], [], [], []
+        for _ in range(B):
+            Q, c, A, l, u, z0 = problems.random_qp(rng, kind, n=n, m=m - (n if kind != 1 else 0))
+            g = problems.qp_gavi(Q, c, A, l, u)
+            avi = qpn_ref.convert(g)
+            Ms.append(avi["M"]); qs.append(avi["o"]); ls.append(avi["l"]); us.append(avi["u"]); z0s.append(np.concatenate([z0, g["A"] @ z0]))
+        Ms, qs, ls, us, z0s = map(np.array, (Ms, qs, ls, us, z0s))
+        zo, so, po, bo = cport.avi_solve_batched(Ms, qs, ls, us, z0s)
+        z, s, p, b = big_engine.avi_solve(Ms, qs, ls, us, z0s)
+        assert np.array_equal(s, so) and np.array_equal(p, po) and np.array_equal(b, bo) and np.array_equal(z, zo)
+
+
+def test_big_gavi_example_levels(big_engine):
+    rng = np.random.default_rng(22)
+    cases = []
+    net = examples.simple_bilevel()
+    g, dec, par = qpn_ref.level_gavi(net, net.depth[2], {})
+    cases.append(("simple_bilevel L2", g, dec, par, rng.normal(size=(48, 4)) * 2))
+    net, g, avi, dec, par = problems.fp_avi()
+    cases.append(("four_player L1", g, dec, par, rng.uniform(-7, 7, (96, 8))))
+    net, X = problems.ra_inits(rng, 96)
+    g, dec, par = qpn_ref.level_gavi(net, net.depth[3], {})
+    cases.append(("robust_avoid L3", g, dec, par, X))
+    for name, g, dec, par, X in cases:
+        B = len(X)
+        dz = g["M"].shape[1]
+        w = X[:, par]
+        z0 = np.zeros((B, dz)); z0[:, :len(dec)] = X[:, dec]
+        ret = big_engine.gavi_solve(g, w, z0)                      # with plans (batch >= 2)
+        one = big_engine.gavi_solve(g, w[:1], z0[:1])              # without
+        for k in range(B):
+            ro = cport.gavi_solve(g, z0[k], w[k])
+            assert ro["status"] == ret["status"][k] and ro["pivots"] == ret["pivots"][k], name
+            assert np.array_equal(ro["basis"], ret["basis"][k]) and np.array_equal(ro["z_full"], ret["z_full"][k]), name
+        assert one["status"][0] == ret["status"][0] and one["pivots"][0] == ret["pivots"][0], name
+        assert np.array_equal(one["z_full"][0], ret["z_full"][0]) and np.array_equal(one["basis"][0], ret["basis"][0]), name
+        assert (ret["status"] == 1).all(), name
+
+
+@pytest.mark.parametrize("n,m,B", [(40, 80, 24), (64, 128, 12)])
+def test_big_monotone_gavi_beyond_shared_memory(engine, n, m, B):
+    """Lifted sizes 200 and 320: no shared-memory tableau exists for them (the second also exceeds one thread per row)."""
+    rng = np.random.default_rng(23 + n)
+    g, xbar = monotone_gavi(rng, n, m)
+    O = rng.normal(size=(B, n))                                    # instances differ in the linear term (as parameters)
+    g["N"] = np.eye(n); g["B"] = np.zeros((m, n))
+    z0 = np.zeros((B, n + m)); z0[:, :n] = xbar + rng.normal(size=(B, n))      # infeasible starts: presolve projection runs
+    ret = engine.gavi_solve(g, O, z0)
+    assert (ret["status"] == 1).all()
+    for k in range(B):
+        ro = cport.gavi_solve(g, z0[k], O[k])
+        assert ro["status"] == ret["status"][k] and ro["pivots"] == ret["pivots"][k]
+        assert np.array_equal(ro["basis"], ret["basis"][k])
+        assert np.array_equal(ro["z_full"], ret["z_full"][k])
+    # the solution is the unique minimiser of a strictly convex QP: KKT residuals
+    x = ret["z"][:, :n]; lam = ret["z"][:, n:]
+    Q, A = g["M"][:, :n], g["A"][:, :n]
+    assert np.abs(x @ Q.T + O - lam @ A).max() < 1e-8
+    assert (x @ A.T - g["l2"] > -1e-8).all() and (lam > -1e-10).all()
+    assert np.abs(lam * (x @ A.T - g["l2"])).max() < 1e-7
+
+
+def test_big_avi_direct_n300_shared_matrix(engine):
+    """A plain AVI with n = 300 (a box-constrained strongly monotone LCP-like problem): plan path, CSR check."""
+    rng = np.random.default_rng(29)
+    n, B = 300, 10
+    G = rng.normal(size=(n, n)) / np.sqrt(n)
+    M = G.T @ G + 0.2 * np.eye(n) + 0.1 * (G - G.T)                 # monotone, not symmetric
+    l = np.where(rng.uniform(size=n) < 0.3, -np.inf, -rng.uniform(0.1, 1, n))
+    u = np.where(rng.uniform(size=n) < 0.3, np.inf, rng.uniform(0.1, 1, n))
+    q = rng.normal(size=(B, n))
+    z0 = rng.normal(size=(B, n))
+    zo, so, po, bo = cport.avi_solve_batched(M, q, l, u, z0)
+    z, s, p, b = engine.avi_solve(M, q, l, u, z0)
+    assert (so == 1).all()
+    assert np.array_equal(s, so) and np.array_equal(p, po) and np.array_equal(b, bo) and np.array_equal(z, zo)
+    bad, r = engine.check_avi(M, q, l, u, z)
+    assert (bad == 0).all()
