@@ -495,12 +495,12 @@ __device__ __forceinline__ void compact_dead(Tab& t) {
 
 // ---- crash: bring interior / free variables into the basis ----------------------------
 template <class TT>
-__device__ __forceinline__ void crash(TT& t) {
+__device__ __forceinline__ void crash(TT& t, bool from_plan) {
     const int n = t.n;
     // phase 0: free variables exchange against rows of free variables only.  Nothing here depends
-    // on the start point or on q (a shared matrix could do it once); the homotopy column is then
-    // rebuilt from r.
-    {
+    // on the start point or on q, so a plan (shared matrix) has done it already: running it again
+    // would retry the variables that found no pivot at their turn, which the specification does not.
+    if (!from_plan) {
         const int piv0 = t.pivots;
         for (int i = 0; i < n; ++i) {
             if (!is_free_var(t, i)) continue;
@@ -626,8 +626,8 @@ __device__ __forceinline__ int lemke(TT& t, int max_pivots) {
 // that solves several AVIs per instance then holds one copy of the engine, and the workspace
 // descriptor travels in registers instead of a local-memory struct.
 struct PivotResult { double zi; int st; int pivots; int code; };
-__device__ __noinline__ PivotResult avi_pivot_run(Tab t, int max_pivots) {
-    crash(t);
+__device__ __noinline__ PivotResult avi_pivot_run(Tab t, int max_pivots, bool from_plan) {
+    crash(t, from_plan);
     repair(t);
     PivotResult out;
     out.st = lemke(t, max_pivots);

@@ -21,6 +21,20 @@
 #pragma once
 #include "avi_pivot.cuh"
 
+#ifdef QPN_BIG_DEBUG
+#include <cstdio>
+#define BIGCHK(cond, what, a, b)                                                                                   \
+    do {                                                                                                           \
+        if (!(cond)) {                                                                                             \
+            if (threadIdx.x == 0) printf("BIGCHK block %d line %d: %s (%d, %d) n=%d ncol=%d piv=%d\n", blockIdx.x, __LINE__, what, (int)(a), (int)(b), t.n, t.ncol, t.pivots); \
+            __syncthreads();                                                                                       \
+            __trap();                                                                                              \
+        }                                                                                                          \
+    } while (0)
+#else
+#define BIGCHK(cond, what, a, b) do { } while (0)
+#endif
+
 namespace qpn {
 
 struct BigTab {
@@ -65,6 +79,7 @@ __device__ __forceinline__ void big_shape(BigTab& t, int n, int cap) { t.n = n; 
 // ---- entering column into shared memory ------------------------------------------------------
 // Block-uniform; ends with a barrier when it had to read.
 __device__ __forceinline__ void big_col(BigTab& t, int c) {
+    BIGCHK(c >= 0 && c < t.ncol, "big_col: column out of range", c, t.ncol);
     if (t.cc == c && t.cpiv == t.pivots) return;
     const int n = t.n, ldr = t.ldr;
     double* d = t.dcol();
@@ -119,6 +134,7 @@ __device__ __noinline__ void big_start(BigTab& t, const double* Md, const double
 
 // ---- rank-1 pivot (avi_scratch.jl:2-7) -------------------------------------------------------
 __device__ __noinline__ void big_pivot(BigTab& t, int rho, int c, bool compact) {
+    BIGCHK(rho >= 0 && rho < t.n, "big_pivot: row out of range", rho, c);
     big_col(t, c);
     const int n = t.n, ldr = t.ldr, ncol = t.ncol;
     const int nce = (ncol + 1) & ~1;
@@ -235,6 +251,7 @@ __device__ __noinline__ double ratio_test(BigTab& t, int c, double sigma, int& r
     }
     block_argmax_idx(t.v, idx >= 0, key, idx);
     rho = idx;
+    BIGCHK(rho >= 0 && rho < n, "ratio_test: no tie winner", rho, c);
     QPN_SYNC();
     if (threadIdx.x == 0) t.v.red_d()[32] = big_ratio(t, dc, rho, sigma);
     QPN_SYNC();
@@ -311,8 +328,8 @@ __device__ __noinline__ void compact_dead(BigTab& t) {
 
 // Runs crash + repair + path following on a started big tableau; z and the basis codes go to
 // zs / code (shared or global, n entries each; code may be null).  Ends with a barrier.
-__device__ __noinline__ int avi_pivot_run_big(BigTab& t, int max_pivots, double* zs, int8_t* code) {
-    crash(t);
+__device__ __noinline__ int avi_pivot_run_big(BigTab& t, int max_pivots, bool from_plan, double* zs, int8_t* code) {
+    crash(t, from_plan);
     repair(t);
     const int st = lemke(t, max_pivots);
     QPN_SYNC();

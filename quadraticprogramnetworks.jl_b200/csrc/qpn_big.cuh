@@ -124,7 +124,7 @@ __device__ __forceinline__ int solve_avi_big(BigTab& t, int n, const PlanDesc* P
                                              double* zs, double* zb, int max_pivots, int8_t* code, int* pivots_acc) {
     if (P) big_start_plan(t, *P, qs, zs, zb);
     else { big_shape(t, n, n + 1); build(t); big_start(t, Md, qs, zs); }
-    int st = avi_pivot_run_big(t, max_pivots, zs, code);
+    int st = avi_pivot_run_big(t, max_pivots, P != nullptr, zs, code);
     *pivots_acc += t.pivots;
     int bad = 0;
     if (P) {

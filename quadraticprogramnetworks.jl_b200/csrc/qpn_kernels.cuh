@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(MAXT, 896 / MAXT) avi_solve_kernel(int n, int 
     }
     load_neg_matrix(t, M, b);
     tab_start(t, qs, zs);
-    const PivotResult pr = avi_pivot_run(t, max_pivots);
+    const PivotResult pr = avi_pivot_run(t, max_pivots, false);
     const double zi = pr.zi; const int8_t code = (int8_t)pr.code;
     int st = pr.st;
     const int piv = pr.pivots;

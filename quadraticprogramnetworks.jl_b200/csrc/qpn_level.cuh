@@ -81,7 +81,7 @@ __device__ __forceinline__ int solve_avi_smem(Tab& t, int n, Build build, const 
     tab_shape(t, n, n + 1);
     build(t);
     tab_start(t, qs, zs);
-    const PivotResult pr = avi_pivot_run(t, max_pivots);
+    const PivotResult pr = avi_pivot_run(t, max_pivots, false);
     const double zi = pr.zi; const int8_t code = (int8_t)pr.code;
     int st = pr.st;
     *pivots_acc += pr.pivots;
@@ -101,7 +101,7 @@ __device__ __forceinline__ int solve_avi_plan(Tab& t, const PlanDesc& P, const d
                                      int max_pivots, int8_t* code_out, int* pivots_acc) {
     const int n = P.n, i = threadIdx.x;
     tab_start_plan(t, P, qs, zs, zb);
-    const PivotResult pr = avi_pivot_run(t, max_pivots);
+    const PivotResult pr = avi_pivot_run(t, max_pivots, true);
     const double zi = pr.zi; const int8_t code = (int8_t)pr.code;
     int st = pr.st;
     *pivots_acc += pr.pivots;

@@ -97,14 +97,16 @@ def test_big_gavi_example_levels(big_engine):
         assert (ret["status"] == 1).all(), name
 
 
-@pytest.mark.parametrize("n,m,B", [(40, 80, 24), (64, 128, 12)])
-def test_big_monotone_gavi_beyond_shared_memory(engine, n, m, B):
+@pytest.mark.parametrize("n,m,B,feasible", [(40, 80, 24, False), (64, 128, 12, False), (64, 128, 24, True)])
+def test_big_monotone_gavi_beyond_shared_memory(engine, n, m, B, feasible):
     """Lifted sizes 200 and 320: no shared-memory tableau exists for them (the second also exceeds one thread per row)."""
     rng = np.random.default_rng(23 + n)
     g, xbar = monotone_gavi(rng, n, m)
     O = rng.normal(size=(B, n))                                    # instances differ in the linear term (as parameters)
     g["N"] = np.eye(n); g["B"] = np.zeros((m, n))
-    z0 = np.zeros((B, n + m)); z0[:, :n] = xbar + rng.normal(size=(B, n))      # infeasible starts: presolve projection runs
+    # infeasible starts: the presolve projection runs.  Feasible start: phase 0 of the plan leaves 64 free
+    # variables without a pivot, which phase 1 must pick up exactly as the specification does.
+    z0 = np.zeros((B, n + m)); z0[:, :n] = xbar + (0.0 if feasible else 1.0) * rng.normal(size=(B, n))
     ret = engine.gavi_solve(g, O, z0)
     assert (ret["status"] == 1).all()
     for k in range(B):
