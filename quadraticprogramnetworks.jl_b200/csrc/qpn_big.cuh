@@ -6,7 +6,10 @@
 
 namespace qpn {
 
-constexpr int QPN_BIG_THREADS = 512;
+#ifndef QPN_BIG_THREADS_N
+#define QPN_BIG_THREADS_N 1024
+#endif
+constexpr int QPN_BIG_THREADS = QPN_BIG_THREADS_N;
 
 // ---- builders: Tg[i][0:n] = -M[i][:]; each ends with a barrier -----------------------------------
 __device__ __forceinline__ void big_zero(BigTab& t, int n) {

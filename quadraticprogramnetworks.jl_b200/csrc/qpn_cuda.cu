@@ -10,6 +10,7 @@
 #include "qpn_kernels.cuh"
 #include "qpn_level.cuh"
 #include "qpn_big.cuh"
+#include "qpn_level_big.cuh"
 
 using namespace qpn;
 
@@ -247,8 +248,17 @@ static int stage_matrix(qpn_handle* h, Arena& a, const MatSlots& s, const qpn_ma
 // One plan: buffers sized for the worst case, filled by plan_build_kernel.
 // blob_out != NULL: a fresh allocation owned by the caller (resident levels); blob_out == NULL: the
 // handle's reusable buffer for one-off calls.
+static bool big_needed(qpn_handle* h, int n, size_t smem_small);
+static int build_plan_big(qpn_handle* h, const GaviDesc& g, int kind, int n_avi, const MatDesc& M, const double* l, const double* u,
+                          int slot, PlanDesc* out, unsigned char** blob_out);
+
 static int build_plan(qpn_handle* h, const GaviDesc& g, int kind, PlanDesc* out, unsigned char** blob_out) {
     const size_t n = (size_t)g.d1 + 2 * g.d2, dz = (size_t)g.d1 + g.d2;
+    if (big_needed(h, (int)n, gavi_smem_bytes(g.d1, g.d2, g.np))) {
+        MatDesc m0;
+        memset(&m0, 0, sizeof m0);
+        return build_plan_big(h, g, kind, 0, m0, nullptr, nullptr, kind, out, blob_out);
+    }
     const size_t ldrw = row_stride((int)n + 1);
     size_t need = 0;
     auto add = [&](size_t bytes) { size_t off = (need + 255) & ~(size_t)255; need = off + bytes; return off; };
@@ -335,7 +345,13 @@ static bool big_needed(qpn_handle* h, int n, size_t smem_small) {
 
 // Grid of persistent CTAs for a big kernel and the workspace for their slots.
 template <class K>
+static int big_grid_ex(qpn_handle* h, K kernel, int nmax, size_t slot_doubles, size_t smem, int batch, int* grid_out);
+template <class K>
 static int big_grid(qpn_handle* h, K kernel, int nmax, size_t smem, int batch, int* grid_out) {
+    return big_grid_ex(h, kernel, nmax, big_slot_doubles(nmax), smem, batch, grid_out);
+}
+template <class K>
+static int big_grid_ex(qpn_handle* h, K kernel, int nmax, size_t slot_doubles, size_t smem, int batch, int* grid_out) {
     if (smem > (size_t)h->max_smem_optin)
         return fail(h, "size n=%d needs %zu B of shared memory per CTA on the global-memory tableau path (limit %d)", nmax, smem,
                     h->max_smem_optin);
@@ -346,9 +362,9 @@ static int big_grid(qpn_handle* h, K kernel, int nmax, size_t smem, int batch, i
     if (h->big_ctas_per_sm > 0 && per_sm > h->big_ctas_per_sm) per_sm = h->big_ctas_per_sm;
     int grid = per_sm * h->sm_count;
     if (grid > batch) grid = batch;
-    const size_t need = (size_t)grid * big_slot_doubles(nmax);
+    const size_t need = (size_t)grid * slot_doubles;
     if (need > h->big_work_doubles) {
-        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaDeviceSynchronize());
         if (h->big_work) cudaFree(h->big_work);
         h->big_work = nullptr; h->big_work_doubles = 0;
         cudaError_t e = cudaMalloc((void**)&h->big_work, 8 * need);
@@ -406,14 +422,13 @@ static int build_plan_big(qpn_handle* h, const GaviDesc& g, int kind, int n_avi,
 static int launch_avi_big(qpn_handle* h, int n, int batch, const MatDesc& M, const double* q, const double* l, const double* u,
                           int lu_shared, const double* z0, int max_pivots, double* z, int32_t* st, int32_t* pv, int8_t* basis,
                           cudaStream_t s) {
-    if (s != h->stream) return fail(h, "the global-memory tableau path (n=%d) runs on the handle's stream only", n);
     const size_t smem = big_smem_bytes(n) + 8 * 3 * (size_t)n + (((size_t)n + 15) & ~(size_t)15);
     int grid = 0;
     if (big_grid(h, avi_solve_big_kernel, n, smem, batch, &grid)) return -1;
     PlanDesc P;
     memset(&P, 0, sizeof P);
     int has_plan = 0;
-    if (M.shared && lu_shared && batch >= 2) {
+    if (M.shared && lu_shared && batch >= 2 && s == h->stream) {      // plans are built (and synchronised) on the handle's stream
         GaviDesc g0;
         memset(&g0, 0, sizeof g0);
         if (build_plan_big(h, g0, 2, n, M, l, u, 0, &P, nullptr)) return -1;
@@ -429,13 +444,12 @@ static int launch_avi_big(qpn_handle* h, int n, int batch, const MatDesc& M, con
 static int launch_gavi_big(qpn_handle* h, const GaviDesc& g, int batch, const double* w, const double* z0, int presolve,
                            int max_pivots, double* z, double* zfull, int32_t* st, int32_t* pv, int8_t* basis, cudaStream_t s) {
     const int n = g.d1 + 2 * g.d2;
-    if (s != h->stream) return fail(h, "the global-memory tableau path (n=%d) runs on the handle's stream only", n);
     const size_t smem = big_smem_bytes(n) + gavi_extra_bytes(g.d1, g.d2, g.np);
     int grid = 0;
     if (big_grid(h, gavi_solve_big_kernel, n, smem, batch, &grid)) return -1;
     GaviPlans plans;
     memset(&plans, 0, sizeof plans);
-    if (batch >= 2) {
+    if (batch >= 2 && s == h->stream) {
         MatDesc m0;
         memset(&m0, 0, sizeof m0);
         if (build_plan_big(h, g, 0, 0, m0, nullptr, nullptr, 0, &plans.A, nullptr) ||

@@ -138,3 +138,81 @@ def test_big_avi_direct_n300_shared_matrix(engine):
     assert np.array_equal(s, so) and np.array_equal(p, po) and np.array_equal(b, bo) and np.array_equal(z, zo)
     bad, r = engine.check_avi(M, q, l, u, z)
     assert (bad == 0).all()
+
+
+def test_big_verify_solution(big_engine):
+    from tests.test_gpu_parity import _verify_cases
+    seen = set()
+    for name, view, X in _verify_cases():
+        sol, lam, how, act = big_engine.verify_solution(view, X)
+        for k in range(len(X)):
+            so, lo, ho, ao = cport.verify_solution(*view, X[k])
+            assert so == sol[k] and ho == how[k], (name, k, ho, how[k])
+            assert np.array_equal(ao, act[k]), (name, k)
+            assert np.array_equal(lo, lam[k]), (name, k, lo, lam[k])
+            seen.add(int(ho))
+    assert {0, 2, 4} <= seen, f"verify_solution branches exercised: {seen}"
+
+
+def test_big_level_examples(big_engine):
+    import qpn_b200
+    rng = np.random.default_rng(24)
+    net = examples.four_player_matrix_game()
+    g, dec, par = qpn_ref.level_gavi(net, net.depth[1], {})
+    proj = rng.normal(size=(4, 8))
+    views = [qpn_ref.node_view(net, p) for p in net.depth[1]]
+    la = qpn_b200.LevelArrays(8, views, g, dec, par, max_iters=150, proj=proj)
+    X = np.vstack([rng.uniform(-5, 5, (40, 8)), rng.uniform(-8, 8, (40, 8))])
+    ro = cport.Level(8, views, g, dec, par, 150, proj).solve(X)
+    ret = big_engine.level_equilibrium(la, X)                                # one-off, plans (batch >= 2 on the big path)
+    for k in ("x", "iters", "pivots", "lam"):
+        assert np.array_equal(ret[k], ro[k]), k
+    lv = qpn_b200.ResidentLevel(big_engine, la)                              # resident, plans built by the big kernel
+    ret = lv.solve(X)
+    for k in ("x", "iters", "pivots", "lam"):
+        assert np.array_equal(ret[k], ro[k]), k
+    lv.release()
+    net, X = problems.ra_inits(rng, 48)
+    g, dec, par = qpn_ref.level_gavi(net, net.depth[3], {})
+    views = [qpn_ref.node_view(net, p) for p in net.depth[3]]
+    la = qpn_b200.LevelArrays(net.n_vars, views, g, dec, par, max_iters=150, proj=None)
+    ro = cport.Level(net.n_vars, views, g, dec, par, 150, None).solve(X)
+    ret = big_engine.level_equilibrium(la, X)
+    assert ro["solved"].all()
+    for k in ("x", "iters", "pivots", "lam"):
+        assert np.array_equal(ret[k], ro[k]), k
+
+
+def single_node_net(rng, n, m):
+    """A one-node QPNet at the shape of SURVEY.md 8d config 5: min 0.5 x'Qx + q'x  s.t.  l <= Ax."""
+    g, xbar = monotone_gavi(rng, n, m)
+    net = examples.Net(n)
+    c = net.add_constraint(g["A"][:, :n], g["l2"], g["u2"])
+    net.add_qp(g["M"][:, :n], rng.normal(size=n), [c], list(range(n)))
+    net.add_edges([])
+    return net, xbar
+
+
+@pytest.mark.parametrize("n,m,B", [(40, 80, 12), (64, 128, 6)])
+def test_big_single_node_level_beyond_shared_memory(engine, n, m, B):
+    """verify_solution (QR of nd x k active rows in the global slot) + solve_qep (lifted 2n + 2m) + verify again, fused."""
+    import qpn_b200
+    rng = np.random.default_rng(31 + n)
+    net, xbar = single_node_net(rng, n, m)
+    g, dec, par = qpn_ref.level_gavi(net, net.depth[1], {})
+    views = [qpn_ref.node_view(net, 1)]
+    proj = rng.normal(size=(3, n))
+    X = xbar + rng.normal(size=(B, n)) * np.array([0.0 if k % 3 == 0 else 1.0 for k in range(B)])[:, None]
+    la = qpn_b200.LevelArrays(n, views, g, dec, par, max_iters=50, proj=proj)
+    ret = engine.level_equilibrium(la, X)
+    ro = cport.Level(n, views, g, dec, par, 50, proj).solve(X, threads=4)
+    assert ro["solved"].all() and (ro["iters"] == 2).all()
+    for k in ("x", "iters", "pivots", "lam"):
+        assert np.array_equal(ret[k], ro[k]), k
+    assert np.array_equal(ret["solved"], ro["solved"])
+    # the stand-alone entry point at the solution and at the start
+    sol, lam, how, act = engine.verify_solution(views[0], np.vstack([ret["x"], X]))
+    for k in range(2 * B):
+        so, lo, ho, ao = cport.verify_solution(*views[0], np.vstack([ret["x"], X])[k])
+        assert so == sol[k] and ho == how[k] and np.array_equal(ao, act[k]) and np.array_equal(lo, lam[k])
+    assert sol[:B].all() and not sol[B:].all()
