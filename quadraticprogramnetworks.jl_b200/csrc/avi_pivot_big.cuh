@@ -142,12 +142,20 @@ __device__ __noinline__ void big_pivot(BigTab& t, int rho, int c, bool compact) 
     double* prow = t.prow();
     const double* prho = t.Tg + (size_t)rho * ldr;
     const double p = dc[rho];
-    for (int j = threadIdx.x; j < nce; j += blockDim.x)
-        prow[j] = (j >= ncol) ? 0.0 : (j == c) ? (1.0 / p) : prho[j] / p;
+    int has_zero = 0;
+    for (int j = threadIdx.x; j < nce; j += blockDim.x) {
+        const double v = (j >= ncol) ? 0.0 : (j == c) ? (1.0 / p) : prho[j] / p;
+        prow[j] = v;
+        has_zero |= (j < ncol && v == 0.0);
+    }
     const int lv = t.rowvar()[rho];
     const bool dead = compact && lv >= n && lv < 2 * n && is_free_var(t, lv - n);
     const int last = ncol - 1;
-    QPN_SYNC();
+    // A mostly dense pivot row takes the branch-free pass (every load of a row in flight at once); a
+    // sparse one skips the column pairs it does not touch.  fma(-d, 0, T) = T, so both give the same values.
+    const int zero_threads = __syncthreads_count(has_zero);
+    const int col_threads = nce < (int)blockDim.x ? nce : (int)blockDim.x;
+    const bool dense = zero_threads * 8 < col_threads;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
     for (int i = w; i < n; i += nw) {
         double* row = t.Tg + (size_t)i * ldr;
@@ -157,16 +165,30 @@ __device__ __noinline__ void big_pivot(BigTab& t, int rho, int c, bool compact) 
                 *reinterpret_cast<double2*>(row + j) = *reinterpret_cast<const double2*>(prow + j);
         } else if (d != 0.0) {
             const double nd = -d;
-#pragma unroll 4
-            for (int j = 2 * lane; j < nce; j += 64) {
-                const double2 pj = *reinterpret_cast<const double2*>(prow + j);
-                if (pj.x == 0.0 && pj.y == 0.0) continue;
-                double2 tv = *reinterpret_cast<double2*>(row + j);
-                if (j == c) tv.x = 0.0;
-                if (j + 1 == c) tv.y = 0.0;
-                tv.x = fma(nd, pj.x, tv.x);
-                tv.y = fma(nd, pj.y, tv.y);
-                *reinterpret_cast<double2*>(row + j) = tv;
+            // four column pairs per lane in flight: predicated loads issued back to back, then the updates
+            for (int j0 = 2 * lane; j0 < nce; j0 += 256) {
+                double2 pj[4], tv[4];
+                bool act[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int j = j0 + 64 * q;
+                    act[q] = j < nce;
+                    pj[q] = act[q] ? *reinterpret_cast<const double2*>(prow + j) : make_double2(0.0, 0.0);
+                    act[q] = act[q] && (dense || pj[q].x != 0.0 || pj[q].y != 0.0);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (act[q]) tv[q] = *reinterpret_cast<const double2*>(row + j0 + 64 * q);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (!act[q]) continue;
+                    const int j = j0 + 64 * q;
+                    if (j == c) tv[q].x = 0.0;
+                    if (j + 1 == c) tv[q].y = 0.0;
+                    tv[q].x = fma(nd, pj[q].x, tv[q].x);
+                    tv[q].y = fma(nd, pj[q].y, tv[q].y);
+                    *reinterpret_cast<double2*>(row + j) = tv[q];
+                }
             }
         }
         if (dead && c != last) {
