@@ -44,6 +44,9 @@ NCU_DRAM_BYTES_PER_LAUNCH_B4096 = 439_296 + 1_024
 NCU_SMEM_WAVEFRONTS_PER_LAUNCH_B4096 = 5_711_598
 NCU_WARP_INSTRUCTIONS_PER_LAUNCH_B4096 = 40_007_087
 SM_COUNT = 148
+# dram__bytes_read.sum + dram__bytes_write.sum of one level_equilibrium_big_kernel launch on the n = 256, m = 512
+# monotone stress level at batch 148 (profiles/r1_big_level_kernel_ncu_full_summary.csv)
+NCU_DRAM_BYTES_BIG_LEVEL_B148 = 999_535_201_000 + 920_568_660_000
 
 
 def inits_for(rank, batch, step=0):
@@ -311,6 +314,44 @@ def main():
                                                "note": "per GPU, device-timed; level 3 of 3 only"}}
     except Exception as e:                                      # the headline must not depend on the extra
         extra = {"robust_avoid_bottom_level": {"error": str(e)[:200]}}
+
+    # ---- BASELINE.json configs[4]: the n = 256, m = 512 monotone stress QP as a one-node QPNet (lifted level AVI
+    # n = 1,536) on the global-memory tableau path: one wave of persistent CTAs (one instance per SM).
+    try:
+        ms = qpn_b200.setup("monotone_stress")
+        ms_solver = qpn_b200.BatchedSolver(ms, engine=eng)
+        ms_level = ms_solver.resident_level(1)
+        info = ms_level.info()
+        Bm = SM_COUNT
+        rng = np.random.default_rng([0xB200, rank, 9])
+        xm = torch.from_numpy(ms.default_initialization + rng.normal(size=(Bm, ms.n_vars))).to(dev)
+        xo = torch.empty_like(xm); so = torch.empty(Bm, dtype=torch.uint8, device=dev)
+        io = torch.empty(Bm, dtype=torch.int32, device=dev); po = torch.empty(Bm, dtype=torch.int32, device=dev)
+        run = lambda: ms_level.solve_dev(Bm, xm.data_ptr(), xo.data_ptr(), so.data_ptr(), io.data_ptr(), po.data_ptr(), None, stream.cuda_stream)
+        run(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        flush.zero_(); e0.record(stream); run(); e1.record(stream); torch.cuda.synchronize()
+        tm = e0.elapsed_time(e1) * 1e-3
+        pv = po.cpu().numpy().astype(np.float64)
+        # algorithmic HBM bytes: every pivot an instance runs itself reads and writes the live tableau once
+        # (16 B per entry, n rows x live columns); the plan's pivots were run once for the whole batch
+        own_pivots = float((pv - info["plan_pivots"]).sum())
+        alg = own_pivots * 16.0 * info["n"] * info["ncol0"]
+        peak_m, _ = measured_hbm_peak()
+        extra["monotone_stress_n256_m512"] = {
+            "value": Bm / tm, "unit": UNIT, "batch": Bm, "ms_per_launch": 1e3 * tm, "all_solved": bool(so.bool().all()),
+            "p50_pivots_per_solve": float(np.median(pv)), "lifted_n": info["n"], "live_columns": info["ncol0"], "plan_pivots": info["plan_pivots"],
+            "path": "global-memory tableau" if info["big"] else "shared-memory tableau",
+            "roofline": {"bound": "hbm", "achieved": NCU_DRAM_BYTES_BIG_LEVEL_B148 / tm / 1e9, "peak": peak_m, "unit": "GB/s",
+                         "frac": NCU_DRAM_BYTES_BIG_LEVEL_B148 / tm / 1e9 / peak_m, "traffic": NCU_DRAM_BYTES_BIG_LEVEL_B148,
+                         "dense_upper_bound_bytes": alg,
+                         "note": "achieved = DRAM bytes of this launch measured by ncu (same batch, same data) / event-timed duration; the dense "
+                                 "bound 16 B x rows x live columns x pivots overstates it: rows with a zero entering entry and column pairs "
+                                 "with zero pivot-row entries are skipped, and L2 (126 MB) serves half of the re-reads"},
+            "note": "per GPU, device-timed; verify -> solve_qep -> verify fused in level_equilibrium_big_kernel"}
+        ms_solver.close()
+    except Exception as e:
+        extra["monotone_stress_n256_m512"] = {"error": str(e)[:200]}
 
     if rank == 0:
         peak, peak_src = measured_hbm_peak()

@@ -63,6 +63,8 @@ int qpn_device(qpn_handle *h);
 /* Number of kernel launches this handle has issued (bench.py's gpu_launches). */
 int64_t qpn_launch_count(qpn_handle *h);
 int qpn_synchronize(qpn_handle *h);
+/* Of those, launches that took the global-memory tableau path (sizes beyond the shared-memory tableau). */
+int64_t qpn_big_launch_count(qpn_handle *h);
 
 /*
  * Replaces PATHSolver.solve_mcp at /root/reference/src/avi.jl:64-70 plus the check at
@@ -217,6 +219,11 @@ int qpn_level_equilibrium_resident_dev(qpn_handle *h, qpn_level_dev *lvd, int ba
  * tableau (lifted n > ~166; up to n = 1,536); "big_ctas_per_sm" caps that path's resident CTAs.
  */
 int qpn_set_option(qpn_handle *h, const char *name, int64_t value);
+
+/* Shape of a resident level's precomputed plans: out[0..7] = {lifted AVI size n, its live columns after the
+ * plan, pivots the plan ran once for the whole batch, presolve AVI size, its live columns, its plan pivots,
+ * 1 if the level runs on the global-memory tableau path, 0}. */
+int qpn_level_info(qpn_handle *h, qpn_level_dev *lvd, int32_t *out);
 
 /* Device buffers owned by the handle (for callers without their own allocator). */
 int qpn_malloc(qpn_handle *h, size_t bytes, void **dptr);

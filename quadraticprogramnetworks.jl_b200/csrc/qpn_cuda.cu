@@ -31,6 +31,7 @@ struct qpn_handle {
     // global-memory tableau slots of the big path (avi_pivot_big.cuh), grow-only
     double* big_work = nullptr;
     size_t big_work_doubles = 0;
+    int64_t big_launches = 0;   // launches that took the global-memory tableau path
     int force_big = 0;          // option "force_big": route every pivoting solve through the big path (tests)
     int big_ctas_per_sm = 0;    // option "big_ctas_per_sm": 0 = as many as fit
 };
@@ -127,6 +128,7 @@ extern "C" int qpn_destroy(qpn_handle* h) {
 extern "C" const char* qpn_last_error(qpn_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 extern "C" int qpn_device(qpn_handle* h) { return h ? h->device : -1; }
 extern "C" int64_t qpn_launch_count(qpn_handle* h) { return h ? h->launches : 0; }
+extern "C" int64_t qpn_big_launch_count(qpn_handle* h) { return h ? h->big_launches : 0; }
 extern "C" int qpn_synchronize(qpn_handle* h) {
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
@@ -372,6 +374,7 @@ static int big_grid_ex(qpn_handle* h, K kernel, int nmax, size_t slot_doubles, s
         h->big_work_doubles = need;
     }
     *grid_out = grid;
+    h->big_launches++;
     return 0;
 }
 

@@ -66,6 +66,8 @@ def load_library():
     lib.qpn_launch_count.restype = C.c_int64
     lib.qpn_launch_count.argtypes = [C.c_void_p]
     lib.qpn_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    lib.qpn_big_launch_count.restype = C.c_int64
+    lib.qpn_big_launch_count.argtypes = [C.c_void_p]
     for name in EXPORTS:
         getattr(lib, name)   # every declared symbol must resolve
     _lib = lib
@@ -80,7 +82,7 @@ EXPORTS = [
     "qpn_halfspace_in_batched", "qpn_verify_solution_batched",
     "qpn_level_equilibrium_batched", "qpn_level_equilibrium_batched_dev",
     "qpn_level_upload", "qpn_level_release", "qpn_level_equilibrium_resident", "qpn_level_equilibrium_resident_dev",
-    "qpn_malloc", "qpn_free", "qpn_memcpy_h2d", "qpn_memcpy_d2h", "qpn_set_option",
+    "qpn_malloc", "qpn_free", "qpn_memcpy_h2d", "qpn_memcpy_d2h", "qpn_set_option", "qpn_big_launch_count", "qpn_level_info",
 ]
 
 
@@ -150,6 +152,11 @@ class Engine:
     @property
     def launches(self):
         return int(self.lib.qpn_launch_count(self.h))
+
+    @property
+    def big_launches(self):
+        """Launches that took the global-memory tableau path."""
+        return int(self.lib.qpn_big_launch_count(self.h))
 
     def synchronize(self):
         self._ck(self.lib.qpn_synchronize(self.h))
@@ -275,6 +282,13 @@ class ResidentLevel:
         ptr = C.c_void_p()
         engine._ck(engine.lib.qpn_level_upload(engine.h, C.byref(level.struct), C.byref(ptr)))
         self.ptr = ptr
+
+    def info(self):
+        """qpn_level_info: plan shapes and which tableau path the level runs on."""
+        out = np.zeros(8, np.int32)
+        self.engine._ck(self.engine.lib.qpn_level_info(self.engine.h, self.ptr, _p(out, ip)))
+        return dict(n=int(out[0]), ncol0=int(out[1]), plan_pivots=int(out[2]), presolve_n=int(out[3]), presolve_ncol0=int(out[4]),
+                    presolve_plan_pivots=int(out[5]), big=bool(out[6]))
 
     def release(self):
         if getattr(self, "ptr", None):

@@ -10,7 +10,7 @@ import math
 
 import numpy as np
 
-from .model import INF, QPNet, dot, matvec, sumsq
+from .model import INF, Aff, QPNet, Quad, dot, matvec, sumsq
 
 _MASK = (1 << 64) - 1
 
@@ -137,7 +137,76 @@ def setup_robust_avoid_simple(num_obj=2, num_poly_faces=5, exploration_vertices=
     return net
 
 
+def _randn_matrix(g, r, c, scale=1.0):
+    return np.array([g.randn() for _ in range(r * c)]).reshape(r, c) * scale
+
+
+def setup_monotone_stress(n=256, m=512, seed=5, **kwargs):
+    """BASELINE.json configs[4] / SURVEY.md 8d config 5 (no file in the reference: a synthetic stress
+    shape): one node,  min 0.5 x'Qx + q'x  s.t.  l <= A x,  Q = G'G + 0.1 I (G iid N(0, 1/n)), rows of A
+    iid N(0,1) normalised, l = A xbar - U(0.1, 1) with xbar ~ N(0, I) feasible, q ~ N(0, I).
+    Its level AVI is the lifted KKT system of size 2(n + m) (solve_qep form, avi.jl:305-377)."""
+    g = SplitMix64(0x5712E55 + seed)
+    G = _randn_matrix(g, n, n, 1.0 / math.sqrt(n))
+    A = _randn_matrix(g, m, n)
+    A /= np.linalg.norm(A, axis=1, keepdims=True)
+    xbar = np.array([g.randn() for _ in range(n)])
+    l = A @ xbar - np.array([0.1 + 0.9 * g.rand() for _ in range(m)])
+    q = np.array([g.randn() for _ in range(n)])
+    net = QPNet(("x", n))
+    con_id = net.add_constraint([Aff(A[r]) for r in range(m)], l, [INF] * m)
+    net.add_qp(Quad(G.T @ G + 0.1 * np.eye(n), q), [con_id], net.var["x"])
+    net.add_edges([])
+    net.assign_constraint_groups()
+    net.set_options(**kwargs)
+    net.default_initialization = xbar
+    net.problem_data.update(xbar=xbar)
+    return net
+
+
+def setup_synthetic_chain(n=64, levels=3, n_params=8, seed=4, **kwargs):
+    """BASELINE.json configs[3] / SURVEY.md 8d config 4 (synthetic): a chain of `levels` nodes with n own
+    variables each (+ n_params parameters nobody owns); node k pays 0.5 x_k'(G'G + I) x_k + x_k'C_k [x_parents; p]
+    with coupling entries N(0, 0.1^2), subject to n/2 box rows and n/2 random halfspaces through a known
+    interior point; edges 1 -> 2 -> ... (node `levels` is the bottom level)."""
+    g = SplitMix64(0xC4A12 + seed)
+    blocks = [(f"x{k}", n) for k in range(1, levels + 1)] + [("p", n_params)]
+    net = QPNet(*blocks)
+    nv = net.n_vars
+    xint = np.array([g.randn() for _ in range(nv)]) * 0.5
+    ids = []
+    for k in range(1, levels + 1):
+        own = [net.index(v) for v in net.var[f"x{k}"]]
+        others = [i for i in range(nv) if i < own[0] or i >= levels * n]          # parents' variables and the parameters
+        G = _randn_matrix(g, n, n, 1.0 / math.sqrt(n))
+        Q = np.zeros((nv, nv))
+        Q[np.ix_(own, own)] = G.T @ G + np.eye(n)
+        if others:
+            C = _randn_matrix(g, n, len(others), 0.1)
+            Q[np.ix_(own, others)] = C
+            Q[np.ix_(others, own)] = C.T
+        nb = n // 2
+        box = [net.var[f"x{k}"][j] for j in range(nb)]
+        H = _randn_matrix(g, n - nb, n)
+        H /= np.linalg.norm(H, axis=1, keepdims=True)
+        half = []
+        for r in range(n - nb):
+            a = np.zeros(nv); a[own] = H[r]
+            half.append(Aff(a))
+        lo = [xint[own[j]] - 1.0 for j in range(nb)] + [float(H[r] @ xint[own]) - (0.1 + 0.9 * g.rand()) for r in range(n - nb)]
+        up = [xint[own[j]] + 1.0 for j in range(nb)] + [INF] * (n - nb)
+        con_id = net.add_constraint(box + half, lo, up)
+        ids.append(net.add_qp(Quad(Q, np.zeros(nv)), [con_id], net.var[f"x{k}"]))
+    net.add_edges([(ids[k], ids[k + 1]) for k in range(levels - 1)])
+    net.assign_constraint_groups()
+    net.set_options(**kwargs)
+    net.default_initialization = xint
+    return net
+
+
 _SETUPS = {
+    "monotone_stress": setup_monotone_stress,
+    "synthetic_chain": setup_synthetic_chain,
     "simple_bilevel": setup_simple_bilevel,
     "four_player_matrix_game": setup_four_player_matrix_game,
     "robust_avoid_simple": setup_robust_avoid_simple,

@@ -107,7 +107,9 @@ def test_big_monotone_gavi_beyond_shared_memory(engine, n, m, B, feasible):
     # infeasible starts: the presolve projection runs.  Feasible start: phase 0 of the plan leaves 64 free
     # variables without a pivot, which phase 1 must pick up exactly as the specification does.
     z0 = np.zeros((B, n + m)); z0[:, :n] = xbar + (0.0 if feasible else 1.0) * rng.normal(size=(B, n))
+    before = engine.big_launches
     ret = engine.gavi_solve(g, O, z0)
+    assert engine.big_launches > before, "this size must run on the global-memory tableau path"
     assert (ret["status"] == 1).all()
     for k in range(B):
         ro = cport.gavi_solve(g, z0[k], O[k])
@@ -204,7 +206,9 @@ def test_big_single_node_level_beyond_shared_memory(engine, n, m, B):
     proj = rng.normal(size=(3, n))
     X = xbar + rng.normal(size=(B, n)) * np.array([0.0 if k % 3 == 0 else 1.0 for k in range(B)])[:, None]
     la = qpn_b200.LevelArrays(n, views, g, dec, par, max_iters=50, proj=proj)
+    before = engine.big_launches
     ret = engine.level_equilibrium(la, X)
+    assert engine.big_launches > before
     ro = cport.Level(n, views, g, dec, par, 50, proj).solve(X, threads=4)
     assert ro["solved"].all() and (ro["iters"] == 2).all()
     for k in ("x", "iters", "pivots", "lam"):
@@ -216,3 +220,45 @@ def test_big_single_node_level_beyond_shared_memory(engine, n, m, B):
         so, lo, ho, ao = cport.verify_solution(*views[0], np.vstack([ret["x"], X])[k])
         assert so == sol[k] and ho == how[k] and np.array_equal(ao, act[k]) and np.array_equal(lo, lam[k])
     assert sol[:B].all() and not sol[B:].all()
+
+
+def test_monotone_stress_net_through_solve(engine):
+    """setup(:monotone_stress) -> solve(qpn, inits): BASELINE.json configs[4] at a size the oracle checks in seconds."""
+    import qpn_b200
+    rng = np.random.default_rng(41)
+    net = qpn_b200.setup("monotone_stress", n=48, m=96)
+    B = 16
+    X = net.default_initialization + rng.normal(size=(B, 48))
+    res = qpn_b200.solve(net, X)
+    g, dec, par = qpn_b200.assembly.level_gavi(net, [1])
+    views = [qpn_b200.assembly.node_view(net, 1)]
+    ro = cport.Level(48, views, g, dec, par, net.options.max_iters, qpn_b200.projection_vectors(net)).solve(X, threads=4)
+    assert ro["solved"].all()
+    for k in range(B):
+        assert res[k]["solved"] and res[k]["pivots"] == ro["pivots"][k] and res[k]["iters"] == ro["iters"][k]
+        assert np.array_equal(res[k]["x_opt"], ro["x"][k])
+    # all starts reach the unique minimiser of the strictly convex QP
+    assert np.ptp(np.array([r["x_opt"] for r in res]), axis=0).max() < 1e-8
+
+
+def test_synthetic_chain_bottom_level(engine):
+    """BASELINE.json configs[3]: the bottom level (node 3: 64 own variables, 136 parameters, lifted n = 256) as a
+    resident level on the global-memory tableau path."""
+    import qpn_b200
+    rng = np.random.default_rng(42)
+    net = qpn_b200.setup("synthetic_chain")
+    solver = qpn_b200.BatchedSolver(net, engine=engine)
+    lv = solver.resident_level(3)
+    info = lv.info()
+    assert info["big"] and info["n"] == 256 and info["plan_pivots"] > 0
+    B = 24
+    X = net.default_initialization + 0.7 * rng.normal(size=(B, net.n_vars))
+    ret = lv.solve(X)
+    pl = net.network_depth_map[3]
+    g, dec, par = qpn_b200.assembly.level_gavi(net, pl)
+    views = [qpn_b200.assembly.node_view(net, p) for p in pl]
+    ro = cport.Level(net.n_vars, views, g, dec, par, net.options.max_iters, solver.proj).solve(X, threads=4)
+    assert ro["solved"].all()
+    for k in ("x", "iters", "pivots", "lam"):
+        assert np.array_equal(ret[k], ro[k]), k
+    solver.close()
