@@ -262,3 +262,32 @@ def test_synthetic_chain_bottom_level(engine):
     for k in ("x", "iters", "pivots", "lam"):
         assert np.array_equal(ret[k], ro[k]), k
     solver.close()
+
+
+def test_big_edge_cases_and_failure_statuses(big_engine):
+    """The edge cases of test_gpu_parity.py (unbounded, infeasible, equality rows, degenerate vertices, fixed
+    variables, MAX_ITERS, empty batch) through the global-memory tableau path."""
+    from tests.test_gpu_parity import test_edge_cases_and_failure_statuses as run
+    before = big_engine.big_launches
+    run(big_engine)
+    assert big_engine.big_launches > before
+
+
+def test_big_avi_larger_random_monotone_per_instance(big_engine):
+    """Per-instance dense matrices (no plan): n = 40 and 96."""
+    rng = np.random.default_rng(34)
+    for n in (40, 96):
+        B = 12
+        Ms, qs, ls, us, z0s = [], [], [], [], []
+        for _ in range(B):
+            G = rng.normal(size=(n, n)) / np.sqrt(n); K = rng.normal(size=(n, n)) * 0.3
+            Ms.append(G.T @ G + 0.05 * np.eye(n) + (K - K.T))
+            qs.append(rng.normal(size=n))
+            ls.append(np.where(rng.uniform(size=n) < 0.3, -np.inf, -rng.uniform(0.1, 1.0, n)))
+            us.append(np.where(rng.uniform(size=n) < 0.3, np.inf, rng.uniform(0.1, 1.0, n)))
+            z0s.append(rng.normal(size=n))
+        Ms, qs, ls, us, z0s = map(np.array, (Ms, qs, ls, us, z0s))
+        zo, so, po, bo = cport.avi_solve_batched(Ms, qs, ls, us, z0s, threads=4)
+        z, s, p, b = big_engine.avi_solve(Ms, qs, ls, us, z0s)
+        assert (so == 1).all()
+        assert np.array_equal(s, so) and np.array_equal(p, po) and np.array_equal(b, bo) and np.array_equal(z, zo)
