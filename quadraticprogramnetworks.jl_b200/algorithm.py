@@ -91,6 +91,24 @@ def solve(qpn, x_init=None, device=0):
     return results[0] if single else results
 
 
+def flatten(qpn):
+    """programs.jl:117-124: the same players with every edge removed (a flat Nash game)."""
+    import copy
+    flat = copy.deepcopy(qpn)
+    flat.network_edges, flat.reachable_nodes, flat.network_depth_map = {}, {}, {}
+    flat._dec_cache = {}
+    flat.add_edges([])
+    return flat
+
+
+def get_flat_initialization(qpn, x0=None, device=0):
+    """programs.jl:126-131: the equilibrium of the flattened net, as a start for the real one."""
+    flat = flatten(qpn)
+    flat.options.gen_solution_map = False
+    ret = solve(flat, np.zeros(qpn.n_vars) if x0 is None else x0, device=device)
+    return ret["x_opt"]
+
+
 # ==============================================================================================
 # Multi-level networks: host recursion of solve_base! with the numeric steps on the device
 # ==============================================================================================

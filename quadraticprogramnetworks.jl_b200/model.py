@@ -142,7 +142,7 @@ class Poly:
         for i in range(m):
             s = normalize_slice(A[i], float(l[i]), float(u[i]), bool(rl[i]), bool(ru[i])) if normalize else \
                 (A[i].copy(), float(l[i]), float(u[i]), bool(rl[i]), bool(ru[i]))
-            key = (tuple(_r5(x) for x in s[0]), _r5(s[1]), _r5(s[2]), s[3], s[4])
+            key = ((np.round(s[0], 5) + 0.0).tobytes(), _r5(s[1]), _r5(s[2]), s[3], s[4])
             if key in seen:
                 continue
             seen.add(key)

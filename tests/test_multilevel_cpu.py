@@ -113,3 +113,37 @@ def test_cycling_exit_is_reported_not_raised():
     net = qpn_b200.setup(":robust_avoid_simple", seed=1)
     ret = qpn_b200.NetSolver(net, OracleEngine()).solve(net.default_initialization)
     assert (not ret["solved"]) and "Cycling" in ret["error"] and ret["x_opt"] is None
+
+
+def test_model_export_round_trip(tmp_path):
+    """QPNet -> flat-array JSON -> QPNet gives the same arrays, graph and options, and the
+    loaded net solves to the same answers (simple_bilevel KATs on the oracle stand-in)."""
+    import json
+    for name in ("simple_bilevel", "four_player_matrix_game", "robust_avoid_simple"):
+        net = qpn_b200.setup(name)
+        path = tmp_path / f"{name}.json"
+        qpn_b200.export_net(net, path)
+        doc = json.loads(path.read_text())                    # strict JSON: infinite bounds are null, never Infinity
+        assert doc["format"] == "qpn-b200/1" and "Infinity" not in path.read_text()
+        net2 = qpn_b200.load_net(path)
+        assert net2.n_vars == net.n_vars and net2.network_depth_map == net.network_depth_map and net2.network_edges == net.network_edges
+        assert net2.options == net.options and np.array_equal(net2.default_initialization, net.default_initialization)
+        for i, qp in net.qps.items():
+            q2 = net2.qps[i]
+            assert np.array_equal(qp.Q, q2.Q) and np.array_equal(qp.q, q2.q) and qp.var_indices == q2.var_indices
+            assert qp.constraint_indices == q2.constraint_indices
+        for i, P in net.constraints.items():
+            assert P == net2.constraints[i] and np.array_equal(P.A, net2.constraints[i].A) and np.array_equal(P.l, net2.constraints[i].l)
+    net2 = qpn_b200.load_net(tmp_path / "simple_bilevel.json")
+    ret = qpn_b200.NetSolver(net2, OracleEngine()).solve(np.array([1.0, 2.0, 0.0, 0.0]))
+    ref = qpn_b200.NetSolver(qpn_b200.setup("simple_bilevel"), OracleEngine()).solve(np.array([1.0, 2.0, 0.0, 0.0]))
+    assert ret["solved"] and np.array_equal(ret["x_opt"], ref["x_opt"])
+
+
+def test_flatten_removes_edges_only():
+    """programs.jl:117-124."""
+    net = qpn_b200.setup("robust_avoid_simple")
+    flat = qpn_b200.flatten(net)
+    assert flat.network_depth_map == {1: [1, 2, 3, 4, 5]} and all(not v for v in flat.network_edges.values())
+    assert net.num_levels() == 3                               # the original is untouched
+    assert flat.decision_inds(5) == sorted(net.qps[5].var_indices)
