@@ -184,6 +184,12 @@ class NetSolver:
             A = np.vstack([p.A for p in polys]); l = np.concatenate([p.l for p in polys]); u = np.concatenate([p.u for p in polys])
         else:
             A, l, u = np.zeros((0, net.n_vars)), np.zeros(0), np.zeros(0)
+        if net.options.check_convexity:                 # qp_processing.jl:69 (raises when the node is not convex)
+            from .qp import check_qp_convexity
+            try:
+                check_qp_convexity(self.engine, qp.Q, A, l, u, dec, pid)
+            except ValueError as err:
+                raise SolveError(str(err)) from None
         sol, lam, how, act = self.engine.verify_solution((qp.Q[dec, :], qp.q[dec], A, l, u, np.asarray(dec, np.int32)), x[None, :])
         return bool(sol[0]), lam[0]
 

@@ -263,6 +263,14 @@ def test_robust_avoid_three_levels_on_gpu(engine):
     check_robust_avoid_end_to_end(engine, seeds=(3,))
 
 
+def test_solve_qp_implicit_bounds_convexity_on_gpu(engine):
+    """Row A8 on the device engine: solve_qp, the batched bound LPs of implicit_bounds, check_qp_convexity."""
+    from tests.test_multilevel_cpu import check_qp_row_a8
+    before = engine.launches
+    check_qp_row_a8(engine)
+    assert engine.launches > before + 8
+
+
 def test_one_off_calls_with_plans_above_threshold(engine):
     """qpn_gavi_solve_batched / qpn_level_equilibrium_batched build one-off plans for batches >= 256."""
     import qpn_b200

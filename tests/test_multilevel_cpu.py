@@ -147,3 +147,41 @@ def test_flatten_removes_edges_only():
     assert flat.network_depth_map == {1: [1, 2, 3, 4, 5]} and all(not v for v in flat.network_edges.values())
     assert net.num_levels() == 3                               # the original is untouched
     assert flat.decision_inds(5) == sorted(net.qps[5].var_indices)
+
+
+def test_solve_qp_implicit_bounds_and_convexity():
+    """SURVEY.md row A8 (qp_processing.jl:1-55, sets.jl:660-713) with the oracle as numeric stand-in."""
+    check_qp_row_a8(OracleEngine())
+
+
+def check_qp_row_a8(eng):
+    from scipy.optimize import minimize
+    rng = np.random.default_rng(5)
+    for trial in range(6):
+        n, m = 4, 7
+        G = rng.normal(size=(n, n)); Q = G.T @ G + 0.1 * np.eye(n); q = rng.normal(size=n)
+        A = rng.normal(size=(m, n)); xb = rng.normal(size=n)
+        l = A @ xb - rng.uniform(0.1, 1, m); u = A @ xb + rng.uniform(0.1, 1, m)
+        x = qpn_b200.solve_qp(eng, Q, q, A, l, u)
+        assert (A @ x >= l - 1e-9).all() and (A @ x <= u + 1e-9).all()
+        cons = [{"type": "ineq", "fun": lambda y, A=A, l=l: A @ y - l}, {"type": "ineq", "fun": lambda y, A=A, u=u: u - A @ y}]
+        ref = minimize(lambda y: 0.5 * y @ Q @ y + q @ y, xb, constraints=cons, method="SLSQP", options=dict(ftol=1e-14, maxiter=500))
+        assert abs((0.5 * x @ Q @ x + q @ x) - ref.fun) < 1e-7
+    with pytest.raises(qpn_b200.qp.SolverFailure):
+        qpn_b200.solve_qp(eng, np.zeros((1, 1)), [-1.0], [[1.0]], [0.0], [np.inf])          # unbounded LP
+    # implicit equalities: x1 + x2 <= 1 and x1 + x2 >= 1 written as two one-sided rows; a true box row; a free direction
+    A = np.array([[1.0, 1.0, 0.0], [-1.0, -1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]])
+    l = np.array([-np.inf, -np.inf, -2.0, 0.5]); u = np.array([1.0, -1.0, 2.0, 0.5])
+    eq, vals = qpn_b200.implicit_bounds(eng, A, l, u)
+    assert eq.tolist() == [True, True, False, True] and np.allclose(vals[[0, 1, 3]], [1.0, -1.0, 0.5])
+    # Q indefinite, but positive on the null space of the implicit equality x1 + x2 = 1 (direction (1,-1,0)) and along x3
+    Q = np.array([[1.0, 3.0, 0.0], [3.0, 1.0, 0.0], [0.0, 0.0, 2.0]])                      # eigenvalues 4, -2, 2; (1,-1,0) -> -2
+    with pytest.raises(ValueError):
+        qpn_b200.check_qp_convexity(eng, Q, A, l, u, [0, 1, 2], 7)
+    Q2 = np.array([[1.0, -3.0, 0.0], [-3.0, 1.0, 0.0], [0.0, 0.0, 2.0]])                   # (1,1,0) -> -2 is excluded by the equality
+    assert qpn_b200.check_qp_convexity(eng, Q2, A, l, u, [0, 1, 2], 7) > 0
+    # the option reaches verify (qp_processing.jl:69): simple_bilevel is convex, the solve is unchanged
+    net = qpn_b200.setup("simple_bilevel", check_convexity=True)
+    ret = qpn_b200.NetSolver(net, eng).solve(np.array([1.0, 2.0, 0.0, 0.0]))
+    ref = qpn_b200.NetSolver(qpn_b200.setup("simple_bilevel"), eng).solve(np.array([1.0, 2.0, 0.0, 0.0]))
+    assert ret["solved"] and np.array_equal(ret["x_opt"], ref["x_opt"])
