@@ -363,3 +363,44 @@ def test_avi_larger_random_monotone(engine):
         assert (so == 1).all(), (n, np.bincount(so))
         assert np.array_equal(s, so) and np.array_equal(p, po) and np.array_equal(b, bo), n
         assert np.array_equal(z, zo), n
+
+
+def test_full_size_batches_by_properties(engine):
+    """BASELINE.json's full sizes, checked through size-independent properties (the oracle cannot run them in
+    seconds): 65,536 four_player equilibria and 65,536 robust_avoid bottom-level equilibria."""
+    import qpn_b200
+    rng = np.random.default_rng(77)
+    # four_player: strongly monotone game -> every start reaches the one equilibrium; solving again from it is a no-op
+    net = qpn_b200.setup("four_player_matrix_game")
+    solver = qpn_b200.BatchedSolver(net, engine=engine)
+    B = 65536
+    X = rng.uniform(-5, 5, (B, 8))
+    ret = solver.solve_batch(X)
+    assert ret["solved"].all() and (ret["iters"] == 2).all()
+    assert np.ptp(ret["x"], axis=0).max() < 1e-9
+    again = solver.solve_batch(ret["x"])
+    assert again["solved"].all() and (again["iters"] == 1).all() and np.array_equal(again["x"], ret["x"])      # idempotent
+    onet = examples.four_player_matrix_game()
+    for k in rng.integers(0, B, 8):
+        ro = qpn_ref.solve_level_bottom(onet, 1, X[k], solver.proj)
+        assert np.array_equal(ro["x"], ret["x"][k]) and ro["pivots"] == ret["pivots"][k]
+    solver.close()
+    # robust_avoid bottom level (BASELINE configs[2] shape: perturbed obstacles): solved everywhere, idempotent, and a
+    # sample agrees with the oracle bit for bit
+    ra = qpn_b200.setup("robust_avoid_simple")
+    rs = qpn_b200.BatchedSolver(ra, engine=engine)
+    lv = rs.resident_level(3)
+    Xr = np.tile(ra.default_initialization, (B, 1))
+    Xr[:, 0:6] += 0.5 * rng.normal(size=(B, 6)); Xr[:, 6:12] = rng.uniform(-1, 1, (B, 6))
+    r1 = lv.solve(Xr)
+    assert r1["solved"].all()
+    assert np.array_equal(r1["x"][:, :12], Xr[:, :12])                       # the bottom level moves only s and eps
+    r2 = lv.solve(r1["x"])
+    assert r2["solved"].all() and (r2["iters"] == 1).all() and np.array_equal(r2["x"], r1["x"])
+    pl = ra.network_depth_map[3]
+    g, dec, par = qpn_b200.assembly.level_gavi(ra, pl)
+    L = cport.Level(ra.n_vars, [qpn_b200.assembly.node_view(ra, p) for p in pl], g, dec, par, ra.options.max_iters, rs.proj)
+    idx = rng.integers(0, B, 64)
+    ro = L.solve(Xr[idx], threads=4)
+    assert np.array_equal(ro["x"], r1["x"][idx]) and np.array_equal(ro["pivots"], r1["pivots"][idx])
+    rs.close()
