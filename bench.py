@@ -217,22 +217,52 @@ def main():
     iters = block[o_it:o_pv].view(torch.int32)
     pivots = block[o_pv:o_sol].view(torch.int32)
     solved = block[o_sol:o_sol + B]
+    # Final gather of solutions / statuses / pivot counts.  Preferred form: the gathered buffer is
+    # symmetric memory, every rank's level kernel stores its outputs straight into ITS slot of rank 0's buffer
+    # (peer stores over NVLink from the kernel's own epilogue, no copy kernel), and a symmetric-memory barrier
+    # on the same stream publishes them.  Falls back to one NCCL all-gather per step when symmetric memory
+    # cannot be set up (or with QPN_BENCH_GATHER=nccl).
+    gather_mode, hdl, out_base = "none", None, block.data_ptr()
     if world > 1:
-        g_block = torch.empty(world * nbytes, dtype=torch.uint8, device=dev)
+        gather_mode = "nccl all_gather_into_tensor"
+        if os.environ.get("QPN_BENCH_GATHER", "p2p") == "p2p":
+            try:
+                import torch.distributed._symmetric_memory as symm
+                g_block = symm.empty(world * nbytes, dtype=torch.uint8, device=dev)
+                hdl = symm.rendezvous(g_block, dist.group.WORLD)
+                out_base = int(hdl.buffer_ptrs[0]) + rank * nbytes
+                gather_mode = "kernel stores into rank 0's symmetric buffer over NVLink + symmetric-memory barrier"
+            except Exception as e:                          # noqa: BLE001
+                hdl = None
+                if rank == 0:
+                    print(f"[bench] symmetric memory unavailable ({str(e)[:120]}); using NCCL all-gather", file=sys.stderr)
+        if hdl is None:
+            g_block = torch.empty(world * nbytes, dtype=torch.uint8, device=dev)
+            out_base = block.data_ptr()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
     def step_dev(k):
-        level.solve_dev(B, x_in[k % len(x_in)].data_ptr(), x_out.data_ptr(), solved.data_ptr(), iters.data_ptr(),
-                        pivots.data_ptr(), None, stream.cuda_stream)
+        level.solve_dev(B, x_in[k % len(x_in)].data_ptr(), out_base, out_base + o_sol, out_base + o_it,
+                        out_base + o_pv, None, stream.cuda_stream)
 
     def gather():
-        if world > 1:
+        if hdl is not None:
+            hdl.barrier(channel=0)
+        elif world > 1:
             dist.all_gather_into_tensor(g_block, block)
 
     for k in range(W):
         step_dev(k); gather()
     torch.cuda.synchronize()
-    assert bool(solved.bool().all()), "warm-up: not every instance reached an equilibrium"
+    if hdl is not None:
+        # rank 0 holds every rank's block: check them all there
+        if rank == 0:
+            gb = g_block.view(world, nbytes)
+            assert bool(gb[:, o_sol:o_sol + B].bool().all()), "warm-up: not every instance (of every rank) reached an equilibrium"
+        solved = g_block[o_sol:o_sol + B] if rank == 0 else None
+        pivots = g_block[o_pv:o_sol].view(torch.int32) if rank == 0 else None
+    else:
+        assert bool(solved.bool().all()), "warm-up: not every instance reached an equilibrium"
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if world > 1:
@@ -253,8 +283,15 @@ def main():
     launches = eng.launches - launches0
     t_kernel = sum(a.elapsed_time(b) for a, b, _ in ev) * 1e-3
     t_step = sum(a.elapsed_time(c) for a, _, c in ev) * 1e-3
-    piv_host = pivots.cpu().numpy()
-    all_solved = bool(solved.bool().all())
+    if hdl is not None and rank == 0:
+        gb = g_block.view(world, nbytes)
+        all_solved = bool(gb[:, o_sol:o_sol + B].bool().all())            # every rank's statuses, gathered on rank 0
+        piv_host = gb[:, o_pv:o_sol].contiguous().view(torch.int32).cpu().numpy().ravel()
+    elif hdl is not None:
+        all_solved, piv_host = True, np.zeros(1)
+    else:
+        piv_host = pivots.cpu().numpy()
+        all_solved = bool(solved.bool().all())
 
     # ---- end-to-end arm: pinned host buffers through the C ABI ---------------------------------
     hx = [torch.from_numpy(inits_for(rank, B, 100 + k)).pin_memory() for k in range(min(K, 8))]
@@ -363,7 +400,7 @@ def main():
             "ms_per_step": 1e3 * t_step / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "n_vars": nv, "avi_size": 32, "l2": "flushed between steps (256 MB write)",
-                       "timing": "CUDA events on the launching stream, max over ranks", "all_solved": all_solved,
+                       "timing": "CUDA events on the launching stream, max over ranks", "all_solved": all_solved, "gather": gather_mode,
                        "p50_pivots_per_solve": float(np.median(piv_host)), "kernel_ms_per_step": 1e3 * t_kernel / K},
             "e2e": {"value": world * B * K / t_e2e, "unit": UNIT, "h2d_bytes_per_step": B * nv * 8, "d2h_bytes_per_step": B * (nv * 8 + 1 + 4 + 4),
                     "timing": "host clock around the synchronous C-ABI call (qpn_level_equilibrium_resident), pinned buffers"},
