@@ -746,7 +746,7 @@ __global__ void __launch_bounds__(MAXT, 896 / MAXT) level_equilibrium_kernel(con
                                          double* __restrict__ x_out, uint8_t* __restrict__ solved_out,
                                          int32_t* __restrict__ iters_out, int32_t* __restrict__ pivots_out,
                                          double* __restrict__ lam_out, double* __restrict__ hist,
-                                         int32_t* __restrict__ hist_count, int hist_cap, int presolve) {
+                                         int32_t* __restrict__ hist_count, int hist_cap, int presolve, int hist_fresh) {
     const int b = blockIdx.x, i = threadIdx.x, nv = lv.nv;
     GaviSmem gs;
     const int n_level = lv.g.d1 + 2 * lv.g.d2;
@@ -767,7 +767,7 @@ __global__ void __launch_bounds__(MAXT, 896 / MAXT) level_equilibrium_kernel(con
     // The history outlives one call when the caller keeps hist / hist_count (the reference's
     // iterate_cache persists across the calls of one top-level solve, algorithm.jl:20-28).
     double* myhist = hist ? hist + (size_t)b * hist_cap * lv.nproj : nullptr;
-    int nhist = (hist && hist_count) ? hist_count[b] : 0;
+    int nhist = (hist && hist_count && !hist_fresh) ? hist_count[b] : 0;      // hist_fresh: this call starts a new top-level solve
     for (int it = 1; it <= lv.max_iters; ++it) {
         iters = it;
         // cycle check (algorithm.jl:14-30): random projections of the iterate against the history

@@ -271,7 +271,8 @@ __global__ void __launch_bounds__(QPN_BIG_THREADS, 1)
 level_equilibrium_big_kernel(const __grid_constant__ LevelDesc lv, int batch, const double* __restrict__ x_init,
                              double* __restrict__ x_out, uint8_t* __restrict__ solved_out, int32_t* __restrict__ iters_out,
                              int32_t* __restrict__ pivots_out, double* __restrict__ lam_out, double* __restrict__ hist,
-                             int32_t* __restrict__ hist_count, int hist_cap, int presolve, double* __restrict__ work, size_t slot_doubles) {
+                             int32_t* __restrict__ hist_count, int hist_cap, int presolve, int hist_fresh, double* __restrict__ work,
+                             size_t slot_doubles) {
     const int i = threadIdx.x, nv = lv.nv;
     const int n_level = lv.g.d1 + 2 * lv.g.d2;
     const int nmax = n_level > lv.max_m ? n_level : lv.max_m;
@@ -298,7 +299,7 @@ level_equilibrium_big_kernel(const __grid_constant__ LevelDesc lv, int batch, co
         QPN_SYNC();
         int solved = 0, piv = 0, iters = 0;
         double* myhist = hist ? hist + (size_t)b * hist_cap * lv.nproj : nullptr;
-        int nhist = (hist && hist_count) ? hist_count[b] : 0;
+        int nhist = (hist && hist_count && !hist_fresh) ? hist_count[b] : 0;
         for (int it = 1; it <= lv.max_iters; ++it) {
             iters = it;
             if (lv.nproj > 0 && myhist) {
