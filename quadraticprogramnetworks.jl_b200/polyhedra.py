@@ -36,6 +36,25 @@ def contains(P, x, tol=1e-6, closed=False):
     return True
 
 
+def contains_prefix(P, x, engine, tol=1e-6):
+    """sets.jl:826-847: `x in poly` when x gives only the first len(x) coordinates -- is there a completion
+    y with  l - A_p x <= A_y y <= u - A_p x ?  The reference asks OSQP for the least-norm y (status 3 =
+    primal infeasible -> false); here the same QP  min 0.5 |y|^2  is solved on the device engine."""
+    x = np.asarray(x, dtype=float)
+    n, d = len(x), P.dim
+    if n == d:
+        return contains(P, x, tol=tol)
+    if len(P) == 0:
+        return True
+    from .qp import SolverFailure, solve_qp
+    shift = P.A[:, :n] @ x
+    try:
+        y = solve_qp(engine, np.eye(d - n), np.zeros(d - n), P.A[:, n:], P.l - shift - tol, P.u - shift + tol)
+    except SolverFailure:
+        return False
+    return bool(np.all(P.A[:, n:] @ y >= P.l - shift - 2 * tol) and np.all(P.A[:, n:] @ y <= P.u - shift + 2 * tol))
+
+
 def intersect(*polys):
     """poly_intersect (sets.jl:936-968): the conjunction of all slices."""
     polys = [p for p in polys if p is not None]

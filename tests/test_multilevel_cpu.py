@@ -185,3 +185,16 @@ def check_qp_row_a8(eng):
     ret = qpn_b200.NetSolver(net, eng).solve(np.array([1.0, 2.0, 0.0, 0.0]))
     ref = qpn_b200.NetSolver(qpn_b200.setup("simple_bilevel"), eng).solve(np.array([1.0, 2.0, 0.0, 0.0]))
     assert ret["solved"] and np.array_equal(ret["x_opt"], ref["x_opt"])
+
+
+def test_projected_membership():
+    """sets.jl:826-847: x in poly with only a prefix of the coordinates given (a feasibility QP over the rest)."""
+    eng = OracleEngine()
+    # {(x, y): 0 <= y <= 1, x - y = 0.5}: x is in the projection iff 0.5 <= x <= 1.5
+    P = Poly(np.array([[0.0, 1.0], [1.0, -1.0]]), [0.0, 0.5], [1.0, 0.5])
+    for x, want in ((0.4, False), (0.5, True), (1.0, True), (1.5, True), (1.6, False)):
+        assert ph.contains_prefix(P, [x], eng) == want, x
+    assert ph.contains_prefix(P, [1.0, 0.5], eng) and not ph.contains_prefix(P, [1.0, 0.6], eng)      # full dimension: plain membership
+    # a lifted solution piece of simple_bilevel's lower node: (x, y, lam) with y = max(x, 0)
+    Q = Poly(np.array([[1.0, -1.0, 0.0], [0.0, 1.0, 0.0], [0.0, 0.0, 1.0]]), [0.0, 0.0, 0.0], [0.0, INF, 0.0])   # x = y >= 0, lam = 0
+    assert ph.contains_prefix(Q, [2.0], eng) and not ph.contains_prefix(Q, [-1.0], eng)
