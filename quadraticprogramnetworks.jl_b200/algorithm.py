@@ -175,6 +175,7 @@ class NetSolver:
         self.lp = ph.LPSolver(engine)
         self.proj = projection_vectors(net)
         self.iterate_cache = {}
+        self.piece_cache = {}          # (node, constraint polys, K) -> local piece / its projection; lives across instances
 
     # ---- qp_processing.jl:57-149 on the device -----------------------------------------------
     def verify(self, pid, polys, dec, x):
@@ -206,7 +207,7 @@ class NetSolver:
 
     def solution_pieces(self, pid, polys, dec, x, lam):
         gen = solgraph.process_solution_graph(self.net, pid, polys, dec, x, lam, self.engine, self.lp,
-                                              exploration_vertices=self.net.options.exploration_vertices)
+                                              exploration_vertices=self.net.options.exploration_vertices, cache=self.piece_cache)
         return gen.collect()
 
     # ---- qp_processing.jl:151-241 ------------------------------------------------------------------

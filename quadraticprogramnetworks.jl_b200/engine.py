@@ -104,7 +104,7 @@ def _p(a, t=dp):
 # Buffers that come back call after call (pinned batches, preallocated outputs) are looked up by identity instead;
 # the cache keeps the array alive, so an id cannot be recycled while its entry exists.
 _PTR_CACHE = {}
-_PTR_CACHE_MAX = 64
+_PTR_CACHE_MAX = 16
 
 
 def _vp(a):

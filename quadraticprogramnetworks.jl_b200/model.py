@@ -134,25 +134,47 @@ class Poly:
 
     def __init__(self, A, l, u, rl=None, ru=None, normalize=True):
         A = np.atleast_2d(np.asarray(A, dtype=float))
+        l, u = np.asarray(l, dtype=float).reshape(-1), np.asarray(u, dtype=float).reshape(-1)
         m = len(l)
         d = A.shape[1]
-        rl = np.zeros(m, bool) if rl is None else np.asarray(rl, bool)
-        ru = np.zeros(m, bool) if ru is None else np.asarray(ru, bool)
-        rows, seen = [], set()
+        A = A.reshape(m, d)
+        rl = np.zeros(m, bool) if rl is None else np.asarray(rl, bool).reshape(-1)
+        ru = np.zeros(m, bool) if ru is None else np.asarray(ru, bool).reshape(-1)
+        if normalize and m:
+            # every row through normalize_slice (sets.jl:76-89), all rows at once
+            A = A.copy()
+            A[np.abs(A) <= 1e-8] = 0.0
+            zero = np.sqrt(np.einsum("ij,ij->i", A, A)) <= 1e-8
+            A[zero] = 0.0
+            first = (A != 0.0).argmax(axis=1)
+            lead = A[np.arange(m), first]
+            n = np.abs(lead)
+            n[zero] = 1.0
+            pos = (lead >= 0) | zero
+            A = A / n[:, None]
+            A[~pos] = -A[~pos]
+            l, u = np.where(pos, l / n, -u / n), np.where(pos, u / n, -l / n)
+            rl, ru = np.where(pos, rl, ru), np.where(pos, ru, rl)
+        elif m:
+            A = A.copy()
+        # equal slices (5-digit rounding, sets.jl:104-112) are stored once, in first-seen order
+        RA = np.round(A, 5) + 0.0
+        with np.errstate(invalid="ignore"):
+            rL = np.where(np.isinf(l), l, np.round(l, 5)) + 0.0
+            rU = np.where(np.isinf(u), u, np.round(u, 5)) + 0.0
+        keys, keep, seen = [], [], set()
         for i in range(m):
-            s = normalize_slice(A[i], float(l[i]), float(u[i]), bool(rl[i]), bool(ru[i])) if normalize else \
-                (A[i].copy(), float(l[i]), float(u[i]), bool(rl[i]), bool(ru[i]))
-            key = ((np.round(s[0], 5) + 0.0).tobytes(), _r5(s[1]), _r5(s[2]), s[3], s[4])
+            key = (RA[i].tobytes(), float(rL[i]), float(rU[i]), bool(rl[i]), bool(ru[i]))
             if key in seen:
                 continue
             seen.add(key)
-            rows.append((s, key))
-        self.A = np.array([r[0][0] for r in rows]).reshape(len(rows), d)
-        self.l = np.array([r[0][1] for r in rows], dtype=float)
-        self.u = np.array([r[0][2] for r in rows], dtype=float)
-        self.rl = np.array([r[0][3] for r in rows], dtype=bool)
-        self.ru = np.array([r[0][4] for r in rows], dtype=bool)
-        self._keys = frozenset(r[1] for r in rows)
+            keys.append(key); keep.append(i)
+        self.A = A[keep].reshape(len(keep), d)
+        self.l = l[keep].astype(float)
+        self.u = u[keep].astype(float)
+        self.rl = rl[keep].astype(bool)
+        self.ru = ru[keep].astype(bool)
+        self._keys = frozenset(keys)
 
     def __len__(self):
         return len(self.l)

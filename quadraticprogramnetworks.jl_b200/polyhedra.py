@@ -79,27 +79,30 @@ def complement(P):
 def simplify(P, tol=1e-6):
     """sets.jl:255-305: merge slices with the same normal, keeping the tighter bounds."""
     keep = []      # [a, l, u, rl, ru]
+    KA = np.zeros((len(P), P.dim))                 # normals of the kept slices, for one vectorised distance per row
+    nonzero = np.sqrt(np.einsum("ij,ij->i", P.A, P.A)) > tol if len(P) else np.zeros(0, bool)
     for i in range(len(P)):
         a, l, u, rl, ru = P.A[i], P.l[i], P.u[i], bool(P.rl[i]), bool(P.ru[i])
-        for k in keep:
-            if np.linalg.norm(k[0] - a) <= tol:           # isapprox(k, s.a; atol=tol)
-                if k[1] > l + tol:
-                    nl, nrl = k[1], k[3]
-                elif l > k[1] + tol:
-                    nl, nrl = l, rl
-                else:
-                    nl, nrl = 0.5 * (k[1] + l) if not (math.isinf(k[1]) and math.isinf(l)) else l, (True if k[3] else rl)
-                if k[2] < u - tol:
-                    nu, nru = k[2], k[4]
-                elif u < k[2] - tol:
-                    nu, nru = u, ru
-                else:
-                    nu, nru = 0.5 * (k[2] + u) if not (math.isinf(k[2]) and math.isinf(u)) else u, (True if k[4] else ru)
-                k[1], k[2], k[3], k[4] = nl, nu, nrl, nru
-                break
-        else:
-            if np.linalg.norm(a) > tol:
-                keep.append([a.copy(), l, u, rl, ru])
+        nk = len(keep)
+        hit = np.flatnonzero(np.sqrt(np.einsum("ij,ij->i", KA[:nk] - a, KA[:nk] - a)) <= tol) if nk else ()
+        if len(hit):                                      # isapprox(k, s.a; atol=tol): the first kept slice with this normal
+            k = keep[int(hit[0])]
+            if k[1] > l + tol:
+                nl, nrl = k[1], k[3]
+            elif l > k[1] + tol:
+                nl, nrl = l, rl
+            else:
+                nl, nrl = 0.5 * (k[1] + l) if not (math.isinf(k[1]) and math.isinf(l)) else l, (True if k[3] else rl)
+            if k[2] < u - tol:
+                nu, nru = k[2], k[4]
+            elif u < k[2] - tol:
+                nu, nru = u, ru
+            else:
+                nu, nru = 0.5 * (k[2] + u) if not (math.isinf(k[2]) and math.isinf(u)) else u, (True if k[4] else ru)
+            k[1], k[2], k[3], k[4] = nl, nu, nrl, nru
+        elif nonzero[i]:
+            KA[nk] = a
+            keep.append([a.copy(), l, u, rl, ru])
     d = P.dim
     if not keep:
         return Poly(np.zeros((0, d)), [], [])
@@ -128,6 +131,10 @@ class LPSolver:
     def __init__(self, engine):
         self.engine = engine
         self.calls = 0
+        # Geometric predicates memoised by polyhedron (Poly hashes / compares by its 5-digit slice keys, the
+        # reference's own notion of equal sets, sets.jl:104-112,141-146): across the instances of a batch the
+        # same pieces come back again and again.
+        self.memo = {}
 
     def solve(self, c, A, l, u, x0=None, rho=0.0):
         c = np.asarray(c, dtype=float)
@@ -146,6 +153,16 @@ class LPSolver:
 
 def exemplar(P, lp, tol=1e-2):
     """sets.jl:591-642.  Returns (empty, example)."""
+    memo = getattr(lp, "memo", None)
+    if memo is None:
+        return _exemplar(P, lp, tol)
+    key = ("exemplar", P, tol)
+    if key not in memo:
+        memo[key] = _exemplar(P, lp, tol)
+    return memo[key]
+
+
+def _exemplar(P, lp, tol):
     n = len(P)
     if n == 0:
         return False, None
@@ -190,6 +207,16 @@ def isempty(P, lp, tol=1e-4, x=None):
 
 def issubset(P1, P2, lp, tol=1e-6):
     """sets.jl:377-407: for every finite bound of P2 minimise the bound's direction over P1."""
+    memo = getattr(lp, "memo", None)
+    if memo is None:
+        return _issubset(P1, P2, lp, tol)
+    key = ("issubset", P1, P2, tol)
+    if key not in memo:
+        memo[key] = _issubset(P1, P2, lp, tol)
+    return memo[key]
+
+
+def _issubset(P1, P2, lp, tol):
     for i in range(len(P2)):
         for bound, dirn in ((P2.l[i], 1.0), (P2.u[i], -1.0)):
             if math.isinf(bound):

@@ -109,8 +109,11 @@ def vertices_of_slice(piece, z, w, nv, lp, max_dim=6):
 class LocalSolutions:
     """LocalGAVISolutions (avi_solutions.jl:92-129) + collect (:277-321)."""
 
-    def __init__(self, engine, lp, g, z, w, dec, par, n_vars, max_vertices=0):
+    def __init__(self, engine, lp, g, z, w, dec, par, n_vars, max_vertices=0, cache=None, cache_key=None):
         self.engine, self.lp, self.g = engine, lp, g
+        # pieces depend on (node, its constraint polys incl. the chosen child pieces, K) only -- not on the point:
+        # memoised across the instances of a batch (SURVEY.md 8f-1)
+        self.cache, self.cache_key = cache, cache_key
         self.z, self.w, self.dec, self.par, self.n_vars = np.asarray(z, float), np.asarray(w, float), list(dec), list(par), n_vars
         self.max_vertices = max_vertices
         self.unexplored_Ks = self._recipes(self.z, self.w)
@@ -130,14 +133,21 @@ class LocalSolutions:
 
     def expand(self, K):
         """avi_solutions.jl:241-261."""
-        piece = local_piece(self.g, K)
+        ent = None if self.cache is None else self.cache.setdefault((self.cache_key, K), {})
+        if ent is None:
+            ent = {}
+        if "piece" not in ent:
+            ent["piece"] = local_piece(self.g, K)
+        piece = ent["piece"]
         zw = np.concatenate([self.z, self.w])
         if len(piece) and ph.isempty(piece, self.lp, tol=1e-4, x=zw):
             return None, []
         verts = []
         if self.max_vertices > 0 and (len(piece) == 0 or ph.contains(piece, zw)):
             verts = vertices_of_slice(piece, self.z, self.w, len(self.dec), self.lp)
-        return project_and_permute(piece, self.dec, self.par, self.n_vars, self.lp), verts
+        if "proj" not in ent:
+            ent["proj"] = project_and_permute(piece, self.dec, self.par, self.n_vars, self.lp)
+        return ent["proj"], verts
 
     def collect(self):
         while self.unexplored_Ks:
@@ -163,8 +173,14 @@ class LocalSolutions:
         return list(self.polys)
 
 
-def process_solution_graph(net, pid, polys, dec, x, lam, engine, lp, exploration_vertices=0):
+def process_solution_graph(net, pid, polys, dec, x, lam, engine, lp, exploration_vertices=0, cache=None):
     """avi.jl:447-477."""
-    g, par = single_node_gavi(net, pid, polys, dec)
+    key = (pid, tuple(polys))
+    if cache is not None and ("gavi", key) in cache:
+        g, par = cache[("gavi", key)]
+    else:
+        g, par = single_node_gavi(net, pid, polys, dec)
+        if cache is not None:
+            cache[("gavi", key)] = (g, par)
     z = np.concatenate([x[dec], lam])
-    return LocalSolutions(engine, lp, g, z, x[par], dec, par, net.n_vars, max_vertices=exploration_vertices)
+    return LocalSolutions(engine, lp, g, z, x[par], dec, par, net.n_vars, max_vertices=exploration_vertices, cache=cache, cache_key=key)
