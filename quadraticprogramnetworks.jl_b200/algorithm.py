@@ -75,9 +75,14 @@ def solve(qpn, x_init=None, device=0):
     single = x.ndim == 1
     solver = _solver_for(qpn, device)
     if qpn.num_levels() != 1 or qpn.options.gen_solution_map:
-        # networks with children (or with the solution map requested): host recursion per instance
-        ns = NetSolver(qpn, solver.engine)
-        outs = [ns.solve(xi) for xi in np.atleast_2d(x)]
+        # networks with children (or with the solution map requested): the per-instance recursion of solve_base!,
+        # every numeric step on the device.  A batch runs one recursion per instance against a BatchingEngine,
+        # which regroups the instances' pending device calls into one launch per (kind, shared data) (batching.py).
+        X = np.atleast_2d(x)
+        if len(X) == 1:
+            outs = [NetSolver(qpn, solver.engine).solve(X[0])]
+        else:
+            outs = solve_multilevel_batch(qpn, X, solver.engine)
         return outs[0] if single else outs
     ret = solver.solve_batch(np.atleast_2d(x))
     results = []
@@ -89,6 +94,22 @@ def solve(qpn, x_init=None, device=0):
             results.append(dict(solved=False, x_fail=ret["x"][b].copy(), x_opt=None,
                                 iters=int(ret["iters"][b]), pivots=int(ret["pivots"][b])))
     return results[0] if single else results
+
+
+def solve_multilevel_batch(qpn, X, engine, chunk=256, stats=None):
+    """solve(qpn, inits) for a network with children: one NetSolver per instance (its own iterate cache and cycle
+    detection), all of them sharing the memoised pieces and driving the device through one BatchingEngine."""
+    from .batching import BatchingEngine
+    pieces, memo, outs = {}, {}, []
+    for lo in range(0, len(X), chunk):
+        be = BatchingEngine(engine)
+        jobs = [(lambda xi=xi: NetSolver(qpn, be, piece_cache=pieces, lp_memo=memo).solve(xi)) for xi in X[lo:lo + chunk]]
+        outs += be.run(jobs)
+        if stats is not None:
+            stats["rounds"] = stats.get("rounds", 0) + be.rounds
+            stats["device_calls"] = stats.get("device_calls", 0) + be.device_calls
+            stats["requests"] = stats.get("requests", 0) + be.requests
+    return outs
 
 
 def flatten(qpn):
@@ -170,12 +191,15 @@ class NetSolver:
     """solve(qpn, x_init) for any QPNet: algorithm.jl:1-127 + qp_processing.jl:151-291 on the host,
     with verify_solution / solve_qep / comp_indices / every LP on the device engine."""
 
-    def __init__(self, net, engine):
+    def __init__(self, net, engine, piece_cache=None, lp_memo=None):
         self.net, self.engine = net, engine
         self.lp = ph.LPSolver(engine)
+        if lp_memo is not None:
+            self.lp.memo = lp_memo     # shared by the instance threads of a batch (batching.py)
         self.proj = projection_vectors(net)
         self.iterate_cache = {}
-        self.piece_cache = {}          # (node, constraint polys, K) -> local piece / its projection; lives across instances
+        # (node, constraint polys, K) -> local piece / its projection; lives across instances
+        self.piece_cache = {} if piece_cache is None else piece_cache
 
     # ---- qp_processing.jl:57-149 on the device -----------------------------------------------
     def verify(self, pid, polys, dec, x):

@@ -135,6 +135,8 @@ class LPSolver:
         # reference's own notion of equal sets, sets.jl:104-112,141-146): across the instances of a batch the
         # same pieces come back again and again.
         self.memo = {}
+        from .batching import plain_once
+        self.once = getattr(engine, "once", plain_once)      # a BatchingEngine memoises across its instance threads
 
     def solve(self, c, A, l, u, x0=None, rho=0.0):
         c = np.asarray(c, dtype=float)
@@ -156,10 +158,7 @@ def exemplar(P, lp, tol=1e-2):
     memo = getattr(lp, "memo", None)
     if memo is None:
         return _exemplar(P, lp, tol)
-    key = ("exemplar", P, tol)
-    if key not in memo:
-        memo[key] = _exemplar(P, lp, tol)
-    return memo[key]
+    return lp.once(memo, ("exemplar", P, tol), lambda: _exemplar(P, lp, tol))
 
 
 def _exemplar(P, lp, tol):
@@ -210,10 +209,7 @@ def issubset(P1, P2, lp, tol=1e-6):
     memo = getattr(lp, "memo", None)
     if memo is None:
         return _issubset(P1, P2, lp, tol)
-    key = ("issubset", P1, P2, tol)
-    if key not in memo:
-        memo[key] = _issubset(P1, P2, lp, tol)
-    return memo[key]
+    return lp.once(memo, ("issubset", P1, P2, tol), lambda: _issubset(P1, P2, lp, tol))
 
 
 def _issubset(P1, P2, lp, tol):

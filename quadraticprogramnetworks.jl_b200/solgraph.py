@@ -133,21 +133,17 @@ class LocalSolutions:
 
     def expand(self, K):
         """avi_solutions.jl:241-261."""
-        ent = None if self.cache is None else self.cache.setdefault((self.cache_key, K), {})
-        if ent is None:
-            ent = {}
-        if "piece" not in ent:
-            ent["piece"] = local_piece(self.g, K)
-        piece = ent["piece"]
+        cache = {} if self.cache is None else self.cache
+        once = self.lp.once
+        piece = once(cache, (self.cache_key, K, "piece"), lambda: local_piece(self.g, K))
         zw = np.concatenate([self.z, self.w])
         if len(piece) and ph.isempty(piece, self.lp, tol=1e-4, x=zw):
             return None, []
         verts = []
         if self.max_vertices > 0 and (len(piece) == 0 or ph.contains(piece, zw)):
             verts = vertices_of_slice(piece, self.z, self.w, len(self.dec), self.lp)
-        if "proj" not in ent:
-            ent["proj"] = project_and_permute(piece, self.dec, self.par, self.n_vars, self.lp)
-        return ent["proj"], verts
+        proj = once(cache, (self.cache_key, K, "proj"), lambda: project_and_permute(piece, self.dec, self.par, self.n_vars, self.lp))
+        return proj, verts
 
     def collect(self):
         while self.unexplored_Ks:

@@ -263,6 +263,12 @@ def test_robust_avoid_three_levels_on_gpu(engine):
     check_robust_avoid_end_to_end(engine, seeds=(3,))
 
 
+def test_batched_state_machine_on_gpu(engine):
+    """SURVEY.md 8f-2 on the device engine: solve(qpn, inits) for networks with children regroups the device calls."""
+    from tests.test_multilevel_cpu import check_batched_state_machine
+    check_batched_state_machine(engine)
+
+
 def test_solve_qp_implicit_bounds_convexity_on_gpu(engine):
     """Row A8 on the device engine: solve_qp, the batched bound LPs of implicit_bounds, check_qp_convexity."""
     from tests.test_multilevel_cpu import check_qp_row_a8

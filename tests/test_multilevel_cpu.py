@@ -198,3 +198,62 @@ def test_projected_membership():
     # a lifted solution piece of simple_bilevel's lower node: (x, y, lam) with y = max(x, 0)
     Q = Poly(np.array([[1.0, -1.0, 0.0], [0.0, 1.0, 0.0], [0.0, 0.0, 1.0]]), [0.0, 0.0, 0.0], [0.0, INF, 0.0])   # x = y >= 0, lam = 0
     assert ph.contains_prefix(Q, [2.0], eng) and not ph.contains_prefix(Q, [-1.0], eng)
+
+
+def check_batched_state_machine(engine):
+    """the batch form regroups the instances' device calls; results are those of the per-instance runs."""
+    rng = np.random.default_rng(8)
+    net = qpn_b200.setup("simple_bilevel")
+    X = np.array([[w1, w2, 0.0, 0.0] for w1, w2 in rng.normal(size=(10, 2)) * 2])
+    seq = [qpn_b200.NetSolver(net, engine).solve(x) for x in X]
+    stats = {}
+    bat = qpn_b200.solve_multilevel_batch(net, X, engine, stats=stats)
+    assert all(a["solved"] and b["solved"] and np.array_equal(a["x_opt"], b["x_opt"]) for a, b in zip(seq, bat))
+    assert stats["device_calls"] < stats["requests"]
+    net = qpn_b200.setup("robust_avoid_simple", seed=3)
+    B = 10
+    X = np.tile(net.default_initialization, (B, 1)); X[:, 0:6] += 0.3 * rng.normal(size=(B, 6)); X[:, 6:12] = rng.uniform(-1, 1, (B, 6))
+    ns = qpn_b200.NetSolver(net, engine)
+    seq = [ns.solve(x) for x in X]
+    stats = {}
+    bat = qpn_b200.solve_multilevel_batch(net, X, engine, chunk=6, stats=stats)            # two chunks: 6 + 4 threads
+    for a, b in zip(seq, bat):
+        assert a["solved"] == b["solved"] and (not a["solved"] or np.array_equal(a["x_opt"], b["x_opt"]))
+    assert sum(b["solved"] for b in bat) >= B - 1 and 3 * stats["device_calls"] < 2 * stats["requests"]
+    # the public entry point takes the batch form for networks with children
+    out = qpn_b200.solve_multilevel_batch(net, X[:3], engine)
+    assert [o["solved"] for o in out] == [b["solved"] for b in bat[:3]]
+
+
+def test_batched_state_machine_matches_per_instance_runs():
+    check_batched_state_machine(OracleEngine())
+
+
+def test_batching_engine_propagates_errors_and_survives_early_exits():
+    """A failing device call reaches every instance of its group as an exception; instances that finish early do
+    not stall the others."""
+    from qpn_b200.batching import BatchingEngine
+
+    class Flaky(OracleEngine):
+        def comp_indices(self, g, z, w, tol=1e-2):
+            raise RuntimeError("device fault (injected)")
+
+    be = BatchingEngine(Flaky())
+    net = qpn_b200.setup("simple_bilevel")
+    g, dec, par = qpn_b200.assembly.level_gavi(net, [1])
+
+    def job(k):
+        if k == 0:
+            return "early"                                   # never touches the engine
+        r = be.gavi_solve(g, np.zeros((1, g["N"].shape[1])), np.zeros((1, g["M"].shape[1])))
+        if k == 1:
+            return int(r["status"][0])
+        try:
+            be.comp_indices(g, r["z"], np.zeros((1, g["N"].shape[1])))
+        except RuntimeError as e:
+            return str(e)
+        return "no error"
+
+    out = be.run([lambda k=k: job(k) for k in range(5)])
+    assert out[0] == "early" and out[1] == 1 and out[2:] == ["device fault (injected)"] * 3
+    assert be.device_calls == 2 and be.requests == 7
