@@ -684,9 +684,21 @@ extern "C" int qpn_halfspace_in_batched(qpn_handle* h, int npoly, int d, int mto
         up(h, a.ptr<uint8_t>(sru), ru, m) || up(h, a.ptr<double>(sx), x, 8 * (size_t)d * npts)) return -1;
     const long long warps = (long long)npoly * npts;
     const int threads = 256;
-    halfspace_in_kernel<<<(unsigned)((warps * 32 + threads - 1) / threads), threads, 0, h->stream>>>(
-        npoly, d, mtot, a.ptr<int32_t>(sp), a.ptr<double>(sA), a.ptr<double>(sl), a.ptr<double>(su), a.ptr<uint8_t>(srl),
-        a.ptr<uint8_t>(sru), npts, a.ptr<double>(sx), tol, a.ptr<uint8_t>(so));
+    const size_t smem_t = 8 * (size_t)d * HS_TP + 4 * (size_t)HS_TP * npoly + 4 * (size_t)mtot;
+    if (npts >= 2 * HS_TP && smem_t <= (size_t)h->max_smem_optin) {
+        // many points: point tiles x all rows, matrix entries reused across 16 points in registers
+        if (smem_t > 48 * 1024) CK(cudaFuncSetAttribute(halfspace_in_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+        int tthreads = roundup32(mtot);                    // one row per thread when the rows fit one pass
+        if (tthreads < 64) tthreads = 64;
+        if (tthreads > 512) tthreads = 512;
+        halfspace_in_tiled_kernel<<<(unsigned)((npts + HS_TP - 1) / HS_TP), tthreads, smem_t, h->stream>>>(
+            npoly, d, mtot, a.ptr<int32_t>(sp), a.ptr<double>(sA), a.ptr<double>(sl), a.ptr<double>(su), a.ptr<uint8_t>(srl),
+            a.ptr<uint8_t>(sru), npts, a.ptr<double>(sx), tol, a.ptr<uint8_t>(so));
+    } else {
+        halfspace_in_kernel<<<(unsigned)((warps * 32 + threads - 1) / threads), threads, 0, h->stream>>>(
+            npoly, d, mtot, a.ptr<int32_t>(sp), a.ptr<double>(sA), a.ptr<double>(sl), a.ptr<double>(su), a.ptr<uint8_t>(srl),
+            a.ptr<uint8_t>(sru), npts, a.ptr<double>(sx), tol, a.ptr<uint8_t>(so));
+    }
     h->launches++;
     CK(cudaGetLastError());
     if (down(h, in_out, a.ptr<uint8_t>(so), (size_t)npoly * npts)) return -1;

@@ -193,4 +193,62 @@ __global__ void halfspace_in_kernel(int npoly, int d, int mtot, const int32_t* _
     if (lane == 0) in_out[(size_t)pt * npoly + p] = (uint8_t)ok;
 }
 
+// ---- the same test for many points: point tiles x all rows -----------------------------------------------
+// One CTA takes HS_TP points (staged in shared memory, coordinate-major so that a warp reads one word per
+// step: a broadcast) and walks every row of every polyhedron: thread t owns rows t, t + blockDim, ... and keeps
+// HS_PP accumulators -- one matrix entry is loaded once per HS_PP points instead of once per point, and each
+// a'x is still one sequential fma chain over the coordinate index (same bits as the oracle).  Row verdicts are
+// AND-ed per (point, poly) in shared memory.  fp64-FMA / shared-memory bound, not HBM bound:
+// 2 m d flop per (poly, point) against 8 d bytes per point.
+constexpr int HS_TP = 64;      // points per CTA
+constexpr int HS_PP = 16;      // points per register pass
+__global__ void __launch_bounds__(512) halfspace_in_tiled_kernel(int npoly, int d, int mtot, const int32_t* __restrict__ poly_ptr,
+                                                                 const double* __restrict__ A, const double* __restrict__ l,
+                                                                 const double* __restrict__ u, const uint8_t* __restrict__ rl,
+                                                                 const uint8_t* __restrict__ ru, int npts, const double* __restrict__ x,
+                                                                 double tol, uint8_t* __restrict__ in_out) {
+    double* xs = reinterpret_cast<double*>(qpn_smem);                       // d x HS_TP, coordinate-major
+    unsigned* okw = reinterpret_cast<unsigned*>(xs + (size_t)d * HS_TP);    // HS_TP x npoly verdict words
+    int* rowpoly = reinterpret_cast<int*>(okw + (size_t)HS_TP * npoly);     // mtot: poly of each row
+    const int p0 = blockIdx.x * HS_TP;
+    const int np_here = min(HS_TP, npts - p0);
+    for (int e = threadIdx.x; e < d * HS_TP; e += blockDim.x) {
+        const int pt = e / d, j = e - pt * d;                              // coalesced read of x
+        xs[(size_t)j * HS_TP + pt] = pt < np_here ? x[(size_t)(p0 + pt) * d + j] : 0.0;
+    }
+    for (int e = threadIdx.x; e < HS_TP * npoly; e += blockDim.x) okw[e] = 1u;
+    for (int p = threadIdx.x; p < npoly; p += blockDim.x)
+        for (int r = poly_ptr[p]; r < poly_ptr[p + 1]; ++r) rowpoly[r] = p;
+    __syncthreads();
+    for (int row = threadIdx.x; row < mtot; row += blockDim.x) {
+        const double lo = l[row] - tol, up = u[row];
+        const bool sl = rl && rl[row], su = ru && ru[row];
+        const int p = rowpoly[row];
+        for (int q0 = 0; q0 < np_here; q0 += HS_PP) {
+            double acc[HS_PP];
+#pragma unroll
+            for (int q = 0; q < HS_PP; ++q) acc[q] = 0.0;
+            for (int j = 0; j < d; ++j) {
+                const double a = A[(size_t)j * mtot + row];
+                const double2* xj = reinterpret_cast<const double2*>(xs + (size_t)j * HS_TP + q0);    // 16-byte aligned: HS_TP, q0 even
+#pragma unroll
+                for (int q = 0; q < HS_PP / 2; ++q) {
+                    const double2 xv = xj[q];                                                        // one broadcast word pair per two fma
+                    acc[2 * q] = fma(a, xv.x, acc[2 * q]);
+                    acc[2 * q + 1] = fma(a, xv.y, acc[2 * q + 1]);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < HS_PP; ++q) {
+                const double ax = acc[q];
+                const bool okl = sl ? (lo < ax) : (lo <= ax);
+                const bool oku = su ? (ax - tol < up) : (ax - tol <= up);
+                if (!(okl && oku) && q0 + q < np_here) okw[(size_t)(q0 + q) * npoly + p] = 0u;     // benign race: everyone writes 0
+            }
+        }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < np_here * npoly; e += blockDim.x) in_out[(size_t)p0 * npoly + e] = (uint8_t)okw[e];
+}
+
 }  // namespace qpn
