@@ -290,8 +290,14 @@ __device__ __noinline__ int pivot_core(Tab t, int rho, int c, bool compact) {
     double* T = t.T();
     const double* prho = T + (size_t)rho * ldr;
     const double p = prho[c];
-    for (int j = i; j < nce; j += blockDim.x)
-        t.prow()[j] = (j >= ncol) ? 0.0 : (j == c) ? (1.0 / p) : prho[j] / p;
+    // The scaled pivot row goes to prow AND straight back into row rho (element j by the thread that scaled it;
+    // element c after the barrier, because every thread still reads p = T[rho][c] above): the update below then
+    // needs no per-element "is this the pivot row" select -- row rho runs the same fma with a zero multiplier.
+    for (int j = i; j < nce; j += blockDim.x) {
+        const double v = (j >= ncol) ? 0.0 : (j == c) ? (1.0 / p) : prho[j] / p;
+        t.prow()[j] = v;
+        if (j < ncol && j != c) T[(size_t)rho * ldr + j] = v;
+    }
     const double d = (i < n) ? T[(size_t)i * ldr + c] : 0.0;
     const int lv = t.rowvar()[rho];                         // leaving variable (read before the barrier)
     // A slack of a free variable never comes back: its column leaves the live range.
@@ -300,16 +306,16 @@ __device__ __noinline__ int pivot_core(Tab t, int rho, int c, bool compact) {
     QPN_SYNC();
     if (i < n) {
         double* row = T + (size_t)i * ldr;
-        row[c] = 0.0;                                     // then column c follows the common formula
         const bool isrho = (i == rho);
-        const double nd = -d;
+        row[c] = isrho ? t.prow()[c] : 0.0;               // then column c follows the common formula
+        const double nd = isrho ? 0.0 : -d;               // fma(0, p_j, prow_j) = prow_j: the pivot row stays as written
 #pragma unroll 2
         for (int j = 0; j < nce; j += 2) {
             const double2 pj = *reinterpret_cast<const double2*>(t.prow() + j);
             if (pj.x == 0.0 && pj.y == 0.0) continue;     // uniform: both columns untouched by this pivot
             double2 tv = *reinterpret_cast<double2*>(row + j);
-            tv.x = isrho ? pj.x : fma(nd, pj.x, tv.x);
-            tv.y = isrho ? pj.y : fma(nd, pj.y, tv.y);
+            tv.x = fma(nd, pj.x, tv.x);
+            tv.y = fma(nd, pj.y, tv.y);
             *reinterpret_cast<double2*>(row + j) = tv;
         }
         if (dead && c != last) row[c] = row[last];        // own row only: no barrier needed
