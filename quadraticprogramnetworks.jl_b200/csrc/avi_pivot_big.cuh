@@ -16,8 +16,15 @@
 // is the very same template code as the shared-memory engine, and each tableau entry is still
 // updated by exactly one fma(-d_i, prow_j, T_ij): results are bit-identical to the CPU oracle.
 //
-// Roofline: HBM / L2 bandwidth.  Algorithmic bytes per pivot: 16 * n * ncol (read + write of the
-// live tableau), + 8 * (n + ncol) for the staged column and row.
+// Delayed updates: a pivot does not sweep the tableau at once.  Its scaled pivot row and its entering column are
+// queued (QPN_BIG_PEND of them, in the CTA's slot, L1 / L2 resident); the entering column and the pivot row the
+// NEXT pivot needs are read from the stale tableau and brought up to date on the fly (one fma per queued update);
+// when the queue is full, ONE pass over the tableau applies all queued rank-1 updates, in order, from registers.
+// Every entry still sees the same sequence of fma(-d_i, prow_j, T_ij) -- only later -- so the bits do not
+// change, while the tableau crosses HBM once per QPN_BIG_PEND pivots instead of once per pivot.
+//
+// Roofline: HBM / L2 bandwidth.  Algorithmic bytes: 16 * n * ncol per QPN_BIG_PEND pivots (read + write of the
+// live tableau), + 8 * (n + ncol) per pivot for the staged column and row.
 #pragma once
 #include "avi_pivot.cuh"
 
@@ -35,14 +42,22 @@
 #define BIGCHK(cond, what, a, b) do { } while (0)
 #endif
 
+#ifndef QPN_BIG_PEND
+#define QPN_BIG_PEND 4
+#endif
+
 namespace qpn {
 
 struct BigTab {
     Tab v;              // shared-memory vectors (carved with no tableau inside: td = 0)
-    double* Tg;         // this CTA's tableau slot in global memory: n x ldr, row-major, negated
+    double* Tg;         // this CTA's tableau slot in global memory: n x ldr, row-major, negated (stale by `npend` pivots)
+    double* Pd;         // queued entering columns: QPN_BIG_PEND x nmax   (same slot, after the tableau)
+    double* Pp;         // queued scaled pivot rows: QPN_BIG_PEND x ldrmax
     int dcol_off;       // byte offset in qpn_smem of the entering-column cache (nmax doubles)
     int n, ldr, ncol, pivots;
     int cc, cpiv;       // which column the cache holds and at which pivot count it was read
+    int npend;          // queued pivots (block-uniform)
+    int prw[QPN_BIG_PEND], pcl[QPN_BIG_PEND];    // their pivot rows / entering columns
 
     __device__ __forceinline__ double* prow() const { return v.prow(); }
     __device__ __forceinline__ double* nbval() const { return v.nbval(); }
@@ -64,27 +79,124 @@ __host__ __device__ __forceinline__ size_t big_smem_bytes(int nmax) {
     return tab_smem_bytes_ex(nmax, 0, row_stride(nmax + 1)) + 8 * (size_t)((nmax + 1) & ~1);
 }
 // Doubles of one global workspace slot.
-__host__ __device__ __forceinline__ size_t big_slot_doubles(int nmax) { return (size_t)nmax * row_stride(nmax + 1); }
+__host__ __device__ __forceinline__ size_t big_slot_doubles(int nmax) {
+    return (size_t)nmax * row_stride(nmax + 1) + (size_t)QPN_BIG_PEND * ((size_t)((nmax + 1) & ~1) + row_stride(nmax + 1));
+}
 
 // Returns the byte offset just past the workspace.
 __device__ __forceinline__ int big_carve(BigTab& t, int nmax, double* slot, int base_off) {
     tab_carve_ex(t.v, nmax, 0, row_stride(nmax + 1), base_off);
     t.dcol_off = base_off + (int)tab_smem_bytes_ex(nmax, 0, row_stride(nmax + 1));
     t.Tg = slot;
-    t.n = nmax; t.ldr = row_stride(nmax + 1); t.ncol = 0; t.pivots = 0; t.cc = -1; t.cpiv = -1;
+    t.Pd = slot + (size_t)nmax * row_stride(nmax + 1);
+    t.Pp = t.Pd + (size_t)QPN_BIG_PEND * ((nmax + 1) & ~1);
+    t.n = nmax; t.ldr = row_stride(nmax + 1); t.ncol = 0; t.pivots = 0; t.cc = -1; t.cpiv = -1; t.npend = 0;
     return base_off + (int)big_smem_bytes(nmax);
 }
-__device__ __forceinline__ void big_shape(BigTab& t, int n, int cap) { t.n = n; t.ldr = row_stride(cap); t.cc = -1; }
+// Shape of the next solve; whatever was queued belongs to a tableau that is about to be overwritten.
+__device__ __forceinline__ void big_shape(BigTab& t, int n, int cap) { t.n = n; t.ldr = row_stride(cap); t.cc = -1; t.npend = 0; }
+__device__ __forceinline__ int big_pd_stride(const BigTab& t) { return (t.v.nmax + 1) & ~1; }
+
+// One queued update applied to the tableau entry (row r, column j) whose current value is v.
+__device__ __forceinline__ double big_apply(const BigTab& t, int l, int r, int j, double v, double dlr, double plj) {
+    if (r == t.prw[l]) return plj;                       // the pivot row was replaced by its scaled self
+    if (dlr == 0.0) return v;                            // rows with a zero entering entry are not touched
+    return fma(-dlr, plj, j == t.pcl[l] ? 0.0 : v);      // column c restarts from 0 (avi_pivot.cuh: row[c] = 0)
+}
 
 // ---- entering column into shared memory ------------------------------------------------------
 // Block-uniform; ends with a barrier when it had to read.
 __device__ __forceinline__ void big_col(BigTab& t, int c) {
     BIGCHK(c >= 0 && c < t.ncol, "big_col: column out of range", c, t.ncol);
     if (t.cc == c && t.cpiv == t.pivots) return;
-    const int n = t.n, ldr = t.ldr;
+    const int n = t.n, ldr = t.ldr, np = t.npend, pds = big_pd_stride(t), lds = t.v.ldrmax;
     double* d = t.dcol();
-    for (int r = threadIdx.x; r < n; r += blockDim.x) d[r] = t.Tg[(size_t)r * ldr + c];
+    for (int r = threadIdx.x; r < n; r += blockDim.x) {
+        double v = t.Tg[(size_t)r * ldr + c];
+        for (int l = 0; l < np; ++l)                     // bring the stale entry up to date, oldest update first
+            v = big_apply(t, l, r, c, v, t.Pd[(size_t)l * pds + r], t.Pp[(size_t)l * lds + c]);
+        d[r] = v;
+    }
     t.cc = c; t.cpiv = t.pivots;
+    QPN_SYNC();
+}
+
+// Apply every queued update to the tableau in one pass (in order, from registers).  When the LAST queued pivot
+// retires its column (`dead_c` >= 0: the slack of a free variable left the basis), column `dead_last` is moved
+// into its place after the updates, as the immediate form does (avi_pivot.cuh: row[c] = row[last]).
+// Ends with a barrier.
+__device__ __noinline__ void big_flush(BigTab& t, int dead_c = -1, int dead_last = -1) {
+    const int np = t.npend;
+    if (np == 0) return;
+    const int n = t.n, ldr = t.ldr, nce = (t.ncol + 1) & ~1, pds = big_pd_stride(t), lds = t.v.ldrmax;
+    // column pairs no queued update touches are neither read nor written
+    unsigned char* touched = reinterpret_cast<unsigned char*>(t.prow());
+    for (int q = threadIdx.x; q < nce / 2; q += blockDim.x) {
+        int any = 0;
+        for (int l = 0; l < np; ++l) {
+            const double2 pj = *reinterpret_cast<const double2*>(t.Pp + (size_t)l * lds + 2 * q);
+            any |= (pj.x != 0.0 || pj.y != 0.0);
+        }
+        touched[q] = (unsigned char)any;
+    }
+    QPN_SYNC();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const bool mv = dead_c >= 0 && dead_c != dead_last;
+    for (int i = w; i < n; i += nw) {
+        double nd[QPN_BIG_PEND];
+        int kind[QPN_BIG_PEND];                          // 0: row untouched by update l, 1: fma, 2: row replaced (pivot row)
+        bool any = false;
+#pragma unroll
+        for (int l = 0; l < QPN_BIG_PEND; ++l) {
+            const double dl = l < np ? t.Pd[(size_t)l * pds + i] : 0.0;
+            nd[l] = -dl;
+            kind[l] = l >= np ? 0 : (i == t.prw[l]) ? 2 : (dl != 0.0) ? 1 : 0;
+            any |= kind[l] != 0;
+        }
+        double* row = t.Tg + (size_t)i * ldr;
+        if (any) {
+            for (int j0 = 2 * lane; j0 < nce; j0 += 256) {
+                double2 tv[4];
+                bool act[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int j = j0 + 64 * q;
+                    act[q] = j < nce && touched[j >> 1];
+                    if (act[q]) tv[q] = *reinterpret_cast<const double2*>(row + j);
+                }
+#pragma unroll
+                for (int l = 0; l < QPN_BIG_PEND; ++l) {
+                    if (kind[l] == 0) continue;           // warp-uniform
+                    const double* ppl = t.Pp + (size_t)l * lds;
+                    const int cz = t.pcl[l];
+                    if (kind[l] == 2) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (act[q]) tv[q] = *reinterpret_cast<const double2*>(ppl + j0 + 64 * q);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            if (!act[q]) continue;
+                            const int j = j0 + 64 * q;
+                            const double2 pj = *reinterpret_cast<const double2*>(ppl + j);
+                            if (j == cz) tv[q].x = 0.0;
+                            if (j + 1 == cz) tv[q].y = 0.0;
+                            tv[q].x = fma(nd[l], pj.x, tv[q].x);
+                            tv[q].y = fma(nd[l], pj.y, tv[q].y);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (act[q]) *reinterpret_cast<double2*>(row + j0 + 64 * q) = tv[q];
+            }
+        }
+        if (mv) {
+            __syncwarp();
+            if (lane == 0) row[dead_c] = row[dead_last];
+        }
+    }
+    t.npend = 0;
     QPN_SYNC();
 }
 
@@ -128,74 +240,38 @@ __device__ __noinline__ void big_start(BigTab& t, const double* Md, const double
         t.colvar()[n] = 2 * n; t.nbval()[n] = 0.0;
         t.rowof()[2 * n] = -1; t.colof()[2 * n] = n;
     }
-    t.ncol = n + 1; t.pivots = 0; t.cc = -1;
+    t.ncol = n + 1; t.pivots = 0; t.cc = -1; t.npend = 0;
     QPN_SYNC();
 }
 
 // ---- rank-1 pivot (avi_scratch.jl:2-7) -------------------------------------------------------
+// rank-1 pivot (avi_scratch.jl:2-7), queued: the scaled pivot row and the entering column go to the slot's queue,
+// the basis bookkeeping happens now, the tableau sweep when the queue is full -- or at once when this pivot
+// retires its column (the slack of a free variable never comes back).  Ends with a barrier.
 __device__ __noinline__ void big_pivot(BigTab& t, int rho, int c, bool compact) {
     BIGCHK(rho >= 0 && rho < t.n, "big_pivot: row out of range", rho, c);
-    big_col(t, c);
-    const int n = t.n, ldr = t.ldr, ncol = t.ncol;
-    const int nce = (ncol + 1) & ~1;
+    big_col(t, c);                                        // current entering column (up to date) in dcol
+    const int n = t.n, ldr = t.ldr, ncol = t.ncol, nce = (ncol + 1) & ~1;
+    const int np = t.npend, pds = big_pd_stride(t), lds = t.v.ldrmax;
     const double* dc = t.dcol();
-    double* prow = t.prow();
-    const double* prho = t.Tg + (size_t)rho * ldr;
     const double p = dc[rho];
-    int has_zero = 0;
+    double* pp = t.Pp + (size_t)np * lds;
+    double* pd = t.Pd + (size_t)np * pds;
     for (int j = threadIdx.x; j < nce; j += blockDim.x) {
-        const double v = (j >= ncol) ? 0.0 : (j == c) ? (1.0 / p) : prho[j] / p;
-        prow[j] = v;
-        has_zero |= (j < ncol && v == 0.0);
+        double v = 0.0;
+        if (j < ncol) {
+            double raw = t.Tg[(size_t)rho * ldr + j];     // the pivot row, brought up to date entry by entry
+            for (int l = 0; l < np; ++l)
+                raw = big_apply(t, l, rho, j, raw, t.Pd[(size_t)l * pds + rho], t.Pp[(size_t)l * lds + j]);
+            v = (j == c) ? (1.0 / p) : raw / p;
+        }
+        pp[j] = v;
     }
+    for (int r = threadIdx.x; r < n; r += blockDim.x) pd[r] = dc[r];
     const int lv = t.rowvar()[rho];
     const bool dead = compact && lv >= n && lv < 2 * n && is_free_var(t, lv - n);
     const int last = ncol - 1;
-    // A mostly dense pivot row takes the branch-free pass (every load of a row in flight at once); a
-    // sparse one skips the column pairs it does not touch.  fma(-d, 0, T) = T, so both give the same values.
-    const int zero_threads = __syncthreads_count(has_zero);
-    const int col_threads = nce < (int)blockDim.x ? nce : (int)blockDim.x;
-    const bool dense = zero_threads * 8 < col_threads;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int i = w; i < n; i += nw) {
-        double* row = t.Tg + (size_t)i * ldr;
-        const double d = dc[i];
-        if (i == rho) {
-            for (int j = 2 * lane; j < nce; j += 64)
-                *reinterpret_cast<double2*>(row + j) = *reinterpret_cast<const double2*>(prow + j);
-        } else if (d != 0.0) {
-            const double nd = -d;
-            // four column pairs per lane in flight: predicated loads issued back to back, then the updates
-            for (int j0 = 2 * lane; j0 < nce; j0 += 256) {
-                double2 pj[4], tv[4];
-                bool act[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int j = j0 + 64 * q;
-                    act[q] = j < nce;
-                    pj[q] = act[q] ? *reinterpret_cast<const double2*>(prow + j) : make_double2(0.0, 0.0);
-                    act[q] = act[q] && (dense || pj[q].x != 0.0 || pj[q].y != 0.0);
-                }
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (act[q]) tv[q] = *reinterpret_cast<const double2*>(row + j0 + 64 * q);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if (!act[q]) continue;
-                    const int j = j0 + 64 * q;
-                    if (j == c) tv[q].x = 0.0;
-                    if (j + 1 == c) tv[q].y = 0.0;
-                    tv[q].x = fma(nd, pj[q].x, tv[q].x);
-                    tv[q].y = fma(nd, pj[q].y, tv[q].y);
-                    *reinterpret_cast<double2*>(row + j) = tv[q];
-                }
-            }
-        }
-        if (dead && c != last) {
-            __syncwarp();
-            if (lane == 0) row[c] = row[last];
-        }
-    }
+    QPN_SYNC();                                           // every thread has read rowvar[rho] before thread 0 rewrites it
     if (threadIdx.x == 0) {
         const int ev = t.colvar()[c];
         const double vent = t.nbval()[c], vlv = t.beta()[rho];
@@ -211,9 +287,12 @@ __device__ __noinline__ void big_pivot(BigTab& t, int rho, int c, bool compact) 
             t.colvar()[c] = lv; t.colof()[lv] = c; t.nbval()[c] = vlv;
         }
     }
-    t.ncol = dead ? last : ncol;
+    t.prw[np] = rho; t.pcl[np] = c;
+    t.npend = np + 1;
     t.pivots++;
     QPN_SYNC();
+    if (dead) { big_flush(t, c, last); t.ncol = last; t.cc = -1; }
+    else if (t.npend == QPN_BIG_PEND) big_flush(t);
 }
 __device__ __forceinline__ void pivot(BigTab& t, int rho, int c, bool compact = true) { big_pivot(t, rho, c, compact); }
 
@@ -296,6 +375,7 @@ __device__ __forceinline__ void move(BigTab& t, int c, double sigma, double thet
 
 // T[:, t] = B^-1 r from the slack columns (see avi_pivot.cuh).  Ends with a barrier.
 __device__ __noinline__ void recompute_tcol(BigTab& t) {
+    big_flush(t);
     const int n = t.n, ldr = t.ldr;
     const int tc = t.colof()[2 * n];
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -314,6 +394,7 @@ __device__ __noinline__ void recompute_tcol(BigTab& t) {
 
 // Drop every dead column (slack of a free variable) from the live range at once.
 __device__ __noinline__ void compact_dead(BigTab& t) {
+    big_flush(t);
     const int n = t.n, ldr = t.ldr;
     int* map = reinterpret_cast<int*>(t.prow());
     if (threadIdx.x == 0) {
@@ -354,6 +435,7 @@ __device__ __noinline__ int avi_pivot_run_big(BigTab& t, int max_pivots, bool fr
     crash(t, from_plan);
     repair(t);
     const int st = lemke(t, max_pivots);
+    t.npend = 0;                                          // z lives in beta / nbval: the queued sweeps are never needed
     QPN_SYNC();
     for (int i = threadIdx.x; i < t.n; i += blockDim.x) {
         const int r = t.rowof()[i];

@@ -114,7 +114,7 @@ __device__ __noinline__ void big_start_plan(BigTab& t, const PlanDesc& P, const 
         t.beta()[i] = rv < n ? zb[rv] : zb[i] - z0[i];
         if (rv < n) t.zst()[rv] = BASIC;
     }
-    t.ncol = P.ncol0; t.pivots = P.npiv0; t.cc = -1;
+    t.ncol = P.ncol0; t.pivots = P.npiv0; t.cc = -1; t.npend = 0;
     QPN_SYNC();
 }
 
@@ -348,6 +348,7 @@ plan_build_big_kernel(const __grid_constant__ GaviDesc g, int kind, int n_avi, c
         const int rho = best_free_row(t, c);
         if (rho >= 0) { pivot(t, rho, c, false); set_zst(t, v, BASIC); }
     }
+    big_flush(t);
     // B^-1 from the slack columns (see recompute_tcol)
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const double* row = t.Tg + (size_t)i * ldr;
