@@ -56,6 +56,7 @@ struct BigTab {
     int dcol_off;       // byte offset in qpn_smem of the entering-column cache (nmax doubles)
     int n, ldr, ncol, pivots;
     int cc, cpiv;       // which column the cache holds and at which pivot count it was read
+    int stage_off, stage_cap;   // spare dynamic shared memory (byte offset, doubles): the queue's pivot rows are staged there for a flush
     int npend;          // queued pivots (block-uniform)
     int prw[QPN_BIG_PEND], pcl[QPN_BIG_PEND];    // their pivot rows / entering columns
 
@@ -91,7 +92,15 @@ __device__ __forceinline__ int big_carve(BigTab& t, int nmax, double* slot, int 
     t.Pd = slot + (size_t)nmax * row_stride(nmax + 1);
     t.Pp = t.Pd + (size_t)QPN_BIG_PEND * ((nmax + 1) & ~1);
     t.n = nmax; t.ldr = row_stride(nmax + 1); t.ncol = 0; t.pivots = 0; t.cc = -1; t.cpiv = -1; t.npend = 0;
+    t.stage_off = 0; t.stage_cap = 0;
     return base_off + (int)big_smem_bytes(nmax);
+}
+// Whatever dynamic shared memory the launch got beyond the `used` bytes of the kernel's own layout.
+__device__ __forceinline__ void big_stage_carve(BigTab& t, int used) {
+    unsigned total;
+    asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(total));
+    t.stage_off = (used + 15) & ~15;
+    t.stage_cap = (int)total > t.stage_off ? ((int)total - t.stage_off) / 8 : 0;
 }
 // Shape of the next solve; whatever was queued belongs to a tableau that is about to be overwritten.
 __device__ __forceinline__ void big_shape(BigTab& t, int n, int cap) { t.n = n; t.ldr = row_stride(cap); t.cc = -1; t.npend = 0; }
@@ -128,13 +137,23 @@ __device__ __forceinline__ void big_col(BigTab& t, int c) {
 __device__ __noinline__ void big_flush(BigTab& t, int dead_c = -1, int dead_last = -1) {
     const int np = t.npend;
     if (np == 0) return;
-    const int n = t.n, ldr = t.ldr, nce = (t.ncol + 1) & ~1, pds = big_pd_stride(t), lds = t.v.ldrmax;
+    const int n = t.n, ldr = t.ldr, nce = (t.ncol + 1) & ~1, pds = big_pd_stride(t);
+    // the queued pivot rows are read once per tableau row: from shared memory when the launch has room to stage them
+    const bool staged = np * nce <= t.stage_cap;
+    const int lds = staged ? nce : t.v.ldrmax;
+    const double* PP = t.Pp;
+    if (staged) {
+        double* st = reinterpret_cast<double*>(qpn_smem + t.stage_off);
+        for (int e = threadIdx.x; e < np * nce; e += blockDim.x) { const int l = e / nce, j = e - l * nce; st[e] = t.Pp[(size_t)l * t.v.ldrmax + j]; }
+        PP = st;
+        QPN_SYNC();
+    }
     // column pairs no queued update touches are neither read nor written
     unsigned char* touched = reinterpret_cast<unsigned char*>(t.prow());
     for (int q = threadIdx.x; q < nce / 2; q += blockDim.x) {
         int any = 0;
         for (int l = 0; l < np; ++l) {
-            const double2 pj = *reinterpret_cast<const double2*>(t.Pp + (size_t)l * lds + 2 * q);
+            const double2 pj = *reinterpret_cast<const double2*>(PP + (size_t)l * lds + 2 * q);
             any |= (pj.x != 0.0 || pj.y != 0.0);
         }
         touched[q] = (unsigned char)any;
@@ -167,7 +186,7 @@ __device__ __noinline__ void big_flush(BigTab& t, int dead_c = -1, int dead_last
 #pragma unroll
                 for (int l = 0; l < QPN_BIG_PEND; ++l) {
                     if (kind[l] == 0) continue;           // warp-uniform
-                    const double* ppl = t.Pp + (size_t)l * lds;
+                    const double* ppl = PP + (size_t)l * lds;
                     const int cz = t.pcl[l];
                     if (kind[l] == 2) {
 #pragma unroll
@@ -244,7 +263,6 @@ __device__ __noinline__ void big_start(BigTab& t, const double* Md, const double
     QPN_SYNC();
 }
 
-// ---- rank-1 pivot (avi_scratch.jl:2-7) -------------------------------------------------------
 // rank-1 pivot (avi_scratch.jl:2-7), queued: the scaled pivot row and the entering column go to the slot's queue,
 // the basis bookkeeping happens now, the tableau sweep when the queue is full -- or at once when this pivot
 // retires its column (the slack of a free variable never comes back).  Ends with a barrier.

@@ -157,9 +157,11 @@ __global__ void __launch_bounds__(QPN_BIG_THREADS, 1)
 avi_solve_big_kernel(int n, int batch, const __grid_constant__ MatDesc M, const __grid_constant__ PlanDesc P, int has_plan,
                      const double* __restrict__ q, const double* __restrict__ l, const double* __restrict__ u, int lu_shared,
                      const double* __restrict__ z0, int max_pivots, double* __restrict__ z_out, int32_t* __restrict__ status_out,
-                     int32_t* __restrict__ pivots_out, int8_t* __restrict__ basis_out, double* __restrict__ work, size_t slot_doubles) {
+                     int32_t* __restrict__ pivots_out, int8_t* __restrict__ basis_out, double* __restrict__ work, size_t slot_doubles,
+                     int smem_used) {
     BigTab t;
     const int off = big_carve(t, n, work + (size_t)blockIdx.x * slot_doubles, 0);
+    big_stage_carve(t, smem_used);
     double* qs = reinterpret_cast<double*>(qpn_smem + off);
     double* zs = qs + n;
     double* zb = zs + n;
@@ -248,10 +250,12 @@ __global__ void __launch_bounds__(QPN_BIG_THREADS, 1)
 gavi_solve_big_kernel(const __grid_constant__ GaviDesc g, const __grid_constant__ GaviPlans plans, int batch,
                       const double* __restrict__ w, const double* __restrict__ z0, int presolve, int max_pivots,
                       double* __restrict__ z_out, double* __restrict__ zfull_out, int32_t* __restrict__ status_out,
-                      int32_t* __restrict__ pivots_out, int8_t* __restrict__ basis_out, double* __restrict__ work, size_t slot_doubles) {
+                      int32_t* __restrict__ pivots_out, int8_t* __restrict__ basis_out, double* __restrict__ work, size_t slot_doubles,
+                      int smem_used) {
     const int dz = g.d1 + g.d2, n = g.d1 + 2 * g.d2;
     BigTab t;
     const int off = big_carve(t, n, work + (size_t)blockIdx.x * slot_doubles, 0);
+    big_stage_carve(t, smem_used);
     GaviSmem s;
     gavi_carve_extra(s, g, off);
     for (int b = blockIdx.x; b < batch; b += gridDim.x) {
@@ -279,11 +283,13 @@ __global__ void __launch_bounds__(QPN_BIG_THREADS, 1)
 plan_build_big_kernel(const __grid_constant__ GaviDesc g, int kind, int n_avi, const __grid_constant__ MatDesc M,
                       const double* __restrict__ l, const double* __restrict__ u, double* __restrict__ T0, double* __restrict__ PT,
                       int* __restrict__ rowvar0, int* __restrict__ colvar0, int* __restrict__ csr_ptr, int* __restrict__ csr_col,
-                      double* __restrict__ csr_val, int* __restrict__ cols_out, int* __restrict__ hdr, double* __restrict__ work) {
+                      double* __restrict__ csr_val, int* __restrict__ cols_out, int* __restrict__ hdr, double* __restrict__ work,
+                      int smem_used) {
     const int d1 = g.d1, d2 = g.d2, dz = d1 + d2;
     const int nmax = kind == 2 ? n_avi : d1 + 2 * d2;
     BigTab t;
     int off = big_carve(t, nmax, work, 0);
+    big_stage_carve(t, smem_used);
     GaviSmem s;
     double *qs, *zs;
     int* cnt;

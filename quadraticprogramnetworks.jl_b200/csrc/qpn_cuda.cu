@@ -346,17 +346,23 @@ static bool big_needed(qpn_handle* h, int n, size_t smem_small) {
 }
 
 // Grid of persistent CTAs for a big kernel and the workspace for their slots.
+// smem_io: in = bytes of the kernel's own layout, out = bytes to launch with (the layout plus room to stage the queued
+// pivot rows of a flush, as far as the SM allows; the kernel finds the spare part through %dynamic_smem_size).
 template <class K>
-static int big_grid_ex(qpn_handle* h, K kernel, int nmax, size_t slot_doubles, size_t smem, int batch, int* grid_out);
+static int big_grid_ex(qpn_handle* h, K kernel, int nmax, size_t slot_doubles, size_t* smem_io, int batch, int* grid_out);
 template <class K>
-static int big_grid(qpn_handle* h, K kernel, int nmax, size_t smem, int batch, int* grid_out) {
-    return big_grid_ex(h, kernel, nmax, big_slot_doubles(nmax), smem, batch, grid_out);
+static int big_grid(qpn_handle* h, K kernel, int nmax, size_t* smem_io, int batch, int* grid_out) {
+    return big_grid_ex(h, kernel, nmax, big_slot_doubles(nmax), smem_io, batch, grid_out);
 }
 template <class K>
-static int big_grid_ex(qpn_handle* h, K kernel, int nmax, size_t slot_doubles, size_t smem, int batch, int* grid_out) {
+static int big_grid_ex(qpn_handle* h, K kernel, int nmax, size_t slot_doubles, size_t* smem_io, int batch, int* grid_out) {
+    size_t smem = *smem_io;
     if (smem > (size_t)h->max_smem_optin)
         return fail(h, "size n=%d needs %zu B of shared memory per CTA on the global-memory tableau path (limit %d)", nmax, smem,
                     h->max_smem_optin);
+    smem = ((smem + 15) & ~(size_t)15) + 8 * (size_t)QPN_BIG_PEND * row_stride(nmax + 1);
+    if (smem > (size_t)h->max_smem_optin) smem = (size_t)h->max_smem_optin;
+    *smem_io = smem;
     CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, QPN_BIG_THREADS, smem));
@@ -390,7 +396,8 @@ static int build_plan_big(qpn_handle* h, const GaviDesc& g, int kind, int n_avi,
                  optr = add(4 * (n + 1)), ocol = add(4 * n * n), ocols = add(4 * (dz + 1)), ohdr = add(16);
     const size_t smem = big_smem_bytes((int)n) + (kind == 2 ? 16 * n : gavi_extra_bytes(g.d1, g.d2, g.np)) + 4 * n + 16;
     int grid = 0;
-    if (big_grid(h, plan_build_big_kernel, (int)n, smem, 1, &grid)) return -1;
+    size_t smem_l = smem;
+    if (big_grid(h, plan_build_big_kernel, (int)n, &smem_l, 1, &grid)) return -1;
     unsigned char* b = nullptr;
     if (blob_out) {
         CK(cudaMalloc((void**)&b, need + 256));
@@ -403,9 +410,10 @@ static int build_plan_big(qpn_handle* h, const GaviDesc& g, int kind, int n_avi,
         }
         b = h->plan_buf[slot];
     }
-    plan_build_big_kernel<<<1, QPN_BIG_THREADS, smem, h->stream>>>(g, kind, n_avi, M, l, u, (double*)(b + oT0), (double*)(b + oPT),
-                                                                   (int*)(b + orv), (int*)(b + ocv), (int*)(b + optr), (int*)(b + ocol),
-                                                                   (double*)(b + oval), (int*)(b + ocols), (int*)(b + ohdr), h->big_work);
+    plan_build_big_kernel<<<1, QPN_BIG_THREADS, smem_l, h->stream>>>(g, kind, n_avi, M, l, u, (double*)(b + oT0), (double*)(b + oPT),
+                                                                     (int*)(b + orv), (int*)(b + ocv), (int*)(b + optr), (int*)(b + ocol),
+                                                                     (double*)(b + oval), (int*)(b + ocols), (int*)(b + ohdr), h->big_work,
+                                                                     (int)smem);
     h->launches++;
     CK(cudaGetLastError());
     int hdr[4];
@@ -427,7 +435,8 @@ static int launch_avi_big(qpn_handle* h, int n, int batch, const MatDesc& M, con
                           cudaStream_t s) {
     const size_t smem = big_smem_bytes(n) + 8 * 3 * (size_t)n + (((size_t)n + 15) & ~(size_t)15);
     int grid = 0;
-    if (big_grid(h, avi_solve_big_kernel, n, smem, batch, &grid)) return -1;
+    size_t smem_l = smem;
+    if (big_grid(h, avi_solve_big_kernel, n, &smem_l, batch, &grid)) return -1;
     PlanDesc P;
     memset(&P, 0, sizeof P);
     int has_plan = 0;
@@ -437,8 +446,8 @@ static int launch_avi_big(qpn_handle* h, int n, int batch, const MatDesc& M, con
         if (build_plan_big(h, g0, 2, n, M, l, u, 0, &P, nullptr)) return -1;
         has_plan = 1;
     }
-    avi_solve_big_kernel<<<grid, QPN_BIG_THREADS, smem, s>>>(n, batch, M, P, has_plan, q, l, u, lu_shared, z0, max_pivots, z, st, pv,
-                                                             basis, h->big_work, big_slot_doubles(n));
+    avi_solve_big_kernel<<<grid, QPN_BIG_THREADS, smem_l, s>>>(n, batch, M, P, has_plan, q, l, u, lu_shared, z0, max_pivots, z, st, pv,
+                                                               basis, h->big_work, big_slot_doubles(n), (int)smem);
     h->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -449,7 +458,8 @@ static int launch_gavi_big(qpn_handle* h, const GaviDesc& g, int batch, const do
     const int n = g.d1 + 2 * g.d2;
     const size_t smem = big_smem_bytes(n) + gavi_extra_bytes(g.d1, g.d2, g.np);
     int grid = 0;
-    if (big_grid(h, gavi_solve_big_kernel, n, smem, batch, &grid)) return -1;
+    size_t smem_l = smem;
+    if (big_grid(h, gavi_solve_big_kernel, n, &smem_l, batch, &grid)) return -1;
     GaviPlans plans;
     memset(&plans, 0, sizeof plans);
     if (batch >= 2 && s == h->stream) {
@@ -460,8 +470,8 @@ static int launch_gavi_big(qpn_handle* h, const GaviDesc& g, int batch, const do
         plans.has = 1;
     }
     if (max_pivots <= 0) max_pivots = 50 * n + 100;
-    gavi_solve_big_kernel<<<grid, QPN_BIG_THREADS, smem, s>>>(g, plans, batch, w, z0, presolve, max_pivots, z, zfull, st, pv, basis,
-                                                              h->big_work, big_slot_doubles(n));
+    gavi_solve_big_kernel<<<grid, QPN_BIG_THREADS, smem_l, s>>>(g, plans, batch, w, z0, presolve, max_pivots, z, zfull, st, pv, basis,
+                                                                h->big_work, big_slot_doubles(n), (int)smem);
     h->launches++;
     CK(cudaGetLastError());
     return 0;

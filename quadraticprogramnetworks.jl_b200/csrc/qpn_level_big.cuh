@@ -223,11 +223,12 @@ __host__ __device__ __forceinline__ size_t verify_big_slot_doubles(int nd, int m
 __global__ void __launch_bounds__(QPN_BIG_THREADS, 1)
 verify_solution_big_kernel(const __grid_constant__ NodeDesc node, int batch, const double* __restrict__ x, double tol,
                            uint8_t* __restrict__ solution_out, double* __restrict__ lam_out, int32_t* __restrict__ how_out,
-                           int8_t* __restrict__ active_out, double* __restrict__ work, size_t slot_doubles) {
+                           int8_t* __restrict__ active_out, double* __restrict__ work, size_t slot_doubles, int smem_used) {
     const int m = node.m, tn = m > 0 ? m : 1;
     BigTab t;
     double* slot = work + (size_t)blockIdx.x * slot_doubles;
     int off = big_carve(t, tn, slot, 0);
+    big_stage_carve(t, smem_used);
     VerifyBig vs;
     vs.base = off; vs.nd = node.nd; vs.m = m; vs.Ab = slot; vs.Ab0 = slot + (size_t)node.nd * tn;
     off += (int)verify_big_bytes(node.nd, m);
@@ -272,13 +273,14 @@ level_equilibrium_big_kernel(const __grid_constant__ LevelDesc lv, int batch, co
                              double* __restrict__ x_out, uint8_t* __restrict__ solved_out, int32_t* __restrict__ iters_out,
                              int32_t* __restrict__ pivots_out, double* __restrict__ lam_out, double* __restrict__ hist,
                              int32_t* __restrict__ hist_count, int hist_cap, int presolve, int hist_fresh, double* __restrict__ work,
-                             size_t slot_doubles) {
+                             size_t slot_doubles, int smem_used) {
     const int i = threadIdx.x, nv = lv.nv;
     const int n_level = lv.g.d1 + 2 * lv.g.d2;
     const int nmax = n_level > lv.max_m ? n_level : lv.max_m;
     BigTab t;
     double* slot = work + (size_t)blockIdx.x * slot_doubles;
     int off = big_carve(t, nmax, slot, 0);
+    big_stage_carve(t, smem_used);
     GaviSmem gs;
     gavi_carve_extra(gs, lv.g, off);
     VerifyBig vs;
