@@ -38,15 +38,15 @@ WORKLOAD = "four_player_matrix_game Nash (edge_list=[]), random inits ~ U(-5,5)^
 HBM_FALLBACK_GBS = 6650.0     # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 # dram__bytes_read.sum + dram__bytes_write.sum of one level_equilibrium_kernel<32> launch at the default
 # batch (4,096), from profiles/r1_final_level_kernel_ncu_full_summary.csv (ncu --set full, same command)
-NCU_DRAM_BYTES_PER_LAUNCH_B4096 = 439_296 + 1_024
+NCU_DRAM_BYTES_PER_LAUNCH_B4096 = 422_912 + 1_024
 # same capture: l1tex__data_pipe_lsu_wavefronts_mem_shared.sum (each wavefront moves up to 128 B) and
 # smsp__inst_executed.sum -- the two on-chip resources that actually bound the pivoting kernel
-NCU_SMEM_WAVEFRONTS_PER_LAUNCH_B4096 = 5_711_598
-NCU_WARP_INSTRUCTIONS_PER_LAUNCH_B4096 = 40_007_087
+NCU_SMEM_WAVEFRONTS_PER_LAUNCH_B4096 = 5_316_090
+NCU_WARP_INSTRUCTIONS_PER_LAUNCH_B4096 = 33_660_807
 SM_COUNT = 148
 # dram__bytes_read.sum + dram__bytes_write.sum of one level_equilibrium_big_kernel launch on the n = 256, m = 512
 # monotone stress level at batch 148 (profiles/r1_big_level_kernel_ncu_full_summary.csv)
-NCU_DRAM_BYTES_BIG_LEVEL_B148 = 999_535_201_000 + 920_568_660_000
+NCU_DRAM_BYTES_BIG_LEVEL_B148 = 453_209_967_000 + 419_249_768_000
 
 
 def inits_for(rank, batch, step=0):
@@ -383,8 +383,9 @@ def main():
                          "frac": NCU_DRAM_BYTES_BIG_LEVEL_B148 / tm / 1e9 / peak_m, "traffic": NCU_DRAM_BYTES_BIG_LEVEL_B148,
                          "dense_upper_bound_bytes": alg,
                          "note": "achieved = DRAM bytes of this launch measured by ncu (same batch, same data) / event-timed duration; the dense "
-                                 "bound 16 B x rows x live columns x pivots overstates it: rows with a zero entering entry and column pairs "
-                                 "with zero pivot-row entries are skipped, and L2 (126 MB) serves half of the re-reads"},
+                                 "bound 16 B x rows x live columns x pivots overstates it by 7x: pivots are queued four deep and swept in one pass, "
+                                 "rows with a zero entering entry and column pairs with zero pivot-row entries are skipped, and L2 serves 70 % of "
+                                 "the sector requests; with that the kernel is no longer HBM bound (L1 36 %, issue 27 %, DRAM 38 % of the copy peak)"},
             "note": "per GPU, device-timed; verify -> solve_qep -> verify fused in level_equilibrium_big_kernel"}
         ms_solver.close()
     except Exception as e:
@@ -409,7 +410,7 @@ def main():
                          "traffic": NCU_DRAM_BYTES_PER_LAUNCH_B4096 if B == 4096 else None,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "kernel": "level_equilibrium_kernel<32>", "peak_source": peak_src,
-                         "note": "the fused pivoting kernel is issue/latency bound in shared memory (ncu: IPC 1.8/SM, fp64 pipe 10 %, "
+                         "note": "the fused pivoting kernel is issue/latency bound in shared memory (ncu: IPC 1.7/SM, fp64 pipe 10 %, "
                                  "0 % tensor), not HBM bound; see DESIGN.md 5 and profiles/"},
             "clocks": clocks,
             "extra": extra,
