@@ -158,23 +158,36 @@ class Poly:
         elif m:
             A = A.copy()
         # equal slices (5-digit rounding, sets.jl:104-112) are stored once, in first-seen order
-        RA = np.round(A, 5) + 0.0
+        K = np.empty((m, d + 4))
+        np.round(A, 5, out=K[:, :d])
         with np.errstate(invalid="ignore"):
-            rL = np.where(np.isinf(l), l, np.round(l, 5)) + 0.0
-            rU = np.where(np.isinf(u), u, np.round(u, 5)) + 0.0
-        keys, keep, seen = [], [], set()
-        for i in range(m):
-            key = (RA[i].tobytes(), float(rL[i]), float(rU[i]), bool(rl[i]), bool(ru[i]))
-            if key in seen:
-                continue
-            seen.add(key)
-            keys.append(key); keep.append(i)
-        self.A = A[keep].reshape(len(keep), d)
-        self.l = l[keep].astype(float)
-        self.u = u[keep].astype(float)
-        self.rl = rl[keep].astype(bool)
-        self.ru = ru[keep].astype(bool)
-        self._keys = frozenset(keys)
+            K[:, d] = np.where(np.isinf(l), l, np.round(l, 5))
+            K[:, d + 1] = np.where(np.isinf(u), u, np.round(u, 5))
+        K[:, d + 2] = rl
+        K[:, d + 3] = ru
+        K += 0.0                                           # -0.0 -> +0.0: equal keys have equal bytes
+        keys = [row.tobytes() for row in K]
+        if m > 1 and len(set(keys)) < m:
+            seen, keep = set(), []
+            for i, key in enumerate(keys):
+                if key not in seen:
+                    seen.add(key); keep.append(i)
+            A, l, u, rl, ru = A[keep], l[keep], u[keep], rl[keep], ru[keep]
+            keys = [keys[i] for i in keep]
+        self.A = np.ascontiguousarray(A, dtype=float).reshape(len(l), d)
+        self.l = np.array(l, dtype=float)
+        self.u = np.array(u, dtype=float)
+        self.rl = np.array(rl, dtype=bool)
+        self.ru = np.array(ru, dtype=bool)
+        self._K = keys
+        self._keyset = None
+
+    @property
+    def _keys(self):
+        """The set of slice keys (built on first use: most polyhedra are temporaries that are never compared)."""
+        if self._keyset is None:
+            self._keyset = frozenset(self._K)
+        return self._keyset
 
     def __len__(self):
         return len(self.l)

@@ -78,15 +78,25 @@ def complement(P):
 
 def simplify(P, tol=1e-6):
     """sets.jl:255-305: merge slices with the same normal, keeping the tighter bounds."""
-    keep = []      # [a, l, u, rl, ru]
-    KA = np.zeros((len(P), P.dim))                 # normals of the kept slices, for one vectorised distance per row
-    nonzero = np.sqrt(np.einsum("ij,ij->i", P.A, P.A)) > tol if len(P) else np.zeros(0, bool)
-    for i in range(len(P)):
-        a, l, u, rl, ru = P.A[i], P.l[i], P.u[i], bool(P.rl[i]), bool(P.ru[i])
-        nk = len(keep)
-        hit = np.flatnonzero(np.sqrt(np.einsum("ij,ij->i", KA[:nk] - a, KA[:nk] - a)) <= tol) if nk else ()
-        if len(hit):                                      # isapprox(k, s.a; atol=tol): the first kept slice with this normal
-            k = keep[int(hit[0])]
+    m, d = len(P), P.dim
+    if m == 0:
+        return Poly(np.zeros((0, d)), [], [])
+    A = P.A
+    nonzero = np.sqrt(np.einsum("ij,ij->i", A, A)) > tol
+    # all pairwise distances between normals at once (m is a few dozen); the sequential part below only looks up
+    # "first kept slice with this normal" (isapprox(k, s.a; atol=tol))
+    diff = A[:, None, :] - A[None, :, :]
+    close = np.sqrt(np.einsum("ijk,ijk->ij", diff, diff)) <= tol
+    L, U, RL, RU = P.l.tolist(), P.u.tolist(), P.rl.tolist(), P.ru.tolist()
+    keep, kept_rows = [], []      # [row, l, u, rl, ru]
+    for i in range(m):
+        l, u, rl, ru = L[i], U[i], RL[i], RU[i]
+        k = None
+        if kept_rows:
+            hit = np.flatnonzero(close[i, kept_rows])
+            if len(hit):
+                k = keep[int(hit[0])]
+        if k is not None:
             if k[1] > l + tol:
                 nl, nrl = k[1], k[3]
             elif l > k[1] + tol:
@@ -101,12 +111,10 @@ def simplify(P, tol=1e-6):
                 nu, nru = 0.5 * (k[2] + u) if not (math.isinf(k[2]) and math.isinf(u)) else u, (True if k[4] else ru)
             k[1], k[2], k[3], k[4] = nl, nu, nrl, nru
         elif nonzero[i]:
-            KA[nk] = a
-            keep.append([a.copy(), l, u, rl, ru])
-    d = P.dim
+            keep.append([i, l, u, rl, ru]); kept_rows.append(i)
     if not keep:
         return Poly(np.zeros((0, d)), [], [])
-    return Poly(np.array([k[0] for k in keep]), [k[1] for k in keep], [k[2] for k in keep], [k[3] for k in keep], [k[4] for k in keep])
+    return Poly(A[kept_rows], [k[1] for k in keep], [k[2] for k in keep], [k[3] for k in keep], [k[4] for k in keep])
 
 
 def poly_slice(P, fixed):

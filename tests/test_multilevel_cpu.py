@@ -257,3 +257,21 @@ def test_batching_engine_propagates_errors_and_survives_early_exits():
     out = be.run([lambda k=k: job(k) for k in range(5)])
     assert out[0] == "early" and out[1] == 1 and out[2:] == ["device fault (injected)"] * 3
     assert be.device_calls == 2 and be.requests == 7
+
+
+def test_multilevel_batch_over_worker_processes():
+    """A multi-level batch sharded over host processes (contiguous shards, one engine handle each): same results,
+    in instance order, as the single-process batch; odd shard sizes."""
+    rng = np.random.default_rng(9)
+    net = qpn_b200.setup("robust_avoid_simple", seed=3)
+    B = 7
+    X = np.tile(net.default_initialization, (B, 1)); X[:, 0:6] += 0.3 * rng.normal(size=(B, 6)); X[:, 6:12] = rng.uniform(-1, 1, (B, 6))
+    one = qpn_b200.solve_multilevel_batch(net, X, OracleEngine())
+    stats = {}
+    par = qpn_b200.solve_multilevel_workers(net, X, 3, engine_factory=OracleEngine, factory_args=(), stats=stats)
+    assert len(par) == B and stats["workers"] == 3 and stats["requests"] > 0
+    for a, b in zip(one, par):
+        assert a["solved"] == b["solved"] and "Sol" not in b
+        assert np.array_equal(a["x_opt"], b["x_opt"]) if a["solved"] else np.array_equal(a["x_fail"], b["x_fail"])
+    kept = qpn_b200.solve_multilevel_workers(net, X[:2], 5, engine_factory=OracleEngine, factory_args=(), keep_sol=True)
+    assert len(kept) == 2 and all("Sol" in r for r in kept if r["solved"])
