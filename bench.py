@@ -124,7 +124,7 @@ def cpu_cores():
         return os.cpu_count() or 1
 
 
-def cpu_baseline(sample_batches=16, batch=4096):
+def cpu_baseline(sample_batches=256, batch=4096):
     cores = cpu_cores()
     L = oracle_level()
     X = np.vstack([inits_for(10_000 + k, batch) for k in range(sample_batches)])
@@ -176,6 +176,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="instances per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-multilevel", action="store_true", help="skip the three-level robust_avoid extra (spawns host worker processes)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -390,6 +391,31 @@ def main():
         ms_solver.close()
     except Exception as e:
         extra["monotone_stress_n256_m512"] = {"error": str(e)[:200]}
+
+    # ---- BASELINE.json configs[2] in full: three-level robust_avoid_simple solves (vertex exploration on), the host
+    # recursion of solve_base! sharded over worker processes that are all served by this rank's engine handle
+    # (workers.py).  Host-bound (piece generation / set operations in the Python mirror): reported as an extra.
+    if world == 1 and not args.no_multilevel:
+        try:
+            ra3 = qpn_b200.setup("robust_avoid_simple", seed=3)
+            nw = max(1, min(cpu_cores() - 1, 15))
+            Bf = 128 * nw
+            rng = np.random.default_rng([0xB200, rank, 11])
+            Xf = np.tile(ra3.default_initialization, (Bf, 1))
+            Xf[:, 0:6] += 0.3 * rng.normal(size=(Bf, 6)); Xf[:, 6:12] = rng.uniform(-1, 1, (Bf, 6))
+            with qpn_b200.MultilevelPool(ra3, nw, engine=eng) as pool:
+                pool.solve(Xf[:4 * nw])                                   # processes up, piece memos warm
+                st = {}
+                l0 = eng.launches
+                t0 = time.perf_counter(); res = pool.solve(Xf, stats=st); tf = time.perf_counter() - t0
+            extra["robust_avoid_three_levels"] = {
+                "value": Bf / tf, "unit": UNIT, "batch": Bf, "host_workers": nw, "wall_s": tf,
+                "solved_fraction": float(np.mean([r["solved"] for r in res])), "device_launches": int(eng.launches - l0),
+                "device_requests_before_regrouping": int(st.get("requests", 0)),
+                "note": "per GPU, host clock, inputs and results in host memory; every numeric step on the device, the recursion of "
+                        "solve_base! in worker processes (host-bound)"}
+        except Exception as e:                                  # noqa: BLE001
+            extra["robust_avoid_three_levels"] = {"error": str(e)[:200]}
 
     if rank == 0:
         peak, peak_src = measured_hbm_peak()

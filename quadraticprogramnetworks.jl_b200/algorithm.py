@@ -72,7 +72,7 @@ def solve(qpn, x_init=None, device=0, workers=1):
 
     Julia's `inits::Matrix` is n_vars x B column-major, i.e. a (B, n_vars) C-contiguous array here.
     workers > 1 (multi-level batches only): the host recursion sharded over that many processes on `device`
-    (`solve_multilevel_workers`); results are identical, `Sol` is not returned."""
+    (workers.py); results are identical, `Sol` is not returned."""
     x = qpn.default_initialization if x_init is None else np.asarray(x_init, dtype=np.float64)
     single = x.ndim == 1
     solver = _solver_for(qpn, device)
@@ -84,7 +84,8 @@ def solve(qpn, x_init=None, device=0, workers=1):
         if len(X) == 1:
             outs = [NetSolver(qpn, solver.engine).solve(X[0])]
         elif workers > 1:
-            outs = solve_multilevel_workers(qpn, X, workers, device=device)
+            from .workers import solve_multilevel_workers
+            outs = solve_multilevel_workers(qpn, X, workers, engine=solver.engine)
         else:
             outs = solve_multilevel_batch(qpn, X, solver.engine)
         return outs[0] if single else outs
@@ -100,11 +101,14 @@ def solve(qpn, x_init=None, device=0, workers=1):
     return results[0] if single else results
 
 
-def solve_multilevel_batch(qpn, X, engine, chunk=256, stats=None):
+def solve_multilevel_batch(qpn, X, engine, chunk=256, stats=None, pieces=None, memo=None):
     """solve(qpn, inits) for a network with children: one NetSolver per instance (its own iterate cache and cycle
-    detection), all of them sharing the memoised pieces and driving the device through one BatchingEngine."""
+    detection), all of them sharing the memoised pieces and driving the device through one BatchingEngine.
+    pieces / memo: the piece and predicate memos, when the caller keeps them across batches (workers.py)."""
     from .batching import BatchingEngine
-    pieces, memo, outs = {}, {}, []
+    pieces = {} if pieces is None else pieces
+    memo = {} if memo is None else memo
+    outs = []
     for lo in range(0, len(X), chunk):
         be = BatchingEngine(engine)
         jobs = [(lambda xi=xi: NetSolver(qpn, be, piece_cache=pieces, lp_memo=memo).solve(xi)) for xi in X[lo:lo + chunk]]
@@ -113,56 +117,6 @@ def solve_multilevel_batch(qpn, X, engine, chunk=256, stats=None):
             stats["rounds"] = stats.get("rounds", 0) + be.rounds
             stats["device_calls"] = stats.get("device_calls", 0) + be.device_calls
             stats["requests"] = stats.get("requests", 0) + be.requests
-    return outs
-
-
-def _device_engine(device):
-    return Engine(device)
-
-
-def _multilevel_worker(task):
-    """One host process of `solve_multilevel_workers`: its own engine handle (CUDA context) on the same device, the
-    recursion of its contiguous shard, and only the fields a batch caller reads sent back."""
-    qpn, X, factory, factory_args, chunk, keep_sol = task
-    eng = factory(*factory_args)
-    stats = {}
-    outs = solve_multilevel_batch(qpn, X, eng, chunk=chunk, stats=stats)
-    if not keep_sol:
-        for r in outs:
-            r.pop("Sol", None)
-    return outs, stats, getattr(eng, "launches", 0)
-
-
-def solve_multilevel_workers(qpn, X, workers, device=0, chunk=256, stats=None, keep_sol=False,
-                             engine_factory=None, factory_args=None):
-    """The multi-level batch sharded over `workers` host processes that share ONE GPU.
-
-    The per-instance recursion of solve_base! (piece generation, set operations, cycle detection) is host work; with
-    the device calls regrouped it is what bounds a multi-level batch, and it is independent per instance.  So the
-    instances are split into contiguous shards (the rule of sharding.shard_range, as across GPUs), each shard runs
-    `solve_multilevel_batch` in its own process with its own engine handle on `device`, and the results come back in
-    instance order.  Every instance is solved by the same code on the same device as with workers = 1, so the
-    results are identical.  `Sol` (the solution pieces of the top level) is dropped unless keep_sol: it is large
-    and a batch caller reads x_opt / solved."""
-    import multiprocessing as mp
-    from .sharding import shard_range
-    X = np.ascontiguousarray(X, dtype=np.float64)
-    workers = max(1, min(int(workers), len(X)))
-    factory = engine_factory or _device_engine
-    fargs = (device,) if factory_args is None else tuple(factory_args)
-    tasks = [(qpn, X[slice(*shard_range(len(X), r, workers))], factory, fargs, chunk, keep_sol) for r in range(workers)]
-    if workers == 1:
-        parts = [_multilevel_worker(tasks[0])]
-    else:
-        with mp.get_context("spawn").Pool(workers) as pool:      # spawn: a forked child cannot re-use the CUDA context
-            parts = pool.map(_multilevel_worker, tasks, chunksize=1)
-    outs = [r for part, _, _ in parts for r in part]
-    if stats is not None:
-        for _, st, launches in parts:
-            for k, v in st.items():
-                stats[k] = stats.get(k, 0) + v
-            stats["launches"] = stats.get("launches", 0) + launches
-        stats["workers"] = workers
     return outs
 
 

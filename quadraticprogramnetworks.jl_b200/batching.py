@@ -136,7 +136,17 @@ class BatchingEngine:
                 stacked = [np.vstack([r.args[k] for r in reqs]) for k in range(len(reqs[0].args))]
                 kw = reqs[0].kwargs
                 self.device_calls += 1
-                if kind == "verify":
+                remote = getattr(self.engine, "remote_call", None)
+                if remote is not None:
+                    # a worker process (workers.py): the regrouped call goes to the process that owns the GPU
+                    out = remote(kind, key, reqs[0].shared, stacked, kw)
+                    if kind in ("verify",):
+                        parts = self._split_tuple(out, sizes)
+                    elif kind == "gavi":
+                        parts = self._split_dict(out, sizes)
+                    else:
+                        parts = self._split_tuple((out,), sizes, single=True)
+                elif kind == "verify":
                     na = self._node_arrays.get(key)
                     if na is None:
                         from .engine import Engine, NodeArrays

@@ -25,7 +25,7 @@ def main():
     print(f"batched:    {B} full solves in {dt:.2f} s ({B/dt:.1f} equilibria/s), launches {eng.launches - l0}, {st}, identical to sequential: {same}", flush=True)
     for w in worker_counts:
         st = {}
-        t = time.time(); par = qpn_b200.solve_multilevel_workers(net, X, w, stats=st); dt = time.time() - t
+        t = time.time(); par = qpn_b200.solve_multilevel_workers(net, X, w, engine=eng, stats=st); dt = time.time() - t
         same = all(a["solved"] == b["solved"] and (not a["solved"] or np.array_equal(a["x_opt"], b["x_opt"])) for a, b in zip(res, par))
         print(f"{w:3d} workers: {B} full solves in {dt:.2f} s ({B/dt:.1f} equilibria/s), solved {np.mean([r['solved'] for r in par]):.3f}, {st}, identical to one process: {same}", flush=True)
 

@@ -269,6 +269,25 @@ def test_batched_state_machine_on_gpu(engine):
     check_batched_state_machine(engine)
 
 
+def test_multilevel_worker_pool_on_gpu(engine):
+    """Host worker processes served by ONE device engine (workers.py): identical to the one-process batch."""
+    import qpn_b200
+    rng = np.random.default_rng(12)
+    net = qpn_b200.setup("robust_avoid_simple", seed=3)
+    B = 21
+    X = np.tile(net.default_initialization, (B, 1)); X[:, 0:6] += 0.3 * rng.normal(size=(B, 6)); X[:, 6:12] = rng.uniform(-1, 1, (B, 6))
+    one = qpn_b200.solve_multilevel_batch(net, X, engine)
+    before = engine.launches
+    with qpn_b200.MultilevelPool(net, 4, engine=engine) as pool:
+        stats = {}
+        par = pool.solve(X, stats=stats)
+    assert engine.launches > before and stats["workers"] == 4 and stats["engine_calls"] > 0
+    for a, b in zip(one, par):
+        assert a["solved"] == b["solved"]
+        assert np.array_equal(a["x_opt"], b["x_opt"]) if a["solved"] else np.array_equal(a["x_fail"], b["x_fail"])
+    assert sum(r["solved"] for r in par) >= B - 2
+
+
 def test_solve_qp_implicit_bounds_convexity_on_gpu(engine):
     """Row A8 on the device engine: solve_qp, the batched bound LPs of implicit_bounds, check_qp_convexity."""
     from tests.test_multilevel_cpu import check_qp_row_a8

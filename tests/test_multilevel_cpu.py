@@ -260,18 +260,37 @@ def test_batching_engine_propagates_errors_and_survives_early_exits():
 
 
 def test_multilevel_batch_over_worker_processes():
-    """A multi-level batch sharded over host processes (contiguous shards, one engine handle each): same results,
-    in instance order, as the single-process batch; odd shard sizes."""
+    """A multi-level batch sharded over host processes served by ONE engine (workers.py): same results, in instance
+    order, as the single-process batch; odd shard sizes; the pool and its memos serve several batches."""
     rng = np.random.default_rng(9)
     net = qpn_b200.setup("robust_avoid_simple", seed=3)
     B = 7
     X = np.tile(net.default_initialization, (B, 1)); X[:, 0:6] += 0.3 * rng.normal(size=(B, 6)); X[:, 6:12] = rng.uniform(-1, 1, (B, 6))
     one = qpn_b200.solve_multilevel_batch(net, X, OracleEngine())
-    stats = {}
-    par = qpn_b200.solve_multilevel_workers(net, X, 3, engine_factory=OracleEngine, factory_args=(), stats=stats)
-    assert len(par) == B and stats["workers"] == 3 and stats["requests"] > 0
-    for a, b in zip(one, par):
-        assert a["solved"] == b["solved"] and "Sol" not in b
-        assert np.array_equal(a["x_opt"], b["x_opt"]) if a["solved"] else np.array_equal(a["x_fail"], b["x_fail"])
-    kept = qpn_b200.solve_multilevel_workers(net, X[:2], 5, engine_factory=OracleEngine, factory_args=(), keep_sol=True)
-    assert len(kept) == 2 and all("Sol" in r for r in kept if r["solved"])
+    with qpn_b200.MultilevelPool(net, 3, engine=OracleEngine()) as pool:
+        for rep in range(2):
+            stats = {}
+            par = pool.solve(X, stats=stats)
+            assert len(par) == B and stats["workers"] == 3 and 0 < stats["engine_calls"] <= stats["device_calls"] < stats["requests"]
+            for a, b in zip(one, par):
+                assert a["solved"] == b["solved"] and "Sol" not in b
+                assert np.array_equal(a["x_opt"], b["x_opt"]) if a["solved"] else np.array_equal(a["x_fail"], b["x_fail"])
+        kept = pool.solve(X[:2], keep_sol=True)                   # fewer instances than workers
+        assert len(kept) == 2 and all("Sol" in r for r in kept if r["solved"])
+    short = qpn_b200.solve_multilevel_workers(net, X[:3], 8, engine=OracleEngine())
+    assert [r["solved"] for r in short] == [r["solved"] for r in one[:3]]
+
+
+def test_worker_pool_reports_engine_errors():
+    """An engine error reaches the caller of pool.solve as it reaches the caller of the one-process batch (an
+    exception, not a hang), and the pool still shuts down."""
+    class Broken(OracleEngine):
+        def verify_solution(self, node, x, tol=1e-4):
+            raise ValueError("device lost")
+    net = qpn_b200.setup("simple_bilevel")
+    X = np.array([[1.0, 2.0, 0.0, 0.0], [0.5, -1.0, 0.0, 0.0], [2.0, 0.1, 0.0, 0.0]])
+    with pytest.raises(Exception, match="device lost"):
+        qpn_b200.solve_multilevel_batch(net, X, Broken())
+    with qpn_b200.MultilevelPool(net, 2, engine=Broken()) as pool:
+        with pytest.raises(RuntimeError, match="device lost"):
+            pool.solve(X)
