@@ -35,7 +35,13 @@ __device__ __noinline__ void tab_start_plan_core(Tab t, const PlanDesc& P, const
     const int n = P.n, i = threadIdx.x;
     const int ldr = t.ldr;
     if (i < n) zb[i] = fmin(fmax(z0[i], t.l()[i]), t.u()[i]);
-    for (int e = i; e < n * ldr; e += blockDim.x) t.T()[e] = P.T0[e];
+    if ((reinterpret_cast<uintptr_t>(P.T0) & 15) == 0) {          // ldr is even and T() is 16-byte aligned: 128-bit copies
+        const double2* src = reinterpret_cast<const double2*>(P.T0);
+        double2* dst = reinterpret_cast<double2*>(t.T());
+        for (int e = i; e < (n * ldr) >> 1; e += blockDim.x) dst[e] = src[e];
+    } else {
+        for (int e = i; e < n * ldr; e += blockDim.x) t.T()[e] = P.T0[e];
+    }
     for (int v = i; v <= 2 * n; v += blockDim.x) { t.rowof()[v] = -1; t.colof()[v] = -1; }
     QPN_SYNC();
     double zi = 0.0;
@@ -50,11 +56,18 @@ __device__ __noinline__ void tab_start_plan_core(Tab t, const PlanDesc& P, const
     }
     QPN_SYNC();
     if (i < n) {
+        // The specification skips zero entries of B^-1; with a finite r (finite q, z0 clamped to finite bounds or finite
+        // itself) fma(0, r_k, acc) == acc bit for bit (acc starts at +0.0 and can never become -0.0), so the branch-free
+        // chain gives the same value and lets the loads run ahead of the dependent fma chain.
         double acc = 0.0;
-        for (int k = 0; k < n; ++k) {
-            const double pik = P.PT[(size_t)k * n + i];
-            if (pik != 0.0) acc = fma(pik, t.rr()[k], acc);
+        const double* pt = P.PT + i;
+        const double* rr = t.rr();
+        int k = 0;
+        for (; k + 4 <= n; k += 4) {
+            const double p0 = pt[(size_t)k * n], p1 = pt[(size_t)(k + 1) * n], p2 = pt[(size_t)(k + 2) * n], p3 = pt[(size_t)(k + 3) * n];
+            acc = fma(p0, rr[k], acc); acc = fma(p1, rr[k + 1], acc); acc = fma(p2, rr[k + 2], acc); acc = fma(p3, rr[k + 3], acc);
         }
+        for (; k < n; ++k) acc = fma(pt[(size_t)k * n], rr[k], acc);
         t.T()[(size_t)i * ldr + P.tcol0] = acc;
         const int rv = P.rowvar0[i];
         t.rowvar()[i] = rv; t.rowof()[rv] = i;
