@@ -83,11 +83,13 @@ def vertices_of_slice(piece, z, w, nv, lp, max_dim=6):
     at the current primal point.  Only needed when exploration_vertices > 0; enumerated as the
     basic solutions of the sliced system (small dimensions only)."""
     n = len(z)
+    dim = n - nv
+    if dim == 0 or dim > max_dim:                 # decided by the sizes alone: no need to slice first
+        return []
     fixed = {j: z[j] for j in range(nv)}
     fixed.update({n + j: w[j] for j in range(len(w))})
     S = ph.simplify(ph.poly_slice(piece, fixed))
-    dim = n - nv
-    if dim == 0 or dim > max_dim or len(S) == 0:
+    if len(S) == 0:
         return []
     rows = []
     for i in range(len(S)):
