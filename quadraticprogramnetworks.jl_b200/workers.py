@@ -10,6 +10,11 @@ GPU.  There is one engine handle (one CUDA context, one set of device buffers) h
 problem data of a call (a node's matrices, a GAVI) crosses the pipe once per worker and is referred to by a small
 integer afterwards.  The workers' piece / predicate memos live as long as the pool, like a resident level.
 
+Calls are merged across workers: one dispatcher thread owns the engine; while a device call runs, the calls the other
+workers send queue up, and the dispatcher then takes ALL of them, groups those with the same (kind, problem data,
+options) -- the workers walk the same network, so the popular ones coincide -- and issues one batched device call
+per group.  Nothing waits for a merge partner: an idle engine serves a lone call at once.
+
 Every instance is solved by the same code against the same device engine as in one process, so the results are
 identical (tests/test_multilevel_cpu.py, tests/test_gpu_parity.py).
 """
@@ -68,6 +73,14 @@ def _pool_worker(conn, qpn, chunk):
     conn.close()
 
 
+class _Pending:
+    __slots__ = ("kind", "gid", "stacked", "kwargs", "result", "error", "ready")
+
+    def __init__(self, kind, gid, stacked, kwargs):
+        self.kind, self.gid, self.stacked, self.kwargs = kind, gid, stacked, kwargs
+        self.result, self.error, self.ready = None, None, threading.Event()
+
+
 class MultilevelPool:
     """`workers` host processes for the multi-level batches of one QPNet, all served by one engine."""
 
@@ -76,8 +89,8 @@ class MultilevelPool:
         self.engine = engine if engine is not None else Engine(device)
         self._device_engine = isinstance(self.engine, Engine)
         self.workers = max(1, int(workers))
-        self.lock = threading.Lock()                     # calls on a handle are serialised by the caller (include/qpn_cuda.h)
-        self.device_calls = 0
+        self.device_calls = 0            # engine calls issued (after merging)
+        self.worker_calls = 0            # calls received from the workers
         ctx = mp.get_context("spawn")                    # spawn: the children must not inherit the CUDA context
         self.conns, self.procs = [], []
         for _ in range(self.workers):
@@ -86,7 +99,29 @@ class MultilevelPool:
             p.start()
             there.close()
             self.conns.append(here); self.procs.append(p)
-        self._shared = [dict() for _ in range(self.workers)]     # per worker: ident -> marshalled problem data
+        self._ident = [dict() for _ in range(self.workers)]      # per worker: its ident -> global id of the problem data
+        self._gid, self._data = {}, []                           # bytes key -> global id ; global id -> marshalled data
+        self._meta = threading.Lock()
+        self._queue, self._cv, self._stop = [], threading.Condition(), False
+        self._dispatcher = threading.Thread(target=self._dispatch, daemon=True)
+        self._dispatcher.start()
+
+    # ---- problem data: crosses the pipe once per worker, marshalled once per pool --------------------------
+    def _register(self, w, kind, ident, shared):
+        from .batching import _gavi_key, _key
+        if kind == "verify":
+            key = ("n", _key(*shared))
+        elif kind in ("gavi", "comp"):
+            key = ("g", _gavi_key(shared))
+        else:
+            key = ("p", _key(*[a for P in shared for a in P]))
+        with self._meta:
+            gid = self._gid.get(key)
+            if gid is None:
+                gid = self._gid[key] = len(self._data)
+                self._data.append(self._marshal(kind, shared))
+            self._ident[w][(kind, ident)] = gid
+        return gid
 
     def _marshal(self, kind, shared):
         if not self._device_engine:
@@ -98,20 +133,56 @@ class MultilevelPool:
             return GaviArrays(shared)
         return shared
 
+    # ---- the one thread that talks to the engine (calls on a handle are serialised, include/qpn_cuda.h) -----
+    def _dispatch(self):
+        while True:
+            with self._cv:
+                while not self._queue and not self._stop:
+                    self._cv.wait()
+                if self._stop and not self._queue:
+                    return
+                batch, self._queue = self._queue, []
+            groups = {}
+            for r in batch:
+                groups.setdefault((r.kind, r.gid, tuple(sorted(r.kwargs.items()))), []).append(r)
+            for (kind, gid, _), reqs in groups.items():
+                try:
+                    data = self._data[gid]
+                    sizes = [len(r.stacked[0]) for r in reqs]
+                    args = [np.vstack([r.stacked[k] for r in reqs]) if len(reqs) > 1 else reqs[0].stacked[k]
+                            for k in range(len(reqs[0].stacked))]
+                    kw = reqs[0].kwargs
+                    self.device_calls += 1
+                    if kind == "verify":
+                        out = self.engine.verify_solution(data, args[0], **kw)
+                        parts = _split(out, sizes)
+                    elif kind == "gavi":
+                        out = self.engine.gavi_solve(data, args[0], args[1], **kw)
+                        keys = list(out)
+                        parts = [dict(zip(keys, p)) for p in _split(tuple(out[k] for k in keys), sizes)]
+                    elif kind == "comp":
+                        parts = [p[0] for p in _split((self.engine.comp_indices(data, args[0], args[1], **kw),), sizes)]
+                    else:
+                        parts = [p[0] for p in _split((self.engine.halfspace_in(data, args[0], **kw),), sizes)]
+                    for r, part in zip(reqs, parts):
+                        r.result = part
+                except Exception as e:                   # noqa: BLE001 -- delivered to every worker of the group
+                    for r in reqs:
+                        r.error = f"{type(e).__name__}: {e}"
+                for r in reqs:
+                    r.ready.set()
+
     def _execute(self, w, kind, ident, shared, stacked, kwargs):
-        table = self._shared[w]
-        if shared is not None:
-            table[ident] = self._marshal(kind, shared)
-        data = table[ident]
-        with self.lock:
-            self.device_calls += 1
-            if kind == "verify":
-                return self.engine.verify_solution(data, stacked[0], **kwargs)
-            if kind == "gavi":
-                return self.engine.gavi_solve(data, stacked[0], stacked[1], **kwargs)
-            if kind == "comp":
-                return self.engine.comp_indices(data, stacked[0], stacked[1], **kwargs)
-            return self.engine.halfspace_in(data, stacked[0], **kwargs)
+        gid = self._register(w, kind, ident, shared) if shared is not None else self._ident[w][(kind, ident)]
+        req = _Pending(kind, gid, stacked, kwargs)
+        with self._cv:
+            self.worker_calls += 1
+            self._queue.append(req)
+            self._cv.notify()
+        req.ready.wait()
+        if req.error is not None:
+            raise RuntimeError(req.error)
+        return req.result
 
     def _serve(self, w, X, keep_sol, out):
         conn = self.conns[w]
@@ -126,7 +197,7 @@ class MultilevelPool:
                 try:
                     conn.send(("ret", self._execute(w, *msg[1:])))
                 except Exception as e:                   # noqa: BLE001 -- delivered to the instances that asked
-                    conn.send(("err", f"{type(e).__name__}: {e}"))
+                    conn.send(("err", str(e)))
         except (EOFError, OSError) as e:
             out[w] = RuntimeError(f"worker {w} died: {e}")
 
@@ -136,7 +207,7 @@ class MultilevelPool:
         X = np.ascontiguousarray(np.atleast_2d(X), dtype=np.float64)
         used = min(self.workers, len(X))
         out = [None] * used
-        calls0 = self.device_calls
+        calls0, wcalls0 = self.device_calls, self.worker_calls
         threads = [threading.Thread(target=self._serve, args=(w, X[slice(*shard_range(len(X), w, used))], keep_sol, out), daemon=True)
                    for w in range(used)]
         for t in threads:
@@ -151,6 +222,7 @@ class MultilevelPool:
                 for k, v in st.items():
                     stats[k] = stats.get(k, 0) + v
             stats["workers"] = used
+            stats["worker_calls"] = self.worker_calls - wcalls0
             stats["engine_calls"] = self.device_calls - calls0
         return [r for part, _ in out for r in part]
 
@@ -167,12 +239,25 @@ class MultilevelPool:
         for c in self.conns:
             c.close()
         self.conns, self.procs = [], []
+        with self._cv:
+            self._stop = True
+            self._cv.notify()
+        self._dispatcher.join(timeout=10)
 
     def __enter__(self):
         return self
 
     def __exit__(self, *exc):
         self.close()
+
+
+def _split(arrays, sizes):
+    """Row ranges of every array of a batched result, one tuple per request."""
+    parts, o = [], 0
+    for sz in sizes:
+        parts.append(tuple(a[o:o + sz] if isinstance(a, np.ndarray) else a for a in arrays))
+        o += sz
+    return parts
 
 
 def solve_multilevel_workers(qpn, X, workers, engine=None, device=0, chunk=256, stats=None, keep_sol=False):

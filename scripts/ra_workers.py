@@ -14,7 +14,7 @@ def main():
     eng = qpn_b200.Engine(0)
     for w in [int(a) for a in sys.argv[2:]]:
         t = time.time()
-        with qpn_b200.MultilevelPool(net, w, engine=eng) as pool:
+        with qpn_b200.MultilevelPool(net, w, engine=eng, chunk=int(os.environ.get('QPN_CHUNK', '256'))) as pool:
             pool.solve(X[:4 * w]); t_up = time.time() - t                     # processes up, memos warm
             st = {}
             t = time.time(); par = pool.solve(X, stats=st); dt = time.time() - t
