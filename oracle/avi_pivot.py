@@ -235,6 +235,20 @@ class _Tab:
                     acc = fma(pik, self.r[k], acc)
             self.T[i, tc] = acc
 
+    def freeze(self):
+        """Rows that hold a FREE variable after phase 0 are frozen.  A free basic never blocks a ratio test, never
+        leaves the basis and is no candidate row of the crash, so no later decision reads its row: only the final z
+        does.  The row as it stands now is a valid equation between the variables whatever pivots follow,
+            x_B[i] = beta0[i] - sum_j T0[i, j] * (x(colvar0[j]) - nbval0[j]),
+        and `solution` evaluates exactly that (sequential fma over the columns) instead of carrying the row through
+        every later pivot.  Engines therefore leave these rows out of their pivot sweeps altogether."""
+        n = self.n
+        self.frozen = [i for i in range(n) if self.rowvar[i] < n and self.is_free(self.rowvar[i])]
+        self.T0 = self.T[self.frozen].copy()
+        self.beta0 = self.beta[self.frozen].copy()
+        self.colvar0 = list(self.colvar)
+        self.nbval0 = self.nbval.copy()
+
     def crash(self):
         n = self.n
         # phase 0: free variables exchange against rows of free variables only.  Nothing here
@@ -251,6 +265,7 @@ class _Tab:
                 self.zst[i] = BASIC
         if self.pivots > piv0:
             self.recompute_tcol()
+        self.freeze()
         # phase 1: everything still floating, against any artificial row
         for i in range(n):
             if self.zst[i] != FLOAT:
@@ -369,14 +384,23 @@ class _Tab:
                     return FAILURE             # blocked by an equation that cannot move
                 ent, sigma = k, (+1.0 if self.zst[k] == AT_L else -1.0)
 
+    def value(self, var):
+        if var in self.rowvar:
+            return self.beta[self.rowvar.index(var)]
+        return self.nbval[self.colvar.index(var)]
+
     def solution(self):
         n = self.n
         z = np.empty(n)
         for i in range(n):
-            if i in self.rowvar:
-                z[i] = self.beta[self.rowvar.index(i)]
-            else:
-                z[i] = self.nbval[self.colvar.index(i)]
+            z[i] = self.value(i)
+        # frozen rows (see freeze): their free variables from the phase-0 equations.  Every variable that was
+        # nonbasic then is nonbasic or basic in an unfrozen row now, so `value` never reads a frozen row.
+        for idx, i in enumerate(self.frozen):
+            acc = self.beta0[idx]
+            for j in range(n + 1):
+                acc = fma(-self.T0[idx, j], self.value(self.colvar0[j]) - self.nbval0[j], acc)
+            z[self.rowvar[i]] = acc
         return z
 
     def basis_codes(self):

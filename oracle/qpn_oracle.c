@@ -48,6 +48,10 @@ typedef struct {
     int *rowof, *colof;     /* inverse maps, -1 when absent */
     int8_t *zst;
     int pivots;
+    /* frozen rows (see freeze): rows holding a FREE variable after phase 0 */
+    int nfrozen;
+    int *frozen, *colvar0;  /* row ids (n), column variables at the freeze (n + 1) */
+    double *T0, *beta0, *nbval0;   /* nfrozen x (n+1) row-major, nfrozen, n + 1 */
 } tab_t;
 
 /* ---- avi_scratch.jl:17-50: normal-map start ------------------------------ */
@@ -67,6 +71,12 @@ static void tab_init(tab_t *t, int n, const double *M, const double *q, const do
     t->colof = iwork;
     t->zst = bwork;
     t->pivots = 0;
+    t->nfrozen = 0;
+    t->frozen = t->colof + 2 * n + 1;
+    t->colvar0 = t->frozen + n;
+    t->nbval0 = zb + n;
+    t->beta0 = t->nbval0 + n + 1;
+    t->T0 = t->beta0 + n;
     for (int i = 0; i < n; ++i) zb[i] = fmin(fmax(z0[i], l[i]), u[i]);
     for (int i = 0; i < n; ++i) {
         double acc = 0.0;
@@ -238,6 +248,39 @@ static void recompute_tcol(tab_t *t) {
     for (int i = 0; i < n; ++i) t->T[(size_t)tc * n + i] = out[i];
 }
 
+/* Rows that hold a FREE variable after phase 0 are frozen: a free basic never blocks a ratio test, never
+ * leaves the basis and is no candidate row of the crash, so no later decision reads its row -- only the final z
+ * does.  The row as it stands now stays a valid equation between the variables,
+ *     x_B[i] = beta0[i] - sum_j T0[i][j] * (x(colvar0[j]) - nbval0[j]),
+ * and the solve evaluates exactly that at the end (frozen_values) instead of carrying the row through every
+ * later pivot.  Same statement as oracle/avi_pivot.py: freeze / solution. */
+static void freeze(tab_t *t) {
+    int n = t->n, nf = 0;
+    for (int i = 0; i < n; ++i)
+        if (t->rowvar[i] < n && t->l[t->rowvar[i]] == -INFINITY && t->u[t->rowvar[i]] == INFINITY) t->frozen[nf++] = i;
+    t->nfrozen = nf;
+    for (int j = 0; j <= n; ++j) { t->colvar0[j] = t->colvar[j]; t->nbval0[j] = t->nbval[j]; }
+    for (int f = 0; f < nf; ++f) {
+        int i = t->frozen[f];
+        t->beta0[f] = t->beta[i];
+        for (int j = 0; j <= n; ++j) t->T0[(size_t)f * (n + 1) + j] = t->T[(size_t)j * n + i];
+    }
+}
+
+static double var_value(const tab_t *t, int v) {
+    return t->rowof[v] >= 0 ? t->beta[t->rowof[v]] : t->nbval[t->colof[v]];
+}
+
+static void frozen_values(const tab_t *t, double *z) {
+    int n = t->n;
+    for (int f = 0; f < t->nfrozen; ++f) {
+        double acc = t->beta0[f];
+        for (int j = 0; j <= n; ++j)
+            acc = fma(-t->T0[(size_t)f * (n + 1) + j], var_value(t, t->colvar0[j]) - t->nbval0[j], acc);
+        z[t->rowvar[t->frozen[f]]] = acc;
+    }
+}
+
 /* ---- crash: bring interior / free variables into the basis -------------------- */
 static void crash(tab_t *t) {
     int n = t->n;
@@ -251,6 +294,7 @@ static void crash(tab_t *t) {
         if (rho >= 0) { pivot(t, rho, c); t->zst[i] = BASIC; }
     }
     if (t->pivots > piv0) recompute_tcol(t);
+    freeze(t);
     /* phase 1: everything still floating, against any artificial row */
     for (int i = 0; i < n; ++i) {
         if (t->zst[i] != FLOATING) continue;
@@ -364,8 +408,8 @@ int qpo_check_avi(int n, const double *M, const double *q, const double *l, cons
     return bad;
 }
 
-size_t qpo_avi_work_doubles(int n) { return (size_t)n * (n + 1) + 5 * (size_t)n + 2; }
-size_t qpo_avi_work_ints(int n) { return 6 * (size_t)n + 3; }
+size_t qpo_avi_work_doubles(int n) { return 2 * (size_t)n * (n + 1) + 7 * (size_t)n + 3; }
+size_t qpo_avi_work_ints(int n) { return 8 * (size_t)n + 4; }
 
 /* avi.jl:63-77 with q = N*w + o already formed.  basis: 1 at lower, 2 interior/basic,
  * 3 at upper, 4 fixed. */
@@ -388,6 +432,7 @@ int qpo_avi_solve(int n, const double *M, const double *q, const double *l, cons
             basis[i] = (l[i] == u[i]) ? 4 : (t.rowof[i] >= 0 || t.zst[i] == FLOATING) ? 2
                        : (t.zst[i] == AT_L ? 1 : 3);
     }
+    frozen_values(&t, z);
     if (st == QPO_SUCCESS && qpo_check_avi(n, M, q, l, u, z, 1e-6, NULL) > 0) st = QPO_FAILURE;
     *status = st;
     *pivots = t.pivots;

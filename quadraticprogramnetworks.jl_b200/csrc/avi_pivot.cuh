@@ -29,7 +29,11 @@ constexpr double PIV_TOL = 1e-9;   // smallest |pivot| accepted in a crash excha
 constexpr double D_TOL = 1e-10;    // |direction entry| treated as zero in ratio tests
 constexpr double TIE_TOL = 1e-10;  // ratios within this (relative) of the minimum tie
 
-enum : int8_t { AT_L = 0, AT_U = 1, FLOATING = 2, BASIC = 3 };
+enum : int8_t { AT_L = 0, AT_U = 1, FLOATING = 2, BASIC = 3, FROZEN = 4 };
+// FROZEN: a free variable that phase 0 of the crash made basic.  It never blocks a ratio test, never leaves the
+// basis and its row is no candidate of the crash, so no decision reads that row: the row stays as it was after
+// phase 0 (it is left out of every later pivot sweep) and the variable's final value is evaluated from it once,
+// at the end (oracle/avi_pivot.py: freeze / solution).  Everywhere else FROZEN reads like BASIC.
 enum : int { ST_SUCCESS = 1, ST_RAY_TERM = 2, ST_MAX_ITERS = 3, ST_FAILURE = 4 };
 
 #define QPN_INF CUDART_INF
@@ -77,10 +81,12 @@ extern __shared__ __align__(16) unsigned char qpn_smem[];
 // Bytes of a workspace with room for `nmax` rows, a tableau buffer of `tdoubles` doubles and
 // rows of up to `ldrmax` doubles.  One workspace serves several solves of different shapes
 // (tab_shape) inside one kernel.
-__host__ __device__ __forceinline__ size_t tab_smem_bytes_ex(int nmax, size_t tdoubles, int ldrmax) {
+// fz = 1: room for the freeze record (column variables / nonbasic values after phase 0); the global-memory
+// engine keeps that record in its slot instead (fz = 0).
+__host__ __device__ __forceinline__ size_t tab_smem_bytes_ex(int nmax, size_t tdoubles, int ldrmax, int fz = 1) {
     tdoubles = (tdoubles + 1) & ~(size_t)1;
-    size_t d = tdoubles + 2 * (size_t)ldrmax + 4 * (size_t)nmax + 36;
-    size_t i = (size_t)nmax + ldrmax + 2 * (size_t)(2 * nmax + 1) + 36;
+    size_t d = tdoubles + (2 + (size_t)fz) * (size_t)ldrmax + 4 * (size_t)nmax + 36;
+    size_t i = (size_t)nmax + (1 + (size_t)fz) * ldrmax + 2 * (size_t)(2 * nmax + 1) + 36;
     size_t b = (size_t)nmax;
     return d * 8 + ((i * 4 + 15) / 16) * 16 + ((b + 15) / 16) * 16;
 }
@@ -98,31 +104,39 @@ struct Tab {
     int ldr;        // row stride of T in doubles for the current solve
     int ncol;       // live columns [0, ncol); uniform across the CTA
     int pivots;     // uniform across the CTA
+    int fz;         // 1: the freeze record lives in this workspace (0: elsewhere, global-memory engine)
+    int ncol0;      // live columns when the rows of free basics were frozen (uniform)
 
+    __device__ __forceinline__ int dl() const { return (2 + fz) * ldrmax; }               // doubles of the per-column vectors
+    __device__ __forceinline__ int il() const { return (1 + fz) * ldrmax; }               // ints of the per-column vectors
     __device__ __forceinline__ double* dbl(int off) const { return reinterpret_cast<double*>(qpn_smem + base) + off; }
     __device__ __forceinline__ double* T() const { return dbl(0); }                       // n x ldr, row-major, negated
     __device__ __forceinline__ double* prow() const { return dbl(td); }                   // ldr  scaled pivot row
     __device__ __forceinline__ double* nbval() const { return dbl(td + ldrmax); }         // ldr  nonbasic values
-    __device__ __forceinline__ double* beta() const { return dbl(td + 2 * ldrmax); }      // n    basic values
-    __device__ __forceinline__ double* l() const { return dbl(td + 2 * ldrmax + nmax); }
-    __device__ __forceinline__ double* u() const { return dbl(td + 2 * ldrmax + 2 * nmax); }
-    __device__ __forceinline__ double* rr() const { return dbl(td + 2 * ldrmax + 3 * nmax); }   // residual r at the start
-    __device__ __forceinline__ double* red_d() const { return dbl(td + 2 * ldrmax + 4 * nmax); }  // 36
-    __device__ __forceinline__ int* ints() const { return reinterpret_cast<int*>(dbl(td + 2 * ldrmax + 4 * nmax + 36)); }
+    __device__ __forceinline__ double* nbval0() const { return dbl(td + 2 * ldrmax); }    // ldr  (fz) nonbasic values at the freeze
+    __device__ __forceinline__ double* beta() const { return dbl(td + dl()); }            // n    basic values
+    __device__ __forceinline__ double* l() const { return dbl(td + dl() + nmax); }
+    __device__ __forceinline__ double* u() const { return dbl(td + dl() + 2 * nmax); }
+    __device__ __forceinline__ double* rr() const { return dbl(td + dl() + 3 * nmax); }   // residual r at the start
+    __device__ __forceinline__ double* red_d() const { return dbl(td + dl() + 4 * nmax); }  // 36
+    __device__ __forceinline__ int* ints() const { return reinterpret_cast<int*>(dbl(td + dl() + 4 * nmax + 36)); }
     __device__ __forceinline__ int* rowvar() const { return ints(); }                     // n     z_i = i, w_i = n+i, t = 2n
     __device__ __forceinline__ int* colvar() const { return ints() + nmax; }              // ldr
-    __device__ __forceinline__ int* rowof() const { return ints() + nmax + ldrmax; }      // 2n+1  row of a variable or -1
-    __device__ __forceinline__ int* colof() const { return ints() + nmax + ldrmax + 2 * nmax + 1; }   // 2n+1 (-1: basic or dead)
-    __device__ __forceinline__ int* red_i() const { return ints() + nmax + ldrmax + 2 * (2 * nmax + 1); }   // 36
-    __device__ __forceinline__ int8_t* zst() const {                                      // n  AT_L / AT_U / FLOATING / BASIC
-        const int ib = nmax + ldrmax + 2 * (2 * nmax + 1) + 36;
+    __device__ __forceinline__ int* colvar0() const { return ints() + nmax + ldrmax; }    // ldr  (fz) column variables at the freeze
+    __device__ __forceinline__ int* rowof() const { return ints() + nmax + il(); }        // 2n+1  row of a variable or -1
+    __device__ __forceinline__ int* colof() const { return ints() + nmax + il() + 2 * nmax + 1; }   // 2n+1 (-1: basic or dead)
+    __device__ __forceinline__ int* red_i() const { return ints() + nmax + il() + 2 * (2 * nmax + 1); }   // 36
+    __device__ __forceinline__ int8_t* zst() const {                                      // n  AT_L / AT_U / FLOATING / BASIC / FROZEN
+        const int ib = nmax + il() + 2 * (2 * nmax + 1) + 36;
         return reinterpret_cast<int8_t*>(reinterpret_cast<unsigned char*>(ints()) + ((ib * 4 + 15) / 16) * 16);
     }
+    // entry (i, j) of a frozen row: in place (the frozen rows of the shared-memory tableau are simply never swept)
+    __device__ __forceinline__ double frozen_entry(int i, int j) const { return T()[(size_t)i * ldr + j]; }
 };
 
-__device__ __forceinline__ void tab_carve_ex(Tab& t, int nmax, size_t tdoubles, int ldrmax, int base_off) {
+__device__ __forceinline__ void tab_carve_ex(Tab& t, int nmax, size_t tdoubles, int ldrmax, int base_off, int fz = 1) {
     t.base = base_off; t.nmax = nmax; t.ldrmax = ldrmax; t.td = (int)((tdoubles + 1) & ~(size_t)1);
-    t.n = nmax; t.ldr = ldrmax; t.ncol = 0; t.pivots = 0;
+    t.n = nmax; t.ldr = ldrmax; t.ncol = 0; t.pivots = 0; t.fz = fz; t.ncol0 = 0;
 }
 __device__ __forceinline__ void tab_carve(Tab& t, int n, int cap, int base_off) {
     tab_carve_ex(t, n, (size_t)n * row_stride(cap), row_stride(cap), base_off);
@@ -216,6 +230,14 @@ __device__ __forceinline__ double block_min(const Tab& t, double v) {   // v >= 
 template <class TT>
 __device__ __forceinline__ bool is_free_var(const TT& t, int k) { return t.l()[k] == -QPN_INF && t.u()[k] == QPN_INF; }
 
+// Does row i hold a frozen free variable?  (reads rowvar[i] and zst: call it before the barrier that precedes a
+// rewrite of either)
+template <class TT>
+__device__ __forceinline__ bool frozen_row(const TT& t, int i) {
+    const int v = t.rowvar()[i];
+    return v < t.n && t.zst()[v] == FROZEN;
+}
+
 template <class TT>
 __device__ __forceinline__ void var_bounds(const TT& t, int var, double& lo, double& up) {
     const int n = t.n;
@@ -236,7 +258,7 @@ __device__ __forceinline__ bool artificial_row(const TT& t, int i) {
     const int k = v - n;
     if (t.l()[k] == t.u()[k]) return false;
     const int8_t s = t.zst()[k];
-    return s == FLOATING || s == BASIC;
+    return s >= FLOATING;                  // FLOATING, BASIC or FROZEN
 }
 
 // ---- start of the normal-map path (avi_scratch.jl:17-50) -----------------------------
@@ -298,13 +320,14 @@ __device__ __noinline__ int pivot_core(Tab t, int rho, int c, bool compact) {
         t.prow()[j] = v;
         if (j < ncol && j != c) T[(size_t)rho * ldr + j] = v;
     }
-    const double d = (i < n) ? T[(size_t)i * ldr + c] : 0.0;
+    const bool live = (i < n) && !frozen_row(t, i);         // frozen rows are never swept (read before the barrier)
+    const double d = live ? T[(size_t)i * ldr + c] : 0.0;
     const int lv = t.rowvar()[rho];                         // leaving variable (read before the barrier)
     // A slack of a free variable never comes back: its column leaves the live range.
     const bool dead = compact && lv >= n && lv < 2 * n && is_free_var(t, lv - n);
     const int last = ncol - 1;
     QPN_SYNC();
-    if (i < n) {
+    if (live) {
         double* row = T + (size_t)i * ldr;
         const bool isrho = (i == rho);
         row[c] = isrho ? t.prow()[c] : 0.0;               // then column c follows the common formula
@@ -401,7 +424,7 @@ __device__ __forceinline__ double ratio_test(const Tab& t, int c, double sigma, 
 __device__ __forceinline__ void move(Tab& t, int c, double sigma, double theta) {
     if (theta == 0.0) return;
     const int i = threadIdx.x;
-    if (i < t.n) {
+    if (i < t.n && !frozen_row(t, i)) {                     // a frozen row keeps the basic value it had at the freeze
         const double ci = t.T()[(size_t)i * t.ldr + c];
         if (ci != 0.0) t.beta()[i] = fma(-(sigma * theta), ci, t.beta()[i]);
     }
@@ -499,6 +522,48 @@ __device__ __forceinline__ void compact_dead(Tab& t) {
     QPN_SYNC();
 }
 
+__device__ __forceinline__ void freeze_hook(Tab&) {}
+
+// ---- freeze (oracle/avi_pivot.py: freeze) ------------------------------------------------
+// Called where phase 0 of the crash has just ended (in this solve or in its plan): marks the free basics FROZEN
+// and records which variable sits in which live column and at what value.  Ends with a barrier.
+template <class TT>
+__device__ __forceinline__ void freeze(TT& t) {
+    const int n = t.n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int v = t.rowvar()[i];
+        if (v < n && is_free_var(t, v)) t.zst()[v] = FROZEN;
+    }
+    for (int j = threadIdx.x; j < t.ncol; j += blockDim.x) { t.colvar0()[j] = t.colvar()[j]; t.nbval0()[j] = t.nbval()[j]; }
+    t.ncol0 = t.ncol;
+    freeze_hook(t);
+    QPN_SYNC();
+}
+
+// Final values of the frozen variables from their phase-0 rows:
+//   x_B[i] = beta[i] - sum_j T0[i][j] * (x(colvar0[j]) - nbval0[j]),  sequential fma over the live columns of the freeze.
+// (Columns that were already dead then carry a variable that stays at its value: they add fma(., 0, acc) = acc in the
+// specification and are simply absent here.)  `dx`: ncol0 doubles of scratch.  Ends with a barrier.
+template <class TT>
+__device__ __forceinline__ void frozen_values(TT& t, double* dx) {
+    const int n = t.n, nc0 = t.ncol0;
+    for (int j = threadIdx.x; j < nc0; j += blockDim.x) {
+        const int v = t.colvar0()[j];
+        const int r = t.rowof()[v], c = t.colof()[v];
+        // (a variable of a live column of the freeze is no slack of a free variable, so it cannot have retired since;
+        // the guard only keeps a corrupted state from indexing out of range)
+        dx[j] = (r >= 0 ? t.beta()[r] : c >= 0 ? t.nbval()[c] : t.nbval0()[j]) - t.nbval0()[j];
+    }
+    QPN_SYNC();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        if (!frozen_row(t, i)) continue;
+        double acc = t.beta()[i];
+        for (int j = 0; j < nc0; ++j) acc = fma(-t.frozen_entry(i, j), dx[j], acc);
+        t.beta()[i] = acc;                                // nobody reads a frozen row's beta in this pass
+    }
+    QPN_SYNC();
+}
+
 // ---- crash: bring interior / free variables into the basis ----------------------------
 template <class TT>
 __device__ __forceinline__ void crash(TT& t, bool from_plan) {
@@ -516,6 +581,7 @@ __device__ __forceinline__ void crash(TT& t, bool from_plan) {
         }
         if (t.pivots > piv0) { recompute_tcol(t); compact_dead(t); }
     }
+    freeze(t);
     // phase 1: everything still floating, against any artificial row
     for (int i = 0; i < n; ++i) {
         if (t.zst()[i] != FLOATING) continue;
@@ -637,6 +703,7 @@ __device__ __noinline__ PivotResult avi_pivot_run(Tab t, int max_pivots, bool fr
     repair(t);
     PivotResult out;
     out.st = lemke(t, max_pivots);
+    frozen_values(t, t.prow());                           // prow is free between pivots
     out.zi = 0.0; out.code = 0; out.pivots = t.pivots;
     const int i = threadIdx.x;
     if (i < t.n) {

@@ -59,6 +59,9 @@ struct BigTab {
     int stage_off, stage_cap;   // spare dynamic shared memory (byte offset, doubles): the queue's pivot rows are staged there for a flush
     int npend;          // queued pivots (block-uniform)
     int prw[QPN_BIG_PEND], pcl[QPN_BIG_PEND];    // their pivot rows / entering columns
+    double* nbv0;       // freeze record (avi_pivot.cuh: freeze), in the slot: nonbasic values ...
+    int* cv0;           // ... and column variables at the freeze
+    int ncol0;
 
     __device__ __forceinline__ double* prow() const { return v.prow(); }
     __device__ __forceinline__ double* nbval() const { return v.nbval(); }
@@ -72,25 +75,33 @@ struct BigTab {
     __device__ __forceinline__ int* colof() const { return v.colof(); }
     __device__ __forceinline__ int8_t* zst() const { return v.zst(); }
     __device__ __forceinline__ double* dcol() const { return reinterpret_cast<double*>(qpn_smem + dcol_off); }
+    __device__ __forceinline__ double* nbval0() const { return nbv0; }
+    __device__ __forceinline__ int* colvar0() const { return cv0; }
+    // a frozen row is never swept and is never part of a queued update: its slot entries are those of the freeze
+    __device__ __forceinline__ double frozen_entry(int i, int j) const { return Tg[(size_t)i * ldr + j]; }
 };
 
 // Shared-memory bytes of the vectors of a big tableau with up to nmax rows (ldr of the full
 // n x (n+1) shape) plus the column cache.
 __host__ __device__ __forceinline__ size_t big_smem_bytes(int nmax) {
-    return tab_smem_bytes_ex(nmax, 0, row_stride(nmax + 1)) + 8 * (size_t)((nmax + 1) & ~1);
+    return tab_smem_bytes_ex(nmax, 0, row_stride(nmax + 1), 0) + 8 * (size_t)((nmax + 1) & ~1);
 }
 // Doubles of one global workspace slot.
 __host__ __device__ __forceinline__ size_t big_slot_doubles(int nmax) {
-    return (size_t)nmax * row_stride(nmax + 1) + (size_t)QPN_BIG_PEND * ((size_t)((nmax + 1) & ~1) + row_stride(nmax + 1));
+    return (size_t)nmax * row_stride(nmax + 1) + (size_t)QPN_BIG_PEND * ((size_t)((nmax + 1) & ~1) + row_stride(nmax + 1)) +
+           row_stride(nmax + 1) + (size_t)row_stride(nmax + 1) / 2 + 1;          // + the freeze record (doubles, ints); stride/2 is odd: the slot stays a multiple of 16 bytes
 }
 
 // Returns the byte offset just past the workspace.
 __device__ __forceinline__ int big_carve(BigTab& t, int nmax, double* slot, int base_off) {
-    tab_carve_ex(t.v, nmax, 0, row_stride(nmax + 1), base_off);
-    t.dcol_off = base_off + (int)tab_smem_bytes_ex(nmax, 0, row_stride(nmax + 1));
+    tab_carve_ex(t.v, nmax, 0, row_stride(nmax + 1), base_off, 0);
+    t.dcol_off = base_off + (int)tab_smem_bytes_ex(nmax, 0, row_stride(nmax + 1), 0);
     t.Tg = slot;
     t.Pd = slot + (size_t)nmax * row_stride(nmax + 1);
     t.Pp = t.Pd + (size_t)QPN_BIG_PEND * ((nmax + 1) & ~1);
+    t.nbv0 = t.Pp + (size_t)QPN_BIG_PEND * row_stride(nmax + 1);
+    t.cv0 = reinterpret_cast<int*>(t.nbv0 + row_stride(nmax + 1));
+    t.ncol0 = 0;
     t.n = nmax; t.ldr = row_stride(nmax + 1); t.ncol = 0; t.pivots = 0; t.cc = -1; t.cpiv = -1; t.npend = 0;
     t.stage_off = 0; t.stage_cap = 0;
     return base_off + (int)big_smem_bytes(nmax);
@@ -102,6 +113,8 @@ __device__ __forceinline__ void big_stage_carve(BigTab& t, int used) {
     t.stage_off = (used + 15) & ~15;
     t.stage_cap = (int)total > t.stage_off ? ((int)total - t.stage_off) / 8 : 0;
 }
+// A column cached before the freeze still holds the entries of the rows that are frozen now.
+__device__ __forceinline__ void freeze_hook(BigTab& t) { t.cc = -1; }
 // Shape of the next solve; whatever was queued belongs to a tableau that is about to be overwritten.
 __device__ __forceinline__ void big_shape(BigTab& t, int n, int cap) { t.n = n; t.ldr = row_stride(cap); t.cc = -1; t.npend = 0; }
 __device__ __forceinline__ int big_pd_stride(const BigTab& t) { return (t.v.nmax + 1) & ~1; }
@@ -121,6 +134,9 @@ __device__ __forceinline__ void big_col(BigTab& t, int c) {
     const int n = t.n, ldr = t.ldr, np = t.npend, pds = big_pd_stride(t), lds = t.v.ldrmax;
     double* d = t.dcol();
     for (int r = threadIdx.x; r < n; r += blockDim.x) {
+        // A frozen row (avi_pivot.cuh: FROZEN) is out of every sweep: a zero entering entry keeps it out of the ratio
+        // test, of move() and -- through the queued column -- of the flush, and it is not even read.
+        if (frozen_row(t, r)) { d[r] = 0.0; continue; }
         double v = t.Tg[(size_t)r * ldr + c];
         for (int l = 0; l < np; ++l)                     // bring the stale entry up to date, oldest update first
             v = big_apply(t, l, r, c, v, t.Pd[(size_t)l * pds + r], t.Pp[(size_t)l * lds + c]);
@@ -210,7 +226,7 @@ __device__ __noinline__ void big_flush(BigTab& t, int dead_c = -1, int dead_last
                     if (act[q]) *reinterpret_cast<double2*>(row + j0 + 64 * q) = tv[q];
             }
         }
-        if (mv) {
+        if (mv && !frozen_row(t, i)) {                    // a frozen row keeps the column layout of the freeze
             __syncwarp();
             if (lane == 0) row[dead_c] = row[dead_last];
         }
@@ -455,6 +471,7 @@ __device__ __noinline__ int avi_pivot_run_big(BigTab& t, int max_pivots, bool fr
     const int st = lemke(t, max_pivots);
     t.npend = 0;                                          // z lives in beta / nbval: the queued sweeps are never needed
     QPN_SYNC();
+    frozen_values(t, t.prow());                           // prow is free between pivots (ldrmax >= ncol0 doubles)
     for (int i = threadIdx.x; i < t.n; i += blockDim.x) {
         const int r = t.rowof()[i];
         zs[i] = r >= 0 ? t.beta()[r] : t.nbval()[t.colof()[i]];
