@@ -46,7 +46,7 @@ NCU_WARP_INSTRUCTIONS_PER_LAUNCH_B4096 = 33_734_535
 SM_COUNT = 148
 # dram__bytes_read.sum + dram__bytes_write.sum of one level_equilibrium_big_kernel launch on the n = 256, m = 512
 # monotone stress level at batch 148 (profiles/r1_big_level_kernel_ncu_full_summary.csv)
-NCU_DRAM_BYTES_BIG_LEVEL_B148 = 453_209_967_000 + 419_249_768_000
+NCU_DRAM_BYTES_BIG_LEVEL_B148 = 262_166_886_000 + 250_972_012_000
 
 
 def inits_for(rank, batch, step=0):
@@ -384,9 +384,10 @@ def main():
                          "frac": NCU_DRAM_BYTES_BIG_LEVEL_B148 / tm / 1e9 / peak_m, "traffic": NCU_DRAM_BYTES_BIG_LEVEL_B148,
                          "dense_upper_bound_bytes": alg,
                          "note": "achieved = DRAM bytes of this launch measured by ncu (same batch, same data) / event-timed duration; the dense "
-                                 "bound 16 B x rows x live columns x pivots overstates it by 7x: pivots are queued four deep and swept in one pass, "
-                                 "rows with a zero entering entry and column pairs with zero pivot-row entries are skipped, and L2 serves 70 % of "
-                                 "the sector requests; with that the kernel is no longer HBM bound (L1 36 %, issue 27 %, DRAM 38 % of the copy peak)"},
+                                 "bound 16 B x rows x live columns x pivots overstates it by 12x: the rows of free basics (1,024 of 1,536) are frozen "
+                                 "after the plan and never swept, pivots are queued four deep and swept in one pass, rows with a zero entering "
+                                 "entry and column pairs with zero pivot-row entries are skipped, and L2 serves 75 % of the sector requests; "
+                                 "the sweep is load-latency bound per SM (L1 36 %, issue 27 %, DRAM 31 % of the copy peak), not HBM bound"},
             "note": "per GPU, device-timed; verify -> solve_qep -> verify fused in level_equilibrium_big_kernel"}
         ms_solver.close()
     except Exception as e:

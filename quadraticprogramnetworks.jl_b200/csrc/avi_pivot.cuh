@@ -106,6 +106,7 @@ struct Tab {
     int pivots;     // uniform across the CTA
     int fz;         // 1: the freeze record lives in this workspace (0: elsewhere, global-memory engine)
     int ncol0;      // live columns when the rows of free basics were frozen (uniform)
+    int own_frozen; // PER THREAD: the row this thread owns (row threadIdx.x) is frozen -- fixed from the freeze to the end of a solve
 
     __device__ __forceinline__ int dl() const { return (2 + fz) * ldrmax; }               // doubles of the per-column vectors
     __device__ __forceinline__ int il() const { return (1 + fz) * ldrmax; }               // ints of the per-column vectors
@@ -136,7 +137,7 @@ struct Tab {
 
 __device__ __forceinline__ void tab_carve_ex(Tab& t, int nmax, size_t tdoubles, int ldrmax, int base_off, int fz = 1) {
     t.base = base_off; t.nmax = nmax; t.ldrmax = ldrmax; t.td = (int)((tdoubles + 1) & ~(size_t)1);
-    t.n = nmax; t.ldr = ldrmax; t.ncol = 0; t.pivots = 0; t.fz = fz; t.ncol0 = 0;
+    t.n = nmax; t.ldr = ldrmax; t.ncol = 0; t.pivots = 0; t.fz = fz; t.ncol0 = 0; t.own_frozen = 0;
 }
 __device__ __forceinline__ void tab_carve(Tab& t, int n, int cap, int base_off) {
     tab_carve_ex(t, n, (size_t)n * row_stride(cap), row_stride(cap), base_off);
@@ -299,6 +300,7 @@ __device__ __forceinline__ void tab_start(Tab& t, const double* q, const double*
     tab_start_core(t, q, z0);
     t.ncol = t.n + 1;
     t.pivots = 0;
+    t.own_frozen = 0;
 }
 
 // ---- rank-1 pivot on the compact tableau (avi_scratch.jl:2-7) --------------------------
@@ -320,7 +322,7 @@ __device__ __noinline__ int pivot_core(Tab t, int rho, int c, bool compact) {
         t.prow()[j] = v;
         if (j < ncol && j != c) T[(size_t)rho * ldr + j] = v;
     }
-    const bool live = (i < n) && !frozen_row(t, i);         // frozen rows are never swept (read before the barrier)
+    const bool live = (i < n) && !t.own_frozen;             // frozen rows are never swept
     const double d = live ? T[(size_t)i * ldr + c] : 0.0;
     const int lv = t.rowvar()[rho];                         // leaving variable (read before the barrier)
     // A slack of a free variable never comes back: its column leaves the live range.
@@ -424,7 +426,7 @@ __device__ __forceinline__ double ratio_test(const Tab& t, int c, double sigma, 
 __device__ __forceinline__ void move(Tab& t, int c, double sigma, double theta) {
     if (theta == 0.0) return;
     const int i = threadIdx.x;
-    if (i < t.n && !frozen_row(t, i)) {                     // a frozen row keeps the basic value it had at the freeze
+    if (i < t.n && !t.own_frozen) {                         // a frozen row keeps the basic value it had at the freeze
         const double ci = t.T()[(size_t)i * t.ldr + c];
         if (ci != 0.0) t.beta()[i] = fma(-(sigma * theta), ci, t.beta()[i]);
     }
@@ -522,7 +524,8 @@ __device__ __forceinline__ void compact_dead(Tab& t) {
     QPN_SYNC();
 }
 
-__device__ __forceinline__ void freeze_hook(Tab&) {}
+// after the marks of freeze(): thread i keeps "my row is frozen" in a register for the rest of the solve
+__device__ __forceinline__ void freeze_hook(Tab& t) { t.own_frozen = (threadIdx.x < t.n) && frozen_row(t, threadIdx.x); }
 
 // ---- freeze (oracle/avi_pivot.py: freeze) ------------------------------------------------
 // Called where phase 0 of the crash has just ended (in this solve or in its plan): marks the free basics FROZEN

@@ -81,6 +81,7 @@ __device__ __forceinline__ void tab_start_plan(Tab& t, const PlanDesc& P, const 
     tab_start_plan_core(t, P, q, z0, zb);
     t.ncol = P.ncol0;
     t.pivots = P.npiv0;
+    t.own_frozen = 0;
 }
 
 // Solve (M z + q) comp. l <= z <= u in the shared-memory tableau.  `build(t)` must fill
