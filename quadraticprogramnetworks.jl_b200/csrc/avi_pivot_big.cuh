@@ -45,6 +45,9 @@
 #ifndef QPN_BIG_PEND
 #define QPN_BIG_PEND 4
 #endif
+#ifndef QPN_BIG_INFLIGHT
+#define QPN_BIG_INFLIGHT 4      // predicated 128-bit tableau loads a lane keeps in flight in the flush (5 and 6 measured: within noise)
+#endif
 
 namespace qpn {
 
@@ -178,6 +181,7 @@ __device__ __noinline__ void big_flush(BigTab& t, int dead_c = -1, int dead_last
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const bool mv = dead_c >= 0 && dead_c != dead_last;
     for (int i = w; i < n; i += nw) {
+        if (frozen_row(t, i)) continue;                  // never swept (warp-uniform; two shared-memory reads instead of the queue's column)
         double nd[QPN_BIG_PEND];
         int kind[QPN_BIG_PEND];                          // 0: row untouched by update l, 1: fma, 2: row replaced (pivot row)
         bool any = false;
@@ -190,11 +194,11 @@ __device__ __noinline__ void big_flush(BigTab& t, int dead_c = -1, int dead_last
         }
         double* row = t.Tg + (size_t)i * ldr;
         if (any) {
-            for (int j0 = 2 * lane; j0 < nce; j0 += 256) {
-                double2 tv[4];
-                bool act[4];
+            for (int j0 = 2 * lane; j0 < nce; j0 += 64 * QPN_BIG_INFLIGHT) {
+                double2 tv[QPN_BIG_INFLIGHT];
+                bool act[QPN_BIG_INFLIGHT];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < QPN_BIG_INFLIGHT; ++q) {
                     const int j = j0 + 64 * q;
                     act[q] = j < nce && touched[j >> 1];
                     if (act[q]) tv[q] = *reinterpret_cast<const double2*>(row + j);
@@ -206,11 +210,11 @@ __device__ __noinline__ void big_flush(BigTab& t, int dead_c = -1, int dead_last
                     const int cz = t.pcl[l];
                     if (kind[l] == 2) {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)
+                        for (int q = 0; q < QPN_BIG_INFLIGHT; ++q)
                             if (act[q]) tv[q] = *reinterpret_cast<const double2*>(ppl + j0 + 64 * q);
                     } else {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
+                        for (int q = 0; q < QPN_BIG_INFLIGHT; ++q) {
                             if (!act[q]) continue;
                             const int j = j0 + 64 * q;
                             const double2 pj = *reinterpret_cast<const double2*>(ppl + j);
@@ -222,11 +226,11 @@ __device__ __noinline__ void big_flush(BigTab& t, int dead_c = -1, int dead_last
                     }
                 }
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
+                for (int q = 0; q < QPN_BIG_INFLIGHT; ++q)
                     if (act[q]) *reinterpret_cast<double2*>(row + j0 + 64 * q) = tv[q];
             }
         }
-        if (mv && !frozen_row(t, i)) {                    // a frozen row keeps the column layout of the freeze
+        if (mv) {                                         // (frozen rows, which keep the column layout of the freeze, were skipped above)
             __syncwarp();
             if (lane == 0) row[dead_c] = row[dead_last];
         }
