@@ -89,6 +89,7 @@ class MultilevelPool:
         self.engine = engine if engine is not None else Engine(device)
         self._device_engine = isinstance(self.engine, Engine)
         self.workers = max(1, int(workers))
+        self.broken = False
         self.device_calls = 0            # engine calls issued (after merging)
         self.worker_calls = 0            # calls received from the workers
         ctx = mp.get_context("spawn")                    # spawn: the children must not inherit the CUDA context
@@ -204,6 +205,8 @@ class MultilevelPool:
     def solve(self, X, keep_sol=False, stats=None):
         """solve(qpn, inits) for the whole batch; results in instance order.  `Sol` (the top level's solution
         pieces) stays in the workers unless keep_sol: it is large and a batch caller reads x_opt / solved."""
+        if self.broken:
+            raise RuntimeError("MultilevelPool: a worker failed in an earlier batch; create a new pool")
         X = np.ascontiguousarray(np.atleast_2d(X), dtype=np.float64)
         used = min(self.workers, len(X))
         out = [None] * used
@@ -216,6 +219,7 @@ class MultilevelPool:
             t.join()
         for o in out:
             if isinstance(o, Exception):
+                self.broken = True       # a worker that failed mid-batch has lost its place in the protocol
                 raise o
         if stats is not None:
             for _, st in out:

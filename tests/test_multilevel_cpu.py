@@ -294,3 +294,5 @@ def test_worker_pool_reports_engine_errors():
     with qpn_b200.MultilevelPool(net, 2, engine=Broken()) as pool:
         with pytest.raises(RuntimeError, match="device lost"):
             pool.solve(X)
+        with pytest.raises(RuntimeError, match="new pool"):
+            pool.solve(X)

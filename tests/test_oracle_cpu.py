@@ -243,3 +243,42 @@ def test_cycle_check_semantics():
     """algorithm.jl:24: proj_vals ~ previous (isapprox, rtol = sqrt(eps)) ends the solve unsolved."""
     assert qpn_ref.projections_equal([1.0, 2.0], [1.0, 2.0 + 1e-9])
     assert not qpn_ref.projections_equal([1.0, 2.0], [1.0, 2.0 + 1e-6])
+
+
+# ---- frozen rows (oracle/avi_pivot.py: freeze) ---------------------------------------------------------------
+def test_frozen_rows_change_no_decision_and_only_last_bits():
+    """The rows of free basics are frozen after phase 0 and their variables evaluated once at the end.  Against the
+    same solve with the freeze switched off (every row carried through every pivot): same status, pivot count and
+    bases; z equal to rounding; and the frozen components satisfy their own equations (M z + q)_k = 0 at least as
+    well as the incremental ones."""
+    from oracle import avi_pivot
+
+    class Unfrozen(avi_pivot._Tab):
+        def freeze(self):
+            super().freeze()
+            self.frozen, self.T0, self.beta0 = [], self.T0[:0], self.beta0[:0]
+
+    def run(cls, M, q, l, u, z0):
+        tab = cls(M, q, l, u, z0)
+        tab.crash(); tab.repair()
+        st = tab.lemke(50 * len(q) + 100)
+        return st, tab.pivots, tab.basis_codes(), tab.solution(), len(tab.frozen)
+
+    rng = np.random.default_rng(5)
+    frozen_seen = 0
+    for kind in (0, 1, 2):
+        for _ in range(12):
+            Q, c, A, lo, up, z0 = problems.random_qp(rng, kind)
+            a = qpn_ref.convert(problems.qp_gavi(Q, c, A, lo, up))
+            M, q, l, u = a["M"], a["o"], a["l"], a["u"]
+            z0f = np.concatenate([z0, A @ z0[:len(c)]])
+            s1, p1, b1, z1, nf = run(avi_pivot._Tab, M, q, l, u, z0f)
+            s2, p2, b2, z2, _ = run(Unfrozen, M, q, l, u, z0f)
+            frozen_seen += nf
+            assert (s1, p1) == (s2, p2) and np.array_equal(b1, b2)
+            assert np.allclose(z1, z2, rtol=1e-9, atol=1e-9)
+            if s1 == 1:
+                free = np.isinf(l) & np.isinf(u)
+                r1, r2 = np.abs((M @ z1 + q)[free]).max(), np.abs((M @ z2 + q)[free]).max()
+                assert r1 <= 10 * r2 + 1e-10
+    assert frozen_seen > 100
