@@ -65,6 +65,11 @@ struct BigTab {
     double* nbv0;       // freeze record (avi_pivot.cuh: freeze), in the slot: nonbasic values ...
     int* cv0;           // ... and column variables at the freeze
     int ncol0;
+    // Started from a plan that exported the swept rows first: only rows 0 .. nact-1 are in the slot, the frozen rows
+    // nact .. n-1 are read from the plan itself (T0f, same row stride; their homotopy entry is (B^-1 r)_i from PTf).
+    int nact, tcol0;
+    const double* T0f;
+    const double* PTf;
 
     __device__ __forceinline__ double* prow() const { return v.prow(); }
     __device__ __forceinline__ double* nbval() const { return v.nbval(); }
@@ -104,7 +109,7 @@ __device__ __forceinline__ int big_carve(BigTab& t, int nmax, double* slot, int 
     t.Pp = t.Pd + (size_t)QPN_BIG_PEND * ((nmax + 1) & ~1);
     t.nbv0 = t.Pp + (size_t)QPN_BIG_PEND * row_stride(nmax + 1);
     t.cv0 = reinterpret_cast<int*>(t.nbv0 + row_stride(nmax + 1));
-    t.ncol0 = 0;
+    t.ncol0 = 0; t.nact = nmax; t.tcol0 = -1; t.T0f = nullptr; t.PTf = nullptr;
     t.n = nmax; t.ldr = row_stride(nmax + 1); t.ncol = 0; t.pivots = 0; t.cc = -1; t.cpiv = -1; t.npend = 0;
     t.stage_off = 0; t.stage_cap = 0;
     return base_off + (int)big_smem_bytes(nmax);
@@ -119,7 +124,9 @@ __device__ __forceinline__ void big_stage_carve(BigTab& t, int used) {
 // A column cached before the freeze still holds the entries of the rows that are frozen now.
 __device__ __forceinline__ void freeze_hook(BigTab& t) { t.cc = -1; }
 // Shape of the next solve; whatever was queued belongs to a tableau that is about to be overwritten.
-__device__ __forceinline__ void big_shape(BigTab& t, int n, int cap) { t.n = n; t.ldr = row_stride(cap); t.cc = -1; t.npend = 0; }
+__device__ __forceinline__ void big_shape(BigTab& t, int n, int cap) {
+    t.n = n; t.ldr = row_stride(cap); t.cc = -1; t.npend = 0; t.nact = n; t.T0f = nullptr; t.PTf = nullptr; t.tcol0 = -1;
+}
 __device__ __forceinline__ int big_pd_stride(const BigTab& t) { return (t.v.nmax + 1) & ~1; }
 
 // One queued update applied to the tableau entry (row r, column j) whose current value is v.
@@ -464,6 +471,37 @@ __device__ __noinline__ void compact_dead(BigTab& t) {
         if (lane == 0 && (nl & 1)) row[nl] = 0.0;
     }
     t.ncol = nl; t.cc = -1;
+    QPN_SYNC();
+}
+
+// frozen_values (avi_pivot.cuh) for the global-memory engine: the same sum, with the frozen rows read from the plan
+// when the instance never copied them (t.T0f); their homotopy entry is (B^-1 r)_i, rebuilt here exactly as the start
+// of a solve builds it for the swept rows.  Ends with a barrier.
+__device__ __noinline__ void frozen_values(BigTab& t, double* dx) {
+    const int n = t.n, nc0 = t.ncol0, ldr = t.ldr;
+    for (int j = threadIdx.x; j < nc0; j += blockDim.x) {
+        const int v = t.colvar0()[j];
+        const int r = t.rowof()[v], c = t.colof()[v];
+        dx[j] = (r >= 0 ? t.beta()[r] : c >= 0 ? t.nbval()[c] : t.nbval0()[j]) - t.nbval0()[j];
+    }
+    QPN_SYNC();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        if (!frozen_row(t, i)) continue;
+        double acc = t.beta()[i];
+        if (t.T0f && i >= t.nact) {
+            const double* row = t.T0f + (size_t)i * ldr;
+            double bir = 0.0;
+            for (int k = 0; k < n; ++k) {
+                const double pik = t.PTf[(size_t)k * n + i];
+                if (pik != 0.0) bir = fma(pik, t.rr()[k], bir);
+            }
+            for (int j = 0; j < nc0; ++j) acc = fma(-(j == t.tcol0 ? bir : row[j]), dx[j], acc);
+        } else {
+            const double* row = t.Tg + (size_t)i * ldr;
+            for (int j = 0; j < nc0; ++j) acc = fma(-row[j], dx[j], acc);
+        }
+        t.beta()[i] = acc;
+    }
     QPN_SYNC();
 }
 

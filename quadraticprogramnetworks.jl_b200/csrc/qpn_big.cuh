@@ -84,10 +84,11 @@ __device__ __noinline__ void big_start_plan(BigTab& t, const PlanDesc& P, const 
     big_shape(t, n, P.ncol0);
     const int ldr = t.ldr;
     for (int i = threadIdx.x; i < n; i += blockDim.x) zb[i] = fmin(fmax(z0[i], t.l()[i]), t.u()[i]);
+    const int nact = P.nact;                              // rows nact .. n-1 are frozen: never copied, read from the plan at the end
     {
         const double2* src = reinterpret_cast<const double2*>(P.T0);
         double2* dst = reinterpret_cast<double2*>(t.Tg);
-        const size_t cnt = (size_t)n * ldr / 2;
+        const size_t cnt = (size_t)nact * ldr / 2;
         for (size_t e = threadIdx.x; e < cnt; e += blockDim.x) dst[e] = src[e];
     }
     for (int v = threadIdx.x; v <= 2 * n; v += blockDim.x) { t.rowof()[v] = -1; t.colof()[v] = -1; }
@@ -103,18 +104,21 @@ __device__ __noinline__ void big_start_plan(BigTab& t, const PlanDesc& P, const 
     }
     QPN_SYNC();
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        double acc = 0.0;
-        for (int k = 0; k < n; ++k) {
-            const double pik = P.PT[(size_t)k * n + i];
-            if (pik != 0.0) acc = fma(pik, t.rr()[k], acc);
+        if (i < nact) {
+            double acc = 0.0;
+            for (int k = 0; k < n; ++k) {
+                const double pik = P.PT[(size_t)k * n + i];
+                if (pik != 0.0) acc = fma(pik, t.rr()[k], acc);
+            }
+            t.Tg[(size_t)i * ldr + P.tcol0] = acc;
         }
-        t.Tg[(size_t)i * ldr + P.tcol0] = acc;
         const int rv = P.rowvar0[i];
         t.rowvar()[i] = rv; t.rowof()[rv] = i;
-        t.beta()[i] = rv < n ? zb[rv] : zb[i] - z0[i];
+        t.beta()[i] = rv < n ? zb[rv] : zb[rv - n] - z0[rv - n];      // (a plan may export its rows in another order: go by the variable)
         if (rv < n) t.zst()[rv] = BASIC;
     }
     t.ncol = P.ncol0; t.pivots = P.npiv0; t.cc = -1; t.npend = 0;
+    t.nact = nact; t.tcol0 = P.tcol0; t.T0f = nact < n ? P.T0 : nullptr; t.PTf = P.PT;
     QPN_SYNC();
 }
 
@@ -355,12 +359,25 @@ plan_build_big_kernel(const __grid_constant__ GaviDesc g, int kind, int n_avi, c
         if (rho >= 0) { pivot(t, rho, c, false); set_zst(t, v, BASIC); }
     }
     big_flush(t);
+    // Export order of the rows (used for B^-1 right below and for T0 / rowvar0 further down): the rows an instance
+    // sweeps first, the rows of free basics (frozen from here on, avi_pivot.cuh: freeze) last, each group in its
+    // original order -- every tie rule only compares swept rows, so their relative order is all that matters.  An
+    // instance then copies rows 0 .. nact-1 and reads the frozen ones from the plan, once, at the end.
+    int* perm = cnt;                                       // the CSR counts are done with
+    if (threadIdx.x == 0) {
+        int na = 0;
+        for (int i = 0; i < n; ++i) if (t.rowvar()[i] >= n) perm[i] = na++;
+        hdr[4] = na;
+        for (int i = 0; i < n; ++i) if (t.rowvar()[i] < n) perm[i] = na++;
+    }
+    QPN_SYNC();
     // B^-1 from the slack columns (see recompute_tcol)
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const double* row = t.Tg + (size_t)i * ldr;
+        const int pi = perm[i];
         for (int kk = 0; kk < n; ++kk) {
             const int ck = t.colof()[n + kk];
-            PT[(size_t)kk * n + i] = ck >= 0 ? -row[ck] : (t.rowof()[n + kk] == i ? -1.0 : 0.0);
+            PT[(size_t)kk * n + pi] = ck >= 0 ? -row[ck] : (t.rowof()[n + kk] == i ? -1.0 : 0.0);
         }
     }
     const int npiv0 = t.pivots;
@@ -371,10 +388,11 @@ plan_build_big_kernel(const __grid_constant__ GaviDesc g, int kind, int n_avi, c
         const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
         for (int i = w; i < n; i += nw) {
             const double* row = t.Tg + (size_t)i * ldr;
-            for (int j = lane; j < ldr0; j += 32) T0[(size_t)i * ldr0 + j] = j < ncol0 ? row[j] : 0.0;
+            const size_t o = (size_t)perm[i] * ldr0;
+            for (int j = lane; j < ldr0; j += 32) T0[o + j] = j < ncol0 ? row[j] : 0.0;
         }
     }
-    for (int i = threadIdx.x; i < n; i += blockDim.x) rowvar0[i] = t.rowvar()[i];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) rowvar0[perm[i]] = t.rowvar()[i];
     for (int j = threadIdx.x; j < ncol0; j += blockDim.x) colvar0[j] = t.colvar()[j];
     if (threadIdx.x == 0) { hdr[0] = ncol0; hdr[1] = npiv0; hdr[2] = t.colof()[2 * n]; hdr[3] = k; }
 }

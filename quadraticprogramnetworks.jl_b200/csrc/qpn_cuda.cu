@@ -291,7 +291,7 @@ static int build_plan(qpn_handle* h, const GaviDesc& g, int kind, PlanDesc* out,
     CK(cudaStreamSynchronize(h->stream));
     PlanDesc P;
     P.n = kind == 1 ? hdr[3] + 2 * g.d2 : (int)n;
-    P.ncol0 = hdr[0]; P.npiv0 = hdr[1]; P.tcol0 = hdr[2];
+    P.ncol0 = hdr[0]; P.npiv0 = hdr[1]; P.tcol0 = hdr[2]; P.nact = P.n;
     P.T0 = (double*)(b + oT0); P.PT = (double*)(b + oPT); P.rowvar0 = (int*)(b + orv); P.colvar0 = (int*)(b + ocv);
     P.csr_ptr = (int*)(b + optr); P.csr_col = (int*)(b + ocol); P.csr_val = (double*)(b + oval);
     P.cols = (int*)(b + ocols); P.ncols = hdr[3];
@@ -331,7 +331,7 @@ static int build_plan_avi(qpn_handle* h, int n_, const MatDesc& M, const double*
     CK(cudaMemcpyAsync(hdr, b + ohdr, sizeof hdr, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     PlanDesc P;
-    P.n = n_; P.ncol0 = hdr[0]; P.npiv0 = hdr[1]; P.tcol0 = hdr[2];
+    P.n = n_; P.ncol0 = hdr[0]; P.npiv0 = hdr[1]; P.tcol0 = hdr[2]; P.nact = n_;
     P.T0 = (double*)(b + oT0); P.PT = (double*)(b + oPT); P.rowvar0 = (int*)(b + orv); P.colvar0 = (int*)(b + ocv);
     P.csr_ptr = (int*)(b + optr); P.csr_col = (int*)(b + ocol); P.csr_val = (double*)(b + oval);
     P.cols = nullptr; P.ncols = 0;
@@ -393,7 +393,7 @@ static int build_plan_big(qpn_handle* h, const GaviDesc& g, int kind, int n_avi,
     size_t need = 0;
     auto add = [&](size_t bytes) { size_t off = (need + 255) & ~(size_t)255; need = off + bytes; return off; };
     const size_t oT0 = add(8 * n * ldrw), oPT = add(8 * n * n), oval = add(8 * n * n), orv = add(4 * n), ocv = add(4 * (n + 1)),
-                 optr = add(4 * (n + 1)), ocol = add(4 * n * n), ocols = add(4 * (dz + 1)), ohdr = add(16);
+                 optr = add(4 * (n + 1)), ocol = add(4 * n * n), ocols = add(4 * (dz + 1)), ohdr = add(32);
     const size_t smem = big_smem_bytes((int)n) + (kind == 2 ? 16 * n : gavi_extra_bytes(g.d1, g.d2, g.np)) + 4 * n + 16;
     int grid = 0;
     size_t smem_l = smem;
@@ -416,12 +416,12 @@ static int build_plan_big(qpn_handle* h, const GaviDesc& g, int kind, int n_avi,
                                                                      (int)smem);
     h->launches++;
     CK(cudaGetLastError());
-    int hdr[4];
+    int hdr[5];
     CK(cudaMemcpyAsync(hdr, b + ohdr, sizeof hdr, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     PlanDesc P;
     P.n = kind == 1 ? hdr[3] + 2 * g.d2 : (int)n;
-    P.ncol0 = hdr[0]; P.npiv0 = hdr[1]; P.tcol0 = hdr[2];
+    P.ncol0 = hdr[0]; P.npiv0 = hdr[1]; P.tcol0 = hdr[2]; P.nact = hdr[4];
     P.T0 = (double*)(b + oT0); P.PT = (double*)(b + oPT); P.rowvar0 = (int*)(b + orv); P.colvar0 = (int*)(b + ocv);
     P.csr_ptr = (int*)(b + optr); P.csr_col = (int*)(b + ocol); P.csr_val = (double*)(b + oval);
     P.cols = (int*)(b + ocols); P.ncols = hdr[3];

@@ -12,6 +12,8 @@ namespace qpn {
 // r), the basis maps and the original matrix in CSR (for r and for the final check).
 struct PlanDesc {
     int n, ncol0, npiv0, tcol0;
+    int nact;                // rows 0 .. nact-1 are swept; rows nact .. n-1 hold free basics (frozen, avi_pivot.cuh) and were
+                             // exported last (stable order).  nact == n: rows in their original order.
     const double* T0;        // n x row_stride(ncol0), row-major
     const double* PT;        // n x n, PT[k*n + i] = (B^-1)[i][k]
     const int* rowvar0;      // n
@@ -71,7 +73,7 @@ __device__ __noinline__ void tab_start_plan_core(Tab t, const PlanDesc& P, const
         t.T()[(size_t)i * ldr + P.tcol0] = acc;
         const int rv = P.rowvar0[i];
         t.rowvar()[i] = rv; t.rowof()[rv] = i;
-        t.beta()[i] = rv < n ? zb[rv] : zb[i] - zi;
+        t.beta()[i] = rv < n ? zb[rv] : zb[rv - n] - z0[rv - n];      // (a plan may export its rows in another order: go by the variable)
         if (rv < n) t.zst()[rv] = BASIC;            // after the barrier that followed the default marks
     }
     QPN_SYNC();
