@@ -393,6 +393,34 @@ def main():
     except Exception as e:
         extra["monotone_stress_n256_m512"] = {"error": str(e)[:200]}
 
+    # ---- BASELINE.json configs[3]: the synthetic 3-level chain (n = 64 per node).  Its levels are measured one at a
+    # time -- here the bottom level (64 own variables, 136 parameters, lifted level AVI n = 256 of which 64 rows are
+    # swept): the full three-level solve needs solution graphs of 64-variable nodes, which neither the host mirror nor
+    # (per its README) the reference produces in usable time.
+    try:
+        ch = qpn_b200.setup("synthetic_chain")
+        ch_solver = qpn_b200.BatchedSolver(ch, engine=eng)
+        ch_level = ch_solver.resident_level(ch.num_levels())
+        cinfo = ch_level.info()
+        Bc = 4096
+        rng = np.random.default_rng([0xB200, rank, 13])
+        xc = torch.from_numpy(ch.default_initialization + 0.7 * rng.normal(size=(Bc, ch.n_vars))).to(dev)
+        xo = torch.empty_like(xc); so = torch.empty(Bc, dtype=torch.uint8, device=dev)
+        io = torch.empty(Bc, dtype=torch.int32, device=dev); po = torch.empty(Bc, dtype=torch.int32, device=dev)
+        run = lambda: ch_level.solve_dev(Bc, xc.data_ptr(), xo.data_ptr(), so.data_ptr(), io.data_ptr(), po.data_ptr(), None, stream.cuda_stream)
+        run(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        flush.zero_(); e0.record(stream); run(); e1.record(stream); torch.cuda.synchronize()
+        tc = e0.elapsed_time(e1) * 1e-3
+        extra["synthetic_chain_bottom_level"] = {
+            "value": Bc / tc, "unit": UNIT, "batch": Bc, "ms_per_launch": 1e3 * tc, "all_solved": bool(so.bool().all()),
+            "p50_pivots_per_solve": float(np.median(po.cpu().numpy())), "lifted_n": cinfo["n"], "live_columns": cinfo["ncol0"],
+            "plan_pivots": cinfo["plan_pivots"],
+            "note": "per GPU, device-timed; level 3 of 3 only; compact tableau slot (swept rows only) in shared memory, two CTAs per SM"}
+        ch_solver.close()
+    except Exception as e:                                      # noqa: BLE001
+        extra["synthetic_chain_bottom_level"] = {"error": str(e)[:200]}
+
     # ---- BASELINE.json configs[2] in full: three-level robust_avoid_simple solves (vertex exploration on), the host
     # recursion of solve_base! sharded over worker processes that are all served by this rank's engine handle
     # (workers.py).  Host-bound (piece generation / set operations in the Python mirror): reported as an extra.

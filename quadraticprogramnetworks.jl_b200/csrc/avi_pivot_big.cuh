@@ -94,18 +94,23 @@ struct BigTab {
 __host__ __device__ __forceinline__ size_t big_smem_bytes(int nmax) {
     return tab_smem_bytes_ex(nmax, 0, row_stride(nmax + 1), 0) + 8 * (size_t)((nmax + 1) & ~1);
 }
-// Doubles of one global workspace slot.
+// Doubles of one workspace slot whose tableau area holds `tcap` doubles (even): tableau, the queue, the freeze record.
+__host__ __device__ __forceinline__ size_t big_slot_doubles_ex(int nmax, size_t tcap) {
+    return tcap + (size_t)QPN_BIG_PEND * ((size_t)((nmax + 1) & ~1) + row_stride(nmax + 1)) +
+           row_stride(nmax + 1) + (size_t)row_stride(nmax + 1) / 2 + 1;          // stride/2 is odd: the slot stays a multiple of 16 bytes
+}
+// ... with room for the full n x (n+1) tableau (a solve without a plan).
 __host__ __device__ __forceinline__ size_t big_slot_doubles(int nmax) {
-    return (size_t)nmax * row_stride(nmax + 1) + (size_t)QPN_BIG_PEND * ((size_t)((nmax + 1) & ~1) + row_stride(nmax + 1)) +
-           row_stride(nmax + 1) + (size_t)row_stride(nmax + 1) / 2 + 1;          // + the freeze record (doubles, ints); stride/2 is odd: the slot stays a multiple of 16 bytes
+    return big_slot_doubles_ex(nmax, (size_t)nmax * row_stride(nmax + 1));
 }
 
 // Returns the byte offset just past the workspace.
-__device__ __forceinline__ int big_carve(BigTab& t, int nmax, double* slot, int base_off) {
+// tcap: doubles of the slot's tableau area (0: the full nmax x (nmax+1) shape).
+__device__ __forceinline__ int big_carve(BigTab& t, int nmax, double* slot, int base_off, size_t tcap = 0) {
     tab_carve_ex(t.v, nmax, 0, row_stride(nmax + 1), base_off, 0);
     t.dcol_off = base_off + (int)tab_smem_bytes_ex(nmax, 0, row_stride(nmax + 1), 0);
     t.Tg = slot;
-    t.Pd = slot + (size_t)nmax * row_stride(nmax + 1);
+    t.Pd = slot + (tcap ? tcap : (size_t)nmax * row_stride(nmax + 1));
     t.Pp = t.Pd + (size_t)QPN_BIG_PEND * ((nmax + 1) & ~1);
     t.nbv0 = t.Pp + (size_t)QPN_BIG_PEND * row_stride(nmax + 1);
     t.cv0 = reinterpret_cast<int*>(t.nbv0 + row_stride(nmax + 1));

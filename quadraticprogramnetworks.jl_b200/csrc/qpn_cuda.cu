@@ -34,6 +34,8 @@ struct qpn_handle {
     int64_t big_launches = 0;   // launches that took the global-memory tableau path
     int force_big = 0;          // option "force_big": route every pivoting solve through the big path (tests)
     int big_ctas_per_sm = 0;    // option "big_ctas_per_sm": 0 = as many as fit
+    int big_smem_threads = 0;   // option "big_smem_threads": threads per CTA when the slot is in shared memory (0 = by size)
+    int big_slot_in_smem = 1;   // option "big_slot_in_smem": 0 = always keep the tableau slot in global memory (tests)
 };
 
 static std::string g_create_error;
@@ -139,6 +141,8 @@ extern "C" int qpn_set_option(qpn_handle* h, const char* name, int64_t value) {
     if (!h || !name) return -1;
     if (!strcmp(name, "force_big")) { h->force_big = value != 0; return 0; }
     if (!strcmp(name, "big_ctas_per_sm")) { h->big_ctas_per_sm = (int)value; return 0; }
+    if (!strcmp(name, "big_slot_in_smem")) { h->big_slot_in_smem = value != 0; return 0; }
+    if (!strcmp(name, "big_smem_threads")) { h->big_smem_threads = (int)value; return 0; }
     return fail(h, "qpn_set_option: unknown option '%s'", name);
 }
 

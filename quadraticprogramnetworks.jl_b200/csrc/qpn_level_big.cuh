@@ -268,19 +268,41 @@ __host__ __device__ __forceinline__ size_t level_big_slot_doubles(const LevelDes
     return a > b ? a : b;
 }
 
+// Compact form of the slot for a level whose two solves start from plans: the tableau area only has to hold the rows
+// an instance sweeps (PlanDesc::nact of them) and the small no-plan tableau of verify_solution's fallback.  0 when
+// the level has no such plans.  When that slot fits shared memory next to the vectors, the level kernel keeps it
+// there (several CTAs of a few warps per SM instead of one CTA of 1,024 threads around a slot in global memory).
+__host__ __device__ __forceinline__ size_t level_big_compact_tcap(const LevelDesc& lv) {
+    if (!lv.has_plans || lv.planA.nact >= lv.planA.n || lv.planB.n <= 0) return 0;
+    size_t a = (size_t)lv.planA.nact * row_stride(lv.planA.ncol0), b = (size_t)lv.planB.nact * row_stride(lv.planB.ncol0);
+    size_t c = (size_t)lv.max_m * row_stride(lv.max_m + 1);
+    size_t tcap = a > b ? a : b;
+    if (c > tcap) tcap = c;
+    return (tcap + 1) & ~(size_t)1;
+}
+__host__ __device__ __forceinline__ size_t level_big_compact_slot_doubles(const LevelDesc& lv, size_t tcap) {
+    const int n = lv.g.d1 + 2 * lv.g.d2;
+    const int nmax = n > lv.max_m ? n : lv.max_m;
+    const size_t a = big_slot_doubles_ex(nmax, tcap), b = 2 * (size_t)lv.max_nd * (lv.max_m > 0 ? lv.max_m : 1);
+    return ((a > b ? a : b) + 1) & ~(size_t)1;
+}
+
+// work == nullptr: the slot (slot_doubles, tableau area tcap) lives in this CTA's dynamic shared memory, right after
+// the smem_used bytes of the layout below.
 __global__ void __launch_bounds__(QPN_BIG_THREADS, 1)
 level_equilibrium_big_kernel(const __grid_constant__ LevelDesc lv, int batch, const double* __restrict__ x_init,
                              double* __restrict__ x_out, uint8_t* __restrict__ solved_out, int32_t* __restrict__ iters_out,
                              int32_t* __restrict__ pivots_out, double* __restrict__ lam_out, double* __restrict__ hist,
                              int32_t* __restrict__ hist_count, int hist_cap, int presolve, int hist_fresh, double* __restrict__ work,
-                             size_t slot_doubles, int smem_used) {
+                             size_t slot_doubles, int smem_used, size_t tcap) {
     const int i = threadIdx.x, nv = lv.nv;
     const int n_level = lv.g.d1 + 2 * lv.g.d2;
     const int nmax = n_level > lv.max_m ? n_level : lv.max_m;
     BigTab t;
-    double* slot = work + (size_t)blockIdx.x * slot_doubles;
-    int off = big_carve(t, nmax, slot, 0);
-    big_stage_carve(t, smem_used);
+    const int slot_off = (smem_used + 15) & ~15;
+    double* slot = work ? work + (size_t)blockIdx.x * slot_doubles : reinterpret_cast<double*>(qpn_smem + slot_off);
+    int off = big_carve(t, nmax, slot, 0, tcap);
+    big_stage_carve(t, work ? smem_used : slot_off + (int)(8 * slot_doubles));
     GaviSmem gs;
     gavi_carve_extra(gs, lv.g, off);
     VerifyBig vs;

@@ -183,7 +183,8 @@ class Engine:
         self._ck(self.lib.qpn_synchronize(self.h))
 
     def set_option(self, name, value):
-        """qpn_set_option: "force_big" (global-memory tableau path for every solve), "big_ctas_per_sm"."""
+        """qpn_set_option: "force_big" (global-memory tableau path for every solve), "big_ctas_per_sm",
+        "big_slot_in_smem" (0: never keep a compact tableau slot in shared memory)."""
         self._ck(self.lib.qpn_set_option(self.h, name.encode(), C.c_int64(int(value))))
 
     # ---- matrices ----------------------------------------------------------------------

@@ -261,6 +261,15 @@ def test_synthetic_chain_bottom_level(engine):
     assert ro["solved"].all()
     for k in ("x", "iters", "pivots", "lam"):
         assert np.array_equal(ret[k], ro[k]), k
+    # the same level with the tableau slot kept in global memory (the default above keeps the compact slot -- only the
+    # 64 swept rows of each solve -- in shared memory): identical results
+    engine.set_option("big_slot_in_smem", 0)
+    try:
+        ret2 = lv.solve(X)
+    finally:
+        engine.set_option("big_slot_in_smem", 1)
+    for k in ("x", "iters", "pivots", "lam"):
+        assert np.array_equal(ret2[k], ro[k]), k
     solver.close()
 
 
