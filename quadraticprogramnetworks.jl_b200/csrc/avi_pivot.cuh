@@ -85,7 +85,7 @@ extern __shared__ __align__(16) unsigned char qpn_smem[];
 // engine keeps that record in its slot instead (fz = 0).
 __host__ __device__ __forceinline__ size_t tab_smem_bytes_ex(int nmax, size_t tdoubles, int ldrmax, int fz = 1) {
     tdoubles = (tdoubles + 1) & ~(size_t)1;
-    size_t d = tdoubles + (2 + (size_t)fz) * (size_t)ldrmax + 4 * (size_t)nmax + 36;
+    size_t d = tdoubles + (2 + (size_t)fz) * (size_t)ldrmax + (4 + (size_t)fz) * (size_t)nmax + 36;
     size_t i = (size_t)nmax + (1 + (size_t)fz) * ldrmax + 2 * (size_t)(2 * nmax + 1) + 36;
     size_t b = (size_t)nmax;
     return d * 8 + ((i * 4 + 15) / 16) * 16 + ((b + 15) / 16) * 16;
@@ -119,8 +119,14 @@ struct Tab {
     __device__ __forceinline__ double* l() const { return dbl(td + dl() + nmax); }
     __device__ __forceinline__ double* u() const { return dbl(td + dl() + 2 * nmax); }
     __device__ __forceinline__ double* rr() const { return dbl(td + dl() + 3 * nmax); }   // residual r at the start
-    __device__ __forceinline__ double* red_d() const { return dbl(td + dl() + 4 * nmax); }  // 36
-    __device__ __forceinline__ int* ints() const { return reinterpret_cast<int*>(dbl(td + dl() + 4 * nmax + 36)); }
+    __device__ __forceinline__ double* birv() const { return dbl(td + dl() + 4 * nmax); }  // n  (fz) (B^-1 r)_i of the frozen rows a plan start did not copy
+    __device__ __forceinline__ double* red_d() const { return dbl(td + dl() + (4 + fz) * nmax); }  // 36: [0,32) per warp, [32] ratio test, [33..35] below
+    // Where the frozen rows are (written by thread 0 at the start of a solve, before a barrier).  A plan that exported the
+    // swept rows first (PlanDesc::nact) leaves T() with rows 0 .. nact-1 only; rows nact .. n-1 are then read from the
+    // plan at the end (same row stride).  Null: every row is in T().
+    __device__ __forceinline__ const double** frozen_src() const { return reinterpret_cast<const double**>(red_d() + 33); }
+    __device__ __forceinline__ int* frozen_hdr() const { return reinterpret_cast<int*>(red_d() + 34); }   // [0] nact, [1] column of t in the plan
+    __device__ __forceinline__ int* ints() const { return reinterpret_cast<int*>(dbl(td + dl() + (4 + fz) * nmax + 36)); }
     __device__ __forceinline__ int* rowvar() const { return ints(); }                     // n     z_i = i, w_i = n+i, t = 2n
     __device__ __forceinline__ int* colvar() const { return ints() + nmax; }              // ldr
     __device__ __forceinline__ int* colvar0() const { return ints() + nmax + ldrmax; }    // ldr  (fz) column variables at the freeze
@@ -293,6 +299,7 @@ __device__ __noinline__ void tab_start_core(Tab t, const double* q, const double
     if (i == 0) {
         t.colvar()[n] = 2 * n; t.nbval()[n] = 0.0;
         t.rowof()[2 * n] = -1; t.colof()[2 * n] = n;
+        *t.frozen_src() = nullptr; t.frozen_hdr()[0] = n; t.frozen_hdr()[1] = -1;
     }
     QPN_SYNC();
 }
@@ -389,7 +396,7 @@ __device__ __noinline__ RatioResult ratio_test_core(const Tab t, int c, double s
     const int n = t.n, i = threadIdx.x;
     double r = QPN_INF, a = 0.0;
     bool is_t = false;
-    if (i < n) {
+    if (i < n && !t.own_frozen) {                           // a frozen row never blocks (and may not be in T() at all)
         const double ci = t.T()[(size_t)i * t.ldr + c];
         const double d = sigma * ci;
         const int v = t.rowvar()[i];
@@ -540,6 +547,35 @@ __device__ __forceinline__ void freeze(TT& t) {
     for (int j = threadIdx.x; j < t.ncol; j += blockDim.x) { t.colvar0()[j] = t.colvar()[j]; t.nbval0()[j] = t.nbval()[j]; }
     t.ncol0 = t.ncol;
     freeze_hook(t);
+    QPN_SYNC();
+}
+
+// frozen_values (below) for the shared-memory workspace: the same sum, with the frozen rows read from the plan when
+// the instance never copied them (t.T0f); their homotopy entry (B^-1 r)_i was left in birv() by the plan start.
+// Ends with a barrier.
+__device__ __noinline__ void frozen_values(Tab t, double* dx) {
+    const int n = t.n, nc0 = t.ncol0, ldr = t.ldr;
+    const double* T0f = *t.frozen_src();
+    const int nact = t.frozen_hdr()[0], tcol0 = t.frozen_hdr()[1];
+    for (int j = threadIdx.x; j < nc0; j += blockDim.x) {
+        const int v = t.colvar0()[j];
+        const int r = t.rowof()[v], c = t.colof()[v];
+        dx[j] = (r >= 0 ? t.beta()[r] : c >= 0 ? t.nbval()[c] : t.nbval0()[j]) - t.nbval0()[j];
+    }
+    QPN_SYNC();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        if (!frozen_row(t, i)) continue;
+        double acc = t.beta()[i];
+        if (T0f && i >= nact) {
+            const double* row = T0f + (size_t)i * ldr;
+            const double bir = t.birv()[i];               // written by the plan start, in the same pass as the swept rows' entries
+            for (int j = 0; j < nc0; ++j) acc = fma(-(j == tcol0 ? bir : row[j]), dx[j], acc);
+        } else {
+            const double* row = t.T() + (size_t)i * ldr;
+            for (int j = 0; j < nc0; ++j) acc = fma(-row[j], dx[j], acc);
+        }
+        t.beta()[i] = acc;                                // nobody reads a frozen row's beta in this pass
+    }
     QPN_SYNC();
 }
 

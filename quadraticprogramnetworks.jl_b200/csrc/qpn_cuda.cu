@@ -269,7 +269,7 @@ static int build_plan(qpn_handle* h, const GaviDesc& g, int kind, PlanDesc* out,
     size_t need = 0;
     auto add = [&](size_t bytes) { size_t off = (need + 255) & ~(size_t)255; need = off + bytes; return off; };
     const size_t oT0 = add(8 * n * ldrw), oPT = add(8 * n * n), oval = add(8 * n * n), orv = add(4 * n), ocv = add(4 * (n + 1)),
-                 optr = add(4 * (n + 1)), ocol = add(4 * n * n), ocols = add(4 * (dz + 1)), ohdr = add(16);
+                 optr = add(4 * (n + 1)), ocol = add(4 * n * n), ocols = add(4 * (dz + 1)), ohdr = add(32);
     unsigned char* b = nullptr;
     const size_t smem = gavi_smem_bytes(g.d1, g.d2, g.np);
     if (smem > (size_t)h->max_smem_optin) return fail(h, "plan: d1=%d d2=%d needs %zu B shared memory", g.d1, g.d2, smem);
@@ -290,12 +290,12 @@ static int build_plan(qpn_handle* h, const GaviDesc& g, int kind, PlanDesc* out,
                                                                   (int*)(b + ohdr));
     h->launches++;
     CK(cudaGetLastError());
-    int hdr[4];
+    int hdr[5];
     CK(cudaMemcpyAsync(hdr, b + ohdr, sizeof hdr, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     PlanDesc P;
     P.n = kind == 1 ? hdr[3] + 2 * g.d2 : (int)n;
-    P.ncol0 = hdr[0]; P.npiv0 = hdr[1]; P.tcol0 = hdr[2]; P.nact = P.n;
+    P.ncol0 = hdr[0]; P.npiv0 = hdr[1]; P.tcol0 = hdr[2]; P.nact = hdr[4];
     P.T0 = (double*)(b + oT0); P.PT = (double*)(b + oPT); P.rowvar0 = (int*)(b + orv); P.colvar0 = (int*)(b + ocv);
     P.csr_ptr = (int*)(b + optr); P.csr_col = (int*)(b + ocol); P.csr_val = (double*)(b + oval);
     P.cols = (int*)(b + ocols); P.ncols = hdr[3];
@@ -315,7 +315,7 @@ static int build_plan_avi(qpn_handle* h, int n_, const MatDesc& M, const double*
     size_t need = 0;
     auto add = [&](size_t bytes) { size_t off = (need + 255) & ~(size_t)255; need = off + bytes; return off; };
     const size_t oT0 = add(8 * n * ldrw), oPT = add(8 * n * n), oval = add(8 * n * n), orv = add(4 * n), ocv = add(4 * (n + 1)),
-                 optr = add(4 * (n + 1)), ocol = add(4 * n * n), ohdr = add(16);
+                 optr = add(4 * (n + 1)), ocol = add(4 * n * n), ohdr = add(32);
     const size_t smem = tab_smem_bytes(n_, n_ + 1) + 8 * 3 * n;
     if (smem > (size_t)h->max_smem_optin) return fail(h, "plan: AVI of size n=%d needs %zu B shared memory", n_, smem);
     if (need + 256 > h->plan_buf_bytes[0]) {
@@ -331,11 +331,11 @@ static int build_plan_avi(qpn_handle* h, int n_, const MatDesc& M, const double*
                                                                   (int*)(b + ohdr));
     h->launches++;
     CK(cudaGetLastError());
-    int hdr[4];
+    int hdr[5];
     CK(cudaMemcpyAsync(hdr, b + ohdr, sizeof hdr, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     PlanDesc P;
-    P.n = n_; P.ncol0 = hdr[0]; P.npiv0 = hdr[1]; P.tcol0 = hdr[2]; P.nact = n_;
+    P.n = n_; P.ncol0 = hdr[0]; P.npiv0 = hdr[1]; P.tcol0 = hdr[2]; P.nact = hdr[4];
     P.T0 = (double*)(b + oT0); P.PT = (double*)(b + oPT); P.rowvar0 = (int*)(b + orv); P.colvar0 = (int*)(b + ocv);
     P.csr_ptr = (int*)(b + optr); P.csr_col = (int*)(b + ocol); P.csr_val = (double*)(b + oval);
     P.cols = nullptr; P.ncols = 0;

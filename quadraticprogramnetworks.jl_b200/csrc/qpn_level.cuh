@@ -37,14 +37,16 @@ __device__ __noinline__ void tab_start_plan_core(Tab t, const PlanDesc& P, const
     const int n = P.n, i = threadIdx.x;
     const int ldr = t.ldr;
     if (i < n) zb[i] = fmin(fmax(z0[i], t.l()[i]), t.u()[i]);
+    const int nact = P.nact;                                      // rows nact .. n-1 are frozen: never copied (read from the plan at the end)
     if ((reinterpret_cast<uintptr_t>(P.T0) & 15) == 0) {          // ldr is even and T() is 16-byte aligned: 128-bit copies
         const double2* src = reinterpret_cast<const double2*>(P.T0);
         double2* dst = reinterpret_cast<double2*>(t.T());
-        for (int e = i; e < (n * ldr) >> 1; e += blockDim.x) dst[e] = src[e];
+        for (int e = i; e < (nact * ldr) >> 1; e += blockDim.x) dst[e] = src[e];
     } else {
-        for (int e = i; e < n * ldr; e += blockDim.x) t.T()[e] = P.T0[e];
+        for (int e = i; e < nact * ldr; e += blockDim.x) t.T()[e] = P.T0[e];
     }
     for (int v = i; v <= 2 * n; v += blockDim.x) { t.rowof()[v] = -1; t.colof()[v] = -1; }
+    if (i == 0) { *t.frozen_src() = nact < n ? P.T0 : nullptr; t.frozen_hdr()[0] = nact; t.frozen_hdr()[1] = P.tcol0; }
     QPN_SYNC();
     double zi = 0.0;
     if (i < n) {
@@ -58,19 +60,22 @@ __device__ __noinline__ void tab_start_plan_core(Tab t, const PlanDesc& P, const
     }
     QPN_SYNC();
     if (i < n) {
-        // The specification skips zero entries of B^-1; with a finite r (finite q, z0 clamped to finite bounds or finite
-        // itself) fma(0, r_k, acc) == acc bit for bit (acc starts at +0.0 and can never become -0.0), so the branch-free
-        // chain gives the same value and lets the loads run ahead of the dependent fma chain.
-        double acc = 0.0;
-        const double* pt = P.PT + i;
-        const double* rr = t.rr();
-        int k = 0;
-        for (; k + 4 <= n; k += 4) {
-            const double p0 = pt[(size_t)k * n], p1 = pt[(size_t)(k + 1) * n], p2 = pt[(size_t)(k + 2) * n], p3 = pt[(size_t)(k + 3) * n];
-            acc = fma(p0, rr[k], acc); acc = fma(p1, rr[k + 1], acc); acc = fma(p2, rr[k + 2], acc); acc = fma(p3, rr[k + 3], acc);
+        {
+            // The specification skips zero entries of B^-1; with a finite r (finite q, z0 clamped to finite bounds or finite
+            // itself) fma(0, r_k, acc) == acc bit for bit (acc starts at +0.0 and can never become -0.0), so the branch-free
+            // chain gives the same value and lets the loads run ahead of the dependent fma chain.
+            double acc = 0.0;
+            const double* pt = P.PT + i;
+            const double* rr = t.rr();
+            int k = 0;
+            for (; k + 4 <= n; k += 4) {
+                const double p0 = pt[(size_t)k * n], p1 = pt[(size_t)(k + 1) * n], p2 = pt[(size_t)(k + 2) * n], p3 = pt[(size_t)(k + 3) * n];
+                acc = fma(p0, rr[k], acc); acc = fma(p1, rr[k + 1], acc); acc = fma(p2, rr[k + 2], acc); acc = fma(p3, rr[k + 3], acc);
+            }
+            for (; k < n; ++k) acc = fma(pt[(size_t)k * n], rr[k], acc);
+            if (i < nact) t.T()[(size_t)i * ldr + P.tcol0] = acc;
+            else t.birv()[i] = acc;                       // a frozen row is not in T(): frozen_values picks its entry up here
         }
-        for (; k < n; ++k) acc = fma(pt[(size_t)k * n], rr[k], acc);
-        t.T()[(size_t)i * ldr + P.tcol0] = acc;
         const int rv = P.rowvar0[i];
         t.rowvar()[i] = rv; t.rowof()[rv] = i;
         t.beta()[i] = rv < n ? zb[rv] : zb[rv - n] - z0[rv - n];      // (a plan may export its rows in another order: go by the variable)
@@ -325,7 +330,7 @@ __host__ inline void gavi_workspace_shape(const GaviDesc& g, GaviPlans& pl, int 
         if (l > ldr) ldr = l;
         if ((size_t)rows * l > td) td = (size_t)rows * l;
     };
-    if (pl.has) { take(pl.A.n, pl.A.ncol0); take(pl.B.n, pl.B.ncol0); }
+    if (pl.has) { take(pl.A.nact, pl.A.ncol0); take(pl.B.nact, pl.B.ncol0); }      // swept rows only
     else take(n, n + 1);
     if (extra_rows > 0) take(extra_rows, extra_cap);
     pl.t_doubles = (int)td; pl.ldr_max = ldr;
@@ -391,12 +396,26 @@ __device__ __forceinline__ void plan_finish(Tab& t, int n, int k, const double* 
         const int rho = best_free_row(t, c);
         if (rho >= 0) { pivot(t, rho, c, false); set_zst(t, v, BASIC); }
     }
+    // Export order of the rows: the rows an instance sweeps first, the rows of free basics (frozen from here on,
+    // avi_pivot.cuh: freeze) last, each group in its original order -- every tie rule only compares swept rows, so
+    // their relative order is all that matters.  An instance then holds rows 0 .. nact-1 only and reads the frozen
+    // ones from the plan, once, at the end.
+    int* perm = cnt;                                       // the CSR counts are done with
+    QPN_SYNC();
+    if (i == 0) {
+        int na = 0;
+        for (int r = 0; r < n; ++r) if (t.rowvar()[r] >= n) perm[r] = na++;
+        hdr[4] = na;
+        for (int r = 0; r < n; ++r) if (t.rowvar()[r] < n) perm[r] = na++;
+    }
+    QPN_SYNC();
     // B^-1 from the slack columns (see recompute_tcol)
     if (i < n) {
         const double* row = t.T() + (size_t)i * t.ldr;
+        const int pi = perm[i];
         for (int kk = 0; kk < n; ++kk) {
             const int ck = t.colof()[n + kk];
-            PT[(size_t)kk * n + i] = ck >= 0 ? -row[ck] : (t.rowof()[n + kk] == i ? -1.0 : 0.0);
+            PT[(size_t)kk * n + pi] = ck >= 0 ? -row[ck] : (t.rowof()[n + kk] == i ? -1.0 : 0.0);
         }
     }
     const int npiv0 = t.pivots;
@@ -405,8 +424,9 @@ __device__ __forceinline__ void plan_finish(Tab& t, int n, int k, const double* 
     const int ncol0 = t.ncol, ldr0 = row_stride(ncol0);
     if (i < n) {
         const double* row = t.T() + (size_t)i * t.ldr;
-        for (int j = 0; j < ldr0; ++j) T0[(size_t)i * ldr0 + j] = j < ncol0 ? row[j] : 0.0;
-        rowvar0[i] = t.rowvar()[i];
+        const int pi = perm[i];
+        for (int j = 0; j < ldr0; ++j) T0[(size_t)pi * ldr0 + j] = j < ncol0 ? row[j] : 0.0;
+        rowvar0[pi] = t.rowvar()[i];
     }
     for (int j = i; j < ncol0; j += blockDim.x) colvar0[j] = t.colvar()[j];
     if (i == 0) { hdr[0] = ncol0; hdr[1] = npiv0; hdr[2] = t.colof()[2 * n]; hdr[3] = k; }
@@ -745,7 +765,7 @@ __host__ inline void level_workspace_shape(LevelDesc& lv) {
         if (l > ldr) ldr = l;
         if ((size_t)rows * l > td) td = (size_t)rows * l;
     };
-    if (lv.has_plans) { take(lv.planA.n, lv.planA.ncol0); take(lv.planB.n, lv.planB.ncol0); }
+    if (lv.has_plans) { take(lv.planA.nact, lv.planA.ncol0); take(lv.planB.nact, lv.planB.ncol0); }      // swept rows only
     else take(n, n + 1);
     lv.t_doubles = (int)td; lv.ldr_max = ldr;
 }

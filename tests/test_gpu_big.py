@@ -242,35 +242,46 @@ def test_monotone_stress_net_through_solve(engine):
 
 
 def test_synthetic_chain_bottom_level(engine):
-    """BASELINE.json configs[3]: the bottom level (node 3: 64 own variables, 136 parameters, lifted n = 256) as a
-    resident level on the global-memory tableau path."""
+    """BASELINE.json configs[3]: the bottom level (node 3: 64 own variables, 136 parameters, lifted n = 256 of which 64
+    rows are swept) as a resident level.  With plans that export the swept rows first it fits the shared-memory
+    engine (thread per row); forced onto the global-memory engine it runs with the compact slot in shared memory and,
+    with that switched off, with the slot in global memory.  All three: bit for bit the oracle."""
     import qpn_b200
     rng = np.random.default_rng(42)
     net = qpn_b200.setup("synthetic_chain")
-    solver = qpn_b200.BatchedSolver(net, engine=engine)
-    lv = solver.resident_level(3)
-    info = lv.info()
-    assert info["big"] and info["n"] == 256 and info["plan_pivots"] > 0
     B = 24
     X = net.default_initialization + 0.7 * rng.normal(size=(B, net.n_vars))
-    ret = lv.solve(X)
     pl = net.network_depth_map[3]
     g, dec, par = qpn_b200.assembly.level_gavi(net, pl)
     views = [qpn_b200.assembly.node_view(net, p) for p in pl]
-    ro = cport.Level(net.n_vars, views, g, dec, par, net.options.max_iters, solver.proj).solve(X, threads=4)
+    proj = qpn_b200.projection_vectors(net)
+    ro = cport.Level(net.n_vars, views, g, dec, par, net.options.max_iters, proj).solve(X, threads=4)
     assert ro["solved"].all()
-    for k in ("x", "iters", "pivots", "lam"):
-        assert np.array_equal(ret[k], ro[k]), k
-    # the same level with the tableau slot kept in global memory (the default above keeps the compact slot -- only the
-    # 64 swept rows of each solve -- in shared memory): identical results
-    engine.set_option("big_slot_in_smem", 0)
+
+    def check(ret):
+        for k in ("x", "iters", "pivots", "lam"):
+            assert np.array_equal(ret[k], ro[k]), k
+
+    solver = qpn_b200.BatchedSolver(net, engine=engine)
+    lv = solver.resident_level(3)
+    info = lv.info()
+    assert not info["big"] and info["n"] == 256 and info["plan_pivots"] > 0 and info["ncol0"] == 65
+    check(lv.solve(X))
+    solver.close()
+    before = engine.big_launches
+    engine.set_option("force_big", 1)
     try:
-        ret2 = lv.solve(X)
+        solver = qpn_b200.BatchedSolver(net, engine=engine)
+        lv = solver.resident_level(3)
+        assert lv.info()["big"]
+        check(lv.solve(X))                                   # compact slot in shared memory
+        engine.set_option("big_slot_in_smem", 0)
+        check(lv.solve(X))                                   # slot in global memory
+        solver.close()
     finally:
         engine.set_option("big_slot_in_smem", 1)
-    for k in ("x", "iters", "pivots", "lam"):
-        assert np.array_equal(ret2[k], ro[k]), k
-    solver.close()
+        engine.set_option("force_big", 0)
+    assert engine.big_launches >= before + 2
 
 
 def test_big_edge_cases_and_failure_statuses(big_engine):
