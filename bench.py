@@ -416,7 +416,8 @@ def main():
             "value": Bc / tc, "unit": UNIT, "batch": Bc, "ms_per_launch": 1e3 * tc, "all_solved": bool(so.bool().all()),
             "p50_pivots_per_solve": float(np.median(po.cpu().numpy())), "lifted_n": cinfo["n"], "live_columns": cinfo["ncol0"],
             "plan_pivots": cinfo["plan_pivots"],
-            "note": "per GPU, device-timed; level 3 of 3 only; compact tableau slot (swept rows only) in shared memory, two CTAs per SM"}
+            "path": "global-memory engine" if cinfo["big"] else "shared-memory tableau (swept rows only: 64 of 256)",
+            "note": "per GPU, device-timed; level 3 of 3 only"}
         ch_solver.close()
     except Exception as e:                                      # noqa: BLE001
         extra["synthetic_chain_bottom_level"] = {"error": str(e)[:200]}
