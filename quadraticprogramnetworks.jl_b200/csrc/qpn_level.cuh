@@ -477,29 +477,39 @@ struct NodeDesc {
 
 struct VerifySmem {
     int base, nd, m;      // byte offset in qpn_smem and the sizes it was carved for
+    int ab;               // byte offset of the two nd x m least-squares matrices: their own region, or -- in the level kernel --
+                          // the tableau buffer, which they time-share (they are dead before the fallback builds its tableau,
+                          // and no solve is in flight while a node is verified)
     __device__ __forceinline__ double* dbl(int off) const { return reinterpret_cast<double*>(qpn_smem + base) + off; }
-    __device__ __forceinline__ double* Ab() const { return dbl(0); }                          // nd x m
-    __device__ __forceinline__ double* Ab0() const { return dbl(nd * m); }                    // nd x m
-    __device__ __forceinline__ double* b() const { return dbl(2 * nd * m); }                  // nd
-    __device__ __forceinline__ double* lam() const { return dbl(2 * nd * m + nd); }           // m
-    __device__ __forceinline__ double* v() const { return dbl(2 * nd * m + nd + m); }         // nd + m
-    __device__ __forceinline__ double* lam_out() const { return dbl(2 * nd * m + 2 * nd + 2 * m); }   // m
-    __device__ __forceinline__ double* qs() const { return dbl(2 * nd * m + 2 * nd + 3 * m); }        // m (fallback AVI)
-    __device__ __forceinline__ double* zs() const { return dbl(2 * nd * m + 2 * nd + 4 * m); }        // m
-    __device__ __forceinline__ int* idx() const { return reinterpret_cast<int*>(dbl(2 * nd * m + 2 * nd + 5 * m)); }   // m
+    __device__ __forceinline__ double* Ab() const { return reinterpret_cast<double*>(qpn_smem + ab); }   // nd x m
+    __device__ __forceinline__ double* Ab0() const { return Ab() + nd * m; }                  // nd x m
+    __device__ __forceinline__ double* b() const { return dbl(0); }                           // nd
+    __device__ __forceinline__ double* lam() const { return dbl(nd); }                        // m
+    __device__ __forceinline__ double* v() const { return dbl(nd + m); }                      // nd + m
+    __device__ __forceinline__ double* lam_out() const { return dbl(2 * nd + 2 * m); }        // m
+    __device__ __forceinline__ double* qs() const { return dbl(2 * nd + 3 * m); }             // m (fallback AVI)
+    __device__ __forceinline__ double* zs() const { return dbl(2 * nd + 4 * m); }             // m
+    __device__ __forceinline__ int* idx() const { return reinterpret_cast<int*>(dbl(2 * nd + 5 * m)); }   // m
     __device__ __forceinline__ int* perm() const { return idx() + m; }                        // m
     __device__ __forceinline__ int8_t* kind() const {                                         // m
         return reinterpret_cast<int8_t*>(reinterpret_cast<unsigned char*>(idx()) + ((2 * m * 4 + 15) / 16) * 16);
     }
 };
 
-__host__ __device__ __forceinline__ size_t verify_smem_bytes(int nd, int m) {
-    size_t dbl = 2 * (size_t)nd * m + 2 * (size_t)nd + 5 * (size_t)m;
+// Bytes of the vectors (everything but the two matrices) ...
+__host__ __device__ __forceinline__ size_t verify_rest_bytes(int nd, int m) {
+    size_t dbl = 2 * (size_t)nd + 5 * (size_t)m;
     size_t ints = 2 * (size_t)m;
-    return dbl * 8 + ((ints * 4 + 15) / 16) * 16 + (((size_t)m + 15) / 16) * 16;
+    return ((dbl * 8 + 15) / 16) * 16 + ((ints * 4 + 15) / 16) * 16 + (((size_t)m + 15) / 16) * 16;
 }
+// ... and with the matrices in a region of their own right behind them.
+__host__ __device__ __forceinline__ size_t verify_smem_bytes(int nd, int m) { return verify_rest_bytes(nd, m) + 16 * (size_t)nd * m; }
 
-__device__ __forceinline__ void verify_carve(VerifySmem& v, int nd, int m, int base_off) { v.base = base_off; v.nd = nd; v.m = m; }
+// ab_off < 0: the matrices follow the vectors; else they live at byte offset ab_off (time-shared tableau buffer).
+__device__ __forceinline__ void verify_carve(VerifySmem& v, int nd, int m, int base_off, int ab_off = -1) {
+    v.base = base_off; v.nd = nd; v.m = m;
+    v.ab = ab_off >= 0 ? ab_off : base_off + (int)verify_rest_bytes(nd, m);
+}
 
 // Householder QR least squares with column pivoting, one thread per column; reductions run
 // down a column sequentially so the bits match oracle/qpn_oracle.c:lstsq_basic.
@@ -760,6 +770,7 @@ __host__ inline void level_workspace_shape(LevelDesc& lv) {
     const int n = lv.g.d1 + 2 * lv.g.d2;
     int ldr = row_stride(lv.max_m + 1);
     size_t td = (size_t)lv.max_m * ldr;                                   // verify_solution's fallback
+    if (2 * (size_t)lv.max_nd * lv.max_m > td) td = 2 * (size_t)lv.max_nd * lv.max_m;   // ... and its two least-squares matrices (VerifySmem::ab)
     auto take = [&](int rows, int cap) {
         const int l = row_stride(cap);
         if (l > ldr) ldr = l;
@@ -772,7 +783,7 @@ __host__ inline void level_workspace_shape(LevelDesc& lv) {
 
 __host__ __device__ __forceinline__ size_t level_smem_bytes(const LevelDesc& lv) {
     return tab_smem_bytes_ex(lv.g.d1 + 2 * lv.g.d2, (size_t)lv.t_doubles, lv.ldr_max) + gavi_extra_bytes(lv.g.d1, lv.g.d2, lv.g.np) +
-           verify_smem_bytes(lv.max_nd, lv.max_m) +
+           verify_rest_bytes(lv.max_nd, lv.max_m) +
            8 * (2 * (size_t)lv.nv + (size_t)(lv.nproj > 0 ? lv.nproj : 1) + (size_t)lv.nd_total + (size_t)lv.lam_total);
 }
 
@@ -789,8 +800,8 @@ __global__ void __launch_bounds__(MAXT, 896 / MAXT) level_equilibrium_kernel(con
     tab_carve_ex(gs.t, n_level, (size_t)lv.t_doubles, lv.ldr_max, 0);
     const int p = gavi_carve_extra(gs, lv.g, (int)tab_smem_bytes_ex(n_level, (size_t)lv.t_doubles, lv.ldr_max));
     VerifySmem vs;
-    verify_carve(vs, lv.max_nd, lv.max_m, p);
-    double* xs = reinterpret_cast<double*>(qpn_smem + p + verify_smem_bytes(lv.max_nd, lv.max_m));
+    verify_carve(vs, lv.max_nd, lv.max_m, p, 0);           // the matrices time-share the tableau buffer (byte offset 0)
+    double* xs = reinterpret_cast<double*>(qpn_smem + p + verify_rest_bytes(lv.max_nd, lv.max_m));
     double* pv = xs + nv;                  // nproj
     double* xn = pv + (lv.nproj > 0 ? lv.nproj : 1);
     double* qt_all = xn + nv;              // nd_total
