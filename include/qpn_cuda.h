@@ -218,7 +218,8 @@ int qpn_level_equilibrium_resident_dev(qpn_handle *h, qpn_level_dev *lvd, int ba
  * the global-memory tableau path that otherwise serves only sizes beyond the shared-memory
  * tableau (lifted n > ~166; up to n = 1,536); "big_ctas_per_sm" caps that path's resident CTAs; "big_slot_in_smem" = 0 keeps
  * that path's tableau slot in global memory even when a resident level's compact slot (swept rows only) would fit
- * shared memory (default 1).
+ * shared memory (default 1); "big_smem_threads" > 0 fixes the threads per CTA of that shared-memory-slot form
+ * (default 0: by the number of swept rows).
  */
 int qpn_set_option(qpn_handle *h, const char *name, int64_t value);
 
