@@ -318,6 +318,32 @@ def test_one_off_calls_with_plans_above_threshold(engine):
         assert np.array_equal(ret[k], ro[k]), k
 
 
+def test_all_rows_frozen_and_no_row_frozen(engine):
+    """Corner cases of the frozen-row rule (oracle/avi_pivot.py: freeze), below and above the batch size at which
+    one-off calls build plans: a system of free variables only (every row frozen, nothing is swept: an unconstrained
+    strictly convex QP) and a box LCP (no free variable: nothing frozen)."""
+    rng = np.random.default_rng(23)
+    n = 6
+    G = rng.normal(size=(n, n)); Q = G.T @ G + 0.5 * np.eye(n)
+    g = dict(M=Q, N=np.eye(n), o=rng.normal(size=n), l1=np.full(n, -np.inf), u1=np.full(n, np.inf),
+             A=np.zeros((0, n)), B=np.zeros((0, n)), l2=np.zeros(0), u2=np.zeros(0))
+    for B in (5, 300):
+        w = rng.normal(size=(B, n)); z0 = rng.normal(size=(B, n))
+        ret = engine.gavi_solve(g, w, z0)
+        assert (ret["status"] == 1).all()
+        for k in range(0, B, max(1, B // 6)):
+            ro = cport.gavi_solve(g, z0[k], w[k])
+            assert ro["status"] == 1 and ro["pivots"] == ret["pivots"][k]
+            assert np.array_equal(ro["z_full"], ret["z_full"][k]) and np.array_equal(ro["basis"], ret["basis"][k])
+            assert np.allclose(Q @ ret["z"][k] + w[k] + g["o"], 0.0, atol=1e-9)
+    M = Q + 0.3 * (G - G.T)
+    for B in (4, 280):
+        q = rng.normal(size=(B, n)); z0 = rng.uniform(-0.5, 1.5, (B, n))
+        z, st, pv, bs = engine.avi_solve(M, q, np.zeros(n), np.ones(n), z0)
+        zo, so, po, bo = cport.avi_solve_batched(M, q, np.zeros(n), np.ones(n), z0, threads=2)
+        assert (so == 1).all() and np.array_equal(st, so) and np.array_equal(pv, po) and np.array_equal(bs, bo) and np.array_equal(z, zo)
+
+
 # ---- edge cases and failure statuses through the C ABI --------------------------------------------
 def _lifted(Q, c, A, l, u, z0):
     g = problems.qp_gavi(np.asarray(Q, float), np.asarray(c, float), np.asarray(A, float), np.asarray(l, float), np.asarray(u, float))
