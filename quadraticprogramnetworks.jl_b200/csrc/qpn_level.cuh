@@ -596,6 +596,11 @@ __device__ __forceinline__ void node_products(const NodeDesc& nd_, const double*
 // Returns 1 when the point whose products qt / ax are given is a solution for the node; lam in
 // vs.lam_out().  tab: a tableau workspace large enough for an AVI of size m (used by the fallback
 // and for the reduction scratch).  qt / ax must be complete (barrier) on entry.
+// WIDE (compile time; the level kernel's instantiations for more than 64 threads): the acceptance test reads the signed
+// entries of A again, one thread per component, instead of keeping a second copy of the matrix (Ab0) in shared memory
+// and checking on one thread -- at nd = m = 64 that copy is 32 KB and the serial check 4,096 dependent steps.  Same
+// arithmetic, same order.  The small instantiations keep the original form (their code is what four_player runs).
+template <bool WIDE>
 __device__ __forceinline__ int verify_solution_smem(Tab& tab, VerifySmem& vs, const NodeDesc& nd_, const double* qt, const double* ax,
                                            double tol, int* how, int* pivots) {
     const int nd = nd_.nd, m = nd_.m, i = threadIdx.x;
@@ -642,20 +647,36 @@ __device__ __forceinline__ int verify_solution_smem(Tab& tab, VerifySmem& vs, co
         const int tcol = e / nd, r = e - tcol * nd;
         const double sgn = (tcol >= np_ && tcol < np_ + nn) ? -1.0 : 1.0;
         const double val = sgn * nd_.A[(size_t)nd_.dec[r] * m + vs.idx()[tcol]];
-        vs.Ab()[e] = val; vs.Ab0()[e] = val;
+        vs.Ab()[e] = val;
+        if (!WIDE) vs.Ab0()[e] = val;
     }
     for (int r = i; r < nd; r += blockDim.x) vs.b()[r] = qt[r];
     QPN_SYNC();
     lstsq_basic_block(tab, nd, k, vs.Ab(), vs.b(), vs.lam(), vs.perm(), vs.v());
     // acceptance (qp_processing.jl:119)
+    if (WIDE) {
+        for (int r = i; r < nd; r += blockDim.x) {
+            double acc = 0.0;
+            for (int t = 0; t < k; ++t) {
+                const double a = nd_.A[(size_t)nd_.dec[r] * m + vs.idx()[t]];
+                acc = fma((t >= np_ && t < np_ + nn) ? -a : a, vs.lam()[t], acc);
+            }
+            vs.v()[r] = acc - qt[r];                      // v: the factorisation's scratch, free again
+        }
+        QPN_SYNC();
+    }
     if (i == 0) {
         int ok = 1;
         for (int t = 0; t < np_ + nn; ++t) if (!(vs.lam()[t] > -tol)) ok = 0;
         double res = 0.0;
         for (int r = 0; r < nd; ++r) {
-            double acc = 0.0;
-            for (int t = 0; t < k; ++t) acc = fma(vs.Ab0()[(size_t)t * nd + r], vs.lam()[t], acc);
-            const double e = acc - qt[r];
+            double e;
+            if (WIDE) e = vs.v()[r];
+            else {
+                double acc = 0.0;
+                for (int t = 0; t < k; ++t) acc = fma(vs.Ab0()[(size_t)t * nd + r], vs.lam()[t], acc);
+                e = acc - qt[r];
+            }
             res = fma(e, e, res);
         }
         if (!(sqrt(res) <= tol)) ok = 0;
@@ -733,7 +754,7 @@ __global__ void verify_solution_kernel(const __grid_constant__ NodeDesc node, in
     node_products(node, xs, qt, ax);
     QPN_SYNC();
     int how = 0, piv = 0;
-    const int sol = verify_solution_smem(tab, vs, node, qt, ax, tol, &how, &piv);
+    const int sol = verify_solution_smem<false>(tab, vs, node, qt, ax, tol, &how, &piv);
     QPN_SYNC();
     for (int r = i; r < m; r += blockDim.x) {
         if (lam_out) lam_out[(size_t)b * m + r] = vs.lam_out()[r];
@@ -770,7 +791,12 @@ __host__ inline void level_workspace_shape(LevelDesc& lv) {
     const int n = lv.g.d1 + 2 * lv.g.d2;
     int ldr = row_stride(lv.max_m + 1);
     size_t td = (size_t)lv.max_m * ldr;                                   // verify_solution's fallback
-    if (2 * (size_t)lv.max_nd * lv.max_m > td) td = 2 * (size_t)lv.max_nd * lv.max_m;   // ... and its two least-squares matrices (VerifySmem::ab)
+    {   // ... and its least-squares matrices (VerifySmem::ab): two, or one in the instantiations for more than 64 threads
+        int need = n > lv.max_m ? n : lv.max_m;
+        if (lv.max_nd > need) need = lv.max_nd;
+        const size_t mats = (need > 64 ? 1 : 2) * (size_t)lv.max_nd * lv.max_m;      // need > 64 <=> level_equilibrium_kernel<128 / 256>
+        if (mats > td) td = mats;
+    }
     auto take = [&](int rows, int cap) {
         const int l = row_stride(cap);
         if (l > ldr) ldr = l;
@@ -872,7 +898,7 @@ __global__ void __launch_bounds__(MAXT, 896 / MAXT) level_equilibrium_kernel(con
             const NodeDesc& node = lv.players[pl];
             int how = 0;
             gs.t.n = n_level;
-            const int sol = verify_solution_smem(gs.t, vs, node, qt_all + lv.nd_off[pl], ax_all + lv.m_off[pl], 1e-4, &how, &piv);
+            const int sol = verify_solution_smem<(MAXT > 64)>(gs.t, vs, node, qt_all + lv.nd_off[pl], ax_all + lv.m_off[pl], 1e-4, &how, &piv);
             QPN_SYNC();
             if (lam_out)
                 for (int r = i; r < node.m; r += blockDim.x)
