@@ -38,11 +38,11 @@ WORKLOAD = "four_player_matrix_game Nash (edge_list=[]), random inits ~ U(-5,5)^
 HBM_FALLBACK_GBS = 6650.0     # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 # dram__bytes_read.sum + dram__bytes_write.sum of one level_equilibrium_kernel<32> launch at the default
 # batch (4,096), from profiles/r1_final_level_kernel_ncu_full_summary.csv (ncu --set full, same command)
-NCU_DRAM_BYTES_PER_LAUNCH_B4096 = 435_200 + 0
+NCU_DRAM_BYTES_PER_LAUNCH_B4096 = 433_152 + 256
 # same capture: l1tex__data_pipe_lsu_wavefronts_mem_shared.sum (each wavefront moves up to 128 B) and
 # smsp__inst_executed.sum -- the two on-chip resources that actually bound the pivoting kernel
-NCU_SMEM_WAVEFRONTS_PER_LAUNCH_B4096 = 4_036_042
-NCU_WARP_INSTRUCTIONS_PER_LAUNCH_B4096 = 34_886_043
+NCU_SMEM_WAVEFRONTS_PER_LAUNCH_B4096 = 3_884_408
+NCU_WARP_INSTRUCTIONS_PER_LAUNCH_B4096 = 34_962_442
 SM_COUNT = 148
 # dram__bytes_read.sum + dram__bytes_write.sum of one level_equilibrium_big_kernel launch on the n = 256, m = 512
 # monotone stress level at batch 148 (profiles/r1_big_level_kernel_ncu_full_summary.csv)
