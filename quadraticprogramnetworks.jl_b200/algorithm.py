@@ -10,7 +10,7 @@ solved / x_opt / Sol  or  solved / x_fail / x_opt=None (algorithm.jl:35,116,125)
 import numpy as np
 
 from . import assembly
-from .engine import Engine, LevelArrays, ResidentLevel
+from .engine import Engine, EngineError, LevelArrays, ResidentLevel
 from .examples import SplitMix64
 
 
@@ -243,46 +243,59 @@ class NetSolver:
         return gen.collect()
 
     # ---- qp_processing.jl:151-241 ------------------------------------------------------------------
-    def process_qp(self, pid, x, S):
+    # process_qp in two phases.  The reference builds a player's solution graph as soon as that player verifies,
+    # even when another player of the level does not -- graphs the level loop then throws away (algorithm.jl:47-52,
+    # 68-101: `continue` re-solves the children).  Here a level first verifies every player against every combination
+    # of child pieces (`verify_phase`) and builds graphs only once all of them verify (`graph_phase`).  Results are the
+    # same except that an error raised while building a graph nobody uses no longer fails the instance.
+    def verify_phase(self, pid, x, S):
         net = self.net
         base = [net.constraints[c] for c in net.qps[pid].constraint_indices]
         dec = net.decision_inds(pid)
-        gen = (pid not in net.network_depth_map[1]) or net.options.gen_solution_map
         children = sorted(net.network_edges[pid])
         if children:
             if any(len(S[j]) < 1 for j in children):
                 raise SolveError("Solution graphs were not properly populated.")
-            results = []
+            combos = []
             for combo in _julia_product([range(len(S[j])) for j in children]):
                 pieces = [S[j][ji] for j, ji in zip(children, combo)]
                 polys = base + pieces
                 ok, lam = self.verify(pid, polys, dec, x)
+                combos.append((ok, combo, pieces, polys, lam))
+            for ok, combo, _, _, _ in combos:
                 if not ok:
-                    results.append(dict(solution=False, subpiece_assignments=dict(zip(children, combo))))
-                else:
-                    sg = None
-                    if gen:
-                        sg = (pieces, ph.remove_subsets(self.solution_pieces(pid, polys, dec, x, lam), self.lp))
-                    results.append(dict(solution=True, solgraph=sg))
-            for r in results:
-                if not r["solution"]:
-                    return dict(solution=False, failed=False, subpiece_assignments=r["subpiece_assignments"])
-            S_out = None
-            if gen:
-                try:
-                    S_out = self.combine([r["solgraph"] for r in results], x)
-                except SolveError:
-                    return dict(solution=False, failed=True, S=None)
-        else:
-            ok, lam = self.verify(pid, base, dec, x)
-            if not ok:
-                return dict(solution=False, failed=False, subpiece_assignments={})
-            S_out = None
-            if gen:
-                S_out = self.solution_pieces(pid, base, dec, x, lam)
-                if len(S_out) == 0:
-                    raise SolveError("This shouldn't happen. Solution graph is empty.")
-        return dict(solution=True, S=S_out, failed=False)
+                    return dict(solution=False, subpiece_assignments=dict(zip(children, combo)))
+            return dict(solution=True, combos=combos, dec=dec)
+        ok, lam = self.verify(pid, base, dec, x)
+        if not ok:
+            return dict(solution=False, subpiece_assignments={})
+        return dict(solution=True, combos=None, base=base, lam=lam, dec=dec)
+
+    def graph_phase(self, pid, x, vr):
+        """The solution graph of a player that verified: dict(S=..., failed=...)."""
+        net = self.net
+        gen = (pid not in net.network_depth_map[1]) or net.options.gen_solution_map
+        if not gen:
+            return dict(S=None, failed=False)
+        dec = vr["dec"]
+        if vr["combos"] is not None:
+            graphs = [(pieces, ph.remove_subsets(self.solution_pieces(pid, polys, dec, x, lam), self.lp))
+                      for _, _, pieces, polys, lam in vr["combos"]]
+            try:
+                return dict(S=self.combine(graphs, x), failed=False)
+            except SolveError:
+                return dict(S=None, failed=True)
+        S_out = self.solution_pieces(pid, vr["base"], dec, x, vr["lam"])
+        if len(S_out) == 0:
+            raise SolveError("This shouldn't happen. Solution graph is empty.")
+        return dict(S=S_out, failed=False)
+
+    def process_qp(self, pid, x, S):
+        """qp_processing.jl:151-241 for one player (both phases)."""
+        vr = self.verify_phase(pid, x, S)
+        if not vr["solution"]:
+            return dict(solution=False, failed=False, subpiece_assignments=vr["subpiece_assignments"])
+        return dict(solution=True, **self.graph_phase(pid, x, vr))
 
     # ---- qp_processing.jl:243-291 ---------------------------------------------------------------------
     def combine(self, solgraphs, x):
@@ -302,13 +315,18 @@ class NetSolver:
     # ---- algorithm.jl:1-127 -------------------------------------------------------------------------------
     def solve(self, x_init):
         self.iterate_cache = {}
-        return self.solve_base(np.asarray(x_init, dtype=np.float64), 1)
+        self.level_iters = {}                               # level -> loop passes of solve_base, summed over its calls
+        ret = self.solve_base(np.asarray(x_init, dtype=np.float64), 1)
+        ret["level_iters"] = [self.level_iters.get(lv, 0) for lv in range(1, self.net.num_levels() + 1)]
+        return ret
 
     def solve_base(self, x_init, level):
         net, opt = self.net, self.net.options
         x = x_init.copy()
         try:
             for _ in range(opt.max_iters):
+                if hasattr(self, "level_iters"):
+                    self.level_iters[level] = self.level_iters.get(level, 0) + 1
                 if opt.check_for_cycling:
                     if opt.num_projections == 0:
                         raise SolveError("Cycling check requested, but num_projections == 0.")
@@ -327,19 +345,20 @@ class NetSolver:
                     S = {}
                 players = sorted(net.network_depth_map[level])
                 children = sorted(set().union(*[set(net.network_edges[i]) for i in players]))
-                results = [self.process_qp(pid, x, S) for pid in players]
-                equilibrium = True
+                vrs = [self.verify_phase(pid, x, S) for pid in players]
+                equilibrium = all(vr["solution"] for vr in vrs)
                 assignments = {i: S[i][0] for i in children}
-                if any(r["failed"] for r in results):
-                    return dict(solved=False, x_fail=x, x_opt=None)
-                for pid, r in zip(players, results):
-                    if not r["solution"]:
-                        equilibrium = False
-                        if level < net.num_levels():
-                            for child, sub in r["subpiece_assignments"].items():
-                                assignments[child] = S[child][sub]
-                    else:
+                if equilibrium:
+                    results = [self.graph_phase(pid, x, vr) for pid, vr in zip(players, vrs)]
+                    if any(r["failed"] for r in results):
+                        return dict(solved=False, x_fail=x, x_opt=None)
+                    for pid, r in zip(players, results):
                         S[pid] = ph.remove_subsets(r["S"], self.lp) if (r["S"] is not None and self._removes(level)) else r["S"]
+                elif level < net.num_levels():
+                    for vr in vrs:
+                        if not vr["solution"]:
+                            for child, sub in vr["subpiece_assignments"].items():
+                                assignments[child] = S[child][sub]
                 if not equilibrium:
                     xnew = self.solve_qep(players, x, assignments)
                     if np.linalg.norm(xnew - x) < 1e-4:
@@ -350,9 +369,11 @@ class NetSolver:
                     self.iterate_cache = {}
                 return dict(solved=True, x_opt=x, Sol=S, identified_request=set(), x_alts=[])
             raise SolveError("Can't find solution")
-        except SolveError as err:
+        except EngineError:
+            raise                                           # a CUDA / library error is not an outcome of the instance
+        except Exception as err:                            # noqa: BLE001 -- algorithm.jl:120-126: `catch err` -> solved=false
             self.iterate_cache = {}
-            return dict(solved=False, x_fail=x, x_opt=None, error=str(err))
+            return dict(solved=False, x_fail=x, x_opt=None, error=str(err) or type(err).__name__)
 
     def _removes(self, level):
         lv = self.net.options.levels_to_remove_subsets

@@ -181,6 +181,16 @@ class Poly:
         self.ru = np.array(ru, dtype=bool)
         self._K = keys
         self._keyset = None
+        self._exact = None
+
+    @property
+    def exact_key(self):
+        """The polyhedron as stored, row order and every bit included: the key of every memo whose value depends on
+        the rows themselves (node GAVIs, pieces, LP results) -- the 5-digit set equality below is the reference's
+        notion of equal SETS, not of equal data."""
+        if self._exact is None:
+            self._exact = (self.A.shape, self.A.tobytes(), self.l.tobytes(), self.u.tobytes(), self.rl.tobytes(), self.ru.tobytes())
+        return self._exact
 
     @property
     def _keys(self):

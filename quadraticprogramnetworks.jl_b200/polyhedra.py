@@ -166,7 +166,7 @@ def exemplar(P, lp, tol=1e-2):
     memo = getattr(lp, "memo", None)
     if memo is None:
         return _exemplar(P, lp, tol)
-    return lp.once(memo, ("exemplar", P, tol), lambda: _exemplar(P, lp, tol))
+    return lp.once(memo, ("exemplar", P.exact_key, tol), lambda: _exemplar(P, lp, tol))
 
 
 def _exemplar(P, lp, tol):
@@ -217,7 +217,7 @@ def issubset(P1, P2, lp, tol=1e-6):
     memo = getattr(lp, "memo", None)
     if memo is None:
         return _issubset(P1, P2, lp, tol)
-    return lp.once(memo, ("issubset", P1, P2, tol), lambda: _issubset(P1, P2, lp, tol))
+    return lp.once(memo, ("issubset", P1.exact_key, P2.exact_key, tol), lambda: _issubset(P1, P2, lp, tol))
 
 
 def _issubset(P1, P2, lp, tol):

@@ -173,7 +173,9 @@ class LocalSolutions:
 
 def process_solution_graph(net, pid, polys, dec, x, lam, engine, lp, exploration_vertices=0, cache=None):
     """avi.jl:447-477."""
-    key = (pid, tuple(polys))
+    # keyed on the exact, ordered rows: lam rides in the row order of `polys`, so two lists that are equal as sets
+    # (5-digit slice keys) but list their rows differently must not share a GAVI
+    key = (pid, tuple(p.exact_key for p in polys))
     if cache is not None and ("gavi", key) in cache:
         g, par = cache[("gavi", key)]
     else:

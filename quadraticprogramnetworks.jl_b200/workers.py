@@ -24,6 +24,8 @@ import time
 
 import numpy as np
 
+from .engine import EngineError
+
 from .sharding import shard_range
 
 
@@ -44,7 +46,7 @@ class RemoteEngine:
         self.conn.send(("call", kind, ident, shared if first else None, stacked, kwargs))
         tag, payload = self.conn.recv()
         if tag == "err":
-            raise RuntimeError(payload)
+            raise EngineError(payload)                     # the device call failed in the process that owns the GPU
         self.launches += 1
         return payload
 

@@ -286,7 +286,7 @@ def test_worker_pool_reports_engine_errors():
     exception, not a hang), and the pool still shuts down."""
     class Broken(OracleEngine):
         def verify_solution(self, node, x, tol=1e-4):
-            raise ValueError("device lost")
+            raise qpn_b200.EngineError("device lost")
     net = qpn_b200.setup("simple_bilevel")
     X = np.array([[1.0, 2.0, 0.0, 0.0], [0.5, -1.0, 0.0, 0.0], [2.0, 0.1, 0.0, 0.0]])
     with pytest.raises(Exception, match="device lost"):
