@@ -234,6 +234,62 @@ int qpn_free(qpn_handle *h, void *dptr);
 int qpn_memcpy_h2d(qpn_handle *h, void *dst, const void *src, size_t bytes);
 int qpn_memcpy_d2h(qpn_handle *h, void *dst, const void *src, size_t bytes);
 
+
+/* =====================================================================================================
+ * Networks with children: the batched solve(qpn, inits::Matrix) of BASELINE.json's north_star.
+ *
+ * Replaces, for a whole batch of independent instances, the recursion of solve_base!
+ * (/root/reference/src/algorithm.jl:1-127) with process_qp / combine (src/qp_processing.jl:151-291), the
+ * IntersectionRoot walk (src/intersection.jl:55-151) and collect(LocalGAVISolutions)
+ * (src/avi_solutions.jl:200-215,241-321,400-496).  The host side is a native state machine (csrc/net/): every
+ * instance advances until it needs numbers, the pending requests of all instances are regrouped by (kind, node /
+ * level GAVI) and run as one kernel launch per group over a list of instance slots whose x stays resident on the
+ * GPU; local pieces, projections and the LP predicates of the set algebra are memoised by exact problem data and
+ * shared by every instance, host thread and batch of the net.
+ *
+ * The network is passed as flat arrays (what setup(:name) produces; players, polys, levels 0-based here):
+ */
+typedef struct {
+    int32_t nv, nplayers, nlevels, npolys;
+    const double *Q;                       /* nplayers x nv x nv, row-major per player (symmetric)      programs.jl:172-201 */
+    const double *q;                       /* nplayers x nv */
+    const int32_t *var_ptr, *var_idx;      /* CSR over players: the player's own variables (QP.var_indices) */
+    const int32_t *con_ptr, *con_idx;      /* CSR over players: its constraint polys (constraint_indices order) */
+    const int32_t *child_ptr, *child_idx;  /* CSR over players: network_edges after add_edges! (programs.jl:274-285) */
+    const int32_t *level_of;               /* per player: 0-based level (network_depth_map) */
+    const int32_t *poly_ptr;               /* npolys + 1 row offsets into poly_A / poly_l / poly_u */
+    const double *poly_A;                  /* rows x nv, ROW-major: one normalised Slice per row (sets.jl:68-92) */
+    const double *poly_l, *poly_u;
+    int32_t max_iters, num_projections, exploration_vertices, gen_solution_map, check_for_cycling;  /* QPNetOptions */
+    const uint8_t *remove_subsets_at;      /* per level: 1 = remove_subsets (levels_to_remove_subsets); NULL = every level */
+    const double *proj;                    /* num_projections vectors of nv entries (algorithm.jl:10-12) */
+} qpn_net_desc;
+
+typedef struct qpn_net qpn_net;
+int qpn_net_create(qpn_handle *h, const qpn_net_desc *desc, qpn_net **out);
+int qpn_net_destroy(qpn_net *net);
+const char *qpn_net_last_error(qpn_net *net);
+/* "threads": host threads that drive the batch (each with its own stream), default 4. */
+int qpn_net_set_option(qpn_net *net, const char *name, int64_t value);
+/*
+ * solve(qpn, inits::Matrix): inits nv x batch (host).  x_out: nv x batch -- x_opt where solved_out[b] = 1, the
+ * reference's x_fail otherwise (algorithm.jl:116,125).  level_iters_out (may be NULL): nlevels x batch loop passes of
+ * solve_base! per level; error_out (may be NULL): batch, 0 = none, 1 cycling detected, 2 AVI solve error,
+ * 3 disagreement between verify and solve_qep, 4 max_iters, 5 empty solution graph, 6 comp_indices assertion,
+ * 7 too many solutions to combine, 8 solution graphs not populated, 9 cycle check without projections.
+ */
+int qpn_net_solve_batched(qpn_net *net, int batch, const double *inits, double *x_out, uint8_t *solved_out,
+                          int32_t *level_iters_out, int32_t *error_out);
+/* The solution graphs of the last batch (ret.Sol of algorithm.jl:116): number of pieces of player `player` for
+ * instance b (-1: none), the id of piece k, and a piece's rows (A: m x nv row-major; rl / ru: 1 = strict). */
+int qpn_net_sol_count(qpn_net *net, int b, int player);
+int qpn_net_sol_piece(qpn_net *net, int b, int player, int k);
+int qpn_net_piece_rows(qpn_net *net, int piece);
+int qpn_net_piece_get(qpn_net *net, int piece, double *A, double *l, double *u, uint8_t *rl, uint8_t *ru);
+/* out[0..11] = {kernel launches, rounds, requests, batched calls, LPs solved, pieces, nodes, level GAVIs,
+ * collect misses, combine misses, 0, 0} since the net was created. */
+int qpn_net_stats(qpn_net *net, int64_t *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,190 @@
+// ORACLE (test infrastructure / CPU baseline): the native network state machine of
+// quadraticprogramnetworks.jl_b200/csrc/net/ with every numeric request served by the C oracle (qpn_oracle.c)
+// on the host -- the same host logic as the product, none of its kernels.  Only tests/, __graft_entry__.smoke()
+// and bench.py's cpu_baseline / --impl reference legs load the library this file builds
+// (oracle/_build/libqpn_net_oracle.so).  Parity status of the numerics: see the header of qpn_oracle.c / DESIGN.md
+// (pinned by the reference's simple_bilevel known answers; unpinned against PATH / OSQP themselves).
+#include <cmath>
+#include <cstring>
+
+#include "../quadraticprogramnetworks.jl_b200/csrc/net/netdesc.hpp"
+
+extern "C" {
+int qpo_gavi_solve(int d1, int d2, int np, const double* M, const double* N, const double* o, const double* l1, const double* u1,
+                   const double* A, const double* B, const double* l2, const double* u2, const double* w, double* z0, int presolve,
+                   int max_pivots, double* z_out, double* zfull_out, int32_t* status, int32_t* pivots, int8_t* basis);
+void qpo_comp_indices(int d1, int d2, int np, const double* M, const double* N, const double* o, const double* l1, const double* u1,
+                      const double* A, const double* B, const double* l2, const double* u2, const double* z, const double* w,
+                      double tol, int8_t* mask);
+int qpo_halfspace_in(int m, int d, const double* A, const double* l, const double* u, const uint8_t* rl, const uint8_t* ru,
+                     const double* x, double tol);
+int qpo_verify_solution(int nd, int nv, int m, const double* Qd, const double* qd, const double* A, const double* l, const double* u,
+                        const int32_t* dec, const double* x, double tol, double* lam_out, int32_t* how, int8_t* active,
+                        int32_t* fallback_pivots);
+}
+
+namespace {
+using namespace qpnnet;
+
+struct OracleStore;
+
+struct OracleWorker : Worker {
+    OracleStore* store;
+    const NetData* net = nullptr;            // set at set_batch (the store learns the net after the solver is built)
+    int B = 0, nv = 0;
+    std::vector<double> X, Xf;
+    explicit OracleWorker(OracleStore* s) : store(s) {}
+
+    int gavi_solve_one(const GaviData& g, const double* w, const double* z0, double* z) override {
+        std::vector<double> z0c(z0, z0 + g.d1 + g.d2);
+        static const double none = 0.0;
+        int32_t st = 0, pv = 0;
+        qpo_gavi_solve(g.d1, g.d2, g.np, g.M.data(), g.N.data(), g.o.data(), g.l1.data(), g.u1.data(), g.A.data(), g.B.data(),
+                       g.l2.data(), g.u2.data(), w ? w : &none, z0c.data(), 1, 0, z, nullptr, &st, &pv, nullptr);
+        return st;
+    }
+    void set_batch(int B_, const double* x_init) override;
+    void run_verify(int, const NodeInfo& n, VerifyReq** reqs, int cnt, bool snap) override {
+        std::vector<double> lam(n.m + 1), z(n.nd + n.m + 1), w(n.par.size() + 1);
+        for (int k = 0; k < cnt; ++k) {
+            VerifyReq& r = *reqs[k];
+            const double* x = X.data() + (size_t)r.inst * nv;
+            int32_t how = 0, fp = 0;
+            r.solution = (uint8_t)qpo_verify_solution(n.nd, n.nv, n.m, n.Qd.data(), n.qd.data(), n.A.data(), n.l.data(), n.u.data(),
+                                                      n.dec.data(), x, 1e-4, lam.data(), &how, nullptr, &fp);
+            if (r.solution) {
+                for (int e = 0; e < n.nd; ++e) z[e] = x[n.dec[e]];
+                for (int i = 0; i < n.m; ++i) z[n.nd + i] = lam[i];
+                for (size_t c = 0; c < n.par.size(); ++c) w[c] = x[n.par[c]];
+                r.mask.assign(n.nd + n.m, 0);
+                const GaviData& g = n.g;
+                qpo_comp_indices(g.d1, g.d2, g.np, g.M.data(), g.N.data(), g.o.data(), g.l1.data(), g.u1.data(), g.A.data(),
+                                 g.B.data(), g.l2.data(), g.u2.data(), z.data(), w.data(), 1e-2, r.mask.data());
+                if (r.want_zw) { r.zw.assign(z.begin(), z.begin() + n.nd + n.m); r.zw.insert(r.zw.end(), w.begin(), w.begin() + n.par.size()); }
+            }
+            if (snap) std::memcpy(Xf.data() + (size_t)r.inst * nv, x, sizeof(double) * nv);
+        }
+    }
+    void run_qep(int, const LevelGaviInfo& L, QepReq** reqs, int cnt, bool snap) override {
+        const GaviData& g = L.g;
+        const int dz = g.d1 + g.d2, ndl = (int)L.dec.size();
+        std::vector<double> w(g.np + 1), z0(dz + 1), z(dz + 1), xn(nv);
+        const int nproj = net->check_for_cycling ? net->num_projections : 0;
+        for (int k = 0; k < cnt; ++k) {
+            QepReq& r = *reqs[k];
+            double* x = X.data() + (size_t)r.inst * nv;
+            for (int j = 0; j < g.np; ++j) w[j] = x[L.par[j]];
+            for (int j = 0; j < dz; ++j) z0[j] = j < ndl ? x[L.dec[j]] : 0.0;
+            qpo_gavi_solve(g.d1, g.d2, g.np, g.M.data(), g.N.data(), g.o.data(), g.l1.data(), g.u1.data(), g.A.data(), g.B.data(),
+                           g.l2.data(), g.u2.data(), w.data(), z0.data(), 1, 0, z.data(), nullptr, &r.status, &r.pivots, nullptr);
+            r.moved = 0;
+            if (r.status == 1) {
+                std::memcpy(xn.data(), x, sizeof(double) * nv);
+                for (int j = 0; j < ndl; ++j) xn[L.dec[j]] = z[j];
+                double dn = 0.0;
+                for (int j = 0; j < nv; ++j) { const double e = xn[j] - x[j]; dn = std::fma(e, e, dn); }
+                r.moved = !(std::sqrt(dn) < 1e-4);
+                if (r.moved) {
+                    std::memcpy(x, xn.data(), sizeof(double) * nv);
+                    r.pv.assign(nproj, 0.0);
+                    for (int q = 0; q < nproj; ++q) {
+                        double acc = 0.0;
+                        for (int j = 0; j < nv; ++j) acc = std::fma(x[j], net->proj[(size_t)q * nv + j], acc);
+                        r.pv[q] = acc;
+                    }
+                }
+            }
+            if (snap) std::memcpy(Xf.data() + (size_t)r.inst * nv, x, sizeof(double) * nv);
+        }
+    }
+    void run_member(MemberReq** reqs, int cnt) override;
+    void run_comp(int, const NodeInfo& n, CompReq** reqs, int cnt) override {
+        const GaviData& g = n.g;
+        for (int k = 0; k < cnt; ++k) {
+            CompReq& r = *reqs[k];
+            r.mask.assign(g.d1 + g.d2, 0);
+            qpo_comp_indices(g.d1, g.d2, g.np, g.M.data(), g.N.data(), g.o.data(), g.l1.data(), g.u1.data(), g.A.data(), g.B.data(),
+                             g.l2.data(), g.u2.data(), r.zw.data(), r.zw.data() + g.d1 + g.d2, 1e-2, r.mask.data());
+        }
+    }
+    void finish() override {}
+    void download(double* x_out, double* xf_out) override {
+        std::memcpy(x_out, X.data(), sizeof(double) * (size_t)B * nv);
+        std::memcpy(xf_out, Xf.data(), sizeof(double) * (size_t)B * nv);
+    }
+};
+
+struct PieceCM { int m = 0; std::vector<double> A, l, u; };      // column-major copy for qpo_halfspace_in
+
+struct OracleStore : Store {
+    const NetData* net = nullptr;
+    std::deque<PieceCM> pieces;
+    std::shared_mutex mu;
+    Worker* make_worker() override { return new OracleWorker(this); }
+    void new_node(int, const NodeInfo&, Worker*) override {}
+    void new_gavi(int, const LevelGaviInfo&, Worker*) override {}
+    void new_piece(int id, const Poly& P, Worker*) override {
+        PieceCM c;
+        c.m = P.m();
+        c.A.assign((size_t)P.m() * P.d, 0.0);
+        for (int i = 0; i < P.m(); ++i) for (int j = 0; j < P.d; ++j) c.A[(size_t)j * P.m() + i] = P.row(i)[j];
+        c.l = P.l; c.u = P.u;
+        std::unique_lock<std::shared_mutex> lk(mu);
+        if ((int)pieces.size() <= id) pieces.resize(id + 1);
+        pieces[id] = std::move(c);
+    }
+};
+
+void OracleWorker::set_batch(int B_, const double* x_init) {
+    net = store->net;
+    B = B_; nv = net->nv;
+    X.assign(x_init, x_init + (size_t)B * nv);
+    Xf = X;
+}
+void OracleWorker::run_member(MemberReq** reqs, int cnt) {
+    for (int k = 0; k < cnt; ++k) {
+        MemberReq& r = *reqs[k];
+        const double* x = X.data() + (size_t)r.inst * nv;
+        r.in.assign(r.pieces->size(), 0);
+        for (size_t q = 0; q < r.pieces->size(); ++q) {
+            const PieceCM* c;
+            { std::shared_lock<std::shared_mutex> lk(store->mu); c = &store->pieces[(*r.pieces)[q]]; }
+            r.in[q] = c->m == 0 ? 1 : (uint8_t)qpo_halfspace_in(c->m, nv, c->A.data(), c->l.data(), c->u.data(), nullptr, nullptr, x, 1e-6);
+        }
+    }
+}
+}  // namespace
+
+using qpnnet::NetObject;
+
+extern "C" {
+int qpo_net_create(const qpn_net_desc* desc, void** out) {
+    if (!desc || !out) return -1;
+    std::vector<qpnnet::Poly> polys;
+    qpnnet::NetData nd = qpnnet::net_from_desc(desc, polys);
+    auto store = std::make_unique<OracleStore>();
+    OracleStore* sp = store.get();
+    NetObject* o = new NetObject();
+    o->solver.reset(new qpnnet::NetSolver(std::move(nd), std::move(polys), std::move(store)));
+    sp->net = &o->solver->net();
+    *out = o;
+    return 0;
+}
+int qpo_net_destroy(void* net) { delete (NetObject*)net; return 0; }
+int qpo_net_set_option(void* net, const char* name, int64_t v) {
+    if (!net || !name) return -1;
+    if (!std::strcmp(name, "threads")) { ((NetObject*)net)->threads = (int)v; return 0; }
+    return -1;
+}
+int qpo_net_solve_batched(void* net, int batch, const double* inits, double* x_out, uint8_t* solved_out, int32_t* level_iters_out,
+                          int32_t* error_out) {
+    return qpnnet::net_solve((NetObject*)net, batch, inits, x_out, solved_out, level_iters_out, error_out);
+}
+int qpo_net_sol_count(void* net, int b, int player) { return qpnnet::net_sol_count((NetObject*)net, b, player); }
+int qpo_net_sol_piece(void* net, int b, int player, int k) { return qpnnet::net_sol_piece((NetObject*)net, b, player, k); }
+int qpo_net_piece_rows(void* net, int piece) { return qpnnet::net_piece_rows((NetObject*)net, piece); }
+int qpo_net_piece_get(void* net, int piece, double* A, double* l, double* u, uint8_t* rl, uint8_t* ru) {
+    return qpnnet::net_piece_get((NetObject*)net, piece, A, l, u, rl, ru);
+}
+int qpo_net_stats(void* net, int64_t* out) { return qpnnet::net_stats((NetObject*)net, out); }
+}

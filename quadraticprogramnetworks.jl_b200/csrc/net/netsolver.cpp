@@ -1,0 +1,840 @@
+// Native batched host state machine for networks with children -- see netsolver.hpp for the shape.
+// Build: g++ -std=c++20 -O2 -ffp-contract=off (the geometry must round like the Python host mirror).
+#include "netsolver.hpp"
+
+#include <cassert>
+#include <condition_variable>
+#include <coroutine>
+#include <cstdio>
+#include <set>
+#include <thread>
+
+namespace qpnnet {
+
+enum { ERR_NONE = 0, ERR_CYCLE, ERR_AVI, ERR_DISAGREE, ERR_MAXIT, ERR_GRAPH_EMPTY, ERR_MASK, ERR_COMBINE, ERR_UNPOPULATED, ERR_NOPROJ };
+
+// =================================================================================================================
+// GeoCache
+// =================================================================================================================
+template <class Map, class Key, class F>
+auto GeoCache::memo(Map& map, const Key& key, F&& compute) -> typename Map::mapped_type {
+    {
+        std::shared_lock<std::shared_mutex> lk(mu_);
+        auto it = map.find(key);
+        if (it != map.end()) return it->second;
+    }
+    auto value = compute();                      // outside the lock: pure, so a racing duplicate computes the same value
+    std::unique_lock<std::shared_mutex> lk(mu_);
+    auto ins = map.emplace(key, value);
+    return ins.first->second;
+}
+
+int GeoCache::intern_poly(Poly&& P, Worker* w) {
+    std::string ek = exact_key(P);
+    {
+        std::shared_lock<std::shared_mutex> lk(mu_);
+        auto it = poly_by_exact_.find(ek);
+        if (it != poly_by_exact_.end()) return it->second;
+    }
+    std::lock_guard<std::mutex> cl(create_mu_);
+    int id;
+    {
+        std::shared_lock<std::shared_mutex> lk(mu_);
+        auto it = poly_by_exact_.find(ek);
+        if (it != poly_by_exact_.end()) return it->second;
+        id = (int)polys_.size();
+    }
+    std::string sk = set_key(P);
+    store_->new_piece(id, P, w);                 // resident before anybody can ask about it
+    std::unique_lock<std::shared_mutex> lk(mu_);
+    auto sit = set_by_key_.emplace(std::move(sk), (int)set_by_key_.size());
+    polys_.push_back(std::move(P));
+    set_ids_.push_back(sit.first->second);
+    poly_by_exact_.emplace(std::move(ek), id);
+    stats.pieces++;
+    return id;
+}
+
+int GeoCache::intern_list(const std::vector<int>& ids) {
+    {
+        std::shared_lock<std::shared_mutex> lk(mu_);
+        auto it = list_ids_.find(ids);
+        if (it != list_ids_.end()) return it->second;
+    }
+    std::unique_lock<std::shared_mutex> lk(mu_);
+    auto it = list_ids_.find(ids);
+    if (it != list_ids_.end()) return it->second;
+    const int id = (int)lists_.size();
+    lists_.push_back(ids);
+    list_ids_.emplace(ids, id);
+    return id;
+}
+
+// ---- assembly (avi.jl:205-251,305-377,447-475; qp_processing.jl:57-66) --------------------------------------------
+static void stack_polys(const GeoCache& c, const std::vector<int>& polys, int nv, std::vector<double>& A_rm, std::vector<double>& l,
+                        std::vector<double>& u) {
+    for (int id : polys) {
+        const Poly& P = c.poly(id);
+        A_rm.insert(A_rm.end(), P.A.begin(), P.A.end());
+        l.insert(l.end(), P.l.begin(), P.l.end());
+        u.insert(u.end(), P.u.begin(), P.u.end());
+    }
+    (void)nv;
+}
+
+int GeoCache::node(int pid, const std::vector<int>& pieces, Worker* w) {
+    std::vector<int> key;
+    key.push_back(pid);
+    key.insert(key.end(), pieces.begin(), pieces.end());
+    {
+        std::shared_lock<std::shared_mutex> lk(mu_);
+        auto it = node_ids_.find(key);
+        if (it != node_ids_.end()) return it->second;
+    }
+    std::lock_guard<std::mutex> cl(create_mu_);
+    int id;
+    {
+        std::shared_lock<std::shared_mutex> lk(mu_);
+        auto it = node_ids_.find(key);
+        if (it != node_ids_.end()) return it->second;
+        id = (int)nodes_.size();
+    }
+    const NetData& net = net_;
+    NodeInfo n;
+    n.pid = pid; n.nv = net.nv;
+    n.polys = net.base[pid];
+    n.polys.insert(n.polys.end(), pieces.begin(), pieces.end());
+    const std::vector<int>& dec = net.dec[pid];
+    n.nd = (int)dec.size();
+    n.dec.assign(dec.begin(), dec.end());
+    std::vector<char> isdec(net.nv, 0);
+    for (int d : dec) isdec[d] = 1;
+    for (int j = 0; j < net.nv; ++j) if (!isdec[j]) n.par.push_back(j);
+    std::vector<double> A, l, u;
+    stack_polys(*this, n.polys, net.nv, A, l, u);
+    const int m = (int)l.size(), nv = net.nv, nd = n.nd, np = (int)n.par.size();
+    n.m = m;
+    n.l = l; n.u = u;
+    n.A.assign((size_t)m * nv, 0.0);
+    for (int i = 0; i < m; ++i) for (int j = 0; j < nv; ++j) n.A[(size_t)j * m + i] = A[(size_t)i * nv + j];
+    const std::vector<double>& Q = net.Q[pid];
+    n.Qd.assign((size_t)nd * nv, 0.0);
+    n.qd.resize(nd);
+    for (int e = 0; e < nd; ++e) {
+        for (int j = 0; j < nv; ++j) n.Qd[(size_t)j * nd + e] = Q[(size_t)dec[e] * nv + j];
+        n.qd[e] = net.q[pid][dec[e]];
+    }
+    // single-node GAVI: (Q_dd x_d + Q_dp w + q_d - A_d' lam) comp. x_d free ; lam comp. l <= A_d x_d + A_p w <= u
+    GaviData& g = n.g;
+    g.d1 = nd; g.d2 = m; g.np = np;
+    const int dz = nd + m;
+    g.M.assign((size_t)nd * dz, 0.0);
+    for (int e = 0; e < nd; ++e) {
+        for (int c = 0; c < nd; ++c) g.M[(size_t)c * nd + e] = Q[(size_t)dec[e] * nv + dec[c]];
+        for (int i = 0; i < m; ++i) g.M[(size_t)(nd + i) * nd + e] = -A[(size_t)i * nv + dec[e]];
+    }
+    g.N.assign((size_t)nd * np, 0.0);
+    for (int e = 0; e < nd; ++e) for (int c = 0; c < np; ++c) g.N[(size_t)c * nd + e] = Q[(size_t)dec[e] * nv + n.par[c]];
+    g.o = n.qd;
+    g.l1.assign(nd, -INF); g.u1.assign(nd, INF);
+    g.A.assign((size_t)m * dz, 0.0);
+    for (int i = 0; i < m; ++i) for (int c = 0; c < nd; ++c) g.A[(size_t)c * m + i] = A[(size_t)i * nv + dec[c]];
+    g.B.assign((size_t)m * np, 0.0);
+    for (int i = 0; i < m; ++i) for (int c = 0; c < np; ++c) g.B[(size_t)c * m + i] = A[(size_t)i * nv + n.par[c]];
+    g.l2 = l; g.u2 = u;
+    store_->new_node(id, n, w);
+    std::unique_lock<std::shared_mutex> lk(mu_);
+    nodes_.push_back(std::move(n));
+    node_ids_.emplace(std::move(key), id);
+    stats.nodes++;
+    return id;
+}
+
+int GeoCache::level_gavi(int level, const std::vector<int>& assignment, Worker* w) {
+    std::vector<int> key;
+    key.push_back(level);
+    key.insert(key.end(), assignment.begin(), assignment.end());
+    {
+        std::shared_lock<std::shared_mutex> lk(mu_);
+        auto it = gavi_ids_.find(key);
+        if (it != gavi_ids_.end()) return it->second;
+    }
+    std::lock_guard<std::mutex> cl(create_mu_);
+    int id;
+    {
+        std::shared_lock<std::shared_mutex> lk(mu_);
+        auto it = gavi_ids_.find(key);
+        if (it != gavi_ids_.end()) return it->second;
+        id = (int)gavis_.size();
+    }
+    const NetData& net = net_;
+    const std::vector<int>& players = net.levels[level];
+    // children of the level, sorted: assignment[k] is the piece of the k-th child
+    std::vector<int> kids;
+    for (int p : players) kids.insert(kids.end(), net.children[p].begin(), net.children[p].end());
+    std::sort(kids.begin(), kids.end());
+    kids.erase(std::unique(kids.begin(), kids.end()), kids.end());
+    std::map<int, int> piece_of;
+    for (size_t k = 0; k < kids.size(); ++k) piece_of[kids[k]] = assignment[k];
+    const int nv = net.nv;
+    LevelGaviInfo L;
+    L.level = level;
+    std::vector<char> isdec(nv, 0);
+    for (int p : players) for (int d : net.dec[p]) isdec[d] = 1;
+    std::vector<int> dec, par, dpos(nv, -1);
+    for (int j = 0; j < nv; ++j) { if (isdec[j]) { dpos[j] = (int)dec.size(); dec.push_back(j); } else par.push_back(j); }
+    const int nd = (int)dec.size(), np = (int)par.size();
+    struct View { std::vector<double> A, l, u; int k, m; };
+    std::vector<View> views;
+    int total_xi = 0, total_lam = 0;
+    for (int p : players) {
+        View v;
+        std::vector<int> polys = net.base[p];
+        for (int j : net.children[p]) polys.push_back(piece_of[j]);
+        stack_polys(*this, polys, nv, v.A, v.l, v.u);
+        v.k = (int)net.dec[p].size(); v.m = (int)v.l.size();
+        total_xi += v.k; total_lam += v.m;
+        views.push_back(std::move(v));
+    }
+    GaviData& g = L.g;
+    const int d1 = nd + total_xi, d2 = total_lam, dz = d1 + d2;
+    g.d1 = d1; g.d2 = d2; g.np = np;
+    g.M.assign((size_t)d1 * dz, 0.0); g.N.assign((size_t)d1 * np, 0.0); g.o.assign(d1, 0.0);
+    g.A.assign((size_t)d2 * dz, 0.0); g.B.assign((size_t)d2 * np, 0.0); g.l2.assign(d2, 0.0); g.u2.assign(d2, 0.0);
+    g.l1.assign(d1, -INF); g.u1.assign(d1, INF);
+    int xi_off = 0, lam_off = 0, row = nd;
+    for (size_t pi = 0; pi < players.size(); ++pi) {
+        const int p = players[pi];
+        const View& v = views[pi];
+        const std::vector<int>& decp = net.dec[p];
+        const std::vector<double>& Q = net.Q[p];
+        for (int e = 0; e < v.k; ++e) {
+            for (int c = 0; c < nd; ++c) g.M[(size_t)c * d1 + row + e] = Q[(size_t)decp[e] * nv + dec[c]];
+            for (int c = 0; c < np; ++c) g.N[(size_t)c * d1 + row + e] = Q[(size_t)decp[e] * nv + par[c]];
+            g.o[row + e] = net.q[p][decp[e]];
+            for (int i = 0; i < v.m; ++i) g.M[(size_t)(d1 + lam_off + i) * d1 + row + e] = -v.A[(size_t)i * nv + decp[e]];
+            g.M[(size_t)(nd + xi_off + e) * d1 + dpos[decp[e]]] = 1.0;        // top rows: sum of the owners' xi = 0
+        }
+        for (int i = 0; i < v.m; ++i) {
+            for (int c = 0; c < nd; ++c) g.A[(size_t)c * d2 + lam_off + i] = v.A[(size_t)i * nv + dec[c]];
+            for (int c = 0; c < np; ++c) g.B[(size_t)c * d2 + lam_off + i] = v.A[(size_t)i * nv + par[c]];
+            g.l2[lam_off + i] = v.l[i]; g.u2[lam_off + i] = v.u[i];
+        }
+        row += v.k; xi_off += v.k; lam_off += v.m;
+    }
+    L.dec.assign(dec.begin(), dec.end());
+    L.par.assign(par.begin(), par.end());
+    store_->new_gavi(id, L, w);
+    std::unique_lock<std::shared_mutex> lk(mu_);
+    gavis_.push_back(std::move(L));
+    gavi_ids_.emplace(std::move(key), id);
+    stats.gavis++;
+    return id;
+}
+
+// ---- predicates ----------------------------------------------------------------------------------------------
+static inline uint64_t pair_key(int a, int b) { return ((uint64_t)(uint32_t)a << 32) | (uint32_t)b; }
+
+bool GeoCache::empty(int pid, double tol, Worker* w) {
+    // two tolerances are in use (1e-4 everywhere on this path); fold the tolerance into the key
+    const uint64_t key = pair_key(pid, tol == 1e-4 ? 0 : 1 + (int)std::lround(-std::log10(tol)));
+    return memo(empty_, key, [&]() -> char {
+        long n = 0;
+        const bool e = exemplar_empty(poly(pid), *w, tol, &n);
+        stats.lps += n;
+        return (char)e;
+    }) != 0;
+}
+
+bool GeoCache::subset(int p1, int p2, Worker* w) {
+    return memo(subset_, pair_key(p1, p2), [&]() -> char {
+        long n = 0;
+        const bool s = issubset(poly(p1), poly(p2), *w, 1e-6, &n);
+        stats.lps += n;
+        return (char)s;
+    }) != 0;
+}
+
+int GeoCache::remove_subsets(int lid, Worker* w) {
+    return memo(remove_subsets_, lid, [&]() -> int {
+        const std::vector<int> ids = list(lid);
+        const int k = (int)ids.size();
+        std::vector<char> is_sub(k, 0);
+        for (int i = 0; i < k; ++i)
+            for (int j = 0; j < k; ++j)
+                if (i != j && !is_sub[j] && subset(ids[i], ids[j], w)) { is_sub[i] = 1; break; }
+        std::vector<int> out;
+        for (int i = 0; i < k; ++i) if (!is_sub[i]) out.push_back(ids[i]);
+        return intern_list(out);
+    });
+}
+
+int GeoCache::intersect2(int a, int b, Worker* w) {
+    return memo(intersect2_, pair_key(a, b), [&]() -> int { return intern_poly(intersect(poly(a), poly(b)), w); });
+}
+
+int GeoCache::intersect_all(const std::vector<int>& ids, Worker* w) {
+    // ph.intersect(*polys): rows of the first, then of the second, ...; one poly alone is rebuilt as it is
+    int cur = ids[0];
+    for (size_t k = 1; k < ids.size(); ++k) {
+        // intersect(intersect(p1, p2), p3) lists the rows in the order of intersect(p1, p2, p3)
+        cur = memo(intersect2_, pair_key(cur, ids[k]) ^ 0x8000000000000000ull,
+                   [&]() -> int { return intern_poly(intersect(poly(cur), poly(ids[k])), w); });
+    }
+    return cur;
+}
+
+const std::vector<int>& GeoCache::complement_of(int pid, Worker* w) {
+    {
+        std::shared_lock<std::shared_mutex> lk(mu_);
+        auto it = complement_.find(pid);
+        if (it != complement_.end()) return it->second;
+    }
+    std::vector<int> ids;
+    for (Poly& c : complement(poly(pid))) ids.push_back(intern_poly(std::move(c), w));
+    std::unique_lock<std::shared_mutex> lk(mu_);
+    return complement_.emplace(pid, std::move(ids)).first->second;
+}
+
+// ---- local pieces (avi_solutions.jl:400-496, 79-90, 241-261) ---------------------------------------------------
+static Poly build_local_piece(const GaviData& g, const std::string& K) {
+    const int d1 = g.d1, d2 = g.d2, n = d1 + d2, m = g.np, d = n + m;
+    Rows r;
+    r.d = d;
+    std::vector<double> row(d);
+    std::vector<double> lo(2 * n), up(2 * n);
+    for (int i = 0; i < n; ++i) {
+        const int k = K[i];
+        double a, b, c, e;
+        if (i < d1) {
+            const double o = g.o[i], l = g.l1[i], u = g.u1[i];
+            switch (k) {
+                case 1: a = -o; b = INF; c = l; e = l; break;
+                case 2: a = -o; b = -o; c = l; e = u; break;
+                case 3: a = -INF; b = -o; c = u; e = u; break;
+                default: a = -INF; b = INF; c = l; e = u; break;
+            }
+        } else {
+            const double l = g.l2[i - d1], u = g.u2[i - d1];
+            switch (k) {
+                case 1: a = 0.0; b = INF; c = l; e = l; break;
+                case 2: a = 0.0; b = 0.0; c = l; e = u; break;
+                case 3: a = -INF; b = 0.0; c = u; e = u; break;
+                default: a = -INF; b = INF; c = l; e = u; break;
+            }
+        }
+        lo[i] = a; up[i] = b; lo[n + i] = c; up[n + i] = e;
+    }
+    for (int i = 0; i < 2 * n; ++i) if (lo[i] > up[i]) lo[i] = up[i];
+    for (int rr = 0; rr < 2 * n; ++rr) {
+        std::fill(row.begin(), row.end(), 0.0);
+        if (rr < d1) {                               // [M N]
+            for (int c = 0; c < n; ++c) row[c] = g.M[(size_t)c * d1 + rr];
+            for (int c = 0; c < m; ++c) row[n + c] = g.N[(size_t)c * d1 + rr];
+        } else if (rr < n) {                         // [0 I2 0]
+            row[d1 + (rr - d1)] = 1.0;
+        } else if (rr < n + d1) {                    // [I1 0 0]
+            row[rr - n] = 1.0;
+        } else {                                     // [A B]
+            const int i = rr - n - d1;
+            for (int c = 0; c < n; ++c) row[c] = g.A[(size_t)c * d2 + i];
+            for (int c = 0; c < m; ++c) row[n + c] = g.B[(size_t)c * d2 + i];
+        }
+        bool any = false;
+        for (int c = 0; c < d; ++c) { if (std::fabs(row[c]) <= 1e-8) row[c] = 0.0; if (row[c] != 0.0) any = true; }
+        if ((std::isinf(lo[rr]) && std::isinf(up[rr])) || !any) continue;
+        r.add(row.data(), lo[rr], up[rr]);
+    }
+    if (r.m() == 0) return make_poly(std::move(r));
+    return simplify(make_poly(std::move(r)));
+}
+
+int GeoCache::local_piece_id(int node, const std::string& K, Worker* w) {
+    std::string key((const char*)&node, 4);
+    key += K;
+    return memo(local_piece_, key, [&]() -> int { return intern_poly(build_local_piece(node_info(node).g, K), w); });
+}
+
+int GeoCache::expand(int node, const std::string& K, Worker* w) {
+    std::string key((const char*)&node, 4);
+    key += K;
+    return memo(expand_, key, [&]() -> int {
+        const NodeInfo& n = node_info(node);
+        const int lp = local_piece_id(node, K, w);
+        const Poly& piece = poly(lp);
+        if (piece.m() > 0 && empty(lp, 1e-4, w)) return -1;
+        // project_and_permute: keep [z[0:nd]; w], scatter the columns to x's ordering
+        const int d = piece.d, nd = n.nd, np = (int)n.par.size();
+        std::vector<int> keep;
+        for (int j = 0; j < nd; ++j) keep.push_back(j);
+        for (int j = d - np; j < d; ++j) keep.push_back(j);
+        long nl = 0;
+        Poly pr = project(piece, keep, *w, &nl);
+        stats.lps += nl;
+        Rows r;
+        r.d = n.nv;
+        std::vector<double> a(n.nv);
+        for (int i = 0; i < pr.m(); ++i) {
+            std::fill(a.begin(), a.end(), 0.0);
+            for (int c = 0; c < nd; ++c) a[n.dec[c]] = pr.row(i)[c];
+            for (int c = 0; c < np; ++c) a[n.par[c]] = pr.row(i)[nd + c];
+            r.add(a.data(), pr.l[i], pr.u[i]);
+        }
+        return intern_poly(simplify(make_poly(std::move(r))), w);
+    });
+}
+
+// all_Ks (avi_solutions.jl:200-215) in lexicographic order; false when an index belongs to no set
+static bool all_Ks(const std::vector<int8_t>& mask, std::vector<std::string>& out) {
+    const size_t n = mask.size();
+    std::vector<std::vector<char>> choices(n);
+    for (size_t i = 0; i < n; ++i) {
+        for (int b = 0; b < 4; ++b) if ((mask[i] >> b) & 1) choices[i].push_back((char)(b + 1));
+        if (choices[i].empty()) return false;
+    }
+    std::vector<size_t> idx(n, 0);
+    std::string K(n, 0);
+    while (true) {
+        for (size_t i = 0; i < n; ++i) K[i] = choices[i][idx[i]];
+        out.push_back(K);
+        size_t i = n;
+        while (i > 0) {
+            --i;
+            if (++idx[i] < choices[i].size()) break;
+            idx[i] = 0;
+            if (i == 0) return true;
+        }
+        if (n == 0) return true;
+    }
+}
+
+int GeoCache::collect(int node, const std::vector<int8_t>& mask, Worker* w, bool* bad_mask) {
+    std::string key((const char*)&node, 4);
+    key.append((const char*)mask.data(), mask.size());
+    *bad_mask = false;
+    const int r = memo(collect_, key, [&]() -> int {
+        stats.collect_miss++;
+        std::vector<std::string> Ks;
+        if (!all_Ks(mask, Ks)) return -2;
+        std::vector<int> out;
+        std::set<int> seen_sets;
+        for (const std::string& K : Ks) {
+            const int p = expand(node, K, w);
+            if (p < 0) continue;
+            if (!seen_sets.insert(set_id(p)).second) continue;
+            out.push_back(p);
+        }
+        return intern_list(out);
+    });
+    if (r == -2) { *bad_mask = true; return -1; }
+    return r;
+}
+
+int GeoCache::leaves(const std::vector<int>& union_lists, const std::vector<int>& red_lengths, const std::vector<uint8_t>& in_bits,
+                     Worker* w) {
+    std::string key;
+    key.append((const char*)union_lists.data(), union_lists.size() * 4);
+    key.append((const char*)red_lengths.data(), red_lengths.size() * 4);
+    key.append((const char*)in_bits.data(), in_bits.size());
+    return memo(leaves_, key, [&]() -> int {
+        stats.combine_miss++;
+        const int n = (int)union_lists.size();
+        std::vector<std::vector<int>> unions(n);
+        std::vector<std::vector<uint8_t>> inside(n);
+        size_t bit = 0;
+        for (int k = 0; k < n; ++k) {
+            unions[k] = list(union_lists[k]);
+            for (int p : unions[k]) inside[k].push_back(poly(p).m() > 0 ? in_bits[bit++] : 1);
+        }
+        std::vector<int> out, idx(n, 0);
+        std::function<void(int, int)> rec = [&](int depth, int cur) {
+            if (depth == n) {
+                bool red = true;
+                for (int k = 0; k < n; ++k) if (!(idx[k] >= (int)unions[k].size() - red_lengths[k])) red = false;
+                if (red) return;                     // the all-complements "red zone" (intersection.jl:123)
+                out.push_back(cur);
+                return;
+            }
+            for (int k = 0; k < (int)unions[depth].size(); ++k) {
+                const int piece = unions[depth][k];
+                if (!inside[depth][k]) continue;
+                const int nxt = cur < 0 ? piece : intersect2(piece, cur, w);
+                if (empty(nxt, 1e-4, w)) continue;
+                idx[depth] = k;
+                rec(depth + 1, nxt);
+            }
+        };
+        rec(0, -1);
+        return intern_list(out);
+    });
+}
+
+// =================================================================================================================
+// coroutines
+// =================================================================================================================
+template <class T>
+struct Task {
+    struct promise_type {
+        T value{};
+        std::coroutine_handle<> cont;
+        Task get_return_object() { return Task{std::coroutine_handle<promise_type>::from_promise(*this)}; }
+        std::suspend_always initial_suspend() noexcept { return {}; }
+        struct Final {
+            bool await_ready() noexcept { return false; }
+            std::coroutine_handle<> await_suspend(std::coroutine_handle<promise_type> h) noexcept {
+                auto c = h.promise().cont;
+                return c ? c : std::noop_coroutine();
+            }
+            void await_resume() noexcept {}
+        };
+        Final final_suspend() noexcept { return {}; }
+        void return_value(T v) { value = std::move(v); }
+        void unhandled_exception() { std::terminate(); }
+    };
+    std::coroutine_handle<promise_type> h;
+    explicit Task(std::coroutine_handle<promise_type> hh) : h(hh) {}
+    Task(Task&& o) noexcept : h(o.h) { o.h = nullptr; }
+    Task(const Task&) = delete;
+    ~Task() { if (h) h.destroy(); }
+    bool await_ready() const noexcept { return false; }
+    std::coroutine_handle<> await_suspend(std::coroutine_handle<> c) noexcept { h.promise().cont = c; return h; }
+    T await_resume() { return std::move(h.promise().value); }
+};
+
+struct Sched {
+    std::vector<VerifyReq*> verify;
+    std::vector<QepReq*> qep;
+    std::vector<MemberReq*> member;
+    std::vector<CompReq*> comp;
+    bool idle() const { return verify.empty() && qep.empty() && member.empty() && comp.empty(); }
+    void post(VerifyReq* r) { verify.push_back(r); }
+    void post(QepReq* r) { qep.push_back(r); }
+    void post(MemberReq* r) { member.push_back(r); }
+    void post(CompReq* r) { comp.push_back(r); }
+};
+
+template <class R>
+struct AwaitReqs {
+    Sched& s;
+    std::vector<R>& reqs;
+    Join join;
+    AwaitReqs(Sched& ss, std::vector<R>& rr) : s(ss), reqs(rr) {}
+    bool await_ready() const noexcept { return reqs.empty(); }
+    void await_suspend(std::coroutine_handle<> h) {
+        join.pending = (int)reqs.size();
+        join.h = h.address();
+        for (auto& r : reqs) { r.join = &join; s.post(&r); }
+    }
+    void await_resume() const noexcept {}
+};
+
+struct LevelRet {
+    bool solved = false;
+    std::vector<int> S;                          // per player: list id, -1 = none
+};
+
+struct Inst {
+    int slot = 0;
+    std::vector<std::vector<std::vector<double>>> hist;     // per level: projections of earlier iterates
+    std::vector<double> pv;                                  // projections of the current x
+    SolveOut* out = nullptr;
+};
+
+struct Ctx {
+    GeoCache& c;
+    Worker* w;
+    Sched sched;
+    const NetData& net;
+    Ctx(GeoCache& cc, Worker* ww) : c(cc), w(ww), net(cc.net()) {}
+};
+
+static bool cycle_hit(const std::vector<double>& pv, const std::vector<double>& prev) {
+    double dd = 0.0, na = 0.0, nb = 0.0;
+    for (size_t k = 0; k < pv.size(); ++k) {
+        const double e = pv[k] - prev[k];
+        dd = std::fma(e, e, dd); na = std::fma(pv[k], pv[k], na); nb = std::fma(prev[k], prev[k], nb);
+    }
+    return std::sqrt(dd) <= 1.4901161193847656e-8 * std::fmax(std::sqrt(na), std::sqrt(nb));       // isapprox, rtol = sqrt(eps)
+}
+
+// Iterators.product order: the FIRST iterator varies fastest (qp_processing.jl:169)
+static void julia_product(const std::vector<int>& sizes, std::vector<std::vector<int>>& out) {
+    const size_t n = sizes.size();
+    for (int s : sizes) if (s == 0) return;
+    std::vector<int> idx(n, 0);
+    while (true) {
+        out.push_back(idx);
+        size_t i = 0;
+        while (i < n && ++idx[i] == sizes[i]) { idx[i] = 0; ++i; }
+        if (i == n) break;
+    }
+}
+
+static Task<LevelRet> solve_base(Ctx& cx, Inst& I, int level) {
+    const NetData& net = cx.net;
+    GeoCache& c = cx.c;
+    Worker* w = cx.w;
+    LevelRet fail;
+    auto failed = [&](int err) {
+        for (auto& h : I.hist) h.clear();
+        if (!I.out->error) I.out->error = err;
+        return fail;
+    };
+    const std::vector<int>& players = net.levels[level];
+    std::vector<int> kids;
+    for (int p : players) kids.insert(kids.end(), net.children[p].begin(), net.children[p].end());
+    std::sort(kids.begin(), kids.end());
+    kids.erase(std::unique(kids.begin(), kids.end()), kids.end());
+
+    for (int it = 0; it < net.max_iters; ++it) {
+        I.out->level_iters[level]++;
+        if (net.check_for_cycling) {
+            if (net.num_projections == 0) co_return failed(ERR_NOPROJ);
+            for (const auto& prev : I.hist[level]) if (cycle_hit(I.pv, prev)) co_return failed(ERR_CYCLE);
+            I.hist[level].push_back(I.pv);
+        }
+        std::vector<int> S(net.nplayers, -1);
+        if (level + 1 < net.nlevels) {
+            LevelRet low = co_await solve_base(cx, I, level + 1);
+            if (!low.solved) co_return fail;
+            S = std::move(low.S);
+        }
+        // ---- verify phase: every player against every combination of its children's pieces -----------------------
+        struct PV { int pid; std::vector<std::vector<int>> combos; int first_req; };
+        std::vector<PV> pvs;
+        std::vector<VerifyReq> reqs;
+        for (int pid : players) {
+            PV pv;
+            pv.pid = pid; pv.first_req = (int)reqs.size();
+            const std::vector<int>& ch = net.children[pid];
+            if (!ch.empty()) {
+                std::vector<int> sizes;
+                for (int j : ch) {
+                    if (S[j] < 0 || c.list(S[j]).empty()) co_return failed(ERR_UNPOPULATED);
+                    sizes.push_back((int)c.list(S[j]).size());
+                }
+                julia_product(sizes, pv.combos);
+                for (const auto& combo : pv.combos) {
+                    std::vector<int> pieces;
+                    for (size_t k = 0; k < ch.size(); ++k) pieces.push_back(c.list(S[ch[k]])[combo[k]]);
+                    VerifyReq r;
+                    r.inst = I.slot; r.node = c.node(pid, pieces, w);
+                    reqs.push_back(std::move(r));
+                }
+            } else {
+                VerifyReq r;
+                r.inst = I.slot; r.node = c.node(pid, {}, w);
+                reqs.push_back(std::move(r));
+            }
+            pvs.push_back(std::move(pv));
+        }
+        co_await AwaitReqs<VerifyReq>(cx.sched, reqs);
+        bool equilibrium = true;
+        for (const auto& r : reqs) if (!r.solution) equilibrium = false;
+
+        if (equilibrium) {
+            // ---- graph phase (process_qp's solution graphs + combine) ------------------------------------------------
+            struct Comb { int pid; std::vector<int> union_lists, red; std::vector<int> flat; };
+            std::vector<Comb> combs;
+            std::vector<int> S_out(net.nplayers, -1);
+            for (const PV& pv : pvs) {
+                const int pid = pv.pid;
+                const bool gen = level != 0 || net.gen_solution_map;
+                if (!gen) continue;
+                const std::vector<int>& ch = net.children[pid];
+                if (ch.empty()) {
+                    bool bad = false;
+                    const int lid = c.collect(reqs[pv.first_req].node, reqs[pv.first_req].mask, w, &bad);
+                    if (bad) co_return failed(ERR_MASK);
+                    if (c.list(lid).empty()) co_return failed(ERR_GRAPH_EMPTY);
+                    S_out[pid] = lid;
+                    continue;
+                }
+                std::vector<int> sols;
+                for (size_t k = 0; k < pv.combos.size(); ++k) {
+                    const VerifyReq& r = reqs[pv.first_req + k];
+                    bool bad = false;
+                    const int lid = c.collect(r.node, r.mask, w, &bad);
+                    if (bad) co_return failed(ERR_MASK);
+                    sols.push_back(c.remove_subsets(lid, w));
+                }
+                if (sols.size() == 1) { S_out[pid] = sols[0]; continue; }
+                Comb cb;
+                cb.pid = pid;
+                int total = 0;
+                for (size_t k = 0; k < pv.combos.size(); ++k) {
+                    std::vector<int> pieces;
+                    for (size_t q = 0; q < ch.size(); ++q) pieces.push_back(c.list(S[ch[q]])[pv.combos[k][q]]);
+                    const int region = c.intersect_all(pieces, w);
+                    const std::vector<int>& comp = c.complement_of(region, w);
+                    std::vector<int> combined = c.list(sols[k]);
+                    combined.insert(combined.end(), comp.begin(), comp.end());
+                    total += (int)combined.size();
+                    cb.red.push_back((int)comp.size());
+                    for (int p : combined) if (c.poly(p).m() > 0) cb.flat.push_back(p);
+                    cb.union_lists.push_back(c.intern_list(combined));
+                }
+                if (cb.union_lists.size() > 3 && total > 20) { if (!I.out->error) I.out->error = ERR_COMBINE; co_return fail; }
+                combs.push_back(std::move(cb));
+            }
+            if (!combs.empty()) {
+                std::vector<MemberReq> mreqs(combs.size());
+                for (size_t k = 0; k < combs.size(); ++k) { mreqs[k].inst = I.slot; mreqs[k].pieces = &combs[k].flat; }
+                co_await AwaitReqs<MemberReq>(cx.sched, mreqs);
+                for (size_t k = 0; k < combs.size(); ++k)
+                    S_out[combs[k].pid] = c.leaves(combs[k].union_lists, combs[k].red, mreqs[k].in, w);
+            }
+            for (int pid : players) {
+                if (S_out[pid] >= 0 && net.remove_subsets_at[level]) S[pid] = c.remove_subsets(S_out[pid], w);
+                else S[pid] = S_out[pid];
+            }
+            if (level == 0) for (auto& h : I.hist) h.clear();
+            LevelRet ok;
+            ok.solved = true; ok.S = std::move(S);
+            co_return ok;
+        }
+        // ---- not an equilibrium: solve_qep with the offending child pieces (algorithm.jl:68-101) -----------------------
+        std::vector<int> assignment(kids.size());
+        for (size_t k = 0; k < kids.size(); ++k) assignment[k] = c.list(S[kids[k]])[0];
+        for (const PV& pv : pvs) {
+            const std::vector<int>& ch = net.children[pv.pid];
+            if (ch.empty()) continue;
+            for (size_t k = 0; k < pv.combos.size(); ++k) {
+                if (reqs[pv.first_req + k].solution) continue;
+                for (size_t q = 0; q < ch.size(); ++q) {
+                    const size_t pos = std::lower_bound(kids.begin(), kids.end(), ch[q]) - kids.begin();
+                    assignment[pos] = c.list(S[ch[q]])[pv.combos[k][q]];
+                }
+                break;                               // the first combination that fails
+            }
+        }
+        std::vector<QepReq> q(1);
+        q[0].inst = I.slot; q[0].gavi = c.level_gavi(level, assignment, w);
+        co_await AwaitReqs<QepReq>(cx.sched, q);
+        I.out->pivots += q[0].pivots;
+        if (q[0].status != 1) co_return failed(ERR_AVI);
+        if (!q[0].moved) co_return failed(ERR_DISAGREE);
+        I.pv = std::move(q[0].pv);
+    }
+    co_return failed(ERR_MAXIT);
+}
+
+static Task<int> solve_root(Ctx& cx, Inst& I) {
+    LevelRet r = co_await solve_base(cx, I, 0);
+    I.out->solved = r.solved;
+    if (r.solved) I.out->sol = std::move(r.S);
+    co_return 0;
+}
+
+// =================================================================================================================
+// NetSolver
+// =================================================================================================================
+NetSolver::NetSolver(NetData net, std::vector<Poly> polys, std::unique_ptr<Store> store)
+    : net_(std::move(net)), store_(std::move(store)) {
+    cache_.reset(new GeoCache(net_, store_.get()));
+    workers_.emplace_back(store_->make_worker());
+    std::vector<int> ids;
+    for (Poly& P : polys) ids.push_back(cache_->intern_poly(std::move(P), workers_[0].get()));
+    for (auto& b : net_.base) for (int& k : b) k = ids[k];
+}
+NetSolver::~NetSolver() { workers_.clear(); cache_.reset(); store_.reset(); }
+
+void NetSolver::run_shard(int tid, int lo, int hi, const double* inits, double* x_out, std::vector<SolveOut>& outs) {
+    const int B = hi - lo, nv = net_.nv;
+    if (B <= 0) return;
+    Worker* w = workers_[tid].get();
+    w->set_batch(B, inits + (size_t)lo * nv);
+    Ctx cx(*cache_, w);
+    std::vector<Inst> insts(B);
+    std::vector<Task<int>> roots;
+    roots.reserve(B);
+    const int np = net_.check_for_cycling ? net_.num_projections : 0;
+    for (int b = 0; b < B; ++b) {
+        Inst& I = insts[b];
+        I.slot = b;
+        I.out = &outs[lo + b];
+        *I.out = SolveOut();
+        I.out->level_iters.assign(net_.nlevels, 0);
+        I.out->sol.assign(net_.nplayers, -1);
+        I.hist.resize(net_.nlevels);
+        I.pv.assign(np, 0.0);
+        const double* x = inits + (size_t)(lo + b) * nv;
+        for (int k = 0; k < np; ++k) {
+            double acc = 0.0;
+            for (int j = 0; j < nv; ++j) acc = std::fma(x[j], net_.proj[(size_t)k * nv + j], acc);
+            I.pv[k] = acc;
+        }
+        roots.push_back(solve_root(cx, I));
+    }
+    for (auto& t : roots) t.h.resume();
+    Stats& st = cache_->stats;
+    std::vector<VerifyReq*> verify;
+    std::vector<QepReq*> qep;
+    std::vector<MemberReq*> member;
+    std::vector<CompReq*> comp;
+    while (!cx.sched.idle()) {
+        verify.swap(cx.sched.verify); qep.swap(cx.sched.qep); member.swap(cx.sched.member); comp.swap(cx.sched.comp);
+        cx.sched.verify.clear(); cx.sched.qep.clear(); cx.sched.member.clear(); cx.sched.comp.clear();
+        st.rounds++;
+        st.requests += (long)(verify.size() + qep.size() + member.size() + comp.size());
+        // one batched call per (kind, resident object); stable order so that runs are reproducible
+        std::stable_sort(verify.begin(), verify.end(), [](const VerifyReq* a, const VerifyReq* b) { return a->node < b->node; });
+        std::stable_sort(qep.begin(), qep.end(), [](const QepReq* a, const QepReq* b) { return a->gavi < b->gavi; });
+        std::stable_sort(comp.begin(), comp.end(), [](const CompReq* a, const CompReq* b) { return a->node < b->node; });
+        for (size_t i = 0; i < verify.size();) {
+            size_t j = i;
+            while (j < verify.size() && verify[j]->node == verify[i]->node) ++j;
+            const NodeInfo& info = cache_->node_info(verify[i]->node);
+            w->run_verify(verify[i]->node, info, &verify[i], (int)(j - i), net_.level_of[info.pid] == 0);
+            st.calls++;
+            i = j;
+        }
+        for (size_t i = 0; i < qep.size();) {
+            size_t j = i;
+            while (j < qep.size() && qep[j]->gavi == qep[i]->gavi) ++j;
+            const LevelGaviInfo& info = cache_->gavi_info(qep[i]->gavi);
+            w->run_qep(qep[i]->gavi, info, &qep[i], (int)(j - i), info.level == 0);
+            st.calls++;
+            i = j;
+        }
+        if (!member.empty()) { w->run_member(member.data(), (int)member.size()); st.calls++; }
+        for (size_t i = 0; i < comp.size();) {
+            size_t j = i;
+            while (j < comp.size() && comp[j]->node == comp[i]->node) ++j;
+            w->run_comp(comp[i]->node, cache_->node_info(comp[i]->node), &comp[i], (int)(j - i));
+            st.calls++;
+            i = j;
+        }
+        w->finish();
+        auto wake = [](Join* jn) {
+            if (--jn->pending == 0) std::coroutine_handle<>::from_address(jn->h).resume();
+        };
+        for (auto* r : verify) wake(r->join);
+        for (auto* r : qep) wake(r->join);
+        for (auto* r : member) wake(r->join);
+        for (auto* r : comp) wake(r->join);
+        verify.clear(); qep.clear(); member.clear(); comp.clear();
+    }
+    std::vector<double> xf((size_t)B * nv);
+    w->download(x_out + (size_t)lo * nv, xf.data());
+    for (int b = 0; b < B; ++b)
+        if (!outs[lo + b].solved) std::memcpy(x_out + (size_t)(lo + b) * nv, xf.data() + (size_t)b * nv, sizeof(double) * nv);
+}
+
+void NetSolver::solve_batched(int B, const double* inits, double* x_out, std::vector<SolveOut>& outs, int threads) {
+    outs.assign(B, SolveOut());
+    if (B <= 0) return;
+    if (threads < 1) threads = 1;
+    if (threads > B) threads = B;
+    while ((int)workers_.size() < threads) workers_.emplace_back(store_->make_worker());
+    if (threads == 1) { run_shard(0, 0, B, inits, x_out, outs); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; ++t) {
+        const int base = B / threads, rem = B % threads;
+        const int lo = t * base + std::min(t, rem), hi = lo + base + (t < rem ? 1 : 0);
+        th.emplace_back([=, &outs]() { run_shard(t, lo, hi, inits, x_out, outs); });
+    }
+    for (auto& t : th) t.join();
+}
+
+}  // namespace qpnnet

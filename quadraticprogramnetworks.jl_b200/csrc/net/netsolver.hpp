@@ -1,0 +1,229 @@
+// Native batched host state machine of solve(qpn, inits::Matrix) for networks with children.
+//
+// What it replaces, in the reference: the recursion of solve_base! (/root/reference/src/algorithm.jl:1-127),
+// process_qp and combine (src/qp_processing.jl:151-291), the IntersectionRoot walk (src/intersection.jl:55-151) and
+// collect(LocalGAVISolutions) with all_Ks / local_piece / expand / project_and_permute
+// (src/avi_solutions.jl:200-215,241-321,400-496,79-90).  Every numeric step -- verify_solution, comp_indices,
+// solve_qep, membership, every LP of the set algebra -- is a request to a numeric backend (the CUDA engine in
+// libqpn_cuda; the C oracle in the test / baseline build under oracle/).
+//
+// Shape.  Each instance of the batch is a C++20 coroutine that reads like the per-instance recursion.  When it
+// needs numbers it posts requests and suspends; a worker thread resumes its instances until all of them wait, groups
+// the pending requests by (kind, resident object) -- instances that verify the same node against the same child
+// pieces, solve the same level GAVI -- and hands each group to the backend as ONE batched call over a list of
+// instance slots (x stays resident in the backend).  Everything geometric is a pure function of exact problem data
+// (node, child pieces, complementarity recipe K), never of the instance, so it is memoised in a cache shared by all
+// instances, worker threads and batches of the net; between device calls an instance costs a few hash
+// look-ups.
+#pragma once
+#include <atomic>
+#include <cstdint>
+#include <deque>
+#include <functional>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <shared_mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "poly.hpp"
+
+namespace qpnnet {
+
+// ---- the network as plain arrays (what setup(:name) produces; programs.jl:79-116) ----------------------------
+struct NetData {
+    int nv = 0, nplayers = 0, nlevels = 0;
+    std::vector<std::vector<double>> Q;          // per player: nv x nv, row-major
+    std::vector<std::vector<double>> q;          // per player: nv
+    std::vector<std::vector<int>> base;          // per player: poly ids of its own constraints (constraint_indices order)
+    std::vector<std::vector<int>> children;      // network_edges (sorted)
+    std::vector<std::vector<int>> dec;           // decision_inds (sorted; programs.jl:340-346)
+    std::vector<std::vector<int>> levels;        // players per level (sorted), levels[0] = level 1
+    std::vector<int> level_of;                   // 0-based level per player
+    // options (QPNetOptions, programs.jl:61-77)
+    int max_iters = 150, num_projections = 4, exploration_vertices = 0, gen_solution_map = 0, check_for_cycling = 1;
+    std::vector<char> remove_subsets_at;         // per level (levels_to_remove_subsets)
+    std::vector<double> proj;                    // num_projections x nv, row-major
+};
+
+// ---- resident objects ---------------------------------------------------------------------------------------
+// One node's view for verify_solution (qp_processing.jl:57-66) plus its single-node GAVI (avi.jl:447-475).
+struct NodeInfo {
+    int pid = 0, nd = 0, nv = 0, m = 0;
+    std::vector<int> polys;                      // base constraint polys followed by the chosen child pieces
+    std::vector<double> Qd, qd, A, l, u;         // column-major: Qd nd x nv, A m x nv
+    std::vector<int32_t> dec, par;
+    GaviData g;                                  // z = [x_dec; lam], w = x_par
+};
+
+// The joint KKT system of a level's players for one assignment of child pieces (avi.jl:305-377,382-404).
+struct LevelGaviInfo {
+    int level = 0;
+    GaviData g;
+    std::vector<int32_t> dec, par;
+};
+
+// ---- requests an instance posts ----------------------------------------------------------------------------------
+struct Join { int pending = 0; void* h = nullptr; };            // coroutine handle address, resumed when pending hits 0
+
+struct VerifyReq {          // verify_solution at the instance's x, then comp_indices of the node GAVI at (x, lam)
+    int inst = 0, node = 0;
+    Join* join = nullptr;
+    uint8_t solution = 0;
+    std::vector<int8_t> mask;                    // nd + m masks (filled when solution)
+    std::vector<double> zw;                      // [z; w] of the node GAVI (only when want_zw)
+    bool want_zw = false;
+};
+struct QepReq {             // solve_qep for a level GAVI; on success x[dec] is replaced
+    int inst = 0, gavi = 0;
+    Join* join = nullptr;
+    int32_t status = 0, pivots = 0;
+    uint8_t moved = 0;                           // norm(xnew - x) >= 1e-4
+    std::vector<double> pv;                      // projections of the new x (cycle check of the next iteration)
+};
+struct MemberReq {          // x in closure(piece) for a list of pieces (intersection.jl:74,82)
+    int inst = 0;
+    Join* join = nullptr;
+    const std::vector<int>* pieces = nullptr;
+    std::vector<uint8_t> in;
+};
+struct CompReq {            // comp_indices of a node GAVI at an explicit point (vertex exploration)
+    int inst = 0, node = 0;
+    Join* join = nullptr;
+    std::vector<double> zw;
+    std::vector<int8_t> mask;
+};
+struct VertReq {            // vertices of the multiplier polytope of a node at the instance's primal point
+    int inst = 0, node = 0;
+    Join* join = nullptr;
+    std::vector<double> zw;                      // the instance's [z; w]
+    std::vector<int8_t> K;                       // the recipe whose piece is sliced
+    std::vector<std::vector<double>> verts;      // out: multiplier parts of the vertices
+};
+
+// ---- numeric backend ---------------------------------------------------------------------------------------------
+struct Worker : LPBackend {
+    // instance slots 0..B-1 of this worker: x = x_fail = init (nv x B column-major)
+    virtual void set_batch(int B, const double* x_init) = 0;
+    // enqueue batched calls (may run asynchronously until finish())
+    virtual void run_verify(int node, const NodeInfo& info, VerifyReq** reqs, int n, bool snap) = 0;
+    virtual void run_qep(int gavi, const LevelGaviInfo& info, QepReq** reqs, int n, bool snap) = 0;
+    virtual void run_member(MemberReq** reqs, int n) = 0;
+    virtual void run_comp(int node, const NodeInfo& info, CompReq** reqs, int n) = 0;
+    virtual void finish() = 0;                   // all results of the enqueued calls are in their requests
+    virtual void download(double* x_out, double* x_fail_out) = 0;
+    virtual int64_t launches() const { return 0; }
+};
+struct Store {              // shared by the workers of one net: resident copies of nodes / GAVIs / pieces
+    virtual ~Store() {}
+    virtual Worker* make_worker() = 0;
+    // called once per object, under the cache's creation lock, with the worker that met the object first
+    virtual void new_node(int id, const NodeInfo& info, Worker* w) = 0;
+    virtual void new_gavi(int id, const LevelGaviInfo& info, Worker* w) = 0;
+    virtual void new_piece(int id, const Poly& P, Worker* w) = 0;
+};
+
+// ---- the cache of everything instance-independent -------------------------------------------------------------
+struct VecHash {
+    size_t operator()(const std::vector<int>& v) const {
+        uint64_t h = 0x9E3779B97F4A7C15ull ^ v.size();
+        for (int x : v) { h ^= (uint64_t)(uint32_t)x + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); }
+        return (size_t)h;
+    }
+};
+
+struct Stats {
+    std::atomic<long> lps{0}, rounds{0}, requests{0}, calls{0}, pieces{0}, nodes{0}, gavis{0}, collect_miss{0}, combine_miss{0};
+};
+
+class GeoCache {
+  public:
+    GeoCache(const NetData& net, Store* store) : net_(net), store_(store) {}
+    const NetData& net() const { return net_; }
+    Stats stats;
+
+    // polyhedra interned by exact content
+    int intern_poly(Poly&& P, Worker* w);
+    const Poly& poly(int id) const { std::shared_lock<std::shared_mutex> lk(mu_); return polys_[id]; }
+    int set_id(int id) const { std::shared_lock<std::shared_mutex> lk(mu_); return set_ids_[id]; }
+    int npolys() const { std::shared_lock<std::shared_mutex> lk(mu_); return (int)polys_.size(); }
+    // lists of polyhedra (solution graphs) interned by their ids
+    int intern_list(const std::vector<int>& ids);
+    const std::vector<int>& list(int id) const { std::shared_lock<std::shared_mutex> lk(mu_); return lists_[id]; }
+
+    int node(int pid, const std::vector<int>& pieces, Worker* w);                 // (player, child pieces) -> node id
+    const NodeInfo& node_info(int id) const { std::shared_lock<std::shared_mutex> lk(mu_); return nodes_[id]; }
+    int level_gavi(int level, const std::vector<int>& assignment, Worker* w);     // (level, piece per child) -> gavi id
+    const LevelGaviInfo& gavi_info(int id) const { std::shared_lock<std::shared_mutex> lk(mu_); return gavis_[id]; }
+
+    // geometry, memoised (the LPs run on worker w)
+    bool empty(int poly, double tol, Worker* w);                                  // exemplar(P)[0]
+    bool subset(int p1, int p2, Worker* w);
+    int remove_subsets(int list, Worker* w);
+    int intersect2(int a, int b, Worker* w);
+    int intersect_all(const std::vector<int>& ids, Worker* w);
+    const std::vector<int>& complement_of(int poly, Worker* w);
+    // (node, recipe K) -> projected piece id, or -1 when the local piece is empty (avi_solutions.jl:241-261)
+    int expand(int node, const std::string& K, Worker* w);
+    // the lifted local piece of (node, K) over (z, w) (avi_solutions.jl:400-496)
+    int local_piece_id(int node, const std::string& K, Worker* w);
+    // collect(LocalGAVISolutions) without vertex exploration: (node, mask) -> list of piece ids
+    int collect(int node, const std::vector<int8_t>& mask, Worker* w, bool* bad_mask);
+    // all non-empty leaves of the intersection tree for one membership pattern (intersection.jl:55-151)
+    int leaves(const std::vector<int>& union_lists, const std::vector<int>& red_lengths, const std::vector<uint8_t>& in_bits,
+               Worker* w);
+
+  private:
+    template <class Map, class Key, class F> auto memo(Map& map, const Key& key, F&& compute) -> typename Map::mapped_type;
+    const NetData& net_;
+    Store* store_;
+    mutable std::shared_mutex mu_;
+    std::mutex create_mu_;                       // serialises the creation of resident objects
+    std::deque<Poly> polys_;
+    std::deque<int> set_ids_;
+    std::unordered_map<std::string, int> poly_by_exact_, set_by_key_;
+    std::deque<std::vector<int>> lists_;
+    std::unordered_map<std::vector<int>, int, VecHash> list_ids_;
+    std::deque<NodeInfo> nodes_;
+    std::unordered_map<std::vector<int>, int, VecHash> node_ids_;
+    std::deque<LevelGaviInfo> gavis_;
+    std::unordered_map<std::vector<int>, int, VecHash> gavi_ids_;
+    std::unordered_map<uint64_t, char> empty_, subset_;
+    std::unordered_map<int, int> remove_subsets_;
+    std::unordered_map<uint64_t, int> intersect2_;
+    std::unordered_map<int, std::vector<int>> complement_;
+    std::unordered_map<std::string, int> expand_, local_piece_, collect_;
+    std::unordered_map<std::string, int> leaves_;
+};
+
+// ---- the solver --------------------------------------------------------------------------------------------------
+struct SolveOut {
+    uint8_t solved = 0;
+    std::vector<int> level_iters;                // loop passes of solve_base! per level, summed over its calls
+    std::vector<int> sol;                        // per player: list id of its solution graph, -1 = none
+    int error = 0;                               // 0 none; see ERR_* in netsolver.cpp
+    int pivots = 0;
+};
+
+class NetSolver {
+  public:
+    // polys: the constraint polys net.base refers to (by position); they are interned first
+    NetSolver(NetData net, std::vector<Poly> polys, std::unique_ptr<Store> store);
+    ~NetSolver();
+    // inits: nv x B column-major.  x_out: nv x B (x_opt, or x_fail when not solved).
+    void solve_batched(int B, const double* inits, double* x_out, std::vector<SolveOut>& outs, int threads);
+    GeoCache& cache() { return *cache_; }
+    const NetData& net() const { return net_; }
+    std::string last_error;
+
+  private:
+    void run_shard(int tid, int lo, int hi, const double* inits, double* x_out, std::vector<SolveOut>& outs);
+    NetData net_;
+    std::unique_ptr<Store> store_;
+    std::unique_ptr<GeoCache> cache_;
+    std::vector<std::unique_ptr<Worker>> workers_;
+};
+
+}  // namespace qpnnet
