@@ -51,31 +51,74 @@ class BatchedSolver:
             raise NotImplementedError("multi-level networks: batched host recursion is the next row (SURVEY.md 8f-2)")
         return self.resident_level(1).solve(np.ascontiguousarray(inits, dtype=np.float64), out=out, want_lam=want_lam)
 
+    def native_net(self, threads=None):
+        """The native state machine for networks with children (qpn_net_*, csrc/net/): built once per net, keeps its
+        resident nodes / level GAVIs / pieces across batches."""
+        if getattr(self, "_native", None) is None:
+            from .netsolve import NetBinding
+            self._native = NetBinding(self.net, self.engine.lib, "qpn_net_", handle=self.engine.h)
+        if threads:
+            self._native.set_option("threads", threads)
+        return self._native
+
     def close(self):
         for lv in self._levels.values():
             lv.release()
         self._levels.clear()
+        if getattr(self, "_native", None) is not None:
+            self._native.close()
+            self._native = None
 
 
 _solvers = {}
 
 
+def _fingerprint(net):
+    """What a resident solver snapshots: the options and the shape of the net.  The reference lets a user change
+    options between solves (set_options!, programs.jl:312-320); a changed fingerprint rebuilds the device copy."""
+    import dataclasses
+    return (repr(dataclasses.astuple(net.options)), len(net.qps), len(net.constraints), net.n_vars)
+
+
+def _evict(key):
+    s = _solvers.pop(key, None)
+    if s is not None:
+        try:
+            s[1].close()
+        except Exception:
+            pass
+
+
 def _solver_for(net, device=0):
+    """One BatchedSolver per (net object, device); dropped when the net is garbage collected (weakref.finalize) and
+    rebuilt when its options / shape change."""
+    import weakref
     key = (id(net), device)
-    if key not in _solvers:
-        _solvers[key] = BatchedSolver(net, device=device)
-    return _solvers[key]
+    fp = _fingerprint(net)
+    hit = _solvers.get(key)
+    if hit is not None and hit[0] != fp:
+        _evict(key)
+        hit = None
+    if hit is None:
+        hit = _solvers[key] = (fp, BatchedSolver(net, device=device))
+        weakref.finalize(net, _evict, key)
+    return hit[1]
 
 
-def solve(qpn, x_init=None, device=0, workers=1):
+def solve(qpn, x_init=None, device=0, workers=1, native=True, threads=None, keep_sol=None):
     """solve(qpn), solve(qpn, x_init) -> one result; solve(qpn, inits::Matrix) -> list of results.
 
     Julia's `inits::Matrix` is n_vars x B column-major, i.e. a (B, n_vars) C-contiguous array here.
-    workers > 1 (multi-level batches only): the host recursion sharded over that many processes on `device`
-    (workers.py); results are identical, `Sol` is not returned."""
+    Networks with children (or with the solution map requested) run on the native batched state machine of
+    libqpn_cuda (`qpn_net_solve_batched`; `threads` host threads drive the batch); `keep_sol` (default: single
+    instances only) also returns the solution graphs `Sol`.  native=False runs the Python host mirror of the same
+    logic instead (one recursion per instance; `workers` > 1 shards it over that many processes, workers.py)."""
     x = qpn.default_initialization if x_init is None else np.asarray(x_init, dtype=np.float64)
     single = x.ndim == 1
     solver = _solver_for(qpn, device)
+    if (qpn.num_levels() != 1 or qpn.options.gen_solution_map) and native:
+        outs = solver.native_net(threads).solve(np.atleast_2d(x), keep_sol=single if keep_sol is None else keep_sol)
+        return outs[0] if single else outs
     if qpn.num_levels() != 1 or qpn.options.gen_solution_map:
         # networks with children (or with the solution map requested): the per-instance recursion of solve_base!,
         # every numeric step on the device.  A batch runs one recursion per instance against a BatchingEngine,

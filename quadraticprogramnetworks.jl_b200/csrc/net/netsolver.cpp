@@ -832,7 +832,7 @@ void NetSolver::solve_batched(int B, const double* inits, double* x_out, std::ve
     for (int t = 0; t < threads; ++t) {
         const int base = B / threads, rem = B % threads;
         const int lo = t * base + std::min(t, rem), hi = lo + base + (t < rem ? 1 : 0);
-        th.emplace_back([=, &outs]() { run_shard(t, lo, hi, inits, x_out, outs); });
+        th.emplace_back([this, t, lo, hi, inits, x_out, &outs]() { run_shard(t, lo, hi, inits, x_out, outs); });
     }
     for (auto& t : th) t.join();
 }

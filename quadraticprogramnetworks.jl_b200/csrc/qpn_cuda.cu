@@ -3,6 +3,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <deque>
+#include <mutex>
+#include <shared_mutex>
 #include <string>
 #include <vector>
 
@@ -721,3 +724,4 @@ extern "C" int qpn_halfspace_in_batched(qpn_handle* h, int npoly, int d, int mto
 }
 
 #include "qpn_level_host.inc"
+#include "qpn_net_host.inc"

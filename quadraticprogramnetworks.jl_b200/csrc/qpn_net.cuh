@@ -1,0 +1,147 @@
+// Kernels of the native network state machine (csrc/net/): the numeric requests of a batch of instances whose x
+// stays resident on the GPU (X: nv x slots, column-major).  Every launch works on a LIST of instance slots -- the
+// instances that asked for the same thing this round -- against a resident node / level GAVI / piece.
+//   net_verify_kernel : verify_solution (qp_processing.jl:57-149) at x, then comp_indices (avi_solutions.jl:587-612)
+//                       of the node's own GAVI at (x, lam) -- what process_qp needs before it builds a solution graph
+//   net_qep_kernel    : solve_qep (avi.jl:382-444) for a level GAVI with plans, the 1e-4 disagreement test and the
+//                       cycle-check projections of the new iterate (algorithm.jl:14-30,95-99); x updated in place
+//   net_member_kernel : x in closure(piece) (intersection.jl:74,82 through sets.jl:820-825), one warp per (instance, piece)
+// The arithmetic of each is the arithmetic of the single-purpose kernels (same device functions, same summation
+// orders), so results are bit-equal to the C oracle's.
+#pragma once
+#include "qpn_level.cuh"
+
+namespace qpn {
+
+// grid = n requests, block = roundup32(max(m, nd, 1)).
+// Dynamic smem: verify_solution_kernel's layout (Tab(m, m+1) + VerifySmem + x(nv) + qt(nd) + ax(m)).
+__global__ void net_verify_kernel(const __grid_constant__ NodeDesc node, const __grid_constant__ GaviDesc g,
+                                  const int32_t* __restrict__ par, int n, const int32_t* __restrict__ inst,
+                                  const double* __restrict__ X, double* __restrict__ Xf, double tol,
+                                  uint8_t* __restrict__ solution_out, int8_t* __restrict__ mask_out) {
+    const int b = blockIdx.x, i = threadIdx.x, m = node.m, nd = node.nd;
+    const int slot = inst[b];
+    const int tn = m > 0 ? m : 1;
+    Tab tab;
+    tab_carve(tab, tn, tn + 1, 0);
+    VerifySmem vs;
+    const int p = (int)tab_smem_bytes(tn, tn + 1);
+    verify_carve(vs, nd, m, p);
+    double* xs = reinterpret_cast<double*>(qpn_smem + p + verify_smem_bytes(nd, m));
+    double* qt = xs + node.nv;
+    double* ax = qt + nd;
+    for (int j = i; j < node.nv; j += blockDim.x) {
+        const double v = X[(size_t)slot * node.nv + j];
+        xs[j] = v;
+        if (Xf) Xf[(size_t)slot * node.nv + j] = v;       // the level-1 iterate as the reference would report it on failure
+    }
+    QPN_SYNC();
+    node_products(node, xs, qt, ax);
+    QPN_SYNC();
+    int how = 0, piv = 0;
+    const int sol = verify_solution_smem<false>(tab, vs, node, qt, ax, tol, &how, &piv);
+    QPN_SYNC();
+    const int dz = nd + m;
+    if (sol) {
+        // comp_indices at z = [x_dec; lam], w = x_par (comp_indices_kernel's sums, term for term)
+        const double* lam = vs.lam_out();
+        for (int r = i; r < dz; r += blockDim.x) {
+            double acc = 0.0, acc2 = 0.0;
+            int8_t mk;
+            if (r < g.d1) {
+                for (int j = 0; j < nd; ++j) acc = fma(g.M[(size_t)j * g.d1 + r], xs[node.dec[j]], acc);
+                for (int j = 0; j < m; ++j) acc = fma(g.M[(size_t)(nd + j) * g.d1 + r], lam[j], acc);
+                for (int j = 0; j < g.np; ++j) acc2 = fma(g.N[(size_t)j * g.d1 + r], xs[par[j]], acc2);
+                const double rr = (acc + acc2) + g.o[r];
+                mk = comp_mask(g.l1[r], g.u1[r], rr, xs[node.dec[r]], 1e-2);
+            } else {
+                const int k = r - g.d1;
+                for (int j = 0; j < nd; ++j) acc = fma(g.A[(size_t)j * g.d2 + k], xs[node.dec[j]], acc);
+                for (int j = 0; j < m; ++j) acc = fma(g.A[(size_t)(nd + j) * g.d2 + k], lam[j], acc);
+                for (int j = 0; j < g.np; ++j) acc2 = fma(g.B[(size_t)j * g.d2 + k], xs[par[j]], acc2);
+                const double s = acc + acc2;
+                mk = comp_mask(g.l2[k], g.u2[k], lam[k], s, 1e-2);
+            }
+            mask_out[(size_t)b * dz + r] = mk;
+        }
+    }
+    if (i == 0) solution_out[b] = (uint8_t)sol;
+}
+
+// grid = n requests, block = roundup32(lifted n).  Dynamic smem: gavi_solve_kernel's layout + x(nv) + xn(nv) + pv(nproj).
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 896 / MAXT)
+net_qep_kernel(const __grid_constant__ GaviDesc g, const __grid_constant__ GaviPlans plans, const int32_t* __restrict__ dec,
+               int nd_level, const int32_t* __restrict__ par, int nv, int nproj, const double* __restrict__ proj, int n_req,
+               const int32_t* __restrict__ inst, double* __restrict__ X, double* __restrict__ Xf, int max_pivots,
+               int32_t* __restrict__ status_out, int32_t* __restrict__ pivots_out, uint8_t* __restrict__ moved_out,
+               double* __restrict__ pv_out) {
+    const int b = blockIdx.x, i = threadIdx.x;
+    const int slot = inst[b];
+    const int dz = g.d1 + g.d2, n = g.d1 + 2 * g.d2;
+    GaviSmem s;
+    tab_carve_ex(s.t, n, (size_t)plans.t_doubles, plans.ldr_max, 0);
+    const int p = gavi_carve_extra(s, g, (int)tab_smem_bytes_ex(n, (size_t)plans.t_doubles, plans.ldr_max));
+    double* xs = reinterpret_cast<double*>(qpn_smem + p);
+    double* xn = xs + nv;
+    double* x = X + (size_t)slot * nv;
+    for (int j = i; j < nv; j += blockDim.x) xs[j] = x[j];
+    QPN_SYNC();
+    for (int j = i; j < g.np; j += blockDim.x) s.w()[j] = xs[par[j]];
+    for (int j = i; j < dz; j += blockDim.x) s.z0()[j] = j < nd_level ? xs[dec[j]] : 0.0;
+    QPN_SYNC();
+    int piv = 0;
+    const int st = gavi_solve_smem(s, g, plans.has ? &plans.A : nullptr, plans.has ? &plans.B : nullptr, 1, max_pivots, &piv);
+    QPN_SYNC();
+    int moved = 0;
+    if (st == ST_SUCCESS) {
+        for (int j = i; j < nv; j += blockDim.x) xn[j] = xs[j];
+        QPN_SYNC();
+        for (int j = i; j < nd_level; j += blockDim.x) xn[dec[j]] = s.zs()[j];
+        QPN_SYNC();
+        double dn = 0.0;
+        for (int j = 0; j < nv; ++j) { const double e = xn[j] - xs[j]; dn = fma(e, e, dn); }
+        moved = !(sqrt(dn) < 1e-4);                       // algorithm.jl:96-97
+        if (moved) {
+            for (int j = i; j < nv; j += blockDim.x) x[j] = xn[j];
+            for (int k = i; k < nproj; k += blockDim.x) {
+                double acc = 0.0;
+                for (int j = 0; j < nv; ++j) acc = fma(xn[j], proj[(size_t)k * nv + j], acc);
+                pv_out[(size_t)b * nproj + k] = acc;
+            }
+        }
+    }
+    if (Xf) {
+        const double* src = moved ? xn : xs;
+        for (int j = i; j < nv; j += blockDim.x) Xf[(size_t)slot * nv + j] = src[j];
+    }
+    if (i == 0) { status_out[b] = st; pivots_out[b] = piv; moved_out[b] = (uint8_t)moved; }
+}
+
+// One (instance, piece) pair: rows of the piece are row-major over nv.
+struct MemberPair {
+    const double* A;
+    const double* l;
+    const double* u;
+    int32_t inst, m;
+};
+
+// One warp per pair; lanes take rows, each dot product sequential in the coordinate index.
+__global__ void net_member_kernel(int npairs, const MemberPair* __restrict__ pairs, int nv, const double* __restrict__ X, double tol,
+                                  uint8_t* __restrict__ in_out) {
+    const int warp = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (warp >= npairs) return;
+    const MemberPair pr = pairs[warp];
+    const double* x = X + (size_t)pr.inst * nv;
+    int ok = 1;
+    for (int row = lane; row < pr.m; row += 32) {
+        const double* a = pr.A + (size_t)row * nv;
+        double ax = 0.0;
+        for (int j = 0; j < nv; ++j) ax = fma(a[j], x[j], ax);
+        if (!((pr.l[row] - tol <= ax) && (ax - tol <= pr.u[row]))) ok = 0;
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    if (lane == 0) in_out[warp] = (uint8_t)ok;
+}
+
+}  // namespace qpn

@@ -3,8 +3,9 @@
 
 The QPNet is flattened to the plain arrays of `qpn_net_desc` -- the same arrays a Julia `QPNet` holds after
 `setup(:name)` (/root/reference/src/programs.jl:79-116) -- and handed over once; a batch then costs one call.
-`NetBinding` is written against a symbol prefix so that the test suite can drive the oracle build of the same state
-machine (`qpo_net_*`, oracle/net_oracle.cpp) through the identical marshalling code.
+`NetBinding` is written against a symbol prefix so that the test suite can drive its checker build of the same state
+machine (the host logic of csrc/net/ over CPU numerics, built under the test infrastructure) through the identical
+marshalling code; the product only ever passes "qpn_net_".
 """
 import ctypes as C
 
@@ -82,8 +83,8 @@ def build_net_desc(qpn):
 
 
 class NetBinding:
-    """One native net object.  lib: a loaded shared library; prefix: "qpn_net_" (CUDA engine; `handle` = qpn_handle*)
-    or "qpo_net_" (oracle build; no handle)."""
+    """One native net object.  lib: a loaded shared library; prefix: "qpn_net_" (CUDA engine; `handle` = qpn_handle*);
+    a library without a handle argument (the tests' checker build) passes handle=None and its own prefix."""
 
     def __init__(self, qpn, lib, prefix="qpn_net_", handle=None, threads=None):
         from .model import Poly

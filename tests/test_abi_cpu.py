@@ -55,7 +55,7 @@ def test_product_does_not_import_oracle():
     pkg = os.path.join(ROOT, "quadraticprogramnetworks.jl_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".inc", ".h")):
+            if f.endswith((".py", ".cu", ".cuh", ".inc", ".h", ".hpp", ".cpp")):
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
                 assert not re.search(r'#include\s*[<"][^>"]*oracle', txt), f        # no native linkage either
