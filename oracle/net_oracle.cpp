@@ -44,70 +44,82 @@ struct OracleWorker : Worker {
         return st;
     }
     void set_batch(int B_, const double* x_init) override;
-    void run_verify(int, const NodeInfo& n, VerifyReq** reqs, int cnt, bool snap) override {
+    // result storage of the current round (the batches point into these)
+    std::deque<std::vector<uint8_t>> u8;
+    std::deque<std::vector<int8_t>> i8;
+    std::deque<std::vector<int32_t>> i32;
+    std::deque<std::vector<double>> f64;
+    bool fresh_round = true;
+    void begin_round() { if (fresh_round) { u8.clear(); i8.clear(); i32.clear(); f64.clear(); fresh_round = false; } }
+
+    void run_verify(int, const NodeInfo& n, VerifyBatch** bs, int nb, bool snap) override {
+        begin_round();
         std::vector<double> lam(n.m + 1), z(n.nd + n.m + 1), w(n.par.size() + 1);
-        for (int k = 0; k < cnt; ++k) {
-            VerifyReq& r = *reqs[k];
-            const double* x = X.data() + (size_t)r.inst * nv;
-            int32_t how = 0, fp = 0;
-            r.solution = (uint8_t)qpo_verify_solution(n.nd, n.nv, n.m, n.Qd.data(), n.qd.data(), n.A.data(), n.l.data(), n.u.data(),
+        const GaviData& g = n.g;
+        const int dz = n.nd + n.m;
+        for (int q = 0; q < nb; ++q) {
+            VerifyBatch& b = *bs[q];
+            u8.emplace_back(b.n, 0);
+            i8.emplace_back((size_t)b.n * dz, 0);
+            uint8_t* sol = u8.back().data();
+            int8_t* mask = i8.back().data();
+            for (int k = 0; k < b.n; ++k) {
+                const double* x = X.data() + (size_t)b.slots[k] * nv;
+                int32_t how = 0, fp = 0;
+                sol[k] = (uint8_t)qpo_verify_solution(n.nd, n.nv, n.m, n.Qd.data(), n.qd.data(), n.A.data(), n.l.data(), n.u.data(),
                                                       n.dec.data(), x, 1e-4, lam.data(), &how, nullptr, &fp);
-            if (r.solution) {
-                for (int e = 0; e < n.nd; ++e) z[e] = x[n.dec[e]];
-                for (int i = 0; i < n.m; ++i) z[n.nd + i] = lam[i];
-                for (size_t c = 0; c < n.par.size(); ++c) w[c] = x[n.par[c]];
-                r.mask.assign(n.nd + n.m, 0);
-                const GaviData& g = n.g;
-                qpo_comp_indices(g.d1, g.d2, g.np, g.M.data(), g.N.data(), g.o.data(), g.l1.data(), g.u1.data(), g.A.data(),
-                                 g.B.data(), g.l2.data(), g.u2.data(), z.data(), w.data(), 1e-2, r.mask.data());
-                if (r.want_zw) { r.zw.assign(z.begin(), z.begin() + n.nd + n.m); r.zw.insert(r.zw.end(), w.begin(), w.begin() + n.par.size()); }
+                if (sol[k]) {
+                    for (int e = 0; e < n.nd; ++e) z[e] = x[n.dec[e]];
+                    for (int i = 0; i < n.m; ++i) z[n.nd + i] = lam[i];
+                    for (size_t c = 0; c < n.par.size(); ++c) w[c] = x[n.par[c]];
+                    qpo_comp_indices(g.d1, g.d2, g.np, g.M.data(), g.N.data(), g.o.data(), g.l1.data(), g.u1.data(), g.A.data(),
+                                     g.B.data(), g.l2.data(), g.u2.data(), z.data(), w.data(), 1e-2, mask + (size_t)k * dz);
+                }
+                if (snap) std::memcpy(Xf.data() + (size_t)b.slots[k] * nv, x, sizeof(double) * nv);
             }
-            if (snap) std::memcpy(Xf.data() + (size_t)r.inst * nv, x, sizeof(double) * nv);
+            b.sol = sol; b.mask = mask; b.dz = dz;
         }
     }
-    void run_qep(int, const LevelGaviInfo& L, QepReq** reqs, int cnt, bool snap) override {
+    void run_qep(int, const LevelGaviInfo& L, QepBatch** bs, int nb, bool snap) override {
+        begin_round();
         const GaviData& g = L.g;
         const int dz = g.d1 + g.d2, ndl = (int)L.dec.size();
         std::vector<double> w(g.np + 1), z0(dz + 1), z(dz + 1), xn(nv);
         const int nproj = net->check_for_cycling ? net->num_projections : 0;
-        for (int k = 0; k < cnt; ++k) {
-            QepReq& r = *reqs[k];
-            double* x = X.data() + (size_t)r.inst * nv;
-            for (int j = 0; j < g.np; ++j) w[j] = x[L.par[j]];
-            for (int j = 0; j < dz; ++j) z0[j] = j < ndl ? x[L.dec[j]] : 0.0;
-            qpo_gavi_solve(g.d1, g.d2, g.np, g.M.data(), g.N.data(), g.o.data(), g.l1.data(), g.u1.data(), g.A.data(), g.B.data(),
-                           g.l2.data(), g.u2.data(), w.data(), z0.data(), 1, 0, z.data(), nullptr, &r.status, &r.pivots, nullptr);
-            r.moved = 0;
-            if (r.status == 1) {
-                std::memcpy(xn.data(), x, sizeof(double) * nv);
-                for (int j = 0; j < ndl; ++j) xn[L.dec[j]] = z[j];
-                double dn = 0.0;
-                for (int j = 0; j < nv; ++j) { const double e = xn[j] - x[j]; dn = std::fma(e, e, dn); }
-                r.moved = !(std::sqrt(dn) < 1e-4);
-                if (r.moved) {
-                    std::memcpy(x, xn.data(), sizeof(double) * nv);
-                    r.pv.assign(nproj, 0.0);
-                    for (int q = 0; q < nproj; ++q) {
-                        double acc = 0.0;
-                        for (int j = 0; j < nv; ++j) acc = std::fma(x[j], net->proj[(size_t)q * nv + j], acc);
-                        r.pv[q] = acc;
+        for (int q = 0; q < nb; ++q) {
+            QepBatch& b = *bs[q];
+            i32.emplace_back(b.n, 0); int32_t* status = i32.back().data();
+            i32.emplace_back(b.n, 0); int32_t* pivots = i32.back().data();
+            u8.emplace_back(b.n, 0); uint8_t* moved = u8.back().data();
+            f64.emplace_back((size_t)b.n * (nproj > 0 ? nproj : 1), 0.0); double* pv = f64.back().data();
+            for (int k = 0; k < b.n; ++k) {
+                double* x = X.data() + (size_t)b.slots[k] * nv;
+                for (int j = 0; j < g.np; ++j) w[j] = x[L.par[j]];
+                for (int j = 0; j < dz; ++j) z0[j] = j < ndl ? x[L.dec[j]] : 0.0;
+                qpo_gavi_solve(g.d1, g.d2, g.np, g.M.data(), g.N.data(), g.o.data(), g.l1.data(), g.u1.data(), g.A.data(), g.B.data(),
+                               g.l2.data(), g.u2.data(), w.data(), z0.data(), 1, 0, z.data(), nullptr, &status[k], &pivots[k], nullptr);
+                if (status[k] == 1) {
+                    std::memcpy(xn.data(), x, sizeof(double) * nv);
+                    for (int j = 0; j < ndl; ++j) xn[L.dec[j]] = z[j];
+                    double dn = 0.0;
+                    for (int j = 0; j < nv; ++j) { const double e = xn[j] - x[j]; dn = std::fma(e, e, dn); }
+                    moved[k] = !(std::sqrt(dn) < 1e-4);
+                    if (moved[k]) {
+                        std::memcpy(x, xn.data(), sizeof(double) * nv);
+                        for (int p = 0; p < nproj; ++p) {
+                            double acc = 0.0;
+                            for (int j = 0; j < nv; ++j) acc = std::fma(x[j], net->proj[(size_t)p * nv + j], acc);
+                            pv[(size_t)k * nproj + p] = acc;
+                        }
                     }
                 }
+                if (snap) std::memcpy(Xf.data() + (size_t)b.slots[k] * nv, x, sizeof(double) * nv);
             }
-            if (snap) std::memcpy(Xf.data() + (size_t)r.inst * nv, x, sizeof(double) * nv);
+            b.status = status; b.pivots = pivots; b.moved = moved; b.pv = pv;
         }
     }
-    void run_member(MemberReq** reqs, int cnt) override;
-    void run_comp(int, const NodeInfo& n, CompReq** reqs, int cnt) override {
-        const GaviData& g = n.g;
-        for (int k = 0; k < cnt; ++k) {
-            CompReq& r = *reqs[k];
-            r.mask.assign(g.d1 + g.d2, 0);
-            qpo_comp_indices(g.d1, g.d2, g.np, g.M.data(), g.N.data(), g.o.data(), g.l1.data(), g.u1.data(), g.A.data(), g.B.data(),
-                             g.l2.data(), g.u2.data(), r.zw.data(), r.zw.data() + g.d1 + g.d2, 1e-2, r.mask.data());
-        }
-    }
-    void finish() override {}
+    void run_member(MemberBatch** bs, int nb) override;
+    void finish() override { fresh_round = true; }
     void download(double* x_out, double* xf_out) override {
         std::memcpy(x_out, X.data(), sizeof(double) * (size_t)B * nv);
         std::memcpy(xf_out, Xf.data(), sizeof(double) * (size_t)B * nv);
@@ -141,16 +153,24 @@ void OracleWorker::set_batch(int B_, const double* x_init) {
     X.assign(x_init, x_init + (size_t)B * nv);
     Xf = X;
 }
-void OracleWorker::run_member(MemberReq** reqs, int cnt) {
-    for (int k = 0; k < cnt; ++k) {
-        MemberReq& r = *reqs[k];
-        const double* x = X.data() + (size_t)r.inst * nv;
-        r.in.assign(r.pieces->size(), 0);
-        for (size_t q = 0; q < r.pieces->size(); ++q) {
-            const PieceCM* c;
-            { std::shared_lock<std::shared_mutex> lk(store->mu); c = &store->pieces[(*r.pieces)[q]]; }
-            r.in[q] = c->m == 0 ? 1 : (uint8_t)qpo_halfspace_in(c->m, nv, c->A.data(), c->l.data(), c->u.data(), nullptr, nullptr, x, 1e-6);
+void OracleWorker::run_member(MemberBatch** bs, int nb) {
+    begin_round();
+    for (int q = 0; q < nb; ++q) {
+        MemberBatch& b = *bs[q];
+        const size_t np = b.pieces->size();
+        std::vector<const PieceCM*> pcs(np);
+        { std::shared_lock<std::shared_mutex> lk(store->mu); for (size_t p = 0; p < np; ++p) pcs[p] = &store->pieces[(*b.pieces)[p]]; }
+        u8.emplace_back((size_t)b.n * np, 0);
+        uint8_t* in = u8.back().data();
+        for (int k = 0; k < b.n; ++k) {
+            const double* x = X.data() + (size_t)b.slots[k] * nv;
+            for (size_t p = 0; p < np; ++p) {
+                const PieceCM* c = pcs[p];
+                in[(size_t)k * np + p] =
+                    c->m == 0 ? 1 : (uint8_t)qpo_halfspace_in(c->m, nv, c->A.data(), c->l.data(), c->u.data(), nullptr, nullptr, x, 1e-6);
+            }
         }
+        b.in = in;
     }
 }
 }  // namespace

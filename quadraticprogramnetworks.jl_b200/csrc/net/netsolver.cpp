@@ -4,8 +4,9 @@
 
 #include <cassert>
 #include <condition_variable>
-#include <coroutine>
+#include <chrono>
 #include <cstdio>
+#include <cstring>
 #include <set>
 #include <thread>
 
@@ -470,87 +471,41 @@ int GeoCache::leaves(const std::vector<int>& union_lists, const std::vector<int>
 }
 
 // =================================================================================================================
-// coroutines
+// the cohort state machine (algorithm.jl:1-127 + qp_processing.jl:151-291, explicit and copyable)
 // =================================================================================================================
-template <class T>
-struct Task {
-    struct promise_type {
-        T value{};
-        std::coroutine_handle<> cont;
-        Task get_return_object() { return Task{std::coroutine_handle<promise_type>::from_promise(*this)}; }
-        std::suspend_always initial_suspend() noexcept { return {}; }
-        struct Final {
-            bool await_ready() noexcept { return false; }
-            std::coroutine_handle<> await_suspend(std::coroutine_handle<promise_type> h) noexcept {
-                auto c = h.promise().cont;
-                return c ? c : std::noop_coroutine();
-            }
-            void await_resume() noexcept {}
-        };
-        Final final_suspend() noexcept { return {}; }
-        void return_value(T v) { value = std::move(v); }
-        void unhandled_exception() { std::terminate(); }
-    };
-    std::coroutine_handle<promise_type> h;
-    explicit Task(std::coroutine_handle<promise_type> hh) : h(hh) {}
-    Task(Task&& o) noexcept : h(o.h) { o.h = nullptr; }
-    Task(const Task&) = delete;
-    ~Task() { if (h) h.destroy(); }
-    bool await_ready() const noexcept { return false; }
-    std::coroutine_handle<> await_suspend(std::coroutine_handle<> c) noexcept { h.promise().cont = c; return h; }
-    T await_resume() { return std::move(h.promise().value); }
+namespace {
+
+struct Frame {                                   // one activation of solve_base! at a level
+    int level = 0, it = 0;
+    std::vector<int> S;                          // per player: list id of its solution graph, -1 = none
+    struct PV { int pid; std::vector<std::vector<int>> combos; int first_req; };
+    std::vector<PV> pvs;                         // verify phase: players and their child-piece combinations
+    std::vector<int> req_nodes;
+    std::vector<uint8_t> sol;                    // answers (uniform over the cohort)
+    std::vector<std::vector<int8_t>> masks;
+    struct Comb { int pid; std::vector<int> union_lists, red, flat; };
+    std::vector<Comb> combs;                     // combine(): players whose leaves wait for membership bits
+    std::vector<int> S_out;
 };
 
-struct Sched {
-    std::vector<VerifyReq*> verify;
-    std::vector<QepReq*> qep;
-    std::vector<MemberReq*> member;
-    std::vector<CompReq*> comp;
-    bool idle() const { return verify.empty() && qep.empty() && member.empty() && comp.empty(); }
-    void post(VerifyReq* r) { verify.push_back(r); }
-    void post(QepReq* r) { qep.push_back(r); }
-    void post(MemberReq* r) { member.push_back(r); }
-    void post(CompReq* r) { comp.push_back(r); }
+enum Wait { W_NONE, W_CYCLE, W_VERIFY, W_MEMBER, W_QEP };
+
+struct Cohort {
+    std::vector<int> members;                    // instance slots
+    std::vector<Frame> stack;
+    std::vector<int> level_iters;
+    Wait wait = W_NONE;
+    std::vector<VerifyBatch> vb;
+    std::vector<MemberBatch> mb;
+    QepBatch qb;
+    bool done = false, solved = false;
+    int error = 0;
+    std::vector<int> sol;
 };
 
-template <class R>
-struct AwaitReqs {
-    Sched& s;
-    std::vector<R>& reqs;
-    Join join;
-    AwaitReqs(Sched& ss, std::vector<R>& rr) : s(ss), reqs(rr) {}
-    bool await_ready() const noexcept { return reqs.empty(); }
-    void await_suspend(std::coroutine_handle<> h) {
-        join.pending = (int)reqs.size();
-        join.h = h.address();
-        for (auto& r : reqs) { r.join = &join; s.post(&r); }
-    }
-    void await_resume() const noexcept {}
-};
-
-struct LevelRet {
-    bool solved = false;
-    std::vector<int> S;                          // per player: list id, -1 = none
-};
-
-struct Inst {
-    int slot = 0;
-    std::vector<std::vector<std::vector<double>>> hist;     // per level: projections of earlier iterates
-    std::vector<double> pv;                                  // projections of the current x
-    SolveOut* out = nullptr;
-};
-
-struct Ctx {
-    GeoCache& c;
-    Worker* w;
-    Sched sched;
-    const NetData& net;
-    Ctx(GeoCache& cc, Worker* ww) : c(cc), w(ww), net(cc.net()) {}
-};
-
-static bool cycle_hit(const std::vector<double>& pv, const std::vector<double>& prev) {
+static bool cycle_hit(const double* pv, const double* prev, int n) {
     double dd = 0.0, na = 0.0, nb = 0.0;
-    for (size_t k = 0; k < pv.size(); ++k) {
+    for (int k = 0; k < n; ++k) {
         const double e = pv[k] - prev[k];
         dd = std::fma(e, e, dd); na = std::fma(pv[k], pv[k], na); nb = std::fma(prev[k], prev[k], nb);
     }
@@ -570,101 +525,124 @@ static void julia_product(const std::vector<int>& sizes, std::vector<std::vector
     }
 }
 
-static Task<LevelRet> solve_base(Ctx& cx, Inst& I, int level) {
-    const NetData& net = cx.net;
-    GeoCache& c = cx.c;
-    Worker* w = cx.w;
-    LevelRet fail;
-    auto failed = [&](int err) {
-        for (auto& h : I.hist) h.clear();
-        if (!I.out->error) I.out->error = err;
-        return fail;
-    };
-    const std::vector<int>& players = net.levels[level];
-    std::vector<int> kids;
-    for (int p : players) kids.insert(kids.end(), net.children[p].begin(), net.children[p].end());
-    std::sort(kids.begin(), kids.end());
-    kids.erase(std::unique(kids.begin(), kids.end()), kids.end());
+struct Machine {
+    GeoCache& c;
+    const NetData& net;
+    Worker* w;
+    int B, nproj;
+    std::vector<double> pv;                      // B x nproj: projections of each instance's current x
+    std::vector<std::vector<std::vector<double>>> hist;      // [slot][level]: flat list of earlier projections
+    std::vector<SolveOut>* outs;
+    int out_base;
+    std::vector<std::unique_ptr<Cohort>> ready;  // to be looked at by the driver
 
-    for (int it = 0; it < net.max_iters; ++it) {
-        I.out->level_iters[level]++;
+    Machine(GeoCache& cc, Worker* ww, int B_, std::vector<SolveOut>* o, int base)
+        : c(cc), net(cc.net()), w(ww), B(B_), nproj(cc.net().check_for_cycling ? cc.net().num_projections : 0), outs(o), out_base(base) {
+        pv.assign((size_t)B * (nproj > 0 ? nproj : 1), 0.0);
+        hist.assign(B, std::vector<std::vector<double>>(net.nlevels));
+    }
+
+    void finish(Cohort& C, bool solved, int err) {
+        for (int s : C.members) for (auto& h : hist[s]) h.clear();       // algorithm.jl:108-114,121-123
+        C.done = true; C.solved = solved; C.error = err; C.wait = W_NONE;
+        if (solved) C.sol = C.stack.front().S;
+    }
+    void fail(Cohort& C, int err) { finish(C, false, err); }
+
+    // ---- algorithm.jl:13-31 --------------------------------------------------------------------------------------------
+    void start_iter(Cohort& C) {
+        Frame& f = C.stack.back();
+        if (f.it == net.max_iters) return fail(C, ERR_MAXIT);
+        f.it++;
+        C.level_iters[f.level]++;
         if (net.check_for_cycling) {
-            if (net.num_projections == 0) co_return failed(ERR_NOPROJ);
-            for (const auto& prev : I.hist[level]) if (cycle_hit(I.pv, prev)) co_return failed(ERR_CYCLE);
-            I.hist[level].push_back(I.pv);
+            if (net.num_projections == 0) return fail(C, ERR_NOPROJ);
+            C.wait = W_CYCLE;                    // the driver splits the cohort by the per-instance check
+            return;
         }
-        std::vector<int> S(net.nplayers, -1);
-        if (level + 1 < net.nlevels) {
-            LevelRet low = co_await solve_base(cx, I, level + 1);
-            if (!low.solved) co_return fail;
-            S = std::move(low.S);
+        after_cycle(C, false);
+    }
+    void after_cycle(Cohort& C, bool hit) {
+        if (hit) return fail(C, ERR_CYCLE);
+        Frame& f = C.stack.back();
+        f.S.assign(net.nplayers, -1);
+        if (f.level + 1 < net.nlevels) {         // algorithm.jl:32-39: the full recursive solve of the level below
+            Frame child;
+            child.level = f.level + 1;
+            C.stack.push_back(std::move(child));
+            return start_iter(C);
         }
-        // ---- verify phase: every player against every combination of its children's pieces -----------------------
-        struct PV { int pid; std::vector<std::vector<int>> combos; int first_req; };
-        std::vector<PV> pvs;
-        std::vector<VerifyReq> reqs;
-        for (int pid : players) {
-            PV pv;
-            pv.pid = pid; pv.first_req = (int)reqs.size();
+        post_verify(C);
+    }
+
+    // ---- process_qp, first phase: every player against every combination of its children's pieces -------------------
+    void post_verify(Cohort& C) {
+        Frame& f = C.stack.back();
+        f.pvs.clear(); f.req_nodes.clear();
+        for (int pid : net.levels[f.level]) {
+            Frame::PV pv;
+            pv.pid = pid; pv.first_req = (int)f.req_nodes.size();
             const std::vector<int>& ch = net.children[pid];
             if (!ch.empty()) {
                 std::vector<int> sizes;
                 for (int j : ch) {
-                    if (S[j] < 0 || c.list(S[j]).empty()) co_return failed(ERR_UNPOPULATED);
-                    sizes.push_back((int)c.list(S[j]).size());
+                    if (f.S[j] < 0 || c.list(f.S[j]).empty()) return fail(C, ERR_UNPOPULATED);
+                    sizes.push_back((int)c.list(f.S[j]).size());
                 }
                 julia_product(sizes, pv.combos);
                 for (const auto& combo : pv.combos) {
                     std::vector<int> pieces;
-                    for (size_t k = 0; k < ch.size(); ++k) pieces.push_back(c.list(S[ch[k]])[combo[k]]);
-                    VerifyReq r;
-                    r.inst = I.slot; r.node = c.node(pid, pieces, w);
-                    reqs.push_back(std::move(r));
+                    for (size_t k = 0; k < ch.size(); ++k) pieces.push_back(c.list(f.S[ch[k]])[combo[k]]);
+                    f.req_nodes.push_back(c.node(pid, pieces, w));
                 }
             } else {
-                VerifyReq r;
-                r.inst = I.slot; r.node = c.node(pid, {}, w);
-                reqs.push_back(std::move(r));
+                f.req_nodes.push_back(c.node(pid, {}, w));
             }
-            pvs.push_back(std::move(pv));
+            f.pvs.push_back(std::move(pv));
         }
-        co_await AwaitReqs<VerifyReq>(cx.sched, reqs);
-        bool equilibrium = true;
-        for (const auto& r : reqs) if (!r.solution) equilibrium = false;
+        C.vb.assign(f.req_nodes.size(), VerifyBatch());
+        for (size_t r = 0; r < f.req_nodes.size(); ++r) {
+            C.vb[r].node = f.req_nodes[r]; C.vb[r].n = (int)C.members.size(); C.vb[r].slots = C.members.data();
+        }
+        C.wait = W_VERIFY;
+    }
 
+    void after_verify(Cohort& C) {
+        Frame& f = C.stack.back();
+        bool equilibrium = true;
+        for (uint8_t s : f.sol) if (!s) equilibrium = false;
+        const int level = f.level;
         if (equilibrium) {
-            // ---- graph phase (process_qp's solution graphs + combine) ------------------------------------------------
-            struct Comb { int pid; std::vector<int> union_lists, red; std::vector<int> flat; };
-            std::vector<Comb> combs;
-            std::vector<int> S_out(net.nplayers, -1);
-            for (const PV& pv : pvs) {
+            // ---- process_qp, second phase: solution graphs + combine (qp_processing.jl:189-218,243-291) -----------------
+            f.combs.clear();
+            f.S_out.assign(net.nplayers, -1);
+            for (const Frame::PV& pv : f.pvs) {
                 const int pid = pv.pid;
                 const bool gen = level != 0 || net.gen_solution_map;
                 if (!gen) continue;
                 const std::vector<int>& ch = net.children[pid];
                 if (ch.empty()) {
                     bool bad = false;
-                    const int lid = c.collect(reqs[pv.first_req].node, reqs[pv.first_req].mask, w, &bad);
-                    if (bad) co_return failed(ERR_MASK);
-                    if (c.list(lid).empty()) co_return failed(ERR_GRAPH_EMPTY);
-                    S_out[pid] = lid;
+                    const int lid = c.collect(f.req_nodes[pv.first_req], f.masks[pv.first_req], w, &bad);
+                    if (bad) return fail(C, ERR_MASK);
+                    if (c.list(lid).empty()) return fail(C, ERR_GRAPH_EMPTY);
+                    f.S_out[pid] = lid;
                     continue;
                 }
                 std::vector<int> sols;
                 for (size_t k = 0; k < pv.combos.size(); ++k) {
-                    const VerifyReq& r = reqs[pv.first_req + k];
                     bool bad = false;
-                    const int lid = c.collect(r.node, r.mask, w, &bad);
-                    if (bad) co_return failed(ERR_MASK);
+                    const int lid = c.collect(f.req_nodes[pv.first_req + k], f.masks[pv.first_req + k], w, &bad);
+                    if (bad) return fail(C, ERR_MASK);
                     sols.push_back(c.remove_subsets(lid, w));
                 }
-                if (sols.size() == 1) { S_out[pid] = sols[0]; continue; }
-                Comb cb;
+                if (sols.size() == 1) { f.S_out[pid] = sols[0]; continue; }
+                Frame::Comb cb;
                 cb.pid = pid;
                 int total = 0;
                 for (size_t k = 0; k < pv.combos.size(); ++k) {
                     std::vector<int> pieces;
-                    for (size_t q = 0; q < ch.size(); ++q) pieces.push_back(c.list(S[ch[q]])[pv.combos[k][q]]);
+                    for (size_t q = 0; q < ch.size(); ++q) pieces.push_back(c.list(f.S[ch[q]])[pv.combos[k][q]]);
                     const int region = c.intersect_all(pieces, w);
                     const std::vector<int>& comp = c.complement_of(region, w);
                     std::vector<int> combined = c.list(sols[k]);
@@ -674,57 +652,171 @@ static Task<LevelRet> solve_base(Ctx& cx, Inst& I, int level) {
                     for (int p : combined) if (c.poly(p).m() > 0) cb.flat.push_back(p);
                     cb.union_lists.push_back(c.intern_list(combined));
                 }
-                if (cb.union_lists.size() > 3 && total > 20) { if (!I.out->error) I.out->error = ERR_COMBINE; co_return fail; }
-                combs.push_back(std::move(cb));
+                if (cb.union_lists.size() > 3 && total > 20) return fail(C, ERR_COMBINE);
+                f.combs.push_back(std::move(cb));
             }
-            if (!combs.empty()) {
-                std::vector<MemberReq> mreqs(combs.size());
-                for (size_t k = 0; k < combs.size(); ++k) { mreqs[k].inst = I.slot; mreqs[k].pieces = &combs[k].flat; }
-                co_await AwaitReqs<MemberReq>(cx.sched, mreqs);
-                for (size_t k = 0; k < combs.size(); ++k)
-                    S_out[combs[k].pid] = c.leaves(combs[k].union_lists, combs[k].red, mreqs[k].in, w);
+            if (!f.combs.empty()) {
+                C.mb.assign(f.combs.size(), MemberBatch());
+                for (size_t k = 0; k < f.combs.size(); ++k) {
+                    C.mb[k].n = (int)C.members.size(); C.mb[k].slots = C.members.data(); C.mb[k].pieces = &f.combs[k].flat;
+                }
+                C.wait = W_MEMBER;
+                return;
             }
-            for (int pid : players) {
-                if (S_out[pid] >= 0 && net.remove_subsets_at[level]) S[pid] = c.remove_subsets(S_out[pid], w);
-                else S[pid] = S_out[pid];
-            }
-            if (level == 0) for (auto& h : I.hist) h.clear();
-            LevelRet ok;
-            ok.solved = true; ok.S = std::move(S);
-            co_return ok;
+            return finish_level(C);
         }
         // ---- not an equilibrium: solve_qep with the offending child pieces (algorithm.jl:68-101) -----------------------
+        std::vector<int> kids;
+        for (int p : net.levels[level]) kids.insert(kids.end(), net.children[p].begin(), net.children[p].end());
+        std::sort(kids.begin(), kids.end());
+        kids.erase(std::unique(kids.begin(), kids.end()), kids.end());
         std::vector<int> assignment(kids.size());
-        for (size_t k = 0; k < kids.size(); ++k) assignment[k] = c.list(S[kids[k]])[0];
-        for (const PV& pv : pvs) {
+        for (size_t k = 0; k < kids.size(); ++k) assignment[k] = c.list(f.S[kids[k]])[0];
+        for (const Frame::PV& pv : f.pvs) {
             const std::vector<int>& ch = net.children[pv.pid];
             if (ch.empty()) continue;
             for (size_t k = 0; k < pv.combos.size(); ++k) {
-                if (reqs[pv.first_req + k].solution) continue;
+                if (f.sol[pv.first_req + k]) continue;
                 for (size_t q = 0; q < ch.size(); ++q) {
                     const size_t pos = std::lower_bound(kids.begin(), kids.end(), ch[q]) - kids.begin();
-                    assignment[pos] = c.list(S[ch[q]])[pv.combos[k][q]];
+                    assignment[pos] = c.list(f.S[ch[q]])[pv.combos[k][q]];
                 }
-                break;                               // the first combination that fails
+                break;                           // the first combination that fails
             }
         }
-        std::vector<QepReq> q(1);
-        q[0].inst = I.slot; q[0].gavi = c.level_gavi(level, assignment, w);
-        co_await AwaitReqs<QepReq>(cx.sched, q);
-        I.out->pivots += q[0].pivots;
-        if (q[0].status != 1) co_return failed(ERR_AVI);
-        if (!q[0].moved) co_return failed(ERR_DISAGREE);
-        I.pv = std::move(q[0].pv);
+        C.qb = QepBatch();
+        C.qb.gavi = c.level_gavi(level, assignment, w);
+        C.qb.n = (int)C.members.size(); C.qb.slots = C.members.data();
+        C.wait = W_QEP;
     }
-    co_return failed(ERR_MAXIT);
-}
 
-static Task<int> solve_root(Ctx& cx, Inst& I) {
-    LevelRet r = co_await solve_base(cx, I, 0);
-    I.out->solved = r.solved;
-    if (r.solved) I.out->sol = std::move(r.S);
-    co_return 0;
-}
+    void after_member(Cohort& C, const std::vector<std::vector<uint8_t>>& bits) {
+        Frame& f = C.stack.back();
+        for (size_t k = 0; k < f.combs.size(); ++k)
+            f.S_out[f.combs[k].pid] = c.leaves(f.combs[k].union_lists, f.combs[k].red, bits[k], w);
+        finish_level(C);
+    }
+
+    void finish_level(Cohort& C) {               // algorithm.jl:84,104-116
+        Frame& f = C.stack.back();
+        for (int pid : net.levels[f.level]) {
+            if (f.S_out[pid] >= 0 && net.remove_subsets_at[f.level]) f.S[pid] = c.remove_subsets(f.S_out[pid], w);
+            else f.S[pid] = f.S_out[pid];
+        }
+        if (C.stack.size() == 1) return finish(C, true, 0);
+        std::vector<int> S = std::move(f.S);
+        C.stack.pop_back();
+        C.stack.back().S = std::move(S);         // S = ret_low.Sol; x = ret_low.x_opt (x is resident: nothing to copy)
+        post_verify(C);
+    }
+
+    void after_qep(Cohort& C, int status, bool moved) {
+        if (status != 1) return fail(C, ERR_AVI);
+        if (!moved) return fail(C, ERR_DISAGREE);
+        start_iter(C);
+    }
+
+    // ---- splitting ---------------------------------------------------------------------------------------------------
+    // Partition C's members by a byte signature; `apply(part, representative index in the old member list)` is called
+    // for every part (C itself is reused for the first one).
+    template <class Sig, class Apply>
+    void split(std::unique_ptr<Cohort> C, Sig&& sig, Apply&& apply) {
+        const int n = (int)C->members.size();
+        std::unordered_map<std::string, int> part_of;
+        std::vector<std::vector<int>> parts;     // indices into the old member list
+        std::string key;
+        for (int k = 0; k < n; ++k) {
+            key.clear();
+            sig(k, key);
+            auto it = part_of.find(key);
+            if (it == part_of.end()) { it = part_of.emplace(key, (int)parts.size()).first; parts.emplace_back(); }
+            parts[it->second].push_back(k);
+        }
+        if (parts.size() > 1) c.stats.cohorts += (long)parts.size() - 1;
+        const std::vector<int> old = C->members;
+        std::vector<std::unique_ptr<Cohort>> out;
+        for (size_t p = 1; p < parts.size(); ++p) {
+            auto D = std::make_unique<Cohort>(*C);
+            D->members.clear();
+            for (int k : parts[p]) D->members.push_back(old[k]);
+            out.push_back(std::move(D));
+        }
+        if (parts.size() > 1) {
+            C->members.clear();
+            for (int k : parts[0]) C->members.push_back(old[k]);
+        }
+        apply(*C, parts[0][0]);
+        for (size_t p = 1; p < parts.size(); ++p) apply(*out[p - 1], parts[p][0]);
+        ready.push_back(std::move(C));
+        for (auto& D : out) ready.push_back(std::move(D));
+    }
+
+    void resolve_cycle(std::unique_ptr<Cohort> C) {
+        const int level = C->stack.back().level;
+        std::vector<uint8_t> hit(C->members.size(), 0);
+        for (size_t k = 0; k < C->members.size(); ++k) {
+            const int s = C->members[k];
+            const double* p = pv.data() + (size_t)s * nproj;
+            std::vector<double>& h = hist[s][level];
+            for (size_t q = 0; q + nproj <= h.size(); q += nproj) if (cycle_hit(p, h.data() + q, nproj)) { hit[k] = 1; break; }
+            if (!hit[k]) h.insert(h.end(), p, p + nproj);
+        }
+        split(std::move(C), [&](int k, std::string& key) { key.push_back((char)hit[k]); },
+              [&](Cohort& P, int rep) { P.wait = W_NONE; after_cycle(P, hit[rep] != 0); });
+    }
+
+    void resolve_verify(std::unique_ptr<Cohort> C) {
+        std::vector<VerifyBatch> vb = C->vb;     // the answers (pointers into the backend's result buffers)
+        split(std::move(C),
+              [&](int k, std::string& key) {
+                  for (const VerifyBatch& b : vb) {
+                      key.push_back((char)b.sol[k]);
+                      if (b.sol[k]) key.append((const char*)b.mask + (size_t)k * b.dz, (size_t)b.dz);
+                  }
+              },
+              [&](Cohort& P, int rep) {
+                  Frame& f = P.stack.back();
+                  f.sol.assign(vb.size(), 0);
+                  f.masks.assign(vb.size(), {});
+                  for (size_t r = 0; r < vb.size(); ++r) {
+                      f.sol[r] = vb[r].sol[rep];
+                      if (f.sol[r]) f.masks[r].assign(vb[r].mask + (size_t)rep * vb[r].dz, vb[r].mask + (size_t)(rep + 1) * vb[r].dz);
+                  }
+                  P.vb.clear();
+                  P.wait = W_NONE;
+                  after_verify(P);
+              });
+    }
+
+    void resolve_member(std::unique_ptr<Cohort> C) {
+        std::vector<MemberBatch> mb = C->mb;
+        std::vector<size_t> np;
+        for (const auto& b : mb) np.push_back(b.pieces->size());
+        split(std::move(C),
+              [&](int k, std::string& key) {
+                  for (size_t r = 0; r < mb.size(); ++r) key.append((const char*)mb[r].in + (size_t)k * np[r], np[r]);
+              },
+              [&](Cohort& P, int rep) {
+                  std::vector<std::vector<uint8_t>> bits(mb.size());
+                  for (size_t r = 0; r < mb.size(); ++r) bits[r].assign(mb[r].in + (size_t)rep * np[r], mb[r].in + (size_t)(rep + 1) * np[r]);
+                  P.mb.clear();
+                  P.wait = W_NONE;
+                  after_member(P, bits);
+              });
+    }
+
+    void resolve_qep(std::unique_ptr<Cohort> C) {
+        const QepBatch qb = C->qb;
+        for (int k = 0; k < qb.n; ++k)           // x moved: its projections are the ones the next cycle check reads
+            if (qb.status[k] == 1 && qb.moved[k] && nproj > 0)
+                std::memcpy(pv.data() + (size_t)qb.slots[k] * nproj, qb.pv + (size_t)k * nproj, sizeof(double) * nproj);
+        split(std::move(C),
+              [&](int k, std::string& key) { key.push_back((char)qb.status[k]); key.push_back((char)qb.moved[k]); },
+              [&](Cohort& P, int rep) { P.wait = W_NONE; after_qep(P, qb.status[rep], qb.moved[rep] != 0); });
+    }
+};
+
+}  // namespace
 
 // =================================================================================================================
 // NetSolver
@@ -743,82 +835,104 @@ void NetSolver::run_shard(int tid, int lo, int hi, const double* inits, double* 
     const int B = hi - lo, nv = net_.nv;
     if (B <= 0) return;
     Worker* w = workers_[tid].get();
+    Stats& st = cache_->stats;
+    auto now = []() { return std::chrono::steady_clock::now(); };
+    auto ns = [](auto a, auto b) { return (long)std::chrono::duration_cast<std::chrono::nanoseconds>(b - a).count(); };
+    auto t_host = now();
     w->set_batch(B, inits + (size_t)lo * nv);
-    Ctx cx(*cache_, w);
-    std::vector<Inst> insts(B);
-    std::vector<Task<int>> roots;
-    roots.reserve(B);
-    const int np = net_.check_for_cycling ? net_.num_projections : 0;
+    st.backend_ns += ns(t_host, now());
+    t_host = now();
+    Machine M(*cache_, w, B, &outs, lo);
     for (int b = 0; b < B; ++b) {
-        Inst& I = insts[b];
-        I.slot = b;
-        I.out = &outs[lo + b];
-        *I.out = SolveOut();
-        I.out->level_iters.assign(net_.nlevels, 0);
-        I.out->sol.assign(net_.nplayers, -1);
-        I.hist.resize(net_.nlevels);
-        I.pv.assign(np, 0.0);
         const double* x = inits + (size_t)(lo + b) * nv;
-        for (int k = 0; k < np; ++k) {
+        for (int k = 0; k < M.nproj; ++k) {
             double acc = 0.0;
             for (int j = 0; j < nv; ++j) acc = std::fma(x[j], net_.proj[(size_t)k * nv + j], acc);
-            I.pv[k] = acc;
+            M.pv[(size_t)b * M.nproj + k] = acc;
         }
-        roots.push_back(solve_root(cx, I));
     }
-    for (auto& t : roots) t.h.resume();
-    Stats& st = cache_->stats;
-    std::vector<VerifyReq*> verify;
-    std::vector<QepReq*> qep;
-    std::vector<MemberReq*> member;
-    std::vector<CompReq*> comp;
-    while (!cx.sched.idle()) {
-        verify.swap(cx.sched.verify); qep.swap(cx.sched.qep); member.swap(cx.sched.member); comp.swap(cx.sched.comp);
-        cx.sched.verify.clear(); cx.sched.qep.clear(); cx.sched.member.clear(); cx.sched.comp.clear();
+    {
+        auto C = std::make_unique<Cohort>();
+        C->members.resize(B);
+        for (int b = 0; b < B; ++b) C->members[b] = b;
+        C->level_iters.assign(net_.nlevels, 0);
+        C->stack.emplace_back();
+        M.start_iter(*C);
+        M.ready.push_back(std::move(C));
+    }
+    std::vector<std::unique_ptr<Cohort>> waiting;
+    std::vector<VerifyBatch*> vlist;
+    std::vector<QepBatch*> qlist;
+    std::vector<MemberBatch*> mlist;
+    while (true) {
+        // ---- everything the host can decide on its own: finished cohorts, cycle checks ---------------------------------
+        while (!M.ready.empty()) {
+            std::unique_ptr<Cohort> C = std::move(M.ready.back());
+            M.ready.pop_back();
+            if (C->done) {
+                for (int s : C->members) {
+                    SolveOut& o = outs[lo + s];
+                    o.solved = C->solved; o.error = C->error; o.level_iters = C->level_iters;
+                    if (C->solved) o.sol = C->sol; else o.sol.assign(net_.nplayers, -1);
+                }
+            } else if (C->wait == W_CYCLE) {
+                M.resolve_cycle(std::move(C));
+            } else {
+                waiting.push_back(std::move(C));
+            }
+        }
+        if (waiting.empty()) break;
+        // ---- one batched backend call per (kind, resident object) over the requests of all waiting cohorts --------------
+        vlist.clear(); qlist.clear(); mlist.clear();
+        long nreq = 0;
+        for (auto& C : waiting) {
+            if (C->wait == W_VERIFY) for (auto& b : C->vb) { vlist.push_back(&b); nreq += b.n; }
+            else if (C->wait == W_QEP) { qlist.push_back(&C->qb); nreq += C->qb.n; }
+            else if (C->wait == W_MEMBER) for (auto& b : C->mb) { mlist.push_back(&b); nreq += b.n; }
+        }
+        std::stable_sort(vlist.begin(), vlist.end(), [](const VerifyBatch* a, const VerifyBatch* b) { return a->node < b->node; });
+        std::stable_sort(qlist.begin(), qlist.end(), [](const QepBatch* a, const QepBatch* b) { return a->gavi < b->gavi; });
+        auto t_back = now();
+        st.host_ns += ns(t_host, t_back);
         st.rounds++;
-        st.requests += (long)(verify.size() + qep.size() + member.size() + comp.size());
-        // one batched call per (kind, resident object); stable order so that runs are reproducible
-        std::stable_sort(verify.begin(), verify.end(), [](const VerifyReq* a, const VerifyReq* b) { return a->node < b->node; });
-        std::stable_sort(qep.begin(), qep.end(), [](const QepReq* a, const QepReq* b) { return a->gavi < b->gavi; });
-        std::stable_sort(comp.begin(), comp.end(), [](const CompReq* a, const CompReq* b) { return a->node < b->node; });
-        for (size_t i = 0; i < verify.size();) {
+        st.requests += nreq;
+        for (size_t i = 0; i < vlist.size();) {
             size_t j = i;
-            while (j < verify.size() && verify[j]->node == verify[i]->node) ++j;
-            const NodeInfo& info = cache_->node_info(verify[i]->node);
-            w->run_verify(verify[i]->node, info, &verify[i], (int)(j - i), net_.level_of[info.pid] == 0);
+            while (j < vlist.size() && vlist[j]->node == vlist[i]->node) ++j;
+            const NodeInfo& info = cache_->node_info(vlist[i]->node);
+            w->run_verify(vlist[i]->node, info, &vlist[i], (int)(j - i), net_.level_of[info.pid] == 0);
             st.calls++;
             i = j;
         }
-        for (size_t i = 0; i < qep.size();) {
+        for (size_t i = 0; i < qlist.size();) {
             size_t j = i;
-            while (j < qep.size() && qep[j]->gavi == qep[i]->gavi) ++j;
-            const LevelGaviInfo& info = cache_->gavi_info(qep[i]->gavi);
-            w->run_qep(qep[i]->gavi, info, &qep[i], (int)(j - i), info.level == 0);
+            while (j < qlist.size() && qlist[j]->gavi == qlist[i]->gavi) ++j;
+            const LevelGaviInfo& info = cache_->gavi_info(qlist[i]->gavi);
+            w->run_qep(qlist[i]->gavi, info, &qlist[i], (int)(j - i), info.level == 0);
             st.calls++;
             i = j;
         }
-        if (!member.empty()) { w->run_member(member.data(), (int)member.size()); st.calls++; }
-        for (size_t i = 0; i < comp.size();) {
-            size_t j = i;
-            while (j < comp.size() && comp[j]->node == comp[i]->node) ++j;
-            w->run_comp(comp[i]->node, cache_->node_info(comp[i]->node), &comp[i], (int)(j - i));
-            st.calls++;
-            i = j;
-        }
+        if (!mlist.empty()) { w->run_member(mlist.data(), (int)mlist.size()); st.calls++; }
         w->finish();
-        auto wake = [](Join* jn) {
-            if (--jn->pending == 0) std::coroutine_handle<>::from_address(jn->h).resume();
-        };
-        for (auto* r : verify) wake(r->join);
-        for (auto* r : qep) wake(r->join);
-        for (auto* r : member) wake(r->join);
-        for (auto* r : comp) wake(r->join);
-        verify.clear(); qep.clear(); member.clear(); comp.clear();
+        t_host = now();
+        st.backend_ns += ns(t_back, t_host);
+        // ---- split every cohort by what its members were told ------------------------------------------------------------
+        std::vector<std::unique_ptr<Cohort>> got;
+        got.swap(waiting);
+        for (auto& C : got) {
+            const Wait wt = C->wait;
+            if (wt == W_VERIFY) M.resolve_verify(std::move(C));
+            else if (wt == W_QEP) M.resolve_qep(std::move(C));
+            else M.resolve_member(std::move(C));
+        }
     }
+    st.host_ns += ns(t_host, now());
+    t_host = now();
     std::vector<double> xf((size_t)B * nv);
     w->download(x_out + (size_t)lo * nv, xf.data());
     for (int b = 0; b < B; ++b)
         if (!outs[lo + b].solved) std::memcpy(x_out + (size_t)(lo + b) * nv, xf.data() + (size_t)b * nv, sizeof(double) * nv);
+    st.backend_ns += ns(t_host, now());
 }
 
 void NetSolver::solve_batched(int B, const double* inits, double* x_out, std::vector<SolveOut>& outs, int threads) {

@@ -7,14 +7,18 @@
 // solve_qep, membership, every LP of the set algebra -- is a request to a numeric backend (the CUDA engine in
 // libqpn_cuda; the C oracle in the test / baseline build under oracle/).
 //
-// Shape.  Each instance of the batch is a C++20 coroutine that reads like the per-instance recursion.  When it
-// needs numbers it posts requests and suspends; a worker thread resumes its instances until all of them wait, groups
-// the pending requests by (kind, resident object) -- instances that verify the same node against the same child
-// pieces, solve the same level GAVI -- and hands each group to the backend as ONE batched call over a list of
-// instance slots (x stays resident in the backend).  Everything geometric is a pure function of exact problem data
-// (node, child pieces, complementarity recipe K), never of the instance, so it is memoised in a cache shared by all
-// instances, worker threads and batches of the net; between device calls an instance costs a few hash
-// look-ups.
+// Shape.  The control state of solve_base! -- which level, which iteration, which solution graphs
+// came up from the children, which child pieces are assigned -- takes few distinct values across a batch (8,192
+// perturbed robust_avoid instances walk 105 distinct control paths).  The machine therefore advances COHORTS:
+// sets of instances that share their whole control state.  A cohort runs the reference's recursion as an explicit,
+// copyable state machine until it needs numbers; its requests (one per node / level GAVI, over the cohort's list of
+// instance slots) are merged with those of the other cohorts into one batched backend call per (kind, resident
+// object); when the answers are back the cohort is split by what its members were told (solution flags,
+// complementarity masks, membership bits, solve status, cycle check) and every part goes on with a copy of the
+// state.  x stays resident in the backend; per instance the host only hashes its answers and keeps the cycle-check
+// history.  Everything geometric is a pure function of exact problem data (node, child pieces, complementarity
+// recipe K), never of the instance, so it is memoised in a cache shared by all cohorts, worker threads and batches
+// of the net.
 #pragma once
 #include <atomic>
 #include <cstdint>
@@ -65,54 +69,42 @@ struct LevelGaviInfo {
     std::vector<int32_t> dec, par;
 };
 
-// ---- requests an instance posts ----------------------------------------------------------------------------------
-struct Join { int pending = 0; void* h = nullptr; };            // coroutine handle address, resumed when pending hits 0
-
-struct VerifyReq {          // verify_solution at the instance's x, then comp_indices of the node GAVI at (x, lam)
-    int inst = 0, node = 0;
-    Join* join = nullptr;
-    uint8_t solution = 0;
-    std::vector<int8_t> mask;                    // nd + m masks (filled when solution)
-    std::vector<double> zw;                      // [z; w] of the node GAVI (only when want_zw)
-    bool want_zw = false;
+// ---- requests a cohort posts -------------------------------------------------------------------------------------
+// A cohort is a set of instances that share their whole control state (level stack, solution graphs, iteration
+// counters): whatever one of them asks, all of them ask.  A request therefore names a resident object and the
+// cohort's list of instance slots; the backend answers with one entry per slot.  Result pointers stay valid until
+// the worker's next round.
+struct VerifyBatch {        // verify_solution at each instance's x, then comp_indices of the node GAVI at (x, lam)
+    int node = 0, n = 0;
+    const int* slots = nullptr;
+    const uint8_t* sol = nullptr;                // n flags
+    const int8_t* mask = nullptr;                // n x dz masks (rows of non-solutions are undefined)
+    int dz = 0;
 };
-struct QepReq {             // solve_qep for a level GAVI; on success x[dec] is replaced
-    int inst = 0, gavi = 0;
-    Join* join = nullptr;
-    int32_t status = 0, pivots = 0;
-    uint8_t moved = 0;                           // norm(xnew - x) >= 1e-4
-    std::vector<double> pv;                      // projections of the new x (cycle check of the next iteration)
+struct QepBatch {           // solve_qep for a level GAVI; on success (and a move of >= 1e-4) x[dec] is replaced
+    int gavi = 0, n = 0;
+    const int* slots = nullptr;
+    const int32_t* status = nullptr;             // n
+    const int32_t* pivots = nullptr;             // n
+    const uint8_t* moved = nullptr;              // n: norm(xnew - x) >= 1e-4
+    const double* pv = nullptr;                  // n x nproj: projections of the new x (valid where status = 1 and moved)
 };
-struct MemberReq {          // x in closure(piece) for a list of pieces (intersection.jl:74,82)
-    int inst = 0;
-    Join* join = nullptr;
+struct MemberBatch {        // x in closure(piece) for a list of pieces (intersection.jl:74,82)
+    int n = 0;
+    const int* slots = nullptr;
     const std::vector<int>* pieces = nullptr;
-    std::vector<uint8_t> in;
-};
-struct CompReq {            // comp_indices of a node GAVI at an explicit point (vertex exploration)
-    int inst = 0, node = 0;
-    Join* join = nullptr;
-    std::vector<double> zw;
-    std::vector<int8_t> mask;
-};
-struct VertReq {            // vertices of the multiplier polytope of a node at the instance's primal point
-    int inst = 0, node = 0;
-    Join* join = nullptr;
-    std::vector<double> zw;                      // the instance's [z; w]
-    std::vector<int8_t> K;                       // the recipe whose piece is sliced
-    std::vector<std::vector<double>> verts;      // out: multiplier parts of the vertices
+    const uint8_t* in = nullptr;                 // n x pieces->size()
 };
 
 // ---- numeric backend ---------------------------------------------------------------------------------------------
 struct Worker : LPBackend {
     // instance slots 0..B-1 of this worker: x = x_fail = init (nv x B column-major)
     virtual void set_batch(int B, const double* x_init) = 0;
-    // enqueue batched calls (may run asynchronously until finish())
-    virtual void run_verify(int node, const NodeInfo& info, VerifyReq** reqs, int n, bool snap) = 0;
-    virtual void run_qep(int gavi, const LevelGaviInfo& info, QepReq** reqs, int n, bool snap) = 0;
-    virtual void run_member(MemberReq** reqs, int n) = 0;
-    virtual void run_comp(int node, const NodeInfo& info, CompReq** reqs, int n) = 0;
-    virtual void finish() = 0;                   // all results of the enqueued calls are in their requests
+    // enqueue batched calls: all batches of one call name the same resident object (they may run until finish())
+    virtual void run_verify(int node, const NodeInfo& info, VerifyBatch** b, int nb, bool snap) = 0;
+    virtual void run_qep(int gavi, const LevelGaviInfo& info, QepBatch** b, int nb, bool snap) = 0;
+    virtual void run_member(MemberBatch** b, int nb) = 0;
+    virtual void finish() = 0;                   // all results of the enqueued calls are behind the batches' pointers
     virtual void download(double* x_out, double* x_fail_out) = 0;
     virtual int64_t launches() const { return 0; }
 };
@@ -135,7 +127,8 @@ struct VecHash {
 };
 
 struct Stats {
-    std::atomic<long> lps{0}, rounds{0}, requests{0}, calls{0}, pieces{0}, nodes{0}, gavis{0}, collect_miss{0}, combine_miss{0};
+    std::atomic<long> lps{0}, rounds{0}, requests{0}, calls{0}, pieces{0}, nodes{0}, gavis{0}, collect_miss{0}, combine_miss{0}, cohorts{0};
+    std::atomic<long> host_ns{0}, backend_ns{0};   // summed over worker threads: instance logic / numeric backend (incl. waits)
 };
 
 class GeoCache {

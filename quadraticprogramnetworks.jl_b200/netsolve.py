@@ -149,14 +149,14 @@ class NetBinding:
         out = {}
         for k, p in enumerate(self.pids):
             n = self._f("sol_count")(self.ptr, int(b), k)
-            if n >= 0:
-                out[p] = [self.piece(self._f("sol_piece")(self.ptr, int(b), k, j)) for j in range(n)]
+            out[p] = [self.piece(self._f("sol_piece")(self.ptr, int(b), k, j)) for j in range(n)] if n >= 0 else None
         return out
 
     def stats(self):
-        out = np.zeros(12, np.int64)
+        out = np.zeros(16, np.int64)
         self._f("stats")(self.ptr, out.ctypes.data_as(C.POINTER(C.c_int64)))
-        names = ["launches", "rounds", "requests", "calls", "lps", "pieces", "nodes", "gavis", "collect_misses", "combine_misses"]
+        names = ["launches", "rounds", "requests", "calls", "lps", "pieces", "nodes", "gavis", "collect_misses", "combine_misses",
+                 "host_ns", "backend_ns", "cohort_splits"]
         return {n: int(v) for n, v in zip(names, out)}
 
     def solve(self, inits, keep_sol=False):

@@ -18,13 +18,14 @@ def main():
     ref = None
     for t in threads:
         nb = NetBinding(net, eng.lib, "qpn_net_", handle=eng.h, threads=t)
-        t0 = time.time(); r0 = nb.solve_arrays(X[: min(B, 512)]); warm = time.time() - t0
+        t0 = time.time(); nb.solve_arrays(X); cold = time.time() - t0
         s0 = nb.stats()
         t0 = time.time(); ret = nb.solve_arrays(X); dt = time.time() - t0
         s1 = nb.stats()
         d = {k: s1[k] - s0[k] for k in s1}
-        print(f"device threads={t}: warm-up {warm:.2f}s; {B} equilibria in {dt:.3f}s = {B / dt:,.0f}/s, solved {ret['solved'].mean():.4f}, "
-              f"launches {d['launches']}, rounds {d['rounds']}, calls {d['calls']}, requests {d['requests']}, new lps {d['lps']}", flush=True)
+        print(f"device threads={t}: cold {cold:.3f}s; warm {B} equilibria in {dt:.3f}s = {B / dt:,.0f}/s, solved {ret['solved'].mean():.4f}, "
+              f"launches {d['launches']}, rounds {d['rounds']}, calls {d['calls']}, requests {d['requests']}, new lps {d['lps']}, "
+              f"host {d['host_ns'] / 1e6:.1f} ms, backend {d['backend_ns'] / 1e6:.1f} ms (summed over threads), cohort splits {d['cohort_splits']}", flush=True)
         if ref is None:
             ref = ret
         else:
