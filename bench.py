@@ -4,18 +4,18 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's engine
     python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference path
 
-One "step" = one pass of the hot path over one batch: `solve(qpn, inits)` for the
-four-player Nash game (BASELINE.json configs[1]: examples/four_player_matrix_game.jl, 4,096
-random initialisations per GPU).  Metric: equilibria/sec (whole job, all GPUs).
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): examples/robust_avoid_simple.jl in
+full -- three levels (ego -> adversaries -> separating planes), exploration_vertices = 10 -- for a batch of 65,536
+perturbed instances, sharded over the GPUs (strong scaling: 65,536 / N per GPU).  One "step" = one
+`solve(qpn, inits::Matrix)` = one `qpn_net_solve_batched` per rank: the whole recursion of solve_base! for every
+instance, every numeric step on the device.  Metric: equilibria/sec (whole job, all GPUs).
 
-  value  device-timed (CUDA events on the launching stream), inputs already resident in HBM,
-         L2 flushed between steps;
-  e2e    the same work through the C-ABI call with pinned HOST buffers (H2D + kernel + D2H
-         inside the timed region);
-  roofline / cpu_baseline / clocks / gpu_launches as the bench contract asks.
-
-Multi-GPU: independent instances are sharded over the ranks (weak scaling, 4,096 per GPU);
-the only collective is the final NCCL all-gather of solutions / statuses / pivot counts.
+  value  inputs (inits) and outputs (x) resident in HBM (qpn_net_solve_batched_dev), timed with CUDA events,
+         L2 flushed between steps, max over ranks, the one result exchange per solve included;
+  e2e    the same through the host-pointer C-ABI call (pinned host buffers; H2D + every launch + D2H inside the
+         timed region), host clock; e2e_pageable: the same with pageable buffers (a Julia Matrix{Float64});
+  roofline / cpu_baseline / clocks / gpu_launches as the bench contract asks; `extra` carries the other BASELINE
+  configs (four_player_matrix_game batch of 4,096; bottom levels; the n = 256 / m = 512 stress shape).
 """
 import argparse
 import json
@@ -34,24 +34,21 @@ import numpy as np  # noqa: E402
 
 METRIC = "QPNet equilibria/sec (batched AVI solves)"
 UNIT = "equilibria/s"
-WORKLOAD = "four_player_matrix_game Nash (edge_list=[]), random inits ~ U(-5,5)^8, one fused level-equilibrium launch per batch"
+WORKLOAD = ("robust_avoid_simple in full (examples/robust_avoid_simple.jl defaults: 2 obstacles, 5 faces, 3 levels, "
+            "exploration_vertices=10, num_projections=5; stand-in problem data seed 3), batch of perturbed instances "
+            "(xe, xo ~ default + N(0, 0.5^2), ue, uo ~ U(-1,1)), one solve(qpn, inits) = solve_base! on every level per instance")
+L2_NOTE = "GPU arm: flushed between steps (256 MB write); CPU arm: not applicable"
+DATA_SEED = 3
 HBM_FALLBACK_GBS = 6650.0     # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
-# dram__bytes_read.sum + dram__bytes_write.sum of one level_equilibrium_kernel<32> launch at the default
-# batch (4,096), from profiles/r1_final_level_kernel_ncu_full_summary.csv (ncu --set full, same command)
-NCU_DRAM_BYTES_PER_LAUNCH_B4096 = 433_152 + 256
-# same capture: l1tex__data_pipe_lsu_wavefronts_mem_shared.sum (each wavefront moves up to 128 B) and
-# smsp__inst_executed.sum -- the two on-chip resources that actually bound the pivoting kernel
-NCU_SMEM_WAVEFRONTS_PER_LAUNCH_B4096 = 3_884_408
-NCU_WARP_INSTRUCTIONS_PER_LAUNCH_B4096 = 34_962_442
 SM_COUNT = 148
-# dram__bytes_read.sum + dram__bytes_write.sum of one level_equilibrium_big_kernel launch on the n = 256, m = 512
-# monotone stress level at batch 148 (profiles/r1_big_level_kernel_ncu_full_summary.csv)
-NCU_DRAM_BYTES_BIG_LEVEL_B148 = 259_560_047_000 + 250_557_664_000
-
-
-def inits_for(rank, batch, step=0):
-    rng = np.random.default_rng([0xB200, rank, step])
-    return rng.uniform(-5.0, 5.0, (batch, 8))
+# ncu --set full captures of the two pivoting kernels of the headline (profiles/r2_*): DRAM bytes (read + write) and
+# shared-memory wavefronts per launch at the launch sizes named there; None until captured
+NCU = {}
+try:
+    with open(os.path.join(ROOT, "profiles", "r2_ncu_constants.json")) as _f:
+        NCU = json.load(_f)
+except Exception:       # noqa: BLE001
+    NCU = {}
 
 
 def measured_hbm_peak():
@@ -107,16 +104,6 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def oracle_level(threads_hint=None):
-    """The CPU restatement of the path (oracle/), used ONLY as the reported baseline."""
-    from oracle import cport, examples as oex, qpn_ref
-    net = oex.four_player_matrix_game()
-    g, dec, par = qpn_ref.level_gavi(net, net.depth[1], {})
-    import qpn_b200
-    proj = qpn_b200.projection_vectors(qpn_b200.setup("four_player_matrix_game"))
-    return cport.Level(8, [qpn_ref.node_view(net, p) for p in net.depth[1]], g, dec, par, 150, proj)
-
-
 def cpu_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -124,59 +111,197 @@ def cpu_cores():
         return os.cpu_count() or 1
 
 
-def cpu_baseline(sample_batches=256, batch=4096):
+# ---- the CPU restatement of the path (oracle/), used ONLY as the reported baseline / reference arm -------------------
+def oracle_net_binding(net, threads):
+    """The native state machine of csrc/net/ built against the C oracle (oracle/net_oracle.cpp): the same host logic
+    as the product, every numeric step on the host cores, `threads` pthreads, none of the product's kernels."""
+    import ctypes as C
+    from qpn_b200 import netsolve
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s"])
+    lib = C.CDLL(os.path.join(ROOT, "oracle", "_build", "libqpn_net_oracle.so"))
+    return netsolve.NetBinding(net, lib, prefix="qpo_net_", threads=threads)
+
+
+def cpu_baseline(sample=4, batch=65536):
+    import qpn_b200
     cores = cpu_cores()
-    L = oracle_level()
-    X = np.vstack([inits_for(10_000 + k, batch) for k in range(sample_batches)])
-    L.solve(X[:batch], threads=cores)                       # warm
+    net = qpn_b200.setup("robust_avoid_simple", seed=DATA_SEED)
+    nb = oracle_net_binding(net, cores)
+    nb.solve_arrays(qpn_b200.examples.robust_avoid_batch(net, 8192, seed=999))          # pieces memoised, threads up
+    Xs = [qpn_b200.examples.robust_avoid_batch(net, batch, seed=2000 + k) for k in range(sample)]
     t0 = time.perf_counter()
-    r = L.solve(X, threads=cores)
+    solved = 0
+    for X in Xs:
+        solved += int(nb.solve_arrays(X)["solved"].sum())
     dt = time.perf_counter() - t0
-    assert r["solved"].all()
-    return {"value": len(X) / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{len(X)} four_player equilibria ({sample_batches} batches of {batch}), C oracle, {cores} pthreads, {dt:.2f} s wall"}
+    n = sample * batch
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} full three-level robust_avoid equilibria ({sample} batches of {batch}), same host state machine as the GPU arm "
+                      f"(cohorts, shared memo of pieces) with the C oracle as numeric backend, {cores} pthreads, {dt:.2f} s wall, "
+                      f"solved fraction {solved / n:.4f}"}
+
+
+def cpu_no_memo_sample(instances=24):
+    """The reference's own structure -- one solve per instance, nothing shared between instances (every solve rebuilds
+    its pieces: local_piece / project / LPs) -- on the C oracle, one instance per host thread."""
+    import concurrent.futures as cf
+    import qpn_b200
+    cores = cpu_cores()
+    net = qpn_b200.setup("robust_avoid_simple", seed=DATA_SEED)
+    X = qpn_b200.examples.robust_avoid_batch(net, instances, seed=777)
+
+    def one(b):
+        nb = oracle_net_binding(net, 1)
+        r = nb.solve_arrays(X[b:b + 1])
+        nb.close()
+        return bool(r["solved"][0])
+    oracle_net_binding(net, 1).close()                                                   # library built and loaded
+    t0 = time.perf_counter()
+    with cf.ThreadPoolExecutor(max_workers=cores) as ex:
+        ok = list(ex.map(one, range(instances)))
+    dt = time.perf_counter() - t0
+    return {"value": instances / dt, "unit": UNIT, "cores": cores, "instances": instances, "wall_s": dt, "solved_fraction": float(np.mean(ok)),
+            "note": "per-instance solves with a fresh net object each (no memo shared between instances), as the reference's solve() works; "
+                    "C oracle numerics, one instance per host thread"}
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU path.  Julia / PATH / OSQP are absent from this
-    image, so the arm times the oracle port on all host cores."""
+    """--impl reference: the reference's own CPU path.  Julia / PATH / OSQP are absent from this image (SURVEY.md F2,
+    F4), so the arm times the port: the same host logic on the C oracle, all host cores, a persistent thread pool per
+    call of the whole batch (threads live for the 65,536 instances of a step)."""
     if rank != 0:
         return
+    import qpn_b200
     cores = cpu_cores()
-    L = oracle_level()
     B = args.batch
+    net = qpn_b200.setup("robust_avoid_simple", seed=DATA_SEED)
+    nb = oracle_net_binding(net, cores)
+    nb.solve_arrays(qpn_b200.examples.robust_avoid_batch(net, min(B, 8192), seed=999))
     for w in range(max(args.warmup, 1)):
-        L.solve(inits_for(0, B, 1000 + w), threads=cores)
-    times = []
+        nb.solve_arrays(qpn_b200.examples.robust_avoid_batch(net, B, seed=1000 + w))
+    Xs = [qpn_b200.examples.robust_avoid_batch(net, B, seed=k) for k in range(min(args.steps, 4))]
+    times, solved = [], 0
     for k in range(args.steps):
-        X = inits_for(0, B, k)
         t0 = time.perf_counter()
-        r = L.solve(X, threads=cores)
+        r = nb.solve_arrays(Xs[k % len(Xs)])
         times.append(time.perf_counter() - t0)
-        assert r["solved"].all()
+        solved += int(r["solved"].sum())
     total = sum(times)
     val = B * args.steps / total
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_step": B,
-                       "note": "CPU arm: one step = one batch of 4096 instances on the host cores (rank 0 only)"},
+            "config": {"workload": WORKLOAD, "batch": B, "l2": L2_NOTE},
+            "detail": {"solved_fraction": solved / (B * args.steps),
+                       "note": "CPU arm: one step = the whole batch on the host cores (rank 0 only); same native host state machine as the GPU "
+                               "arm (csrc/net/) with oracle/qpn_oracle.c as numeric backend"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} steps x {B} equilibria, C oracle (oracle/qpn_oracle.c), {cores} pthreads"},
+                             "sample": f"{args.steps} steps x {B} full three-level robust_avoid equilibria, {cores} pthreads"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
+# ---- extras: the other BASELINE configs, measured on this rank's GPU ----------------------------------------------------
+def extras(qpn_b200, torch, eng, dev, stream, flush, rank):
+    extra = {}
+    ev = lambda: (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+
+    def timed(run, reps):
+        run(); torch.cuda.synchronize()
+        t = 0.0
+        for _ in range(reps):
+            e0, e1 = ev()
+            flush.zero_(); e0.record(stream); run(); e1.record(stream); torch.cuda.synchronize()
+            t += e0.elapsed_time(e1) * 1e-3
+        return t / reps
+
+    def level_run(net, level, X):
+        solver = qpn_b200.BatchedSolver(net, engine=eng)
+        lv = solver.resident_level(level)
+        B = len(X)
+        xd = torch.from_numpy(X).to(dev)
+        xo = torch.empty_like(xd); so = torch.empty(B, dtype=torch.uint8, device=dev)
+        io = torch.empty(B, dtype=torch.int32, device=dev); po = torch.empty(B, dtype=torch.int32, device=dev)
+        run = lambda: lv.solve_dev(B, xd.data_ptr(), xo.data_ptr(), so.data_ptr(), io.data_ptr(), po.data_ptr(), None, stream.cuda_stream)
+        return solver, lv, run, so, po
+
+    # BASELINE configs[1]: four_player_matrix_game, 4,096 random initialisations, one fused level launch
+    try:
+        fp = qpn_b200.setup("four_player_matrix_game")
+        B = 4096
+        X = np.random.default_rng([0xB200, rank, 0]).uniform(-5.0, 5.0, (B, 8))
+        solver, lv, run, so, po = level_run(fp, 1, X)
+        t = timed(run, 10)
+        hx = torch.from_numpy(X).pin_memory().numpy()
+        out = dict(x=torch.empty((B, 8), dtype=torch.float64).pin_memory().numpy(), solved=torch.empty(B, dtype=torch.uint8).pin_memory().numpy(),
+                   iters=torch.empty(B, dtype=torch.int32).pin_memory().numpy(), pivots=torch.empty(B, dtype=torch.int32).pin_memory().numpy(), lam=None)
+        for _ in range(3):
+            lv.solve(hx, out=out, want_lam=False)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            lv.solve(hx, out=out, want_lam=False)
+        te = (time.perf_counter() - t0) / 10
+        extra["four_player_matrix_game_b4096"] = {"value": B / t, "unit": UNIT, "batch": B, "ms_per_launch": 1e3 * t, "e2e_value": B / te,
+                                                  "all_solved": bool(so.bool().all()), "p50_pivots_per_solve": float(np.median(po.cpu().numpy())),
+                                                  "note": "BASELINE configs[1]; per GPU, device-timed (e2e_value: pinned host buffers through the C ABI)"}
+        solver.close()
+    except Exception as e:                                      # noqa: BLE001 -- the headline must not depend on an extra
+        extra["four_player_matrix_game_b4096"] = {"error": str(e)[:200]}
+    # bottom level of the headline network alone (level 3 of 3), fused level kernel
+    try:
+        ra = qpn_b200.setup("robust_avoid_simple", seed=DATA_SEED)
+        X = qpn_b200.examples.robust_avoid_batch(ra, 8192, seed=7)
+        solver, lv, run, so, po = level_run(ra, ra.num_levels(), X)
+        t = timed(run, 5)
+        extra["robust_avoid_bottom_level"] = {"value": len(X) / t, "unit": UNIT, "batch": len(X), "ms_per_launch": 1e3 * t,
+                                               "all_solved": bool(so.bool().all()), "p50_pivots_per_solve": float(np.median(po.cpu().numpy())),
+                                               "note": "per GPU, device-timed; level 3 of 3 only (fused verify -> solve_qep -> verify kernel)"}
+        solver.close()
+    except Exception as e:                                      # noqa: BLE001
+        extra["robust_avoid_bottom_level"] = {"error": str(e)[:200]}
+    # BASELINE configs[3]: synthetic 3-level chain, n = 64 per node -- its bottom level (lifted n = 256, 64 rows swept)
+    try:
+        ch = qpn_b200.setup("synthetic_chain")
+        X = ch.default_initialization + 0.7 * np.random.default_rng([0xB200, rank, 13]).normal(size=(4096, ch.n_vars))
+        solver, lv, run, so, po = level_run(ch, ch.num_levels(), X)
+        info = lv.info()
+        t = timed(run, 2)
+        extra["synthetic_chain_bottom_level"] = {"value": len(X) / t, "unit": UNIT, "batch": len(X), "ms_per_launch": 1e3 * t,
+                                                  "all_solved": bool(so.bool().all()), "p50_pivots_per_solve": float(np.median(po.cpu().numpy())),
+                                                  "lifted_n": info["n"], "live_columns": info["ncol0"], "plan_pivots": info["plan_pivots"],
+                                                  "note": "per GPU, device-timed; level 3 of 3 only"}
+        solver.close()
+    except Exception as e:                                      # noqa: BLE001
+        extra["synthetic_chain_bottom_level"] = {"error": str(e)[:200]}
+    # BASELINE configs[4]: n = 256, m = 512 monotone stress QP as a one-node QPNet (lifted level AVI n = 1,536)
+    try:
+        ms = qpn_b200.setup("monotone_stress")
+        X = ms.default_initialization + np.random.default_rng([0xB200, rank, 9]).normal(size=(SM_COUNT, ms.n_vars))
+        solver, lv, run, so, po = level_run(ms, 1, X)
+        info = lv.info()
+        t = timed(run, 1)
+        extra["monotone_stress_n256_m512"] = {"value": len(X) / t, "unit": UNIT, "batch": len(X), "ms_per_launch": 1e3 * t,
+                                               "all_solved": bool(so.bool().all()), "p50_pivots_per_solve": float(np.median(po.cpu().numpy())),
+                                               "lifted_n": info["n"], "live_columns": info["ncol0"], "plan_pivots": info["plan_pivots"],
+                                               "path": "global-memory tableau" if info["big"] else "shared-memory tableau",
+                                               "note": "per GPU, device-timed; one wave of persistent CTAs"}
+        solver.close()
+    except Exception as e:                                      # noqa: BLE001
+        extra["monotone_stress_n256_m512"] = {"error": str(e)[:200]}
+    return extra
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=4096, help="instances per GPU per step")
+    ap.add_argument("--batch", type=int, default=65536, help="instances per step, whole job (sharded over the GPUs)")
+    ap.add_argument("--threads", type=int, default=0, help="host threads per rank that drive the batch (0 = by core count)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-multilevel", action="store_true", help="skip the three-level robust_avoid extra (spawns host worker processes)")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -191,304 +316,197 @@ def main():
     import torch
     import torch.distributed as dist
     import qpn_b200
+    from qpn_b200.netsolve import NetBinding
+    from qpn_b200.sharding import BlockLayout, ResultGather, shard_range
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    net = qpn_b200.setup("four_player_matrix_game")
-    solver = qpn_b200.BatchedSolver(net, device=local_rank)     # raises if libqpn_cuda / the GPU is missing
-    eng = solver.engine
-    level = solver.resident_level(1)
-    B, nv, K, W = args.batch, net.n_vars, args.steps, args.warmup
-    # An explicit stream: torch's default stream has handle 0, which the C ABI reads as "use the
-    # handle's own stream" -- the events below must sit on the stream the kernel is launched on.
+    net = qpn_b200.setup("robust_avoid_simple", seed=DATA_SEED)
+    eng = qpn_b200.Engine(local_rank)                           # raises if libqpn_cuda / the GPU is missing
+    threads = args.threads or max(1, min(12, cpu_cores() // world))
+    nb = NetBinding(net, eng.lib, "qpn_net_", handle=eng.h, threads=threads)
+    Btot, nv, nl, K, W = args.batch, net.n_vars, net.num_levels(), args.steps, args.warmup
+    lo, hi = shard_range(Btot, rank, world)
+    B = hi - lo
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
-    assert stream.cuda_stream != 0
 
-    # ---- device-resident arm -------------------------------------------------------------------
-    x_in = [torch.from_numpy(inits_for(rank, B, k)).to(dev) for k in range(min(K, 8))]
-    # Outputs of one rank live in ONE contiguous block [x_out | iters | pivots | solved] so that the
-    # final gather of solutions / statuses / pivot counts is a single NCCL all-gather.
-    o_it, o_pv, o_sol = B * nv * 8, B * nv * 8 + 4 * B, B * nv * 8 + 8 * B
-    nbytes = (o_sol + B + 15) // 16 * 16
-    block = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    x_out = block[:o_it].view(torch.float64).view(B, nv)
-    iters = block[o_it:o_pv].view(torch.int32)
-    pivots = block[o_pv:o_sol].view(torch.int32)
-    solved = block[o_sol:o_sol + B]
-    # Final gather of solutions / statuses / pivot counts.  Preferred form: the gathered buffer is
-    # symmetric memory, every rank's level kernel stores its outputs straight into ITS slot of rank 0's buffer
-    # (peer stores over NVLink from the kernel's own epilogue, no copy kernel), and a symmetric-memory barrier
-    # on the same stream publishes them.  Falls back to one NCCL all-gather per step when symmetric memory
-    # cannot be set up (or with QPN_BENCH_GATHER=nccl).
-    gather_mode, hdl, out_base = "none", None, block.data_ptr()
+    # ---- inputs: a few distinct batches, rotated over the steps; every rank generates the job's batch and keeps its shard
+    nsets = min(max(K, W), 4)
+    host_sets = [qpn_b200.examples.robust_avoid_batch(net, Btot, seed=k)[lo:hi].copy() for k in range(nsets)]
+    dev_in = [torch.from_numpy(X).to(dev) for X in host_sets]
+    dev_out = torch.empty((B, nv), dtype=torch.float64, device=dev)
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
+    flags = dict(solved=pin((B,), torch.uint8), level_iters=pin((B, nl), torch.int32), error=pin((B,), torch.int32))
+    # the one exchange per solve: x | solved | level_iters | error of every rank in one block
+    gather = None
     if world > 1:
-        gather_mode = "nccl all_gather_into_tensor"
-        if os.environ.get("QPN_BENCH_GATHER", "p2p") == "p2p":
-            try:
-                import torch.distributed._symmetric_memory as symm
-                g_block = symm.empty(world * nbytes, dtype=torch.uint8, device=dev)
-                hdl = symm.rendezvous(g_block, dist.group.WORLD)
-                out_base = int(hdl.buffer_ptrs[0]) + rank * nbytes
-                gather_mode = "kernel stores into rank 0's symmetric buffer over NVLink + symmetric-memory barrier"
-            except Exception as e:                          # noqa: BLE001
-                hdl = None
-                if rank == 0:
-                    print(f"[bench] symmetric memory unavailable ({str(e)[:120]}); using NCCL all-gather", file=sys.stderr)
-        if hdl is None:
-            g_block = torch.empty(world * nbytes, dtype=torch.uint8, device=dev)
-            out_base = block.data_ptr()
+        layout = BlockLayout([("x", np.float64, (nv,)), ("solved", np.uint8, ()), ("level_iters", np.int32, (nl,)), ("error", np.int32, ())],
+                             max(h - l for l, h in (shard_range(Btot, r, world) for r in range(world))))
+        gather = ResultGather(layout, device=dev, group=None, mode=os.environ.get("QPN_BENCH_GATHER", "nccl"))
+        xoff, soff = layout.fields[0][3], layout.fields[1][3]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
     def step_dev(k):
-        level.solve_dev(B, x_in[k % len(x_in)].data_ptr(), out_base, out_base + o_sol, out_base + o_it,
-                        out_base + o_pv, None, stream.cuda_stream)
-
-    def gather():
-        if hdl is not None:
-            hdl.barrier(channel=0)
-        elif world > 1:
-            dist.all_gather_into_tensor(g_block, block)
+        nb.solve_dev(B, dev_in[k % nsets].data_ptr(), dev_out.data_ptr(), out=flags)
+        if gather is not None:
+            # x is already on the device; the flags are produced on the host: pack them behind x and exchange once
+            blk = gather.block
+            blk[xoff: xoff + B * nv * 8].view(torch.float64).copy_(dev_out.view(-1), non_blocking=True)
+            hb = gather.host_block.numpy()
+            layout.pack({"x": np.zeros((0, nv)), "solved": flags["solved"], "level_iters": flags["level_iters"], "error": flags["error"]}, hb)
+            blk[soff:].copy_(gather.host_block[soff:], non_blocking=True)
+            gather.exchange_device()
+            stream.synchronize()
 
     for k in range(W):
-        step_dev(k); gather()
+        step_dev(k)
     torch.cuda.synchronize()
-    if hdl is not None:
-        # rank 0 holds every rank's block: check them all there
-        if rank == 0:
-            gb = g_block.view(world, nbytes)
-            assert bool(gb[:, o_sol:o_sol + B].bool().all()), "warm-up: not every instance (of every rank) reached an equilibrium"
-        solved = g_block[o_sol:o_sol + B] if rank == 0 else None
-        pivots = g_block[o_pv:o_sol].view(torch.int32) if rank == 0 else None
-    else:
-        assert bool(solved.bool().all()), "warm-up: not every instance reached an equilibrium"
+    solved_frac_warm = float(flags["solved"].mean())
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    launches0 = eng.launches
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    st0, pr0 = nb.stats(), nb.profile()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    solved_total = 0
+    iters_sum = np.zeros(nl)
     for k in range(K):
         flush.zero_()                                   # evict the previous step's lines from L2 (not timed)
+        torch.cuda.synchronize()
         ev[k][0].record(stream)
         step_dev(k)
         ev[k][1].record(stream)
-        gather()
-        ev[k][2].record(stream)
+        solved_total += int(flags["solved"].sum())
+        iters_sum += flags["level_iters"].sum(0)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    launches = eng.launches - launches0
-    t_kernel = sum(a.elapsed_time(b) for a, b, _ in ev) * 1e-3
-    t_step = sum(a.elapsed_time(c) for a, _, c in ev) * 1e-3
-    if hdl is not None and rank == 0:
-        gb = g_block.view(world, nbytes)
-        all_solved = bool(gb[:, o_sol:o_sol + B].bool().all())            # every rank's statuses, gathered on rank 0
-        piv_host = gb[:, o_pv:o_sol].contiguous().view(torch.int32).cpu().numpy().ravel()
-    elif hdl is not None:
-        all_solved, piv_host = True, np.zeros(1)
-    else:
-        piv_host = pivots.cpu().numpy()
-        all_solved = bool(solved.bool().all())
+    st1, pr1 = nb.stats(), nb.profile()
+    t_step = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
+    launches = st1["launches"] - st0["launches"]
 
-    # ---- end-to-end arm: pinned host buffers through the C ABI ---------------------------------
-    hx = [torch.from_numpy(inits_for(rank, B, 100 + k)).pin_memory() for k in range(min(K, 8))]
-    out = dict(x=torch.empty((B, nv), dtype=torch.float64).pin_memory().numpy(),
-               solved=torch.empty(B, dtype=torch.uint8).pin_memory().numpy(),
-               iters=torch.empty(B, dtype=torch.int32).pin_memory().numpy(),
-               pivots=torch.empty(B, dtype=torch.int32).pin_memory().numpy(), lam=None)
-    hxn = [t.numpy() for t in hx]
-    for k in range(W):
-        level.solve(hxn[k % len(hxn)], out=out, want_lam=False)
-    torch.cuda.synchronize()
+    # ---- end-to-end arm: pinned host buffers through the host-pointer C-ABI call ------------------------------------
+    hx = [torch.from_numpy(X).pin_memory().numpy() for X in host_sets]
+    hout = dict(x=pin((B, nv), torch.float64), **flags)
+    for k in range(2):
+        nb.solve_arrays(hx[k % nsets], out=hout)
     if world > 1:
         dist.barrier()
+    pe0 = nb.profile()
     t_e2e = 0.0
     for k in range(K):
         flush.zero_()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        level.solve(hxn[k % len(hxn)], out=out, want_lam=False)        # H2D + kernel + D2H + sync
+        r = nb.solve_arrays(hx[k % nsets], out=hout)           # H2D + every launch of the solve + D2H + sync
+        if gather is not None:
+            gather.exchange({"x": r["x"], "solved": flags["solved"], "level_iters": flags["level_iters"], "error": flags["error"]})
         t_e2e += time.perf_counter() - t0
-        assert out["solved"].all()
+    pe1 = nb.profile()
     clocks = sampler.stop() if sampler else None
+    # pageable host buffers (what a Julia Matrix{Float64} is): the same call, staged through the driver's bounce buffers
+    t_page = 0.0
+    reps_page = min(K, 3)
+    for k in range(reps_page):
+        Xp = np.array(host_sets[k % nsets])
+        t0 = time.perf_counter()
+        nb.solve_arrays(Xp)
+        t_page += time.perf_counter() - t0
+
+    # ---- per-kernel durations: one extra pass with every launch bracketed by CUDA events on its stream ----------------
+    nb.set_option("profile", 1)
+    pk0 = nb.profile()
+    for k in range(2):
+        nb.solve_dev(B, dev_in[k % nsets].data_ptr(), dev_out.data_ptr(), out=flags)
+    pk1 = nb.profile()
+    nb.set_option("profile", 0)
+    kern = {k: {f: pk1[k][f] - pk0[k][f] for f in ("launches", "units", "ms")} for k in ("verify", "solve_qep", "member")}
 
     if world > 1:
-        t = torch.tensor([t_kernel, t_step, t_e2e], dtype=torch.float64, device=dev)
+        t = torch.tensor([t_step, t_e2e, t_page], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_kernel, t_step, t_e2e = (float(v) for v in t.cpu())
-        ok = torch.tensor([int(all_solved)], device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        all_solved = bool(ok.item())
+        t_step, t_e2e, t_page = (float(v) for v in t.cpu())
+        s = torch.tensor([solved_total, launches], dtype=torch.float64, device=dev)
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        solved_total, launches = (float(v) for v in s.cpu())
 
-    # ---- secondary workload (reported under "extra", not the headline): the bottom level of
-    # robust_avoid_simple (BASELINE.json configs[2]; LP-like nodes, lifted AVI n = 52, presolve on
-    # every instance).  The full three-level solve is still a per-instance host recursion.
     extra = None
-    try:
-        ra = qpn_b200.setup("robust_avoid_simple")
-        ra_solver = qpn_b200.BatchedSolver(ra, engine=eng)
-        ra_level = ra_solver.resident_level(ra.num_levels())
-        Br = 8192
-        rng = np.random.default_rng([0xB200, rank, 7])
-        Xr = np.tile(ra.default_initialization, (Br, 1))
-        Xr[:, 0:6] += 0.5 * rng.normal(size=(Br, 6)); Xr[:, 6:12] = rng.uniform(-1, 1, (Br, 6))
-        xr = torch.from_numpy(Xr).to(dev)
-        xo = torch.empty_like(xr); so = torch.empty(Br, dtype=torch.uint8, device=dev)
-        io = torch.empty(Br, dtype=torch.int32, device=dev); po = torch.empty(Br, dtype=torch.int32, device=dev)
-        run = lambda: ra_level.solve_dev(Br, xr.data_ptr(), xo.data_ptr(), so.data_ptr(), io.data_ptr(), po.data_ptr(), None, stream.cuda_stream)
-        for _ in range(3):
-            run()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        tr = 0.0
-        for _ in range(5):
-            flush.zero_(); e0.record(stream); run(); e1.record(stream); torch.cuda.synchronize(); tr += e0.elapsed_time(e1) * 1e-3
-        extra = {"robust_avoid_bottom_level": {"value": 5 * Br / tr, "unit": UNIT, "batch": Br, "ms_per_launch": 1e3 * tr / 5,
-                                               "all_solved": bool(so.bool().all()), "p50_pivots_per_solve": float(np.median(po.cpu().numpy())),
-                                               "note": "per GPU, device-timed; level 3 of 3 only"}}
-    except Exception as e:                                      # the headline must not depend on the extra
-        extra = {"robust_avoid_bottom_level": {"error": str(e)[:200]}}
-
-    # ---- BASELINE.json configs[4]: the n = 256, m = 512 monotone stress QP as a one-node QPNet (lifted level AVI
-    # n = 1,536) on the global-memory tableau path: one wave of persistent CTAs (one instance per SM).
-    try:
-        ms = qpn_b200.setup("monotone_stress")
-        ms_solver = qpn_b200.BatchedSolver(ms, engine=eng)
-        ms_level = ms_solver.resident_level(1)
-        info = ms_level.info()
-        Bm = SM_COUNT
-        rng = np.random.default_rng([0xB200, rank, 9])
-        xm = torch.from_numpy(ms.default_initialization + rng.normal(size=(Bm, ms.n_vars))).to(dev)
-        xo = torch.empty_like(xm); so = torch.empty(Bm, dtype=torch.uint8, device=dev)
-        io = torch.empty(Bm, dtype=torch.int32, device=dev); po = torch.empty(Bm, dtype=torch.int32, device=dev)
-        run = lambda: ms_level.solve_dev(Bm, xm.data_ptr(), xo.data_ptr(), so.data_ptr(), io.data_ptr(), po.data_ptr(), None, stream.cuda_stream)
-        run(); torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        flush.zero_(); e0.record(stream); run(); e1.record(stream); torch.cuda.synchronize()
-        tm = e0.elapsed_time(e1) * 1e-3
-        pv = po.cpu().numpy().astype(np.float64)
-        # algorithmic HBM bytes: every pivot an instance runs itself reads and writes the live tableau once
-        # (16 B per entry, n rows x live columns); the plan's pivots were run once for the whole batch
-        own_pivots = float((pv - info["plan_pivots"]).sum())
-        alg = own_pivots * 16.0 * info["n"] * info["ncol0"]
-        peak_m, _ = measured_hbm_peak()
-        extra["monotone_stress_n256_m512"] = {
-            "value": Bm / tm, "unit": UNIT, "batch": Bm, "ms_per_launch": 1e3 * tm, "all_solved": bool(so.bool().all()),
-            "p50_pivots_per_solve": float(np.median(pv)), "lifted_n": info["n"], "live_columns": info["ncol0"], "plan_pivots": info["plan_pivots"],
-            "path": "global-memory tableau" if info["big"] else "shared-memory tableau",
-            "roofline": {"bound": "hbm", "achieved": NCU_DRAM_BYTES_BIG_LEVEL_B148 / tm / 1e9, "peak": peak_m, "unit": "GB/s",
-                         "frac": NCU_DRAM_BYTES_BIG_LEVEL_B148 / tm / 1e9 / peak_m, "traffic": NCU_DRAM_BYTES_BIG_LEVEL_B148,
-                         "dense_upper_bound_bytes": alg,
-                         "note": "achieved = DRAM bytes of this launch measured by ncu (same batch, same data) / event-timed duration; the dense "
-                                 "bound 16 B x rows x live columns x pivots overstates it by 12x: the rows of free basics (1,024 of 1,536) are frozen "
-                                 "after the plan and never swept, pivots are queued four deep and swept in one pass, rows with a zero entering "
-                                 "entry and column pairs with zero pivot-row entries are skipped, and L2 serves 75 % of the sector requests; "
-                                 "the sweep is load-latency bound per SM (L1 36 %, issue 27 %, DRAM 31 % of the copy peak), not HBM bound"},
-            "note": "per GPU, device-timed; verify -> solve_qep -> verify fused in level_equilibrium_big_kernel"}
-        ms_solver.close()
-    except Exception as e:
-        extra["monotone_stress_n256_m512"] = {"error": str(e)[:200]}
-
-    # ---- BASELINE.json configs[3]: the synthetic 3-level chain (n = 64 per node).  Its levels are measured one at a
-    # time -- here the bottom level (64 own variables, 136 parameters, lifted level AVI n = 256 of which 64 rows are
-    # swept): the full three-level solve needs solution graphs of 64-variable nodes, which neither the host mirror nor
-    # (per its README) the reference produces in usable time.
-    try:
-        ch = qpn_b200.setup("synthetic_chain")
-        ch_solver = qpn_b200.BatchedSolver(ch, engine=eng)
-        ch_level = ch_solver.resident_level(ch.num_levels())
-        cinfo = ch_level.info()
-        Bc = 4096
-        rng = np.random.default_rng([0xB200, rank, 13])
-        xc = torch.from_numpy(ch.default_initialization + 0.7 * rng.normal(size=(Bc, ch.n_vars))).to(dev)
-        xo = torch.empty_like(xc); so = torch.empty(Bc, dtype=torch.uint8, device=dev)
-        io = torch.empty(Bc, dtype=torch.int32, device=dev); po = torch.empty(Bc, dtype=torch.int32, device=dev)
-        run = lambda: ch_level.solve_dev(Bc, xc.data_ptr(), xo.data_ptr(), so.data_ptr(), io.data_ptr(), po.data_ptr(), None, stream.cuda_stream)
-        run(); torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        flush.zero_(); e0.record(stream); run(); e1.record(stream); torch.cuda.synchronize()
-        tc = e0.elapsed_time(e1) * 1e-3
-        extra["synthetic_chain_bottom_level"] = {
-            "value": Bc / tc, "unit": UNIT, "batch": Bc, "ms_per_launch": 1e3 * tc, "all_solved": bool(so.bool().all()),
-            "p50_pivots_per_solve": float(np.median(po.cpu().numpy())), "lifted_n": cinfo["n"], "live_columns": cinfo["ncol0"],
-            "plan_pivots": cinfo["plan_pivots"],
-            "path": "global-memory engine" if cinfo["big"] else "shared-memory tableau (swept rows only: 64 of 256)",
-            "note": "per GPU, device-timed; level 3 of 3 only"}
-        ch_solver.close()
-    except Exception as e:                                      # noqa: BLE001
-        extra["synthetic_chain_bottom_level"] = {"error": str(e)[:200]}
-
-    # ---- BASELINE.json configs[2] in full: three-level robust_avoid_simple solves (vertex exploration on), the host
-    # recursion of solve_base! sharded over worker processes that are all served by this rank's engine handle
-    # (workers.py).  Host-bound (piece generation / set operations in the Python mirror): reported as an extra.
-    if world == 1 and not args.no_multilevel:
+    if rank == 0 and not args.no_extras:
         try:
-            ra3 = qpn_b200.setup("robust_avoid_simple", seed=3)
-            nw = max(1, min(cpu_cores() - 1, 15))
-            Bf = 128 * nw
-            rng = np.random.default_rng([0xB200, rank, 11])
-            Xf = np.tile(ra3.default_initialization, (Bf, 1))
-            Xf[:, 0:6] += 0.3 * rng.normal(size=(Bf, 6)); Xf[:, 6:12] = rng.uniform(-1, 1, (Bf, 6))
-            with qpn_b200.MultilevelPool(ra3, nw, engine=eng) as pool:
-                pool.solve(Xf[:4 * nw])                                   # processes up, piece memos warm
-                st = {}
-                l0 = eng.launches
-                t0 = time.perf_counter(); res = pool.solve(Xf, stats=st); tf = time.perf_counter() - t0
-            extra["robust_avoid_three_levels"] = {
-                "value": Bf / tf, "unit": UNIT, "batch": Bf, "host_workers": nw, "wall_s": tf,
-                "solved_fraction": float(np.mean([r["solved"] for r in res])), "device_launches": int(eng.launches - l0),
-                "device_requests_before_regrouping": int(st.get("requests", 0)),
-                "note": "per GPU, host clock, inputs and results in host memory; every numeric step on the device, the recursion of "
-                        "solve_base! in worker processes (host-bound)"}
+            extra = extras(qpn_b200, torch, eng, dev, stream, flush, rank)
         except Exception as e:                                  # noqa: BLE001
-            extra["robust_avoid_three_levels"] = {"error": str(e)[:200]}
+            extra = {"error": str(e)[:200]}
 
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
-        # algorithmic HBM bytes of one launch: x in, x/solved/iters/pivots out, + the level's matrices once
-        alg_bytes = B * (8 * nv + 8 * nv + 1 + 4 + 4) + 8 * (32 * 32 + 3 * 32 + 4 * (2 * 8 + 2 + 2 * 8 + 4)) + 8 * 4 * nv
-        achieved = alg_bytes / (t_kernel / K) / 1e9
+        nproj = net.options.num_projections
+        dom = max(kern, key=lambda k: kern[k]["ms"])
+        # algorithmic HBM bytes per unit of each kernel: slot index + x in (+ x out) + flags / masks / projections
+        alg_unit = {"solve_qep": 4 + 8 * nv + 8 * nv + 9 + 8 * nproj, "verify": 4 + 8 * nv + 1 + 16, "member": 32 + 8 * nv + 1}
+        kd = kern[dom]
+        per_launch_units = kd["units"] / max(kd["launches"], 1)
+        launch_s = kd["ms"] * 1e-3 / max(kd["launches"], 1)
+        achieved = alg_unit[dom] * per_launch_units / launch_s / 1e9 if launch_s > 0 else 0.0
+        total_kern_ms = sum(v["ms"] for v in kern.values())
+        ncu_k = NCU.get(dom, {})
         line = {
-            "metric": METRIC, "value": world * B * K / t_step, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": 1e3 * t_step / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": Btot * K / t_step, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": 1e3 * t_step / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "n_vars": nv, "avi_size": 32, "l2": "flushed between steps (256 MB write)",
-                       "timing": "CUDA events on the launching stream, max over ranks", "all_solved": all_solved, "gather": gather_mode,
-                       "p50_pivots_per_solve": float(np.median(piv_host)), "kernel_ms_per_step": 1e3 * t_kernel / K},
-            "e2e": {"value": world * B * K / t_e2e, "unit": UNIT, "h2d_bytes_per_step": B * nv * 8, "d2h_bytes_per_step": B * (nv * 8 + 1 + 4 + 4),
-                    "timing": "host clock around the synchronous C-ABI call (qpn_level_equilibrium_resident), pinned buffers"},
+            "config": {"workload": WORKLOAD, "batch": Btot, "l2": L2_NOTE},
+            "detail": {"instances_per_gpu": B, "host_threads_per_rank": threads, "n_vars": nv, "levels": nl,
+                       "timing": "CUDA events around the synchronous call on every rank, max over ranks; the one result exchange per solve included",
+                       "solved_fraction": solved_total / (Btot * K), "mean_iterations_per_level": (iters_sum / (B * K)).tolist(),
+                       "gather": (gather.mode + ": one block per rank per solve") if gather else "none (1 GPU)",
+                       "rounds_per_step": (st1["rounds"] - st0["rounds"]) / K, "batched_calls_per_step": (st1["calls"] - st0["calls"]) / K,
+                       "requests_per_step": (st1["requests"] - st0["requests"]) / K, "new_lps_in_timed_region": st1["lps"] - st0["lps"],
+                       "host_ms_per_step_summed_over_threads": (st1["host_ns"] - st0["host_ns"]) / 1e6 / K,
+                       "backend_ms_per_step_summed_over_threads": (st1["backend_ns"] - st0["backend_ns"]) / 1e6 / K,
+                       "staged_h2d_bytes_per_step": (pr1["h2d_bytes"] - pr0["h2d_bytes"]) / K,
+                       "staged_d2h_bytes_per_step": (pr1["d2h_bytes"] - pr0["d2h_bytes"]) / K},
+            "e2e": {"value": Btot * K / t_e2e, "unit": UNIT, "h2d_bytes_per_step": (pe1["h2d_bytes"] - pe0["h2d_bytes"]) / K,
+                    "d2h_bytes_per_step": (pe1["d2h_bytes"] - pe0["d2h_bytes"]) / K,
+                    "timing": "host clock around the synchronous C-ABI call (qpn_net_solve_batched), pinned host buffers; bytes counted by the "
+                              "library: inits in, request lists in, flags / masks / statuses out, x and x_fail out (this rank)"},
+            "e2e_pageable": {"value": Btot * reps_page / t_page, "unit": UNIT, "steps": reps_page,
+                             "note": "same call with pageable numpy buffers (a Julia Matrix{Float64} is pageable)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH_B4096 if B == 4096 else None,
-                         "algorithmic_bytes_per_launch": alg_bytes,
-                         "kernel": "level_equilibrium_kernel<32>", "peak_source": peak_src,
-                         "note": "the fused pivoting kernel is issue/latency bound in shared memory (ncu: IPC 1.7/SM, fp64 pipe 10 %, "
-                                 "0 % tensor), not HBM bound; see DESIGN.md 5 and profiles/"},
+                         "traffic": ncu_k.get("dram_bytes_per_launch"),
+                         "kernel": {"solve_qep": "net_qep_kernel", "verify": "net_verify_kernel", "member": "net_member_kernel"}[dom],
+                         "algorithmic_bytes_per_unit": alg_unit[dom], "units_per_launch": per_launch_units,
+                         "avg_launch_ms": 1e3 * launch_s, "peak_source": peak_src,
+                         "kernel_time_share": {k: (v["ms"] / total_kern_ms if total_kern_ms else 0.0) for k, v in kern.items()},
+                         "kernel_ms_per_step": {k: v["ms"] / 2 for k, v in kern.items()},
+                         "launches_per_step": {k: v["launches"] / 2 for k, v in kern.items()},
+                         "note": "durations from a separate pass with every launch bracketed by CUDA events on its own stream (host threads run "
+                                 "concurrent streams, so the per-kernel sums exceed the step time when launches overlap); the pivoting kernels are "
+                                 "issue / shared-memory-latency bound (fp64 rank-1 updates in shared memory), not HBM bound: see roofline_onchip, "
+                                 "DESIGN.md 5 and profiles/"},
             "clocks": clocks,
             "extra": extra,
         }
-        if B == 4096:
-            # On-chip view (not the contract's HBM/tensor roofline, which this latency/issue-bound fp64 kernel
-            # cannot approach): shared-memory bandwidth 128 B/clk/SM and issue rate 4 warp-instr/clk/SM at the
-            # SM clock seen during the run; counts per launch from the committed ncu capture.
+        if ncu_k.get("smem_wavefronts_per_unit"):
             clk = (clocks or {}).get("sm_mhz") or 1965.0
-            t_k = t_kernel / K
             smem_peak = SM_COUNT * 128 * clk * 1e6 / 1e12
-            issue_peak = SM_COUNT * 4 * clk * 1e6 / 1e12
-            line["roofline_onchip"] = {
-                "smem": {"achieved": NCU_SMEM_WAVEFRONTS_PER_LAUNCH_B4096 * 128 / t_k / 1e12, "peak": smem_peak, "unit": "TB/s",
-                         "frac": NCU_SMEM_WAVEFRONTS_PER_LAUNCH_B4096 * 128 / t_k / 1e12 / smem_peak},
-                "issue": {"achieved": NCU_WARP_INSTRUCTIONS_PER_LAUNCH_B4096 / t_k / 1e12, "peak": issue_peak, "unit": "T warp-instr/s",
-                          "frac": NCU_WARP_INSTRUCTIONS_PER_LAUNCH_B4096 / t_k / 1e12 / issue_peak},
-                "source": "profiles/r1_final_level_kernel_ncu_full_summary.csv"}
+            wf = ncu_k["smem_wavefronts_per_unit"] * per_launch_units
+            line["roofline_onchip"] = {"smem": {"achieved": wf * 128 / launch_s / 1e12, "peak": smem_peak, "unit": "TB/s",
+                                                "frac": wf * 128 / launch_s / 1e12 / smem_peak},
+                                       "source": ncu_k.get("source")}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
+            if extra is not None:
+                try:
+                    extra["cpu_reference_structure_no_shared_memo"] = cpu_no_memo_sample()
+                except Exception as e:                          # noqa: BLE001
+                    extra["cpu_reference_structure_no_shared_memo"] = {"error": str(e)[:200]}
         print(json.dumps(line), flush=True)
-    solver.close()
+    nb.close()
+    eng.close()
     if world > 1:
         dist.destroy_process_group()
 

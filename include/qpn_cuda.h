@@ -269,7 +269,7 @@ typedef struct qpn_net qpn_net;
 int qpn_net_create(qpn_handle *h, const qpn_net_desc *desc, qpn_net **out);
 int qpn_net_destroy(qpn_net *net);
 const char *qpn_net_last_error(qpn_net *net);
-/* "threads": host threads that drive the batch (each with its own stream), default 4. */
+/* "threads": host threads that drive the batch (each with its own stream), default 4; "profile": see qpn_net_profile. */
 int qpn_net_set_option(qpn_net *net, const char *name, int64_t value);
 /*
  * solve(qpn, inits::Matrix): inits nv x batch (host).  x_out: nv x batch -- x_opt where solved_out[b] = 1, the
@@ -280,6 +280,14 @@ int qpn_net_set_option(qpn_net *net, const char *name, int64_t value);
  */
 int qpn_net_solve_batched(qpn_net *net, int batch, const double *inits, double *x_out, uint8_t *solved_out,
                           int32_t *level_iters_out, int32_t *error_out);
+/* The same with inits / x_out in DEVICE memory of the net's GPU (the flags and counters are produced on the host). */
+int qpn_net_solve_batched_dev(qpn_net *net, int batch, const double *inits_dev, double *x_out_dev, uint8_t *solved_out,
+                              int32_t *level_iters_out, int32_t *error_out);
+/* Kernel accounting since the net was created.  out[0..15]: for k in {verify, solve_qep, membership}:
+ * out[4k] launches, out[4k+1] units (instances; pairs for membership), out[4k+2] summed duration in ms -- durations
+ * only accumulate while option "profile" = 1 (every launch is then bracketed by CUDA events on its stream);
+ * out[12] / out[13]: bytes copied host-to-device / device-to-host. */
+int qpn_net_profile(qpn_net *net, double *out);
 /* The solution graphs of the last batch (ret.Sol of algorithm.jl:116): number of pieces of player `player` for
  * instance b (-1: none), the id of piece k, and a piece's rows (A: m x nv row-major; rl / ru: 1 = strict). */
 int qpn_net_sol_count(qpn_net *net, int b, int player);

@@ -84,6 +84,7 @@ EXPORTS = [
     "qpn_level_upload", "qpn_level_release", "qpn_level_equilibrium_resident", "qpn_level_equilibrium_resident_dev",
     "qpn_malloc", "qpn_free", "qpn_memcpy_h2d", "qpn_memcpy_d2h", "qpn_set_option", "qpn_big_launch_count", "qpn_level_info",
     "qpn_net_create", "qpn_net_destroy", "qpn_net_last_error", "qpn_net_set_option", "qpn_net_solve_batched",
+    "qpn_net_solve_batched_dev", "qpn_net_profile",
     "qpn_net_sol_count", "qpn_net_sol_piece", "qpn_net_piece_rows", "qpn_net_piece_get", "qpn_net_stats",
 ]
 

@@ -204,6 +204,19 @@ def setup_synthetic_chain(n=64, levels=3, n_params=8, seed=4, **kwargs):
     return net
 
 
+def robust_avoid_batch(net, batch, seed=0, sigma=0.5):
+    """The perturbed instances of BASELINE.json configs[2]: the default initialisation with the
+    parameters xe, xo (ego / obstacle positions: nobody owns them) moved by N(0, sigma^2) -- "perturbed obstacles" --
+    and the controls ue, uo started at U(-1, 1).  Returns (batch, n_vars)."""
+    rng = np.random.default_rng([0xB200, int(seed)])
+    nxo = len(net.var["xo"])
+    X = np.tile(net.default_initialization, (batch, 1))
+    X[:, 0:2 + nxo] += sigma * rng.normal(size=(batch, 2 + nxo))
+    lo, hi = 2 + nxo, 2 + nxo + 2 + len(net.var["uo"])
+    X[:, lo:hi] = rng.uniform(-1.0, 1.0, (batch, hi - lo))
+    return X
+
+
 _SETUPS = {
     "monotone_stress": setup_monotone_stress,
     "synthetic_chain": setup_synthetic_chain,

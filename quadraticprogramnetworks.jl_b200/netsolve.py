@@ -119,12 +119,17 @@ class NetBinding:
         except Exception:
             pass
 
-    def solve_arrays(self, inits):
-        """inits (B, nv) -> dict of arrays: x (B, nv), solved (B,), level_iters (B, nlevels), error (B,)."""
-        X = np.ascontiguousarray(np.atleast_2d(inits), dtype=np.float64)
+    def solve_arrays(self, inits, out=None):
+        """inits (B, nv) -> dict of arrays: x (B, nv), solved (B,), level_iters (B, nlevels), error (B,).
+        out: preallocated arrays of those names (e.g. pinned memory)."""
+        X = inits if (isinstance(inits, np.ndarray) and inits.ndim == 2 and inits.dtype == np.float64 and inits.flags.c_contiguous) \
+            else np.ascontiguousarray(np.atleast_2d(inits), dtype=np.float64)
         B = X.shape[0]
-        x = np.empty((B, self.nv)); solved = np.zeros(B, np.uint8)
-        iters = np.zeros((B, self.nlevels), np.int32); err = np.zeros(B, np.int32)
+        if out is not None:
+            x, solved, iters, err = out["x"], out["solved"], out["level_iters"], out["error"]
+        else:
+            x = np.empty((B, self.nv)); solved = np.zeros(B, np.uint8)
+            iters = np.zeros((B, self.nlevels), np.int32); err = np.zeros(B, np.int32)
         rc = self._f("solve_batched")(self.ptr, B, X.ctypes.data_as(dp), x.ctypes.data_as(dp), solved.ctypes.data_as(ubp),
                                       iters.ctypes.data_as(ip), err.ctypes.data_as(ip))
         if rc != 0:
@@ -134,7 +139,28 @@ class NetBinding:
                 msg = (self.lib.qpn_net_last_error(self.ptr) or b"").decode()
             from .engine import EngineError
             raise EngineError(f"{self.prefix}solve_batched failed: {msg}")
-        return dict(x=x, solved=solved.astype(bool), level_iters=iters, error=err)
+        return dict(x=x, solved=solved.view(bool) if solved.dtype == np.uint8 else solved, level_iters=iters, error=err)
+
+    def solve_dev(self, batch, inits_ptr, x_out_ptr, out=None):
+        """Device-resident form (qpn_net_solve_batched_dev): inits / x_out are device pointers (nv x batch)."""
+        B = int(batch)
+        out = out or dict(solved=np.zeros(B, np.uint8), level_iters=np.zeros((B, self.nlevels), np.int32), error=np.zeros(B, np.int32))
+        rc = self._f("solve_batched_dev")(self.ptr, B, C.c_void_p(int(inits_ptr)), C.c_void_p(int(x_out_ptr)), out["solved"].ctypes.data_as(ubp),
+                                          out["level_iters"].ctypes.data_as(ip), out["error"].ctypes.data_as(ip))
+        if rc != 0:
+            from .engine import EngineError
+            self.lib.qpn_net_last_error.restype = C.c_char_p
+            raise EngineError("qpn_net_solve_batched_dev failed: " + (self.lib.qpn_net_last_error(self.ptr) or b"").decode())
+        return out
+
+    def profile(self):
+        """qpn_net_profile: launches / units / summed ms per kernel kind, staged bytes per direction."""
+        o = np.zeros(16)
+        self._f("profile")(self.ptr, o.ctypes.data_as(dp))
+        kinds = ("verify", "solve_qep", "member")
+        d = {k: dict(launches=int(o[4 * i]), units=int(o[4 * i + 1]), ms=float(o[4 * i + 2])) for i, k in enumerate(kinds)}
+        d["h2d_bytes"], d["d2h_bytes"] = int(o[12]), int(o[13])
+        return d
 
     def piece(self, pid):
         m = self._f("piece_rows")(self.ptr, int(pid))

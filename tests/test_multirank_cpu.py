@@ -69,3 +69,42 @@ def test_sharded_solve_equals_unsharded_gloo():
     ref = L.solve(X)
     assert np.array_equal(full["x"], ref["x"]) and np.array_equal(full["pivots"], ref["pivots"])
     assert np.array_equal(full["solved"].astype(bool), ref["solved"]) and np.array_equal(full["iters"], ref["iters"])
+
+
+def _net_worker(rank, world, port, B, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    import qpn_b200
+    from tests.native_oracle import oracle_net
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    net = qpn_b200.setup("robust_avoid_simple", seed=3)
+    X = qpn_b200.examples.robust_avoid_batch(net, B, seed=5)
+    full = qpn_b200.sharding.solve_net_sharded(oracle_net(net, threads=2), X)
+    if rank == 0:
+        q.put(full)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_network_solve_equals_unsharded_gloo():
+    """solve(qpn, inits) of the three-level robust_avoid net sharded over two ranks (native state machine on the oracle
+    numerics per rank, ONE exchange of the packed result block) == the unsharded batch."""
+    import torch.multiprocessing as mp
+    import qpn_b200
+    from tests.native_oracle import oracle_net
+    B, world = 37, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_net_worker, args=(r, world, port, B, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    full = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    net = qpn_b200.setup("robust_avoid_simple", seed=3)
+    ref = oracle_net(net).solve_arrays(qpn_b200.examples.robust_avoid_batch(net, B, seed=5))
+    for k in ("x", "solved", "level_iters", "error"):
+        assert np.array_equal(full[k], ref[k]), k
