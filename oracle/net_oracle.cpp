@@ -120,9 +120,18 @@ struct OracleWorker : Worker {
     }
     void run_member(MemberBatch** bs, int nb) override;
     void finish() override { fresh_round = true; }
-    void download(double* x_out, double* xf_out) override {
-        std::memcpy(x_out, X.data(), sizeof(double) * (size_t)B * nv);
-        std::memcpy(xf_out, Xf.data(), sizeof(double) * (size_t)B * nv);
+    void projections(double* pv_out) override {
+        const int nproj = net->check_for_cycling ? net->num_projections : 0;
+        for (int b = 0; b < B; ++b)
+            for (int k = 0; k < nproj; ++k) {
+                double acc = 0.0;
+                for (int j = 0; j < nv; ++j) acc = std::fma(X[(size_t)b * nv + j], net->proj[(size_t)k * nv + j], acc);
+                pv_out[(size_t)b * nproj + k] = acc;
+            }
+    }
+    void download(double* x_out, const uint8_t* solved) override {
+        for (int b = 0; b < B; ++b)
+            std::memcpy(x_out + (size_t)b * nv, (solved[b] ? X.data() : Xf.data()) + (size_t)b * nv, sizeof(double) * nv);
     }
 };
 

@@ -843,14 +843,7 @@ void NetSolver::run_shard(int tid, int lo, int hi, const double* inits, double* 
     st.backend_ns += ns(t_host, now());
     t_host = now();
     Machine M(*cache_, w, B, &outs, lo);
-    for (int b = 0; b < B; ++b) {
-        const double* x = inits + (size_t)(lo + b) * nv;
-        for (int k = 0; k < M.nproj; ++k) {
-            double acc = 0.0;
-            for (int j = 0; j < nv; ++j) acc = std::fma(x[j], net_.proj[(size_t)k * nv + j], acc);
-            M.pv[(size_t)b * M.nproj + k] = acc;
-        }
-    }
+    if (M.nproj > 0) w->projections(M.pv.data());
     {
         auto C = std::make_unique<Cohort>();
         C->members.resize(B);
@@ -928,10 +921,9 @@ void NetSolver::run_shard(int tid, int lo, int hi, const double* inits, double* 
     }
     st.host_ns += ns(t_host, now());
     t_host = now();
-    std::vector<double> xf((size_t)B * nv);
-    w->download(x_out + (size_t)lo * nv, xf.data());
-    for (int b = 0; b < B; ++b)
-        if (!outs[lo + b].solved) std::memcpy(x_out + (size_t)(lo + b) * nv, xf.data() + (size_t)b * nv, sizeof(double) * nv);
+    std::vector<uint8_t> solved(B);
+    for (int b = 0; b < B; ++b) solved[b] = outs[lo + b].solved;
+    w->download(x_out + (size_t)lo * nv, solved.data());
     st.backend_ns += ns(t_host, now());
 }
 

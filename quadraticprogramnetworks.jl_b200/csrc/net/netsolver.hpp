@@ -105,7 +105,10 @@ struct Worker : LPBackend {
     virtual void run_qep(int gavi, const LevelGaviInfo& info, QepBatch** b, int nb, bool snap) = 0;
     virtual void run_member(MemberBatch** b, int nb) = 0;
     virtual void finish() = 0;                   // all results of the enqueued calls are behind the batches' pointers
-    virtual void download(double* x_out, double* x_fail_out) = 0;
+    // projections of every slot's x onto the net's cycle-check vectors: pv_out B x nproj (algorithm.jl:14)
+    virtual void projections(double* pv_out) = 0;
+    // x_out (nv x B) = x where solved[b], the reference's x_fail otherwise (algorithm.jl:116,125)
+    virtual void download(double* x_out, const uint8_t* solved) = 0;
     virtual int64_t launches() const { return 0; }
 };
 struct Store {              // shared by the workers of one net: resident copies of nodes / GAVIs / pieces

@@ -118,6 +118,26 @@ net_qep_kernel(const __grid_constant__ GaviDesc g, const __grid_constant__ GaviP
     if (i == 0) { status_out[b] = st; pivots_out[b] = piv; moved_out[b] = (uint8_t)moved; }
 }
 
+// pv[b][k] = sum_j x_b[j] proj[k][j] (sequential fma, as the level kernel's cycle check): one thread per (slot, k).
+__global__ void net_proj_kernel(int B, int nv, int nproj, const double* __restrict__ X, const double* __restrict__ proj,
+                                double* __restrict__ pv) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)B * nproj) return;
+    const int b = (int)(gid / nproj), k = (int)(gid - (long long)b * nproj);
+    const double* x = X + (size_t)b * nv;
+    double acc = 0.0;
+    for (int j = 0; j < nv; ++j) acc = fma(x[j], proj[(size_t)k * nv + j], acc);
+    pv[gid] = acc;
+}
+
+// x_out[b] = solved[b] ? X[b] : Xf[b]  (what the reference returns as x_opt / x_fail)
+__global__ void net_select_kernel(int B, int nv, const double* __restrict__ X, const double* __restrict__ Xf,
+                                  const uint8_t* __restrict__ solved, double* __restrict__ x_out) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)B * nv) return;
+    x_out[gid] = solved[gid / nv] ? X[gid] : Xf[gid];
+}
+
 // One (instance, piece) pair: rows of the piece are row-major over nv.
 struct MemberPair {
     const double* A;

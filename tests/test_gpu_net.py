@@ -67,3 +67,21 @@ def test_solve_dispatches_multilevel_batches_to_the_native_path(engine):
     assert all(same_result(a, b) for a, b in zip(outs, ref))
     one = qpn_b200.solve(net, X[0])
     assert one["solved"] and set(one["Sol"]) == {1, 2, 3, 4, 5} and same_result(one, ref[0])
+
+
+def test_device_pointer_entry_equals_host_entry(engine):
+    """qpn_net_solve_batched_dev (inits / x_out in device memory) == qpn_net_solve_batched, x_fail rows included."""
+    import torch
+    net = qpn_b200.setup("robust_avoid_simple", seed=1)          # seed 1: many instances end in the cycling exit
+    X = ra_inits(net, 200, seed=4)
+    nb = cuda_net(net, engine, threads=2)
+    host = nb.solve_arrays(X)
+    xin = torch.from_numpy(X).cuda()
+    xout = torch.empty_like(xin)
+    flags = nb.solve_dev(len(X), xin.data_ptr(), xout.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(xout.cpu().numpy(), host["x"]) and np.array_equal(flags["solved"].astype(bool), host["solved"])
+    assert np.array_equal(flags["level_iters"], host["level_iters"]) and np.array_equal(flags["error"], host["error"])
+    assert (~host["solved"]).any() and host["solved"].any()
+    prof = nb.profile()
+    assert prof["verify"]["launches"] > 0 and prof["solve_qep"]["launches"] > 0 and prof["h2d_bytes"] > 0
