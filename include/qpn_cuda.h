@@ -228,6 +228,16 @@ int qpn_set_option(qpn_handle *h, const char *name, int64_t value);
  * 1 if the level runs on the global-memory tableau path, 0}. */
 int qpn_level_info(qpn_handle *h, qpn_level_dev *lvd, int32_t *out);
 
+/* Page-lock a host buffer the caller owns (a Julia `Matrix{Float64}` is pageable: `GC.@preserve` keeps it alive but does
+ * not pin it) so that the host-pointer entry points reach it without staging: cudaHostRegister with the portable and
+ * mapped flags.  Unregister before the buffer is freed.  Registration costs ~ 0.1 ms per MB: do it once per buffer that
+ * is reused, not per call. */
+int qpn_host_register(qpn_handle *h, void *ptr, size_t bytes);
+int qpn_host_unregister(qpn_handle *h, void *ptr);
+/* sizeof of every struct that crosses this ABI, so that a binding (ctypes, Julia) can check its own mirror at load
+ * time: out[0..5] = {qpn_matrix, qpn_gavi, qpn_node, qpn_level, qpn_net_desc, 0}. */
+int qpn_abi_struct_sizes(int32_t *out);
+
 /* Device buffers owned by the handle (for callers without their own allocator). */
 int qpn_malloc(qpn_handle *h, size_t bytes, void **dptr);
 int qpn_free(qpn_handle *h, void *dptr);
@@ -276,7 +286,8 @@ int qpn_net_set_option(qpn_net *net, const char *name, int64_t value);
  * reference's x_fail otherwise (algorithm.jl:116,125).  level_iters_out (may be NULL): nlevels x batch loop passes of
  * solve_base! per level; error_out (may be NULL): batch, 0 = none, 1 cycling detected, 2 AVI solve error,
  * 3 disagreement between verify and solve_qep, 4 max_iters, 5 empty solution graph, 6 comp_indices assertion,
- * 7 too many solutions to combine, 8 solution graphs not populated, 9 cycle check without projections.
+ * 7 too many solutions to combine, 8 solution graphs not populated, 9 cycle check without projections (low byte;
+ * for 2 the next byte holds the StatusCode solve_qep returned and the third byte the 0-based level).
  */
 int qpn_net_solve_batched(qpn_net *net, int batch, const double *inits, double *x_out, uint8_t *solved_out,
                           int32_t *level_iters_out, int32_t *error_out);
@@ -301,5 +312,11 @@ int qpn_net_stats(qpn_net *net, int64_t *out);
 
 #ifdef __cplusplus
 }
+/* layout of the structs above on the LP64 targets this library is built for (checked again by the bindings at load time) */
+static_assert(sizeof(qpn_matrix) == 48, "qpn_matrix layout");
+static_assert(sizeof(qpn_gavi) == 88, "qpn_gavi layout");
+static_assert(sizeof(qpn_node) == 64, "qpn_node layout");
+static_assert(sizeof(qpn_level) == 144, "qpn_level layout");
+static_assert(sizeof(qpn_net_desc) == 160, "qpn_net_desc layout");
 #endif
 #endif /* QPN_CUDA_H */

@@ -711,7 +711,8 @@ struct Machine {
     }
 
     void after_qep(Cohort& C, int status, bool moved) {
-        if (status != 1) return fail(C, ERR_AVI);
+        // the level and the solver's StatusCode ride in the upper bytes of the error word (triage of unsolved instances)
+        if (status != 1) return fail(C, ERR_AVI | ((status & 0xff) << 8) | ((C.stack.back().level & 0xff) << 16));
         if (!moved) return fail(C, ERR_DISAGREE);
         start_iter(C);
     }

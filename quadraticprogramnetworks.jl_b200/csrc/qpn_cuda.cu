@@ -172,6 +172,25 @@ extern "C" int qpn_memcpy_d2h(qpn_handle* h, void* dst, const void* src, size_t 
     return 0;
 }
 
+extern "C" int qpn_host_register(qpn_handle* h, void* ptr, size_t bytes) {
+    if (!h || !ptr) return -1;
+    CK(cudaSetDevice(h->device));
+    CK(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+    return 0;
+}
+extern "C" int qpn_host_unregister(qpn_handle* h, void* ptr) {
+    if (!h || !ptr) return -1;
+    CK(cudaSetDevice(h->device));
+    CK(cudaHostUnregister(ptr));
+    return 0;
+}
+extern "C" int qpn_abi_struct_sizes(int32_t* out) {
+    if (!out) return -1;
+    out[0] = (int32_t)sizeof(qpn_matrix); out[1] = (int32_t)sizeof(qpn_gavi); out[2] = (int32_t)sizeof(qpn_node);
+    out[3] = (int32_t)sizeof(qpn_level); out[4] = (int32_t)sizeof(qpn_net_desc); out[5] = 0;
+    return 0;
+}
+
 // ---- scratch arena -------------------------------------------------------------------------
 // Host-pointer entry points stage their operands here.  reset -> reserve (grow once) -> take.
 struct Arena {

@@ -70,6 +70,13 @@ def load_library():
     lib.qpn_big_launch_count.argtypes = [C.c_void_p]
     for name in EXPORTS:
         getattr(lib, name)   # every declared symbol must resolve
+    # the ctypes mirrors of the ABI structs must have the library's layout
+    sizes = (C.c_int32 * 6)()
+    lib.qpn_abi_struct_sizes(sizes)
+    from .netsolve import QpnNetDesc
+    mine = [C.sizeof(QpnMatrix), C.sizeof(QpnGavi), C.sizeof(QpnNode), C.sizeof(QpnLevel), C.sizeof(QpnNetDesc)]
+    if list(sizes)[:5] != mine:
+        raise EngineError(f"ABI struct sizes differ: library {list(sizes)[:5]}, ctypes mirrors {mine}")
     _lib = lib
     return lib
 
@@ -84,7 +91,7 @@ EXPORTS = [
     "qpn_level_upload", "qpn_level_release", "qpn_level_equilibrium_resident", "qpn_level_equilibrium_resident_dev",
     "qpn_malloc", "qpn_free", "qpn_memcpy_h2d", "qpn_memcpy_d2h", "qpn_set_option", "qpn_big_launch_count", "qpn_level_info",
     "qpn_net_create", "qpn_net_destroy", "qpn_net_last_error", "qpn_net_set_option", "qpn_net_solve_batched",
-    "qpn_net_solve_batched_dev", "qpn_net_profile",
+    "qpn_net_solve_batched_dev", "qpn_net_profile", "qpn_host_register", "qpn_host_unregister", "qpn_abi_struct_sizes",
     "qpn_net_sol_count", "qpn_net_sol_piece", "qpn_net_piece_rows", "qpn_net_piece_get", "qpn_net_stats",
 ]
 
@@ -184,6 +191,15 @@ class Engine:
 
     def synchronize(self):
         self._ck(self.lib.qpn_synchronize(self.h))
+
+    def host_register(self, a):
+        """Page-lock a numpy array the caller owns (qpn_host_register): the host-pointer entry points then read / write
+        it in place.  Returns the array; call host_unregister before it is freed."""
+        self._ck(self.lib.qpn_host_register(self.h, C.c_void_p(a.ctypes.data), C.c_size_t(a.nbytes)))
+        return a
+
+    def host_unregister(self, a):
+        self._ck(self.lib.qpn_host_unregister(self.h, C.c_void_p(a.ctypes.data)))
 
     def set_option(self, name, value):
         """qpn_set_option: "force_big" (global-memory tableau path for every solve), "big_ctas_per_sm",

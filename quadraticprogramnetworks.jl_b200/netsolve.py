@@ -196,6 +196,6 @@ class NetBinding:
                     r["Sol"] = self.sol(b)
                 outs.append(r)
             else:
-                outs.append(dict(solved=False, x_fail=ret["x"][b].copy(), x_opt=None, error=ERRORS.get(int(ret["error"][b]), "?"),
+                outs.append(dict(solved=False, x_fail=ret["x"][b].copy(), x_opt=None, error=ERRORS.get(int(ret["error"][b]) & 0xff, "?"), error_code=int(ret["error"][b]),
                                  level_iters=ret["level_iters"][b].tolist()))
         return outs

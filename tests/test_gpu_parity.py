@@ -455,3 +455,50 @@ def test_full_size_batches_by_properties(engine):
     ro = L.solve(Xr[idx], threads=4)
     assert np.array_equal(ro["x"], r1["x"][idx]) and np.array_equal(ro["pivots"], r1["pivots"][idx])
     rs.close()
+
+
+def test_verify_solution_fallback_accepted_on_device(engine):
+    """qp_processing.jl:129-146: the least-squares multipliers have a negative entry, the sign-constrained fallback
+    finds valid ones (how == 3) -- on the device, bit-equal to the oracle, for the row orders that reach the branch."""
+    import itertools
+    Qd, qd = np.zeros((2, 2)), np.array([1.0, 1.0])
+    A = np.array([[1.0, 0.0], [0.0, 1.0], [1.0, -1.0]])             # x >= 0, y >= 0, x - y >= 0, all active at 0
+    l, u = np.zeros(3), np.full(3, np.inf)
+    dec = np.array([0, 1], np.int32)
+    seen = set()
+    for perm in itertools.permutations(range(3)):
+        view = (Qd, qd, A[list(perm)], l, u, dec)
+        sol, lam, how, act = engine.verify_solution(view, np.zeros((3, 2)))
+        so, lo, ho, ao = cport.verify_solution(*view, np.zeros(2))
+        assert sol.all() and (how == ho).all() and np.array_equal(lam[0], lo) and np.array_equal(act[0], ao)
+        assert np.allclose(A[list(perm)].T @ lam[0], qd, atol=1e-8) and (lam[0] > -1e-4).all()
+        seen.add(int(ho))
+    assert seen == {2, 3}, seen
+    # the fallback's rejection (how == 4): the gradient is outside the cone of the active normals
+    view = (Qd, np.array([-1.0, 0.5]), A, l, u, dec)
+    sol, lam, how, act = engine.verify_solution(view, np.zeros((1, 2)))
+    so, lo, ho, ao = cport.verify_solution(*view, np.zeros(2))
+    assert (not sol[0]) and how[0] == ho == 4 and np.array_equal(lam[0], lo)
+
+
+def test_verify_solution_square_singular_active_matrix(engine):
+    """Known deviation: when the active matrix Abar is SQUARE and singular the reference's `Abar \\ qt`
+    is a sparse LU that throws and falls through to the PATH branch (qp_processing.jl:114-115,129-146); here the
+    rank-revealing QR returns a basic solution directly.  The `solution` flag agrees (a valid multiplier exists either
+    way); lam / how may differ.  Pinned here: device == oracle, and the multiplier returned is a valid one."""
+    Qd, qd = np.zeros((2, 3)), np.array([2.0, 2.0])
+    A = np.array([[1.0, 1.0, 0.0], [1.0, 1.0, 0.0]])               # x + y >= 0 (own constraint) and x + y <= 0 (a child's piece)
+    l, u = np.array([0.0, -np.inf]), np.array([np.inf, 0.0])
+    dec = np.array([0, 1], np.int32)
+    view = (Qd, qd, A, l, u, dec)
+    x = np.zeros((2, 3))
+    sol, lam, how, act = engine.verify_solution(view, x)
+    so, lo, ho, ao = cport.verify_solution(*view, x[0])
+    assert sol.all() and so and how[0] == ho and np.array_equal(lam[0], lo) and np.array_equal(act[0], ao)
+    assert list(act[0]) == [1, 2]                                    # pos_inds / neg_inds: Abar = [a, -a] is 2 x 2 and singular
+    assert np.allclose(A[:, :2].T @ lam[0], qd, atol=1e-8) and lam[0][0] > -1e-4 and lam[0][1] < 1e-4
+    # and a gradient outside the range of Abar is not a solution on either path
+    view = (Qd, np.array([2.0, -2.0]), A, l, u, dec)
+    sol, lam, how, act = engine.verify_solution(view, x)
+    so, lo, ho, ao = cport.verify_solution(*view, x[0])
+    assert (not sol.any()) and (not so) and how[0] == ho

@@ -282,3 +282,60 @@ def test_frozen_rows_change_no_decision_and_only_last_bits():
                 r1, r2 = np.abs((M @ z1 + q)[free]).max(), np.abs((M @ z2 + q)[free]).max()
                 assert r1 <= 10 * r2 + 1e-10
     assert frozen_seen > 100
+
+
+def test_degenerate_lps_do_not_cycle():
+    """Tie rule of the ratio test (t first, then largest |d|, then lowest row): highly degenerate LPs -- cones through
+    the origin cut by a box, small integer data, so most ratio tests tie -- must all end in SUCCESS well inside the
+    pivot cap, at HiGHS's optimal value.  (north_star names lexicographic tie-breaking; the rule here is deterministic
+    but carries no anti-cycling proof, so this is the evidence: 300 degenerate instances, none runs into the cap.)"""
+    from scipy.optimize import linprog
+    rng = np.random.default_rng(77)
+    worst = 0.0
+    for trial in range(300):
+        n = int(rng.integers(2, 6)); m = int(rng.integers(n + 1, 3 * n + 2))
+        A = rng.integers(-1, 2, (m, n)).astype(float)
+        A = A[np.abs(A).sum(1) > 0]
+        m = len(A)
+        c = rng.integers(-2, 3, n).astype(float)
+        # A x >= 0 (every row through the origin) and -1 <= x <= 1: the origin is a vertex where all m rows are active
+        AA = np.vstack([A, np.eye(n)]); l = np.concatenate([np.zeros(m), -np.ones(n)]); u = np.concatenate([np.full(m, INF), np.ones(n)])
+        g = problems.qp_gavi(np.zeros((n, n)), c, AA, l, u)
+        ret = cport.gavi_solve(g, np.zeros(n + len(l)), np.zeros(0))
+        ref = linprog(c, A_ub=-A, b_ub=np.zeros(m), bounds=[(-1, 1)] * n, method="highs")
+        assert ref.status == 0
+        npiv_cap = 50 * (n + 2 * len(l)) + 100
+        assert ret["status"] == 1 and ret["pivots"] < npiv_cap, (trial, ret["status"], ret["pivots"])
+        worst = max(worst, ret["pivots"] / npiv_cap)
+        assert abs(float(c @ ret["z"][:n]) - ref.fun) < 1e-7, (trial, float(c @ ret["z"][:n]), ref.fun)
+    assert worst < 0.2
+
+
+def test_julia_goldens_are_consumed_when_present():
+    """tests/golden/julia/ is where output of julia/ref_julia.jl goes (true reference goldens: PATH's own solves).
+    None exist in this image -- the test then only checks the schema file; any that are dropped in later are
+    checked against the schema and solved on the oracle stand-in with the tolerances of
+    scripts/compare_with_julia_goldens.py."""
+    import json
+    schema = json.load(open(os.path.join(GOLDEN, "julia_goldens.schema.json")))
+    assert set(schema["required"]) == {"example", "threads", "seconds", "equilibria_per_s", "inits", "solved", "x"}
+    jdir = os.path.join(GOLDEN, "julia")
+    files = [f for f in os.listdir(jdir) if f.endswith("_goldens.json")] if os.path.isdir(jdir) else []
+    for f in files:
+        G = json.load(open(os.path.join(jdir, f)))
+        assert set(schema["required"]) <= set(G), f
+        assert len(G["inits"]) == len(G["solved"]) == len(G["x"]) and all(len(a) == len(b) for a, b in zip(G["inits"], G["x"])), f
+        model = os.path.join(jdir, f.replace("_goldens.json", "_model.json"))
+        assert os.path.exists(model), f"{f}: the model exported by julia/QPNCuda.jl: export_qpnet must sit next to the goldens"
+        import qpn_b200
+        from tests.native_oracle import oracle_net
+        net = qpn_b200.load_net(model)
+        X = np.array(G["inits"], dtype=float)
+        if net.num_levels() == 1 and not net.options.gen_solution_map:
+            continue                                                # flat games: compared on the device (scripts/compare_with_julia_goldens.py)
+        ret = oracle_net(net, threads=2).solve_arrays(X)
+        ref_solved = np.array(G["solved"], bool)
+        both = ret["solved"] & ref_solved
+        assert np.mean(ret["solved"] == ref_solved) > 0.9, f
+        if G["example"] == "simple_bilevel":
+            assert np.abs(ret["x"][both] - np.array(G["x"], dtype=float)[both]).max(initial=0.0) < 1e-4, f
