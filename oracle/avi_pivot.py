@@ -199,6 +199,8 @@ class _Tab:
     def try_exchange(self, var):
         """Bring nonbasic var in through an artificial row (no movement)."""
         c = self.col_of(var)
+        if c < 0:                                   # the variable is basic: nothing to bring in
+            return False
         rho = self.best_artificial_row(c)
         if rho < 0:
             return False

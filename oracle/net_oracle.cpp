@@ -8,6 +8,7 @@
 #include <cstring>
 
 #include "../quadraticprogramnetworks.jl_b200/csrc/net/netdesc.hpp"
+#include "../quadraticprogramnetworks.jl_b200/csrc/net/vertex_enum.h"
 
 extern "C" {
 int qpo_gavi_solve(int d1, int d2, int np, const double* M, const double* N, const double* o, const double* l1, const double* u1,
@@ -63,6 +64,15 @@ struct OracleWorker : Worker {
             i8.emplace_back((size_t)b.n * dz, 0);
             uint8_t* sol = u8.back().data();
             int8_t* mask = i8.back().data();
+            const int want = b.want_vertices > QPN_VE_MAXV ? QPN_VE_MAXV : b.want_vertices;
+            const int vb = (n.m + 1) / 2, vstride = want * vb;
+            uint8_t *vcount = nullptr, *vmask = nullptr;
+            if (want > 0) {
+                u8.emplace_back(b.n, 0); vcount = u8.back().data();
+                u8.emplace_back((size_t)b.n * vstride + 1, 0); vmask = u8.back().data();
+            }
+            std::vector<double> ax(n.m + 1), qt(n.nd + 1), V((size_t)QPN_VE_MAXV * QPN_VE_MAXA), zv(dz + 1);
+            std::vector<int8_t> mv(dz + 1);
             for (int k = 0; k < b.n; ++k) {
                 const double* x = X.data() + (size_t)b.slots[k] * nv;
                 int32_t how = 0, fp = 0;
@@ -74,10 +84,37 @@ struct OracleWorker : Worker {
                     for (size_t c = 0; c < n.par.size(); ++c) w[c] = x[n.par[c]];
                     qpo_comp_indices(g.d1, g.d2, g.np, g.M.data(), g.N.data(), g.o.data(), g.l1.data(), g.u1.data(), g.A.data(),
                                      g.B.data(), g.l2.data(), g.u2.data(), z.data(), w.data(), 1e-2, mask + (size_t)k * dz);
+                    if (want > 0) {
+                        // expand's get_verts (avi_solutions.jl:252-255): vertices of the multiplier polytope at x, then comp_indices there
+                        for (int e = 0; e < n.nd; ++e) {
+                            double acc = 0.0;
+                            for (int j = 0; j < nv; ++j) acc = std::fma(n.Qd[(size_t)j * n.nd + e], x[j], acc);
+                            qt[e] = acc + n.qd[e];
+                        }
+                        for (int i = 0; i < n.m; ++i) {
+                            double acc = 0.0;
+                            for (int j = 0; j < nv; ++j) acc = std::fma(n.A[(size_t)j * n.m + i], x[j], acc);
+                            ax[i] = acc;
+                        }
+                        int idxA[QPN_VE_MAXA], na = 0;
+                        const int nvx = qpn_multiplier_vertices(n.nd, n.m, nv, n.A.data(), n.dec.data(), n.l.data(), n.u.data(), ax.data(),
+                                                                qt.data(), lam.data(), want, idxA, &na, V.data());
+                        vcount[k] = (uint8_t)nvx;
+                        for (int q = 0; q < nvx; ++q) {
+                            for (int e = 0; e < n.nd; ++e) zv[e] = z[e];
+                            for (int i = 0; i < n.m; ++i) zv[n.nd + i] = 0.0;
+                            for (int j = 0; j < na; ++j) zv[n.nd + idxA[j]] = V[(size_t)q * QPN_VE_MAXA + j];
+                            qpo_comp_indices(g.d1, g.d2, g.np, g.M.data(), g.N.data(), g.o.data(), g.l1.data(), g.u1.data(), g.A.data(),
+                                             g.B.data(), g.l2.data(), g.u2.data(), zv.data(), w.data(), 1e-2, mv.data());
+                            uint8_t* nib = vmask + (size_t)k * vstride + (size_t)q * vb;
+                            for (int i = 0; i < n.m; ++i) nib[i >> 1] |= (uint8_t)((mv[n.nd + i] & 0xf) << ((i & 1) * 4));
+                        }
+                    }
                 }
                 if (snap) std::memcpy(Xf.data() + (size_t)b.slots[k] * nv, x, sizeof(double) * nv);
             }
             b.sol = sol; b.mask = mask; b.dz = dz;
+            b.vcount = vcount; b.vmask = vmask; b.vstride = vstride; b.vbytes = vb;
         }
     }
     void run_qep(int, const LevelGaviInfo& L, QepBatch** bs, int nb, bool snap) override {

@@ -210,6 +210,7 @@ static void leave_at(tab_t *t, int rho, int which) {
 
 static int try_exchange(tab_t *t, int var) {
     int c = t->colof[var];
+    if (c < 0) return 0;                       /* the variable is basic: nothing to bring in */
     int rho = best_artificial_row(t, c);
     if (rho < 0) return 0;
     pivot(t, rho, c);

@@ -409,14 +409,27 @@ static bool all_Ks(const std::vector<int8_t>& mask, std::vector<std::string>& ou
     }
 }
 
-int GeoCache::collect(int node, const std::vector<int8_t>& mask, Worker* w, bool* bad_mask) {
+int GeoCache::collect(int node, const std::vector<int8_t>& mask, const std::vector<int8_t>& extra, Worker* w, bool* bad_mask) {
     std::string key((const char*)&node, 4);
     key.append((const char*)mask.data(), mask.size());
+    key.append((const char*)extra.data(), extra.size());
     *bad_mask = false;
     const int r = memo(collect_, key, [&]() -> int {
         stats.collect_miss++;
+        // collect(LocalGAVISolutions), avi_solutions.jl:277-321: the recipes of the point first, then those of the
+        // explored vertices that are new, each group in sorted order
         std::vector<std::string> Ks;
         if (!all_Ks(mask, Ks)) return -2;
+        std::set<std::string> explored(Ks.begin(), Ks.end());
+        std::set<std::string> fresh;
+        const size_t dz = mask.size();
+        for (size_t o = 0; dz > 0 && o + dz <= extra.size(); o += dz) {
+            std::vector<int8_t> vm(extra.begin() + o, extra.begin() + o + dz);
+            std::vector<std::string> Kv;
+            if (!all_Ks(vm, Kv)) return -2;
+            for (auto& K : Kv) if (!explored.count(K)) fresh.insert(K);
+        }
+        Ks.insert(Ks.end(), fresh.begin(), fresh.end());
         std::vector<int> out;
         std::set<int> seen_sets;
         for (const std::string& K : Ks) {
@@ -483,6 +496,7 @@ struct Frame {                                   // one activation of solve_base
     std::vector<int> req_nodes;
     std::vector<uint8_t> sol;                    // answers (uniform over the cohort)
     std::vector<std::vector<int8_t>> masks;
+    std::vector<std::vector<int8_t>> vmasks;     // per request: masks at the explored vertices, concatenated
     struct Comb { int pid; std::vector<int> union_lists, red, flat; };
     std::vector<Comb> combs;                     // combine(): players whose leaves wait for membership bits
     std::vector<int> S_out;
@@ -603,6 +617,9 @@ struct Machine {
         C.vb.assign(f.req_nodes.size(), VerifyBatch());
         for (size_t r = 0; r < f.req_nodes.size(); ++r) {
             C.vb[r].node = f.req_nodes[r]; C.vb[r].n = (int)C.members.size(); C.vb[r].slots = C.members.data();
+            // solution graphs are built for every level but the first (qp_processing.jl:158); that is where vertices matter
+            const bool gen = f.level != 0 || net.gen_solution_map;
+            C.vb[r].want_vertices = (gen && net.exploration_vertices > 1) ? net.exploration_vertices - 1 : 0;
         }
         C.wait = W_VERIFY;
     }
@@ -623,7 +640,7 @@ struct Machine {
                 const std::vector<int>& ch = net.children[pid];
                 if (ch.empty()) {
                     bool bad = false;
-                    const int lid = c.collect(f.req_nodes[pv.first_req], f.masks[pv.first_req], w, &bad);
+                    const int lid = c.collect(f.req_nodes[pv.first_req], f.masks[pv.first_req], f.vmasks[pv.first_req], w, &bad);
                     if (bad) return fail(C, ERR_MASK);
                     if (c.list(lid).empty()) return fail(C, ERR_GRAPH_EMPTY);
                     f.S_out[pid] = lid;
@@ -632,7 +649,7 @@ struct Machine {
                 std::vector<int> sols;
                 for (size_t k = 0; k < pv.combos.size(); ++k) {
                     bool bad = false;
-                    const int lid = c.collect(f.req_nodes[pv.first_req + k], f.masks[pv.first_req + k], w, &bad);
+                    const int lid = c.collect(f.req_nodes[pv.first_req + k], f.masks[pv.first_req + k], f.vmasks[pv.first_req + k], w, &bad);
                     if (bad) return fail(C, ERR_MASK);
                     sols.push_back(c.remove_subsets(lid, w));
                 }
@@ -772,16 +789,34 @@ struct Machine {
               [&](int k, std::string& key) {
                   for (const VerifyBatch& b : vb) {
                       key.push_back((char)b.sol[k]);
-                      if (b.sol[k]) key.append((const char*)b.mask + (size_t)k * b.dz, (size_t)b.dz);
+                      if (b.sol[k]) {
+                          key.append((const char*)b.mask + (size_t)k * b.dz, (size_t)b.dz);
+                          if (b.vcount) {
+                              key.push_back((char)b.vcount[k]);
+                              key.append((const char*)b.vmask + (size_t)k * b.vstride, (size_t)b.vcount[k] * b.vbytes);
+                          }
+                      }
                   }
               },
               [&](Cohort& P, int rep) {
                   Frame& f = P.stack.back();
                   f.sol.assign(vb.size(), 0);
                   f.masks.assign(vb.size(), {});
+                  f.vmasks.assign(vb.size(), {});
                   for (size_t r = 0; r < vb.size(); ++r) {
                       f.sol[r] = vb[r].sol[rep];
-                      if (f.sol[r]) f.masks[r].assign(vb[r].mask + (size_t)rep * vb[r].dz, vb[r].mask + (size_t)(rep + 1) * vb[r].dz);
+                      if (!f.sol[r]) continue;
+                      f.masks[r].assign(vb[r].mask + (size_t)rep * vb[r].dz, vb[r].mask + (size_t)(rep + 1) * vb[r].dz);
+                      if (!vb[r].vcount) continue;
+                      // a vertex keeps the primal part of the point: only the masks of the m multiplier rows change
+                      const int dz = vb[r].dz, m2 = vb[r].vbytes, nvx = vb[r].vcount[rep];
+                      const int mrows = c.node_info(vb[r].node).m, nd = dz - mrows;
+                      for (int q = 0; q < nvx; ++q) {
+                          const uint8_t* nib = vb[r].vmask + (size_t)rep * vb[r].vstride + (size_t)q * m2;
+                          std::vector<int8_t> vm = f.masks[r];
+                          for (int i = 0; i < mrows; ++i) vm[nd + i] = (int8_t)((nib[i >> 1] >> ((i & 1) * 4)) & 0xf);
+                          f.vmasks[r].insert(f.vmasks[r].end(), vm.begin(), vm.end());
+                      }
                   }
                   P.vb.clear();
                   P.wait = W_NONE;

@@ -80,6 +80,13 @@ struct VerifyBatch {        // verify_solution at each instance's x, then comp_i
     const uint8_t* sol = nullptr;                // n flags
     const int8_t* mask = nullptr;                // n x dz masks (rows of non-solutions are undefined)
     int dz = 0;
+    // vertex exploration (exploration_vertices > 0; expand's get_verts, avi_solutions.jl:252-255): per slot the number
+    // of new vertices of its multiplier polytope and, per vertex, the comp_indices masks of the m multiplier rows at
+    // that vertex, two rows per byte (low nibble first)
+    int want_vertices = 0;                       // in: explore up to this many new vertices (0 = none)
+    const uint8_t* vcount = nullptr;             // n
+    const uint8_t* vmask = nullptr;              // n x vstride
+    int vstride = 0, vbytes = 0;                 // bytes per slot / per vertex (= ceil(m / 2))
 };
 struct QepBatch {           // solve_qep for a level GAVI; on success (and a move of >= 1e-4) x[dec] is replaced
     int gavi = 0, n = 0;
@@ -166,7 +173,8 @@ class GeoCache {
     // the lifted local piece of (node, K) over (z, w) (avi_solutions.jl:400-496)
     int local_piece_id(int node, const std::string& K, Worker* w);
     // collect(LocalGAVISolutions) without vertex exploration: (node, mask) -> list of piece ids
-    int collect(int node, const std::vector<int8_t>& mask, Worker* w, bool* bad_mask);
+    // `extra`: the masks at the explored vertices, concatenated (each nd + m entries)
+    int collect(int node, const std::vector<int8_t>& mask, const std::vector<int8_t>& extra, Worker* w, bool* bad_mask);
     // all non-empty leaves of the intersection tree for one membership pattern (intersection.jl:55-151)
     int leaves(const std::vector<int>& union_lists, const std::vector<int>& red_lengths, const std::vector<uint8_t>& in_bits,
                Worker* w);

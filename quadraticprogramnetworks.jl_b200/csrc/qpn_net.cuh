@@ -10,6 +10,7 @@
 // orders), so results are bit-equal to the C oracle's.
 #pragma once
 #include "qpn_level.cuh"
+#include "net/vertex_enum.h"
 
 namespace qpn {
 
@@ -18,7 +19,8 @@ namespace qpn {
 __global__ void net_verify_kernel(const __grid_constant__ NodeDesc node, const __grid_constant__ GaviDesc g,
                                   const int32_t* __restrict__ par, int n, const int32_t* __restrict__ inst,
                                   const double* __restrict__ X, double* __restrict__ Xf, double tol,
-                                  uint8_t* __restrict__ solution_out, int8_t* __restrict__ mask_out) {
+                                  uint8_t* __restrict__ solution_out, int8_t* __restrict__ mask_out, int want_v,
+                                  uint8_t* __restrict__ vcount_out, uint8_t* __restrict__ vmask_out) {
     const int b = blockIdx.x, i = threadIdx.x, m = node.m, nd = node.nd;
     const int slot = inst[b];
     const int tn = m > 0 ? m : 1;
@@ -66,6 +68,42 @@ __global__ void net_verify_kernel(const __grid_constant__ NodeDesc node, const _
         }
     }
     if (i == 0) solution_out[b] = (uint8_t)sol;
+    if (want_v > 0) {
+        // expand's get_verts (avi_solutions.jl:252-255): the vertices of the node's multiplier polytope at x, enumerated by
+        // one thread (net/vertex_enum.h), then comp_indices at every vertex by all of them -- only the masks of the m
+        // multiplier rows can differ from the point's own, two rows per output byte
+        double* Vs = ax + m;                              // QPN_VE_MAXV x QPN_VE_MAXA doubles behind the kernel's vectors
+        int* hdr = reinterpret_cast<int*>(Vs + QPN_VE_MAXV * QPN_VE_MAXA);     // [0] vertices, [1] active rows, [2..] their indices
+        if (i == 0) {
+            int nvx = 0, a = 0;
+            if (sol) nvx = qpn_multiplier_vertices(nd, m, node.nv, node.A, node.dec, node.l, node.u, ax, qt, vs.lam_out(), want_v, hdr + 2, &a, Vs);
+            hdr[0] = nvx; hdr[1] = a;
+            vcount_out[b] = (uint8_t)nvx;
+        }
+        QPN_SYNC();
+        const int nvx = hdr[0], a = hdr[1], vbytes = (m + 1) >> 1;
+        double* lv = vs.zs();
+        for (int q = 0; q < nvx; ++q) {
+            for (int r = i; r < m; r += blockDim.x) lv[r] = 0.0;
+            QPN_SYNC();
+            for (int j = i; j < a; j += blockDim.x) lv[hdr[2 + j]] = Vs[q * QPN_VE_MAXA + j];
+            QPN_SYNC();
+            for (int t = i; t < vbytes; t += blockDim.x) {
+                int packed = 0;
+                for (int h = 0; h < 2; ++h) {
+                    const int k = 2 * t + h;
+                    if (k >= m) break;
+                    double acc = 0.0, acc2 = 0.0;
+                    for (int j = 0; j < nd; ++j) acc = fma(g.A[(size_t)j * g.d2 + k], xs[node.dec[j]], acc);
+                    for (int j = 0; j < m; ++j) acc = fma(g.A[(size_t)(nd + j) * g.d2 + k], lv[j], acc);
+                    for (int j = 0; j < g.np; ++j) acc2 = fma(g.B[(size_t)j * g.d2 + k], xs[par[j]], acc2);
+                    packed |= (comp_mask(g.l2[k], g.u2[k], lv[k], acc + acc2, 1e-2) & 0xf) << (4 * h);
+                }
+                vmask_out[(size_t)b * want_v * vbytes + (size_t)q * vbytes + t] = (uint8_t)packed;
+            }
+            QPN_SYNC();
+        }
+    }
 }
 
 // grid = n requests, block = roundup32(lifted n).  Dynamic smem: gavi_solve_kernel's layout + x(nv) + xn(nv) + pv(nproj).

@@ -78,34 +78,73 @@ def project_and_permute(piece, dec, par, n_vars, lp):
     return ph.simplify(Poly(A, proj.l, proj.u))
 
 
-def vertices_of_slice(piece, z, w, nv, lp, max_dim=6):
-    """The get_verts call of `expand` (avi_solutions.jl:252-255): vertices of the multiplier polytope
-    at the current primal point.  Only needed when exploration_vertices > 0; enumerated as the
-    basic solutions of the sliced system (small dimensions only)."""
-    n = len(z)
-    dim = n - nv
-    if dim == 0 or dim > max_dim:                 # decided by the sizes alone: no need to slice first
+def multiplier_vertices(g, z, w, max_new, max_active=12, max_nd=8):
+    """The get_verts call of `expand` (avi_solutions.jl:252-255, sets.jl:439-453): vertices of the multiplier polytope of
+    a node at the current primal point.  Slicing a local piece at the primal part of z and at w leaves a polyhedron in
+    the multipliers alone -- stationarity A_d' lam = qt, a sign per multiplier whose row is active, zero elsewhere; the
+    recipe with the fewest "inactive" choices slices to the whole polytope Lambda(x), every other one to a face of it,
+    so the vertices `collect` can queue are those of Lambda(x).  The rows fixed at zero are eliminated and the basic
+    solutions of the remaining system enumerated (bases in lexicographic order); the reference uses Polyhedra.jl's
+    double description.  Returns at most max_new vertices that differ from lam itself at 5 digits, as full z vectors."""
+    d1, m = len(g["l1"]), len(g["l2"])
+    z, w = np.asarray(z, float), np.asarray(w, float)
+    lam = z[d1:]
+    if max_new <= 0 or d1 > max_nd:                            # the caps of the native enumeration (csrc/net/vertex_enum.h)
         return []
-    fixed = {j: z[j] for j in range(nv)}
-    fixed.update({n + j: w[j] for j in range(len(w))})
-    S = ph.simplify(ph.poly_slice(piece, fixed))
-    if len(S) == 0:
+    max_new = min(max_new, 15)
+    Ad = g["A"][:, :d1]                                       # m x nd
+    ax = Ad @ z[:d1] + g["B"] @ w
+    qt = g["M"][:, :d1] @ z[:d1] + g["N"] @ w + g["o"]         # Q_dd x_d + Q_dp w + q_d
+    lo = np.abs(ax - g["l2"]) <= 1e-6
+    up = np.abs(ax - g["u2"]) <= 1e-6
+    act = np.flatnonzero(lo | up)
+    if (np.abs(np.delete(lam, act)) > 1e-6).any() or len(act) == 0 or len(act) > max_active:
+        return []                                             # the point is in no piece at the slice tolerance / nothing to enumerate
+    sgn = np.where(lo[act] & up[act], 0, np.where(lo[act], 1, -1))
+    G = Ad[act].T                                             # nd x a
+    if (np.abs(G @ lam[act] - qt) > 1e-6).any():
         return []
-    rows = []
-    for i in range(len(S)):
-        if not np.isinf(S.l[i]):
-            rows.append((S.A[i], S.l[i]))
-        if not np.isinf(S.u[i]) and S.u[i] != S.l[i]:
-            rows.append((S.A[i], S.u[i]))
-    verts = []
-    for comb in itertools.combinations(range(len(rows)), dim):
-        Am = np.array([rows[k][0] for k in comb]); bm = np.array([rows[k][1] for k in comb])
-        if abs(np.linalg.det(Am)) < 1e-9:
+    # independent equations: elimination with full pivoting (as the native code picks them)
+    W = G.copy(); rows, cols = list(range(d1)), list(range(len(act))); r = 0
+    while r < min(d1, len(act)):
+        sub = np.abs(W[np.ix_(rows[r:], cols[r:])])
+        if sub.size == 0 or sub.max() <= 1e-9:
+            break
+        e, k = np.unravel_index(int(np.argmax(sub)), sub.shape)      # first maximum in row-major order
+        rows[r], rows[r + e] = rows[r + e], rows[r]; cols[r], cols[r + k] = cols[r + k], cols[r]
+        for ee in rows[r + 1:]:
+            f = W[ee, cols[r]] / W[rows[r], cols[r]]
+            if f != 0.0:
+                W[ee, cols[r:]] -= f * W[rows[r], cols[r:]]
+        r += 1
+    a = len(act)
+    if a <= r or int((sgn == 0).sum()) > r:
+        return []
+    eqs = sorted(rows[:r])
+    free = set(np.flatnonzero(sgn == 0).tolist())
+    key = lambda v: tuple(np.rint(np.asarray(v) * 1e5))
+    seen, out = {key(lam[act])}, []
+    for comb in itertools.combinations(range(a), r):
+        if not free <= set(comb):
             continue
-        v = np.linalg.solve(Am, bm)
-        if ph.contains(S, v, tol=1e-6, closed=True) and not any(np.allclose(v, q, atol=1e-5) for q in verts):
-            verts.append(v)
-    return [np.concatenate([z[:nv], v, w]) for v in verts]
+        Mx = G[np.ix_(eqs, comb)]
+        if abs(np.linalg.det(Mx)) < 1e-12:
+            continue
+        try:
+            y = np.linalg.solve(Mx, qt[eqs])
+        except np.linalg.LinAlgError:
+            continue
+        cand = np.zeros(a); cand[list(comb)] = y
+        if ((sgn != 0) & (sgn * cand < -1e-6)).any() or (np.abs(G @ cand - qt) > 1e-6).any():
+            continue
+        if key(cand) in seen:
+            continue
+        seen.add(key(cand))
+        lv = np.zeros(m); lv[act] = cand
+        out.append(np.concatenate([z[:d1], lv]))
+        if len(out) == max_new:
+            break
+    return out
 
 
 class LocalSolutions:
@@ -134,40 +173,34 @@ class LocalSolutions:
         return all_Ks(mask)
 
     def expand(self, K):
-        """avi_solutions.jl:241-261."""
+        """avi_solutions.jl:241-261 (the vertices of the slice are those of the node's multiplier polytope whatever K is:
+        `collect` computes them once)."""
         cache = {} if self.cache is None else self.cache
         once = self.lp.once
         piece = once(cache, (self.cache_key, K, "piece"), lambda: local_piece(self.g, K))
         zw = np.concatenate([self.z, self.w])
         if len(piece) and ph.isempty(piece, self.lp, tol=1e-4, x=zw):
-            return None, []
-        verts = []
-        if self.max_vertices > 0 and (len(piece) == 0 or ph.contains(piece, zw)):
-            verts = vertices_of_slice(piece, self.z, self.w, len(self.dec), self.lp)
-        proj = once(cache, (self.cache_key, K, "proj"), lambda: project_and_permute(piece, self.dec, self.par, self.n_vars, self.lp))
-        return proj, verts
+            return None
+        return once(cache, (self.cache_key, K, "proj"), lambda: project_and_permute(piece, self.dec, self.par, self.n_vars, self.lp))
 
     def collect(self):
-        while self.unexplored_Ks:
-            for K in sorted(self.unexplored_Ks):          # deterministic order (the reference iterates a Set)
-                piece, verts = self.expand(K)
+        """avi_solutions.jl:277-321: the recipes of the point, then -- exploration_vertices permitting -- those of the
+        vertices of its multiplier polytope that are new, each group in sorted order (the reference iterates Sets)."""
+        rounds = [sorted(self.unexplored_Ks)]
+        explored = set(rounds[0])
+        if self.max_vertices > 1:
+            fresh = set()
+            for v in multiplier_vertices(self.g, self.z, self.w, self.max_vertices - 1):
+                fresh |= self._recipes(v, self.w) - explored
+            rounds.append(sorted(fresh))
+        for Ks in rounds:
+            for K in Ks:
+                piece = self.expand(K)
                 if piece is None:
                     continue
                 if piece not in self._poly_keys:
                     self._poly_keys.add(piece); self.polys.append(piece)
-                for v in verts:
-                    key = self._vkey(v)
-                    if key not in self.explored_vertices and all(key != self._vkey(q) for q in self.unexplored_vertices):
-                        self.unexplored_vertices.append(v)
-            self.explored_Ks |= self.unexplored_Ks
-            self.unexplored_Ks = set()
-            if not self.unexplored_vertices:
-                break
-            while self.unexplored_vertices and len(self.explored_vertices) < self.max_vertices:
-                v = self.unexplored_vertices.pop()
-                self.explored_vertices.append(self._vkey(v))
-                n = len(self.z)
-                self.unexplored_Ks |= self._recipes(v[:n], v[n:]) - self.explored_Ks
+        self.explored_Ks, self.unexplored_Ks = explored | set(rounds[-1]), set()
         return list(self.polys)
 
 

@@ -55,7 +55,7 @@ def test_robust_avoid_three_levels_device_equals_oracle(engine, seed, B):
     st = nb.stats()
     assert st["launches"] > 0 and st["calls"] < st["requests"] / 4
     if seed == 3:
-        assert np.mean([r["solved"] for r in dev]) > 0.95
+        assert np.mean([r["solved"] for r in dev]) > 0.9
 
 
 def test_solve_dispatches_multilevel_batches_to_the_native_path(engine):
