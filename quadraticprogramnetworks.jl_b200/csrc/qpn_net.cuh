@@ -14,14 +14,55 @@
 
 namespace qpn {
 
-// grid = n requests, block = roundup32(max(m, nd, 1)).
-// Dynamic smem: verify_solution_kernel's layout (Tab(m, m+1) + VerifySmem + x(nv) + qt(nd) + ax(m)).
-__global__ void net_verify_kernel(const __grid_constant__ NodeDesc node, const __grid_constant__ GaviDesc g,
-                                  const int32_t* __restrict__ par, int n, const int32_t* __restrict__ inst,
-                                  const double* __restrict__ X, double* __restrict__ Xf, double tol,
-                                  uint8_t* __restrict__ solution_out, int8_t* __restrict__ mask_out, int want_v,
-                                  uint8_t* __restrict__ vcount_out, uint8_t* __restrict__ vmask_out) {
-    const int b = blockIdx.x, i = threadIdx.x, m = node.m, nd = node.nd;
+// Resident tables of the store (device memory): what a request's group refers to.
+struct NodeTabEntry {
+    NodeDesc node;
+    GaviDesc g;             // the node's own GAVI (process_solution_graph, avi.jl:447-475)
+    const int32_t* par;
+    int dz, pad;
+};
+struct GaviTabEntry {
+    GaviDesc g;
+    GaviPlans plans;
+    const int32_t *dec, *par;
+    int nd_level, n;
+};
+struct PieceTabEntry {
+    const double *A, *l, *u;    // rows row-major over nv
+    int m, pad;
+};
+// One group of a launch: `count` consecutive requests (from `start`) against the same resident object.
+struct VGroup { int node, start, count, snap; unsigned mask_off, vm_off; int want, pad; };
+struct QGroup { int gavi, start, count, snap; };
+
+__device__ __forceinline__ int find_group_start(const int* starts, int ngroups, int b) {
+    int lo = 0, hi = ngroups - 1;          // last group whose start <= b
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (starts[mid] <= b) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// grid = all verify requests of a round (every node's group back to back), block = roundup32(max over the groups of
+// max(m, nd, 1)).  Dynamic smem: the largest group's verify_solution_kernel layout (Tab(m, m+1) + VerifySmem + x(nv) +
+// qt(nd) + ax(m)) plus the vertex scratch.
+__global__ void net_verify_kernel(const NodeTabEntry* __restrict__ table, const VGroup* __restrict__ groups,
+                                  const int* __restrict__ gstarts, int ngroups, const int32_t* __restrict__ inst,
+                                  const double* __restrict__ X, double* __restrict__ Xf_all, double tol,
+                                  uint8_t* __restrict__ solution_out, int8_t* __restrict__ mask_base,
+                                  uint8_t* __restrict__ vcount_out, uint8_t* __restrict__ vmask_base) {
+    const int b = blockIdx.x, i = threadIdx.x;
+    const VGroup grp = groups[find_group_start(gstarts, ngroups, b)];
+    const NodeTabEntry& ent = table[grp.node];
+    const NodeDesc node = ent.node;
+    const GaviDesc g = ent.g;
+    const int32_t* par = ent.par;
+    const int m = node.m, nd = node.nd, want_v = grp.want;
+    double* Xf = grp.snap ? Xf_all : nullptr;
+    const int kloc = b - grp.start;
+    int8_t* my_mask = mask_base + grp.mask_off + (size_t)kloc * (nd + m);
+    uint8_t* my_vmask = vmask_base + grp.vm_off + (size_t)kloc * want_v * ((m + 1) >> 1);
     const int slot = inst[b];
     const int tn = m > 0 ? m : 1;
     Tab tab;
@@ -64,7 +105,7 @@ __global__ void net_verify_kernel(const __grid_constant__ NodeDesc node, const _
                 const double s = acc + acc2;
                 mk = comp_mask(g.l2[k], g.u2[k], lam[k], s, 1e-2);
             }
-            mask_out[(size_t)b * dz + r] = mk;
+            my_mask[r] = mk;
         }
     }
     if (i == 0) solution_out[b] = (uint8_t)sol;
@@ -99,24 +140,34 @@ __global__ void net_verify_kernel(const __grid_constant__ NodeDesc node, const _
                     for (int j = 0; j < g.np; ++j) acc2 = fma(g.B[(size_t)j * g.d2 + k], xs[par[j]], acc2);
                     packed |= (comp_mask(g.l2[k], g.u2[k], lv[k], acc + acc2, 1e-2) & 0xf) << (4 * h);
                 }
-                vmask_out[(size_t)b * want_v * vbytes + (size_t)q * vbytes + t] = (uint8_t)packed;
+                my_vmask[(size_t)q * vbytes + t] = (uint8_t)packed;
             }
             QPN_SYNC();
         }
     }
 }
 
-// grid = n requests, block = roundup32(lifted n).  Dynamic smem: gavi_solve_kernel's layout + x(nv) + xn(nv) + pv(nproj).
+// grid = the solve_qep requests of a round whose level GAVIs fall into this thread bucket (groups back to back),
+// block = the bucket's largest roundup32(lifted n).  Dynamic smem: the largest group's gavi_solve_kernel layout + x(nv) +
+// xn(nv) + pv(nproj).
 template <int MAXT>
 __global__ void __launch_bounds__(MAXT, 896 / MAXT)
-net_qep_kernel(const __grid_constant__ GaviDesc g, const __grid_constant__ GaviPlans plans, const int32_t* __restrict__ dec,
-               int nd_level, const int32_t* __restrict__ par, int nv, int nproj, const double* __restrict__ proj, int n_req,
-               const int32_t* __restrict__ inst, double* __restrict__ X, double* __restrict__ Xf, int max_pivots,
-               int32_t* __restrict__ status_out, int32_t* __restrict__ pivots_out, uint8_t* __restrict__ moved_out,
-               double* __restrict__ pv_out) {
+net_qep_kernel(const GaviTabEntry* __restrict__ table, const QGroup* __restrict__ groups, const int* __restrict__ gstarts,
+               int ngroups, int nv, int nproj, const double* __restrict__ proj, const int32_t* __restrict__ inst,
+               double* __restrict__ X, double* __restrict__ Xf_all, int32_t* __restrict__ status_out,
+               int32_t* __restrict__ pivots_out, uint8_t* __restrict__ moved_out, double* __restrict__ pv_out) {
     const int b = blockIdx.x, i = threadIdx.x;
+    const QGroup grp = groups[find_group_start(gstarts, ngroups, b)];
+    const GaviTabEntry& ent = table[grp.gavi];
+    const GaviDesc g = ent.g;
+    const GaviPlans& plans = ent.plans;
+    const int32_t* dec = ent.dec;
+    const int32_t* par = ent.par;
+    const int nd_level = ent.nd_level;
+    double* Xf = grp.snap ? Xf_all : nullptr;
     const int slot = inst[b];
     const int dz = g.d1 + g.d2, n = g.d1 + 2 * g.d2;
+    const int max_pivots = 50 * n + 100;
     GaviSmem s;
     tab_carve_ex(s.t, n, (size_t)plans.t_doubles, plans.ldr_max, 0);
     const int p = gavi_carve_extra(s, g, (int)tab_smem_bytes_ex(n, (size_t)plans.t_doubles, plans.ldr_max));
@@ -176,27 +227,23 @@ __global__ void net_select_kernel(int B, int nv, const double* __restrict__ X, c
     x_out[gid] = solved[gid / nv] ? X[gid] : Xf[gid];
 }
 
-// One (instance, piece) pair: rows of the piece are row-major over nv.
-struct MemberPair {
-    const double* A;
-    const double* l;
-    const double* u;
-    int32_t inst, m;
-};
+// One (instance, piece) pair of a membership round.
+struct MemberPair { int32_t inst, piece; };
 
 // One warp per pair; lanes take rows, each dot product sequential in the coordinate index.
-__global__ void net_member_kernel(int npairs, const MemberPair* __restrict__ pairs, int nv, const double* __restrict__ X, double tol,
-                                  uint8_t* __restrict__ in_out) {
+__global__ void net_member_kernel(int npairs, const MemberPair* __restrict__ pairs, const PieceTabEntry* __restrict__ pieces, int nv,
+                                  const double* __restrict__ X, double tol, uint8_t* __restrict__ in_out) {
     const int warp = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (warp >= npairs) return;
     const MemberPair pr = pairs[warp];
+    const PieceTabEntry pc = pieces[pr.piece];
     const double* x = X + (size_t)pr.inst * nv;
     int ok = 1;
-    for (int row = lane; row < pr.m; row += 32) {
-        const double* a = pr.A + (size_t)row * nv;
+    for (int row = lane; row < pc.m; row += 32) {
+        const double* a = pc.A + (size_t)row * nv;
         double ax = 0.0;
         for (int j = 0; j < nv; ++j) ax = fma(a[j], x[j], ax);
-        if (!((pr.l[row] - tol <= ax) && (ax - tol <= pr.u[row]))) ok = 0;
+        if (!((pc.l[row] - tol <= ax) && (ax - tol <= pc.u[row]))) ok = 0;
     }
     ok = __all_sync(0xffffffffu, ok);
     if (lane == 0) in_out[warp] = (uint8_t)ok;
