@@ -56,12 +56,14 @@ def test_monotone_stress_n256_m512_one_wave(engine):
     # (rows whose leading coefficient was negative are stored flipped -- sets.jl:76-89 -- so a row may be bounded above
     # and its multiplier negative)
     ax = x @ P.A.T
-    assert np.abs(x @ qp.Q.T + qp.q - lam @ P.A).max() < 1e-8
-    assert (ax >= P.l - 1e-8).all() and (ax <= P.u + 1e-8).all()
+    # (the solve accepts its own AVI residual at 1e-6 per component -- avi.jl:148-156 -- and verify_solution re-derives lam
+    # by least squares, so 1e-5 is the scale to expect; the measured maximum on this wave is 1.1e-6)
+    assert np.abs(x @ qp.Q.T + qp.q - lam @ P.A).max() < 1e-5
+    assert (ax >= P.l - 1e-6).all() and (ax <= P.u + 1e-6).all()
     lower_only, upper_only = np.isinf(P.u) & ~np.isinf(P.l), np.isinf(P.l) & ~np.isinf(P.u)
-    assert lam[:, lower_only].min(initial=0.0) > -1e-8 and lam[:, upper_only].max(initial=0.0) < 1e-8
+    assert lam[:, lower_only].min(initial=0.0) > -1e-6 and lam[:, upper_only].max(initial=0.0) < 1e-6
     gap = np.where(lower_only, ax - P.l, np.where(upper_only, P.u - ax, 0.0))
-    assert np.abs(lam * gap).max() < 1e-8                            # complementarity
+    assert np.abs(lam * gap).max() < 1e-5                            # complementarity
     solver.close()
 
 
