@@ -424,7 +424,7 @@ def main():
         nb.solve_dev(B, dev_in[k % nsets].data_ptr(), dev_out.data_ptr(), out=flags)
     pk1 = nb.profile()
     nb.set_option("profile", 0)
-    kern = {k: {f: pk1[k][f] - pk0[k][f] for f in ("launches", "units", "ms")} for k in ("verify", "solve_qep", "member")}
+    kern = {k: {f: pk1[k][f] - pk0[k][f] for f in ("launches", "units", "ms")} for k in ("verify", "solve_qep", "member", "group", "cycle")}
 
     if world > 1:
         t = torch.tensor([t_step, t_e2e, t_page], dtype=torch.float64, device=dev)

@@ -294,10 +294,11 @@ int qpn_net_solve_batched(qpn_net *net, int batch, const double *inits, double *
 /* The same with inits / x_out in DEVICE memory of the net's GPU (the flags and counters are produced on the host). */
 int qpn_net_solve_batched_dev(qpn_net *net, int batch, const double *inits_dev, double *x_out_dev, uint8_t *solved_out,
                               int32_t *level_iters_out, int32_t *error_out);
-/* Kernel accounting since the net was created.  out[0..15]: for k in {verify, solve_qep, membership}:
- * out[4k] launches, out[4k+1] units (instances; pairs for membership), out[4k+2] summed duration in ms -- durations
- * only accumulate while option "profile" = 1 (every launch is then bracketed by CUDA events on its stream);
- * out[12] / out[13]: bytes copied host-to-device / device-to-host. */
+/* Kernel accounting since the net was created.  out[0..23]: for k in {verify, solve_qep, membership, grouping (the
+ * segmented sort of every cohort's members by their answers, the boundary scan and the gather of one representative's
+ * answers per part), cycle check}: out[4k] launches, out[4k+1] units (instances; pairs for membership), out[4k+2] summed
+ * duration in ms -- durations only accumulate while option "profile" = 1 (every launch is then bracketed by CUDA events
+ * on its stream); out[20] / out[21]: bytes copied host-to-device / device-to-host. */
 int qpn_net_profile(qpn_net *net, double *out);
 /* The solution graphs of the last batch (ret.Sol of algorithm.jl:116): number of pieces of player `player` for
  * instance b (-1: none), the id of piece k, and a piece's rows (A: m x nv row-major; rl / ru: 1 = strict). */

@@ -6,9 +6,11 @@
 // (pinned by the reference's simple_bilevel known answers; unpinned against PATH / OSQP themselves).
 #include <cmath>
 #include <cstring>
+#include <unordered_map>
 
 #include "../quadraticprogramnetworks.jl_b200/csrc/net/netdesc.hpp"
 #include "../quadraticprogramnetworks.jl_b200/csrc/net/vertex_enum.h"
+#include "../quadraticprogramnetworks.jl_b200/csrc/net/cycle_check.h"
 
 extern "C" {
 int qpo_gavi_solve(int d1, int d2, int np, const double* M, const double* N, const double* o, const double* l1, const double* u1,
@@ -29,11 +31,19 @@ using namespace qpnnet;
 
 struct OracleStore;
 
+struct PieceCM { int m = 0; std::vector<double> A, l, u; };      // column-major copy for qpo_halfspace_in
+
 struct OracleWorker : Worker {
     OracleStore* store;
     const NetData* net = nullptr;            // set at set_batch (the store learns the net after the solver is built)
-    int B = 0, nv = 0;
-    std::vector<double> X, Xf;
+    const GeoCache* cache = nullptr;
+    int B = 0, nv = 0, nproj = 0;
+    std::vector<double> X, Xf, PV;
+    std::vector<int> order, next_order;
+    std::vector<std::vector<std::vector<double>>> hist;      // [slot][level]: flat list of earlier projections
+    std::vector<int32_t> result_of;
+    std::vector<Post> posts;
+    std::deque<std::vector<uint8_t>> reps;   // representative answers of the current round
     explicit OracleWorker(OracleStore* s) : store(s) {}
 
     int gavi_solve_one(const GaviData& g, const double* w, const double* z0, double* z) override {
@@ -44,138 +54,164 @@ struct OracleWorker : Worker {
                        g.l2.data(), g.u2.data(), w ? w : &none, z0c.data(), 1, 0, z, nullptr, &st, &pv, nullptr);
         return st;
     }
-    void set_batch(int B_, const double* x_init) override;
-    // result storage of the current round (the batches point into these)
-    std::deque<std::vector<uint8_t>> u8;
-    std::deque<std::vector<int8_t>> i8;
-    std::deque<std::vector<int32_t>> i32;
-    std::deque<std::vector<double>> f64;
-    bool fresh_round = true;
-    void begin_round() { if (fresh_round) { u8.clear(); i8.clear(); i32.clear(); f64.clear(); fresh_round = false; } }
-
-    void run_verify(int, const NodeInfo& n, VerifyBatch** bs, int nb, bool snap) override {
-        begin_round();
-        std::vector<double> lam(n.m + 1), z(n.nd + n.m + 1), w(n.par.size() + 1);
-        const GaviData& g = n.g;
-        const int dz = n.nd + n.m;
-        for (int q = 0; q < nb; ++q) {
-            VerifyBatch& b = *bs[q];
-            u8.emplace_back(b.n, 0);
-            i8.emplace_back((size_t)b.n * dz, 0);
-            uint8_t* sol = u8.back().data();
-            int8_t* mask = i8.back().data();
-            const int want = b.want_vertices > QPN_VE_MAXV ? QPN_VE_MAXV : b.want_vertices;
-            const int vb = (n.m + 1) / 2, vstride = want * vb;
-            uint8_t *vcount = nullptr, *vmask = nullptr;
-            if (want > 0) {
-                u8.emplace_back(b.n, 0); vcount = u8.back().data();
-                u8.emplace_back((size_t)b.n * vstride + 1, 0); vmask = u8.back().data();
-            }
-            std::vector<double> ax(n.m + 1), qt(n.nd + 1), V((size_t)QPN_VE_MAXV * QPN_VE_MAXA), zv(dz + 1);
-            std::vector<int8_t> mv(dz + 1);
-            for (int k = 0; k < b.n; ++k) {
-                const double* x = X.data() + (size_t)b.slots[k] * nv;
-                int32_t how = 0, fp = 0;
-                sol[k] = (uint8_t)qpo_verify_solution(n.nd, n.nv, n.m, n.Qd.data(), n.qd.data(), n.A.data(), n.l.data(), n.u.data(),
-                                                      n.dec.data(), x, 1e-4, lam.data(), &how, nullptr, &fp);
-                if (sol[k]) {
-                    for (int e = 0; e < n.nd; ++e) z[e] = x[n.dec[e]];
-                    for (int i = 0; i < n.m; ++i) z[n.nd + i] = lam[i];
-                    for (size_t c = 0; c < n.par.size(); ++c) w[c] = x[n.par[c]];
-                    qpo_comp_indices(g.d1, g.d2, g.np, g.M.data(), g.N.data(), g.o.data(), g.l1.data(), g.u1.data(), g.A.data(),
-                                     g.B.data(), g.l2.data(), g.u2.data(), z.data(), w.data(), 1e-2, mask + (size_t)k * dz);
-                    if (want > 0) {
-                        // expand's get_verts (avi_solutions.jl:252-255): vertices of the multiplier polytope at x, then comp_indices there
-                        for (int e = 0; e < n.nd; ++e) {
-                            double acc = 0.0;
-                            for (int j = 0; j < nv; ++j) acc = std::fma(n.Qd[(size_t)j * n.nd + e], x[j], acc);
-                            qt[e] = acc + n.qd[e];
-                        }
-                        for (int i = 0; i < n.m; ++i) {
-                            double acc = 0.0;
-                            for (int j = 0; j < nv; ++j) acc = std::fma(n.A[(size_t)j * n.m + i], x[j], acc);
-                            ax[i] = acc;
-                        }
-                        int idxA[QPN_VE_MAXA], na = 0;
-                        const int nvx = qpn_multiplier_vertices(n.nd, n.m, nv, n.A.data(), n.dec.data(), n.l.data(), n.u.data(), ax.data(),
-                                                                qt.data(), lam.data(), want, idxA, &na, V.data());
-                        vcount[k] = (uint8_t)nvx;
-                        for (int q = 0; q < nvx; ++q) {
-                            for (int e = 0; e < n.nd; ++e) zv[e] = z[e];
-                            for (int i = 0; i < n.m; ++i) zv[n.nd + i] = 0.0;
-                            for (int j = 0; j < na; ++j) zv[n.nd + idxA[j]] = V[(size_t)q * QPN_VE_MAXA + j];
-                            qpo_comp_indices(g.d1, g.d2, g.np, g.M.data(), g.N.data(), g.o.data(), g.l1.data(), g.u1.data(), g.A.data(),
-                                             g.B.data(), g.l2.data(), g.u2.data(), zv.data(), w.data(), 1e-2, mv.data());
-                            uint8_t* nib = vmask + (size_t)k * vstride + (size_t)q * vb;
-                            for (int i = 0; i < n.m; ++i) nib[i >> 1] |= (uint8_t)((mv[n.nd + i] & 0xf) << ((i & 1) * 4));
-                        }
-                    }
-                }
-                if (snap) std::memcpy(Xf.data() + (size_t)b.slots[k] * nv, x, sizeof(double) * nv);
-            }
-            b.sol = sol; b.mask = mask; b.dz = dz;
-            b.vcount = vcount; b.vmask = vmask; b.vstride = vstride; b.vbytes = vb;
+    void project(int slot) {
+        for (int k = 0; k < nproj; ++k) {
+            double acc = 0.0;
+            for (int j = 0; j < nv; ++j) acc = std::fma(X[(size_t)slot * nv + j], net->proj[(size_t)k * nv + j], acc);
+            PV[(size_t)slot * nproj + k] = acc;
         }
     }
-    void run_qep(int, const LevelGaviInfo& L, QepBatch** bs, int nb, bool snap) override {
-        begin_round();
+    void set_batch(int B_, const double* x_init) override;
+    int post(const Post& p) override { posts.push_back(p); return (int)posts.size() - 1; }
+    void mark_done(Seg seg, int result) override { for (int k = 0; k < seg.n; ++k) result_of[order[seg.off + k]] = result; }
+
+    // the answers of one member, in the byte layout of Part::rep (netsolver.hpp)
+    void answer_cycle(const Post& p, int slot, uint8_t* out) {
+        const double* pv = PV.data() + (size_t)slot * nproj;
+        std::vector<double>& h = hist[slot][p.level];
+        bool hit = false;
+        for (size_t q = 0; q + nproj <= h.size() && !hit; q += nproj) hit = qpn_cycle_hit(pv, h.data() + q, nproj);
+        if (!hit) h.insert(h.end(), pv, pv + nproj);
+        out[0] = hit;
+    }
+    void answer_verify(const Post& p, int slot, uint8_t* out) {
+        const double* x = X.data() + (size_t)slot * nv;
+        const int want = p.want_vertices;
+        for (int r = 0; r < p.nnodes; ++r) {
+            const NodeInfo& n = cache->node_info(p.nodes[r]);
+            const GaviData& g = n.g;
+            const int dz = n.nd + n.m, vb = (n.m + 1) / 2;
+            std::vector<double> lam(n.m + 1), z(dz + 1), w(n.par.size() + 1), ax(n.m + 1), qt(n.nd + 1), V((size_t)QPN_VE_MAXV * QPN_VE_MAXA), zv(dz + 1);
+            std::vector<int8_t> mv(dz + 1);
+            int8_t* mask = (int8_t*)out + 1;
+            uint8_t* vcount = out + 1 + dz;
+            uint8_t* vmask = out + 2 + dz;
+            int32_t how = 0, fp = 0;
+            out[0] = (uint8_t)qpo_verify_solution(n.nd, n.nv, n.m, n.Qd.data(), n.qd.data(), n.A.data(), n.l.data(), n.u.data(), n.dec.data(), x,
+                                                  1e-4, lam.data(), &how, nullptr, &fp);
+            if (out[0]) {
+                for (int e = 0; e < n.nd; ++e) z[e] = x[n.dec[e]];
+                for (int i = 0; i < n.m; ++i) z[n.nd + i] = lam[i];
+                for (size_t c = 0; c < n.par.size(); ++c) w[c] = x[n.par[c]];
+                qpo_comp_indices(g.d1, g.d2, g.np, g.M.data(), g.N.data(), g.o.data(), g.l1.data(), g.u1.data(), g.A.data(), g.B.data(),
+                                 g.l2.data(), g.u2.data(), z.data(), w.data(), 1e-2, mask);
+                if (want > 0) {
+                    // expand's get_verts (avi_solutions.jl:252-255): vertices of the multiplier polytope at x, then comp_indices there
+                    for (int e = 0; e < n.nd; ++e) {
+                        double acc = 0.0;
+                        for (int j = 0; j < nv; ++j) acc = std::fma(n.Qd[(size_t)j * n.nd + e], x[j], acc);
+                        qt[e] = acc + n.qd[e];
+                    }
+                    for (int i = 0; i < n.m; ++i) {
+                        double acc = 0.0;
+                        for (int j = 0; j < nv; ++j) acc = std::fma(n.A[(size_t)j * n.m + i], x[j], acc);
+                        ax[i] = acc;
+                    }
+                    int idxA[QPN_VE_MAXA], na = 0;
+                    const int nvx = qpn_multiplier_vertices(n.nd, n.m, nv, n.A.data(), n.dec.data(), n.l.data(), n.u.data(), ax.data(), qt.data(),
+                                                            lam.data(), want, idxA, &na, V.data());
+                    *vcount = (uint8_t)nvx;
+                    for (int q = 0; q < nvx; ++q) {
+                        for (int e = 0; e < n.nd; ++e) zv[e] = z[e];
+                        for (int i = 0; i < n.m; ++i) zv[n.nd + i] = 0.0;
+                        for (int j = 0; j < na; ++j) zv[n.nd + idxA[j]] = V[(size_t)q * QPN_VE_MAXA + j];
+                        qpo_comp_indices(g.d1, g.d2, g.np, g.M.data(), g.N.data(), g.o.data(), g.l1.data(), g.u1.data(), g.A.data(), g.B.data(),
+                                         g.l2.data(), g.u2.data(), zv.data(), w.data(), 1e-2, mv.data());
+                        uint8_t* nib = vmask + (size_t)q * vb;
+                        for (int i = 0; i < n.m; ++i) nib[i >> 1] |= (uint8_t)((mv[n.nd + i] & 0xf) << ((i & 1) * 4));
+                    }
+                }
+            }
+            if (p.snap) std::memcpy(Xf.data() + (size_t)slot * nv, x, sizeof(double) * nv);
+            out += verify_rep_bytes(dz, n.m, want);
+        }
+    }
+    void answer_qep(const Post& p, int slot, uint8_t* out) {
+        const LevelGaviInfo& L = cache->gavi_info(p.gavi);
         const GaviData& g = L.g;
         const int dz = g.d1 + g.d2, ndl = (int)L.dec.size();
         std::vector<double> w(g.np + 1), z0(dz + 1), z(dz + 1), xn(nv);
-        const int nproj = net->check_for_cycling ? net->num_projections : 0;
-        for (int q = 0; q < nb; ++q) {
-            QepBatch& b = *bs[q];
-            i32.emplace_back(b.n, 0); int32_t* status = i32.back().data();
-            i32.emplace_back(b.n, 0); int32_t* pivots = i32.back().data();
-            u8.emplace_back(b.n, 0); uint8_t* moved = u8.back().data();
-            f64.emplace_back((size_t)b.n * (nproj > 0 ? nproj : 1), 0.0); double* pv = f64.back().data();
-            for (int k = 0; k < b.n; ++k) {
-                double* x = X.data() + (size_t)b.slots[k] * nv;
-                for (int j = 0; j < g.np; ++j) w[j] = x[L.par[j]];
-                for (int j = 0; j < dz; ++j) z0[j] = j < ndl ? x[L.dec[j]] : 0.0;
-                qpo_gavi_solve(g.d1, g.d2, g.np, g.M.data(), g.N.data(), g.o.data(), g.l1.data(), g.u1.data(), g.A.data(), g.B.data(),
-                               g.l2.data(), g.u2.data(), w.data(), z0.data(), 1, 0, z.data(), nullptr, &status[k], &pivots[k], nullptr);
-                if (status[k] == 1) {
-                    std::memcpy(xn.data(), x, sizeof(double) * nv);
-                    for (int j = 0; j < ndl; ++j) xn[L.dec[j]] = z[j];
-                    double dn = 0.0;
-                    for (int j = 0; j < nv; ++j) { const double e = xn[j] - x[j]; dn = std::fma(e, e, dn); }
-                    moved[k] = !(std::sqrt(dn) < 1e-4);
-                    if (moved[k]) {
-                        std::memcpy(x, xn.data(), sizeof(double) * nv);
-                        for (int p = 0; p < nproj; ++p) {
-                            double acc = 0.0;
-                            for (int j = 0; j < nv; ++j) acc = std::fma(x[j], net->proj[(size_t)p * nv + j], acc);
-                            pv[(size_t)k * nproj + p] = acc;
-                        }
-                    }
-                }
-                if (snap) std::memcpy(Xf.data() + (size_t)b.slots[k] * nv, x, sizeof(double) * nv);
+        double* x = X.data() + (size_t)slot * nv;
+        for (int j = 0; j < g.np; ++j) w[j] = x[L.par[j]];
+        for (int j = 0; j < dz; ++j) z0[j] = j < ndl ? x[L.dec[j]] : 0.0;
+        int32_t status = 0, pivots = 0;
+        uint8_t moved = 0;
+        qpo_gavi_solve(g.d1, g.d2, g.np, g.M.data(), g.N.data(), g.o.data(), g.l1.data(), g.u1.data(), g.A.data(), g.B.data(), g.l2.data(),
+                       g.u2.data(), w.data(), z0.data(), 1, 0, z.data(), nullptr, &status, &pivots, nullptr);
+        if (status == 1) {
+            std::memcpy(xn.data(), x, sizeof(double) * nv);
+            for (int j = 0; j < ndl; ++j) xn[L.dec[j]] = z[j];
+            double dn = 0.0;
+            for (int j = 0; j < nv; ++j) { const double e = xn[j] - x[j]; dn = std::fma(e, e, dn); }
+            moved = !(std::sqrt(dn) < 1e-4);
+            if (moved) {
+                std::memcpy(x, xn.data(), sizeof(double) * nv);
+                project(slot);
             }
-            b.status = status; b.pivots = pivots; b.moved = moved; b.pv = pv;
         }
+        if (p.snap) std::memcpy(Xf.data() + (size_t)slot * nv, x, sizeof(double) * nv);
+        std::memcpy(out, &status, 4);
+        out[4] = moved;
     }
-    void run_member(MemberBatch** bs, int nb) override;
-    void finish() override { fresh_round = true; }
-    void projections(double* pv_out) override {
-        const int nproj = net->check_for_cycling ? net->num_projections : 0;
-        for (int b = 0; b < B; ++b)
-            for (int k = 0; k < nproj; ++k) {
-                double acc = 0.0;
-                for (int j = 0; j < nv; ++j) acc = std::fma(X[(size_t)b * nv + j], net->proj[(size_t)k * nv + j], acc);
-                pv_out[(size_t)b * nproj + k] = acc;
+    void answer_member(const Post& p, int slot, uint8_t* out);
+
+    void finish_round(std::vector<Part>& parts) override {
+        parts.clear();
+        reps.clear();
+        next_order.clear();
+        std::vector<uint8_t> rows;
+        for (size_t ci = 0; ci < posts.size(); ++ci) {
+            const Post& p = posts[ci];
+            size_t rb = 0;
+            if (p.kind == POST_CYCLE) rb = 1;
+            else if (p.kind == POST_QEP) rb = 8;
+            else if (p.kind == POST_MEMBER) { for (int k = 0; k < p.nlists; ++k) rb += p.piece_lists[k]->size(); }
+            else for (int r = 0; r < p.nnodes; ++r) { const NodeInfo& n = cache->node_info(p.nodes[r]); rb += verify_rep_bytes(n.nd + n.m, n.m, p.want_vertices); }
+            const size_t stride = rb ? rb : 1;
+            rows.assign(stride * p.seg.n, 0);
+            for (int k = 0; k < p.seg.n; ++k) {
+                const int slot = order[p.seg.off + k];
+                uint8_t* out = rows.data() + stride * k;
+                if (p.kind == POST_CYCLE) answer_cycle(p, slot, out);
+                else if (p.kind == POST_VERIFY) answer_verify(p, slot, out);
+                else if (p.kind == POST_QEP) answer_qep(p, slot, out);
+                else answer_member(p, slot, out);
             }
+            // partition by the answers, parts in order of first appearance, members in their old order
+            std::unordered_map<std::string, int> part_of;
+            std::vector<std::vector<int>> members;
+            for (int k = 0; k < p.seg.n; ++k) {
+                std::string key((const char*)rows.data() + stride * k, stride);
+                auto it = part_of.find(key);
+                if (it == part_of.end()) { it = part_of.emplace(std::move(key), (int)members.size()).first; members.emplace_back(); }
+                members[it->second].push_back(k);
+            }
+            for (auto& mem : members) {
+                Part pt;
+                pt.cohort = (int)ci;
+                pt.seg = Seg{(int)next_order.size(), (int)mem.size()};
+                reps.emplace_back(rows.begin() + stride * mem[0], rows.begin() + stride * (mem[0] + 1));
+                pt.rep = reps.back().data();
+                for (int k : mem) next_order.push_back(order[p.seg.off + k]);
+                parts.push_back(pt);
+            }
+        }
+        order.swap(next_order);
+        posts.clear();
     }
-    void download(double* x_out, const uint8_t* solved) override {
-        for (int b = 0; b < B; ++b)
-            std::memcpy(x_out + (size_t)b * nv, (solved[b] ? X.data() : Xf.data()) + (size_t)b * nv, sizeof(double) * nv);
+    void download(double* x_out, int32_t* result_of_slot, const uint8_t* solved_of_result, int nresults) override {
+        for (int b = 0; b < B; ++b) {
+            const int r = result_of[b];
+            result_of_slot[b] = r;
+            const bool solved = r >= 0 && r < nresults && solved_of_result[r];
+            std::memcpy(x_out + (size_t)b * nv, (solved ? X.data() : Xf.data()) + (size_t)b * nv, sizeof(double) * nv);
+        }
     }
 };
 
-struct PieceCM { int m = 0; std::vector<double> A, l, u; };      // column-major copy for qpo_halfspace_in
-
 struct OracleStore : Store {
     const NetData* net = nullptr;
+    const GeoCache* cache = nullptr;
     std::deque<PieceCM> pieces;
     std::shared_mutex mu;
     Worker* make_worker() override { return new OracleWorker(this); }
@@ -195,29 +231,27 @@ struct OracleStore : Store {
 
 void OracleWorker::set_batch(int B_, const double* x_init) {
     net = store->net;
+    cache = store->cache;
     B = B_; nv = net->nv;
+    nproj = net->check_for_cycling ? net->num_projections : 0;
     X.assign(x_init, x_init + (size_t)B * nv);
     Xf = X;
+    PV.assign((size_t)B * (nproj > 0 ? nproj : 1), 0.0);
+    for (int b = 0; b < B; ++b) project(b);
+    order.resize(B);
+    for (int b = 0; b < B; ++b) order[b] = b;
+    hist.assign(B, std::vector<std::vector<double>>(net->nlevels));
+    result_of.assign(B, -1);
+    posts.clear();
 }
-void OracleWorker::run_member(MemberBatch** bs, int nb) {
-    begin_round();
-    for (int q = 0; q < nb; ++q) {
-        MemberBatch& b = *bs[q];
-        const size_t np = b.pieces->size();
-        std::vector<const PieceCM*> pcs(np);
-        { std::shared_lock<std::shared_mutex> lk(store->mu); for (size_t p = 0; p < np; ++p) pcs[p] = &store->pieces[(*b.pieces)[p]]; }
-        u8.emplace_back((size_t)b.n * np, 0);
-        uint8_t* in = u8.back().data();
-        for (int k = 0; k < b.n; ++k) {
-            const double* x = X.data() + (size_t)b.slots[k] * nv;
-            for (size_t p = 0; p < np; ++p) {
-                const PieceCM* c = pcs[p];
-                in[(size_t)k * np + p] =
-                    c->m == 0 ? 1 : (uint8_t)qpo_halfspace_in(c->m, nv, c->A.data(), c->l.data(), c->u.data(), nullptr, nullptr, x, 1e-6);
-            }
+void OracleWorker::answer_member(const Post& p, int slot, uint8_t* out) {
+    const double* x = X.data() + (size_t)slot * nv;
+    for (int q = 0; q < p.nlists; ++q)
+        for (int id : *p.piece_lists[q]) {
+            const PieceCM* c;
+            { std::shared_lock<std::shared_mutex> lk(store->mu); c = &store->pieces[id]; }
+            *out++ = c->m == 0 ? 1 : (uint8_t)qpo_halfspace_in(c->m, nv, c->A.data(), c->l.data(), c->u.data(), nullptr, nullptr, x, 1e-6);
         }
-        b.in = in;
-    }
 }
 }  // namespace
 
@@ -233,6 +267,7 @@ int qpo_net_create(const qpn_net_desc* desc, void** out) {
     NetObject* o = new NetObject();
     o->solver.reset(new qpnnet::NetSolver(std::move(nd), std::move(polys), std::move(store)));
     sp->net = &o->solver->net();
+    sp->cache = &o->solver->cache();
     *out = o;
     return 0;
 }

@@ -1,6 +1,7 @@
 // Native batched host state machine for networks with children -- see netsolver.hpp for the shape.
 // Build: g++ -std=c++20 -O2 -ffp-contract=off (the geometry must round like the Python host mirror).
 #include "netsolver.hpp"
+#include "vertex_enum.h"
 
 #include <cassert>
 #include <condition_variable>
@@ -494,37 +495,28 @@ struct Frame {                                   // one activation of solve_base
     struct PV { int pid; std::vector<std::vector<int>> combos; int first_req; };
     std::vector<PV> pvs;                         // verify phase: players and their child-piece combinations
     std::vector<int> req_nodes;
+    int want = 0;                                // vertices asked for with the verify requests
     std::vector<uint8_t> sol;                    // answers (uniform over the cohort)
     std::vector<std::vector<int8_t>> masks;
     std::vector<std::vector<int8_t>> vmasks;     // per request: masks at the explored vertices, concatenated
     struct Comb { int pid; std::vector<int> union_lists, red, flat; };
     std::vector<Comb> combs;                     // combine(): players whose leaves wait for membership bits
+    std::vector<const std::vector<int>*> comb_lists;
     std::vector<int> S_out;
+    int gavi = -1;                               // solve_qep phase
 };
 
 enum Wait { W_NONE, W_CYCLE, W_VERIFY, W_MEMBER, W_QEP };
 
 struct Cohort {
-    std::vector<int> members;                    // instance slots
+    Seg seg;                                     // its members in the worker's order array
     std::vector<Frame> stack;
     std::vector<int> level_iters;
     Wait wait = W_NONE;
-    std::vector<VerifyBatch> vb;
-    std::vector<MemberBatch> mb;
-    QepBatch qb;
     bool done = false, solved = false;
     int error = 0;
     std::vector<int> sol;
 };
-
-static bool cycle_hit(const double* pv, const double* prev, int n) {
-    double dd = 0.0, na = 0.0, nb = 0.0;
-    for (int k = 0; k < n; ++k) {
-        const double e = pv[k] - prev[k];
-        dd = std::fma(e, e, dd); na = std::fma(pv[k], pv[k], na); nb = std::fma(prev[k], prev[k], nb);
-    }
-    return std::sqrt(dd) <= 1.4901161193847656e-8 * std::fmax(std::sqrt(na), std::sqrt(nb));       // isapprox, rtol = sqrt(eps)
-}
 
 // Iterators.product order: the FIRST iterator varies fastest (qp_processing.jl:169)
 static void julia_product(const std::vector<int>& sizes, std::vector<std::vector<int>>& out) {
@@ -543,21 +535,11 @@ struct Machine {
     GeoCache& c;
     const NetData& net;
     Worker* w;
-    int B, nproj;
-    std::vector<double> pv;                      // B x nproj: projections of each instance's current x
-    std::vector<std::vector<std::vector<double>>> hist;      // [slot][level]: flat list of earlier projections
-    std::vector<SolveOut>* outs;
-    int out_base;
     std::vector<std::unique_ptr<Cohort>> ready;  // to be looked at by the driver
 
-    Machine(GeoCache& cc, Worker* ww, int B_, std::vector<SolveOut>* o, int base)
-        : c(cc), net(cc.net()), w(ww), B(B_), nproj(cc.net().check_for_cycling ? cc.net().num_projections : 0), outs(o), out_base(base) {
-        pv.assign((size_t)B * (nproj > 0 ? nproj : 1), 0.0);
-        hist.assign(B, std::vector<std::vector<double>>(net.nlevels));
-    }
+    Machine(GeoCache& cc, Worker* ww) : c(cc), net(cc.net()), w(ww) {}
 
     void finish(Cohort& C, bool solved, int err) {
-        for (int s : C.members) for (auto& h : hist[s]) h.clear();       // algorithm.jl:108-114,121-123
         C.done = true; C.solved = solved; C.error = err; C.wait = W_NONE;
         if (solved) C.sol = C.stack.front().S;
     }
@@ -571,7 +553,7 @@ struct Machine {
         C.level_iters[f.level]++;
         if (net.check_for_cycling) {
             if (net.num_projections == 0) return fail(C, ERR_NOPROJ);
-            C.wait = W_CYCLE;                    // the driver splits the cohort by the per-instance check
+            C.wait = W_CYCLE;                    // per instance: the backend splits the cohort by the outcome
             return;
         }
         after_cycle(C, false);
@@ -614,13 +596,9 @@ struct Machine {
             }
             f.pvs.push_back(std::move(pv));
         }
-        C.vb.assign(f.req_nodes.size(), VerifyBatch());
-        for (size_t r = 0; r < f.req_nodes.size(); ++r) {
-            C.vb[r].node = f.req_nodes[r]; C.vb[r].n = (int)C.members.size(); C.vb[r].slots = C.members.data();
-            // solution graphs are built for every level but the first (qp_processing.jl:158); that is where vertices matter
-            const bool gen = f.level != 0 || net.gen_solution_map;
-            C.vb[r].want_vertices = (gen && net.exploration_vertices > 1) ? net.exploration_vertices - 1 : 0;
-        }
+        // solution graphs are built for every level but the first (qp_processing.jl:158); that is where vertices matter
+        const bool gen = f.level != 0 || net.gen_solution_map;
+        f.want = (gen && net.exploration_vertices > 1) ? std::min(net.exploration_vertices - 1, (int)QPN_VE_MAXV) : 0;
         C.wait = W_VERIFY;
     }
 
@@ -672,14 +650,7 @@ struct Machine {
                 if (cb.union_lists.size() > 3 && total > 20) return fail(C, ERR_COMBINE);
                 f.combs.push_back(std::move(cb));
             }
-            if (!f.combs.empty()) {
-                C.mb.assign(f.combs.size(), MemberBatch());
-                for (size_t k = 0; k < f.combs.size(); ++k) {
-                    C.mb[k].n = (int)C.members.size(); C.mb[k].slots = C.members.data(); C.mb[k].pieces = &f.combs[k].flat;
-                }
-                C.wait = W_MEMBER;
-                return;
-            }
+            if (!f.combs.empty()) { C.wait = W_MEMBER; return; }
             return finish_level(C);
         }
         // ---- not an equilibrium: solve_qep with the offending child pieces (algorithm.jl:68-101) -----------------------
@@ -701,16 +672,17 @@ struct Machine {
                 break;                           // the first combination that fails
             }
         }
-        C.qb = QepBatch();
-        C.qb.gavi = c.level_gavi(level, assignment, w);
-        C.qb.n = (int)C.members.size(); C.qb.slots = C.members.data();
+        f.gavi = c.level_gavi(level, assignment, w);
         C.wait = W_QEP;
     }
 
-    void after_member(Cohort& C, const std::vector<std::vector<uint8_t>>& bits) {
+    void after_member(Cohort& C, const uint8_t* bits) {
         Frame& f = C.stack.back();
-        for (size_t k = 0; k < f.combs.size(); ++k)
-            f.S_out[f.combs[k].pid] = c.leaves(f.combs[k].union_lists, f.combs[k].red, bits[k], w);
+        for (size_t k = 0; k < f.combs.size(); ++k) {
+            const size_t np = f.combs[k].flat.size();
+            f.S_out[f.combs[k].pid] = c.leaves(f.combs[k].union_lists, f.combs[k].red, std::vector<uint8_t>(bits, bits + np), w);
+            bits += np;
+        }
         finish_level(C);
     }
 
@@ -734,121 +706,61 @@ struct Machine {
         start_iter(C);
     }
 
-    // ---- splitting ---------------------------------------------------------------------------------------------------
-    // Partition C's members by a byte signature; `apply(part, representative index in the old member list)` is called
-    // for every part (C itself is reused for the first one).
-    template <class Sig, class Apply>
-    void split(std::unique_ptr<Cohort> C, Sig&& sig, Apply&& apply) {
-        const int n = (int)C->members.size();
-        std::unordered_map<std::string, int> part_of;
-        std::vector<std::vector<int>> parts;     // indices into the old member list
-        std::string key;
-        for (int k = 0; k < n; ++k) {
-            key.clear();
-            sig(k, key);
-            auto it = part_of.find(key);
-            if (it == part_of.end()) { it = part_of.emplace(key, (int)parts.size()).first; parts.emplace_back(); }
-            parts[it->second].push_back(k);
+    // ---- the request a waiting cohort posts, and what it does with a representative's answers ---------------------------
+    Post make_post(Cohort& C) {
+        Frame& f = C.stack.back();
+        Post p;
+        p.seg = C.seg;
+        switch (C.wait) {
+            case W_CYCLE: p.kind = POST_CYCLE; p.level = f.level; break;
+            case W_VERIFY:
+                p.kind = POST_VERIFY; p.nodes = f.req_nodes.data(); p.nnodes = (int)f.req_nodes.size(); p.want_vertices = f.want;
+                p.snap = f.level == 0;
+                break;
+            case W_MEMBER:
+                f.comb_lists.clear();
+                for (const Frame::Comb& cb : f.combs) f.comb_lists.push_back(&cb.flat);
+                p.kind = POST_MEMBER; p.piece_lists = f.comb_lists.data(); p.nlists = (int)f.comb_lists.size();
+                break;
+            default: p.kind = POST_QEP; p.gavi = f.gavi; p.snap = f.level == 0; break;
         }
-        if (parts.size() > 1) c.stats.cohorts += (long)parts.size() - 1;
-        const std::vector<int> old = C->members;
-        std::vector<std::unique_ptr<Cohort>> out;
-        for (size_t p = 1; p < parts.size(); ++p) {
-            auto D = std::make_unique<Cohort>(*C);
-            D->members.clear();
-            for (int k : parts[p]) D->members.push_back(old[k]);
-            out.push_back(std::move(D));
-        }
-        if (parts.size() > 1) {
-            C->members.clear();
-            for (int k : parts[0]) C->members.push_back(old[k]);
-        }
-        apply(*C, parts[0][0]);
-        for (size_t p = 1; p < parts.size(); ++p) apply(*out[p - 1], parts[p][0]);
-        ready.push_back(std::move(C));
-        for (auto& D : out) ready.push_back(std::move(D));
+        return p;
     }
 
-    void resolve_cycle(std::unique_ptr<Cohort> C) {
-        const int level = C->stack.back().level;
-        std::vector<uint8_t> hit(C->members.size(), 0);
-        for (size_t k = 0; k < C->members.size(); ++k) {
-            const int s = C->members[k];
-            const double* p = pv.data() + (size_t)s * nproj;
-            std::vector<double>& h = hist[s][level];
-            for (size_t q = 0; q + nproj <= h.size(); q += nproj) if (cycle_hit(p, h.data() + q, nproj)) { hit[k] = 1; break; }
-            if (!hit[k]) h.insert(h.end(), p, p + nproj);
+    void apply(Cohort& P, const uint8_t* rep) {
+        const Wait wt = P.wait;
+        P.wait = W_NONE;
+        Frame& f = P.stack.back();
+        if (wt == W_CYCLE) return after_cycle(P, rep[0] != 0);
+        if (wt == W_MEMBER) return after_member(P, rep);
+        if (wt == W_QEP) {
+            int32_t status;
+            std::memcpy(&status, rep, 4);
+            return after_qep(P, status, rep[4] != 0);
         }
-        split(std::move(C), [&](int k, std::string& key) { key.push_back((char)hit[k]); },
-              [&](Cohort& P, int rep) { P.wait = W_NONE; after_cycle(P, hit[rep] != 0); });
-    }
-
-    void resolve_verify(std::unique_ptr<Cohort> C) {
-        std::vector<VerifyBatch> vb = C->vb;     // the answers (pointers into the backend's result buffers)
-        split(std::move(C),
-              [&](int k, std::string& key) {
-                  for (const VerifyBatch& b : vb) {
-                      key.push_back((char)b.sol[k]);
-                      if (b.sol[k]) {
-                          key.append((const char*)b.mask + (size_t)k * b.dz, (size_t)b.dz);
-                          if (b.vcount) {
-                              key.push_back((char)b.vcount[k]);
-                              key.append((const char*)b.vmask + (size_t)k * b.vstride, (size_t)b.vcount[k] * b.vbytes);
-                          }
-                      }
-                  }
-              },
-              [&](Cohort& P, int rep) {
-                  Frame& f = P.stack.back();
-                  f.sol.assign(vb.size(), 0);
-                  f.masks.assign(vb.size(), {});
-                  f.vmasks.assign(vb.size(), {});
-                  for (size_t r = 0; r < vb.size(); ++r) {
-                      f.sol[r] = vb[r].sol[rep];
-                      if (!f.sol[r]) continue;
-                      f.masks[r].assign(vb[r].mask + (size_t)rep * vb[r].dz, vb[r].mask + (size_t)(rep + 1) * vb[r].dz);
-                      if (!vb[r].vcount) continue;
-                      // a vertex keeps the primal part of the point: only the masks of the m multiplier rows change
-                      const int dz = vb[r].dz, m2 = vb[r].vbytes, nvx = vb[r].vcount[rep];
-                      const int mrows = c.node_info(vb[r].node).m, nd = dz - mrows;
-                      for (int q = 0; q < nvx; ++q) {
-                          const uint8_t* nib = vb[r].vmask + (size_t)rep * vb[r].vstride + (size_t)q * m2;
-                          std::vector<int8_t> vm = f.masks[r];
-                          for (int i = 0; i < mrows; ++i) vm[nd + i] = (int8_t)((nib[i >> 1] >> ((i & 1) * 4)) & 0xf);
-                          f.vmasks[r].insert(f.vmasks[r].end(), vm.begin(), vm.end());
-                      }
-                  }
-                  P.vb.clear();
-                  P.wait = W_NONE;
-                  after_verify(P);
-              });
-    }
-
-    void resolve_member(std::unique_ptr<Cohort> C) {
-        std::vector<MemberBatch> mb = C->mb;
-        std::vector<size_t> np;
-        for (const auto& b : mb) np.push_back(b.pieces->size());
-        split(std::move(C),
-              [&](int k, std::string& key) {
-                  for (size_t r = 0; r < mb.size(); ++r) key.append((const char*)mb[r].in + (size_t)k * np[r], np[r]);
-              },
-              [&](Cohort& P, int rep) {
-                  std::vector<std::vector<uint8_t>> bits(mb.size());
-                  for (size_t r = 0; r < mb.size(); ++r) bits[r].assign(mb[r].in + (size_t)rep * np[r], mb[r].in + (size_t)(rep + 1) * np[r]);
-                  P.mb.clear();
-                  P.wait = W_NONE;
-                  after_member(P, bits);
-              });
-    }
-
-    void resolve_qep(std::unique_ptr<Cohort> C) {
-        const QepBatch qb = C->qb;
-        for (int k = 0; k < qb.n; ++k)           // x moved: its projections are the ones the next cycle check reads
-            if (qb.status[k] == 1 && qb.moved[k] && nproj > 0)
-                std::memcpy(pv.data() + (size_t)qb.slots[k] * nproj, qb.pv + (size_t)k * nproj, sizeof(double) * nproj);
-        split(std::move(C),
-              [&](int k, std::string& key) { key.push_back((char)qb.status[k]); key.push_back((char)qb.moved[k]); },
-              [&](Cohort& P, int rep) { P.wait = W_NONE; after_qep(P, qb.status[rep], qb.moved[rep] != 0); });
+        const size_t nr = f.req_nodes.size();
+        f.sol.assign(nr, 0);
+        f.masks.assign(nr, {});
+        f.vmasks.assign(nr, {});
+        for (size_t r = 0; r < nr; ++r) {
+            const NodeInfo& info = c.node_info(f.req_nodes[r]);
+            const int mrows = info.m, nd = info.nd, dz = nd + mrows, vbytes = (mrows + 1) / 2;
+            const uint8_t* mask = rep + 1;
+            const int nvx = rep[1 + dz];
+            const uint8_t* vmask = rep + 2 + dz;
+            f.sol[r] = rep[0];
+            rep += verify_rep_bytes(dz, mrows, f.want);
+            if (!f.sol[r]) continue;
+            f.masks[r].assign((const int8_t*)mask, (const int8_t*)mask + dz);
+            // a vertex keeps the primal part of the point: only the masks of the m multiplier rows change
+            for (int q = 0; q < nvx && q < f.want; ++q) {
+                const uint8_t* nib = vmask + (size_t)q * vbytes;
+                std::vector<int8_t> vm = f.masks[r];
+                for (int i = 0; i < mrows; ++i) vm[nd + i] = (int8_t)((nib[i >> 1] >> ((i & 1) * 4)) & 0xf);
+                f.vmasks[r].insert(f.vmasks[r].end(), vm.begin(), vm.end());
+            }
+        }
+        after_verify(P);
     }
 };
 
@@ -878,88 +790,79 @@ void NetSolver::run_shard(int tid, int lo, int hi, const double* inits, double* 
     w->set_batch(B, inits + (size_t)lo * nv);
     st.backend_ns += ns(t_host, now());
     t_host = now();
-    Machine M(*cache_, w, B, &outs, lo);
-    if (M.nproj > 0) w->projections(M.pv.data());
+    Machine M(*cache_, w);
     {
         auto C = std::make_unique<Cohort>();
-        C->members.resize(B);
-        for (int b = 0; b < B; ++b) C->members[b] = b;
+        C->seg = Seg{0, B};
         C->level_iters.assign(net_.nlevels, 0);
         C->stack.emplace_back();
         M.start_iter(*C);
         M.ready.push_back(std::move(C));
     }
+    std::vector<SolveOut> results;               // outcome per finished cohort; instances carry an index into it
     std::vector<std::unique_ptr<Cohort>> waiting;
-    std::vector<VerifyBatch*> vlist;
-    std::vector<QepBatch*> qlist;
-    std::vector<MemberBatch*> mlist;
+    std::vector<Part> parts;
     while (true) {
-        // ---- everything the host can decide on its own: finished cohorts, cycle checks ---------------------------------
+        // ---- everything the host can decide on its own --------------------------------------------------------------
         while (!M.ready.empty()) {
             std::unique_ptr<Cohort> C = std::move(M.ready.back());
             M.ready.pop_back();
             if (C->done) {
-                for (int s : C->members) {
-                    SolveOut& o = outs[lo + s];
-                    o.solved = C->solved; o.error = C->error; o.level_iters = C->level_iters;
-                    if (C->solved) o.sol = C->sol; else o.sol.assign(net_.nplayers, -1);
-                }
-            } else if (C->wait == W_CYCLE) {
-                M.resolve_cycle(std::move(C));
+                SolveOut o;
+                o.solved = C->solved; o.error = C->error; o.level_iters = C->level_iters;
+                if (C->solved) o.sol = C->sol; else o.sol.assign(net_.nplayers, -1);
+                w->mark_done(C->seg, (int)results.size());
+                results.push_back(std::move(o));
             } else {
                 waiting.push_back(std::move(C));
             }
         }
         if (waiting.empty()) break;
-        // ---- one batched backend call per (kind, resident object) over the requests of all waiting cohorts --------------
-        vlist.clear(); qlist.clear(); mlist.clear();
+        // ---- one round of the backend over the requests of all waiting cohorts -------------------------------------------
         long nreq = 0;
         for (auto& C : waiting) {
-            if (C->wait == W_VERIFY) for (auto& b : C->vb) { vlist.push_back(&b); nreq += b.n; }
-            else if (C->wait == W_QEP) { qlist.push_back(&C->qb); nreq += C->qb.n; }
-            else if (C->wait == W_MEMBER) for (auto& b : C->mb) { mlist.push_back(&b); nreq += b.n; }
+            const Post p = M.make_post(*C);
+            nreq += (long)p.seg.n * (p.kind == POST_VERIFY ? p.nnodes : p.kind == POST_MEMBER ? p.nlists : 1);
+            w->post(p);
         }
-        std::stable_sort(vlist.begin(), vlist.end(), [](const VerifyBatch* a, const VerifyBatch* b) { return a->node < b->node; });
-        std::stable_sort(qlist.begin(), qlist.end(), [](const QepBatch* a, const QepBatch* b) { return a->gavi < b->gavi; });
         auto t_back = now();
         st.host_ns += ns(t_host, t_back);
         st.rounds++;
         st.requests += nreq;
-        for (size_t i = 0; i < vlist.size();) {
-            size_t j = i;
-            while (j < vlist.size() && vlist[j]->node == vlist[i]->node) ++j;
-            const NodeInfo& info = cache_->node_info(vlist[i]->node);
-            w->run_verify(vlist[i]->node, info, &vlist[i], (int)(j - i), net_.level_of[info.pid] == 0);
-            st.calls++;
-            i = j;
-        }
-        for (size_t i = 0; i < qlist.size();) {
-            size_t j = i;
-            while (j < qlist.size() && qlist[j]->gavi == qlist[i]->gavi) ++j;
-            const LevelGaviInfo& info = cache_->gavi_info(qlist[i]->gavi);
-            w->run_qep(qlist[i]->gavi, info, &qlist[i], (int)(j - i), info.level == 0);
-            st.calls++;
-            i = j;
-        }
-        if (!mlist.empty()) { w->run_member(mlist.data(), (int)mlist.size()); st.calls++; }
-        w->finish();
+        st.calls += (long)waiting.size();
+        w->finish_round(parts);
         t_host = now();
         st.backend_ns += ns(t_back, t_host);
-        // ---- split every cohort by what its members were told ------------------------------------------------------------
+        // ---- every part of a cohort goes on with a copy of the state and its representative's answers -----------------------
         std::vector<std::unique_ptr<Cohort>> got;
         got.swap(waiting);
-        for (auto& C : got) {
-            const Wait wt = C->wait;
-            if (wt == W_VERIFY) M.resolve_verify(std::move(C));
-            else if (wt == W_QEP) M.resolve_qep(std::move(C));
-            else M.resolve_member(std::move(C));
+        for (size_t i = 0; i < parts.size();) {
+            size_t j = i;
+            while (j < parts.size() && parts[j].cohort == parts[i].cohort) ++j;
+            std::unique_ptr<Cohort>& C = got[parts[i].cohort];
+            if (j - i > 1) st.cohorts += (long)(j - i - 1);
+            for (size_t k = i + 1; k < j; ++k) {
+                auto D = std::make_unique<Cohort>(*C);
+                D->seg = parts[k].seg;
+                M.apply(*D, parts[k].rep);
+                M.ready.push_back(std::move(D));
+            }
+            C->seg = parts[i].seg;
+            M.apply(*C, parts[i].rep);
+            M.ready.push_back(std::move(C));
+            i = j;
         }
     }
     st.host_ns += ns(t_host, now());
     t_host = now();
-    std::vector<uint8_t> solved(B);
-    for (int b = 0; b < B; ++b) solved[b] = outs[lo + b].solved;
-    w->download(x_out + (size_t)lo * nv, solved.data());
+    std::vector<uint8_t> solved(results.size() + 1, 0);
+    for (size_t r = 0; r < results.size(); ++r) solved[r] = results[r].solved;
+    std::vector<int32_t> res_of(B, -1);
+    w->download(x_out + (size_t)lo * nv, res_of.data(), solved.data(), (int)results.size());
+    for (int b = 0; b < B; ++b) {
+        if (res_of[b] >= 0 && res_of[b] < (int)results.size()) outs[lo + b] = results[res_of[b]];
+        else { outs[lo + b].level_iters.assign(net_.nlevels, 0); outs[lo + b].sol.assign(net_.nplayers, -1); outs[lo + b].error = ERR_MAXIT; }
+    }
     st.backend_ns += ns(t_host, now());
 }
 

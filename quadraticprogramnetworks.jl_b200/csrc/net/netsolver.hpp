@@ -71,51 +71,58 @@ struct LevelGaviInfo {
 
 // ---- requests a cohort posts -------------------------------------------------------------------------------------
 // A cohort is a set of instances that share their whole control state (level stack, solution graphs, iteration
-// counters): whatever one of them asks, all of them ask.  A request therefore names a resident object and the
-// cohort's list of instance slots; the backend answers with one entry per slot.  Result pointers stay valid until
-// the worker's next round.
-struct VerifyBatch {        // verify_solution at each instance's x, then comp_indices of the node GAVI at (x, lam)
-    int node = 0, n = 0;
-    const int* slots = nullptr;
-    const uint8_t* sol = nullptr;                // n flags
-    const int8_t* mask = nullptr;                // n x dz masks (rows of non-solutions are undefined)
-    int dz = 0;
-    // vertex exploration (exploration_vertices > 0; expand's get_verts, avi_solutions.jl:252-255): per slot the number
-    // of new vertices of its multiplier polytope and, per vertex, the comp_indices masks of the m multiplier rows at
-    // that vertex, two rows per byte (low nibble first)
-    int want_vertices = 0;                       // in: explore up to this many new vertices (0 = none)
-    const uint8_t* vcount = nullptr;             // n
-    const uint8_t* vmask = nullptr;              // n x vstride
-    int vstride = 0, vbytes = 0;                 // bytes per slot / per vertex (= ceil(m / 2))
+// counters): whatever one of them asks, all of them ask.  The backend keeps the instance slots of a worker in an ORDER
+// array in which every live cohort is a contiguous segment; a request names a resident object and the cohort's
+// segment.  The backend answers every member, partitions the segment by the members' answers (on the GPU: a 64-bit
+// signature per member, a segmented sort, a boundary scan -- the host never sees per-instance data) and hands back,
+// per part, its new segment and the answers of ONE representative member.
+struct Seg { int off = 0, n = 0; };
+
+enum PostKind { POST_CYCLE = 0, POST_VERIFY = 1, POST_MEMBER = 2, POST_QEP = 3 };
+
+struct Post {
+    int kind = POST_CYCLE;
+    Seg seg;
+    // POST_CYCLE: the cycle check of algorithm.jl:14-30 for the iterate history of (instance, level); a miss appends
+    int level = 0;
+    // POST_VERIFY: verify_solution at each instance's x, then comp_indices of the node GAVI at (x, lam), for each of the
+    // cohort's nodes; want_vertices > 0: expand's get_verts too (avi_solutions.jl:252-255): up to that many new vertices of
+    // the multiplier polytope and the comp_indices masks of the m multiplier rows at each, two rows per byte
+    const int* nodes = nullptr;
+    int nnodes = 0, want_vertices = 0, snap = 0;
+    // POST_MEMBER: x in closure(piece) for the pieces of each list (intersection.jl:74,82)
+    const std::vector<int>* const* piece_lists = nullptr;
+    int nlists = 0;
+    // POST_QEP: solve_qep for a level GAVI; on success (and a move of >= 1e-4) x[dec] is replaced
+    int gavi = 0;
 };
-struct QepBatch {           // solve_qep for a level GAVI; on success (and a move of >= 1e-4) x[dec] is replaced
-    int gavi = 0, n = 0;
-    const int* slots = nullptr;
-    const int32_t* status = nullptr;             // n
-    const int32_t* pivots = nullptr;             // n
-    const uint8_t* moved = nullptr;              // n: norm(xnew - x) >= 1e-4
-    const double* pv = nullptr;                  // n x nproj: projections of the new x (valid where status = 1 and moved)
+
+// Answers of a part's representative, as bytes:
+//   POST_CYCLE : [hit]
+//   POST_VERIFY: per node r: [sol] [mask: dz_r] [vcount] [vmask: want * ceil(m_r / 2)]   (mask / vertices valid when sol)
+//   POST_MEMBER: per list, per piece: [in]
+//   POST_QEP   : [status: int32] [moved] [3 pad]
+struct Part {
+    int cohort = 0;                              // index of the post within the round
+    Seg seg;                                     // the part's segment in the NEW order
+    const uint8_t* rep = nullptr;                // valid until the worker's next round
 };
-struct MemberBatch {        // x in closure(piece) for a list of pieces (intersection.jl:74,82)
-    int n = 0;
-    const int* slots = nullptr;
-    const std::vector<int>* pieces = nullptr;
-    const uint8_t* in = nullptr;                 // n x pieces->size()
-};
+static inline int verify_rep_bytes(int dz, int m, int want) { return 2 + dz + want * ((m + 1) / 2); }
 
 // ---- numeric backend ---------------------------------------------------------------------------------------------
 struct Worker : LPBackend {
-    // instance slots 0..B-1 of this worker: x = x_fail = init (nv x B column-major)
+    // instance slots 0..B-1 of this worker: x = x_fail = init (nv x B column-major); order = identity (one segment
+    // {0, B}); cycle-check histories empty; the projections of every x taken
     virtual void set_batch(int B, const double* x_init) = 0;
-    // enqueue batched calls: all batches of one call name the same resident object (they may run until finish())
-    virtual void run_verify(int node, const NodeInfo& info, VerifyBatch** b, int nb, bool snap) = 0;
-    virtual void run_qep(int gavi, const LevelGaviInfo& info, QepBatch** b, int nb, bool snap) = 0;
-    virtual void run_member(MemberBatch** b, int nb) = 0;
-    virtual void finish() = 0;                   // all results of the enqueued calls are behind the batches' pointers
-    // projections of every slot's x onto the net's cycle-check vectors: pv_out B x nproj (algorithm.jl:14)
-    virtual void projections(double* pv_out) = 0;
-    // x_out (nv x B) = x where solved[b], the reference's x_fail otherwise (algorithm.jl:116,125)
-    virtual void download(double* x_out, const uint8_t* solved) = 0;
+    // enqueue a cohort's request for this round; returns its index within the round
+    virtual int post(const Post& p) = 0;
+    // the members of a finished cohort get `result` (an index into the caller's table of outcomes)
+    virtual void mark_done(Seg seg, int result) = 0;
+    // run the round: parts ordered by cohort, then by position in the new order
+    virtual void finish_round(std::vector<Part>& parts) = 0;
+    // result_of_slot (B): what mark_done recorded; x_out (nv x B) = x where solved_of_result[result], the reference's
+    // x_fail otherwise (algorithm.jl:116,125)
+    virtual void download(double* x_out, int32_t* result_of_slot, const uint8_t* solved_of_result, int nresults) = 0;
     virtual int64_t launches() const { return 0; }
 };
 struct Store {              // shared by the workers of one net: resident copies of nodes / GAVIs / pieces

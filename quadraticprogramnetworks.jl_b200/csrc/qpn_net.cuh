@@ -1,16 +1,20 @@
 // Kernels of the native network state machine (csrc/net/): the numeric requests of a batch of instances whose x
-// stays resident on the GPU (X: nv x slots, column-major).  Every launch works on a LIST of instance slots -- the
-// instances that asked for the same thing this round -- against a resident node / level GAVI / piece.
+// stays resident on the GPU (X: nv x slots, column-major), and the partition of the batch into cohorts.
+//   net_cycle_kernel  : the cycle check of solve_base! (algorithm.jl:14-30) against the (instance, level) history
 //   net_verify_kernel : verify_solution (qp_processing.jl:57-149) at x, then comp_indices (avi_solutions.jl:587-612)
-//                       of the node's own GAVI at (x, lam) -- what process_qp needs before it builds a solution graph
+//                       of the node's own GAVI at (x, lam) -- what process_qp needs before it builds a solution graph --
+//                       and the vertices of the multiplier polytope for expand (avi_solutions.jl:252-255)
 //   net_qep_kernel    : solve_qep (avi.jl:382-444) for a level GAVI with plans, the 1e-4 disagreement test and the
 //                       cycle-check projections of the new iterate (algorithm.jl:14-30,95-99); x updated in place
-//   net_member_kernel : x in closure(piece) (intersection.jl:74,82 through sets.jl:820-825), one warp per (instance, piece)
-// The arithmetic of each is the arithmetic of the single-purpose kernels (same device functions, same summation
-// orders), so results are bit-equal to the C oracle's.
+//   net_member_kernel : x in closure(piece) (intersection.jl:74,82 through sets.jl:820-825)
+//   net_round_*       : the members of every cohort sorted by what they were told, cut into parts, one representative's
+//                       answers per part copied out -- the only per-round data the host reads
+// The arithmetic of each numeric kernel is the arithmetic of the single-purpose kernels (same device functions, same
+// summation orders), so results are bit-equal to the C oracle's.
 #pragma once
 #include "qpn_level.cuh"
 #include "net/vertex_enum.h"
+#include "net/cycle_check.h"
 
 namespace qpn {
 
@@ -31,9 +35,39 @@ struct PieceTabEntry {
     const double *A, *l, *u;    // rows row-major over nv
     int m, pad;
 };
-// One group of a launch: `count` consecutive requests (from `start`) against the same resident object.
-struct VGroup { int node, start, count, snap; unsigned mask_off, vm_off; int want, pad; };
-struct QGroup { int gavi, start, count, snap; };
+
+// ---- a round of the state machine --------------------------------------------------------------------------------
+// The instance slots of a worker live in an ORDER array in which every live cohort is a contiguous segment.  A round's
+// posts number their members 0 .. total-1 (`dst`: cohort after cohort); every kernel of the round adds what it told a
+// member to that member's 64-bit signature keys[dst] (a sum of mixed (position, byte) terms over the member's answer
+// bytes: commutative, so the threads of a launch may add in any order and the sum is deterministic).  net_round_* then
+// sort each cohort's members by signature (cub::DeviceSegmentedSort, stable), cut the sorted segments into parts and
+// copy ONE representative's answers per part; the sorted slots are the next round's order array.
+enum { RK_CYCLE = 0, RK_VERIFY = 1, RK_MEMBER = 2, RK_QEP = 3 };
+struct CohortDev {
+    int kind, src_off, n, dst_off;
+    int first, count;                  // verify: its groups in the VGroup table; member: its MGroup, pieces per member
+    int rep_bytes, level;
+};
+struct VGroup {                        // one (cohort, node) of the verify launch: `count` pairs from pair `start`
+    int node, start, count, snap;
+    int src_off, dst_off, want, rep_off;   // rep_off: byte offset of this node's answers in the member's answer row
+    unsigned mask_off, vm_off;         // byte offsets of the group's rows in the mask / vertex-mask buffers
+    int dz, vbytes;
+};
+struct QGroup { int gavi, start, count, snap, src_off, dst_off; };
+struct MGroup { int start, count, src_off, dst_off, np, list_off; unsigned out_off; int pad; };   // pairs piece-major: idx = p * count + k
+struct DoneDev { int src_off, n, result, pad; };
+struct PartDev { int pos, cohort, old, data_off; };
+
+__host__ __device__ __forceinline__ unsigned long long qpn_mix64(unsigned long long x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return x;
+}
+// the signature term of answer byte `byte` at offset `pos` of the member's answer row (the layout of Part::rep)
+__host__ __device__ __forceinline__ unsigned long long qpn_sig_term(unsigned pos, unsigned byte) {
+    return qpn_mix64((((unsigned long long)pos + 1ull) << 8) | (unsigned long long)(byte & 0xffu));
+}
 
 __device__ __forceinline__ int find_group_start(const int* starts, int ngroups, int b) {
     int lo = 0, hi = ngroups - 1;          // last group whose start <= b
@@ -44,14 +78,68 @@ __device__ __forceinline__ int find_group_start(const int* starts, int ngroups, 
     return lo;
 }
 
-// grid = all verify requests of a round (every node's group back to back), block = roundup32(max over the groups of
-// max(m, nd, 1)).  Dynamic smem: the largest group's verify_solution_kernel layout (Tab(m, m+1) + VerifySmem + x(nv) +
+// adds the warp's terms to *key (every lane of the warp must call it)
+__device__ __forceinline__ void sig_add_warp(unsigned long long* key, unsigned long long term) {
+    for (int o = 16; o > 0; o >>= 1) term += __shfl_xor_sync(0xffffffffu, term, o);
+    if ((threadIdx.x & 31) == 0 && term != 0ull) atomicAdd(key, term);
+}
+
+// One thread per member of the round: its slot, an empty signature, its own index as the sort payload.
+__global__ void net_round_fill_kernel(const CohortDev* __restrict__ cohorts, const int* __restrict__ cstarts, int ncohorts, int total,
+                                      const int32_t* __restrict__ order, int32_t* __restrict__ slot_of, unsigned long long* __restrict__ keys,
+                                      int32_t* __restrict__ vals) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= total) return;
+    const CohortDev c = cohorts[find_group_start(cstarts, ncohorts, d)];
+    slot_of[d] = order[c.src_off + (d - c.dst_off)];
+    keys[d] = 0ull;
+    vals[d] = d;
+}
+
+// The members of finished cohorts get the index of their outcome.
+__global__ void net_done_kernel(const DoneDev* __restrict__ done, const int32_t* __restrict__ order, int32_t* __restrict__ result_of) {
+    const DoneDev d = done[blockIdx.x];
+    for (int k = threadIdx.x; k < d.n; k += blockDim.x) result_of[order[d.src_off + k]] = d.result;
+}
+
+// The cycle check, one thread per member.  History of (slot, level): a linked list through `prev` in an append-only
+// log (entry e: nproj projections at ent_pv[e * nproj], link ent_prev[e]); a miss appends at log_base + its index in the
+// launch (the host sized the log for every member of the launch).
+__global__ void net_cycle_kernel(const CohortDev* __restrict__ cohorts, const int* __restrict__ cidx, const int* __restrict__ cycstarts,
+                                 int ncyc, int total, int nlevels, int nproj, const int32_t* __restrict__ slot_of,
+                                 const double* __restrict__ PV, int32_t* __restrict__ head, double* __restrict__ ent_pv,
+                                 int32_t* __restrict__ ent_prev, int log_base, uint8_t* __restrict__ hit_out,
+                                 unsigned long long* __restrict__ keys) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int q = find_group_start(cycstarts, ncyc, t);
+    const CohortDev c = cohorts[cidx[q]];
+    const int d = c.dst_off + (t - cycstarts[q]);
+    const int slot = slot_of[d];
+    const double* pv = PV + (size_t)slot * nproj;
+    int32_t* hd = head + (size_t)slot * nlevels + c.level;
+    int hit = 0;
+    // (the reference scans its cache from the oldest entry; "any earlier iterate" does not depend on the order)
+    for (int e = *hd; e >= 0 && !hit; e = ent_prev[e]) hit = qpn_cycle_hit(pv, ent_pv + (size_t)e * nproj, nproj);
+    if (!hit) {
+        const int e = log_base + t;
+        for (int k = 0; k < nproj; ++k) ent_pv[(size_t)e * nproj + k] = pv[k];
+        ent_prev[e] = *hd;
+        *hd = e;
+    }
+    hit_out[d] = (uint8_t)hit;
+    keys[d] += qpn_sig_term(0u, (unsigned)hit);        // the member's only answer this round: no other thread adds to it
+}
+
+// grid = all verify requests of a round (every (cohort, node) group back to back), block = roundup32(max over the groups
+// of max(m, nd, 1)).  Dynamic smem: the largest group's verify_solution_kernel layout (Tab(m, m+1) + VerifySmem + x(nv) +
 // qt(nd) + ax(m)) plus the vertex scratch.
 __global__ void net_verify_kernel(const NodeTabEntry* __restrict__ table, const VGroup* __restrict__ groups,
-                                  const int* __restrict__ gstarts, int ngroups, const int32_t* __restrict__ inst,
+                                  const int* __restrict__ gstarts, int ngroups, const int32_t* __restrict__ order,
                                   const double* __restrict__ X, double* __restrict__ Xf_all, double tol,
                                   uint8_t* __restrict__ solution_out, int8_t* __restrict__ mask_base,
-                                  uint8_t* __restrict__ vcount_out, uint8_t* __restrict__ vmask_base) {
+                                  uint8_t* __restrict__ vcount_out, uint8_t* __restrict__ vmask_base,
+                                  unsigned long long* __restrict__ keys) {
     const int b = blockIdx.x, i = threadIdx.x;
     const VGroup grp = groups[find_group_start(gstarts, ngroups, b)];
     const NodeTabEntry& ent = table[grp.node];
@@ -63,7 +151,10 @@ __global__ void net_verify_kernel(const NodeTabEntry* __restrict__ table, const 
     const int kloc = b - grp.start;
     int8_t* my_mask = mask_base + grp.mask_off + (size_t)kloc * (nd + m);
     uint8_t* my_vmask = vmask_base + grp.vm_off + (size_t)kloc * want_v * ((m + 1) >> 1);
-    const int slot = inst[b];
+    const int slot = order[grp.src_off + kloc];
+    unsigned long long* key = keys + grp.dst_off + kloc;
+    const unsigned rp = (unsigned)grp.rep_off;
+    unsigned long long sig = 0ull;
     const int tn = m > 0 ? m : 1;
     Tab tab;
     tab_carve(tab, tn, tn + 1, 0);
@@ -106,9 +197,10 @@ __global__ void net_verify_kernel(const NodeTabEntry* __restrict__ table, const 
                 mk = comp_mask(g.l2[k], g.u2[k], lam[k], s, 1e-2);
             }
             my_mask[r] = mk;
+            sig += qpn_sig_term(rp + 1u + (unsigned)r, (unsigned)(uint8_t)mk);
         }
     }
-    if (i == 0) solution_out[b] = (uint8_t)sol;
+    if (i == 0) { solution_out[b] = (uint8_t)sol; sig += qpn_sig_term(rp, (unsigned)sol); }
     if (want_v > 0) {
         // expand's get_verts (avi_solutions.jl:252-255): the vertices of the node's multiplier polytope at x, enumerated by
         // one thread (net/vertex_enum.h), then comp_indices at every vertex by all of them -- only the masks of the m
@@ -120,6 +212,7 @@ __global__ void net_verify_kernel(const NodeTabEntry* __restrict__ table, const 
             if (sol) nvx = qpn_multiplier_vertices(nd, m, node.nv, node.A, node.dec, node.l, node.u, ax, qt, vs.lam_out(), want_v, hdr + 2, &a, Vs);
             hdr[0] = nvx; hdr[1] = a;
             vcount_out[b] = (uint8_t)nvx;
+            if (sol) sig += qpn_sig_term(rp + 1u + (unsigned)dz, (unsigned)nvx);
         }
         QPN_SYNC();
         const int nvx = hdr[0], a = hdr[1], vbytes = (m + 1) >> 1;
@@ -141,10 +234,12 @@ __global__ void net_verify_kernel(const NodeTabEntry* __restrict__ table, const 
                     packed |= (comp_mask(g.l2[k], g.u2[k], lv[k], acc + acc2, 1e-2) & 0xf) << (4 * h);
                 }
                 my_vmask[(size_t)q * vbytes + t] = (uint8_t)packed;
+                sig += qpn_sig_term(rp + 2u + (unsigned)dz + (unsigned)(q * vbytes + t), (unsigned)packed);
             }
             QPN_SYNC();
         }
     }
+    sig_add_warp(key, sig);
 }
 
 // grid = the solve_qep requests of a round whose level GAVIs fall into this thread bucket (groups back to back),
@@ -153,9 +248,9 @@ __global__ void net_verify_kernel(const NodeTabEntry* __restrict__ table, const 
 template <int MAXT>
 __global__ void __launch_bounds__(MAXT, 896 / MAXT)
 net_qep_kernel(const GaviTabEntry* __restrict__ table, const QGroup* __restrict__ groups, const int* __restrict__ gstarts,
-               int ngroups, int nv, int nproj, const double* __restrict__ proj, const int32_t* __restrict__ inst,
+               int ngroups, int nv, int nproj, const double* __restrict__ proj, const int32_t* __restrict__ order,
                double* __restrict__ X, double* __restrict__ Xf_all, int32_t* __restrict__ status_out,
-               int32_t* __restrict__ pivots_out, uint8_t* __restrict__ moved_out, double* __restrict__ pv_out) {
+               uint8_t* __restrict__ moved_out, double* __restrict__ PV, unsigned long long* __restrict__ keys) {
     const int b = blockIdx.x, i = threadIdx.x;
     const QGroup grp = groups[find_group_start(gstarts, ngroups, b)];
     const GaviTabEntry& ent = table[grp.gavi];
@@ -165,7 +260,8 @@ net_qep_kernel(const GaviTabEntry* __restrict__ table, const QGroup* __restrict_
     const int32_t* par = ent.par;
     const int nd_level = ent.nd_level;
     double* Xf = grp.snap ? Xf_all : nullptr;
-    const int slot = inst[b];
+    const int kloc = b - grp.start;
+    const int slot = order[grp.src_off + kloc], d = grp.dst_off + kloc;
     const int dz = g.d1 + g.d2, n = g.d1 + 2 * g.d2;
     const int max_pivots = 50 * n + 100;
     GaviSmem s;
@@ -193,10 +289,10 @@ net_qep_kernel(const GaviTabEntry* __restrict__ table, const QGroup* __restrict_
         moved = !(sqrt(dn) < 1e-4);                       // algorithm.jl:96-97
         if (moved) {
             for (int j = i; j < nv; j += blockDim.x) x[j] = xn[j];
-            for (int k = i; k < nproj; k += blockDim.x) {
+            for (int k = i; k < nproj; k += blockDim.x) {     // what the next cycle check of this instance compares
                 double acc = 0.0;
                 for (int j = 0; j < nv; ++j) acc = fma(xn[j], proj[(size_t)k * nv + j], acc);
-                pv_out[(size_t)b * nproj + k] = acc;
+                PV[(size_t)slot * nproj + k] = acc;
             }
         }
     }
@@ -204,7 +300,11 @@ net_qep_kernel(const GaviTabEntry* __restrict__ table, const QGroup* __restrict_
         const double* src = moved ? xn : xs;
         for (int j = i; j < nv; j += blockDim.x) Xf[(size_t)slot * nv + j] = src[j];
     }
-    if (i == 0) { status_out[b] = st; pivots_out[b] = piv; moved_out[b] = (uint8_t)moved; }
+    if (i == 0) {
+        status_out[d] = st; moved_out[d] = (uint8_t)moved;
+        // answer row: [status: int32 little endian] [moved]
+        keys[d] += qpn_sig_term(0u, (unsigned)st & 0xffu) + qpn_sig_term(1u, ((unsigned)st >> 8) & 0xffu) + qpn_sig_term(4u, (unsigned)moved);
+    }
 }
 
 // pv[b][k] = sum_j x_b[j] proj[k][j] (sequential fma, as the level kernel's cycle check): one thread per (slot, k).
@@ -219,34 +319,112 @@ __global__ void net_proj_kernel(int B, int nv, int nproj, const double* __restri
     pv[gid] = acc;
 }
 
-// x_out[b] = solved[b] ? X[b] : Xf[b]  (what the reference returns as x_opt / x_fail)
+// x_out[b] = solved(result_of[b]) ? X[b] : Xf[b]  (what the reference returns as x_opt / x_fail)
 __global__ void net_select_kernel(int B, int nv, const double* __restrict__ X, const double* __restrict__ Xf,
-                                  const uint8_t* __restrict__ solved, double* __restrict__ x_out) {
+                                  const int32_t* __restrict__ result_of, const uint8_t* __restrict__ solved_of_result, int nresults,
+                                  double* __restrict__ x_out) {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)B * nv) return;
-    x_out[gid] = solved[gid / nv] ? X[gid] : Xf[gid];
+    const int r = result_of[gid / nv];
+    x_out[gid] = (r >= 0 && r < nresults && solved_of_result[r]) ? X[gid] : Xf[gid];
+}
+// a[i] = i (or `fill` when fill >= -1... see callers): start of a batch
+__global__ void net_iota_kernel(int n, int32_t* __restrict__ a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = i;
+}
+__global__ void net_fill_i32_kernel(long long n, int32_t* __restrict__ a, int fill) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = fill;
 }
 
-// One (instance, piece) pair of a membership round.
-struct MemberPair { int32_t inst, piece; };
-
-// One warp per pair; lanes take rows, each dot product sequential in the coordinate index.
-__global__ void net_member_kernel(int npairs, const MemberPair* __restrict__ pairs, const PieceTabEntry* __restrict__ pieces, int nv,
-                                  const double* __restrict__ X, double tol, uint8_t* __restrict__ in_out) {
-    const int warp = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-    if (warp >= npairs) return;
-    const MemberPair pr = pairs[warp];
-    const PieceTabEntry pc = pieces[pr.piece];
-    const double* x = X + (size_t)pr.inst * nv;
+// Membership: one thread per (member, piece) pair of a cohort, consecutive threads = consecutive members of the same
+// piece (the piece's rows are read at one address by the whole warp); each dot product sequential in the coordinate
+// index.  A pair whose piece has no rows is inside.
+__global__ void net_member_kernel(int npairs, const MGroup* __restrict__ groups, const int* __restrict__ gstarts, int ngroups,
+                                  const int32_t* __restrict__ piece_ids, const PieceTabEntry* __restrict__ pieces, int nv,
+                                  const int32_t* __restrict__ order, const double* __restrict__ X, double tol, uint8_t* __restrict__ in_out,
+                                  unsigned long long* __restrict__ keys) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= npairs) return;
+    const MGroup grp = groups[find_group_start(gstarts, ngroups, t)];
+    const int loc = t - grp.start, p = loc / grp.count, k = loc - p * grp.count;
+    const PieceTabEntry pc = pieces[piece_ids[grp.list_off + p]];
+    const double* x = X + (size_t)order[grp.src_off + k] * nv;
     int ok = 1;
-    for (int row = lane; row < pc.m; row += 32) {
+    for (int row = 0; row < pc.m; ++row) {
         const double* a = pc.A + (size_t)row * nv;
         double ax = 0.0;
         for (int j = 0; j < nv; ++j) ax = fma(a[j], x[j], ax);
         if (!((pc.l[row] - tol <= ax) && (ax - tol <= pc.u[row]))) ok = 0;
     }
-    ok = __all_sync(0xffffffffu, ok);
-    if (lane == 0) in_out[warp] = (uint8_t)ok;
+    in_out[grp.out_off + (size_t)k * grp.np + p] = (uint8_t)ok;
+    atomicAdd(keys + grp.dst_off + k, qpn_sig_term((unsigned)p, (unsigned)ok));
+}
+
+// After the segmented sort: position `pos` of the new order holds the member that had index vals[pos] in this round.
+// A position whose signature differs from its predecessor's (or that opens a cohort) starts a part: it takes the next
+// part record and room for one answer row.  hdr[0] = parts, hdr[1] = answer bytes.
+__global__ void net_round_boundary_kernel(const CohortDev* __restrict__ cohorts, const int* __restrict__ cstarts, int ncohorts, int total,
+                                          const unsigned long long* __restrict__ keys_sorted, const int32_t* __restrict__ vals_sorted,
+                                          const int32_t* __restrict__ slot_of, int32_t* __restrict__ order_next, PartDev* __restrict__ parts,
+                                          int* __restrict__ hdr) {
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= total) return;
+    const int ci = find_group_start(cstarts, ncohorts, pos);
+    const CohortDev c = cohorts[ci];
+    const int old = vals_sorted[pos];
+    order_next[pos] = slot_of[old];
+    if (pos == c.dst_off || keys_sorted[pos] != keys_sorted[pos - 1]) {
+        const int q = atomicAdd(hdr, 1);
+        const int off = atomicAdd(hdr + 1, (c.rep_bytes + 7) & ~7);
+        parts[q] = PartDev{pos, ci, old, off};
+    }
+}
+
+// One CTA per part (grid-stride over the parts the boundary kernel counted): the representative's answers, in the layout
+// of Part::rep (csrc/net/netsolver.hpp).
+__global__ void net_round_gather_kernel(const CohortDev* __restrict__ cohorts, const VGroup* __restrict__ vgroups, const MGroup* __restrict__ mgroups,
+                                        const PartDev* __restrict__ parts, const int* __restrict__ hdr, const uint8_t* __restrict__ hit,
+                                        const uint8_t* __restrict__ sol, const int8_t* __restrict__ mask_base, const uint8_t* __restrict__ vcount,
+                                        const uint8_t* __restrict__ vmask_base, const uint8_t* __restrict__ in_bits,
+                                        const int32_t* __restrict__ status, const uint8_t* __restrict__ moved, uint8_t* __restrict__ rep) {
+    const int nparts = hdr[0];
+    for (int q = blockIdx.x; q < nparts; q += gridDim.x) {
+        const PartDev pt = parts[q];
+        const CohortDev c = cohorts[pt.cohort];
+        uint8_t* out = rep + pt.data_off;
+        const int k = pt.old - c.dst_off;
+        if (c.kind == RK_CYCLE) {
+            if (threadIdx.x == 0) out[0] = hit[pt.old];
+        } else if (c.kind == RK_QEP) {
+            if (threadIdx.x == 0) {
+                const int st = status[pt.old];
+                out[0] = (uint8_t)(st & 0xff); out[1] = (uint8_t)((st >> 8) & 0xff); out[2] = (uint8_t)((st >> 16) & 0xff); out[3] = (uint8_t)((st >> 24) & 0xff);
+                out[4] = moved[pt.old]; out[5] = out[6] = out[7] = 0;
+            }
+        } else if (c.kind == RK_MEMBER) {
+            const MGroup g = mgroups[c.first];
+            for (int p = threadIdx.x; p < g.np; p += blockDim.x) out[p] = in_bits[g.out_off + (size_t)k * g.np + p];
+        } else {
+            for (int r = 0; r < c.count; ++r) {
+                const VGroup g = vgroups[c.first + r];
+                uint8_t* o = out + g.rep_off;
+                const int pair = g.start + k;
+                const int s = sol[pair];
+                if (threadIdx.x == 0) { o[0] = (uint8_t)s; o[1 + g.dz] = (s && g.want > 0) ? vcount[pair] : 0; }
+                if (s) {
+                    const int8_t* mk = mask_base + g.mask_off + (size_t)k * g.dz;
+                    for (int j = threadIdx.x; j < g.dz; j += blockDim.x) o[1 + j] = (uint8_t)mk[j];
+                    if (g.want > 0) {
+                        const int nb = (int)vcount[pair] * g.vbytes;
+                        const uint8_t* vm = vmask_base + g.vm_off + (size_t)k * g.want * g.vbytes;
+                        for (int j = threadIdx.x; j < nb; j += blockDim.x) o[2 + g.dz + j] = vm[j];
+                    }
+                }
+            }
+        }
+    }
 }
 
 }  // namespace qpn

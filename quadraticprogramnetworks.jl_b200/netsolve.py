@@ -155,11 +155,11 @@ class NetBinding:
 
     def profile(self):
         """qpn_net_profile: launches / units / summed ms per kernel kind, staged bytes per direction."""
-        o = np.zeros(16)
+        o = np.zeros(24)
         self._f("profile")(self.ptr, o.ctypes.data_as(dp))
-        kinds = ("verify", "solve_qep", "member")
+        kinds = ("verify", "solve_qep", "member", "group", "cycle")
         d = {k: dict(launches=int(o[4 * i]), units=int(o[4 * i + 1]), ms=float(o[4 * i + 2])) for i, k in enumerate(kinds)}
-        d["h2d_bytes"], d["d2h_bytes"] = int(o[12]), int(o[13])
+        d["h2d_bytes"], d["d2h_bytes"] = int(o[20]), int(o[21])
         return d
 
     def piece(self, pid):
