@@ -13,7 +13,7 @@
 // summation orders), so results are bit-equal to the C oracle's.
 #pragma once
 #include "qpn_level.cuh"
-#include "net/vertex_enum.h"
+#include "vertex_enum_warp.cuh"
 #include "net/cycle_check.h"
 
 namespace qpn {
@@ -133,7 +133,7 @@ __global__ void net_cycle_kernel(const CohortDev* __restrict__ cohorts, const in
 
 // grid = all verify requests of a round (every (cohort, node) group back to back), block = roundup32(max over the groups
 // of max(m, nd, 1)).  Dynamic smem: the largest group's verify_solution_kernel layout (Tab(m, m+1) + VerifySmem + x(nv) +
-// qt(nd) + ax(m)) plus the vertex scratch.
+// qt(nd) + ax(m)) plus the vertex scratch (ve_scratch_bytes).
 __global__ void net_verify_kernel(const NodeTabEntry* __restrict__ table, const VGroup* __restrict__ groups,
                                   const int* __restrict__ gstarts, int ngroups, const int32_t* __restrict__ order,
                                   const double* __restrict__ X, double* __restrict__ Xf_all, double tol,
@@ -203,16 +203,19 @@ __global__ void net_verify_kernel(const NodeTabEntry* __restrict__ table, const 
     if (i == 0) { solution_out[b] = (uint8_t)sol; sig += qpn_sig_term(rp, (unsigned)sol); }
     if (want_v > 0) {
         // expand's get_verts (avi_solutions.jl:252-255): the vertices of the node's multiplier polytope at x, enumerated by
-        // one thread (net/vertex_enum.h), then comp_indices at every vertex by all of them -- only the masks of the m
+        // the first warp (vertex_enum_warp.cuh), then comp_indices at every vertex by all threads -- only the masks of the m
         // multiplier rows can differ from the point's own, two rows per output byte
-        double* Vs = ax + m;                              // QPN_VE_MAXV x QPN_VE_MAXA doubles behind the kernel's vectors
-        int* hdr = reinterpret_cast<int*>(Vs + QPN_VE_MAXV * QPN_VE_MAXA);     // [0] vertices, [1] active rows, [2..] their indices
-        if (i == 0) {
+        const VeSmem ve = ve_carve(ax + m, nd);           // behind the kernel's vectors
+        double* Vs = ve.V;
+        int* hdr = ve.hdr;                                // [0] vertices, [1] active rows; their indices in ve.idxA
+        if (i < 32) {
             int nvx = 0, a = 0;
-            if (sol) nvx = qpn_multiplier_vertices(nd, m, node.nv, node.A, node.dec, node.l, node.u, ax, qt, vs.lam_out(), want_v, hdr + 2, &a, Vs);
-            hdr[0] = nvx; hdr[1] = a;
-            vcount_out[b] = (uint8_t)nvx;
-            if (sol) sig += qpn_sig_term(rp + 1u + (unsigned)dz, (unsigned)nvx);
+            if (sol) nvx = multiplier_vertices_warp(ve, nd, m, node.A, node.dec, node.l, node.u, ax, qt, vs.lam_out(), want_v, &a);
+            if (i == 0) {
+                hdr[0] = nvx; hdr[1] = a;
+                vcount_out[b] = (uint8_t)nvx;
+                if (sol) sig += qpn_sig_term(rp + 1u + (unsigned)dz, (unsigned)nvx);
+            }
         }
         QPN_SYNC();
         const int nvx = hdr[0], a = hdr[1], vbytes = (m + 1) >> 1;
@@ -220,7 +223,7 @@ __global__ void net_verify_kernel(const NodeTabEntry* __restrict__ table, const 
         for (int q = 0; q < nvx; ++q) {
             for (int r = i; r < m; r += blockDim.x) lv[r] = 0.0;
             QPN_SYNC();
-            for (int j = i; j < a; j += blockDim.x) lv[hdr[2 + j]] = Vs[q * QPN_VE_MAXA + j];
+            for (int j = i; j < a; j += blockDim.x) lv[ve.idxA[j]] = Vs[q * QPN_VE_MAXA + j];
             QPN_SYNC();
             for (int t = i; t < vbytes; t += blockDim.x) {
                 int packed = 0;
