@@ -325,7 +325,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     net = qpn_b200.setup("robust_avoid_simple", seed=DATA_SEED)
     eng = qpn_b200.Engine(local_rank)                           # raises if libqpn_cuda / the GPU is missing
-    threads = args.threads or max(1, min(12, cpu_cores() // world))
+    threads = args.threads or max(1, min(2, cpu_cores() // world))   # cohorts are split on the device: two streams hide the round trips
     nb = NetBinding(net, eng.lib, "qpn_net_", handle=eng.h, threads=threads)
     Btot, nv, nl, K, W = args.batch, net.n_vars, net.num_levels(), args.steps, args.warmup
     lo, hi = shard_range(Btot, rank, world)
@@ -446,7 +446,8 @@ def main():
         nproj = net.options.num_projections
         dom = max(kern, key=lambda k: kern[k]["ms"])
         # algorithmic HBM bytes per unit of each kernel: slot index + x in (+ x out) + flags / masks / projections
-        alg_unit = {"solve_qep": 4 + 8 * nv + 8 * nv + 9 + 8 * nproj, "verify": 4 + 8 * nv + 1 + 16, "member": 32 + 8 * nv + 1}
+        alg_unit = {"solve_qep": 4 + 8 * nv + 8 * nv + 5 + 8 * nproj + 8, "verify": 4 + 8 * nv + 1 + 16 + 8, "member": 4 + 8 * nv + 1 + 8,
+                    "group": 4 + 4 + 2 * (8 + 4) + 4, "cycle": 4 + 8 * nproj * 2 + 4 + 1 + 8}
         kd = kern[dom]
         per_launch_units = kd["units"] / max(kd["launches"], 1)
         launch_s = kd["ms"] * 1e-3 / max(kd["launches"], 1)
@@ -471,13 +472,14 @@ def main():
             "e2e": {"value": Btot * K / t_e2e, "unit": UNIT, "h2d_bytes_per_step": (pe1["h2d_bytes"] - pe0["h2d_bytes"]) / K,
                     "d2h_bytes_per_step": (pe1["d2h_bytes"] - pe0["d2h_bytes"]) / K,
                     "timing": "host clock around the synchronous C-ABI call (qpn_net_solve_batched), pinned host buffers; bytes counted by the "
-                              "library: inits in, request lists in, flags / masks / statuses out, x and x_fail out (this rank)"},
+                              "library: inits in, round tables in, one representative's answers per cohort part out, x and outcome index out (this rank)"},
             "e2e_pageable": {"value": Btot * reps_page / t_page, "unit": UNIT, "steps": reps_page,
                              "note": "same call with pageable numpy buffers (a Julia Matrix{Float64} is pageable)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_k.get("dram_bytes_per_launch"),
-                         "kernel": {"solve_qep": "net_qep_kernel", "verify": "net_verify_kernel", "member": "net_member_kernel"}[dom],
+                         "kernel": {"solve_qep": "net_qep_kernel", "verify": "net_verify_kernel", "member": "net_member_kernel",
+                                    "group": "net_round_* + cub::DeviceSegmentedSort", "cycle": "net_cycle_kernel"}[dom],
                          "algorithmic_bytes_per_unit": alg_unit[dom], "units_per_launch": per_launch_units,
                          "avg_launch_ms": 1e3 * launch_s, "peak_source": peak_src,
                          "kernel_time_share": {k: (v["ms"] / total_kern_ms if total_kern_ms else 0.0) for k, v in kern.items()},

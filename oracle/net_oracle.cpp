@@ -66,17 +66,20 @@ struct OracleWorker : Worker {
     void mark_done(Seg seg, int result) override { for (int k = 0; k < seg.n; ++k) result_of[order[seg.off + k]] = result; }
 
     // the answers of one member, in the byte layout of Part::rep (netsolver.hpp)
-    void answer_cycle(const Post& p, int slot, uint8_t* out) {
+    // the chain of cycle checks a verify request begins with: 0 = no hit, 1 + level of the first hit
+    uint8_t cycle_chain(const Post& p, int slot) {
         const double* pv = PV.data() + (size_t)slot * nproj;
-        std::vector<double>& h = hist[slot][p.level];
-        bool hit = false;
-        for (size_t q = 0; q + nproj <= h.size() && !hit; q += nproj) hit = qpn_cycle_hit(pv, h.data() + q, nproj);
-        if (!hit) h.insert(h.end(), pv, pv + nproj);
-        out[0] = hit;
+        for (int level = p.cyc_level; level < p.cyc_level + p.ncyc; ++level) {
+            std::vector<double>& h = hist[slot][level];
+            for (size_t q = 0; q + nproj <= h.size(); q += nproj) if (qpn_cycle_hit(pv, h.data() + q, nproj)) return (uint8_t)(1 + level);
+            h.insert(h.end(), pv, pv + nproj);
+        }
+        return 0;
     }
     void answer_verify(const Post& p, int slot, uint8_t* out) {
         const double* x = X.data() + (size_t)slot * nv;
         const int want = p.want_vertices;
+        *out++ = cycle_chain(p, slot);
         for (int r = 0; r < p.nnodes; ++r) {
             const NodeInfo& n = cache->node_info(p.nodes[r]);
             const GaviData& g = n.g;
@@ -163,17 +166,18 @@ struct OracleWorker : Worker {
         for (size_t ci = 0; ci < posts.size(); ++ci) {
             const Post& p = posts[ci];
             size_t rb = 0;
-            if (p.kind == POST_CYCLE) rb = 1;
-            else if (p.kind == POST_QEP) rb = 8;
+            if (p.kind == POST_QEP) rb = 8;
             else if (p.kind == POST_MEMBER) { for (int k = 0; k < p.nlists; ++k) rb += p.piece_lists[k]->size(); }
-            else for (int r = 0; r < p.nnodes; ++r) { const NodeInfo& n = cache->node_info(p.nodes[r]); rb += verify_rep_bytes(n.nd + n.m, n.m, p.want_vertices); }
+            else {
+                rb = 1;
+                for (int r = 0; r < p.nnodes; ++r) { const NodeInfo& n = cache->node_info(p.nodes[r]); rb += verify_rep_bytes(n.nd + n.m, n.m, p.want_vertices); }
+            }
             const size_t stride = rb ? rb : 1;
             rows.assign(stride * p.seg.n, 0);
             for (int k = 0; k < p.seg.n; ++k) {
                 const int slot = order[p.seg.off + k];
                 uint8_t* out = rows.data() + stride * k;
-                if (p.kind == POST_CYCLE) answer_cycle(p, slot, out);
-                else if (p.kind == POST_VERIFY) answer_verify(p, slot, out);
+                if (p.kind == POST_VERIFY) answer_verify(p, slot, out);
                 else if (p.kind == POST_QEP) answer_qep(p, slot, out);
                 else answer_member(p, slot, out);
             }

@@ -506,11 +506,12 @@ struct Frame {                                   // one activation of solve_base
     int gavi = -1;                               // solve_qep phase
 };
 
-enum Wait { W_NONE, W_CYCLE, W_VERIFY, W_MEMBER, W_QEP };
+enum Wait { W_NONE, W_VERIFY, W_MEMBER, W_QEP };
 
 struct Cohort {
     Seg seg;                                     // its members in the worker's order array
     std::vector<Frame> stack;
+    int cyc_level = 0, ncyc = 0;                 // cycle checks that ride with the next verify request (levels cyc_level ..)
     std::vector<int> level_iters;
     Wait wait = W_NONE;
     bool done = false, solved = false;
@@ -545,28 +546,27 @@ struct Machine {
     }
     void fail(Cohort& C, int err) { finish(C, false, err); }
 
-    // ---- algorithm.jl:13-31 --------------------------------------------------------------------------------------------
+    // ---- algorithm.jl:13-39 --------------------------------------------------------------------------------------------
+    // A loop pass begins with the cycle check of its level and, above the last level, with the full recursive solve of
+    // the level below -- whose first pass begins the same way.  Nothing numeric happens until the bottom level's nodes
+    // are verified and x does not change on the way down, so the checks of the whole chain are posted together with
+    // that verify request; if one of them hits, the passes opened below it are taken back (apply()).
     void start_iter(Cohort& C) {
-        Frame& f = C.stack.back();
-        if (f.it == net.max_iters) return fail(C, ERR_MAXIT);
-        f.it++;
-        C.level_iters[f.level]++;
-        if (net.check_for_cycling) {
-            if (net.num_projections == 0) return fail(C, ERR_NOPROJ);
-            C.wait = W_CYCLE;                    // per instance: the backend splits the cohort by the outcome
-            return;
-        }
-        after_cycle(C, false);
-    }
-    void after_cycle(Cohort& C, bool hit) {
-        if (hit) return fail(C, ERR_CYCLE);
-        Frame& f = C.stack.back();
-        f.S.assign(net.nplayers, -1);
-        if (f.level + 1 < net.nlevels) {         // algorithm.jl:32-39: the full recursive solve of the level below
-            Frame child;
+        while (true) {
+            Frame& f = C.stack.back();
+            if (f.it == net.max_iters) return fail(C, ERR_MAXIT);
+            f.it++;
+            C.level_iters[f.level]++;
+            if (net.check_for_cycling) {
+                if (net.num_projections == 0) return fail(C, ERR_NOPROJ);
+                if (C.ncyc == 0) C.cyc_level = f.level;
+                C.ncyc++;
+            }
+            f.S.assign(net.nplayers, -1);
+            if (f.level + 1 >= net.nlevels) break;
+            Frame child;                         // algorithm.jl:32-39: the full recursive solve of the level below
             child.level = f.level + 1;
             C.stack.push_back(std::move(child));
-            return start_iter(C);
         }
         post_verify(C);
     }
@@ -712,10 +712,9 @@ struct Machine {
         Post p;
         p.seg = C.seg;
         switch (C.wait) {
-            case W_CYCLE: p.kind = POST_CYCLE; p.level = f.level; break;
             case W_VERIFY:
                 p.kind = POST_VERIFY; p.nodes = f.req_nodes.data(); p.nnodes = (int)f.req_nodes.size(); p.want_vertices = f.want;
-                p.snap = f.level == 0;
+                p.snap = f.level == 0; p.cyc_level = C.cyc_level; p.ncyc = C.ncyc;
                 break;
             case W_MEMBER:
                 f.comb_lists.clear();
@@ -731,13 +730,18 @@ struct Machine {
         const Wait wt = P.wait;
         P.wait = W_NONE;
         Frame& f = P.stack.back();
-        if (wt == W_CYCLE) return after_cycle(P, rep[0] != 0);
         if (wt == W_MEMBER) return after_member(P, rep);
         if (wt == W_QEP) {
             int32_t status;
             std::memcpy(&status, rep, 4);
             return after_qep(P, status, rep[4] != 0);
         }
+        if (rep[0] != 0) {                       // a cycle check hit at level rep[0] - 1: the passes opened below it never began
+            for (int l = rep[0]; l < P.cyc_level + P.ncyc; ++l) P.level_iters[l]--;
+            return fail(P, ERR_CYCLE);
+        }
+        P.ncyc = 0;
+        ++rep;
         const size_t nr = f.req_nodes.size();
         f.sol.assign(nr, 0);
         f.masks.assign(nr, {});

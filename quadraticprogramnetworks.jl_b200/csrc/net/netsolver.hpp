@@ -78,16 +78,20 @@ struct LevelGaviInfo {
 // per part, its new segment and the answers of ONE representative member.
 struct Seg { int off = 0, n = 0; };
 
-enum PostKind { POST_CYCLE = 0, POST_VERIFY = 1, POST_MEMBER = 2, POST_QEP = 3 };
+enum PostKind { POST_VERIFY = 1, POST_MEMBER = 2, POST_QEP = 3 };
 
 struct Post {
-    int kind = POST_CYCLE;
+    int kind = POST_VERIFY;
     Seg seg;
-    // POST_CYCLE: the cycle check of algorithm.jl:14-30 for the iterate history of (instance, level); a miss appends
-    int level = 0;
     // POST_VERIFY: verify_solution at each instance's x, then comp_indices of the node GAVI at (x, lam), for each of the
     // cohort's nodes; want_vertices > 0: expand's get_verts too (avi_solutions.jl:252-255): up to that many new vertices of
-    // the multiplier polytope and the comp_indices masks of the m multiplier rows at each, two rows per byte
+    // the multiplier polytope and the comp_indices masks of the m multiplier rows at each, two rows per byte.
+    // Before that, the cycle checks the loop passes leading here begin with (algorithm.jl:14-30): levels
+    // cyc_level .. cyc_level + ncyc - 1 in turn, each against the iterate history of (instance, level), a miss appended,
+    // the first hit ends the chain (a new pass of level L opens fresh passes of every level below it before anything is
+    // verified, and x does not change in between, so the checks ride with the verify request instead of costing a
+    // round each)
+    int cyc_level = 0, ncyc = 0;
     const int* nodes = nullptr;
     int nnodes = 0, want_vertices = 0, snap = 0;
     // POST_MEMBER: x in closure(piece) for the pieces of each list (intersection.jl:74,82)
@@ -98,8 +102,8 @@ struct Post {
 };
 
 // Answers of a part's representative, as bytes:
-//   POST_CYCLE : [hit]
-//   POST_VERIFY: per node r: [sol] [mask: dz_r] [vcount] [vmask: want * ceil(m_r / 2)]   (mask / vertices valid when sol)
+//   POST_VERIFY: [cycle: 0 = no hit, 1 + level of the first hit]; per node r: [sol] [mask: dz_r] [vcount]
+//                [vmask: want * ceil(m_r / 2)]   (mask / vertices valid when sol)
 //   POST_MEMBER: per list, per piece: [in]
 //   POST_QEP   : [status: int32] [moved] [3 pad]
 struct Part {

@@ -43,11 +43,12 @@ struct PieceTabEntry {
 // bytes: commutative, so the threads of a launch may add in any order and the sum is deterministic).  net_round_* then
 // sort each cohort's members by signature (cub::DeviceSegmentedSort, stable), cut the sorted segments into parts and
 // copy ONE representative's answers per part; the sorted slots are the next round's order array.
-enum { RK_CYCLE = 0, RK_VERIFY = 1, RK_MEMBER = 2, RK_QEP = 3 };
+enum { RK_VERIFY = 1, RK_MEMBER = 2, RK_QEP = 3 };
 struct CohortDev {
     int kind, src_off, n, dst_off;
     int first, count;                  // verify: its groups in the VGroup table; member: its MGroup, pieces per member
-    int rep_bytes, level;
+    int rep_bytes, cyc_level;          // verify: the cycle checks it begins with: levels cyc_level .. cyc_level + ncyc - 1,
+    int ncyc, log_off, pad0, pad1;     //         their history entries from log_base + log_off (ncyc per member)
 };
 struct VGroup {                        // one (cohort, node) of the verify launch: `count` pairs from pair `start`
     int node, start, count, snap;
@@ -102,33 +103,37 @@ __global__ void net_done_kernel(const DoneDev* __restrict__ done, const int32_t*
     for (int k = threadIdx.x; k < d.n; k += blockDim.x) result_of[order[d.src_off + k]] = d.result;
 }
 
-// The cycle check, one thread per member.  History of (slot, level): a linked list through `prev` in an append-only
-// log (entry e: nproj projections at ent_pv[e * nproj], link ent_prev[e]); a miss appends at log_base + its index in the
-// launch (the host sized the log for every member of the launch).
+// The cycle checks a verify request begins with (algorithm.jl:14-30), one thread per member: levels cyc_level ..
+// cyc_level + ncyc - 1 in turn, the first hit ends the chain.  History of (slot, level): a linked list through `prev` in
+// an append-only log (entry e: nproj projections at ent_pv[e * nproj], link ent_prev[e]); a miss appends at
+// log_base + log_off + member * ncyc + position in the chain (the host sized the log for every member of the launch).
+// hit_out: 0 = no hit, 1 + level of the first hit -- byte 0 of the member's answer row.
 __global__ void net_cycle_kernel(const CohortDev* __restrict__ cohorts, const int* __restrict__ cidx, const int* __restrict__ cycstarts,
-                                 int ncyc, int total, int nlevels, int nproj, const int32_t* __restrict__ slot_of,
+                                 int ncyc_cohorts, int total, int nlevels, int nproj, const int32_t* __restrict__ slot_of,
                                  const double* __restrict__ PV, int32_t* __restrict__ head, double* __restrict__ ent_pv,
                                  int32_t* __restrict__ ent_prev, int log_base, uint8_t* __restrict__ hit_out,
                                  unsigned long long* __restrict__ keys) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
-    const int q = find_group_start(cycstarts, ncyc, t);
+    const int q = find_group_start(cycstarts, ncyc_cohorts, t);
     const CohortDev c = cohorts[cidx[q]];
-    const int d = c.dst_off + (t - cycstarts[q]);
+    const int k = t - cycstarts[q], d = c.dst_off + k;
     const int slot = slot_of[d];
     const double* pv = PV + (size_t)slot * nproj;
-    int32_t* hd = head + (size_t)slot * nlevels + c.level;
-    int hit = 0;
-    // (the reference scans its cache from the oldest entry; "any earlier iterate" does not depend on the order)
-    for (int e = *hd; e >= 0 && !hit; e = ent_prev[e]) hit = qpn_cycle_hit(pv, ent_pv + (size_t)e * nproj, nproj);
-    if (!hit) {
-        const int e = log_base + t;
-        for (int k = 0; k < nproj; ++k) ent_pv[(size_t)e * nproj + k] = pv[k];
+    int code = 0;
+    for (int j = 0; j < c.ncyc && !code; ++j) {
+        int32_t* hd = head + (size_t)slot * nlevels + c.cyc_level + j;
+        int hit = 0;
+        // (the reference scans its cache from the oldest entry; "any earlier iterate" does not depend on the order)
+        for (int e = *hd; e >= 0 && !hit; e = ent_prev[e]) hit = qpn_cycle_hit(pv, ent_pv + (size_t)e * nproj, nproj);
+        if (hit) { code = 1 + c.cyc_level + j; break; }
+        const int e = log_base + c.log_off + k * c.ncyc + j;
+        for (int i = 0; i < nproj; ++i) ent_pv[(size_t)e * nproj + i] = pv[i];
         ent_prev[e] = *hd;
         *hd = e;
     }
-    hit_out[d] = (uint8_t)hit;
-    keys[d] += qpn_sig_term(0u, (unsigned)hit);        // the member's only answer this round: no other thread adds to it
+    hit_out[d] = (uint8_t)code;
+    if (code) atomicAdd(keys + d, qpn_sig_term(0u, (unsigned)code));     // (the verify kernel adds to the same signature)
 }
 
 // grid = all verify requests of a round (every (cohort, node) group back to back), block = roundup32(max over the groups
@@ -398,9 +403,7 @@ __global__ void net_round_gather_kernel(const CohortDev* __restrict__ cohorts, c
         const CohortDev c = cohorts[pt.cohort];
         uint8_t* out = rep + pt.data_off;
         const int k = pt.old - c.dst_off;
-        if (c.kind == RK_CYCLE) {
-            if (threadIdx.x == 0) out[0] = hit[pt.old];
-        } else if (c.kind == RK_QEP) {
+        if (c.kind == RK_QEP) {
             if (threadIdx.x == 0) {
                 const int st = status[pt.old];
                 out[0] = (uint8_t)(st & 0xff); out[1] = (uint8_t)((st >> 8) & 0xff); out[2] = (uint8_t)((st >> 16) & 0xff); out[3] = (uint8_t)((st >> 24) & 0xff);
@@ -410,6 +413,7 @@ __global__ void net_round_gather_kernel(const CohortDev* __restrict__ cohorts, c
             const MGroup g = mgroups[c.first];
             for (int p = threadIdx.x; p < g.np; p += blockDim.x) out[p] = in_bits[g.out_off + (size_t)k * g.np + p];
         } else {
+            if (threadIdx.x == 0) out[0] = c.ncyc > 0 ? hit[pt.old] : 0;
             for (int r = 0; r < c.count; ++r) {
                 const VGroup g = vgroups[c.first + r];
                 uint8_t* o = out + g.rep_off;
