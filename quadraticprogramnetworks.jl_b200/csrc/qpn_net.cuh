@@ -50,11 +50,11 @@ struct CohortDev {
     int rep_bytes, cyc_level;          // verify: the cycle checks it begins with: levels cyc_level .. cyc_level + ncyc - 1,
     int ncyc, log_off, pad0, pad1;     //         their history entries from log_base + log_off (ncyc per member)
 };
-struct VGroup {                        // one (cohort, node) of the verify launch: `count` pairs from pair `start`
-    int node, start, count, snap;
+struct VGroup {                        // one (cohort, node) of a verify launch: `count` pairs from pair `start` of the launch
+    int node, start, count, snap;      // (pair0: index of its first pair among all verify pairs of the round)
     int src_off, dst_off, want, rep_off;   // rep_off: byte offset of this node's answers in the member's answer row
     unsigned mask_off, vm_off;         // byte offsets of the group's rows in the mask / vertex-mask buffers
-    int dz, vbytes;
+    int dz, vbytes, pair0, pad;
 };
 struct QGroup { int gavi, start, count, snap, src_off, dst_off; };
 struct MGroup { int start, count, src_off, dst_off, np, list_off; unsigned out_off; int pad; };   // pairs piece-major: idx = p * count + k
@@ -136,8 +136,9 @@ __global__ void net_cycle_kernel(const CohortDev* __restrict__ cohorts, const in
     if (code) atomicAdd(keys + d, qpn_sig_term(0u, (unsigned)code));     // (the verify kernel adds to the same signature)
 }
 
-// grid = all verify requests of a round (every (cohort, node) group back to back), block = roundup32(max over the groups
-// of max(m, nd, 1)).  Dynamic smem: the largest group's verify_solution_kernel layout (Tab(m, m+1) + VerifySmem + x(nv) +
+// grid = the verify requests of a round that explore vertices, or those that do not ((cohort, node) groups back to back:
+// two launches, so that the requests of the first level do not carry the vertex scratch), block = roundup32(max over the
+// groups of max(m, nd, 1)).  Dynamic smem: the largest group's verify_solution_kernel layout (Tab(m, m+1) + VerifySmem + x(nv) +
 // qt(nd) + ax(m)) plus the vertex scratch (ve_scratch_bytes).
 __global__ void net_verify_kernel(const NodeTabEntry* __restrict__ table, const VGroup* __restrict__ groups,
                                   const int* __restrict__ gstarts, int ngroups, const int32_t* __restrict__ order,
@@ -205,7 +206,8 @@ __global__ void net_verify_kernel(const NodeTabEntry* __restrict__ table, const 
             sig += qpn_sig_term(rp + 1u + (unsigned)r, (unsigned)(uint8_t)mk);
         }
     }
-    if (i == 0) { solution_out[b] = (uint8_t)sol; sig += qpn_sig_term(rp, (unsigned)sol); }
+    const int pair = grp.pair0 + kloc;
+    if (i == 0) { solution_out[pair] = (uint8_t)sol; sig += qpn_sig_term(rp, (unsigned)sol); }
     if (want_v > 0) {
         // expand's get_verts (avi_solutions.jl:252-255): the vertices of the node's multiplier polytope at x, enumerated by
         // the first warp (vertex_enum_warp.cuh), then comp_indices at every vertex by all threads -- only the masks of the m
@@ -218,7 +220,7 @@ __global__ void net_verify_kernel(const NodeTabEntry* __restrict__ table, const 
             if (sol) nvx = multiplier_vertices_warp(ve, nd, m, node.A, node.dec, node.l, node.u, ax, qt, vs.lam_out(), want_v, &a);
             if (i == 0) {
                 hdr[0] = nvx; hdr[1] = a;
-                vcount_out[b] = (uint8_t)nvx;
+                vcount_out[pair] = (uint8_t)nvx;
                 if (sol) sig += qpn_sig_term(rp + 1u + (unsigned)dz, (unsigned)nvx);
             }
         }
@@ -417,7 +419,7 @@ __global__ void net_round_gather_kernel(const CohortDev* __restrict__ cohorts, c
             for (int r = 0; r < c.count; ++r) {
                 const VGroup g = vgroups[c.first + r];
                 uint8_t* o = out + g.rep_off;
-                const int pair = g.start + k;
+                const int pair = g.pair0 + k;
                 const int s = sol[pair];
                 if (threadIdx.x == 0) { o[0] = (uint8_t)s; o[1 + g.dz] = (s && g.want > 0) ? vcount[pair] : 0; }
                 if (s) {

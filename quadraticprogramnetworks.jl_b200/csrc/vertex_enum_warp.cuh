@@ -4,7 +4,7 @@
 //   * the active rows by ballot, the matrix of the slice (G) and its elimination copy (W) in shared memory;
 //   * the rank-revealing elimination with full pivoting as a warp arg-max (ties to the first entry in row-major order,
 //     as the serial scan takes them) and one entry per lane in the update;
-//   * the C(a, r) candidate bases 32 at a time: lane t unranks the (base + t)-th combination in lexicographic order and
+//   * the C(a, r) candidate bases QPN_VE_LANES at a time: lane t unranks the (base + t)-th combination in lexicographic order and
 //     solves its r x r system in its own stretch of shared memory; lane 0 then appends the admissible candidates in
 //     combination order, so the vertices come out in the serial order and the same ones are dropped as duplicates.
 #pragma once
@@ -13,11 +13,12 @@
 namespace qpn {
 
 // doubles of shared memory the routine needs behind V (QPN_VE_MAXV x QPN_VE_MAXA) for nodes with at most nd decision variables
+#define QPN_VE_LANES 16      // candidate bases solved at a time (each needs its own stretch of shared memory)
 __host__ __device__ __forceinline__ int ve_lane_stride(int nd) { return (nd * nd + nd + QPN_VE_MAXA) | 1; }
 __host__ __device__ __forceinline__ size_t ve_scratch_bytes(int nd) {
     if (nd > QPN_VE_MAXND) nd = 0;
     // V, G, W, fE | per-lane Mx, y, cand | idxA, sgn, rowperm, colperm, rows, hdr
-    return 8 * ((size_t)QPN_VE_MAXV * QPN_VE_MAXA + 2 * QPN_VE_MAXND * QPN_VE_MAXA + QPN_VE_MAXND + 32 * (size_t)ve_lane_stride(nd)) +
+    return 8 * ((size_t)QPN_VE_MAXV * QPN_VE_MAXA + 2 * QPN_VE_MAXND * QPN_VE_MAXA + QPN_VE_MAXND + QPN_VE_LANES * (size_t)ve_lane_stride(nd)) +
            4 * (3 * QPN_VE_MAXA + 2 * QPN_VE_MAXND + 8);
 }
 
@@ -42,7 +43,7 @@ __device__ __forceinline__ VeSmem ve_carve(double* base, int nd) {
     s.fE = s.W + QPN_VE_MAXND * QPN_VE_MAXA;
     s.lanes = s.fE + QPN_VE_MAXND;
     s.stride = ve_lane_stride(nd > QPN_VE_MAXND ? 0 : nd);
-    s.idxA = reinterpret_cast<int*>(s.lanes + 32 * s.stride);
+    s.idxA = reinterpret_cast<int*>(s.lanes + QPN_VE_LANES * s.stride);
     s.sgn = s.idxA + QPN_VE_MAXA;
     s.rowperm = s.sgn + QPN_VE_MAXA;
     s.colperm = s.rowperm + QPN_VE_MAXND;
@@ -146,15 +147,15 @@ __device__ __forceinline__ int multiplier_vertices_warp(const VeSmem& s, int nd,
     unsigned freemask = 0;
     for (int k = 0; k < a; ++k) if (s.sgn[k] == 0) freemask |= 1u << k;
     if (__popc(freemask) > r) return 0;
-    // ---- the candidate bases, 32 at a time ------------------------------------------------------------------------------
+    // ---- the candidate bases, QPN_VE_LANES at a time ------------------------------------------------------------------------------
     const int total = ve_binom(a, r);
     double* Mx = s.lanes + lane * s.stride;      // r x r, row stride r
     double* y = Mx + nd * nd;
     double* cand = y + nd;
     int nv_found = 0;
-    for (int base = 0; base < total && nv_found < max_new; base += 32) {
+    for (int base = 0; base < total && nv_found < max_new; base += QPN_VE_LANES) {
         int c = base + lane;
-        bool ok = c < total;
+        bool ok = c < total && lane < QPN_VE_LANES;
         unsigned comb = 0, combmask = 0;         // comb[i] in nibble i
         if (ok) {
             int x = 0;
