@@ -840,6 +840,7 @@ void NetSolver::run_shard(int tid, int lo, int hi, const double* inits, double* 
         // ---- every part of a cohort goes on with a copy of the state and its representative's answers -----------------------
         std::vector<std::unique_ptr<Cohort>> got;
         got.swap(waiting);
+        const auto t_apply = now();
         for (size_t i = 0; i < parts.size();) {
             size_t j = i;
             while (j < parts.size() && parts[j].cohort == parts[i].cohort) ++j;
@@ -856,6 +857,7 @@ void NetSolver::run_shard(int tid, int lo, int hi, const double* inits, double* 
             M.ready.push_back(std::move(C));
             i = j;
         }
+        st.apply_ns += ns(t_apply, now());
     }
     st.host_ns += ns(t_host, now());
     t_host = now();

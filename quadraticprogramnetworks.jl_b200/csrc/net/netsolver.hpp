@@ -138,6 +138,33 @@ struct Store {              // shared by the workers of one net: resident copies
     virtual void new_piece(int id, const Poly& P, Worker* w) = 0;
 };
 
+// Append-only array whose elements never move and can be READ without a lock while one writer appends (the writers
+// are serialised by the cache's mutex; an id reaches a reader only through one of the cache's maps, under that mutex,
+// after the element was constructed).  The state machine reads polys / lists / nodes several times per cohort per round.
+template <class T> class StableVec {
+    static constexpr size_t CH = 1024, MAXCH = 1 << 15;
+    std::unique_ptr<std::atomic<T*>[]> chunks_;
+    std::atomic<size_t> size_{0};
+
+  public:
+    StableVec() : chunks_(new std::atomic<T*>[MAXCH]()) {}
+    StableVec(const StableVec&) = delete;
+    StableVec& operator=(const StableVec&) = delete;
+    ~StableVec() {
+        const size_t n = size_.load();
+        for (size_t i = 0; i < n; ++i) chunks_[i / CH].load()[i % CH].~T();
+        for (size_t c = 0; c * CH < n; ++c) ::operator delete((void*)chunks_[c].load());
+    }
+    size_t size() const { return size_.load(std::memory_order_acquire); }
+    const T& operator[](size_t i) const { return chunks_[i / CH].load(std::memory_order_acquire)[i % CH]; }
+    void push_back(T v) {
+        const size_t i = size_.load(std::memory_order_relaxed);
+        if (i % CH == 0) chunks_[i / CH].store((T*)::operator new(sizeof(T) * CH), std::memory_order_release);
+        new (&chunks_[i / CH].load(std::memory_order_relaxed)[i % CH]) T(std::move(v));
+        size_.store(i + 1, std::memory_order_release);
+    }
+};
+
 // ---- the cache of everything instance-independent -------------------------------------------------------------
 struct VecHash {
     size_t operator()(const std::vector<int>& v) const {
@@ -149,7 +176,7 @@ struct VecHash {
 
 struct Stats {
     std::atomic<long> lps{0}, rounds{0}, requests{0}, calls{0}, pieces{0}, nodes{0}, gavis{0}, collect_miss{0}, combine_miss{0}, cohorts{0};
-    std::atomic<long> host_ns{0}, backend_ns{0};   // summed over worker threads: instance logic / numeric backend (incl. waits)
+    std::atomic<long> host_ns{0}, backend_ns{0}, apply_ns{0};   // summed over worker threads: instance logic / numeric backend (incl. waits)
 };
 
 class GeoCache {
@@ -160,17 +187,17 @@ class GeoCache {
 
     // polyhedra interned by exact content
     int intern_poly(Poly&& P, Worker* w);
-    const Poly& poly(int id) const { std::shared_lock<std::shared_mutex> lk(mu_); return polys_[id]; }
-    int set_id(int id) const { std::shared_lock<std::shared_mutex> lk(mu_); return set_ids_[id]; }
-    int npolys() const { std::shared_lock<std::shared_mutex> lk(mu_); return (int)polys_.size(); }
+    const Poly& poly(int id) const { return polys_[id]; }
+    int set_id(int id) const { return set_ids_[id]; }
+    int npolys() const { return (int)polys_.size(); }
     // lists of polyhedra (solution graphs) interned by their ids
     int intern_list(const std::vector<int>& ids);
-    const std::vector<int>& list(int id) const { std::shared_lock<std::shared_mutex> lk(mu_); return lists_[id]; }
+    const std::vector<int>& list(int id) const { return lists_[id]; }
 
     int node(int pid, const std::vector<int>& pieces, Worker* w);                 // (player, child pieces) -> node id
-    const NodeInfo& node_info(int id) const { std::shared_lock<std::shared_mutex> lk(mu_); return nodes_[id]; }
+    const NodeInfo& node_info(int id) const { return nodes_[id]; }
     int level_gavi(int level, const std::vector<int>& assignment, Worker* w);     // (level, piece per child) -> gavi id
-    const LevelGaviInfo& gavi_info(int id) const { std::shared_lock<std::shared_mutex> lk(mu_); return gavis_[id]; }
+    const LevelGaviInfo& gavi_info(int id) const { return gavis_[id]; }
 
     // geometry, memoised (the LPs run on worker w)
     bool empty(int poly, double tol, Worker* w);                                  // exemplar(P)[0]
@@ -196,14 +223,14 @@ class GeoCache {
     Store* store_;
     mutable std::shared_mutex mu_;
     std::mutex create_mu_;                       // serialises the creation of resident objects
-    std::deque<Poly> polys_;
-    std::deque<int> set_ids_;
+    StableVec<Poly> polys_;
+    StableVec<int> set_ids_;
     std::unordered_map<std::string, int> poly_by_exact_, set_by_key_;
-    std::deque<std::vector<int>> lists_;
+    StableVec<std::vector<int>> lists_;
     std::unordered_map<std::vector<int>, int, VecHash> list_ids_;
-    std::deque<NodeInfo> nodes_;
+    StableVec<NodeInfo> nodes_;
     std::unordered_map<std::vector<int>, int, VecHash> node_ids_;
-    std::deque<LevelGaviInfo> gavis_;
+    StableVec<LevelGaviInfo> gavis_;
     std::unordered_map<std::vector<int>, int, VecHash> gavi_ids_;
     std::unordered_map<uint64_t, char> empty_, subset_;
     std::unordered_map<int, int> remove_subsets_;
