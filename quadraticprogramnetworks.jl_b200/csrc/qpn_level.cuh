@@ -31,6 +31,35 @@ __device__ __forceinline__ double csr_row_dot(const PlanDesc& P, int i, const do
     return acc;
 }
 
+// ---- TMA: the plan's exchanged tableau into the instance's shared-memory tableau ----------------------------------------
+// The swept rows of T0 lie in global memory exactly as the instance keeps them in shared memory (same row stride, rows
+// 0 .. nact-1 back to back), so the start of a solve is ONE bulk asynchronous copy (cp.async.bulk, completion counted in
+// bytes on an mbarrier) issued by one thread; the other threads build the residual, the basis maps and B^-1 r meanwhile
+// and wait on the barrier only where the tableau is first touched.  Used when the tile is large enough to pay for the
+// barrier (QPN_TMA_MIN_BYTES: robust_avoid's levels 5.7 - 40 KB, the synthetic chain's 34 KB; four_player's 640 B keeps
+// the 128-bit copy loop).
+#ifndef QPN_TMA_MIN_BYTES
+#define QPN_TMA_MIN_BYTES 2048
+#endif
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile("{\n .reg .pred p;\n QPN_WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra QPN_DONE_%=;\n bra QPN_WAIT_%=;\n QPN_DONE_%=:\n}"
+                 ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_inval(unsigned long long* bar) {
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // Start of a solve from a plan: same state as tab_start + phase 0 + recompute_tcol + compact_dead.
 // t.l() / t.u() hold the bounds; zb: n doubles of scratch.  Ends with a barrier.
 __device__ __noinline__ void tab_start_plan_core(Tab t, const PlanDesc& P, const double* q, const double* z0, double* zb) {
@@ -38,7 +67,21 @@ __device__ __noinline__ void tab_start_plan_core(Tab t, const PlanDesc& P, const
     const int ldr = t.ldr;
     if (i < n) zb[i] = fmin(fmax(z0[i], t.l()[i]), t.u()[i]);
     const int nact = P.nact;                                      // rows nact .. n-1 are frozen: never copied (read from the plan at the end)
-    if ((reinterpret_cast<uintptr_t>(P.T0) & 15) == 0) {          // ldr is even and T() is 16-byte aligned: 128-bit copies
+    const unsigned tbytes = (unsigned)(nact * ldr) * 8u;          // ldr is even: a multiple of 16
+    unsigned long long* tbar = reinterpret_cast<unsigned long long*>(t.red_d() + 35);
+    const bool aligned = (reinterpret_cast<uintptr_t>(P.T0) & 15) == 0;   // (T() is 16-byte aligned)
+    const bool tma = aligned && tbytes >= QPN_TMA_MIN_BYTES;
+    if (tma) {
+        if (i == 0) {
+            // every earlier access to the tableau buffer by this CTA lies before a barrier this thread has passed; the fence
+            // orders them before the copy engine's writes
+            mbar_init(tbar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(tbar, tbytes);
+            tma_load_1d(t.T(), P.T0, tbytes, tbar);
+        }
+    } else if (aligned) {                                         // 128-bit copies
         const double2* src = reinterpret_cast<const double2*>(P.T0);
         double2* dst = reinterpret_cast<double2*>(t.T());
         for (int e = i; e < (nact * ldr) >> 1; e += blockDim.x) dst[e] = src[e];
@@ -59,6 +102,7 @@ __device__ __noinline__ void tab_start_plan_core(Tab t, const PlanDesc& P, const
         t.colvar()[j] = v; t.colof()[v] = j; t.nbval()[j] = v < n ? zb[v] : 0.0;
     }
     QPN_SYNC();
+    double birv_i = 0.0;
     if (i < n) {
         {
             // The specification skips zero entries of B^-1; with a finite r (finite q, z0 clamped to finite bounds or finite
@@ -73,15 +117,18 @@ __device__ __noinline__ void tab_start_plan_core(Tab t, const PlanDesc& P, const
                 acc = fma(p0, rr[k], acc); acc = fma(p1, rr[k + 1], acc); acc = fma(p2, rr[k + 2], acc); acc = fma(p3, rr[k + 3], acc);
             }
             for (; k < n; ++k) acc = fma(pt[(size_t)k * n], rr[k], acc);
-            if (i < nact) t.T()[(size_t)i * ldr + P.tcol0] = acc;
-            else t.birv()[i] = acc;                       // a frozen row is not in T(): frozen_values picks its entry up here
+            birv_i = acc;
+            if (i >= nact) t.birv()[i] = acc;             // a frozen row is not in T(): frozen_values picks its entry up here
         }
         const int rv = P.rowvar0[i];
         t.rowvar()[i] = rv; t.rowof()[rv] = i;
         t.beta()[i] = rv < n ? zb[rv] : zb[rv - n] - z0[rv - n];      // (a plan may export its rows in another order: go by the variable)
         if (rv < n) t.zst()[rv] = BASIC;            // after the barrier that followed the default marks
     }
+    if (tma) mbar_wait(tbar, 0);                      // the tableau has landed (phase 0 of a barrier initialised in this call)
+    if (i < nact) t.T()[(size_t)i * ldr + P.tcol0] = birv_i;      // the homotopy column replaces the plan's placeholder
     QPN_SYNC();
+    if (tma && i == 0) mbar_inval(tbar);              // the next solve of this CTA initialises it again
 }
 __device__ __forceinline__ void tab_start_plan(Tab& t, const PlanDesc& P, const double* q, const double* z0, double* zb) {
     tab_shape(t, P.n, P.ncol0);
