@@ -484,6 +484,232 @@ int GeoCache::leaves(const std::vector<int>& union_lists, const std::vector<int>
     });
 }
 
+// Iterators.product order: the FIRST iterator varies fastest (qp_processing.jl:169)
+static void julia_product(const std::vector<int>& sizes, std::vector<std::vector<int>>& out) {
+    const size_t n = sizes.size();
+    for (int s : sizes) if (s == 0) return;
+    std::vector<int> idx(n, 0);
+    while (true) {
+        out.push_back(idx);
+        size_t i = 0;
+        while (i < n && ++idx[i] == sizes[i]) { idx[i] = 0; ++i; }
+        if (i == n) break;
+    }
+}
+
+// ---- memoised transitions ---------------------------------------------------------------------------------------
+// process_qp, first phase: every player of the level against every combination of its children's pieces
+int GeoCache::verify_plan(int level, const std::vector<int>& S, Worker* w) {
+    std::vector<int> key;
+    key.reserve(S.size() + 1);
+    key.push_back(level);
+    key.insert(key.end(), S.begin(), S.end());
+    {
+        std::shared_lock<std::shared_mutex> lk(mu_);
+        auto it = plan_ids_.find(key);
+        if (it != plan_ids_.end()) return it->second;
+    }
+    const NetData& net = net_;
+    VerifyPlan P;
+    P.level = level; P.S = S;
+    // solution graphs are built for every level but the first (qp_processing.jl:158); that is where vertices matter
+    const bool gen = level != 0 || net.gen_solution_map;
+    P.want = (gen && net.exploration_vertices > 1) ? std::min(net.exploration_vertices - 1, (int)QPN_VE_MAXV) : 0;
+    for (int pid : net.levels[level]) {
+        VerifyPlan::PV pv;
+        pv.pid = pid; pv.first_req = (int)P.req_nodes.size();
+        const std::vector<int>& ch = net.children[pid];
+        if (!ch.empty()) {
+            std::vector<int> sizes;
+            for (int j : ch) {
+                if (S[j] < 0 || list(S[j]).empty()) { P.error = ERR_UNPOPULATED; break; }
+                sizes.push_back((int)list(S[j]).size());
+            }
+            if (P.error) break;
+            julia_product(sizes, pv.combos);
+            for (const auto& combo : pv.combos) {
+                std::vector<int> pieces;
+                for (size_t k = 0; k < ch.size(); ++k) pieces.push_back(list(S[ch[k]])[combo[k]]);
+                P.req_nodes.push_back(node(pid, pieces, w));
+            }
+        } else {
+            P.req_nodes.push_back(node(pid, {}, w));
+        }
+        P.pvs.push_back(std::move(pv));
+    }
+    P.rep_bytes = 1;
+    for (int nid : P.req_nodes) { const NodeInfo& n = node_info(nid); P.rep_bytes += verify_rep_bytes(n.nd + n.m, n.m, P.want); }
+    std::unique_lock<std::shared_mutex> lk(mu_);
+    auto it = plan_ids_.find(key);
+    if (it != plan_ids_.end()) return it->second;
+    const int id = (int)plans_.size();
+    plans_.push_back(std::move(P));
+    plan_ids_.emplace(std::move(key), id);
+    return id;
+}
+
+// algorithm.jl:84,104-116: the level's graphs (after remove_subsets where the level asks for it) join those from below
+int GeoCache::finish_graphs(const VerifyPlan& P, const std::vector<int>& S_out, Worker* w) {
+    std::vector<int> S = P.S;
+    for (int pid : net_.levels[P.level]) {
+        if (S_out[pid] >= 0 && net_.remove_subsets_at[P.level]) S[pid] = remove_subsets(S_out[pid], w);
+        else S[pid] = S_out[pid];
+    }
+    return intern_list(S);
+}
+
+int GeoCache::verify_outcome(int plan_id, const uint8_t* rep, Worker* w) {
+    const VerifyPlan& P = plan(plan_id);
+    const NetData& net = net_;
+    const size_t nr = P.req_nodes.size();
+    // the key: the answers that matter (flags; masks and vertex masks where a node is at a solution)
+    std::string key((const char*)&plan_id, 4);
+    {
+        const uint8_t* r = rep;
+        for (size_t k = 0; k < nr; ++k) {
+            const NodeInfo& info = node_info(P.req_nodes[k]);
+            const int dz = info.nd + info.m, vbytes = (info.m + 1) / 2;
+            key.push_back((char)r[0]);
+            if (r[0]) {
+                const int nvx = std::min((int)r[1 + dz], P.want);
+                key.append((const char*)r + 1, (size_t)dz);
+                key.push_back((char)nvx);
+                key.append((const char*)r + 2 + dz, (size_t)nvx * vbytes);
+            }
+            r += verify_rep_bytes(dz, info.m, P.want);
+        }
+    }
+    {
+        std::shared_lock<std::shared_mutex> lk(mu_);
+        auto it = outcome_ids_.find(key);
+        if (it != outcome_ids_.end()) return it->second;
+    }
+    // ---- parse ---------------------------------------------------------------------------------------------------------
+    std::vector<uint8_t> sol(nr, 0);
+    std::vector<std::vector<int8_t>> masks(nr), vmasks(nr);
+    for (size_t r = 0; r < nr; ++r) {
+        const NodeInfo& info = node_info(P.req_nodes[r]);
+        const int mrows = info.m, nd = info.nd, dz = nd + mrows, vbytes = (mrows + 1) / 2;
+        const uint8_t* mask = rep + 1;
+        const int nvx = rep[1 + dz];
+        const uint8_t* vmask = rep + 2 + dz;
+        sol[r] = rep[0];
+        rep += verify_rep_bytes(dz, mrows, P.want);
+        if (!sol[r]) continue;
+        masks[r].assign((const int8_t*)mask, (const int8_t*)mask + dz);
+        // a vertex keeps the primal part of the point: only the masks of the m multiplier rows change
+        for (int q = 0; q < nvx && q < P.want; ++q) {
+            const uint8_t* nib = vmask + (size_t)q * vbytes;
+            std::vector<int8_t> vm = masks[r];
+            for (int i = 0; i < mrows; ++i) vm[nd + i] = (int8_t)((nib[i >> 1] >> ((i & 1) * 4)) & 0xf);
+            vmasks[r].insert(vmasks[r].end(), vm.begin(), vm.end());
+        }
+    }
+    VerifyOutcome O;
+    O.plan = plan_id;
+    const int level = P.level;
+    bool equilibrium = true;
+    for (uint8_t s : sol) if (!s) equilibrium = false;
+    auto failed = [&](int err) { O.kind = VerifyOutcome::FAIL; O.error = err; };
+    if (equilibrium) {
+        // ---- process_qp, second phase: solution graphs + combine (qp_processing.jl:189-218,243-291) -----------------
+        O.S_out.assign(net.nplayers, -1);
+        O.kind = VerifyOutcome::DONE;
+        for (const VerifyPlan::PV& pv : P.pvs) {
+            const int pid = pv.pid;
+            const bool gen = level != 0 || net.gen_solution_map;
+            if (!gen) continue;
+            const std::vector<int>& ch = net.children[pid];
+            if (ch.empty()) {
+                bool bad = false;
+                const int lid = collect(P.req_nodes[pv.first_req], masks[pv.first_req], vmasks[pv.first_req], w, &bad);
+                if (bad) { failed(ERR_MASK); break; }
+                if (list(lid).empty()) { failed(ERR_GRAPH_EMPTY); break; }
+                O.S_out[pid] = lid;
+                continue;
+            }
+            std::vector<int> sols;
+            bool bad = false;
+            for (size_t k = 0; k < pv.combos.size() && !bad; ++k) {
+                const int lid = collect(P.req_nodes[pv.first_req + k], masks[pv.first_req + k], vmasks[pv.first_req + k], w, &bad);
+                if (!bad) sols.push_back(remove_subsets(lid, w));
+            }
+            if (bad) { failed(ERR_MASK); break; }
+            if (sols.size() == 1) { O.S_out[pid] = sols[0]; continue; }
+            VerifyOutcome::Comb cb;
+            cb.pid = pid;
+            int total = 0;
+            for (size_t k = 0; k < pv.combos.size(); ++k) {
+                std::vector<int> pieces;
+                for (size_t q = 0; q < ch.size(); ++q) pieces.push_back(list(P.S[ch[q]])[pv.combos[k][q]]);
+                const int region = intersect_all(pieces, w);
+                const std::vector<int>& comp = complement_of(region, w);
+                std::vector<int> combined = list(sols[k]);
+                combined.insert(combined.end(), comp.begin(), comp.end());
+                total += (int)combined.size();
+                cb.red.push_back((int)comp.size());
+                for (int p : combined) if (poly(p).m() > 0) cb.flat.push_back(p);
+                cb.union_lists.push_back(intern_list(combined));
+            }
+            if (cb.union_lists.size() > 3 && total > 20) { failed(ERR_COMBINE); break; }
+            O.combs.push_back(std::move(cb));
+        }
+        if (O.kind != VerifyOutcome::FAIL) {
+            if (!O.combs.empty()) O.kind = VerifyOutcome::MEMBER;
+            else O.S_new = finish_graphs(P, O.S_out, w);
+        }
+    } else {
+        // ---- not an equilibrium: solve_qep with the offending child pieces (algorithm.jl:68-101) -----------------------
+        std::vector<int> kids;
+        for (int p : net.levels[level]) kids.insert(kids.end(), net.children[p].begin(), net.children[p].end());
+        std::sort(kids.begin(), kids.end());
+        kids.erase(std::unique(kids.begin(), kids.end()), kids.end());
+        std::vector<int> assignment(kids.size());
+        for (size_t k = 0; k < kids.size(); ++k) assignment[k] = list(P.S[kids[k]])[0];
+        for (const VerifyPlan::PV& pv : P.pvs) {
+            const std::vector<int>& ch = net.children[pv.pid];
+            if (ch.empty()) continue;
+            for (size_t k = 0; k < pv.combos.size(); ++k) {
+                if (sol[pv.first_req + k]) continue;
+                for (size_t q = 0; q < ch.size(); ++q) {
+                    const size_t pos = std::lower_bound(kids.begin(), kids.end(), ch[q]) - kids.begin();
+                    assignment[pos] = list(P.S[ch[q]])[pv.combos[k][q]];
+                }
+                break;                           // the first combination that fails
+            }
+        }
+        O.kind = VerifyOutcome::QEP;
+        O.gavi = level_gavi(level, assignment, w);
+    }
+    std::unique_lock<std::shared_mutex> lk(mu_);
+    auto it = outcome_ids_.find(key);
+    if (it != outcome_ids_.end()) return it->second;
+    const int id = (int)outcomes_.size();
+    outcomes_.push_back(std::move(O));
+    // (the lists of a stored outcome never move: the membership request points at them)
+    VerifyOutcome& stored = const_cast<VerifyOutcome&>(outcomes_[id]);
+    for (const VerifyOutcome::Comb& cb : stored.combs) stored.comb_lists.push_back(&cb.flat);
+    outcome_ids_.emplace(std::move(key), id);
+    return id;
+}
+
+int GeoCache::member_outcome(int outcome_id, const uint8_t* bits, Worker* w) {
+    const VerifyOutcome& O = outcome(outcome_id);
+    size_t np = 0;
+    for (const VerifyOutcome::Comb& cb : O.combs) np += cb.flat.size();
+    std::string key((const char*)&outcome_id, 4);
+    key.append((const char*)bits, np);
+    return memo(member_ids_, key, [&]() -> int {
+        std::vector<int> S_out = O.S_out;
+        const uint8_t* b = bits;
+        for (const VerifyOutcome::Comb& cb : O.combs) {
+            S_out[cb.pid] = leaves(cb.union_lists, cb.red, std::vector<uint8_t>(b, b + cb.flat.size()), w);
+            b += cb.flat.size();
+        }
+        return finish_graphs(plan(O.plan), S_out, w);
+    });
+}
+
 // =================================================================================================================
 // the cohort state machine (algorithm.jl:1-127 + qp_processing.jl:151-291, explicit and copyable)
 // =================================================================================================================
@@ -491,19 +717,8 @@ namespace {
 
 struct Frame {                                   // one activation of solve_base! at a level
     int level = 0, it = 0;
+    int plan = -1, outcome = -1;                 // memoised: what is being verified, what the answers led to
     std::vector<int> S;                          // per player: list id of its solution graph, -1 = none
-    struct PV { int pid; std::vector<std::vector<int>> combos; int first_req; };
-    std::vector<PV> pvs;                         // verify phase: players and their child-piece combinations
-    std::vector<int> req_nodes;
-    int want = 0;                                // vertices asked for with the verify requests
-    std::vector<uint8_t> sol;                    // answers (uniform over the cohort)
-    std::vector<std::vector<int8_t>> masks;
-    std::vector<std::vector<int8_t>> vmasks;     // per request: masks at the explored vertices, concatenated
-    struct Comb { int pid; std::vector<int> union_lists, red, flat; };
-    std::vector<Comb> combs;                     // combine(): players whose leaves wait for membership bits
-    std::vector<const std::vector<int>*> comb_lists;
-    std::vector<int> S_out;
-    int gavi = -1;                               // solve_qep phase
 };
 
 enum Wait { W_NONE, W_VERIFY, W_MEMBER, W_QEP };
@@ -518,19 +733,6 @@ struct Cohort {
     int error = 0;
     std::vector<int> sol;
 };
-
-// Iterators.product order: the FIRST iterator varies fastest (qp_processing.jl:169)
-static void julia_product(const std::vector<int>& sizes, std::vector<std::vector<int>>& out) {
-    const size_t n = sizes.size();
-    for (int s : sizes) if (s == 0) return;
-    std::vector<int> idx(n, 0);
-    while (true) {
-        out.push_back(idx);
-        size_t i = 0;
-        while (i < n && ++idx[i] == sizes[i]) { idx[i] = 0; ++i; }
-        if (i == n) break;
-    }
-}
 
 struct Machine {
     GeoCache& c;
@@ -571,139 +773,23 @@ struct Machine {
         post_verify(C);
     }
 
-    // ---- process_qp, first phase: every player against every combination of its children's pieces -------------------
+    // ---- process_qp, first phase (memoised: GeoCache::verify_plan) -------------------------------------------------------
     void post_verify(Cohort& C) {
         Frame& f = C.stack.back();
-        f.pvs.clear(); f.req_nodes.clear();
-        for (int pid : net.levels[f.level]) {
-            Frame::PV pv;
-            pv.pid = pid; pv.first_req = (int)f.req_nodes.size();
-            const std::vector<int>& ch = net.children[pid];
-            if (!ch.empty()) {
-                std::vector<int> sizes;
-                for (int j : ch) {
-                    if (f.S[j] < 0 || c.list(f.S[j]).empty()) return fail(C, ERR_UNPOPULATED);
-                    sizes.push_back((int)c.list(f.S[j]).size());
-                }
-                julia_product(sizes, pv.combos);
-                for (const auto& combo : pv.combos) {
-                    std::vector<int> pieces;
-                    for (size_t k = 0; k < ch.size(); ++k) pieces.push_back(c.list(f.S[ch[k]])[combo[k]]);
-                    f.req_nodes.push_back(c.node(pid, pieces, w));
-                }
-            } else {
-                f.req_nodes.push_back(c.node(pid, {}, w));
-            }
-            f.pvs.push_back(std::move(pv));
-        }
-        // solution graphs are built for every level but the first (qp_processing.jl:158); that is where vertices matter
-        const bool gen = f.level != 0 || net.gen_solution_map;
-        f.want = (gen && net.exploration_vertices > 1) ? std::min(net.exploration_vertices - 1, (int)QPN_VE_MAXV) : 0;
+        f.plan = c.verify_plan(f.level, f.S, w);
+        const VerifyPlan& P = c.plan(f.plan);
+        if (P.error) return fail(C, P.error);
         C.wait = W_VERIFY;
     }
 
-    void after_verify(Cohort& C) {
-        Frame& f = C.stack.back();
-        bool equilibrium = true;
-        for (uint8_t s : f.sol) if (!s) equilibrium = false;
-        const int level = f.level;
-        if (equilibrium) {
-            // ---- process_qp, second phase: solution graphs + combine (qp_processing.jl:189-218,243-291) -----------------
-            f.combs.clear();
-            f.S_out.assign(net.nplayers, -1);
-            for (const Frame::PV& pv : f.pvs) {
-                const int pid = pv.pid;
-                const bool gen = level != 0 || net.gen_solution_map;
-                if (!gen) continue;
-                const std::vector<int>& ch = net.children[pid];
-                if (ch.empty()) {
-                    bool bad = false;
-                    const int lid = c.collect(f.req_nodes[pv.first_req], f.masks[pv.first_req], f.vmasks[pv.first_req], w, &bad);
-                    if (bad) return fail(C, ERR_MASK);
-                    if (c.list(lid).empty()) return fail(C, ERR_GRAPH_EMPTY);
-                    f.S_out[pid] = lid;
-                    continue;
-                }
-                std::vector<int> sols;
-                for (size_t k = 0; k < pv.combos.size(); ++k) {
-                    bool bad = false;
-                    const int lid = c.collect(f.req_nodes[pv.first_req + k], f.masks[pv.first_req + k], f.vmasks[pv.first_req + k], w, &bad);
-                    if (bad) return fail(C, ERR_MASK);
-                    sols.push_back(c.remove_subsets(lid, w));
-                }
-                if (sols.size() == 1) { f.S_out[pid] = sols[0]; continue; }
-                Frame::Comb cb;
-                cb.pid = pid;
-                int total = 0;
-                for (size_t k = 0; k < pv.combos.size(); ++k) {
-                    std::vector<int> pieces;
-                    for (size_t q = 0; q < ch.size(); ++q) pieces.push_back(c.list(f.S[ch[q]])[pv.combos[k][q]]);
-                    const int region = c.intersect_all(pieces, w);
-                    const std::vector<int>& comp = c.complement_of(region, w);
-                    std::vector<int> combined = c.list(sols[k]);
-                    combined.insert(combined.end(), comp.begin(), comp.end());
-                    total += (int)combined.size();
-                    cb.red.push_back((int)comp.size());
-                    for (int p : combined) if (c.poly(p).m() > 0) cb.flat.push_back(p);
-                    cb.union_lists.push_back(c.intern_list(combined));
-                }
-                if (cb.union_lists.size() > 3 && total > 20) return fail(C, ERR_COMBINE);
-                f.combs.push_back(std::move(cb));
-            }
-            if (!f.combs.empty()) { C.wait = W_MEMBER; return; }
-            return finish_level(C);
-        }
-        // ---- not an equilibrium: solve_qep with the offending child pieces (algorithm.jl:68-101) -----------------------
-        std::vector<int> kids;
-        for (int p : net.levels[level]) kids.insert(kids.end(), net.children[p].begin(), net.children[p].end());
-        std::sort(kids.begin(), kids.end());
-        kids.erase(std::unique(kids.begin(), kids.end()), kids.end());
-        std::vector<int> assignment(kids.size());
-        for (size_t k = 0; k < kids.size(); ++k) assignment[k] = c.list(f.S[kids[k]])[0];
-        for (const Frame::PV& pv : f.pvs) {
-            const std::vector<int>& ch = net.children[pv.pid];
-            if (ch.empty()) continue;
-            for (size_t k = 0; k < pv.combos.size(); ++k) {
-                if (f.sol[pv.first_req + k]) continue;
-                for (size_t q = 0; q < ch.size(); ++q) {
-                    const size_t pos = std::lower_bound(kids.begin(), kids.end(), ch[q]) - kids.begin();
-                    assignment[pos] = c.list(f.S[ch[q]])[pv.combos[k][q]];
-                }
-                break;                           // the first combination that fails
-            }
-        }
-        f.gavi = c.level_gavi(level, assignment, w);
-        C.wait = W_QEP;
-    }
-
-    void after_member(Cohort& C, const uint8_t* bits) {
-        Frame& f = C.stack.back();
-        for (size_t k = 0; k < f.combs.size(); ++k) {
-            const size_t np = f.combs[k].flat.size();
-            f.S_out[f.combs[k].pid] = c.leaves(f.combs[k].union_lists, f.combs[k].red, std::vector<uint8_t>(bits, bits + np), w);
-            bits += np;
-        }
-        finish_level(C);
-    }
-
-    void finish_level(Cohort& C) {               // algorithm.jl:84,104-116
-        Frame& f = C.stack.back();
-        for (int pid : net.levels[f.level]) {
-            if (f.S_out[pid] >= 0 && net.remove_subsets_at[f.level]) f.S[pid] = c.remove_subsets(f.S_out[pid], w);
-            else f.S[pid] = f.S_out[pid];
-        }
+    // algorithm.jl:104-116: the level is done; its graphs go up
+    void finish_level(Cohort& C, int S_new) {
+        C.stack.back().S = c.list(S_new);
         if (C.stack.size() == 1) return finish(C, true, 0);
-        std::vector<int> S = std::move(f.S);
+        std::vector<int> S = std::move(C.stack.back().S);
         C.stack.pop_back();
         C.stack.back().S = std::move(S);         // S = ret_low.Sol; x = ret_low.x_opt (x is resident: nothing to copy)
         post_verify(C);
-    }
-
-    void after_qep(Cohort& C, int status, bool moved) {
-        // the level and the solver's StatusCode ride in the upper bytes of the error word (triage of unsolved instances)
-        if (status != 1) return fail(C, ERR_AVI | ((status & 0xff) << 8) | ((C.stack.back().level & 0xff) << 16));
-        if (!moved) return fail(C, ERR_DISAGREE);
-        start_iter(C);
     }
 
     // ---- the request a waiting cohort posts, and what it does with a representative's answers ---------------------------
@@ -712,16 +798,18 @@ struct Machine {
         Post p;
         p.seg = C.seg;
         switch (C.wait) {
-            case W_VERIFY:
-                p.kind = POST_VERIFY; p.nodes = f.req_nodes.data(); p.nnodes = (int)f.req_nodes.size(); p.want_vertices = f.want;
+            case W_VERIFY: {
+                const VerifyPlan& P = c.plan(f.plan);
+                p.kind = POST_VERIFY; p.nodes = P.req_nodes.data(); p.nnodes = (int)P.req_nodes.size(); p.want_vertices = P.want;
                 p.snap = f.level == 0; p.cyc_level = C.cyc_level; p.ncyc = C.ncyc;
                 break;
-            case W_MEMBER:
-                f.comb_lists.clear();
-                for (const Frame::Comb& cb : f.combs) f.comb_lists.push_back(&cb.flat);
-                p.kind = POST_MEMBER; p.piece_lists = f.comb_lists.data(); p.nlists = (int)f.comb_lists.size();
+            }
+            case W_MEMBER: {
+                const VerifyOutcome& O = c.outcome(f.outcome);
+                p.kind = POST_MEMBER; p.piece_lists = O.comb_lists.data(); p.nlists = (int)O.comb_lists.size();
                 break;
-            default: p.kind = POST_QEP; p.gavi = f.gavi; p.snap = f.level == 0; break;
+            }
+            default: p.kind = POST_QEP; p.gavi = c.outcome(f.outcome).gavi; p.snap = f.level == 0; break;
         }
         return p;
     }
@@ -730,41 +818,28 @@ struct Machine {
         const Wait wt = P.wait;
         P.wait = W_NONE;
         Frame& f = P.stack.back();
-        if (wt == W_MEMBER) return after_member(P, rep);
+        if (wt == W_MEMBER) return finish_level(P, c.member_outcome(f.outcome, rep, w));
         if (wt == W_QEP) {
             int32_t status;
             std::memcpy(&status, rep, 4);
-            return after_qep(P, status, rep[4] != 0);
+            // the level and the solver's StatusCode ride in the upper bytes of the error word (triage of unsolved instances)
+            if (status != 1) return fail(P, ERR_AVI | ((status & 0xff) << 8) | ((f.level & 0xff) << 16));
+            if (rep[4] == 0) return fail(P, ERR_DISAGREE);           // algorithm.jl:96-97
+            return start_iter(P);
         }
         if (rep[0] != 0) {                       // a cycle check hit at level rep[0] - 1: the passes opened below it never began
             for (int l = rep[0]; l < P.cyc_level + P.ncyc; ++l) P.level_iters[l]--;
             return fail(P, ERR_CYCLE);
         }
         P.ncyc = 0;
-        ++rep;
-        const size_t nr = f.req_nodes.size();
-        f.sol.assign(nr, 0);
-        f.masks.assign(nr, {});
-        f.vmasks.assign(nr, {});
-        for (size_t r = 0; r < nr; ++r) {
-            const NodeInfo& info = c.node_info(f.req_nodes[r]);
-            const int mrows = info.m, nd = info.nd, dz = nd + mrows, vbytes = (mrows + 1) / 2;
-            const uint8_t* mask = rep + 1;
-            const int nvx = rep[1 + dz];
-            const uint8_t* vmask = rep + 2 + dz;
-            f.sol[r] = rep[0];
-            rep += verify_rep_bytes(dz, mrows, f.want);
-            if (!f.sol[r]) continue;
-            f.masks[r].assign((const int8_t*)mask, (const int8_t*)mask + dz);
-            // a vertex keeps the primal part of the point: only the masks of the m multiplier rows change
-            for (int q = 0; q < nvx && q < f.want; ++q) {
-                const uint8_t* nib = vmask + (size_t)q * vbytes;
-                std::vector<int8_t> vm = f.masks[r];
-                for (int i = 0; i < mrows; ++i) vm[nd + i] = (int8_t)((nib[i >> 1] >> ((i & 1) * 4)) & 0xf);
-                f.vmasks[r].insert(f.vmasks[r].end(), vm.begin(), vm.end());
-            }
+        f.outcome = c.verify_outcome(f.plan, rep + 1, w);
+        const VerifyOutcome& O = c.outcome(f.outcome);
+        switch (O.kind) {
+            case VerifyOutcome::FAIL: return fail(P, O.error);
+            case VerifyOutcome::QEP: P.wait = W_QEP; return;
+            case VerifyOutcome::MEMBER: P.wait = W_MEMBER; return;
+            default: return finish_level(P, O.S_new);
         }
-        after_verify(P);
     }
 };
 

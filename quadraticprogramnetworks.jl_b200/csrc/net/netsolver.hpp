@@ -179,6 +179,28 @@ struct Stats {
     std::atomic<long> host_ns{0}, backend_ns{0}, apply_ns{0};   // summed over worker threads: instance logic / numeric backend (incl. waits)
 };
 
+// ---- memoised transitions of the cohort machine ------------------------------------------------------------------
+// What a level asks to have verified is a pure function of (level, solution graphs below it); what follows the answers is
+// a pure function of (that plan, the answers).  Both are memoised like the geometry, so a cohort's step in a round is two
+// hash lookups instead of a walk through the (already memoised) set algebra.
+struct VerifyPlan {                              // process_qp, first phase (qp_processing.jl:151-188)
+    int level = 0, error = 0, want = 0, rep_bytes = 0;
+    struct PV { int pid; std::vector<std::vector<int>> combos; int first_req; };
+    std::vector<PV> pvs;                         // players and their child-piece combinations
+    std::vector<int> req_nodes;                  // one node per (player, combination)
+    std::vector<int> S;                          // the solution graphs it was built for (per player: list id, -1 = none)
+};
+struct VerifyOutcome {                           // what the answers to a plan lead to
+    enum { FAIL = 0, QEP = 1, DONE = 2, MEMBER = 3 };
+    int kind = FAIL, error = 0, plan = 0;
+    int gavi = -1;                               // QEP: the level GAVI with the offending child pieces (algorithm.jl:68-101)
+    int S_new = -1;                              // DONE: list id of the solution graphs with this level's added (algorithm.jl:84,104-116)
+    struct Comb { int pid; std::vector<int> union_lists, red, flat; };
+    std::vector<Comb> combs;                     // MEMBER: players whose leaves wait for membership bits (combine, qp_processing.jl:243-291)
+    std::vector<const std::vector<int>*> comb_lists;
+    std::vector<int> S_out;                      // MEMBER: the graphs that are already final
+};
+
 class GeoCache {
   public:
     GeoCache(const NetData& net, Store* store) : net_(net), store_(store) {}
@@ -217,8 +239,20 @@ class GeoCache {
     int leaves(const std::vector<int>& union_lists, const std::vector<int>& red_lengths, const std::vector<uint8_t>& in_bits,
                Worker* w);
 
+    // memoised transitions
+    int verify_plan(int level, const std::vector<int>& S, Worker* w);
+    const VerifyPlan& plan(int id) const { return plans_[id]; }
+    int verify_outcome(int plan, const uint8_t* answers, Worker* w);          // answers: the rows behind the cycle byte
+    const VerifyOutcome& outcome(int id) const { return outcomes_[id]; }
+    int member_outcome(int outcome, const uint8_t* bits, Worker* w);          // -> list id of the new solution graphs
+
   private:
     template <class Map, class Key, class F> auto memo(Map& map, const Key& key, F&& compute) -> typename Map::mapped_type;
+    int finish_graphs(const VerifyPlan& P, const std::vector<int>& S_out, Worker* w);
+    StableVec<VerifyPlan> plans_;
+    std::unordered_map<std::vector<int>, int, VecHash> plan_ids_;
+    StableVec<VerifyOutcome> outcomes_;
+    std::unordered_map<std::string, int> outcome_ids_, member_ids_;
     const NetData& net_;
     Store* store_;
     mutable std::shared_mutex mu_;
