@@ -105,7 +105,7 @@ inline int net_stats(NetObject* o, int64_t* out) {
     Stats& s = o->solver->cache().stats;
     out[0] = o->launches ? o->launches() : 0;
     out[1] = s.rounds; out[2] = s.requests; out[3] = s.calls; out[4] = s.lps; out[5] = s.pieces; out[6] = s.nodes; out[7] = s.gavis;
-    out[8] = s.collect_miss; out[9] = s.combine_miss; out[10] = s.host_ns; out[11] = s.backend_ns; out[12] = s.cohorts; out[13] = s.apply_ns;
+    out[8] = s.collect_miss; out[9] = s.combine_miss; out[10] = s.host_ns; out[11] = s.backend_ns; out[12] = s.cohorts; out[13] = s.apply_ns; out[14] = s.lps_empty; out[15] = s.lp_calls;
     return 0;
 }
 

@@ -243,17 +243,20 @@ bool GeoCache::empty(int pid, double tol, Worker* w) {
     return memo(empty_, key, [&]() -> char {
         long n = 0;
         const bool e = exemplar_empty(poly(pid), *w, tol, &n);
-        stats.lps += n;
+        stats.lps += n; stats.lps_empty += n; stats.lp_calls += n;
         return (char)e;
     }) != 0;
 }
 
 bool GeoCache::subset(int p1, int p2, Worker* w) {
     return memo(subset_, pair_key(p1, p2), [&]() -> char {
-        long n = 0;
-        const bool s = issubset(poly(p1), poly(p2), *w, 1e-6, &n);
-        stats.lps += n;
-        return (char)s;
+        // the LPs of P2's bounds over P1 in batched calls of 1, 2, 4, ... (issubset_many): a pair that is no subset costs
+        // about what the serial scan of sets.jl:377-407 costs, a pair that is one a handful of launches instead of 2 m
+        long n = 0, calls = 0;
+        std::vector<char> res;
+        issubset_many(poly(p1), {&poly(p2)}, *w, res, 1e-6, &n, &calls);
+        stats.lps += n; stats.lps_subset += n; stats.lp_calls += calls;
+        return res[0];
     }) != 0;
 }
 
@@ -372,7 +375,7 @@ int GeoCache::expand(int node, const std::string& K, Worker* w) {
         for (int j = d - np; j < d; ++j) keep.push_back(j);
         long nl = 0;
         Poly pr = project(piece, keep, *w, &nl);
-        stats.lps += nl;
+        stats.lps += nl; stats.lps_project += nl; stats.lp_calls += nl;
         Rows r;
         r.d = n.nv;
         std::vector<double> a(n.nv);

@@ -176,7 +176,8 @@ struct VecHash {
 
 struct Stats {
     std::atomic<long> lps{0}, rounds{0}, requests{0}, calls{0}, pieces{0}, nodes{0}, gavis{0}, collect_miss{0}, combine_miss{0}, cohorts{0};
-    std::atomic<long> host_ns{0}, backend_ns{0}, apply_ns{0};   // summed over worker threads: instance logic / numeric backend (incl. waits)
+    std::atomic<long> host_ns{0}, backend_ns{0}, apply_ns{0};
+    std::atomic<long> lps_empty{0}, lps_subset{0}, lps_project{0}, lp_calls{0};   // where the LPs of the set algebra come from   // summed over worker threads: instance logic / numeric backend (incl. waits)
 };
 
 // ---- memoised transitions of the cohort machine ------------------------------------------------------------------

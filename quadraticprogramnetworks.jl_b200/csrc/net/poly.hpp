@@ -246,6 +246,11 @@ struct LPBackend {
     virtual ~LPBackend() {}
     // z0, z: d1 + d2 entries.  Returns the StatusCode (1 = SUCCESS).
     virtual int gavi_solve_one(const GaviData& g, const double* w, const double* z0, double* z) = 0;
+    // The same GAVI for `batch` parameter vectors in one call (W: np x batch, Z0 / Z: (d1 + d2) x batch, column-major).
+    virtual void gavi_solve_many(const GaviData& g, int batch, const double* W, const double* Z0, double* Z, int32_t* status) {
+        const int dz = g.d1 + g.d2;
+        for (int b = 0; b < batch; ++b) status[b] = gavi_solve_one(g, W + (size_t)b * g.np, Z0 + (size_t)b * dz, Z + (size_t)b * dz);
+    }
 };
 
 struct LPResult { int status = 0; std::vector<double> x, lam; double obj = 0.0; };
@@ -369,6 +374,76 @@ static inline bool issubset(const Poly& P1, const Poly& P2, LPBackend& be, doubl
             if (res.obj < dirn * bound - tol) return false;
         }
     return true;
+}
+
+// issubset(P1, P2) for several P2 at once (remove_subsets, sets.jl:889-902, asks for every pair of a list): the LPs of the
+// bounds of all P2 share P1's rows, so they go out as batched GAVI solves with the cost vector as the parameter
+// (M = [0 -A'], N = I, o = 0, w = +-a) instead of one launch per bound.  The reference stops at the first bound that
+// fails; here every P2 still in the race contributes its next 1, 2, 4, ... bounds per call, so a pair that is no subset
+// costs about as many LPs as the serial scan and the whole list a handful of launches.  out[k] = P1 subset of P2s[k].
+static inline void issubset_many(const Poly& P1, const std::vector<const Poly*>& P2s, LPBackend& be, std::vector<char>& out,
+                                 double tol = 1e-6, long* lp_count = nullptr, long* call_count = nullptr) {
+    const size_t K = P2s.size();
+    out.assign(K, 1);
+    const int n = P1.d, m = P1.m();
+    // the finite bounds of every P2 in the order of the serial scan
+    struct Bound { int row; double dirn, rhs; };
+    std::vector<std::vector<Bound>> bounds(K);
+    for (size_t k = 0; k < K; ++k) {
+        const Poly& P2 = *P2s[k];
+        for (int i = 0; i < P2.m(); ++i)
+            for (int side = 0; side < 2; ++side) {
+                const double bound = side == 0 ? P2.l[i] : P2.u[i], dirn = side == 0 ? 1.0 : -1.0;
+                if (std::isinf(bound)) continue;
+                bounds[k].push_back({i, dirn, dirn * bound - tol});
+            }
+        if (m == 0 && !bounds[k].empty()) out[k] = 0;
+    }
+    if (m == 0) return;
+    GaviData g;
+    g.d1 = n; g.d2 = m; g.np = n;
+    const int dz = n + m;
+    g.M.assign((size_t)n * dz, 0.0);
+    for (int i = 0; i < m; ++i)
+        for (int j = 0; j < n; ++j) g.M[(size_t)(n + i) * n + j] = -P1.A[(size_t)i * n + j];
+    g.N.assign((size_t)n * n, 0.0);
+    for (int j = 0; j < n; ++j) g.N[(size_t)j * n + j] = 1.0;
+    g.o.assign(n, 0.0);
+    g.l1.assign(n, -INF); g.u1.assign(n, INF);
+    g.A.assign((size_t)m * dz, 0.0);
+    for (int i = 0; i < m; ++i)
+        for (int j = 0; j < n; ++j) g.A[(size_t)j * m + i] = P1.A[(size_t)i * n + j];
+    g.B.assign((size_t)m * n, 0.0);
+    g.l2 = P1.l; g.u2 = P1.u;
+    std::vector<size_t> next(K, 0);
+    std::vector<double> W, Z0, Z;
+    std::vector<int32_t> st;
+    struct Item { int k; double rhs; };
+    std::vector<Item> items;
+    for (size_t chunk = 1;; chunk *= 2) {
+        W.clear(); items.clear();
+        for (size_t k = 0; k < K; ++k) {
+            if (!out[k]) continue;
+            const Poly& P2 = *P2s[k];
+            for (size_t c = 0; c < chunk && next[k] < bounds[k].size(); ++c, ++next[k]) {
+                const Bound& bd = bounds[k][next[k]];
+                for (int j = 0; j < n; ++j) W.push_back(bd.dirn * P2.row(bd.row)[j]);
+                items.push_back({(int)k, bd.rhs});
+            }
+        }
+        if (items.empty()) return;
+        const int B = (int)items.size();
+        Z0.assign((size_t)dz * B, 0.0); Z.assign((size_t)dz * B, 0.0); st.assign(B, 0);
+        be.gavi_solve_many(g, B, W.data(), Z0.data(), Z.data(), st.data());
+        if (lp_count) *lp_count += B;
+        if (call_count) ++*call_count;
+        for (int b = 0; b < B; ++b) {
+            if (st[b] != 1) { out[items[b].k] = 0; continue; }
+            double obj = 0.0;
+            for (int j = 0; j < n; ++j) obj += W[(size_t)b * n + j] * Z[(size_t)b * dz + j];
+            if (obj < items[b].rhs) out[items[b].k] = 0;
+        }
+    }
 }
 
 // ---- projection (replaces sets.jl:501-523) ----------------------------------------------------------------------

@@ -182,7 +182,7 @@ class NetBinding:
         out = np.zeros(16, np.int64)
         self._f("stats")(self.ptr, out.ctypes.data_as(C.POINTER(C.c_int64)))
         names = ["launches", "rounds", "requests", "calls", "lps", "pieces", "nodes", "gavis", "collect_misses", "combine_misses",
-                 "host_ns", "backend_ns", "cohort_splits", "apply_ns"]
+                 "host_ns", "backend_ns", "cohort_splits", "apply_ns", "lps_empty", "lp_calls"]
         return {n: int(v) for n, v in zip(names, out)}
 
     def solve(self, inits, keep_sol=False):
