@@ -1,6 +1,7 @@
 """Triage of the unsolved instances of the full three-level robust_avoid batch: exit reason of
 every instance that does not reach an equilibrium, by level and by the StatusCode the failing solve_qep returned.
-Runs the oracle build of the native state machine (same results as the device: tests/test_gpu_net.py), all host cores.
+Runs the oracle build of the native state machine on all host cores, or -- with QPN_TRIAGE_DEVICE=1 -- the device (same
+results: tests/test_gpu_net.py).
 usage: triage_unsolved.py [B] [data seeds ...]"""
 import collections, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -20,7 +21,12 @@ def main():
     for seed in seeds:
         net = qpn_b200.setup("robust_avoid_simple", seed=seed)
         X = qpn_b200.examples.robust_avoid_batch(net, B, seed=0)
-        r = oracle_net(net, threads=os.cpu_count()).solve_arrays(X)
+        if os.environ.get("QPN_TRIAGE_DEVICE") == "1":
+            from qpn_b200.netsolve import NetBinding
+            eng = qpn_b200.Engine(0)
+            r = NetBinding(net, eng.lib, "qpn_net_", handle=eng.h, threads=2).solve_arrays(X)
+        else:
+            r = oracle_net(net, threads=os.cpu_count()).solve_arrays(X)
         c = collections.Counter(int(e) for e in r["error"][~r["solved"]])
         for code, n in sorted(c.items(), key=lambda kv: -kv[1]):
             low, st, lv = code & 0xff, (code >> 8) & 0xff, (code >> 16) & 0xff
