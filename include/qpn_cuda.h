@@ -15,6 +15,12 @@
  *  - Host entry points copy in/out on the handle's stream and do not retain host
  *    pointers past return.  `_dev` entry points take device pointers of the
  *    handle's device and run asynchronously on the stream given (0 = handle's).
+ *    A handle keeps scratch that is not ordered between streams (plan buffers, the
+ *    tableau workspace of the global-memory path, the staging arena, the cycle-check
+ *    history of a resident level): every `_dev` call on one handle must use the SAME
+ *    stream, and a host-pointer call on that handle may only follow once that stream
+ *    has been synchronised.  Concurrent streams need one handle each (they are cheap:
+ *    the network path creates one per host thread).
  *  - One handle per GPU; calls on one handle must be serialised by the caller.
  *  - There is no CPU fallback: without a usable CUDA device qpn_create fails.
  */
