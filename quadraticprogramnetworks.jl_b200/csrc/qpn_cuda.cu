@@ -77,6 +77,12 @@ static inline int roundup32(int n) { return n < 32 ? 32 : ((n + 31) / 32) * 32; 
 
 // Kernels that pivot are instantiated per block-size bucket so that __launch_bounds__ can cap the
 // registers at 768 resident threads per SM (24 CTAs of 32 threads: one wave for 4,096 instances / 148 SMs... nearly).
+// The dynamic shared-memory limit of a kernel is an attribute of the FUNCTION, shared by every host thread of the
+// process: handles of different threads launch the same kernels with different sizes, so a per-launch value would race
+// (thread A raises the limit, thread B lowers it, A's launch fails with "invalid argument").  Every launch that needs more
+// than the default 48 KB therefore sets the same value: the device's opt-in maximum.
+static int g_smem_cap = 0;
+static inline int qpn_smem_cap() { return g_smem_cap; }
 #define QPN_LAUNCH_BUCKETED(KERNEL, threads, grid, smem, stream, ...)                                            \
     do {                                                                                                         \
         const int thr_ = (threads);                                                                              \
@@ -87,7 +93,7 @@ static inline int roundup32(int n) { return n < 32 ? 32 : ((n + 31) / 32) * 32; 
     } while (0)
 #define QPN_LAUNCH_ONE(KINST, thr, grid, smem, stream, ...)                                                      \
     do {                                                                                                         \
-        if ((smem) > 48 * 1024) CK(cudaFuncSetAttribute(KINST, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))); \
+        if ((smem) > 48 * 1024) CK(cudaFuncSetAttribute(KINST, cudaFuncAttributeMaxDynamicSharedMemorySize, qpn_smem_cap())); \
         KINST<<<(grid), (thr), (smem), (stream)>>>(__VA_ARGS__);                                                 \
     } while (0)
 
@@ -109,6 +115,7 @@ extern "C" int qpn_create(int device, qpn_handle** out) {
     h = new qpn_handle();
     h->device = device;
     h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    g_smem_cap = h->max_smem_optin;                  // (every handle of the process sits on the same kind of device)
     h->sm_count = prop.multiProcessorCount;
     if ((e = cudaSetDevice(device)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
@@ -306,7 +313,7 @@ static int build_plan(qpn_handle* h, const GaviDesc& g, int kind, PlanDesc* out,
         }
         b = h->plan_buf[kind];
     }
-    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(plan_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(plan_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, qpn_smem_cap()));
     plan_build_kernel<<<1, roundup32((int)n), smem, h->stream>>>(g, kind, (double*)(b + oT0), (double*)(b + oPT), (int*)(b + orv), (int*)(b + ocv),
                                                                   (int*)(b + optr), (int*)(b + ocol), (double*)(b + oval), (int*)(b + ocols),
                                                                   (int*)(b + ohdr));
@@ -347,7 +354,7 @@ static int build_plan_avi(qpn_handle* h, int n_, const MatDesc& M, const double*
         h->plan_buf_bytes[0] = 2 * (need + 256);
     }
     unsigned char* b = h->plan_buf[0];
-    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(plan_build_avi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(plan_build_avi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, qpn_smem_cap()));
     plan_build_avi_kernel<<<1, roundup32(n_), smem, h->stream>>>(n_, M, l, u, (double*)(b + oT0), (double*)(b + oPT), (int*)(b + orv),
                                                                   (int*)(b + ocv), (int*)(b + optr), (int*)(b + ocol), (double*)(b + oval),
                                                                   (int*)(b + ohdr));
@@ -389,7 +396,7 @@ static int big_grid_ex(qpn_handle* h, K kernel, int nmax, size_t slot_doubles, s
     smem = ((smem + 15) & ~(size_t)15) + 8 * (size_t)QPN_BIG_PEND * row_stride(nmax + 1);
     if (smem > (size_t)h->max_smem_optin) smem = (size_t)h->max_smem_optin;
     *smem_io = smem;
-    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, qpn_smem_cap()));
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, QPN_BIG_THREADS, smem));
     if (per_sm < 1) return fail(h, "big path: kernel does not fit an SM (n=%d, %zu B shared memory)", nmax, smem);
@@ -723,7 +730,7 @@ extern "C" int qpn_halfspace_in_batched(qpn_handle* h, int npoly, int d, int mto
     const size_t smem_t = 8 * (size_t)d * HS_TP + 4 * (size_t)HS_TP * npoly + 4 * (size_t)mtot;
     if (npts >= 2 * HS_TP && smem_t <= (size_t)h->max_smem_optin) {
         // many points: point tiles x all rows, matrix entries reused across 16 points in registers
-        if (smem_t > 48 * 1024) CK(cudaFuncSetAttribute(halfspace_in_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+        if (smem_t > 48 * 1024) CK(cudaFuncSetAttribute(halfspace_in_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, qpn_smem_cap()));
         int tthreads = roundup32(mtot);                    // one row per thread when the rows fit one pass
         if (tthreads < 64) tthreads = 64;
         if (tthreads > 512) tthreads = 512;
