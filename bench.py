@@ -226,6 +226,30 @@ def extras(qpn_b200, torch, eng, dev, stream, flush, rank):
         run = lambda: lv.solve_dev(B, xd.data_ptr(), xo.data_ptr(), so.data_ptr(), io.data_ptr(), po.data_ptr(), None, stream.cuda_stream)
         return solver, lv, run, so, po
 
+    # BASELINE configs[3] END TO END at the node size whose solution graphs are tractable: the synthetic 3-level chain with 6
+    # variables per node (26 variables), 4,096 instances through qpn_net_solve_batched (host buffers, host clock)
+    try:
+        from qpn_b200.netsolve import NetBinding
+        ch = qpn_b200.setup("synthetic_chain", n=6, levels=3, n_params=8)
+        B = 4096
+        Xc = np.tile(ch.default_initialization, (B, 1)) + np.random.default_rng([0xB200, rank, 3]).normal(size=(B, ch.n_vars))
+        nbc = NetBinding(ch, eng.lib, "qpn_net_", handle=eng.h, threads=2)
+        t0 = time.perf_counter(); nbc.solve_arrays(Xc); cold = time.perf_counter() - t0
+        nbc.solve_arrays(Xc)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            rc = nbc.solve_arrays(Xc)
+        tw = (time.perf_counter() - t0) / 3
+        extra["synthetic_chain_end_to_end_n6"] = {"value": B / tw, "unit": UNIT, "batch": B, "ms_per_solve": 1e3 * tw, "cold_first_solve_s": cold,
+                                                  "solved_fraction": float(rc["solved"].mean()),
+                                                  "mean_passes_per_level": rc["level_iters"].mean(0).round(2).tolist(),
+                                                  "note": "three levels x 6 variables per node + 8 parameters, solve(qpn, inits) end to end (the whole "
+                                                          "recursion, solution graphs included); the first solve of a net also builds and memoises its "
+                                                          "geometry (cold_first_solve_s); n = 64 per node is out of reach for the solution graphs"}
+        nbc.close()
+    except Exception as e:                                  # noqa: BLE001
+        extra["synthetic_chain_end_to_end_n6"] = {"error": str(e)[:200]}
+
     # BASELINE configs[1]: four_player_matrix_game, 4,096 random initialisations, one fused level launch
     try:
         fp = qpn_b200.setup("four_player_matrix_game")

@@ -85,3 +85,19 @@ def test_device_pointer_entry_equals_host_entry(engine):
     assert (~host["solved"]).any() and host["solved"].any()
     prof = nb.profile()
     assert prof["verify"]["launches"] > 0 and prof["solve_qep"]["launches"] > 0 and prof["h2d_bytes"] > 0
+
+
+def test_synthetic_chain_end_to_end_device_equals_oracle(engine):
+    """BASELINE configs[3] end to end at the node sizes whose solution graphs are tractable (three levels, 4 variables per
+    node + 8 parameters): the whole recursion on the device against the oracle build, instance by instance.  The LPs of
+    its geometry reach sizes whose kernels need more than 48 KB of shared memory from TWO host threads at once -- the
+    case in which a per-launch value of the kernels' shared-memory attribute used to race."""
+    net = qpn_b200.setup("synthetic_chain", n=4, levels=3, n_params=8)
+    rng = np.random.default_rng(4)
+    X = np.tile(net.default_initialization, (96, 1)) + rng.normal(size=(96, net.n_vars))
+    nb = cuda_net(net, engine, threads=2)
+    dev = nb.solve(X, keep_sol=True)
+    ref = oracle_net(net, threads=4).solve(X, keep_sol=True)
+    bad = [b for b, (a, r) in enumerate(zip(dev, ref)) if not same_result(a, r, sol=True)]
+    assert not bad, (len(bad), bad[:8])
+    assert np.mean([r["solved"] for r in dev]) > 0.8
