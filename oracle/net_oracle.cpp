@@ -76,7 +76,7 @@ struct OracleWorker : Worker {
         }
         return 0;
     }
-    void answer_verify(const Post& p, int slot, uint8_t* out) {
+    void answer_verify(const Post& p, int slot, uint8_t* out, int snap) {
         const double* x = X.data() + (size_t)slot * nv;
         const int want = p.want_vertices;
         *out++ = cycle_chain(p, slot);
@@ -125,7 +125,7 @@ struct OracleWorker : Worker {
                     }
                 }
             }
-            if (p.snap) std::memcpy(Xf.data() + (size_t)slot * nv, x, sizeof(double) * nv);
+            if (snap) std::memcpy(Xf.data() + (size_t)slot * nv, x, sizeof(double) * nv);
             out += verify_rep_bytes(dz, n.m, want);
         }
     }
@@ -155,6 +155,8 @@ struct OracleWorker : Worker {
         if (p.snap) std::memcpy(Xf.data() + (size_t)slot * nv, x, sizeof(double) * nv);
         std::memcpy(out, &status, 4);
         out[4] = moved;
+        // the verify request that rides along (netsolver.hpp): answered where the solve succeeded and moved
+        if (p.nnodes > 0 && status == 1 && moved) answer_verify(p, slot, out + 8, p.vsnap);
     }
     void answer_member(const Post& p, int slot, uint8_t* out);
 
@@ -166,7 +168,13 @@ struct OracleWorker : Worker {
         for (size_t ci = 0; ci < posts.size(); ++ci) {
             const Post& p = posts[ci];
             size_t rb = 0;
-            if (p.kind == POST_QEP) rb = 8;
+            if (p.kind == POST_QEP) {
+                rb = 8;
+                if (p.nnodes > 0) {
+                    rb += 1;
+                    for (int r = 0; r < p.nnodes; ++r) { const NodeInfo& n = cache->node_info(p.nodes[r]); rb += verify_rep_bytes(n.nd + n.m, n.m, p.want_vertices); }
+                }
+            }
             else if (p.kind == POST_MEMBER) { for (int k = 0; k < p.nlists; ++k) rb += p.piece_lists[k]->size(); }
             else {
                 rb = 1;
@@ -177,7 +185,7 @@ struct OracleWorker : Worker {
             for (int k = 0; k < p.seg.n; ++k) {
                 const int slot = order[p.seg.off + k];
                 uint8_t* out = rows.data() + stride * k;
-                if (p.kind == POST_VERIFY) answer_verify(p, slot, out);
+                if (p.kind == POST_VERIFY) answer_verify(p, slot, out, p.snap);
                 else if (p.kind == POST_QEP) answer_qep(p, slot, out);
                 else answer_member(p, slot, out);
             }

@@ -742,8 +742,11 @@ struct Machine {
     const NetData& net;
     Worker* w;
     std::vector<std::unique_ptr<Cohort>> ready;  // to be looked at by the driver
+    int bottom_plan = -1;                        // what the first pass of the bottom level verifies (no graphs below it)
 
-    Machine(GeoCache& cc, Worker* ww) : c(cc), net(cc.net()), w(ww) {}
+    Machine(GeoCache& cc, Worker* ww) : c(cc), net(cc.net()), w(ww) {
+        bottom_plan = c.verify_plan(net.nlevels - 1, std::vector<int>(net.nplayers, -1), w);
+    }
 
     void finish(Cohort& C, bool solved, int err) {
         C.done = true; C.solved = solved; C.error = err; C.wait = W_NONE;
@@ -812,7 +815,18 @@ struct Machine {
                 p.kind = POST_MEMBER; p.piece_lists = O.comb_lists.data(); p.nlists = (int)O.comb_lists.size();
                 break;
             }
-            default: p.kind = POST_QEP; p.gavi = c.outcome(f.outcome).gavi; p.snap = f.level == 0; break;
+            default: {
+                p.kind = POST_QEP; p.gavi = c.outcome(f.outcome).gavi; p.snap = f.level == 0;
+                // after a successful solve: start_iter() at this level, i.e. the cycle checks of levels f.level .. last and the
+                // bottom level's verify request -- posted now, answered in the same round
+                const VerifyPlan& P = c.plan(bottom_plan);
+                if (!P.error) {
+                    p.nodes = P.req_nodes.data(); p.nnodes = (int)P.req_nodes.size(); p.want_vertices = P.want;
+                    p.vsnap = net.nlevels == 1;
+                    if (net.check_for_cycling && net.num_projections > 0) { p.cyc_level = f.level; p.ncyc = net.nlevels - f.level; }
+                }
+                break;
+            }
         }
         return p;
     }
@@ -828,8 +842,17 @@ struct Machine {
             // the level and the solver's StatusCode ride in the upper bytes of the error word (triage of unsolved instances)
             if (status != 1) return fail(P, ERR_AVI | ((status & 0xff) << 8) | ((f.level & 0xff) << 16));
             if (rep[4] == 0) return fail(P, ERR_DISAGREE);           // algorithm.jl:96-97
-            return start_iter(P);
+            start_iter(P);
+            // the verify request start_iter() arrived at was answered in the same round (make_post)
+            if (P.done || P.wait != W_VERIFY || P.stack.back().plan != bottom_plan || c.plan(bottom_plan).error) return;
+            P.wait = W_NONE;
+            return apply_verify(P, rep + 8);
         }
+        apply_verify(P, rep);
+    }
+
+    void apply_verify(Cohort& P, const uint8_t* rep) {
+        Frame& f = P.stack.back();
         if (rep[0] != 0) {                       // a cycle check hit at level rep[0] - 1: the passes opened below it never began
             for (int l = rep[0]; l < P.cyc_level + P.ncyc; ++l) P.level_iters[l]--;
             return fail(P, ERR_CYCLE);

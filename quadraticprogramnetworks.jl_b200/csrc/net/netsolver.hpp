@@ -97,15 +97,19 @@ struct Post {
     // POST_MEMBER: x in closure(piece) for the pieces of each list (intersection.jl:74,82)
     const std::vector<int>* const* piece_lists = nullptr;
     int nlists = 0;
-    // POST_QEP: solve_qep for a level GAVI; on success (and a move of >= 1e-4) x[dec] is replaced
-    int gavi = 0;
+    // POST_QEP: solve_qep for a level GAVI; on success (and a move of >= 1e-4) x[dec] is replaced.  What follows a
+    // successful solve is known in advance -- the next loop pass of the level opens passes of every level below it and ends
+    // up verifying the bottom level's nodes at the new x -- so that verify request (nodes / nnodes / want_vertices, its
+    // cycle checks cyc_level / ncyc, vsnap in place of snap) rides along when nnodes > 0 and is answered for the members
+    // whose solve succeeded and moved
+    int gavi = 0, vsnap = 0;
 };
 
 // Answers of a part's representative, as bytes:
 //   POST_VERIFY: [cycle: 0 = no hit, 1 + level of the first hit]; per node r: [sol] [mask: dz_r] [vcount]
 //                [vmask: want * ceil(m_r / 2)]   (mask / vertices valid when sol)
 //   POST_MEMBER: per list, per piece: [in]
-//   POST_QEP   : [status: int32] [moved] [3 pad]
+//   POST_QEP   : [status: int32] [moved] [3 pad], then (nnodes > 0) the POST_VERIFY answers of the request that rides along
 struct Part {
     int cohort = 0;                              // index of the post within the round
     Seg seg;                                     // the part's segment in the NEW order

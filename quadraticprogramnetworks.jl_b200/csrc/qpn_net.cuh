@@ -48,13 +48,14 @@ struct CohortDev {
     int kind, src_off, n, dst_off;
     int first, count;                  // verify: its groups in the VGroup table; member: its MGroup, pieces per member
     int rep_bytes, cyc_level;          // verify: the cycle checks it begins with: levels cyc_level .. cyc_level + ncyc - 1,
-    int ncyc, log_off, pad0, pad1;     //         their history entries from log_base + log_off (ncyc per member)
-};
+    int ncyc, log_off, cyc_pos, pad1;  //         their history entries from log_base + log_off (ncyc per member), the offset of
+};                                     //         their byte in the answer row.  A solve_qep cohort may carry the verify request
+                                       //         that follows a successful solve (first / count / cyc_* as for verify; cyc_pos = 8)
 struct VGroup {                        // one (cohort, node) of a verify launch: `count` pairs from pair `start` of the launch
     int node, start, count, snap;      // (pair0: index of its first pair among all verify pairs of the round)
     int src_off, dst_off, want, rep_off;   // rep_off: byte offset of this node's answers in the member's answer row
     unsigned mask_off, vm_off;         // byte offsets of the group's rows in the mask / vertex-mask buffers
-    int dz, vbytes, pair0, pad;
+    int dz, vbytes, pair0, gate;       // gate: answered only where the cohort's solve_qep of this round succeeded and moved
 };
 struct QGroup { int gavi, start, count, snap, src_off, dst_off; };
 struct MGroup { int start, count, src_off, dst_off, np, list_off; unsigned out_off; int pad; };   // pairs piece-major: idx = p * count + k
@@ -112,12 +113,14 @@ __global__ void net_cycle_kernel(const CohortDev* __restrict__ cohorts, const in
                                  int ncyc_cohorts, int total, int nlevels, int nproj, const int32_t* __restrict__ slot_of,
                                  const double* __restrict__ PV, int32_t* __restrict__ head, double* __restrict__ ent_pv,
                                  int32_t* __restrict__ ent_prev, int log_base, uint8_t* __restrict__ hit_out,
-                                 unsigned long long* __restrict__ keys) {
+                                 unsigned long long* __restrict__ keys, const int32_t* __restrict__ qep_status,
+                                 const uint8_t* __restrict__ qep_moved) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
     const int q = find_group_start(cycstarts, ncyc_cohorts, t);
     const CohortDev c = cohorts[cidx[q]];
     const int k = t - cycstarts[q], d = c.dst_off + k;
+    if (c.kind == RK_QEP && !(qep_status[d] == 1 && qep_moved[d])) { hit_out[d] = 0; return; }   // no new pass begins
     const int slot = slot_of[d];
     const double* pv = PV + (size_t)slot * nproj;
     int code = 0;
@@ -133,7 +136,7 @@ __global__ void net_cycle_kernel(const CohortDev* __restrict__ cohorts, const in
         *hd = e;
     }
     hit_out[d] = (uint8_t)code;
-    if (code) atomicAdd(keys + d, qpn_sig_term(0u, (unsigned)code));     // (the verify kernel adds to the same signature)
+    if (code) atomicAdd(keys + d, qpn_sig_term((unsigned)c.cyc_pos, (unsigned)code));     // (other kernels add to the same signature)
 }
 
 // grid = the verify requests of a round that explore vertices, or those that do not ((cohort, node) groups back to back:
@@ -145,9 +148,17 @@ __global__ void net_verify_kernel(const NodeTabEntry* __restrict__ table, const 
                                   const double* __restrict__ X, double* __restrict__ Xf_all, double tol,
                                   uint8_t* __restrict__ solution_out, int8_t* __restrict__ mask_base,
                                   uint8_t* __restrict__ vcount_out, uint8_t* __restrict__ vmask_base,
-                                  unsigned long long* __restrict__ keys) {
+                                  unsigned long long* __restrict__ keys, const int32_t* __restrict__ qep_status,
+                                  const uint8_t* __restrict__ qep_moved) {
     const int b = blockIdx.x, i = threadIdx.x;
     const VGroup grp = groups[find_group_start(gstarts, ngroups, b)];
+    if (grp.gate) {                                       // rides with a solve_qep: only where it succeeded and moved
+        const int d = grp.dst_off + (b - grp.start);
+        if (!(qep_status[d] == 1 && qep_moved[d])) {
+            if (i == 0) { solution_out[grp.pair0 + (b - grp.start)] = 0; if (grp.want > 0) vcount_out[grp.pair0 + (b - grp.start)] = 0; }
+            return;
+        }
+    }
     const NodeTabEntry& ent = table[grp.node];
     const NodeDesc node = ent.node;
     const GaviDesc g = ent.g;
@@ -411,11 +422,12 @@ __global__ void net_round_gather_kernel(const CohortDev* __restrict__ cohorts, c
                 out[0] = (uint8_t)(st & 0xff); out[1] = (uint8_t)((st >> 8) & 0xff); out[2] = (uint8_t)((st >> 16) & 0xff); out[3] = (uint8_t)((st >> 24) & 0xff);
                 out[4] = moved[pt.old]; out[5] = out[6] = out[7] = 0;
             }
-        } else if (c.kind == RK_MEMBER) {
+        }
+        if (c.kind == RK_MEMBER) {
             const MGroup g = mgroups[c.first];
             for (int p = threadIdx.x; p < g.np; p += blockDim.x) out[p] = in_bits[g.out_off + (size_t)k * g.np + p];
-        } else {
-            if (threadIdx.x == 0) out[0] = c.ncyc > 0 ? hit[pt.old] : 0;
+        } else if (c.kind == RK_VERIFY || c.count > 0) {     // a verify request, alone or behind a solve_qep
+            if (threadIdx.x == 0) out[c.cyc_pos] = c.ncyc > 0 ? hit[pt.old] : 0;
             for (int r = 0; r < c.count; ++r) {
                 const VGroup g = vgroups[c.first + r];
                 uint8_t* o = out + g.rep_off;
