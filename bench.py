@@ -41,8 +41,8 @@ L2_NOTE = "GPU arm: flushed between steps (256 MB write); CPU arm: not applicabl
 DATA_SEED = 3
 HBM_FALLBACK_GBS = 6650.0     # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 SM_COUNT = 148
-# ncu --set full captures of the two pivoting kernels of the headline (profiles/r2_*): DRAM bytes (read + write) and
-# shared-memory wavefronts per launch at the launch sizes named there; None until captured
+# ncu --set full captures of the two dominant kernels of the headline (profiles/r2_*): DRAM bytes (read + write),
+# shared-memory wavefronts and warp instructions per unit at the launch sizes named there
 NCU = {}
 try:
     with open(os.path.join(ROOT, "profiles", "r2_ncu_constants.json")) as _f:
@@ -501,7 +501,7 @@ def main():
                              "note": "same call with pageable numpy buffers (a Julia Matrix{Float64} is pageable)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_k.get("dram_bytes_per_launch"),
+                         "traffic": (ncu_k["dram_bytes_per_unit"] * per_launch_units) if ncu_k.get("dram_bytes_per_unit") else None,
                          "kernel": {"solve_qep": "net_qep_kernel", "verify": "net_verify_kernel", "member": "net_member_kernel",
                                     "group": "net_round_* + cub::DeviceSegmentedSort", "cycle": "net_cycle_kernel"}[dom],
                          "algorithmic_bytes_per_unit": alg_unit[dom], "units_per_launch": per_launch_units,
@@ -523,6 +523,13 @@ def main():
             line["roofline_onchip"] = {"smem": {"achieved": wf * 128 / launch_s / 1e12, "peak": smem_peak, "unit": "TB/s",
                                                 "frac": wf * 128 / launch_s / 1e12 / smem_peak},
                                        "source": ncu_k.get("source")}
+            if ncu_k.get("warp_instructions_per_unit"):
+                issue_peak = SM_COUNT * 4 * clk * 1e6
+                wi = ncu_k["warp_instructions_per_unit"] * per_launch_units
+                line["roofline_onchip"]["issue"] = {"achieved": wi / launch_s / 1e12, "peak": issue_peak / 1e12, "unit": "T warp-instructions/s",
+                                                    "frac": wi / launch_s / issue_peak,
+                                                    "note": "the average launch of a solve is smaller than the captured one: the tail rounds of a batch "
+                                                            "hold a few cohorts and run at the latency of one dependent chain"}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
             if extra is not None:
