@@ -48,8 +48,8 @@ struct CohortDev {
     int kind, src_off, n, dst_off;
     int first, count;                  // verify: its groups in the VGroup table; member: its MGroup, pieces per member
     int rep_bytes, cyc_level;          // verify: the cycle checks it begins with: levels cyc_level .. cyc_level + ncyc - 1,
-    int ncyc, log_off, cyc_pos, pad1;  //         their history entries from log_base + log_off (ncyc per member), the offset of
-};                                     //         their byte in the answer row.  A solve_qep cohort may carry the verify request
+    int ncyc, log_off, cyc_pos, pad1;  //         (log_off: unused), the offset of their byte in the answer row.
+};                                     //          A solve_qep cohort may carry the verify request
                                        //         that follows a successful solve (first / count / cyc_* as for verify; cyc_pos = 8)
 struct VGroup {                        // one (cohort, node) of a verify launch: `count` pairs from pair `start` of the launch
     int node, start, count, snap;      // (pair0: index of its first pair among all verify pairs of the round)
@@ -105,16 +105,18 @@ __global__ void net_done_kernel(const DoneDev* __restrict__ done, const int32_t*
 }
 
 // The cycle checks a verify request begins with (algorithm.jl:14-30), one thread per member: levels cyc_level ..
-// cyc_level + ncyc - 1 in turn, the first hit ends the chain.  History of (slot, level): a linked list through `prev` in
-// an append-only log (entry e: nproj projections at ent_pv[e * nproj], link ent_prev[e]); a miss appends at
-// log_base + log_off + member * ncyc + position in the chain (the host sized the log for every member of the launch).
-// hit_out: 0 = no hit, 1 + level of the first hit -- byte 0 of the member's answer row.
+// cyc_level + ncyc - 1 in turn, the first hit ends the chain.  History of (slot, level): a list of CHUNKS of
+// QPN_HIST_CHUNK entries (nproj projections each, contiguous, so the loads of a chunk are in flight together and a history
+// of k entries costs k / 8 dependent hops instead of k), newest chunk first; `cnt` entries in all.  A miss appends; a
+// new chunk comes from the bump counter *alloc (the host keeps the log large enough for one chunk per check of the
+// launch).  hit_out: 0 = no hit, 1 + level of the first hit -- the cycle byte of the member's answer row.
+#define QPN_HIST_CHUNK 8
 __global__ void net_cycle_kernel(const CohortDev* __restrict__ cohorts, const int* __restrict__ cidx, const int* __restrict__ cycstarts,
                                  int ncyc_cohorts, int total, int nlevels, int nproj, const int32_t* __restrict__ slot_of,
-                                 const double* __restrict__ PV, int32_t* __restrict__ head, double* __restrict__ ent_pv,
-                                 int32_t* __restrict__ ent_prev, int log_base, uint8_t* __restrict__ hit_out,
-                                 unsigned long long* __restrict__ keys, const int32_t* __restrict__ qep_status,
-                                 const uint8_t* __restrict__ qep_moved) {
+                                 const double* __restrict__ PV, int32_t* __restrict__ head, int32_t* __restrict__ count,
+                                 double* __restrict__ ent_pv, int32_t* __restrict__ ent_next, int* __restrict__ alloc,
+                                 uint8_t* __restrict__ hit_out, unsigned long long* __restrict__ keys,
+                                 const int32_t* __restrict__ qep_status, const uint8_t* __restrict__ qep_moved) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
     const int q = find_group_start(cycstarts, ncyc_cohorts, t);
@@ -125,15 +127,29 @@ __global__ void net_cycle_kernel(const CohortDev* __restrict__ cohorts, const in
     const double* pv = PV + (size_t)slot * nproj;
     int code = 0;
     for (int j = 0; j < c.ncyc && !code; ++j) {
-        int32_t* hd = head + (size_t)slot * nlevels + c.cyc_level + j;
-        int hit = 0;
+        const size_t idx = (size_t)slot * nlevels + c.cyc_level + j;
+        const int cnt = count[idx];
+        int hd = head[idx], hit = 0;
+        int in_chunk = cnt ? ((cnt - 1) % QPN_HIST_CHUNK) + 1 : 0;       // entries of the newest chunk
         // (the reference scans its cache from the oldest entry; "any earlier iterate" does not depend on the order)
-        for (int e = *hd; e >= 0 && !hit; e = ent_prev[e]) hit = qpn_cycle_hit(pv, ent_pv + (size_t)e * nproj, nproj);
+        for (int ch = hd; ch >= 0 && !hit; ch = ent_next[ch]) {
+            const double* base = ent_pv + (size_t)ch * QPN_HIST_CHUNK * nproj;
+#pragma unroll
+            for (int e = 0; e < QPN_HIST_CHUNK; ++e)
+                if (e < in_chunk) hit |= qpn_cycle_hit(pv, base + (size_t)e * nproj, nproj) ? 1 : 0;
+            in_chunk = QPN_HIST_CHUNK;
+        }
         if (hit) { code = 1 + c.cyc_level + j; break; }
-        const int e = log_base + c.log_off + k * c.ncyc + j;
-        for (int i = 0; i < nproj; ++i) ent_pv[(size_t)e * nproj + i] = pv[i];
-        ent_prev[e] = *hd;
-        *hd = e;
+        const int pos = cnt % QPN_HIST_CHUNK;
+        if (pos == 0) {
+            const int nc = atomicAdd(alloc, 1);
+            ent_next[nc] = hd;
+            head[idx] = nc;
+            hd = nc;
+        }
+        double* dst = ent_pv + ((size_t)hd * QPN_HIST_CHUNK + pos) * nproj;
+        for (int i = 0; i < nproj; ++i) dst[i] = pv[i];
+        count[idx] = cnt + 1;
     }
     hit_out[d] = (uint8_t)code;
     if (code) atomicAdd(keys + d, qpn_sig_term((unsigned)c.cyc_pos, (unsigned)code));     // (other kernels add to the same signature)
