@@ -565,15 +565,19 @@ __device__ __forceinline__ void lstsq_basic_block(const Tab& red, int nd, int k,
                                          int* perm, double* v) {
     const int j = threadIdx.x;
     const int steps = nd < k ? nd : k;
+    #pragma unroll 1
     for (int c = j; c < k; c += blockDim.x) perm[c] = c;
     QPN_SYNC();
     int rank = 0;
+    #pragma unroll 1
     for (int c = 0; c < steps; ++c) {
         double best = -1.0; int jb = -1;
         // candidates j in [c, k): handled in strides so k may exceed blockDim
+        #pragma unroll 1
         for (int jj = j; jj < k; jj += blockDim.x) {
             if (jj < c) continue;
             double s = 0.0;
+            #pragma unroll 1
             for (int i = c; i < nd; ++i) s = fma(Ab[(size_t)jj * nd + i], Ab[(size_t)jj * nd + i], s);
             if (jb < 0 || s > best) { best = s; jb = jj; }
         }
@@ -584,6 +588,7 @@ __device__ __forceinline__ void lstsq_basic_block(const Tab& red, int nd, int k,
         if (nrm <= 1e-10) break;
         QPN_SYNC();
         if (jb != c) {
+            #pragma unroll 1
             for (int i = j; i < nd; i += blockDim.x) {
                 const double tmp = Ab[(size_t)c * nd + i];
                 Ab[(size_t)c * nd + i] = Ab[(size_t)jb * nd + i];
@@ -593,17 +598,22 @@ __device__ __forceinline__ void lstsq_basic_block(const Tab& red, int nd, int k,
         }
         QPN_SYNC();
         const double alpha = Ab[(size_t)c * nd + c] > 0.0 ? -nrm : nrm;
+        #pragma unroll 1
         for (int i = c + j; i < nd; i += blockDim.x) v[i] = Ab[(size_t)c * nd + i] - (i == c ? alpha : 0.0);
         QPN_SYNC();
         double vn = 0.0;
+        #pragma unroll 1
         for (int i = c; i < nd; ++i) vn = fma(v[i], v[i], vn);
         if (vn > 0.0) {
+            #pragma unroll 1
             for (int jj = j; jj < k + 1; jj += blockDim.x) {
                 if (jj < c) continue;
                 double* col = (jj < k) ? Ab + (size_t)jj * nd : b;     // the rhs rides as column k
                 double s = 0.0;
+                #pragma unroll 1
                 for (int i = c; i < nd; ++i) s = fma(v[i], col[i], s);
                 s = (2.0 * s) / vn;
+                #pragma unroll 1
                 for (int i = c; i < nd; ++i) col[i] = fma(-s, v[i], col[i]);
             }
         }
@@ -612,12 +622,16 @@ __device__ __forceinline__ void lstsq_basic_block(const Tab& red, int nd, int k,
     }
     QPN_SYNC();
     if (j == 0) {
+        #pragma unroll 1
         for (int t = 0; t < k; ++t) lam[t] = 0.0;
+        #pragma unroll 1
         for (int i = rank - 1; i >= 0; --i) {
             double acc = b[i];
+            #pragma unroll 1
             for (int t = i + 1; t < rank; ++t) acc = fma(-Ab[(size_t)t * nd + i], v[t], acc);
             v[i] = acc / Ab[(size_t)i * nd + i];
         }
+        #pragma unroll 1
         for (int i = 0; i < rank; ++i) lam[perm[i]] = v[i];
     }
     QPN_SYNC();
@@ -627,13 +641,16 @@ __device__ __forceinline__ void lstsq_basic_block(const Tab& red, int nd, int k,
 // Thread r takes row r; each dot product is sequential in the variable index.
 __device__ __forceinline__ void node_products(const NodeDesc& nd_, const double* x, double* qt, double* ax) {
     const int nd = nd_.nd, nv = nd_.nv, m = nd_.m;
+    #pragma unroll 1
     for (int r = threadIdx.x; r < nd + m; r += blockDim.x) {
         double acc = 0.0;
         if (r < nd) {
+            #pragma unroll 4
             for (int j = 0; j < nv; ++j) acc = fma(nd_.Qd[(size_t)j * nd + r], x[j], acc);
             qt[r] = acc + nd_.qd[r];
         } else {
             const int rr = r - nd;
+            #pragma unroll 4
             for (int j = 0; j < nv; ++j) acc = fma(nd_.A[(size_t)j * m + rr], x[j], acc);
             ax[rr] = acc;
         }
@@ -652,6 +669,7 @@ __device__ __forceinline__ int verify_solution_smem(Tab& tab, VerifySmem& vs, co
                                            double tol, int* how, int* pivots) {
     const int nd = nd_.nd, m = nd_.m, i = threadIdx.x;
     int infeasible = 0;
+    #pragma unroll 1
     for (int r = i; r < m; r += blockDim.x) {
         const double acc = ax[r];
         vs.lam_out()[r] = 0.0;
@@ -663,10 +681,12 @@ __device__ __forceinline__ int verify_solution_smem(Tab& tab, VerifySmem& vs, co
     infeasible = QPN_SYNC_OR(infeasible);
     if (infeasible) { *how = 0; return 0; }
     double nq = 0.0;
+    #pragma unroll 1
     for (int r = 0; r < nd; ++r) nq = fma(qt[r], qt[r], nq);
     if (m == 0) { *how = 1; return sqrt(nq) <= tol ? 1 : 0; }
     // no active row at all (the common case at an interior point): skip the serial ordering below
     int any_active = 0;
+    #pragma unroll 1
     for (int r = i; r < m; r += blockDim.x) any_active |= (vs.kind()[r] != 0);
     any_active = QPN_SYNC_OR(any_active);
     // order the active rows: lower-active, upper-active, both (qp_processing.jl:105-114)
@@ -674,8 +694,11 @@ __device__ __forceinline__ int verify_solution_smem(Tab& tab, VerifySmem& vs, co
         if (i == 0) { tab.red_i()[32] = 0; tab.red_i()[33] = 0; tab.red_i()[34] = 0; }
     } else if (i == 0) {
         int k = 0, np_ = 0, nn = 0;
+        #pragma unroll 1
         for (int r = 0; r < m; ++r) if (vs.kind()[r] == 1) { vs.idx()[k++] = r; np_++; }
+        #pragma unroll 1
         for (int r = 0; r < m; ++r) if (vs.kind()[r] == 2) { vs.idx()[k++] = r; nn++; }
+        #pragma unroll 1
         for (int r = 0; r < m; ++r) if (vs.kind()[r] == 3) { vs.idx()[k++] = r; }
         tab.red_i()[32] = k; tab.red_i()[33] = np_; tab.red_i()[34] = nn;
     }
@@ -690,6 +713,7 @@ __device__ __forceinline__ int verify_solution_smem(Tab& tab, VerifySmem& vs, co
         *how = 4;
         return 0;
     }
+    #pragma unroll 1
     for (int e = i; e < nd * k; e += blockDim.x) {
         const int tcol = e / nd, r = e - tcol * nd;
         const double sgn = (tcol >= np_ && tcol < np_ + nn) ? -1.0 : 1.0;
@@ -697,13 +721,16 @@ __device__ __forceinline__ int verify_solution_smem(Tab& tab, VerifySmem& vs, co
         vs.Ab()[e] = val;
         if (!WIDE) vs.Ab0()[e] = val;
     }
+    #pragma unroll 1
     for (int r = i; r < nd; r += blockDim.x) vs.b()[r] = qt[r];
     QPN_SYNC();
     lstsq_basic_block(tab, nd, k, vs.Ab(), vs.b(), vs.lam(), vs.perm(), vs.v());
     // acceptance (qp_processing.jl:119)
     if (WIDE) {
+        #pragma unroll 1
         for (int r = i; r < nd; r += blockDim.x) {
             double acc = 0.0;
+            #pragma unroll 1
             for (int t = 0; t < k; ++t) {
                 const double a = nd_.A[(size_t)nd_.dec[r] * m + vs.idx()[t]];
                 acc = fma((t >= np_ && t < np_ + nn) ? -a : a, vs.lam()[t], acc);
@@ -714,13 +741,16 @@ __device__ __forceinline__ int verify_solution_smem(Tab& tab, VerifySmem& vs, co
     }
     if (i == 0) {
         int ok = 1;
+        #pragma unroll 1
         for (int t = 0; t < np_ + nn; ++t) if (!(vs.lam()[t] > -tol)) ok = 0;
         double res = 0.0;
+        #pragma unroll 1
         for (int r = 0; r < nd; ++r) {
             double e;
             if (WIDE) e = vs.v()[r];
             else {
                 double acc = 0.0;
+                #pragma unroll 1
                 for (int t = 0; t < k; ++t) acc = fma(vs.Ab0()[(size_t)t * nd + r], vs.lam()[t], acc);
                 e = acc - qt[r];
             }
@@ -731,6 +761,7 @@ __device__ __forceinline__ int verify_solution_smem(Tab& tab, VerifySmem& vs, co
     }
     QPN_SYNC();
     if (tab.red_i()[35]) {
+        #pragma unroll 1
         for (int t = i; t < k; t += blockDim.x)
             vs.lam_out()[vs.idx()[t]] = (t >= np_ && t < np_ + nn) ? -vs.lam()[t] : vs.lam()[t];
         QPN_SYNC();
@@ -740,8 +771,10 @@ __device__ __forceinline__ int verify_solution_smem(Tab& tab, VerifySmem& vs, co
     // fallback (qp_processing.jl:129-146): sign-constrained least squares as the box AVI
     //   (Ad Ad') lam - Ad qt  comp.  lb <= lam <= ub
     QPN_SYNC();
+    #pragma unroll 1
     for (int r = i; r < m; r += blockDim.x) {
         double acc = 0.0;
+        #pragma unroll 4
         for (int t = 0; t < nd; ++t) acc = fma(nd_.A[(size_t)nd_.dec[t] * m + r], qt[t], acc);
         vs.qs()[r] = -acc;
         vs.zs()[r] = 0.0;
@@ -752,9 +785,11 @@ __device__ __forceinline__ int verify_solution_smem(Tab& tab, VerifySmem& vs, co
     QPN_SYNC();
     auto build = [&](Tab& tt) {
         const int ldr = tt.ldr;
+        #pragma unroll 1
         for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
             const int c = e / m, r = e - c * m;
             double acc = 0.0;
+            #pragma unroll 4
             for (int t = 0; t < nd; ++t) acc = fma(nd_.A[(size_t)nd_.dec[t] * m + r], nd_.A[(size_t)nd_.dec[t] * m + c], acc);
             tt.T()[(size_t)r * ldr + c] = -acc;
         }
@@ -767,14 +802,17 @@ __device__ __forceinline__ int verify_solution_smem(Tab& tab, VerifySmem& vs, co
     if (st != ST_SUCCESS) { *how = 5; return 0; }
     if (i == 0) {
         double res2 = 0.0;
+        #pragma unroll 1
         for (int t = 0; t < nd; ++t) {
             double acc = 0.0;
+            #pragma unroll 4
             for (int r = 0; r < m; ++r) acc = fma(nd_.A[(size_t)nd_.dec[t] * m + r], vs.zs()[r], acc);
             const double e = acc - qt[t];
             res2 = fma(e, e, res2);
         }
         tab.red_i()[35] = sqrt(res2) <= 1e-4 ? 1 : 0;
     }
+    #pragma unroll 1
     for (int r = i; r < m; r += blockDim.x) vs.lam_out()[r] = vs.zs()[r];
     QPN_SYNC();
     const int ok2 = tab.red_i()[35];

@@ -64,6 +64,7 @@ __device__ __forceinline__ int multiplier_vertices_warp(const VeSmem& s, int nd,
     if (max_new > QPN_VE_MAXV) max_new = QPN_VE_MAXV;
     // ---- active rows (serial lines 39-48: any inactive row with a multiplier, or more than MAXA active rows: nothing) ----
     int a = 0, fail = 0;
+    #pragma unroll 1
     for (int base = 0; base < m; base += 32) {
         const int i = base + lane;
         bool lo = false, up = false, bad = false;
@@ -82,6 +83,7 @@ __device__ __forceinline__ int multiplier_vertices_warp(const VeSmem& s, int nd,
     if (a == 0) return 0;
     __syncwarp();
     // ---- G = A_d' on the active rows (nd x a), W its elimination copy ------------------------------------------------------
+    #pragma unroll 1
     for (int idx = lane; idx < nd * a; idx += 32) {
         const int e = idx / a, k = idx - e * a;
         const double v = A[(size_t)dec[e] * m + s.idxA[k]];
@@ -92,8 +94,10 @@ __device__ __forceinline__ int multiplier_vertices_warp(const VeSmem& s, int nd,
     __syncwarp();
     {   // the point itself must satisfy the slice's equalities at the piece tolerance
         bool bad = false;
+        #pragma unroll 1
         for (int e = lane; e < nd; e += 32) {
             double sum = 0.0;
+            #pragma unroll 1
             for (int k = 0; k < a; ++k) sum = fma(s.G[e * QPN_VE_MAXA + k], lam[s.idxA[k]], sum);
             if (fabs(sum - qt[e]) > 1e-6) bad = true;
         }
@@ -102,15 +106,18 @@ __device__ __forceinline__ int multiplier_vertices_warp(const VeSmem& s, int nd,
     // ---- rank and an independent row set by elimination with full pivoting -----------------------------------------------
     int r = 0;
     const int lim = nd < a ? nd : a;
+    #pragma unroll 1
     for (; r < lim; ++r) {
         const int wr = a - r, cnt = (nd - r) * wr;
         double best = 1e-9;
         int bidx = -1;
+        #pragma unroll 1
         for (int idx = lane; idx < cnt; idx += 32) {
             const int e = r + idx / wr, k = r + idx % wr;
             const double v = fabs(s.W[s.rowperm[e] * QPN_VE_MAXA + s.colperm[k]]);
             if (v > best) { best = v; bidx = idx; }
         }
+        #pragma unroll 1
         for (int o = 16; o > 0; o >>= 1) {
             const double ov = __shfl_xor_sync(FULL, best, o);
             const int oi = __shfl_xor_sync(FULL, bidx, o);
@@ -125,9 +132,11 @@ __device__ __forceinline__ int multiplier_vertices_warp(const VeSmem& s, int nd,
         }
         __syncwarp();
         const double piv = s.W[s.rowperm[r] * QPN_VE_MAXA + s.colperm[r]];
+        #pragma unroll 1
         for (int e = r + 1 + lane; e < nd; e += 32) s.fE[e] = s.W[s.rowperm[e] * QPN_VE_MAXA + s.colperm[r]] / piv;
         __syncwarp();
         const int ucnt = (nd - r - 1) * wr;
+        #pragma unroll 1
         for (int idx = lane; idx < ucnt; idx += 32) {
             const int e = r + 1 + idx / wr, k = r + idx % wr;
             const double f = s.fE[e];
@@ -139,12 +148,15 @@ __device__ __forceinline__ int multiplier_vertices_warp(const VeSmem& s, int nd,
     }
     if (a <= r) return 0;                        // independent columns: the polytope is the point lam itself
     if (lane == 0) {                             // the r equations in ascending order
+        #pragma unroll 1
         for (int e = 0; e < r; ++e) s.rows[e] = s.rowperm[e];
+        #pragma unroll 1
         for (int i = 1; i < r; ++i) { const int t = s.rows[i]; int j = i - 1; while (j >= 0 && s.rows[j] > t) { s.rows[j + 1] = s.rows[j]; --j; } s.rows[j + 1] = t; }
     }
     __syncwarp();
     // free multipliers (equality rows) must be basic: a polyhedron with a line among them has no vertices
     unsigned freemask = 0;
+    #pragma unroll 1
     for (int k = 0; k < a; ++k) if (s.sgn[k] == 0) freemask |= 1u << k;
     if (__popc(freemask) > r) return 0;
     // ---- the candidate bases, QPN_VE_LANES at a time ------------------------------------------------------------------------------
@@ -153,13 +165,16 @@ __device__ __forceinline__ int multiplier_vertices_warp(const VeSmem& s, int nd,
     double* y = Mx + nd * nd;
     double* cand = y + nd;
     int nv_found = 0;
+    #pragma unroll 1
     for (int base = 0; base < total && nv_found < max_new; base += QPN_VE_LANES) {
         int c = base + lane;
         bool ok = c < total && lane < QPN_VE_LANES;
         unsigned comb = 0, combmask = 0;         // comb[i] in nibble i
         if (ok) {
             int x = 0;
+            #pragma unroll 1
             for (int i = 0; i < r; ++i) {
+                #pragma unroll 1
                 while (true) {
                     const int skip = ve_binom(a - x - 1, r - i - 1);
                     if (skip <= c) { c -= skip; ++x; } else break;
@@ -171,42 +186,57 @@ __device__ __forceinline__ int multiplier_vertices_warp(const VeSmem& s, int nd,
         }
         if (ok) {
             // solve G[rows, comb] y = qt[rows] (Gaussian elimination with partial pivoting; every multiply-add an fma)
+            #pragma unroll 1
             for (int i = 0; i < r; ++i) {
+                #pragma unroll 1
                 for (int j = 0; j < r; ++j) Mx[i * r + j] = s.G[s.rows[i] * QPN_VE_MAXA + ((comb >> (4 * j)) & 15)];
                 y[i] = qt[s.rows[i]];
             }
+            #pragma unroll 1
             for (int cc = 0; cc < r && ok; ++cc) {
                 int p = cc;
+                #pragma unroll 1
                 for (int i = cc + 1; i < r; ++i) if (fabs(Mx[i * r + cc]) > fabs(Mx[p * r + cc])) p = i;
                 if (fabs(Mx[p * r + cc]) < 1e-9) { ok = false; break; }
                 if (p != cc) {
+                    #pragma unroll 1
                     for (int j = 0; j < r; ++j) { const double t = Mx[p * r + j]; Mx[p * r + j] = Mx[cc * r + j]; Mx[cc * r + j] = t; }
                     const double t = y[p]; y[p] = y[cc]; y[cc] = t;
                 }
+                #pragma unroll 1
                 for (int i = cc + 1; i < r; ++i) {
                     const double f = Mx[i * r + cc] / Mx[cc * r + cc];
                     if (f == 0.0) continue;
+                    #pragma unroll 1
                     for (int j = cc; j < r; ++j) Mx[i * r + j] = fma(-f, Mx[cc * r + j], Mx[i * r + j]);
                     y[i] = fma(-f, y[cc], y[i]);
                 }
             }
         }
         if (ok) {
+            #pragma unroll 1
             for (int i = r - 1; i >= 0; --i) {
                 double sum = y[i];
+                #pragma unroll 1
                 for (int j = i + 1; j < r; ++j) sum = fma(-Mx[i * r + j], y[j], sum);
                 y[i] = sum / Mx[i * r + i];
             }
+            #pragma unroll 1
             for (int k = 0; k < a; ++k) cand[k] = 0.0;
+            #pragma unroll 1
             for (int i = 0; i < r; ++i) cand[(comb >> (4 * i)) & 15] = y[i];
+            #pragma unroll 1
             for (int k = 0; k < a && ok; ++k) if (s.sgn[k] != 0 && s.sgn[k] * cand[k] < -1e-6) ok = false;
+            #pragma unroll 1
             for (int e = 0; e < nd && ok; ++e) {      // every stationarity equation, not only the r chosen ones
                 double sum = 0.0;
+                #pragma unroll 1
                 for (int k = 0; k < a; ++k) sum = fma(s.G[e * QPN_VE_MAXA + k], cand[k], sum);
                 if (fabs(sum - qt[e]) > 1e-6) ok = false;
             }
             if (ok) {                                 // QuantizedVector (avi_solutions.jl:23-32): equal to the point at 5 digits
                 bool same = true;
+                #pragma unroll 1
                 for (int k = 0; k < a; ++k) same &= (rint(cand[k] * 1e5) == rint(lam[s.idxA[k]] * 1e5));
                 if (same) ok = false;
             }
@@ -214,17 +244,21 @@ __device__ __forceinline__ int multiplier_vertices_warp(const VeSmem& s, int nd,
         unsigned good = __ballot_sync(FULL, ok);
         if (lane == 0) {
             // in combination order: new at 5 digits against the vertices found so far
+            #pragma unroll 1
             while (good && nv_found < max_new) {
                 const int t = __ffs(good) - 1;
                 good &= good - 1;
                 const double* ct = s.lanes + t * s.stride + nd * nd + nd;
                 bool dup = false;
+                #pragma unroll 1
                 for (int q = 0; q < nv_found && !dup; ++q) {
                     bool eq = true;
+                    #pragma unroll 1
                     for (int k = 0; k < a; ++k) eq &= (rint(ct[k] * 1e5) == rint(s.V[q * QPN_VE_MAXA + k] * 1e5));
                     dup = eq;
                 }
                 if (!dup) {
+                    #pragma unroll 1
                     for (int k = 0; k < a; ++k) s.V[nv_found * QPN_VE_MAXA + k] = ct[k];
                     ++nv_found;
                 }
