@@ -184,6 +184,7 @@ __device__ __forceinline__ void block_argmax(const Tab& t, bool valid, double& v
         if ((threadIdx.x & 31) == 0) { t.red_d()[w] = wv; t.red_i()[w] = widx; }
         QPN_SYNC();
         wv = t.red_d()[0]; widx = t.red_i()[0];
+        #pragma unroll 1
         for (int k = 1; k < nw; ++k) {
             const double v2 = t.red_d()[k]; const int i2 = t.red_i()[k];
             if (i2 >= 0 && (widx < 0 || v2 > wv)) { wv = v2; widx = i2; }      // warps are in row order: ties keep the lower row
@@ -210,6 +211,7 @@ __device__ __forceinline__ void block_argmax_idx(const Tab& t, bool valid, doubl
         if ((threadIdx.x & 31) == 0) { t.red_d()[w] = wv; t.red_i()[w] = widx; }
         QPN_SYNC();
         wv = t.red_d()[0]; widx = t.red_i()[0];
+        #pragma unroll 1
         for (int k = 1; k < nw; ++k) {
             const double v2 = t.red_d()[k]; const int i2 = t.red_i()[k];
             if (i2 >= 0 && (widx < 0 || v2 > wv || (v2 == wv && i2 < widx))) { wv = v2; widx = i2; }
@@ -229,6 +231,7 @@ __device__ __forceinline__ double block_min(const Tab& t, double v) {   // v >= 
         if ((threadIdx.x & 31) == 0) t.red_d()[w] = m;
         QPN_SYNC();
         m = t.red_d()[0];
+        #pragma unroll 1
         for (int k = 1; k < nw; ++k) m = fmin(m, t.red_d()[k]);
     }
     return m;
@@ -280,6 +283,7 @@ __device__ __noinline__ void tab_start_core(Tab t, const double* q, const double
     if (i < n) {
         double* row = t.T() + (size_t)i * t.ldr;
         double acc = 0.0;
+        #pragma unroll 4
         for (int j = 0; j < n; ++j) {
             const double mij = -row[j];
             if (mij != 0.0) acc = fma(mij, zb[j], acc);
@@ -324,6 +328,7 @@ __device__ __noinline__ int pivot_core(Tab t, int rho, int c, bool compact) {
     // The scaled pivot row goes to prow AND straight back into row rho (element j by the thread that scaled it;
     // element c after the barrier, because every thread still reads p = T[rho][c] above): the update below then
     // needs no per-element "is this the pivot row" select -- row rho runs the same fma with a zero multiplier.
+    #pragma unroll 1
     for (int j = i; j < nce; j += blockDim.x) {
         const double v = (j >= ncol) ? 0.0 : (j == c) ? (1.0 / p) : prho[j] / p;
         t.prow()[j] = v;
@@ -494,6 +499,7 @@ __device__ __forceinline__ void recompute_tcol(Tab& t) {
     if (i < n) {
         double* row = t.T() + (size_t)i * t.ldr;
         double acc = 0.0;
+        #pragma unroll 4
         for (int k = 0; k < n; ++k) {
             const int ck = t.colof()[n + k];
             const double pik = ck >= 0 ? -row[ck] : (t.rowof()[n + k] == i ? -1.0 : 0.0);
@@ -510,11 +516,13 @@ __device__ __forceinline__ void compact_dead(Tab& t) {
     int* map = reinterpret_cast<int*>(t.prow());            // scratch: prow is free between pivots
     if (i == 0) {
         int nl = 0;
+        #pragma unroll 1
         for (int j = 0; j < t.ncol; ++j) {
             const int v = t.colvar()[j];
             if (v >= n && v < 2 * n && is_free_var(t, v - n)) t.colof()[v] = -1;
             else map[nl++] = j;
         }
+        #pragma unroll 1
         for (int d = 0; d < nl; ++d) {
             const int sidx = map[d];
             if (sidx != d) { const int v = t.colvar()[sidx]; t.colvar()[d] = v; t.nbval()[d] = t.nbval()[sidx]; t.colof()[v] = d; }
@@ -525,6 +533,7 @@ __device__ __forceinline__ void compact_dead(Tab& t) {
     const int nl = t.red_i()[32];
     if (i < n) {
         double* row = t.T() + (size_t)i * t.ldr;
+        #pragma unroll 1
         for (int d = 0; d < nl; ++d) { const int sidx = map[d]; if (sidx != d) row[d] = row[sidx]; }   // sidx >= d: in place
     }
     t.ncol = nl;
@@ -540,10 +549,12 @@ __device__ __forceinline__ void freeze_hook(Tab& t) { t.own_frozen = (threadIdx.
 template <class TT>
 __device__ __forceinline__ void freeze(TT& t) {
     const int n = t.n;
+    #pragma unroll 1
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const int v = t.rowvar()[i];
         if (v < n && is_free_var(t, v)) t.zst()[v] = FROZEN;
     }
+    #pragma unroll 1
     for (int j = threadIdx.x; j < t.ncol; j += blockDim.x) { t.colvar0()[j] = t.colvar()[j]; t.nbval0()[j] = t.nbval()[j]; }
     t.ncol0 = t.ncol;
     freeze_hook(t);
@@ -557,21 +568,25 @@ __device__ __noinline__ void frozen_values(Tab t, double* dx) {
     const int n = t.n, nc0 = t.ncol0, ldr = t.ldr;
     const double* T0f = *t.frozen_src();
     const int nact = t.frozen_hdr()[0], tcol0 = t.frozen_hdr()[1];
+    #pragma unroll 1
     for (int j = threadIdx.x; j < nc0; j += blockDim.x) {
         const int v = t.colvar0()[j];
         const int r = t.rowof()[v], c = t.colof()[v];
         dx[j] = (r >= 0 ? t.beta()[r] : c >= 0 ? t.nbval()[c] : t.nbval0()[j]) - t.nbval0()[j];
     }
     QPN_SYNC();
+    #pragma unroll 1
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         if (!frozen_row(t, i)) continue;
         double acc = t.beta()[i];
         if (T0f && i >= nact) {
             const double* row = T0f + (size_t)i * ldr;
             const double bir = t.birv()[i];               // written by the plan start, in the same pass as the swept rows' entries
+            #pragma unroll 4
             for (int j = 0; j < nc0; ++j) acc = fma(-(j == tcol0 ? bir : row[j]), dx[j], acc);
         } else {
             const double* row = t.T() + (size_t)i * ldr;
+            #pragma unroll 4
             for (int j = 0; j < nc0; ++j) acc = fma(-row[j], dx[j], acc);
         }
         t.beta()[i] = acc;                                // nobody reads a frozen row's beta in this pass
@@ -586,6 +601,7 @@ __device__ __noinline__ void frozen_values(Tab t, double* dx) {
 template <class TT>
 __device__ __forceinline__ void frozen_values(TT& t, double* dx) {
     const int n = t.n, nc0 = t.ncol0;
+    #pragma unroll 1
     for (int j = threadIdx.x; j < nc0; j += blockDim.x) {
         const int v = t.colvar0()[j];
         const int r = t.rowof()[v], c = t.colof()[v];
@@ -594,9 +610,11 @@ __device__ __forceinline__ void frozen_values(TT& t, double* dx) {
         dx[j] = (r >= 0 ? t.beta()[r] : c >= 0 ? t.nbval()[c] : t.nbval0()[j]) - t.nbval0()[j];
     }
     QPN_SYNC();
+    #pragma unroll 1
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         if (!frozen_row(t, i)) continue;
         double acc = t.beta()[i];
+        #pragma unroll 4
         for (int j = 0; j < nc0; ++j) acc = fma(-t.frozen_entry(i, j), dx[j], acc);
         t.beta()[i] = acc;                                // nobody reads a frozen row's beta in this pass
     }
@@ -612,6 +630,7 @@ __device__ __forceinline__ void crash(TT& t, bool from_plan) {
     // would retry the variables that found no pivot at their turn, which the specification does not.
     if (!from_plan) {
         const int piv0 = t.pivots;
+        #pragma unroll 1
         for (int i = 0; i < n; ++i) {
             if (!is_free_var(t, i)) continue;
             const int c = t.colof()[i];
@@ -622,6 +641,7 @@ __device__ __forceinline__ void crash(TT& t, bool from_plan) {
     }
     freeze(t);
     // phase 1: everything still floating, against any artificial row
+    #pragma unroll 1
     for (int i = 0; i < n; ++i) {
         if (t.zst()[i] != FLOATING) continue;
         const int c = t.colof()[i];
@@ -631,6 +651,7 @@ __device__ __forceinline__ void crash(TT& t, bool from_plan) {
         int rb[2], wb[2]; double th[2], own[2], step[2];
         own[0] = t.u()[i] - t.nbval()[c];        // read before the ratio tests (synchronisation rule)
         own[1] = t.nbval()[c] - t.l()[i];
+        #pragma unroll 1
         for (int s = 0; s < 2; ++s) {
             const double sigma = s == 0 ? 1.0 : -1.0;
             th[s] = ratio_test(t, c, sigma, rb[s], wb[s]);
@@ -673,9 +694,11 @@ template <class TT>
 __device__ __forceinline__ void repair(TT& t) {
     const int n = t.n;
     bool progress = true;
+    #pragma unroll 1
     while (progress) {
         progress = false;
         if (!any_artificial_row(t)) return;
+        #pragma unroll 1
         for (int k = 0; k < n; ++k) {
             const int8_t s = t.zst()[k];
             if ((s == AT_L || s == AT_U) && t.l()[k] != t.u()[k] && t.rowof()[k] < 0 && t.rowof()[n + k] < 0) {
@@ -683,6 +706,7 @@ __device__ __forceinline__ void repair(TT& t) {
                 else if (try_exchange(t, k)) { set_zst(t, k, BASIC); progress = true; }
             }
         }
+        #pragma unroll 1
         for (int k = 0; k < n; ++k)
             if (t.zst()[k] == FLOATING && t.rowof()[k] < 0)
                 if (try_exchange(t, k)) { set_zst(t, k, BASIC); progress = true; }
@@ -694,6 +718,7 @@ template <class TT>
 __device__ __forceinline__ int lemke(TT& t, int max_pivots) {
     const int n = t.n;
     int ent = 2 * n; double sigma = 1.0;
+    #pragma unroll 1
     for (;;) {
         if (t.pivots > max_pivots) return ST_MAX_ITERS;
         const int c = t.colof()[ent];

@@ -84,10 +84,13 @@ __device__ __noinline__ void tab_start_plan_core(Tab t, const PlanDesc& P, const
     } else if (aligned) {                                         // 128-bit copies
         const double2* src = reinterpret_cast<const double2*>(P.T0);
         double2* dst = reinterpret_cast<double2*>(t.T());
+        #pragma unroll 1
         for (int e = i; e < (nact * ldr) >> 1; e += blockDim.x) dst[e] = src[e];
     } else {
+        #pragma unroll 1
         for (int e = i; e < nact * ldr; e += blockDim.x) t.T()[e] = P.T0[e];
     }
+    #pragma unroll 1
     for (int v = i; v <= 2 * n; v += blockDim.x) { t.rowof()[v] = -1; t.colof()[v] = -1; }
     if (i == 0) { *t.frozen_src() = nact < n ? P.T0 : nullptr; t.frozen_hdr()[0] = nact; t.frozen_hdr()[1] = P.tcol0; }
     QPN_SYNC();
@@ -97,6 +100,7 @@ __device__ __noinline__ void tab_start_plan_core(Tab t, const PlanDesc& P, const
         t.rr()[i] = ((csr_row_dot(P, i, zb) + q[i]) + zi) - zb[i];
         t.zst()[i] = (zi <= t.l()[i]) ? AT_L : (zi >= t.u()[i]) ? AT_U : FLOATING;
     }
+    #pragma unroll 1
     for (int j = i; j < P.ncol0; j += blockDim.x) {
         const int v = P.colvar0[j];
         t.colvar()[j] = v; t.colof()[v] = j; t.nbval()[j] = v < n ? zb[v] : 0.0;
@@ -112,10 +116,12 @@ __device__ __noinline__ void tab_start_plan_core(Tab t, const PlanDesc& P, const
             const double* pt = P.PT + i;
             const double* rr = t.rr();
             int k = 0;
+            #pragma unroll 1
             for (; k + 4 <= n; k += 4) {
                 const double p0 = pt[(size_t)k * n], p1 = pt[(size_t)(k + 1) * n], p2 = pt[(size_t)(k + 2) * n], p3 = pt[(size_t)(k + 3) * n];
                 acc = fma(p0, rr[k], acc); acc = fma(p1, rr[k + 1], acc); acc = fma(p2, rr[k + 2], acc); acc = fma(p3, rr[k + 3], acc);
             }
+            #pragma unroll 4
             for (; k < n; ++k) acc = fma(pt[(size_t)k * n], rr[k], acc);
             birv_i = acc;
             if (i >= nact) t.birv()[i] = acc;             // a frozen row is not in T(): frozen_values picks its entry up here
@@ -228,13 +234,16 @@ __device__ __forceinline__ int gavi_carve(GaviSmem& s, const GaviDesc& g, int ba
 // s0 = A z0 + B w (c = B w kept).  Ends with a barrier.
 __device__ __forceinline__ void gavi_slack(GaviSmem& s, const GaviDesc& g, bool recompute_c) {
     const int i = threadIdx.x, dz = g.d1 + g.d2;
+    #pragma unroll 1
     for (int r = i; r < g.d2; r += blockDim.x) {
         if (recompute_c) {
             double acc = 0.0;
+            #pragma unroll 4
             for (int j = 0; j < g.np; ++j) acc = fma(g.B[(size_t)j * g.d2 + r], s.w()[j], acc);
             s.c()[r] = acc;
         }
         double acc = 0.0;
+        #pragma unroll 4
         for (int j = 0; j < dz; ++j) acc = fma(g.A[(size_t)j * g.d2 + r], s.z0()[j], acc);
         s.s0()[r] = acc + s.c()[r];
     }
@@ -247,16 +256,20 @@ __device__ __forceinline__ void build_presolve(Tab& tt, const GaviDesc& g, const
     const int ldr = tt.ldr, d2 = g.d2, pn = k + 2 * d2;
     if (threadIdx.x < pn) {
         double* row = tt.T() + (size_t)threadIdx.x * ldr;
+        #pragma unroll 1
         for (int j = 0; j < pn; ++j) row[j] = 0.0;
     }
     QPN_SYNC();
+    #pragma unroll 1
     for (int e = threadIdx.x; e < k * d2; e += blockDim.x) {
         const int a = e / d2, r = e - a * d2;
         const double v = g.A[(size_t)cols[a] * d2 + r];
         tt.T()[(size_t)a * ldr + (k + r)] = v;         // -(-A')   row a, column k+r
         tt.T()[(size_t)(k + r) * ldr + a] = -v;        // -(A)     row k+r, column a
     }
+    #pragma unroll 1
     for (int e = threadIdx.x; e < k; e += blockDim.x) tt.T()[(size_t)e * ldr + e] = -1.0;
+    #pragma unroll 1
     for (int e = threadIdx.x; e < d2; e += blockDim.x) {
         tt.T()[(size_t)(k + e) * ldr + (k + d2 + e)] = 1.0;      // -(-1)  row k+e, column k+d2+e
         tt.T()[(size_t)(k + d2 + e) * ldr + (k + e)] = -1.0;     // -(+1)  row k+d2+e, column k+e
@@ -270,12 +283,17 @@ __device__ __forceinline__ void build_lifted(Tab& tt, const GaviDesc& g) {
     if (r < n) {
         double* row = tt.T() + (size_t)r * ldr;
         if (r < d1) {
+            #pragma unroll 4
             for (int j = 0; j < dz; ++j) row[j] = -g.M[(size_t)j * d1 + r];
+            #pragma unroll 1
             for (int j = dz; j < n; ++j) row[j] = 0.0;
         } else if (r < dz) {
+            #pragma unroll 4
             for (int j = 0; j < dz; ++j) row[j] = -g.A[(size_t)j * d2 + (r - d1)];
+            #pragma unroll 1
             for (int j = dz; j < n; ++j) row[j] = (j - dz == r - d1) ? 1.0 : 0.0;
         } else {
+            #pragma unroll 1
             for (int j = 0; j < n; ++j) row[j] = (j - d1 == r - dz) ? -1.0 : 0.0;
         }
     }
@@ -285,14 +303,17 @@ __device__ __forceinline__ void build_lifted(Tab& tt, const GaviDesc& g) {
 // Non-zero columns of A into cols[0..k), k into cols[dz].  Ends with a barrier.
 __device__ __forceinline__ void find_cols(const GaviDesc& g, int* cols) {
     const int dz = g.d1 + g.d2, d2 = g.d2, i = threadIdx.x;
+    #pragma unroll 1
     for (int j = i; j < dz; j += blockDim.x) {
         bool nz = false;
+        #pragma unroll 4
         for (int r = 0; r < d2; ++r) nz |= (g.A[(size_t)j * d2 + r] != 0.0);
         cols[j] = nz ? 1 : 0;
     }
     QPN_SYNC();
     if (i == 0) {
         int k = 0;
+        #pragma unroll 1
         for (int j = 0; j < dz; ++j) if (cols[j]) cols[k++] = j;
         cols[dz] = k;
     }
@@ -309,6 +330,7 @@ __device__ __forceinline__ int gavi_solve_smem(GaviSmem& s, const GaviDesc& g, c
     gavi_slack(s, g, true);
     if (presolve && d2 > 0) {
         int infeasible = 0;
+        #pragma unroll 1
         for (int r = i; r < d2; r += blockDim.x)
             if (!(g.l2[r] <= s.s0()[r] && s.s0()[r] <= g.u2[r])) infeasible = 1;
         infeasible = QPN_SYNC_OR(infeasible);
@@ -325,7 +347,9 @@ __device__ __forceinline__ int gavi_solve_smem(GaviSmem& s, const GaviDesc& g, c
                 else if (i < k + d2) {
                     const int r = i - k;
                     double full = 0.0, part = 0.0;
+                    #pragma unroll 4
                     for (int j = 0; j < dz; ++j) full = fma(g.A[(size_t)j * d2 + r], s.z0()[j], full);
+                    #pragma unroll 4
                     for (int a = 0; a < k; ++a) part = fma(g.A[(size_t)cols[a] * d2 + r], s.z0()[cols[a]], part);
                     s.qs()[i] = (full - part) + s.c()[r];
                     s.zs()[i] = 0.0; t.l()[i] = -QPN_INF; t.u()[i] = QPN_INF;
@@ -348,6 +372,7 @@ __device__ __forceinline__ int gavi_solve_smem(GaviSmem& s, const GaviDesc& g, c
     if (i < n) {
         if (i < d1) {
             double acc = 0.0;
+            #pragma unroll 4
             for (int j = 0; j < g.np; ++j) acc = fma(g.N[(size_t)j * d1 + i], s.w()[j], acc);
             s.qs()[i] = acc + g.o[i];
             t.l()[i] = g.l1[i]; t.u()[i] = g.u1[i];
@@ -577,7 +602,7 @@ __device__ __forceinline__ void lstsq_basic_block(const Tab& red, int nd, int k,
         for (int jj = j; jj < k; jj += blockDim.x) {
             if (jj < c) continue;
             double s = 0.0;
-            #pragma unroll 1
+            #pragma unroll 4
             for (int i = c; i < nd; ++i) s = fma(Ab[(size_t)jj * nd + i], Ab[(size_t)jj * nd + i], s);
             if (jb < 0 || s > best) { best = s; jb = jj; }
         }
@@ -602,7 +627,7 @@ __device__ __forceinline__ void lstsq_basic_block(const Tab& red, int nd, int k,
         for (int i = c + j; i < nd; i += blockDim.x) v[i] = Ab[(size_t)c * nd + i] - (i == c ? alpha : 0.0);
         QPN_SYNC();
         double vn = 0.0;
-        #pragma unroll 1
+        #pragma unroll 4
         for (int i = c; i < nd; ++i) vn = fma(v[i], v[i], vn);
         if (vn > 0.0) {
             #pragma unroll 1
@@ -610,10 +635,10 @@ __device__ __forceinline__ void lstsq_basic_block(const Tab& red, int nd, int k,
                 if (jj < c) continue;
                 double* col = (jj < k) ? Ab + (size_t)jj * nd : b;     // the rhs rides as column k
                 double s = 0.0;
-                #pragma unroll 1
+                #pragma unroll 4
                 for (int i = c; i < nd; ++i) s = fma(v[i], col[i], s);
                 s = (2.0 * s) / vn;
-                #pragma unroll 1
+                #pragma unroll 4
                 for (int i = c; i < nd; ++i) col[i] = fma(-s, v[i], col[i]);
             }
         }
@@ -627,7 +652,7 @@ __device__ __forceinline__ void lstsq_basic_block(const Tab& red, int nd, int k,
         #pragma unroll 1
         for (int i = rank - 1; i >= 0; --i) {
             double acc = b[i];
-            #pragma unroll 1
+            #pragma unroll 4
             for (int t = i + 1; t < rank; ++t) acc = fma(-Ab[(size_t)t * nd + i], v[t], acc);
             v[i] = acc / Ab[(size_t)i * nd + i];
         }
