@@ -159,7 +159,11 @@ __global__ void net_cycle_kernel(const CohortDev* __restrict__ cohorts, const in
 // two launches, so that the requests of the first level do not carry the vertex scratch), block = roundup32(max over the
 // groups of max(m, nd, 1)).  Dynamic smem: the largest group's verify_solution_kernel layout (Tab(m, m+1) + VerifySmem + x(nv) +
 // qt(nd) + ax(m)) plus the vertex scratch (ve_scratch_bytes).
-__global__ void net_verify_kernel(const NodeTabEntry* __restrict__ table, const VGroup* __restrict__ groups,
+// MAXT = 64: the nodes of the examples (at most 64 rows): registers capped so that 24 one-warp CTAs fit an SM; MAXT = 1024:
+// any node.
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, MAXT <= 64 ? 12 : 1)
+net_verify_kernel(const NodeTabEntry* __restrict__ table, const VGroup* __restrict__ groups,
                                   const int* __restrict__ gstarts, int ngroups, const int32_t* __restrict__ order,
                                   const double* __restrict__ X, double* __restrict__ Xf_all, double tol,
                                   uint8_t* __restrict__ solution_out, int8_t* __restrict__ mask_base,

@@ -13,7 +13,7 @@
 namespace qpn {
 
 // doubles of shared memory the routine needs behind V (QPN_VE_MAXV x QPN_VE_MAXA) for nodes with at most nd decision variables
-#define QPN_VE_LANES 16      // candidate bases solved at a time (each needs its own stretch of shared memory)
+#define QPN_VE_LANES 8      // candidate bases solved at a time (each needs its own stretch of shared memory)
 __host__ __device__ __forceinline__ int ve_lane_stride(int nd) { return (nd * nd + nd + QPN_VE_MAXA) | 1; }
 __host__ __device__ __forceinline__ size_t ve_scratch_bytes(int nd) {
     if (nd > QPN_VE_MAXND) nd = 0;
