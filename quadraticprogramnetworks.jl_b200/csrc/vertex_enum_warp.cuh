@@ -117,11 +117,15 @@ __device__ __forceinline__ int multiplier_vertices_warp(const VeSmem& s, int nd,
             const double v = fabs(s.W[s.rowperm[e] * QPN_VE_MAXA + s.colperm[k]]);
             if (v > best) { best = v; bidx = idx; }
         }
-        #pragma unroll 1
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ov = __shfl_xor_sync(FULL, best, o);
-            const int oi = __shfl_xor_sync(FULL, bidx, o);
-            if (oi >= 0 && (bidx < 0 || ov > best || (ov == best && oi < bidx))) { best = ov; bidx = oi; }
+        {
+            // warp arg-max by REDUX: the bit pattern of a non-negative double orders like an unsigned integer (two 32-bit
+            // maxima), then the lowest row-major index among the lanes that hold the maximum
+            const unsigned hi = bidx >= 0 ? (unsigned)__double2hiint(best) : 0u, lo = bidx >= 0 ? (unsigned)__double2loint(best) : 0u;
+            const unsigned mh = __reduce_max_sync(FULL, hi);
+            const unsigned ml = __reduce_max_sync(FULL, hi == mh ? lo : 0u);
+            const bool mine = bidx >= 0 && hi == mh && lo == ml;
+            const unsigned widx = __reduce_min_sync(FULL, mine ? (unsigned)bidx : 0xffffffffu);
+            bidx = widx == 0xffffffffu ? -1 : (int)widx;
         }
         if (bidx < 0) break;
         __syncwarp();
