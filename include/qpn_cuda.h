@@ -314,7 +314,8 @@ int qpn_net_piece_rows(qpn_net *net, int piece);
 int qpn_net_piece_get(qpn_net *net, int piece, double *A, double *l, double *u, uint8_t *rl, uint8_t *ru);
 /* out[0..15] = {kernel launches, rounds, requests, batched calls, LPs solved, pieces, nodes, level GAVIs,
  * collect misses, combine misses, host ns in the instance logic, host ns in / waiting for the numeric backend (both
- * summed over the host threads), cohort splits, 0, 0, 0} since the net was created. */
+ * summed over the host threads), cohort splits, host ns applying the answers of a round, LPs of emptiness tests,
+ * batched LP calls} since the net was created. */
 int qpn_net_stats(qpn_net *net, int64_t *out);
 
 #ifdef __cplusplus
