@@ -122,7 +122,7 @@ def oracle_net_binding(net, threads):
     return netsolve.NetBinding(net, lib, prefix="qpo_net_", threads=threads)
 
 
-def cpu_baseline(sample=4, batch=65536):
+def cpu_baseline(sample=2, batch=65536):        # ~ 28 s of CPU work on the 16 host threads of the B200 box
     import qpn_b200
     cores = cpu_cores()
     net = qpn_b200.setup("robust_avoid_simple", seed=DATA_SEED)
