@@ -258,6 +258,19 @@ def test_simple_bilevel_known_answers_on_gpu(engine):
     assert engine.launches > before + 50
 
 
+def test_set_algebra_on_device_matches_oracle(engine):
+    """SURVEY A11 / A12 / A13 directly on the device engine: exemplar / isempty, issubset / remove_subsets, complement,
+    intersection emptiness, projection -- the hand cases of the CPU suite, then every predicate on a family of random
+    polytopes with the same answers as with the oracle as the LP engine."""
+    from tests.oracle_engine import OracleEngine
+    from tests.test_multilevel_cpu import check_polyhedra_operations, set_algebra_answers
+    before = engine.launches
+    check_polyhedra_operations(engine)
+    dev = set_algebra_answers(engine)
+    assert engine.launches > before + 100
+    assert dev == set_algebra_answers(OracleEngine())
+
+
 def test_robust_avoid_three_levels_on_gpu(engine):
     from tests.test_multilevel_cpu import check_robust_avoid_end_to_end
     check_robust_avoid_end_to_end(engine, seeds=(3,))

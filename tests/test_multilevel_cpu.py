@@ -45,8 +45,10 @@ def test_lower_level_solution_map_is_the_kink():
         assert any(ph.contains(p, pt, tol=1e-9) for p in pieces) == inside, (x, y)
 
 
-def test_polyhedra_operations():
-    lp = ph.LPSolver(OracleEngine())
+def check_polyhedra_operations(engine):
+    """exemplar / isempty (sets.jl:591-655), issubset / remove_subsets (:377-407,889-902), complement (:918-975),
+    project + simplify -- every LP through `engine`."""
+    lp = ph.LPSolver(engine)
     box = Poly(np.eye(2), [0.0, 0.0], [1.0, 1.0])
     tri = Poly(np.array([[1.0, 0.0], [0.0, 1.0], [1.0, 1.0]]), [0.0, 0.0, -INF], [INF, INF, 1.0])
     assert ph.issubset(tri, box, lp) and not ph.issubset(box, tri, lp)
@@ -71,6 +73,39 @@ def test_polyhedra_operations():
     assert ph.contains(pr, np.array([1.5])) and not ph.contains(pr, np.array([2.5])) and not ph.contains(pr, np.array([-0.5]))
     # simplify merges the two one-sided rows that projection produces into one two-sided slice
     assert len(ph.simplify(pr)) == 1
+
+
+def random_polytopes(seed, count, d=3):
+    """Boxes cut by random halfspaces through or beside a random point: some empty, some nested, some overlapping."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for k in range(count):
+        c = rng.normal(size=d)
+        A = np.vstack([np.eye(d), rng.normal(size=(3, d))])
+        lo = np.concatenate([c - rng.uniform(0.2, 1.5, d), A[d:] @ c - rng.uniform(-0.3, 1.0, 3)])
+        up = np.concatenate([c + rng.uniform(0.2, 1.5, d), np.full(3, INF)])
+        out.append(Poly(A, lo, up))
+    return out
+
+
+def set_algebra_answers(engine, seed=11, count=14):
+    """Every geometric predicate of the path on a family of random polytopes, as plain data (compared between engines)."""
+    lp = ph.LPSolver(engine)
+    P = random_polytopes(seed, count)
+    empty = [bool(ph.isempty(p, lp)) for p in P]
+    live = [p for p, e in zip(P, empty) if not e]
+    sub = [[bool(ph.issubset(a, b, lp)) for b in live] for a in live]
+    kept = len(ph.remove_subsets(live, lp))
+    inter_empty = [[bool(ph.isempty(ph.intersect(a, b), lp)) for b in live] for a in live]
+    proj_rows = [len(ph.project(p, [0, 1], lp)) for p in live[:6]]
+    return dict(empty=empty, sub=sub, kept=kept, inter_empty=inter_empty, proj_rows=proj_rows)
+
+
+def test_polyhedra_operations():
+    check_polyhedra_operations(OracleEngine())
+    ans = set_algebra_answers(OracleEngine())
+    n = len(ans["sub"])
+    assert all(ans["sub"][i][i] for i in range(n)) and ans["kept"] <= n          # reflexive; remove_subsets only drops
 
 
 def test_solve_dispatch_keeps_result_fields():
