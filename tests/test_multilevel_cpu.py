@@ -76,14 +76,27 @@ def check_polyhedra_operations(engine):
 
 
 def random_polytopes(seed, count, d=3):
-    """Boxes cut by random halfspaces through or beside a random point: some empty, some nested, some overlapping."""
+    """Boxes cut by random halfspaces; every third one is a shrunken copy of its predecessor (a subset), every fifth one
+    carries a contradictory pair of rows (empty)."""
     rng = np.random.default_rng(seed)
     out = []
     for k in range(count):
+        if k % 3 == 2:
+            prev = out[-1]
+            pl = np.where(np.isinf(prev.l), prev.u - 1.0, prev.l)                # (a flipped row is bounded above only)
+            pu = np.where(np.isinf(prev.u), prev.l + 1.0, prev.u)
+            mid = 0.5 * (pl + pu)
+            lo = np.where(np.isinf(prev.l), -INF, pl + 0.25 * (mid - pl))
+            up = np.where(np.isinf(prev.u), INF, pu - 0.25 * (pu - mid))
+            out.append(Poly(prev.A.copy(), lo, up, normalize=False))
+            continue
         c = rng.normal(size=d)
         A = np.vstack([np.eye(d), rng.normal(size=(3, d))])
-        lo = np.concatenate([c - rng.uniform(0.2, 1.5, d), A[d:] @ c - rng.uniform(-0.3, 1.0, 3)])
+        lo = np.concatenate([c - rng.uniform(0.2, 1.5, d), A[d:] @ c - rng.uniform(0.1, 1.0, 3)])
         up = np.concatenate([c + rng.uniform(0.2, 1.5, d), np.full(3, INF)])
+        if k % 5 == 4:
+            a = rng.normal(size=(1, d))
+            A = np.vstack([A, a, -a]); lo = np.concatenate([lo, [1.0, 1.0]]); up = np.concatenate([up, [INF, INF]])    # a x >= 1 and -a x >= 1
         out.append(Poly(A, lo, up))
     return out
 
@@ -105,7 +118,9 @@ def test_polyhedra_operations():
     check_polyhedra_operations(OracleEngine())
     ans = set_algebra_answers(OracleEngine())
     n = len(ans["sub"])
-    assert all(ans["sub"][i][i] for i in range(n)) and ans["kept"] <= n          # reflexive; remove_subsets only drops
+    assert all(ans["sub"][i][i] for i in range(n)) and ans["kept"] < n           # reflexive; the shrunken copies are dropped
+    assert any(ans["empty"]) and not all(ans["empty"])
+    assert sum(map(sum, ans["sub"])) > n                                         # some proper subsets
 
 
 def test_solve_dispatch_keeps_result_fields():
