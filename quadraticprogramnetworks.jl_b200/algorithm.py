@@ -286,11 +286,10 @@ class NetSolver:
         return gen.collect()
 
     # ---- qp_processing.jl:151-241 ------------------------------------------------------------------
-    # process_qp in two phases.  The reference builds a player's solution graph as soon as that player verifies,
-    # even when another player of the level does not -- graphs the level loop then throws away (algorithm.jl:47-52,
-    # 68-101: `continue` re-solves the children).  Here a level first verifies every player against every combination
-    # of child pieces (`verify_phase`) and builds graphs only once all of them verify (`graph_phase`).  Results are the
-    # same except that an error raised while building a graph nobody uses no longer fails the instance.
+    # process_qp in two phases: a level first verifies every player against every combination of child pieces
+    # (`verify_phase`), then builds the graph of every player that verified (`graph_phase`) -- as the reference does per
+    # player, including for a level that is NOT at an equilibrium, where the graphs are thrown away (algorithm.jl:47-52,
+    # 68-101) but an error raised while building one, or a failed combine, still ends the solve (algorithm.jl:56-63,120-126).
     def verify_phase(self, pid, x, S):
         net = self.net
         base = [net.constraints[c] for c in net.qps[pid].constraint_indices]
@@ -397,7 +396,13 @@ class NetSolver:
                         return dict(solved=False, x_fail=x, x_opt=None)
                     for pid, r in zip(players, results):
                         S[pid] = ph.remove_subsets(r["S"], self.lp) if (r["S"] is not None and self._removes(level)) else r["S"]
-                elif level < net.num_levels():
+                else:
+                    # the reference has built (and will discard) the graph of every player that did verify: what raises or
+                    # fails there ends the solve (solve_base's catch-all turns a raise into solved=false)
+                    for pid, vr in zip(players, vrs):
+                        if vr["solution"] and self.graph_phase(pid, x, vr)["failed"]:
+                            return dict(solved=False, x_fail=x, x_opt=None)
+                if (not equilibrium) and level < net.num_levels():
                     for vr in vrs:
                         if not vr["solution"]:
                             for child, sub in vr["subpiece_assignments"].items():

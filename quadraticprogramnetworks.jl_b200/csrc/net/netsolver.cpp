@@ -614,55 +614,77 @@ int GeoCache::verify_outcome(int plan_id, const uint8_t* rep, Worker* w) {
     bool equilibrium = true;
     for (uint8_t s : sol) if (!s) equilibrium = false;
     auto failed = [&](int err) { O.kind = VerifyOutcome::FAIL; O.error = err; };
+    // ---- process_qp, second phase, for one player whose every combination verified: its solution graph, or what is needed to
+    // combine the graphs of its combinations (qp_processing.jl:189-218,243-291).  Returns an error code (0 = none).
+    auto build_player = [&](const VerifyPlan::PV& pv, std::vector<int>& S_out, std::vector<VerifyOutcome::Comb>& combs) -> int {
+        const int pid = pv.pid;
+        const bool gen = level != 0 || net.gen_solution_map;
+        if (!gen) return 0;
+        const std::vector<int>& ch = net.children[pid];
+        if (ch.empty()) {
+            bool bad = false;
+            const int lid = collect(P.req_nodes[pv.first_req], masks[pv.first_req], vmasks[pv.first_req], w, &bad);
+            if (bad) return ERR_MASK;
+            if (list(lid).empty()) return ERR_GRAPH_EMPTY;
+            S_out[pid] = lid;
+            return 0;
+        }
+        std::vector<int> sols;
+        for (size_t k = 0; k < pv.combos.size(); ++k) {
+            bool bad = false;
+            const int lid = collect(P.req_nodes[pv.first_req + k], masks[pv.first_req + k], vmasks[pv.first_req + k], w, &bad);
+            if (bad) return ERR_MASK;
+            sols.push_back(remove_subsets(lid, w));
+        }
+        if (sols.size() == 1) { S_out[pid] = sols[0]; return 0; }
+        VerifyOutcome::Comb cb;
+        cb.pid = pid;
+        int total = 0;
+        for (size_t k = 0; k < pv.combos.size(); ++k) {
+            std::vector<int> pieces;
+            for (size_t q = 0; q < ch.size(); ++q) pieces.push_back(list(P.S[ch[q]])[pv.combos[k][q]]);
+            const int region = intersect_all(pieces, w);
+            const std::vector<int>& comp = complement_of(region, w);
+            std::vector<int> combined = list(sols[k]);
+            combined.insert(combined.end(), comp.begin(), comp.end());
+            total += (int)combined.size();
+            cb.red.push_back((int)comp.size());
+            for (int p : combined) if (poly(p).m() > 0) cb.flat.push_back(p);
+            cb.union_lists.push_back(intern_list(combined));
+        }
+        if (cb.union_lists.size() > 3 && total > 20) return ERR_COMBINE;
+        combs.push_back(std::move(cb));
+        return 0;
+    };
     if (equilibrium) {
-        // ---- process_qp, second phase: solution graphs + combine (qp_processing.jl:189-218,243-291) -----------------
         O.S_out.assign(net.nplayers, -1);
         O.kind = VerifyOutcome::DONE;
         for (const VerifyPlan::PV& pv : P.pvs) {
-            const int pid = pv.pid;
-            const bool gen = level != 0 || net.gen_solution_map;
-            if (!gen) continue;
-            const std::vector<int>& ch = net.children[pid];
-            if (ch.empty()) {
-                bool bad = false;
-                const int lid = collect(P.req_nodes[pv.first_req], masks[pv.first_req], vmasks[pv.first_req], w, &bad);
-                if (bad) { failed(ERR_MASK); break; }
-                if (list(lid).empty()) { failed(ERR_GRAPH_EMPTY); break; }
-                O.S_out[pid] = lid;
-                continue;
-            }
-            std::vector<int> sols;
-            bool bad = false;
-            for (size_t k = 0; k < pv.combos.size() && !bad; ++k) {
-                const int lid = collect(P.req_nodes[pv.first_req + k], masks[pv.first_req + k], vmasks[pv.first_req + k], w, &bad);
-                if (!bad) sols.push_back(remove_subsets(lid, w));
-            }
-            if (bad) { failed(ERR_MASK); break; }
-            if (sols.size() == 1) { O.S_out[pid] = sols[0]; continue; }
-            VerifyOutcome::Comb cb;
-            cb.pid = pid;
-            int total = 0;
-            for (size_t k = 0; k < pv.combos.size(); ++k) {
-                std::vector<int> pieces;
-                for (size_t q = 0; q < ch.size(); ++q) pieces.push_back(list(P.S[ch[q]])[pv.combos[k][q]]);
-                const int region = intersect_all(pieces, w);
-                const std::vector<int>& comp = complement_of(region, w);
-                std::vector<int> combined = list(sols[k]);
-                combined.insert(combined.end(), comp.begin(), comp.end());
-                total += (int)combined.size();
-                cb.red.push_back((int)comp.size());
-                for (int p : combined) if (poly(p).m() > 0) cb.flat.push_back(p);
-                cb.union_lists.push_back(intern_list(combined));
-            }
-            if (cb.union_lists.size() > 3 && total > 20) { failed(ERR_COMBINE); break; }
-            O.combs.push_back(std::move(cb));
+            const int err = build_player(pv, O.S_out, O.combs);
+            if (err) { failed(err); break; }
         }
         if (O.kind != VerifyOutcome::FAIL) {
             if (!O.combs.empty()) O.kind = VerifyOutcome::MEMBER;
             else O.S_new = finish_graphs(P, O.S_out, w);
         }
     } else {
-        // ---- not an equilibrium: solve_qep with the offending child pieces (algorithm.jl:68-101) -----------------------
+        // ---- not an equilibrium: solve_qep with the offending child pieces (algorithm.jl:68-101).  The reference has by now
+        // built the graph of every player that DID verify (process_qp does both phases per player) and ends the solve if that
+        // raised or the player's combine failed (algorithm.jl:56-63,120-126), although the graphs themselves are thrown away:
+        // the same checks here, the graphs memoised for the pass in which the level does verify.
+        O.kind = VerifyOutcome::QEP;
+        for (const VerifyPlan::PV& pv : P.pvs) {
+            bool all_sol = true;
+            const size_t nreq = pv.combos.empty() ? 1 : pv.combos.size();
+            for (size_t k = 0; k < nreq; ++k) if (!sol[pv.first_req + k]) all_sol = false;
+            if (!all_sol) continue;
+            std::vector<int> S_tmp(net.nplayers, -1);
+            std::vector<VerifyOutcome::Comb> combs_tmp;
+            const int err = build_player(pv, S_tmp, combs_tmp);
+            if (err) { failed(err); break; }
+        }
+    }
+    if (!equilibrium && O.kind != VerifyOutcome::FAIL) {
         std::vector<int> kids;
         for (int p : net.levels[level]) kids.insert(kids.end(), net.children[p].begin(), net.children[p].end());
         std::sort(kids.begin(), kids.end());
@@ -681,7 +703,6 @@ int GeoCache::verify_outcome(int plan_id, const uint8_t* rep, Worker* w) {
                 break;                           // the first combination that fails
             }
         }
-        O.kind = VerifyOutcome::QEP;
         O.gavi = level_gavi(level, assignment, w);
     }
     std::unique_lock<std::shared_mutex> lk(mu_);
