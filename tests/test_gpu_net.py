@@ -101,3 +101,15 @@ def test_synthetic_chain_end_to_end_device_equals_oracle(engine):
     bad = [b for b, (a, r) in enumerate(zip(dev, ref)) if not same_result(a, r, sol=True)]
     assert not bad, (len(bad), bad[:8])
     assert np.mean([r["solved"] for r in dev]) > 0.8
+
+
+@pytest.mark.parametrize("edges", [[(1, 2), (3, 4)], [(1, 2), (2, 3), (3, 4)], [(1, 2), (1, 3), (1, 4)]])
+def test_hierarchical_four_player_device_equals_oracle(engine, edges):
+    """examples/four_player_matrix_game.jl with edges (two to four levels): device == oracle build, instance by instance."""
+    net = qpn_b200.setup("four_player_matrix_game", edge_list=edges)
+    X = np.random.default_rng(7).uniform(-5.0, 5.0, (256, 8))
+    dev = cuda_net(net, engine, threads=2).solve(X, keep_sol=True)
+    ref = oracle_net(net, threads=4).solve(X, keep_sol=True)
+    assert all(r["solved"] for r in dev)
+    bad = [b for b, (a, r) in enumerate(zip(dev, ref)) if not same_result(a, r, sol=True)]
+    assert not bad, (len(bad), bad[:8])

@@ -76,3 +76,16 @@ def test_native_reports_failures_per_instance():
     assert (not outs[0]["solved"]) and outs[0]["x_opt"] is None and "x_fail" in outs[0] and "Can't find" in outs[0]["error"]
     ref = mirror_results(net, np.array([[1.0, 0.0, 3.0, 0.0], [1.0, 0.0, 0.0, 0.0]]))
     assert all(same_result(a, b) for a, b in zip(outs, ref))
+
+
+@pytest.mark.parametrize("edges", [[(1, 2), (3, 4)], [(1, 2), (2, 3), (3, 4)], [(1, 2), (1, 3), (1, 4)], [(1, 2), (2, 3)]])
+def test_native_matches_mirror_on_hierarchical_four_player(edges):
+    """examples/four_player_matrix_game.jl with edges (the example sweeps the power set of edge lists: parallel bilevel,
+    a four-level chain, one leader with three followers, ...): native == mirror, every instance solved."""
+    net = qpn_b200.setup("four_player_matrix_game", edge_list=edges)
+    X = np.random.default_rng(7).uniform(-5.0, 5.0, (24, 8))
+    nat = oracle_net(net, threads=2).solve(X, keep_sol=True)
+    ref = mirror_results(net, X)
+    assert all(r["solved"] for r in nat)
+    bad = [b for b, (a, r) in enumerate(zip(nat, ref)) if not same_result(a, r, sol=True)]
+    assert not bad, bad
