@@ -250,6 +250,29 @@ def extras(qpn_b200, torch, eng, dev, stream, flush, rank):
     except Exception as e:                                  # noqa: BLE001
         extra["synthetic_chain_end_to_end_n6"] = {"error": str(e)[:200]}
 
+    # examples/four_player_matrix_game.jl with edges (the example sweeps the power set of edge lists): the four-level chain
+    # 1 -> 2 -> 3 -> 4, 4,096 random initialisations through qpn_net_solve_batched (host buffers, host clock)
+    try:
+        from qpn_b200.netsolve import NetBinding
+        fh = qpn_b200.setup("four_player_matrix_game", edge_list=[(1, 2), (2, 3), (3, 4)])
+        B = 4096
+        Xh = np.random.default_rng([0xB200, rank, 4]).uniform(-5.0, 5.0, (B, 8))
+        nbh = NetBinding(fh, eng.lib, "qpn_net_", handle=eng.h, threads=2)
+        t0 = time.perf_counter(); nbh.solve_arrays(Xh); cold = time.perf_counter() - t0
+        nbh.solve_arrays(Xh)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            rh = nbh.solve_arrays(Xh)
+        th = (time.perf_counter() - t0) / 5
+        extra["four_player_four_level_chain_b4096"] = {"value": B / th, "unit": UNIT, "batch": B, "ms_per_solve": 1e3 * th, "cold_first_solve_s": cold,
+                                                      "solved_fraction": float(rh["solved"].mean()),
+                                                      "mean_passes_per_level": rh["level_iters"].mean(0).round(2).tolist(),
+                                                      "note": "edge_list = [(1,2),(2,3),(3,4)]: four levels, solution graphs at three of them; "
+                                                              "solve(qpn, inits) end to end"}
+        nbh.close()
+    except Exception as e:                                  # noqa: BLE001
+        extra["four_player_four_level_chain_b4096"] = {"error": str(e)[:200]}
+
     # BASELINE configs[1]: four_player_matrix_game, 4,096 random initialisations, one fused level launch
     try:
         fp = qpn_b200.setup("four_player_matrix_game")
