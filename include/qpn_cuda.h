@@ -285,7 +285,7 @@ typedef struct qpn_net qpn_net;
 int qpn_net_create(qpn_handle *h, const qpn_net_desc *desc, qpn_net **out);
 int qpn_net_destroy(qpn_net *net);
 const char *qpn_net_last_error(qpn_net *net);
-/* "threads": host threads that drive the batch (each with its own stream), default 4; "profile": see qpn_net_profile. */
+/* "threads": host threads that drive the batch (each with its own stream), default 2; "profile": see qpn_net_profile. */
 int qpn_net_set_option(qpn_net *net, const char *name, int64_t value);
 /*
  * solve(qpn, inits::Matrix): inits nv x batch (host).  x_out: nv x batch -- x_opt where solved_out[b] = 1, the

@@ -61,7 +61,7 @@ inline NetData net_from_desc(const qpn_net_desc* d, std::vector<Poly>& polys_out
 struct NetObject {
     std::unique_ptr<NetSolver> solver;
     std::vector<SolveOut> outs;
-    int threads = 4;
+    int threads = 2;                             // host threads (streams) that drive a batch: two hide each other's round trips, more add nothing
     std::string err;
     std::function<int64_t()> launches;
 };
