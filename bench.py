@@ -334,6 +334,16 @@ def extras(qpn_b200, torch, eng, dev, stream, flush, rank):
                                                "path": "global-memory tableau" if info["big"] else "shared-memory tableau",
                                                "note": "per GPU, device-timed; one wave of persistent CTAs"}
         solver.close()
+        # ... and at the batch BASELINE.json names (4,096): 28 waves of the same persistent grid, one timed launch
+        X4 = ms.default_initialization + np.random.default_rng([0xB200, rank, 10]).normal(size=(4096, ms.n_vars))
+        solver, lv, run, so, po = level_run(ms, 1, X4)
+        e0, e1 = ev()
+        flush.zero_(); e0.record(stream); run(); e1.record(stream); torch.cuda.synchronize()
+        t4 = e0.elapsed_time(e1) * 1e-3
+        extra["monotone_stress_n256_m512_b4096"] = {"value": len(X4) / t4, "unit": UNIT, "batch": len(X4), "s_per_launch": t4,
+                                                     "all_solved": bool(so.bool().all()), "p50_pivots_per_solve": float(np.median(po.cpu().numpy())),
+                                                     "note": "BASELINE configs[4] at its own batch; per GPU, device-timed, one launch"}
+        solver.close()
     except Exception as e:                                      # noqa: BLE001
         extra["monotone_stress_n256_m512"] = {"error": str(e)[:200]}
     return extra
