@@ -11,14 +11,15 @@
 // came up from the children, which child pieces are assigned -- takes few distinct values across a batch (8,192
 // perturbed robust_avoid instances walk 105 distinct control paths).  The machine therefore advances COHORTS:
 // sets of instances that share their whole control state.  A cohort runs the reference's recursion as an explicit,
-// copyable state machine until it needs numbers; its requests (one per node / level GAVI, over the cohort's list of
-// instance slots) are merged with those of the other cohorts into one batched backend call per (kind, resident
-// object); when the answers are back the cohort is split by what its members were told (solution flags,
-// complementarity masks, membership bits, solve status, cycle check) and every part goes on with a copy of the
-// state.  x stays resident in the backend; per instance the host only hashes its answers and keeps the cycle-check
-// history.  Everything geometric is a pure function of exact problem data (node, child pieces, complementarity
-// recipe K), never of the instance, so it is memoised in a cache shared by all cohorts, worker threads and batches
-// of the net.
+// copyable state machine until it needs numbers and then posts ONE request per round over its members (verify these
+// nodes -- with the cycle checks that precede them --, these membership tests, this solve_qep -- with the verify request
+// that follows a successful solve).  The BACKEND answers every member, partitions the cohort by the answers and hands
+// back one representative's answers per part (on the GPU the partition is a segmented sort by a 64-bit signature of
+// the answers and the host never sees per-instance data; x, the cycle-check histories and the instance order stay
+// resident there); every part goes on with a copy of the state.  Everything geometric is a pure function of exact
+// problem data (node, child pieces, complementarity recipe K), never of the instance, and so are the machine's own
+// transitions (what a level asks to have verified; what follows the answers): all of it is memoised in a cache
+// shared by all cohorts, worker threads and batches of the net.
 #pragma once
 #include <atomic>
 #include <cstdint>
