@@ -5,6 +5,7 @@
 // (oracle/_build/libqpn_net_oracle.so).  Parity status of the numerics: see the header of qpn_oracle.c / DESIGN.md
 // (pinned by the reference's simple_bilevel known answers; unpinned against PATH / OSQP themselves).
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <unordered_map>
 
@@ -46,6 +47,9 @@ struct OracleWorker : Worker {
     std::deque<std::vector<uint8_t>> reps;   // representative answers of the current round
     explicit OracleWorker(OracleStore* s) : store(s) {}
 
+    // (test hook: QPN_ORACLE_WIDE=1 makes the host backend take the wide-batch path of the set algebra, which the CUDA
+    // backend always takes, so that the CPU suite can check that it changes no result)
+    bool wide_batches() const override { static const bool w = getenv("QPN_ORACLE_WIDE") != nullptr; return w; }
     int gavi_solve_one(const GaviData& g, const double* w, const double* z0, double* z) override {
         std::vector<double> z0c(z0, z0 + g.d1 + g.d2);
         static const double none = 0.0;

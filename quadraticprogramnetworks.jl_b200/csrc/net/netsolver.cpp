@@ -264,6 +264,28 @@ int GeoCache::remove_subsets(int lid, Worker* w) {
     return memo(remove_subsets_, lid, [&]() -> int {
         const std::vector<int> ids = list(lid);
         const int k = (int)ids.size();
+        if (w->wide_batches()) {
+            // every pair the scan below may ask for, the pairs of one P1 in a handful of wide calls (the scan stops at the
+            // first superset, so some of these LPs it would have skipped: on a GPU they ride along for free)
+            for (int i = 0; i < k; ++i) {
+                std::vector<int> todo;
+                {
+                    std::shared_lock<std::shared_mutex> lk(mu_);
+                    for (int j = 0; j < k; ++j)
+                        if (j != i && ids[j] != ids[i] && !subset_.count(pair_key(ids[i], ids[j])) &&
+                            std::find(todo.begin(), todo.end(), ids[j]) == todo.end()) todo.push_back(ids[j]);
+                }
+                if (todo.size() < 2) continue;
+                std::vector<const Poly*> P2s;
+                for (int id : todo) P2s.push_back(&poly(id));
+                std::vector<char> res;
+                long n = 0, calls = 0;
+                issubset_many(poly(ids[i]), P2s, *w, res, 1e-6, &n, &calls);
+                stats.lps += n; stats.lps_subset += n; stats.lp_calls += calls;
+                std::unique_lock<std::shared_mutex> lk(mu_);
+                for (size_t q = 0; q < todo.size(); ++q) subset_.emplace(pair_key(ids[i], todo[q]), res[q]);
+            }
+        }
         std::vector<char> is_sub(k, 0);
         for (int i = 0; i < k; ++i)
             for (int j = 0; j < k; ++j)

@@ -247,6 +247,9 @@ struct LPBackend {
     // z0, z: d1 + d2 entries.  Returns the StatusCode (1 = SUCCESS).
     virtual int gavi_solve_one(const GaviData& g, const double* w, const double* z0, double* z) = 0;
     // The same GAVI for `batch` parameter vectors in one call (W: np x batch, Z0 / Z: (d1 + d2) x batch, column-major).
+    // true: a batched call costs about what a single solve costs (a GPU): callers then prefer a few wide calls over many
+    // narrow ones even when that solves LPs a serial scan would have skipped
+    virtual bool wide_batches() const { return false; }
     virtual void gavi_solve_many(const GaviData& g, int batch, const double* W, const double* Z0, double* Z, int32_t* status) {
         const int dz = g.d1 + g.d2;
         for (int b = 0; b < batch; ++b) status[b] = gavi_solve_one(g, W + (size_t)b * g.np, Z0 + (size_t)b * dz, Z + (size_t)b * dz);

@@ -89,3 +89,24 @@ def test_native_matches_mirror_on_hierarchical_four_player(edges):
     assert all(r["solved"] for r in nat)
     bad = [b for b, (a, r) in enumerate(zip(nat, ref)) if not same_result(a, r, sol=True)]
     assert not bad, bad
+
+
+def test_wide_batched_subset_lps_change_no_result():
+    """The CUDA backend batches the subset tests of remove_subsets across all pairs of a list (LPBackend::wide_batches); the
+    oracle build takes the same path with QPN_ORACLE_WIDE=1 (read once per process): same results, fewer LP calls."""
+    import subprocess, sys
+    code = ("import sys, json, hashlib; sys.path.insert(0, %r); import numpy as np, qpn_b200\n"
+            "from tests.native_oracle import oracle_net, ra_inits\n"
+            "net = qpn_b200.setup('robust_avoid_simple', seed=3); X = ra_inits(net, 160, seed=3)\n"
+            "nb = oracle_net(net, threads=2); r = nb.solve_arrays(X); s = nb.stats()\n"
+            "h = hashlib.sha256(r['x'].tobytes() + r['solved'].tobytes() + r['level_iters'].tobytes()).hexdigest()\n"
+            "print(json.dumps(dict(h=h, calls=s['lp_calls'], lps=s['lps'])))\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for wide in (False, True):
+        env = dict(os.environ)
+        env.pop("QPN_ORACLE_WIDE", None)
+        if wide:
+            env["QPN_ORACLE_WIDE"] = "1"
+        outs.append(json.loads(subprocess.check_output([sys.executable, "-c", code], env=env).decode().strip().splitlines()[-1]))
+    assert outs[0]["h"] == outs[1]["h"]
+    assert outs[1]["calls"] < outs[0]["calls"]
