@@ -60,7 +60,9 @@ inline NetData net_from_desc(const qpn_net_desc* d, std::vector<Poly>& polys_out
 // One net object behind the C ABI.
 struct NetObject {
     std::unique_ptr<NetSolver> solver;
-    std::vector<SolveOut> outs;
+    std::vector<int> result_of;                  // per instance of the last batch: index into `results`
+    std::vector<SolveOut> results;
+    const SolveOut* out(int b) const { return (b >= 0 && b < (int)result_of.size() && result_of[b] >= 0) ? &results[result_of[b]] : nullptr; }
     int threads = 2;                             // host threads (streams) that drive a batch: two hide each other's round trips, more add nothing
     std::string err;
     std::function<int64_t()> launches;
@@ -68,24 +70,26 @@ struct NetObject {
 
 inline int net_solve(NetObject* o, int batch, const double* inits, double* x_out, uint8_t* solved_out, int32_t* level_iters_out,
                      int32_t* error_out) {
-    o->solver->solve_batched(batch, inits, x_out, o->outs, o->threads);
+    o->solver->solve_batched(batch, inits, x_out, o->result_of, o->results, o->threads);
     const int nl = o->solver->net().nlevels;
     for (int b = 0; b < batch; ++b) {
-        if (solved_out) solved_out[b] = o->outs[b].solved;
-        if (level_iters_out) for (int l = 0; l < nl; ++l) level_iters_out[(size_t)b * nl + l] = o->outs[b].level_iters[l];
-        if (error_out) error_out[b] = o->outs[b].error;
+        const SolveOut& r = o->results[o->result_of[b]];
+        if (solved_out) solved_out[b] = r.solved;
+        if (level_iters_out) for (int l = 0; l < nl; ++l) level_iters_out[(size_t)b * nl + l] = r.level_iters[l];
+        if (error_out) error_out[b] = r.error;
     }
     return 0;
 }
 inline int net_sol_count(NetObject* o, int b, int player) {
-    if (b < 0 || b >= (int)o->outs.size() || player < 0 || player >= (int)o->outs[b].sol.size()) return -1;
-    const int lid = o->outs[b].sol[player];
+    const SolveOut* r = o->out(b);
+    if (!r || player < 0 || player >= (int)r->sol.size()) return -1;
+    const int lid = r->sol[player];
     return lid < 0 ? -1 : (int)o->solver->cache().list(lid).size();
 }
 inline int net_sol_piece(NetObject* o, int b, int player, int k) {
     const int n = net_sol_count(o, b, player);
     if (k < 0 || k >= n) return -1;
-    return o->solver->cache().list(o->outs[b].sol[player])[k];
+    return o->solver->cache().list(o->out(b)->sol[player])[k];
 }
 inline int net_piece_rows(NetObject* o, int piece) {
     if (piece < 0 || piece >= o->solver->cache().npolys()) return -1;

@@ -927,7 +927,7 @@ NetSolver::NetSolver(NetData net, std::vector<Poly> polys, std::unique_ptr<Store
 }
 NetSolver::~NetSolver() { workers_.clear(); cache_.reset(); store_.reset(); }
 
-void NetSolver::run_shard(int tid, int lo, int hi, const double* inits, double* x_out, std::vector<SolveOut>& outs) {
+void NetSolver::run_shard(int tid, int lo, int hi, const double* inits, double* x_out, int* result_of, std::vector<SolveOut>& results) {
     const int B = hi - lo, nv = net_.nv;
     if (B <= 0) return;
     Worker* w = workers_[tid].get();
@@ -947,7 +947,7 @@ void NetSolver::run_shard(int tid, int lo, int hi, const double* inits, double* 
         M.start_iter(*C);
         M.ready.push_back(std::move(C));
     }
-    std::vector<SolveOut> results;               // outcome per finished cohort; instances carry an index into it
+    results.clear();                             // outcome per finished cohort; instances carry an index into it
     std::vector<std::unique_ptr<Cohort>> waiting;
     std::vector<Part> parts;
     while (true) {
@@ -1009,27 +1009,46 @@ void NetSolver::run_shard(int tid, int lo, int hi, const double* inits, double* 
     for (size_t r = 0; r < results.size(); ++r) solved[r] = results[r].solved;
     std::vector<int32_t> res_of(B, -1);
     w->download(x_out + (size_t)lo * nv, res_of.data(), solved.data(), (int)results.size());
+    // (an instance no cohort finished -- cannot happen unless the backend failed -- reads as unsolved)
+    int lost = -1;
     for (int b = 0; b < B; ++b) {
-        if (res_of[b] >= 0 && res_of[b] < (int)results.size()) outs[lo + b] = results[res_of[b]];
-        else { outs[lo + b].level_iters.assign(net_.nlevels, 0); outs[lo + b].sol.assign(net_.nplayers, -1); outs[lo + b].error = ERR_MAXIT; }
+        if (res_of[b] >= 0 && res_of[b] < (int)results.size()) { result_of[b] = res_of[b]; continue; }
+        if (lost < 0) {
+            SolveOut o;
+            o.level_iters.assign(net_.nlevels, 0); o.sol.assign(net_.nplayers, -1); o.error = ERR_MAXIT;
+            lost = (int)results.size();
+            results.push_back(std::move(o));
+        }
+        result_of[b] = lost;
     }
     st.backend_ns += ns(t_host, now());
 }
 
-void NetSolver::solve_batched(int B, const double* inits, double* x_out, std::vector<SolveOut>& outs, int threads) {
-    outs.assign(B, SolveOut());
+void NetSolver::solve_batched(int B, const double* inits, double* x_out, std::vector<int>& result_of, std::vector<SolveOut>& results, int threads) {
+    result_of.assign(B > 0 ? B : 0, -1);
+    results.clear();
     if (B <= 0) return;
     if (threads < 1) threads = 1;
     if (threads > B) threads = B;
     while ((int)workers_.size() < threads) workers_.emplace_back(store_->make_worker());
-    if (threads == 1) { run_shard(0, 0, B, inits, x_out, outs); return; }
+    if (threads == 1) { run_shard(0, 0, B, inits, x_out, result_of.data(), results); return; }
+    std::vector<std::vector<SolveOut>> shard_results(threads);
+    std::vector<std::pair<int, int>> range(threads);
     std::vector<std::thread> th;
     for (int t = 0; t < threads; ++t) {
         const int base = B / threads, rem = B % threads;
         const int lo = t * base + std::min(t, rem), hi = lo + base + (t < rem ? 1 : 0);
-        th.emplace_back([this, t, lo, hi, inits, x_out, &outs]() { run_shard(t, lo, hi, inits, x_out, outs); });
+        range[t] = {lo, hi};
+        th.emplace_back([this, t, lo, hi, inits, x_out, &result_of, &shard_results]() {
+            run_shard(t, lo, hi, inits, x_out, result_of.data() + lo, shard_results[t]);
+        });
     }
     for (auto& t : th) t.join();
+    for (int t = 0; t < threads; ++t) {          // one table: the shards' outcomes back to back
+        const int off = (int)results.size();
+        for (auto& r : shard_results[t]) results.push_back(std::move(r));
+        if (off) for (int b = range[t].first; b < range[t].second; ++b) result_of[b] += off;
+    }
 }
 
 }  // namespace qpnnet

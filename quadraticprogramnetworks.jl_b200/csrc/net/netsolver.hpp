@@ -294,14 +294,15 @@ class NetSolver {
     // polys: the constraint polys net.base refers to (by position); they are interned first
     NetSolver(NetData net, std::vector<Poly> polys, std::unique_ptr<Store> store);
     ~NetSolver();
-    // inits: nv x B column-major.  x_out: nv x B (x_opt, or x_fail when not solved).
-    void solve_batched(int B, const double* inits, double* x_out, std::vector<SolveOut>& outs, int threads);
+    // inits: nv x B column-major.  x_out: nv x B (x_opt, or x_fail when not solved).  The outcome of instance b is
+    // results[result_of[b]]: instances that ended in the same cohort share one entry (a batch has a few thousand).
+    void solve_batched(int B, const double* inits, double* x_out, std::vector<int>& result_of, std::vector<SolveOut>& results, int threads);
     GeoCache& cache() { return *cache_; }
     const NetData& net() const { return net_; }
     std::string last_error;
 
   private:
-    void run_shard(int tid, int lo, int hi, const double* inits, double* x_out, std::vector<SolveOut>& outs);
+    void run_shard(int tid, int lo, int hi, const double* inits, double* x_out, int* result_of, std::vector<SolveOut>& results);
     NetData net_;
     std::unique_ptr<Store> store_;
     std::unique_ptr<GeoCache> cache_;
